@@ -1,0 +1,449 @@
+"""Synthetic networks + demand for the BASELINE.json configs, emitted as SYMFLAT1 tables
+(and, for small cases, as a reference-format `ROOT_SYMUBRUIT` XML document so a user with
+a real SymuVia build can cross-check: SURVEY.md Appendix B).
+
+What is flattened here is what the reference builds at load time:
+  * links / lanes (`TuyauMicro`, `VoieMicro`: `symuvia/src/tuyau.cpp:1503-1615`);
+  * signalised junctions (`CarrefourAFeuxEx::Init`, `symuvia/src/CarrefourAFeuxEx.cpp:215-1196`):
+    one single-lane internal link per allowed movement (entry lane -> exit lane), running
+    straight from the entry lane's downstream end to the exit lane's upstream end
+    (`:660-732`), entry links typed 'D' (`:379`), internal links 'C' (merge) or 'R' when the
+    exit has a single upstream movement (`:860-880`);
+  * stop lines (`CarrefourAFeuxEx::FinInit`, `:1205-1275`): `ligne_feu = 0` puts one
+    `LigneDeFeu` per (entry lane, exit link, exit lane) at the entry lane's end;
+  * fixed-time signal plans (`ControleurDeFeux`, `symuvia/src/ControleurDeFeux.cpp:203-307`).
+All generators are deterministic (NumPy `default_rng(seed)`).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import flat as F
+
+VL = dict(name="VL", w=-5.8823, kx=0.17, vx=25.0, esp=1.0, decel=0.0, tau_lc=4.0, pi_rab=0.0,
+          law=F.LAW_NEWELL, plages=[(1.5, 1e9)])
+PL = dict(name="PL", w=-4.5, kx=0.08, vx=22.0, esp=1.0, decel=0.0, tau_lc=4.0, pi_rab=0.0,
+          law=F.LAW_NEWELL, plages=[(1.0, 1e9)])
+
+
+class NetBuilder:
+    """Accumulates the flat tables. Ids are dense ints in creation order."""
+
+    def __init__(self, dt=1.0, n_steps=100, seed=42, accbornee=False, relax=1.0, chgtvoie=False,
+                 dst_chgtvoie=50.0):
+        self.params = np.zeros(F.P_NPARAMS)
+        self.params[F.P_DT] = dt
+        self.params[F.P_NSTEPS] = n_steps
+        self.params[F.P_SEED] = seed
+        self.params[F.P_ACCBORNEE] = float(accbornee)
+        self.params[F.P_RELAX] = relax
+        self.params[F.P_CHGTVOIE] = float(chgtvoie)
+        self.params[F.P_DSTCHGT] = dst_chgtvoie
+        self.classes: List[dict] = []
+        self.nodes: List[List[int]] = []          # type, ctrl, 0, 0
+        self.node_names: List[str] = []
+        self.node_xy: List[Tuple[float, float]] = []
+        self.links: List[List[int]] = []
+        self.link_f: List[List[float]] = []
+        self.link_names: List[str] = []
+        self.link_geom: List[Tuple[float, float, float, float]] = []
+        self.lanes: List[List[int]] = []
+        self.lane_f: List[float] = []
+        self.succ: List[List[Tuple[int, int, int, float]]] = []     # per lane
+        self.sl: List[List[Tuple[int, int, int, int, int, float]]] = []
+        self.ctrl: List[dict] = []
+        self.routes: List[List[int]] = []
+        self.entries: List[dict] = []
+        self.exits: List[Tuple[int, int, float]] = []
+        self.iv_i: List[List[int]] = []
+        self.iv_f: List[List[float]] = []
+
+    # -- topology ---------------------------------------------------------------------------
+    def add_class(self, c: dict) -> int:
+        self.classes.append(c)
+        return len(self.classes) - 1
+
+    def add_node(self, typ: str, name: str, xy=(0.0, 0.0), ctrl=-1) -> int:
+        self.nodes.append([ord(typ), ctrl, 0, 0])
+        self.node_names.append(name)
+        self.node_xy.append(xy)
+        return len(self.nodes) - 1
+
+    def add_link(self, name: str, up: int, down: int, n_lanes: int, length: float, vit_reg: float,
+                 type_aval: str, brick: int = -1, prev_lane: int = -1, geom=(0.0, 0.0, 0.0, 0.0),
+                 lane_lengths: Optional[List[float]] = None) -> int:
+        k = len(self.links)
+        first = len(self.lanes)
+        self.links.append([first, n_lanes, up, down, ord(type_aval), brick, 0, 0])
+        self.link_f.append([length, vit_reg])
+        self.link_names.append(name)
+        self.link_geom.append(geom)
+        for n in range(n_lanes):
+            self.lanes.append([k, n, prev_lane, 0])
+            self.lane_f.append(length if lane_lengths is None else lane_lengths[n])
+            self.succ.append([])
+            self.sl.append([])
+        return k
+
+    def lane_of(self, link: int, num: int) -> int:
+        return self.links[link][0] + num
+
+    def add_succ(self, lane: int, key_link: int, next_lane: int, rate=1.0, draws=1):
+        self.succ[lane].append((key_link, next_lane, draws, rate))
+
+    def add_stopline(self, lane: int, pos: float, ctrl: int, up_link: int, up_num: int,
+                     down_link: int, down_num: int):
+        self.sl[lane].append((ctrl, up_link, up_num, down_link, down_num, pos))
+
+    def add_ctrl(self, cycle: float, seqs: List[dict]) -> int:
+        """seqs: [{len: float, signals: [(link_in, link_out, green, amber, delay)]}]"""
+        self.ctrl.append(dict(cycle=cycle, seqs=seqs))
+        return len(self.ctrl) - 1
+
+    def add_route(self, links: List[int]) -> int:
+        self.routes.append(list(links))
+        return len(self.routes) - 1
+
+    def add_entry(self, node: int, link: int, demand: List[Tuple[float, float]],
+                  dests: List[Tuple[int, float, List[Tuple[int, float]]]],
+                  lane_coefs: Optional[List[float]] = None, type_coefs: Optional[List[float]] = None,
+                  exponential=False) -> int:
+        """demand: [(duration_s, level veh/s)]; dests: [(exit_idx, coeff, [(route, coeff)])]."""
+        self.entries.append(dict(node=node, link=link, demand=demand, dests=dests, lane_coefs=lane_coefs,
+                                 type_coefs=type_coefs, exponential=exponential))
+        return len(self.entries) - 1
+
+    def add_exit(self, node: int, link: int, capacity=-1.0) -> int:
+        self.exits.append((node, link, capacity))
+        return len(self.exits) - 1
+
+    def add_init_vehicle(self, cls: int, lane: int, route: int, route_pos: int, pos: float, v: float,
+                         a: float = 0.0):
+        self.iv_i.append([cls, lane, route, route_pos])
+        self.iv_f.append([pos, v, a])
+
+    # -- emit -------------------------------------------------------------------------------
+    def sections(self) -> Dict[str, np.ndarray]:
+        T = len(self.classes)
+        cls = np.zeros((T, F.CLS_STRIDE))
+        for i, c in enumerate(self.classes):
+            cls[i, F.C_W], cls[i, F.C_KX], cls[i, F.C_VX] = c["w"], c["kx"], c["vx"]
+            cls[i, F.C_ESP], cls[i, F.C_DECEL] = c["esp"], c["decel"]
+            cls[i, F.C_TAULC], cls[i, F.C_PIRAB], cls[i, F.C_LAW] = c["tau_lc"], c["pi_rab"], c["law"]
+            cls[i, F.C_NPLAGE] = len(c["plages"])
+            for j, (ax, vs) in enumerate(c["plages"][:4]):
+                cls[i, F.C_PLAGE0 + 2 * j] = ax
+                cls[i, F.C_PLAGE0 + 2 * j + 1] = vs
+        L = len(self.lanes)
+        succ_off = np.zeros(L + 1, np.int32)
+        sl_off = np.zeros(L + 1, np.int32)
+        succ_i, succ_f, sl_i, sl_f = [], [], [], []
+        for l in range(L):
+            for (k, nl, dr, rate) in self.succ[l]:
+                succ_i.append([k, nl, dr])
+                succ_f.append(rate)
+            succ_off[l + 1] = len(succ_i)
+            for (c, ul, un, dl, dn, pos) in self.sl[l]:
+                sl_i.append([c, ul, un, dl, dn, 0])
+                sl_f.append(pos)
+            sl_off[l + 1] = len(sl_i)
+        ctrl_i, ctrl_f, seq_i, seq_f, sig_i, sig_f = [], [], [], [], [], []
+        for c in self.ctrl:
+            ctrl_i.append([len(seq_i), len(c["seqs"])])
+            ctrl_f.append(c["cycle"])
+            for s in c["seqs"]:
+                seq_i.append([len(sig_i), len(s["signals"])])
+                seq_f.append(s["len"])
+                for (li, lo, g, a, d) in s["signals"]:
+                    sig_i.append([li, lo])
+                    sig_f.append([g, a, d])
+        route_off = np.zeros(len(self.routes) + 1, np.int32)
+        rl: List[int] = []
+        for i, r in enumerate(self.routes):
+            rl.extend(r)
+            route_off[i + 1] = len(rl)
+        entry_i, dem_f, dest_i, dest_f, dr_i, dr_f, lanecoef, typecoef = [], [], [], [], [], [], [], []
+        for e in self.entries:
+            nl = self.links[e["link"]][1]
+            lc = e["lane_coefs"] or [1.0 / nl] * nl
+            tc = e["type_coefs"] or ([1.0] + [0.0] * (T - 1))
+            entry_i.append([e["node"], e["link"], len(dem_f), len(e["demand"]), len(dest_i), len(e["dests"]),
+                            len(lanecoef), len(typecoef) | (int(e["exponential"]) << 30)])
+            dem_f.extend([list(d) for d in e["demand"]])
+            lanecoef.extend(lc)
+            typecoef.extend(tc)
+            for (ex, coeff, rts) in e["dests"]:
+                dest_i.append([ex, len(dr_i), len(rts)])
+                dest_f.append(coeff)
+                for (r, rc) in rts:
+                    dr_i.append(r)
+                    dr_f.append(rc)
+
+        def I(a, w):
+            return np.asarray(a, np.int32).reshape(-1, w) if len(a) else np.zeros((0, w), np.int32)
+
+        def D(a, w=1):
+            return np.asarray(a, np.float64).reshape(-1, w) if len(a) else np.zeros((0, w), np.float64)
+
+        def names(lst):
+            return np.frombuffer(("\0".join(lst) + "\0").encode(), np.uint8)
+
+        return {
+            "params": self.params, "cls": cls,
+            "link_i": I(self.links, F.LINK_I), "link_f": D(self.link_f, F.LINK_F),
+            "link_geom": D(self.link_geom, 4),
+            "lane_i": I(self.lanes, F.LANE_I), "lane_f": D(self.lane_f),
+            "succ_off": succ_off, "succ_i": I(succ_i, F.SUCC_I), "succ_f": D(succ_f),
+            "sl_off": sl_off, "sl_i": I(sl_i, F.SL_I), "sl_f": D(sl_f),
+            "ctrl_i": I(ctrl_i, 2), "ctrl_f": D(ctrl_f), "seq_i": I(seq_i, 2), "seq_f": D(seq_f),
+            "sig_i": I(sig_i, 2), "sig_f": D(sig_f, 3),
+            "node_i": I(self.nodes, F.NODE_I), "node_xy": D(self.node_xy, 2),
+            "route_off": route_off, "route_links": np.asarray(rl, np.int32),
+            "entry_i": I(entry_i, F.ENTRY_I), "dem_f": D(dem_f, 2), "dest_i": I(dest_i, F.DEST_I),
+            "dest_f": D(dest_f), "droute_i": np.asarray(dr_i, np.int32), "droute_f": D(dr_f),
+            "lanecoef_f": D(lanecoef), "typecoef_f": D(typecoef),
+            "exit_i": I([[n, l] for (n, l, _) in self.exits], F.EXIT_I),
+            "exit_f": D([c for (_, _, c) in self.exits]),
+            "iv_i": I(self.iv_i, F.IV_I), "iv_f": D(self.iv_f, F.IV_F),
+            "names_link": names(self.link_names), "names_node": names(self.node_names),
+            "names_cls": names([c["name"] for c in self.classes]),
+        }
+
+    def write(self, path: str) -> None:
+        F.write(path, self.sections())
+
+
+# ---------------------------------------------------------------------------------------------
+# C1: single link
+# ---------------------------------------------------------------------------------------------
+def single_link(length=2000.0, n_lanes=1, vit_reg=25.0, demand=0.5, n_steps=3600, dt=1.0, seed=42,
+                law=F.LAW_NEWELL, exit_capacity=-1.0, signal=None, classes=None, type_coefs=None,
+                exponential=False, accbornee=False) -> NetBuilder:
+    """BASELINE config C1: Entree -> one link -> Sortie, deterministic demand (veh/s).
+
+    `signal=(green, amber, red)` adds a mid-link pass-through repartiteur with a fixed-time
+    stop line (two links of length/2), used by the signal known-answer tests.
+    """
+    b = NetBuilder(dt=dt, n_steps=n_steps, seed=seed, accbornee=accbornee)
+    for c in (classes or [dict(VL, law=law)]):
+        b.add_class(c)
+    e = b.add_node("E", "E1", (0.0, 0.0))
+    s = b.add_node("S", "S1", (length, 0.0))
+    if signal is None:
+        l1 = b.add_link("T1", e, s, n_lanes, length, vit_reg, "S", geom=(0, 0, length, 0))
+        route = b.add_route([l1])
+        last = l1
+    else:
+        g, a, r = signal
+        ctrl = b.add_ctrl(g + a + r, [dict(len=g + a + r, signals=[])])
+        rn = b.add_node("R", "R1", (length / 2, 0.0), ctrl=ctrl)
+        l1 = b.add_link("T1", e, rn, n_lanes, length / 2, vit_reg, "R", geom=(0, 0, length / 2, 0))
+        l2 = b.add_link("T2", rn, s, n_lanes, length / 2, vit_reg, "S", geom=(length / 2, 0, length, 0))
+        b.ctrl[ctrl]["seqs"][0]["signals"].append((l1, l2, g, a, 0.0))
+        for n in range(n_lanes):
+            b.add_succ(b.lane_of(l1, n), l2, b.lane_of(l2, n), 1.0, 1)
+            b.add_stopline(b.lane_of(l1, n), length / 2, ctrl, l1, n, l2, n)
+        route = b.add_route([l1, l2])
+        last = l2
+    x = b.add_exit(s, last, exit_capacity)
+    b.add_entry(e, l1, [(1e12, demand)], [(x, 1.0, [(route, 1.0)])], type_coefs=type_coefs,
+                exponential=exponential)
+    return b
+
+
+# ---------------------------------------------------------------------------------------------
+# C2 / C4 / C5: Manhattan grid of signalised junctions
+# ---------------------------------------------------------------------------------------------
+_DIRS = [(1, 0), (0, 1), (-1, 0), (0, -1)]       # E, N, W, S
+_DNAME = "ENWS"
+
+
+def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, green=30.0, amber=3.0,
+         n_steps=1800, dt=1.0, seed=42, demand_per_lane=0.2, demand_duration=1e12,
+         preseed_per_lane=0.0, shuffle=False, classes=None, offsets=False, law=F.LAW_NEWELL,
+         ny: Optional[int] = None) -> NetBuilder:
+    """n x ny grid of CAF junctions (BASELINE configs C2/C4/C5).
+
+    Every approach lane k may go straight / right / left into exit lane k (no U-turn);
+    signals: sequence 0 serves the E/W-bound approaches, sequence 1 the N/S-bound ones.
+    `preseed_per_lane` > 0 places that many vehicles on every non-stub external lane with
+    staircase routes to the boundary (C4/C5: no demand, population steady over the run).
+    """
+    ny = n if ny is None else ny
+    rng = np.random.default_rng(seed)
+    b = NetBuilder(dt=dt, n_steps=n_steps, seed=seed)
+    for c in (classes or [dict(VL, law=law)]):
+        b.add_class(c)
+    cyc = 2 * (green + amber)
+    J = {}
+    for i in range(n):
+        for j in range(ny):
+            ctrl = b.add_ctrl(cyc, [dict(len=green + amber, signals=[]), dict(len=green + amber, signals=[])])
+            J[(i, j)] = b.add_node("C", f"J{i}_{j}", (i * block, j * block), ctrl=ctrl)
+    out_link: Dict[Tuple[int, int, int], int] = {}    # (i, j, d) link leaving junction (i,j) heading d
+    in_link: Dict[Tuple[int, int, int], int] = {}     # (i, j, d) link arriving at junction (i,j) heading d
+    link_dir: Dict[int, int] = {}
+    stub_entries, stub_exits = [], []
+    L = block - 2 * setback
+    for i in range(n):
+        for j in range(ny):
+            x0, y0 = i * block, j * block
+            for d, (dx, dy) in enumerate(_DIRS):
+                i2, j2 = i + dx, j + dy
+                gx0, gy0 = x0 + dx * setback, y0 + dy * setback
+                if 0 <= i2 < n and 0 <= j2 < ny:
+                    gx1, gy1 = i2 * block - dx * setback, j2 * block - dy * setback
+                    k = b.add_link(f"L{i}_{j}{_DNAME[d]}", J[(i, j)], J[(i2, j2)], n_lanes, L, vit_reg, "D",
+                                   geom=(gx0, gy0, gx1, gy1))
+                    out_link[(i, j, d)] = k
+                    in_link[(i2, j2, d)] = k
+                    link_dir[k] = d
+                else:
+                    # boundary: exit stub leaving the grid and entry stub coming in
+                    s = b.add_node("S", f"S{i}_{j}{_DNAME[d]}", (x0 + dx * block, y0 + dy * block))
+                    k = b.add_link(f"X{i}_{j}{_DNAME[d]}", J[(i, j)], s, n_lanes, L, vit_reg, "S",
+                                   geom=(gx0, gy0, x0 + dx * (block - setback), y0 + dy * (block - setback)))
+                    out_link[(i, j, d)] = k
+                    link_dir[k] = d
+                    stub_exits.append((b.add_exit(s, k), k, i, j, d))
+                    e = b.add_node("E", f"E{i}_{j}{_DNAME[d]}", (x0 + dx * block, y0 + dy * block))
+                    din = (d + 2) % 4
+                    k2 = b.add_link(f"N{i}_{j}{_DNAME[d]}", e, J[(i, j)], n_lanes, L, vit_reg, "D",
+                                    geom=(x0 + dx * (block - setback), y0 + dy * (block - setback), gx0, gy0))
+                    in_link[(i, j, din)] = k2
+                    link_dir[k2] = din
+                    stub_entries.append((e, k2, i, j, din))
+
+    def lane_pt(link: int, num: int, end: bool) -> Tuple[float, float]:
+        gx0, gy0, gx1, gy1 = b.link_geom[link]
+        dx, dy = _DIRS[link_dir[link]]
+        off = (num + 0.5) * lane_w
+        px, py = (gx1, gy1) if end else (gx0, gy0)
+        return px + dy * off, py - dx * off           # right-hand side of travel direction
+
+    # CAF internal movements
+    exit_in_count: Dict[int, int] = {}
+    moves = []
+    for (i, j), node in J.items():
+        for din in range(4):
+            a = in_link.get((i, j, din))
+            if a is None:
+                continue
+            for turn in (0, 3, 1):                     # straight, right, left (relative)
+                dout = (din + turn) % 4
+                o = out_link.get((i, j, dout))
+                if o is None:
+                    continue
+                moves.append((node, i, j, a, o, din))
+                exit_in_count[o] = exit_in_count.get(o, 0) + n_lanes
+    for (node, i, j, a, o, din) in moves:
+        ctrl = b.nodes[node][1]
+        seq = 0 if din in (0, 2) else 1
+        b.ctrl[ctrl]["seqs"][seq]["signals"].append((a, o, green, amber, 0.0))
+        for k in range(n_lanes):
+            ax, ay = lane_pt(a, k, True)
+            ox, oy = lane_pt(o, k, False)
+            ln = math.hypot(ox - ax, oy - ay)
+            ent_lane = b.lane_of(a, k)
+            il = b.add_link(f"I{b.link_names[a]}_{b.link_names[o]}_{k + 1}", node, node, 1, ln, vit_reg,
+                            "C" if exit_in_count[o] > 1 else "R", brick=node, prev_lane=ent_lane,
+                            geom=(ax, ay, ox, oy))
+            link_dir[il] = din
+            b.add_succ(ent_lane, o, b.lane_of(il, 0), 1.0, 1)
+            b.add_succ(b.lane_of(il, 0), o, b.lane_of(o, k), 1.0, 1)
+            b.add_stopline(ent_lane, b.lane_f[ent_lane], ctrl, a, k, o, k)
+
+    # routing helpers on the (link -> link) graph without U-turns
+    nxt: Dict[int, List[int]] = {}
+    for (node, i, j, a, o, din) in moves:
+        nxt.setdefault(a, []).append(o)
+
+    if demand_per_lane > 0:
+        # shortest paths entry stub -> exit stub (BFS over links; neighbour order straight, right, left)
+        exit_of_link = {k: x for (x, k, _, _, _) in stub_exits}
+        for (e, k0, i, j, din) in stub_entries:
+            prev = {k0: -1}
+            order = [k0]
+            for cur in order:
+                for o in nxt.get(cur, []):
+                    if o not in prev:
+                        prev[o] = cur
+                        order.append(o)
+            dests = []
+            for (x, kx, xi, xj, xd) in stub_exits:
+                if kx not in prev or (xi == i and xj == j):
+                    continue
+                path = [kx]
+                while prev[path[-1]] != -1:
+                    path.append(prev[path[-1]])
+                dests.append((x, 1.0, [(b.add_route(path[::-1]), 1.0)]))
+            tot = len(dests)
+            dests = [(x, 1.0 / tot, r) for (x, _, r) in dests]
+            b.add_entry(e, k0, [(demand_duration, demand_per_lane * n_lanes), (1e12, 0.0)], dests)
+
+    if preseed_per_lane > 0:
+        cls0 = b.classes[0]
+        inv_kx = 1.0 / cls0["kx"]
+        vmax = min(cls0["vx"], vit_reg)
+        ext_links = [k for k in range(len(b.links)) if b.links[k][5] < 0 and chr(b.links[k][4]) == "D"
+                     and b.link_names[k][0] == "L"]
+        # two staircase routes per link: (d, d+1) and (d, d-1)
+        link_at = {v: key for key, v in out_link.items()}
+        route_ids: Dict[int, List[int]] = {}
+        for k in ext_links:
+            (i, j, d) = link_at[k]
+            rts = []
+            for side in (1, 3):
+                d2 = (d + side) % 4
+                path = [k]
+                ci, cj = i + _DIRS[d][0], j + _DIRS[d][1]   # junction at the end of k
+                cd = d
+                while True:
+                    # choose next heading among {d, d2} (monotone staircase => no repeated link)
+                    cand = [dd for dd in (d, d2) if (ci, cj, dd) in out_link]
+                    pick = cand[int(rng.integers(len(cand)))] if len(cand) > 1 else cand[0]
+                    o = out_link[(ci, cj, pick)]
+                    path.append(o)
+                    if chr(b.links[o][4]) == "S":
+                        break
+                    ci, cj = ci + _DIRS[pick][0], cj + _DIRS[pick][1]
+                    cd = pick
+                rts.append(b.add_route(path))
+            route_ids[k] = rts
+        seeds = []
+        for k in ext_links:
+            for num in range(n_lanes):
+                m = int(preseed_per_lane) + (1 if rng.random() < preseed_per_lane - int(preseed_per_lane) else 0)
+                m = min(m, int(L / inv_kx) - 1)
+                if m <= 0:
+                    continue
+                # uniform slots with jitter, min spacing 1/Kx
+                slot = L / m
+                jit = max(0.0, slot - inv_kx - 1e-6)
+                pos = np.sort((np.arange(m) + 0.5) * slot - 0.5 * jit + rng.random(m) * jit * 0.999)
+                for q in range(m):
+                    s = (pos[q + 1] - pos[q]) if q + 1 < m else 1e9
+                    v = min(vmax, max(0.0, -cls0["w"] * (s * cls0["kx"] - 1.0)))
+                    seeds.append((k, num, float(pos[q]), float(v), route_ids[k][int(rng.integers(2))]))
+        if shuffle:
+            perm = rng.permutation(len(seeds))
+            seeds = [seeds[p] for p in perm]
+        for (k, num, p, v, r) in seeds:
+            b.add_init_vehicle(0, b.lane_of(k, num), r, 0, p, v)
+    return b
+
+
+def config(name: str, **kw) -> NetBuilder:
+    """Named BASELINE.json configurations."""
+    if name == "C1":
+        return single_link(**kw)
+    if name == "C2":
+        return grid(n=10, n_steps=1800, demand_per_lane=0.2, demand_duration=1200.0, **kw)
+    if name == "C4":
+        return grid(n=100, n_steps=300, demand_per_lane=0.0, preseed_per_lane=12.6, **kw)
+    if name == "C5":
+        return grid(n=300, n_steps=100, demand_per_lane=0.0, preseed_per_lane=14.0, **kw)
+    raise KeyError(name)

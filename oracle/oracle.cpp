@@ -1,0 +1,881 @@
+// ======================================================================================
+// oracle.cpp — CPU restatement of SymuVia's per-time-step microscopic vehicle update.
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may build, load or call this file.  The product
+// (open-symuvia_b200/csrc) never includes, links or executes anything under oracle/.
+//
+// PARITY UNPINNED: the reference (licit-lab/Open-SymuVia) ships no tests, golden vectors or
+// sample networks and cannot be compiled in this image (Boost, Xerces-C,
+// XQilla, GDAL, ODBC absent — SURVEY.md §8c).  This restatement follows the cited reference
+// code line by line and is pinned only by analytic known-answer tests (tests/test_oracle_kat.py).
+// Third-party arithmetic restated from its published algorithm: Boost.Random (version
+// unpinned by the reference: conda/meta.yaml:22-23) — mt19937 + uniform_int<>(0,0x7FFE)
+// (RandManager.cpp:5,26-30), bucket-rejection of boost/random/uniform_int_distribution.hpp
+// (Boost >= 1.47).
+//
+// Structure mirrors the reference on purpose (AoS vehicles with [0]=end/[1]=start of step,
+// per-lane std::set ordered by vehicle id with linear neighbour scans, leader-first
+// recursion) so each function can be compared with the file:line it cites.  All paths are
+// relative to /root/reference/symuvia/src.
+//
+// Build: g++ -O2 -ffp-contract=off -std=c++17 -shared -fPIC (see oracle/Makefile).
+// ======================================================================================
+#include <algorithm>
+#include <cassert>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr double UNDEF_POSITION = -DBL_MIN;       // symUtil.h:9
+constexpr double MAXIMUM_RANDOM_NUMBER = 32767.0; // RandManager.h:9 (0x7fff)
+constexpr double NONVAL_DOUBLE = 9999;            // symUtil.h:16
+
+// ---- flat container (format: include/symflat.h) --------------------------------------------
+struct Sec { int dtype = 0; std::vector<char> raw; size_t count = 0; };
+struct Flat {
+  std::map<std::string, Sec> s;
+  bool load(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    char magic[8];
+    uint32_t n = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SYMFLAT1", 8) != 0) { fclose(f); return false; }
+    if (fread(&n, 4, 1, f) != 1) { fclose(f); return false; }
+    for (uint32_t i = 0; i < n; i++) {
+      char name[25] = {0};
+      uint32_t dt; uint64_t cnt;
+      if (fread(name, 1, 24, f) != 24 || fread(&dt, 4, 1, f) != 1 || fread(&cnt, 8, 1, f) != 1) { fclose(f); return false; }
+      size_t isz = dt == 0 ? 4 : dt == 1 ? 8 : 1;
+      Sec sec; sec.dtype = (int)dt; sec.count = cnt; sec.raw.resize(cnt * isz);
+      if (cnt && fread(sec.raw.data(), 1, sec.raw.size(), f) != sec.raw.size()) { fclose(f); return false; }
+      size_t pad = (8 - (sec.raw.size() % 8)) % 8; char tmp[8];
+      if (pad && fread(tmp, 1, pad, f) != pad) { fclose(f); return false; }
+      s[name] = std::move(sec);
+    }
+    fclose(f);
+    return true;
+  }
+  const int* I(const char* n) const { auto it = s.find(n); return it == s.end() ? nullptr : (const int*)it->second.raw.data(); }
+  const double* D(const char* n) const { auto it = s.find(n); return it == s.end() ? nullptr : (const double*)it->second.raw.data(); }
+  size_t N(const char* n) const { auto it = s.find(n); return it == s.end() ? 0 : it->second.count; }
+};
+
+// ---- RNG: RandManager.cpp:5-30 --------------------------------------------------------------
+struct MT19937 {                                  // boost::mt19937 == std::mt19937 (standard MT19937)
+  uint32_t mt[624]; int idx = 624;
+  void seed(uint32_t s) { mt[0] = s; for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i; idx = 624; }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; i++) {
+        uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+};
+struct RandManager {
+  MT19937 gen; unsigned count = 0;
+  void mySrand(unsigned seed) { gen.seed(seed); count = 0; }       // RandManager.cpp:10-24
+  int myRand() {                                                    // RandManager.cpp:26-30
+    count++;
+    // uniform_int<>(0, 0x7FFE) on a 32-bit engine: range+1 = 32767, bucket = 0xFFFFFFFF / 32767
+    // = 131076 (remainder 3 != range so no +1); reject results > range.
+    const uint32_t bucket = 0xFFFFFFFFu / 32767u;
+    for (;;) { uint32_t r = gen.next() / bucket; if (r <= 32766u) return (int)r; }
+  }
+};
+
+// ---- static tables ----------------------------------------------------------------------------
+struct Cls { double w, kx, vx, esp, decel, tau_lc, pi_rab; int law; std::vector<std::pair<double, double>> plages;
+  double debit_max() const { return w * kx / ((w / vx) - 1); }     // DiagFonda.cpp:47
+  double k_crit() const { return w * kx / (w - vx); }              // DiagFonda.cpp:48
+  double acc_max(double v) const {                                  // vehicule.cpp:157-175
+    for (auto& p : plages) if (v <= p.second + 0.000001) return p.first;
+    return plages.empty() ? 0.0 : plages.back().first; }
+};
+struct Link { int first_lane, n_lanes, up_node, down_node; char type_aval; int brick; double length, vit_reg; };
+struct Succ { int key_link, next_lane, flags; double rate; };
+struct StopLine { int ctrl, up_link, up_num, down_link, down_num; double pos; };
+struct Lane { int link, num, prev_lane, flags; double length; std::vector<Succ> succ; std::vector<StopLine> sl;
+  double next_inst_sortie = 0; };                                   // voie.h GetNextInstSortie (default 0)
+struct Signal { int link_in, link_out; double green, amber, delay; };
+struct Seq { double len; std::vector<Signal> sig; };
+struct Ctrl { double cycle; std::vector<Seq> seqs; };
+struct DestRoute { int route; double coeff; };
+struct Dest { int exit; double coeff; std::vector<DestRoute> routes; };
+struct Veh;
+struct Entry { int node, link; std::vector<std::pair<double, double>> demand; std::vector<Dest> dests;
+  std::vector<double> lane_coefs, type_coefs; bool exponential = false;
+  double crit = 0, last_inst_creation = 0;                         // m_dbCritCreationVeh, m_dbLastInstCreation
+  std::vector<int> pret;                                           // m_mapVehPret[link][lane] (-1 none)
+  std::vector<std::deque<Veh*>> attente; };                        // m_mapVehEnAttente[link][lane]
+struct Exit { int node, link; double capacity; };
+
+// ---- car-following context: carFollowing/CarFollowingContext.h, NewellContext.h ---------------
+struct Ctx {
+  std::vector<int> lanes; Veh* leader = nullptr; int leader_id = -1; double leader_dist = 0;
+  double start_pos = 0; bool free_flow = true; double deltaN = 1; bool contraction = false;
+};
+
+// ---- vehicle: vehicule.h:310-420 --------------------------------------------------------------
+struct Veh {
+  int id = 0, cls = 0; double w = 0, kx = 0, vx = 0, vit_max = 0;
+  double pos[2], vit[2], acc[2]; int lane[2], link[2];
+  int route = -1, route_pos = 0, next_link = -1;
+  bool deja_calcule = false, regime_fluide = true, regime_fluide_leader = true, arret_au_feu = false;
+  bool end_leg = false, b_deceleration = false, attente_insertion = false;
+  double deceleration = -1;
+  double inst_creation = 0, creation_pos = 0, generation_pos = UNDEF_POSITION, heure_entree = 0, inst_sortie = -1;
+  double inst_dest_reached = 0; int dest_enter_lane = -1;
+  double dst_parcourue = 0, vit_reg_tuy_act = 0;
+  int voie_desiree = -1; int prev_lane = -1;
+  std::vector<int> used_lanes; std::map<int, double> tirage;      // m_LstUsedLanes, m_NextVoieTirage
+  std::vector<int> tuyaux_parcourus;
+  std::unique_ptr<Ctx> ctx, prev_ctx;
+  bool in_list = false; int dead = 0;
+};
+struct LessId { bool operator()(const Veh* a, const Veh* b) const { return a->id < b->id; } };   // tools.h:67-74
+
+struct Exited { int id; double inst; };
+
+// =================================================================================================
+struct Sim {
+  // parameters
+  double dt = 1, duree = 0; unsigned seed = 0; bool accbornee = false; double relax = 1; bool chgtvoie = false;
+  double dst_chgtvoie = 50; double bevel = 0;
+  std::vector<Cls> cls; std::vector<Link> links; std::vector<Lane> lanes; std::vector<Ctrl> ctrls;
+  std::vector<std::vector<int>> routes; std::vector<Entry> entries; std::vector<Exit> exits;
+  std::vector<int> node_type, node_ctrl;
+  // dynamic
+  double t = 0; int ninst = 0; int last_id = 0; RandManager rnd;
+  std::vector<Veh*> lst;                                           // m_LstVehicles (order is part of the contract)
+  std::vector<std::unique_ptr<Veh>> owned;                         // everything ever created and still alive
+  std::vector<std::set<Veh*, LessId>> lane_set;                   // VoieMicro::m_LstVehiculesAnt (voie.h:240)
+  std::vector<int> nb_entre, nb_sorti;                            // Tuyau::m_mapNbVehEntre/Sorti (tuyau.h:531-532), [link*T+cls]
+  std::vector<Exited> exited;                                      // removed this step
+  std::vector<Veh*> graveyard;
+  double min_kv = 0, max_vit_max = 0, max_debit_max = 0;
+  long n_ties = 0, n_loops = 0, n_created = 0;
+
+  // ---------------------------------------------------------------------------------------------
+  bool load(const char* path) {
+    Flat f; if (!f.load(path)) return false;
+    const double* P = f.D("params");
+    dt = P[0]; duree = P[1] * dt; seed = (unsigned)P[2]; accbornee = P[3] != 0; relax = P[4]; chgtvoie = P[5] != 0;
+    dst_chgtvoie = P[6];
+    const double* C = f.D("cls"); size_t T = f.N("cls") / 24;
+    for (size_t i = 0; i < T; i++) { const double* c = C + 24 * i; Cls k; k.w = c[0]; k.kx = c[1]; k.vx = c[2]; k.esp = c[3];
+      k.decel = c[4]; k.tau_lc = c[5]; k.pi_rab = c[6]; k.law = (int)c[7];
+      for (int j = 0; j < (int)c[8]; j++) k.plages.push_back({c[9 + 2 * j], c[10 + 2 * j]});
+      cls.push_back(k); }
+    const int* li = f.I("link_i"); const double* lf = f.D("link_f"); size_t K = f.N("link_i") / 8;
+    for (size_t k = 0; k < K; k++) links.push_back({li[8 * k], li[8 * k + 1], li[8 * k + 2], li[8 * k + 3], (char)li[8 * k + 4], li[8 * k + 5], lf[2 * k], lf[2 * k + 1]});
+    const int* la = f.I("lane_i"); const double* laf = f.D("lane_f"); size_t L = f.N("lane_i") / 4;
+    const int* so = f.I("succ_off"); const int* si = f.I("succ_i"); const double* sf = f.D("succ_f");
+    const int* lo = f.I("sl_off"); const int* sli = f.I("sl_i"); const double* slf = f.D("sl_f");
+    for (size_t l = 0; l < L; l++) { Lane x; x.link = la[4 * l]; x.num = la[4 * l + 1]; x.prev_lane = la[4 * l + 2]; x.flags = la[4 * l + 3]; x.length = laf[l];
+      for (int m = so[l]; m < so[l + 1]; m++) x.succ.push_back({si[3 * m], si[3 * m + 1], si[3 * m + 2], sf[m]});
+      for (int m = lo[l]; m < lo[l + 1]; m++) x.sl.push_back({sli[6 * m], sli[6 * m + 1], sli[6 * m + 2], sli[6 * m + 3], sli[6 * m + 4], slf[m]});
+      lanes.push_back(std::move(x)); }
+    const int* ci = f.I("ctrl_i"); const double* cf = f.D("ctrl_f"); const int* qi = f.I("seq_i"); const double* qf = f.D("seq_f");
+    const int* gi = f.I("sig_i"); const double* gf = f.D("sig_f");
+    for (size_t c = 0; c < f.N("ctrl_i") / 2; c++) { Ctrl x; x.cycle = cf[c];
+      for (int q = ci[2 * c]; q < ci[2 * c] + ci[2 * c + 1]; q++) { Seq s; s.len = qf[q];
+        for (int g = qi[2 * q]; g < qi[2 * q] + qi[2 * q + 1]; g++) s.sig.push_back({gi[2 * g], gi[2 * g + 1], gf[3 * g], gf[3 * g + 1], gf[3 * g + 2]});
+        x.seqs.push_back(std::move(s)); }
+      ctrls.push_back(std::move(x)); }
+    const int* ni = f.I("node_i");
+    for (size_t n = 0; n < f.N("node_i") / 4; n++) { node_type.push_back(ni[4 * n]); node_ctrl.push_back(ni[4 * n + 1]); }
+    const int* ro = f.I("route_off"); const int* rl = f.I("route_links");
+    for (size_t r = 0; r + 1 < f.N("route_off"); r++) routes.emplace_back(rl + ro[r], rl + ro[r + 1]);
+    const int* xi = f.I("exit_i"); const double* xf = f.D("exit_f");
+    for (size_t x = 0; x < f.N("exit_i") / 2; x++) exits.push_back({xi[2 * x], xi[2 * x + 1], xf[x]});
+    const int* ei = f.I("entry_i"); const double* df = f.D("dem_f"); const int* di = f.I("dest_i"); const double* dcf = f.D("dest_f");
+    const int* dri = f.I("droute_i"); const double* drf = f.D("droute_f"); const double* lcf = f.D("lanecoef_f"); const double* tcf = f.D("typecoef_f");
+    for (size_t e = 0; e < f.N("entry_i") / 8; e++) { const int* r = ei + 8 * e; Entry x; x.node = r[0]; x.link = r[1];
+      for (int d = r[2]; d < r[2] + r[3]; d++) x.demand.push_back({df[2 * d], df[2 * d + 1]});
+      for (int d = r[4]; d < r[4] + r[5]; d++) { Dest y; y.exit = di[3 * d]; y.coeff = dcf[d];
+        for (int q = di[3 * d + 1]; q < di[3 * d + 1] + di[3 * d + 2]; q++) y.routes.push_back({dri[q], drf[q]});
+        x.dests.push_back(std::move(y)); }
+      int nl = links[x.link].n_lanes; x.exponential = (r[7] >> 30) & 1; int tco = r[7] & 0x3fffffff;
+      for (int k = 0; k < nl; k++) x.lane_coefs.push_back(lcf[r[6] + k]);
+      for (size_t k = 0; k < T; k++) x.type_coefs.push_back(tcf[tco + k]);
+      x.pret.assign(nl, -1); x.attente.resize(nl);
+      entries.push_back(std::move(x)); }
+    lane_set.resize(lanes.size()); nb_entre.assign(links.size() * T, 0); nb_sorti.assign(links.size() * T, 0);
+    // Reseau::GetMinKv reseau.cpp:9719-9737, GetMaxVitMax :9700-9715, m_dbMaxDebitMax :5915
+    min_kv = 999; max_vit_max = 0; max_debit_max = 0;
+    for (auto& c : cls) { double kv = -c.kx * c.w / (c.vx - c.w); if (kv < min_kv) min_kv = kv; if (c.vx > max_vit_max) max_vit_max = c.vx;
+      if (c.debit_max() > max_debit_max) max_debit_max = c.debit_max(); }
+    rnd.mySrand(seed);                                              // reseau.cpp:983-995 (seed != 0)
+    // initial vehicles: reseau.cpp:11680-11773 (load), :1293-1340 (copy into m_LstVehicles at InitSimuTrafic)
+    const int* ivi = f.I("iv_i"); const double* ivf = f.D("iv_f");
+    for (size_t v = 0; v < f.N("iv_i") / 4; v++) {
+      Veh* p = new_vehicle(ivi[4 * v], last_id++, false);   // law object copied, no draw (vehicule.cpp:5246-5250)
+      p->lane[0] = ivi[4 * v + 1]; p->link[0] = lanes[p->lane[0]].link; p->route = ivi[4 * v + 2]; p->route_pos = ivi[4 * v + 3];
+      p->pos[0] = ivf[3 * v]; p->vit[0] = ivf[3 * v + 1]; p->acc[0] = ivf[3 * v + 2];
+      p->vit_reg_tuy_act = links[p->link[0]].vit_reg; p->heure_entree = 0;
+      add_vehicule(p);
+    }
+    return true;
+  }
+
+  // Vehicule::Vehicule vehicule.cpp:417-483 (state = UNDEF / vitmax / 0), law pick CarFollowingFactory.cpp:88-137
+  Veh* new_vehicle(int c, int id, bool draw_law = true) {
+    auto v = std::make_unique<Veh>(); Veh* p = v.get();
+    p->id = id; p->cls = c; p->w = cls[c].w; p->kx = cls[c].kx; p->vx = cls[c].vx; p->vit_max = cls[c].vx;
+    for (int i = 0; i < 2; i++) { p->pos[i] = UNDEF_POSITION; p->vit[i] = p->vit_max; p->acc[i] = 0; p->lane[i] = -1; p->link[i] = -1; }
+    if (draw_law && cls[c].law != 0) rnd.myRand();       // scripted-law coefficient pick draws once: CarFollowingFactory.cpp:99
+    owned.push_back(std::move(v));
+    return p;
+  }
+  void add_vehicule(Veh* p) { lst.push_back(p); p->in_list = true; }   // Reseau::AddVehicule reseau.cpp:4386-4395
+
+  // ------------------------------------------------------------------------------------------
+  // small accessors
+  double len_ex(int l) const { return (lanes[l].flags & 1) ? lanes[l].length - bevel : lanes[l].length; }   // voie.cpp:1451-1457
+  bool chgt_voie_obligatoire(int l) const { return lanes[l].flags & 1; }                                   // voie.cpp:789-810
+  double vit_reg(int link) const { return links[link].vit_reg; }           // tuyau.cpp:951-977 (no per-portion exceptions in scope)
+  double max_influence(const Veh* v) const {
+    const Cls& c = cls[v->cls];
+    if (c.law == 0) return 1.0 / min_kv;                                   // NewellCarFollowing.cpp:48-51
+    if (c.law == 1) return 3 * v->vit_max * dt;                           // GippsCarFollowing.cpp:45-48
+    double dec = c.decel; if (dec == 0) dec = DBL_MAX;                     // IDMCarFollowing.cpp:49-59
+    double s = c.esp + std::max<double>(1 * v->vit_max + v->vit_max * v->vit_max / (2.0 * sqrt(c.acc_max(v->vit_max) * dec)), 0);
+    return 3 * s;
+  }
+  double veh_length(const Veh* v) const { return 1 / v->kx - cls[v->cls].esp; }   // AbstractCarFollowing.cpp:50-53
+
+  // ------------------------------------------------------------------------------------------
+  // signals: ControleurDeFeux.cpp:203-307, :1517-1558, :96-148
+  int couleur(const Ctrl& c, double inst, int te, int ts, double* prop) const {   // 0 red 1 green 2 amber
+    int nsec = (int)inst;                                   // STimeSpan((int)dbInstant), plan starts with the simulation
+    int ntmp = nsec % (int)c.cycle;                         // :250-251
+    double prev = 0; const Seq* seq = nullptr; double tcur = 0;
+    for (auto& s : c.seqs) { if (prev + s.len > ntmp) { tcur = ntmp - prev; seq = &s; break; } prev += s.len; }   // :1209-1228
+    if (!seq) return 1;                                     // :280-281 (no sequence -> green)
+    const Signal* sg = nullptr;
+    for (auto& g : seq->sig) if (g.link_in == te && g.link_out == ts) { sg = &g; break; }
+    if (!sg) return 0;                                      // :293-295
+    int col;
+    if (tcur < sg->delay) col = 0; else if (tcur < sg->delay + sg->green) col = 1;
+    else if (sg->delay + sg->green <= tcur && tcur < sg->delay + sg->green + sg->amber) col = 2; else col = 0;   // :1517-1541
+    if (prop) {
+      if (col != 0) *prop = std::min<double>(1, (tcur - sg->delay) / dt);                                      // :1544-1549
+      else if (tcur < sg->delay) *prop = 1 - std::min<double>(1, tcur / dt);
+      else *prop = 1 - std::min<double>(1, (tcur - (sg->delay + sg->green + sg->amber) / dt));                 // :1555 (sic)
+    }
+    return col;
+  }
+  int statut_couleur(int ctrl, double inst, int te, int ts, double* prop) const {     // GetStatutCouleurFeux :96-148
+    const Ctrl& c = ctrls[ctrl];
+    int col = couleur(c, inst, te, ts, prop);
+    int pcol = (inst - dt > 0) ? couleur(c, inst - dt, te, ts, nullptr) : 1;
+    if (col == 0 && pcol == 0) { *prop = 0; return 0; }
+    if ((col == 1 || col == 2) && (pcol == 1 || pcol == 2)) { *prop = 1; return col; }
+    if (col == 1 && pcol == 0) return 1;
+    if (col == 0 && (pcol == 1 || pcol == 2)) { *prop = 1; return 0; }
+    return 0;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // routing: Vehicule::CalculNextTuyau vehicule.cpp:2764-2826 ('iti' mode, predefined path)
+  // Vehicule::GetItineraireIndex(isSameTuyau): first index of `link` in the route.  Routes in scope never
+  // repeat a link, so searching forward from the cursor first returns the same index.
+  int route_index(const Veh* v, int link) const {
+    const auto& r = routes[v->route];
+    for (size_t k = (size_t)std::max(0, v->route_pos); k < r.size(); k++) if (r[k] == link) return (int)k;
+    for (size_t k = 0; k < r.size() && (int)k < v->route_pos; k++) if (r[k] == link) return (int)k;
+    return -1;
+  }
+  int calcul_next_tuyau(Veh* v, int link) {
+    if (v->next_link >= 0 && link >= 0 && links[link].brick >= 0) return v->next_link;       // :2784-2789
+    const auto& r = routes[v->route];
+    // internal link: use the route link upstream of the brick (:2798-2806) = link of the movement's entry lane
+    if (links[link].brick >= 0) link = lanes[lanes[links[link].first_lane].prev_lane].link;
+    int i = route_index(v, link);                                                            // :2808
+    if (i < 0) return -1;
+    return (i + 1 < (int)r.size()) ? r[i + 1] : -1;                                          // :2811-2823
+  }
+  // Vehicule::GetTirage vehicule.cpp:1779-1795
+  double get_tirage(Veh* v, int lane_am) {
+    auto it = v->tirage.find(lane_am);
+    if (it != v->tirage.end()) return it->second;
+    double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER;
+    v->tirage[lane_am] = r; return r;
+  }
+  // Vehicule::CalculNextVoie vehicule.cpp:3070-3469, 'iti' branch (:3347-3366, :3384-3461) on flattened
+  // movements: succ rows of a lane = allowed (next external link -> lane) with rates (Connection.h
+  // GetCoeffsMouvementAutorise); for an internal CAF lane the key is the exit link and the memo key is the
+  // entry lane (pVAm, :3389), CarrefourAFeuxEx::GetNextTroncon resolves to the single successor.
+  int calcul_next_voie(Veh* v, int lane) {
+    if (lane < 0) return -1;
+    if (chgt_voie_obligatoire(lane)) return -1;                                               // :3105-3108
+    const Lane& L = lanes[lane]; const Link& T = links[L.link];
+    if (T.type_aval == 'S' || T.type_aval == 'P' || T.type_aval == 'E') return -1;            // no pCnx -> NULL (:3463)
+    const auto& r = routes[v->route];
+    int ref_link = L.link; int lane_am = lane;
+    if (T.brick >= 0) { lane_am = L.prev_lane; ref_link = lanes[lane_am].link; }              // :3172-3199 (GetVoieAmont)
+    int i = route_index(v, ref_link);                                                         // GetItineraireIndex(isSameTuyau) :3350
+    if (i < 0 || i + 1 >= (int)r.size()) return -1;                                           // :3350-3357
+    int ts = r[i + 1];
+    // allowed movement lookup
+    double sum = 0; bool any = false;
+    for (auto& s : L.succ) if (s.key_link == ts) { any = true; break; }
+    if (!any) return -1;                                                                      // bMvtAutorise false (:3446-3449)
+    double rand = get_tirage(v, lane_am);                                                     // :3413
+    for (auto& s : L.succ) if (s.key_link == ts && s.rate > 0) { sum += s.rate; if (rand <= sum) return s.next_lane; }   // :3421-3444
+    return -1;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // leader searches: reseau.cpp:3583-3640 (GetNearAvalVehicule), :3650-3820 (GetPrevVehicule),
+  // tie-breakers :14041-14128
+  Veh* get_leader_of(Veh* v) const { return (v->ctx && v->ctx->leader) ? v->ctx->leader : nullptr; }   // vehicule.cpp:5636-5644
+  Veh* get_last_vehicule(std::vector<Veh*>& l) {                                            // :14041-14081
+    if (l.size() == 1) return l[0];
+    if (l.empty()) return nullptr;
+    n_ties++;
+    for (size_t i = 0; i < l.size(); i++) { bool fol = false;
+      for (size_t j = 0; j < l.size() && !fol; j++) if (i != j) { Veh* ld = get_leader_of(l[j]); if (ld && ld->id == l[i]->id) fol = true; }
+      if (!fol) return l[i]; }
+    return l.back();
+  }
+  Veh* get_near_aval_vehicule(int lane, double pos, Veh* excl) {                            // :3583-3640
+    std::vector<Veh*> l; if (lane < 0) return nullptr;
+    double pv = lanes[lane].length + 0.00001;
+    for (Veh* c : lane_set[lane]) {
+      if (c->pos[1] >= pos && c->pos[1] <= pv) { if (!excl || excl->id != c->id) {
+        if (c->pos[1] == pv) l.push_back(c); else { l.resize(1); l[0] = c; pv = c->pos[1]; } } } }
+    return get_last_vehicule(l);
+  }
+  Veh* get_prev_vehicule(Veh* v) {                                                          // :3650-3718 (bSearchNextVoie=false)
+    int lane = v->lane[1]; if (lane < 0) return nullptr;
+    std::vector<Veh*> l; double pv = lanes[lane].length + 1;
+    for (Veh* c : lane_set[lane]) {
+      if ((c->pos[1] > v->pos[1] || (v->pos[0] == UNDEF_POSITION && c->pos[1] == v->pos[1])) && c->pos[1] <= pv && c != v) {
+        if (c->pos[1] == pv) l.push_back(c); else { l.resize(1); l[0] = c; pv = c->pos[1]; } } }
+    return get_last_vehicule(l);
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // context: CarFollowingContext.cpp:38-170, NewellContext.cpp:31-169, AbstractCarFollowing.cpp:671-685
+  void build_context(Veh* v, double range) {
+    v->prev_ctx = std::move(v->ctx);
+    v->ctx = std::make_unique<Ctx>(); Ctx& c = *v->ctx; Ctx* prev = v->prev_ctx.get();
+    c.start_pos = v->pos[1];
+    // BuildLstLanes :108-125
+    int lane = v->lane[1]; c.lanes.push_back(lane);
+    double dist = len_ex(lane) - (v->pos[1] + v->creation_pos);
+    while (dist < range && (lane = calcul_next_voie(v, lane)) >= 0) { c.lanes.push_back(lane); dist += len_ex(lane); }
+    // SearchLeaders :128-170 (the `break` leaves the lane loop at the first vehicle found, accepted or not)
+    double d = 0;
+    for (size_t i = 0; i < c.lanes.size(); i++) {
+      int ln = c.lanes[i];
+      if (i == 0) {
+        Veh* ld = get_prev_vehicule(v);
+        if (ld) { double g = ld->pos[1] - (v->pos[1] + v->creation_pos); if (g <= range) { c.leader = ld; c.leader_id = ld->id; c.leader_dist = g; } break; }
+        d += len_ex(ln) - (v->pos[1] + v->creation_pos);
+      } else {
+        Veh* ld = get_near_aval_vehicule(ln, 0, nullptr);
+        if (ld) { double g = ld->pos[1] + d; if (g <= range) { c.leader = ld; c.leader_id = ld->id; c.leader_dist = g; } break; }
+        d += len_ex(ln);
+      }
+    }
+    if (cls[v->cls].law == 0) {                                                              // NewellContext::Build :31-44
+      if (prev) c.contraction = prev->contraction;
+      // ComputeDeltaN :121-169
+      double dn;
+      if (!c.leader) dn = 1;
+      else if (c.contraction) dn = prev->deltaN;
+      else if (!prev) dn = 1;
+      else if (prev->leader_id < 0 || prev->leader_id != c.leader_id || prev->free_flow) {
+        double kv = -c.leader->kx * c.leader->w / (c.leader->vit[1] - c.leader->w);
+        dn = std::min<double>(1, kv * c.leader_dist);
+      } else dn = prev->deltaN;
+      c.deltaN = dn;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Newell: NewellCarFollowing.cpp:53-136, :204-398
+  double newell_free(Veh* v, double dtv, const Ctx& c) {                                    // :70-111
+    double start = c.start_pos, trav = 0, rem = dtv;
+    for (size_t i = 0; i < c.lanes.size(); i++) {
+      int ln = c.lanes[i]; double sp = i == 0 ? start : 0; double lex = len_ex(ln);
+      double vmax_lane = vit_reg(lanes[ln].link);
+      double vdes = std::min<double>(v->vit_max, vmax_lane);
+      if (accbornee) vdes = std::min<double>(vdes, v->vit[1] + cls[v->cls].acc_max(v->vit[1]) * dtv);
+      double tt = (lanes[ln].length - sp) / vdes;
+      if (tt >= rem || i == c.lanes.size() - 1) { trav += rem * vdes; break; }
+      trav += lex - sp; rem -= tt;
+    }
+    return trav;
+  }
+  double newell_relax(double cur, Veh* v, Veh* L, double vL, double dtv, const Ctx& c) {    // :113-136
+    double kv = -L->kx * L->w / (L->vit[1] - L->w);
+    double kvfin = -L->kx * L->w / (vL - L->w);
+    double r = cur / (-v->kx * L->w);
+    if (c.contraction) return cur;
+    double res;
+    if ((dt - r) >= -0.0001) res = std::min<double>(1, (cur / kv + std::min<double>(r / dtv * (vL - L->vit[1]) + relax, vL) * dt) * kvfin);
+    else res = std::min<double>(1, (cur / kv + std::min<double>((vL - L->vit[1]) + relax, vL) * dt) * kvfin);
+    return std::max<double>(cur, res);
+  }
+  double newell_cong(Veh* v, double dtv, Ctx& c) {                                          // :204-398
+    Veh* L = c.leader; double dist = c.leader_dist; double vL;
+    if (L->deja_calcule) vL = L->vit[0];
+    else {                                                                                   // :217-230 (at most one leader in the context)
+      if (accbornee) vL = std::min<double>(std::min<double>(L->vit_reg_tuy_act, L->vit_max), L->vit[1] + cls[v->cls].acc_max(L->vit[1]) * dt);
+      else vL = std::min<double>(L->vit_reg_tuy_act, L->vit_max);
+    }
+    // :233-263 red-light correction: the inner `ControleurDeFeux *pCDF` declarations shadow the outer
+    // NULL pointer, so the branch never fires — nothing to restate.
+    // :266-298 non-priority merge-branch leader correction: part of row A10 (merge points), see oracle/README.md.
+    double dn0 = c.deltaN;
+    double dn1 = newell_relax(dn0, v, L, vL, dtv, c);
+    c.deltaN = dn1;
+    double r = dn0 / (-L->kx * L->w);
+    double kvfin = -L->kx * L->w / (vL - L->w);
+    double pc;
+    if ((dt - r) >= -0.0001) {
+      pc = dist + vL * dt - dn1 / kvfin;
+      if (pc <= 0.0001 && dn0 < 1) { c.deltaN = dn0; pc = dist + vL * dt - dn0 / kvfin; }
+    } else {
+      double alpha = -L->w * L->kx * dt / dn0;
+      if (dtv < dt) pc = dist + vL * dt - dn1 / kvfin;
+      else { pc = alpha * dist + vL * dt - alpha * dn1 / kvfin;
+        if (pc <= 0.0001 && dn0 < 1) { c.deltaN = dn0; pc = alpha * dist + vL * dt - alpha * dn0 / kvfin; } }
+    }
+    return pc;
+  }
+  // Gipps: GippsCarFollowing.cpp:50-122 ; IDM: IDMCarFollowing.cpp:61-211 ; distance AbstractCarFollowing.cpp:692-716
+  double compute_law(Veh* v, double dtv, Ctx& c) {
+    const Cls& k = cls[v->cls];
+    if (k.law == 0) {                                                                        // Newell InternalCompute :53-68
+      bool ff = true; double d = newell_free(v, dtv, c);
+      if (c.leader) { double dc = newell_cong(v, dtv, c); if (dc < d) { ff = false; d = dc; } }
+      c.free_flow = ff; return d;
+    }
+    int fl = c.lanes.front(); double vmaxl = std::min<double>(v->vit_max, vit_reg(lanes[fl].link));
+    if (k.law == 1) {
+      const double A = 2.5, B = 0.025, G = 0.5, TH = 1;
+      bool ff = true;
+      double vf = v->vit[1] + A * k.acc_max(v->vit[1]) * dtv * (1 - v->vit[1] / vmaxl) * pow(B + v->vit[1] / vmaxl, G);
+      if (c.leader) { Veh* L = c.leader;
+        double dmax = -k.decel; if (dmax == 0) dmax = -DBL_MAX;
+        double dlmax = -cls[L->cls].decel; if (dlmax == 0) dlmax = -DBL_MAX;
+        double fac = dmax * (dtv / 2.0 + TH);
+        double sq = fac * fac - dmax * (2.0 * (c.leader_dist - (veh_length(L) + k.esp)) - v->vit[1] * dtv - L->vit[1] * L->vit[1] / dlmax);
+        double vc = sq >= 0 ? fac + sqrt(sq) : 0;
+        if (vc < vf) { ff = false; vf = vc; } }
+      c.free_flow = ff; return vf * dtv;
+    }
+    // IDM (non-improved: CarFollowingFactory.cpp:118)
+    double sp = v->vit[1], relpos, relsp;
+    if (c.leader) { relpos = c.leader_dist - veh_length(c.leader); relsp = v->vit[1] - c.leader->vit[1]; }
+    else { relpos = DBL_MAX; relsp = v->vit[1]; }
+    double amax = k.acc_max(sp); double dec = k.decel; if (dec == 0) dec = DBL_MAX;
+    double z;
+    if (relpos <= 0) z = 2;
+    else { double dsp = k.esp + std::max<double>(1 * sp + (sp * relsp) / (2.0 * sqrt(amax * dec)), 0); z = dsp / relpos; }
+    c.free_flow = z < 1;
+    double a = amax * (1.0 - pow(sp / vmaxl, 4) - pow(z, 1.5));
+    return v->vit[1] * dtv + 0.5 * a * dtv * dtv;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Vehicule::CalculDeceleration vehicule.cpp:1017-1074
+  double calcul_deceleration(Veh* v, double pas, double limite) {
+    double g = limite;
+    if (v->ctx->free_flow) {
+      v->b_deceleration = true;
+      if (v->deceleration == -1) v->deceleration = cls[v->cls].decel;                       // vehicule.cpp:142-154 (sigma = 0)
+      double dd = 0;
+      if (v->deceleration != 0) { double N = floor(v->vit[1] / (v->deceleration * dt)); dd = N * v->vit[1] * dt - ((N + 1) * N / 2) * v->deceleration * dt * dt; }
+      else return g;
+      if (v->vit[1] == 0) { double tm = sqrt(2.0 * limite / v->deceleration); double s = v->deceleration * tm; g = std::min<double>(g, s * pas); }
+      else { double ld = limite - dd; double T = ld / v->vit[1];
+        if (T <= pas) { if (T < 0) T = 0; g = std::max<double>(std::min<double>(g, v->vit[1] * pas - v->deceleration * (pas - T)), 0); } }
+    }
+    return g;
+  }
+  // Vehicule::CalculTraficFeux vehicule.cpp:1799-1945
+  bool calcul_trafic_feux(Veh* v, double inst, double dtv, double start_of_lane, double start_on_lane, double end_on_lane,
+                          double goal, int lane, size_t ilane, const std::vector<int>& lst, double& mini, bool& arret) {
+    bool infl = false; int aval = -1;
+    for (auto& lf : lanes[lane].sl) {
+      if (lf.pos >= start_on_lane) {
+        int am = links[lanes[lane].link].brick >= 0 ? lanes[lane].prev_lane : lane;          // :1840-1847 (GetPrevVoie of an internal lane)
+        if (am >= 0 && lf.up_link == lanes[am].link && lf.up_num == lanes[am].num) {
+          if (aval < 0) {
+            for (size_t n = ilane + 1; n < lst.size() && aval < 0; n++) if (links[lanes[lst[n]].link].brick < 0) aval = lst[n];
+            if (aval < 0) { aval = lst.back(); do { aval = calcul_next_voie(v, aval); } while (aval >= 0 && links[lanes[aval].link].brick >= 0); }
+          }
+          if (aval >= 0 && lf.down_link == lanes[aval].link && lf.down_num == lanes[aval].num) {
+            double p = 0; int col = statut_couleur(lf.ctrl, inst, lf.up_link, lf.down_link, &p);
+            double dloc = (start_of_lane - start_on_lane) + lf.pos;
+            if (col == 0 && fabs(p) < 0.00001) { mini = dloc; arret = true; return true; }
+            double ts = v->vit[1] > 0 ? dloc / v->vit[1] : dloc / (end_on_lane / dtv);
+            if (col != 1 && p > 0) { if (ts > p * dtv) { mini = dloc; arret = true; return true; } }
+            if (col == 1 && p < 1) {
+              if (ts > dtv * (1 - p)) {} else { infl = true; if (v->vit[1] > 0) mini = goal - (1 - p) * v->vit[1] * dtv; else mini = goal * p; }
+            }
+            break;
+          }
+        }
+      }
+    }
+    return infl;
+  }
+  // Sortie::GetNextEnterInstant sortie.cpp:60-118
+  double next_enter_instant(const Exit& x, int nvoie, double prev, double inst, double pas) {
+    double cap = x.capacity < 0 ? NONVAL_DOUBLE : x.capacity;
+    if (cap >= NONVAL_DOUBLE) return inst;
+    double cum = 0, cump = 0, ti = prev;
+    while (cum < 1 && ti <= duree) { cump = cum; cum += cap * pas / nvoie; ti += pas; }
+    if (cum < 1) return -1;
+    return (ti - pas) + (1 - cump) / (cum - cump) * pas;
+  }
+  // Vehicule::CheckNetworkInfluence vehicule.cpp:1591-1708
+  bool check_network_influence(Veh* v, double inst, double dtv, int lane, double llen, size_t ilane, const std::vector<int>& lst,
+                               double trav, double goal, double start, double end, double& mini) {
+    bool infl = false; mini = DBL_MAX; const Link& T = links[lanes[lane].link];
+    if (end > llen) {                                                                        // 1 - lane end
+      bool stop = chgt_voie_obligatoire(lane) || ((ilane == lst.size() - 1) && T.type_aval != 'S' && T.type_aval != 'P');
+      if (stop) { v->regime_fluide = false; infl = true; mini = std::min<double>(mini, trav + llen - start); }
+    }
+    // 2 - next trip node deceleration: the only trip node in scope is the final exit, reached by crossing
+    // the lane end (GetNextTripNodeDistance returns DBL_MAX for a punctual exit) -> no effect.
+    if (T.type_aval == 'S' || T.type_aval == 'P') {                                          // exit capacity :1636-1666
+      double pcrit = llen - max_influence(v);
+      if (end > pcrit) {
+        double ts = lanes[lane].next_inst_sortie;
+        if (ts < 0) { infl = true; mini = std::min<double>(mini, trav + pcrit - start); }
+        else if (ts > inst - dtv) { double vv = (trav + llen - start) / (ts - (inst - dtv)); infl = true; mini = std::min<double>(mini, vv * dtv); }
+      }
+    }
+    // 3 - downstream punctual connection (Convergent::ComputeTraffic convergent.cpp:1368-1403): row A10, pending.
+    // 4 - signals :1680-1705
+    double ml = goal + 1; bool arret = false;
+    if (calcul_trafic_feux(v, inst, dtv, trav, start, end, goal, lane, ilane, lst, ml, arret)) {
+      if (arret) { double md = calcul_deceleration(v, dtv, ml); ml = std::min<double>(ml, md); }
+      if (ml < goal) { infl = true; if (ml < mini) { mini = ml; if (arret) { v->regime_fluide = false; v->arret_au_feu = true; } } }
+    }
+    return infl;
+  }
+
+  bool is_leg_done(Veh* v, int lane, double llen, double end) {                             // TripLeg.cpp:91-117, Position.cpp:394-404
+    const Link& T = links[lanes[lane].link];
+    if (!(end > llen && T.type_aval == 'S')) return false;
+    return routes[v->route].back() == lanes[lane].link;
+  }
+  void update_used_lanes(Veh* v) {                                                          // vehicule.cpp:1751-1775
+    if (!v->used_lanes.empty()) {
+      for (size_t i = 0; i < v->used_lanes.size(); i++) if (v->used_lanes[i] == v->lane[0]) { v->used_lanes.resize(i); break; }
+      if (v->link[0] >= 0 && v->link[0] == v->link[1]) v->used_lanes.clear();
+    }
+  }
+  void set_voie_ant(Veh* v, int lane) {                                                     // vehicule.cpp:928-955
+    if (v->lane[1] >= 0) lane_set[v->lane[1]].erase(v);
+    v->lane[1] = lane;
+    if (lane >= 0) lane_set[lane].insert(v);
+  }
+  static void set_acc(Veh* v, double a) { if (fabs(a) < 0.000001) a = 0; v->acc[0] = a; }  // vehicule.h:501
+
+  // ------------------------------------------------------------------------------------------
+  // Vehicule::CalculTraficEx vehicule.cpp:1192-1588
+  void calcul_trafic_ex(Veh* v, double inst, std::vector<int>& ids) {
+    if (v->deja_calcule) return;
+    for (int id : ids) if (id == v->id) { if (cls[v->cls].law == 0) n_loops++; return; }   // :1203-1216
+    ids.push_back(v->id);
+    int prevlane = v->lane[1];
+    if (prevlane < 0) { prevlane = v->lane[0]; set_voie_ant(v, prevlane); }                 // :1220-1232
+    bool created;
+    if (v->pos[1] <= UNDEF_POSITION) {                                                       // :1235-1268 (generation position never > 0 at an Entree)
+      created = true;
+      if (v->pos[0] <= UNDEF_POSITION) v->pos[1] = 0; else v->pos[1] = v->pos[0];
+    } else { created = false; v->creation_pos = 0; }
+    double dtv = dt - std::max<double>(0, v->inst_creation);                                // :1278
+    double range = max_influence(v) + dtv * v->vit_max;                                     // :1299, :1710-1715
+    build_context(v, range);                                                                 // :1302
+    Ctx& c = *v->ctx;
+    if (c.leader) calcul_trafic_ex(c.leader, inst, ids);                                    // :1304-1309 leader first
+    double goal = compute_law(v, dtv, c);                                                    // :1312
+    v->regime_fluide = c.free_flow; v->regime_fluide_leader = v->regime_fluide;             // :1313-1315
+    v->arret_au_feu = false;
+    double start = v->pos[1] + v->creation_pos;
+    double mgoal = goal + 1, trav = 0;
+    const std::vector<int> lst = c.lanes;
+    for (size_t i = 0; i < lst.size(); i++) {                                               // :1324-1341
+      int ln = lst[i]; double sp = i == 0 ? start : 0; double llen = len_ex(ln); double ep = goal - trav + sp; double ml;
+      if (check_network_influence(v, inst, dtv, ln, llen, i, lst, trav, goal, sp, ep, ml)) if (ml < mgoal) mgoal = ml;
+      trav += std::min<double>(ep, llen) - sp;
+    }
+    goal = std::min<double>(goal, mgoal);                                                    // :1343
+    bool cancel = false;
+    if (created && goal + v->creation_pos <= 0) { cancel = true; v->creation_pos = v->creation_pos + goal; }   // :1346-1351
+    goal = std::max<double>(0, goal);
+    if (created && !v->regime_fluide && c.leader) v->vit[0] = std::min<double>(v->vit_max, c.leader->vit[1]);   // :1358-1365
+    else v->vit[0] = dtv != 0 ? goal / dtv : v->vit_max;
+    if (created) set_acc(v, 0); else set_acc(v, dtv != 0 ? (v->vit[0] - v->vit[1]) / dtv : 0);   // :1368-1375
+    v->used_lanes.clear(); trav = 0; double trav_dest = 0; int dest_lane = -1;
+    for (size_t i = 0; i < lst.size(); i++) {                                               // :1384-1506
+      int ln = lst[i]; double sp = i == 0 ? start : 0; double llen = len_ex(ln); double ep = goal - trav + sp;
+      trav += std::min<double>(ep, llen) - sp;
+      char ta = links[lanes[ln].link].type_aval; bool is_exit = ta == 'P' || ta == 'S'; bool last = i == lst.size() - 1;
+      if ((last && !is_exit && ep > llen) || (v->arret_au_feu && ep > llen && ep < llen + 0.00001)) ep = llen;   // :1397-1403
+      bool reached = is_leg_done(v, ln, llen, ep);
+      if (reached) { dest_lane = ln; trav_dest = trav; }
+      if (reached) { v->link[0] = lanes[ln].link; v->lane[0] = ln; v->pos[0] = ep; break; }  // :1417-1423
+      else if (ep <= llen) { v->link[0] = lanes[ln].link; v->lane[0] = ln; v->pos[0] = ep; break; }   // :1425-1431
+      // :1485-1496 AddInsVeh on the downstream punctual connection: consumed by row A10 (merge points), pending.
+      if (i > 0) v->used_lanes.push_back(ln);                                                // :1499-1502
+      v->voie_desiree = -1;                                                                  // :1505
+    }
+    if (dest_lane >= 0) {                                                                    // :1512-1527
+      double ti = goal > 0.0001 ? inst - dtv + dtv * (trav_dest / goal) : inst - dtv;
+      v->end_leg = true; v->dest_enter_lane = dest_lane; v->inst_dest_reached = ti;
+    }
+    if (!v->end_leg && v->link[0] >= 0) update_used_lanes(v);                               // :1560-1564 (traversees off)
+    if (cancel) { v->pos[1] = UNDEF_POSITION; v->pos[0] = UNDEF_POSITION; }                 // :1567-1571
+    v->deja_calcule = true; v->inst_creation = 0;                                           // :1573-1574
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Vehicule::DecalVarTrafic vehicule.cpp:958-1015 (history depth > 2 is never read by the micro path)
+  void decal(Veh* v) {
+    v->deja_calcule = false; v->attente_insertion = false; v->b_deceleration = false; v->end_leg = false;
+    if (v->lane[0] != v->lane[1]) v->prev_lane = v->lane[1];
+    v->pos[1] = v->pos[0]; if (v->pos[1] != UNDEF_POSITION && fabs(v->pos[1]) < 0.00001) v->pos[1] = 0;
+    v->lane[1] = v->lane[0]; v->link[1] = v->link[0]; v->vit[1] = v->vit[0]; v->acc[1] = v->acc[0];
+    v->lane[0] = -1; v->link[0] = -1; v->pos[0] = 0; v->vit[0] = 0; v->acc[0] = 0;
+  }
+  // Reseau::InitVehicules reseau.cpp:3901-3976
+  void init_vehicules() {
+    for (auto& s : lane_set) s.clear();
+    for (Veh* v : lst) {
+      decal(v);
+      if (v->lane[1] >= 0) lane_set[v->lane[1]].insert(v);
+      if (v->link[1] >= 0) {
+        if (v->next_link < 0) v->next_link = calcul_next_tuyau(v, v->link[1]);
+        // CalculVoiesPossibles / CalculVoieDesiree (vehicule.cpp:4749-5039) only feed the lane-change
+        // procedure (row A9, pending); they draw no random numbers.
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // demand: usage/SymuViaTripNode.cpp:847-955 (UpdateCritCreationVeh), :212-325 (CreationVehicules),
+  // :331-840 (GenerateVehicle), :1642-1851 (InsertionVehEnAttente)
+  double demande_value(const Entry& e, double inst) const {
+    double acc = 0; for (auto& d : e.demand) { acc += d.first; if (inst <= acc) return d.second; }
+    return e.demand.empty() ? 0 : e.demand.back().second;
+  }
+  void update_crit_creation(Entry& e, double inst, bool due_to_creation) {                  // :847-955
+    if (!e.exponential) { e.crit += demande_value(e, inst) * dt; return; }                  // :905-911
+    if (fabs(demande_value(e, inst) - demande_value(e, inst - dt)) > DBL_EPSILON || fabs(inst - dt) < DBL_EPSILON || due_to_creation) {   // :915-917
+      double niveau = demande_value(e, inst); if (niveau > max_debit_max) niveau = max_debit_max;
+      double r = 0; while (r <= 0) r = (double)rnd.myRand() / MAXIMUM_RANDOM_NUMBER;
+      e.crit = niveau > 0 ? inst - log(r) * (1 - niveau / max_debit_max) / niveau + 1 / max_debit_max : DBL_MAX;   // :935-940
+    }
+  }
+  Veh* generate_vehicle(Entry& e, double inst, double inst_creat) {                         // :331-840
+    const Link& T = links[e.link];
+    // lane draw: CalculNumVoie :1928-1999
+    int nv = 0; { double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER; double sum = 0;
+      for (; nv < T.n_lanes; nv++) { double cf = e.lane_coefs[nv]; if (cf <= 0) continue; sum += cf; if (sum >= r) break; }
+      if (nv >= T.n_lanes) nv = T.n_lanes - 1; }
+    // type draw: RepartitionTypeVehicule.cpp:78-125
+    int tv = -1; { double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER; double sum = 0; int lastnn = -1;
+      for (size_t i = 0; i < cls.size(); i++) { double cf = e.type_coefs[i]; if (cf <= 0) continue; lastnn = (int)i; sum += cf; if (r <= sum) { tv = (int)i; break; } }
+      if (tv < 0) tv = lastnn; }
+    Veh* v = new_vehicle(tv, last_id++);                                                     // IncLastIdVeh, ctor, InitializeCarFollowing
+    // destination draw: GetDestination :1255-1322
+    int d = -1; { double r = (double)rnd.myRand() / MAXIMUM_RANDOM_NUMBER; double sum = 0;
+      for (size_t i = 0; i < e.dests.size(); i++) { if (e.dests[i].coeff <= 0) continue; sum += e.dests[i].coeff; if (i == e.dests.size() - 1) sum = 1;
+        if (r <= sum) { d = (int)i; break; } } }
+    if (d < 0) { return nullptr; }
+    // itinerary draw: :515-556
+    { double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER; double sum = 0; const Dest& D = e.dests[d]; v->route = D.routes.back().route;
+      for (auto& q : D.routes) { sum += q.coeff; if (r <= sum) { v->route = q.route; break; } } }
+    v->route_pos = 0;
+    v->lane[0] = T.first_lane + nv; v->link[0] = e.link;                                    // SetVoie / SetTuyau :688-691
+    v->inst_creation = inst_creat; v->heure_entree = inst - dt + inst_creat;                // :722-724
+    v->vit_reg_tuy_act = T.vit_reg;
+    rnd.myRand();                                                                            // TirageJorge vehicule.cpp:747-759 (unconditional draw)
+    n_created++;
+    // ready / waiting lists :780-817 (CanInsertVehicle is always true for an Entree: SymuViaTripNode.h:217)
+    if (e.pret[nv] != -1 || !e.attente[nv].empty()) e.attente[nv].push_back(v);
+    else { e.pret[nv] = v->id; add_vehicule(v); }
+    return v;
+  }
+  void creation_vehicules(Entry& e, double inst) {                                          // :212-325
+    for (;;) {
+      bool creation; double inst_creat = 0;
+      if (e.exponential) {
+        creation = e.crit <= inst;
+        if (creation) { inst_creat = e.crit - (inst - dt); if (inst - dt + inst_creat >= 0) update_crit_creation(e, inst - dt + inst_creat, true); }
+      } else {
+        creation = e.crit >= 1;
+        if (creation) { double q = demande_value(e, inst); if (q != 0.0) { inst_creat = dt - (e.crit - 1) * dt / (q * dt); e.crit -= 1; } }
+      }
+      if (!creation) break;
+      generate_vehicle(e, inst, inst_creat);
+    }
+  }
+  Veh* from_id(int id) { for (Veh* v : lst) if (v->id == id) return v; return nullptr; }
+  void insertion_veh_en_attente(Entry& e, double inst) {                                    // :1642-1851
+    int nl = links[e.link].n_lanes;
+    for (int nv = 0; nv < nl; nv++) {
+      if (e.pret[nv] != -1) {
+        Veh* p = from_id(e.pret[nv]);
+        if (!p) continue;
+        if (p->pos[0] > p->generation_pos) {
+          e.pret[nv] = -1;
+          double ie = inst;
+          if (p->vit[0] > 0) { ie -= dst_parcourue_ex(p) / p->vit[0]; ie = std::max<double>(p->heure_entree, ie); }
+          e.last_inst_creation = ie;
+        } else continue;
+      }
+      if (!e.attente[nv].empty()) {
+        Veh* p = e.attente[nv].front();
+        // CanInsertVehicle() == true -> first branch :1747-1789
+        std::vector<int> ids; calcul_trafic_ex(p, inst, ids);
+        if (p->pos[0] > p->generation_pos) {
+          e.attente[nv].pop_front(); add_vehicule(p);
+          double ie = inst;
+          if (p->vit[0] > 0) { ie -= dst_parcourue_ex(p) / p->vit[0]; ie = std::max<double>(p->heure_entree, ie); }
+          e.last_inst_creation = ie;
+        } else { p->pos[0] = UNDEF_POSITION; p->vit[0] = p->vit_max; p->inst_creation = 0; p->deja_calcule = false; }
+      }
+    }
+  }
+  double dst_parcourue_ex(Veh* v) {                                                         // vehicule.cpp:3879-3915
+    if (v->link[0] == v->link[1]) return v->pos[0] - v->pos[1];
+    if (v->link[1] < 0 && v->lane[1] == v->lane[0]) return v->pos[0];
+    double d;
+    if (v->lane[1] >= 0) d = lanes[v->lane[1]].length - v->pos[1]; else return v->vit[0] * dt;
+    for (int u : v->used_lanes) if (v->lane[0] != u) d += lanes[u].length;
+    return d + v->pos[0];
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Vehicule::FinCalculTrafic vehicule.cpp:4254-4583
+  void fin_calcul_trafic(Veh* v, double inst) {
+    size_t T = cls.size();
+    if (v->link[1] != v->link[0] || v->link[0] == v->next_link) {                          // :4309-4325
+      if (v->link[0] >= 0 && links[v->link[0]].brick >= 0) {
+        // keep next_link only if it is a downstream link of the brick
+        bool aval = v->next_link >= 0 && links[v->next_link].up_node == links[v->link[0]].brick;
+        if (!aval) v->next_link = -1;
+      } else v->next_link = -1;
+    }
+    if (v->link[1] < 0 || v->lane[1] < 0) v->dst_parcourue = v->pos[0];                     // :4328-4333
+    else if (v->link[0] < 0) v->dst_parcourue += lanes[v->lane[1]].length - v->pos[1];
+    else v->dst_parcourue += v->vit[0] * dt;
+    if ((v->link[1] >= 0 || v->link[0] >= 0) && v->link[1] != v->link[0]) {                // :4337-4442 ('iti' counters)
+      int tp = v->link[1], tn = v->link[0];
+      if (tp >= 0 && links[tp].brick < 0) nb_sorti[tp * T + v->cls]++;
+      if (tn >= 0 && links[tn].brick < 0) nb_entre[tn * T + v->cls]++;
+    }
+    // route cursor: index of the last external link entered (GetItineraireIndex on a repeat-free route)
+    if (v->link[0] >= 0 && links[v->link[0]].brick < 0 && v->link[0] != v->link[1]) {
+      int k = route_index(v, v->link[0]); if (k >= 0) v->route_pos = k;
+    }
+    if (!v->b_deceleration) v->deceleration = -1;                                           // :4555-4559
+    if (v->end_leg) {                                                                        // :4577-4581 -> TripNode::VehiculeEnter TripNode.cpp:167-177
+      int dl = v->dest_enter_lane;
+      v->link[0] = -1; v->lane[0] = -1; v->deja_calcule = true; v->inst_sortie = v->inst_dest_reached;
+      // Sortie::VehiculeEnter sortie.cpp:119-130
+      for (auto& x : exits) if (x.link == lanes[dl].link) {
+        lanes[dl].next_inst_sortie = next_enter_instant(x, links[lanes[dl].link].n_lanes, v->inst_dest_reached, inst, dt);
+        break; }
+      v->regime_fluide = true;
+    }
+  }
+  // Reseau::SupprimeVehicules reseau.cpp:3984-4216 (order preserved)
+  void supprime_vehicules() {
+    exited.clear();
+    std::vector<Veh*> keep; keep.reserve(lst.size());
+    for (Veh* v : lst) { if (v->link[0] < 0) { exited.push_back({v->id, v->inst_sortie}); v->in_list = false; } else keep.push_back(v); }
+    // Storage of a vehicle removed at step k is released at the end of step k+1: until every survivor has
+    // rebuilt its context, Ctx::leader may still point at it (the reference holds shared_ptrs).
+    if (!graveyard.empty()) {
+      owned.erase(std::remove_if(owned.begin(), owned.end(), [](const std::unique_ptr<Veh>& p) { return p->dead == 2; }), owned.end());
+      graveyard.clear();
+    }
+    if (keep.size() != lst.size()) {
+      for (Veh* v : lst) if (v->link[0] < 0) { v->dead = 2; graveyard.push_back(v); }
+      lst.swap(keep);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------
+  // Reseau::SimuTrafic reseau.cpp:2028-2428 + SimuTraficMicroMacro :14152-14470
+  int step() {
+    t += dt; ninst++;                                                                        // :2105-2106
+    for (auto& e : entries) update_crit_creation_step(e);                                   // :2219-2223
+    init_vehicules();                                                                        // :2250
+    for (auto& e : entries) creation_vehicules(e, t);                                       // :2255 -> :14143
+    // ChangementDeVoie :14181 (row A9, pending) ; ComputeFirstVehicules :14184 (only consumed by flux nodes)
+    for (size_t i = 0; i < lst.size(); i++) { std::vector<int> ids; calcul_trafic_ex(lst[i], t, ids); }   // MiseAJourVehicules :3827-3865
+    for (auto& e : entries) insertion_veh_en_attente(e, t);                                 // :14293-14296
+    // Convergent::CalculInsertion :14310-14314 (row A10, pending)
+    for (Veh* v : lst) fin_calcul_trafic(v, t);                                             // :14364 -> :3871
+    supprime_vehicules();                                                                    // :14418
+    for (Veh* v : lst) if (v->link[0] >= 0 && v->lane[0] >= 0) v->vit_reg_tuy_act = links[v->link[0]].vit_reg;   // UpdateVitessesReg :2606-2627
+    return (int)lst.size();
+  }
+  void update_crit_creation_step(Entry& e) {
+    if (e.exponential) update_crit_creation(e, t, false); else update_crit_creation(e, t, false);
+  }
+};
+
+}  // namespace
+
+// ---- C API (ctypes) -------------------------------------------------------------------------------
+extern "C" {
+void* orc_load(const char* path) { auto* s = new Sim(); if (!s->load(path)) { delete s; return nullptr; } return s; }
+void orc_free(void* h) { delete (Sim*)h; }
+int orc_step(void* h) { return ((Sim*)h)->step(); }
+int orc_nveh(void* h) { return (int)((Sim*)h)->lst.size(); }
+double orc_time(void* h) { return ((Sim*)h)->t; }
+unsigned orc_rng_count(void* h) { return ((Sim*)h)->rnd.count; }
+long orc_counter(void* h, int which) { Sim* s = (Sim*)h; return which == 0 ? s->n_ties : which == 1 ? s->n_loops : s->n_created; }
+// state of m_LstVehicles in list order after the step
+void orc_dump(void* h, int* id, int* lane, int* route_pos, int* flags, double* pos, double* vit, double* acc, double* deltaN) {
+  Sim* s = (Sim*)h; size_t i = 0;
+  for (Veh* v : s->lst) {
+    id[i] = v->id; lane[i] = v->lane[0]; route_pos[i] = v->route_pos;
+    flags[i] = (v->regime_fluide ? 1 : 0) | (v->arret_au_feu ? 2 : 0) | ((v->ctx && v->ctx->free_flow) ? 4 : 0) | (v->cls << 8);
+    pos[i] = v->pos[0]; vit[i] = v->vit[0]; acc[i] = v->acc[0]; deltaN[i] = v->ctx ? v->ctx->deltaN : 1.0; i++;
+  }
+}
+int orc_leaders(void* h, int* leader_id) { Sim* s = (Sim*)h; size_t i = 0; for (Veh* v : s->lst) leader_id[i++] = v->ctx ? v->ctx->leader_id : -1; return (int)i; }
+void orc_link_counts(void* h, int* entre, int* sorti) { Sim* s = (Sim*)h; size_t n = s->nb_entre.size();
+  memcpy(entre, s->nb_entre.data(), n * 4); memcpy(sorti, s->nb_sorti.data(), n * 4); }
+int orc_exited(void* h, int* ids, double* inst, int cap) { Sim* s = (Sim*)h; int n = 0;
+  for (auto& e : s->exited) { if (n < cap) { ids[n] = e.id; inst[n] = e.inst; } n++; } return n; }
+int orc_waiting(void* h) { Sim* s = (Sim*)h; int n = 0; for (auto& e : s->entries) for (auto& q : e.attente) n += (int)q.size(); return n; }
+// raw RNG access for the known-answer test of the generator itself
+void* orc_rng_new(unsigned seed) { auto* r = new RandManager(); r->mySrand(seed); return r; }
+int orc_rng_next(void* r) { return ((RandManager*)r)->myRand(); }
+unsigned orc_rng_raw(void* r) { return ((RandManager*)r)->gen.next(); }
+void orc_rng_free(void* r) { delete (RandManager*)r; }
+}
