@@ -1,0 +1,64 @@
+/* symgpu.h — thin C-ABI between the SymuVia-compatible host library and the sm_100a kernels.
+ *
+ * This is the seam SURVEY.md §8(b) places inside Reseau::SimuTrafic
+ * (symuvia/src/reseau.cpp:2250-2258): everything from InitVehicules (:3901) to
+ * SupprimeVehicules (:3984) runs on the device behind `symgpu_step`; vehicle creation at the
+ * origins (usage/SymuViaTripNode.cpp:212-325) stays on the host and feeds rows in, the
+ * trajectory rows the XML writers consume (Vehicule::SortieTrafic, vehicule.cpp:1993) come out.
+ * Plain pointers and sizes only; no CPU fallback exists: every entry point fails with
+ * SYMGPU_E_NODEVICE when no CUDA device is usable.
+ */
+#ifndef SYMGPU_H
+#define SYMGPU_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct symgpu_ctx symgpu_ctx;
+
+enum { SYMGPU_OK = 0, SYMGPU_E_NODEVICE = -1, SYMGPU_E_LOAD = -2, SYMGPU_E_CUDA = -3, SYMGPU_E_CAPACITY = -4,
+       SYMGPU_E_UNSUPPORTED = -5, SYMGPU_E_ARG = -6 };
+
+/* counters readable through symgpu_counter() */
+enum { SYMGPU_CNT_TIES = 0,      /* equal-position leader candidates met (reseau.cpp:14041-14128 tie-break not replayed) */
+       SYMGPU_CNT_LOOPS = 1,     /* leader-recursion loops broken (vehicule.cpp:1201-1216) */
+       SYMGPU_CNT_CREATED = 2,   /* vehicles generated at origins */
+       SYMGPU_CNT_PASSES = 3,    /* follow passes launched (dependency wavefronts) */
+       SYMGPU_CNT_LAUNCHES = 4,  /* kernels launched since creation */
+       SYMGPU_CNT_SLOTS = 5,     /* vehicle slots in use (alive + holes) */
+       SYMGPU_CNT_CTX_OVERFLOW = 6 /* context lane list longer than the device bound (must stay 0) */ };
+
+/* Replaces Reseau::LoadReseauXML + InitSimuTrafic for an already flattened network (include/symflat.h). */
+int symgpu_create(const char* symflat_path, int device, symgpu_ctx** out);
+void symgpu_destroy(symgpu_ctx* c);
+const char* symgpu_last_error(void);
+
+/* One Reseau::SimuTrafic time step (reseau.cpp:2028-2428): returns vehicles on the network after the step. */
+int symgpu_step(symgpu_ctx* c);
+/* n_steps steps back to back; no per-step host copies unless the network has origins. */
+int symgpu_run(symgpu_ctx* c, int n_steps);
+/* One step + trajectory rows copied into caller (host) buffers of capacity `cap` rows: the data
+ * Vehicule::SortieTrafic (vehicule.cpp:1993-2176) hands to DocTrafic::AddTrajectoire.  Returns rows written. */
+int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
+
+int symgpu_num_vehicles(symgpu_ctx* c);
+double symgpu_time(symgpu_ctx* c);
+unsigned symgpu_rng_count(symgpu_ctx* c);       /* RandManager::m_Count (RandManager.cpp:26-30) */
+long symgpu_counter(symgpu_ctx* c, int which);
+double symgpu_last_step_ms(symgpu_ctx* c);      /* device time of the last step (CUDA events on the step stream) */
+
+/* State of m_LstVehicles (list order) after the last step; any pointer may be NULL. Returns rows. */
+int symgpu_get_state(symgpu_ctx* c, int cap, int* id, int* lane, int* route_pos, int* flags, double* pos, double* vit,
+                     double* acc, double* deltaN, int* leader_id);
+/* Tuyau::m_mapNbVehEntre / m_mapNbVehSorti (tuyau.h:531-532), arrays of n_links * n_classes. */
+int symgpu_get_link_counts(symgpu_ctx* c, int* entre, int* sorti);
+/* Vehicles removed by Reseau::SupprimeVehicules (reseau.cpp:3984) during the last step. */
+int symgpu_get_exited(symgpu_ctx* c, int cap, int* id, double* instant);
+int symgpu_num_links(symgpu_ctx* c);
+int symgpu_num_classes(symgpu_ctx* c);
+int symgpu_waiting(symgpu_ctx* c);              /* vehicles queued at origins (m_mapVehEnAttente) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

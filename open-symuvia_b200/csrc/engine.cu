@@ -1,0 +1,804 @@
+// engine.cu — B200 (sm_100a) engine of SymuVia's per-time-step microscopic vehicle update and its C-ABI
+// (include/symgpu.h).  One symgpu_ctx = one Reseau: static network tables and the vehicle
+// struct-of-arrays live in HBM; one call to symgpu_step() replaces Reseau::SimuTrafic phases
+// InitVehicules .. SupprimeVehicules (symuvia/src/reseau.cpp:2250-2258, :14152-14470).
+//
+// Step pipeline (all on one stream, no host round trip unless the network has origins):
+//   k_signals      A8   per stop line: colour + green fraction of this step (ControleurDeFeux.cpp:96-148)
+//   k_prepare      A2   per vehicle : lane membership histogram          (reseau.cpp:3901-3976)
+//   scan + k_scatter + k_sort_lanes  A3: counting sort by lane, in-lane order by (position, id), own-lane
+//                       leader links, lane tail                          (reseau.cpp:3583-3820)
+//   k_context      A3/A5/A12 per vehicle: context lanes, leader, deltaN, free-flow distance
+//   k_follow_pass  A4-A7 per lane  : ordered chain front -> back (leader first, vehicule.cpp:1304-1309);
+//                       wavefront passes over the "lane head follows another lane's tail" dependency
+//   k_break_loop   A4   leader-recursion loop breaking                   (vehicule.cpp:1201-1216)
+//   k_entries      N1   first waiting vehicle of each origin lane        (usage/SymuViaTripNode.cpp:1642-1851)
+//   k_final        A13  finalisation, link counters, exits               (vehicule.cpp:4254-4583, reseau.cpp:3984)
+// There is no CPU fallback: without a CUDA device symgpu_create() fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/symgpu.h"
+#include "flatnet.h"
+#include "micro.cuh"
+
+using namespace symb200;
+
+static thread_local std::string g_err;
+#define CK(call)                                                                                         \
+  do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return SYMGPU_E_CUDA; } } while (0)
+
+__constant__ DevParams cP;
+
+// ------------------------------------------------------------------------------------------------
+// device tables for signals
+struct DevSig { const int *ctrl_seq_off, *ctrl_nseq; const double* ctrl_cycle; const int *seq_sig_off, *seq_nsig;
+  const double* seq_len; const int *sig_in, *sig_out; const double *sig_green, *sig_amber, *sig_delay; };
+
+// ControleurDeFeux::GetCouleurFeux (ControleurDeFeux.cpp:258-307) + PlanDeFeux::GetSequence (:1209-1228) +
+// SignalActif::GetCouleurFeux / GetRapVertOrange (:1517-1558).  0 red, 1 green, 2 amber.
+__device__ inline int couleur(const DevSig& S, int ctrl, double inst, int te, int ts, double dt, double* prop) {
+  int nsec = (int)inst;
+  int ntmp = nsec % (int)S.ctrl_cycle[ctrl];
+  double prev = 0, tcur = 0; int seq = -1;
+  for (int q = S.ctrl_seq_off[ctrl]; q < S.ctrl_seq_off[ctrl] + S.ctrl_nseq[ctrl]; q++) {
+    if (prev + S.seq_len[q] > ntmp) { tcur = ntmp - prev; seq = q; break; }
+    prev += S.seq_len[q];
+  }
+  if (seq < 0) return 1;
+  int g = -1;
+  for (int k = S.seq_sig_off[seq]; k < S.seq_sig_off[seq] + S.seq_nsig[seq]; k++) if (S.sig_in[k] == te && S.sig_out[k] == ts) { g = k; break; }
+  if (g < 0) return 0;
+  double delay = S.sig_delay[g], green = S.sig_green[g], amber = S.sig_amber[g];
+  int col;
+  if (tcur < delay) col = 0; else if (tcur < delay + green) col = 1;
+  else if (delay + green <= tcur && tcur < delay + green + amber) col = 2; else col = 0;
+  if (prop) {
+    if (col != 0) *prop = fmin(1.0, (tcur - delay) / dt);
+    else if (tcur < delay) *prop = 1 - fmin(1.0, tcur / dt);
+    else *prop = 1 - fmin(1.0, (tcur - (delay + green + amber) / dt));
+  }
+  return col;
+}
+// ControleurDeFeux::GetStatutCouleurFeux (ControleurDeFeux.cpp:96-148), once per stop line and step
+__global__ void k_signals(DevSig S, const int* sl_i, int n_sl, double inst, int* col_out, double* prop_out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sl) return;
+  int ctrl = sl_i[6 * s], te = sl_i[6 * s + 1], ts = sl_i[6 * s + 3];
+  double dt = cP.dt, p = 0;
+  int col = couleur(S, ctrl, inst, te, ts, dt, &p);
+  int pcol = (inst - dt > 0) ? couleur(S, ctrl, inst - dt, te, ts, dt, nullptr) : 1;
+  int res;
+  if (col == 0 && pcol == 0) { p = 0; res = 0; }
+  else if ((col == 1 || col == 2) && (pcol == 1 || pcol == 2)) { p = 1; res = col; }
+  else if (col == 1 && pcol == 0) res = 1;
+  else if (col == 0 && (pcol == 1 || pcol == 2)) { p = 1; res = 0; }
+  else res = 0;
+  col_out[s] = res; prop_out[s] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prepare(DevVeh V, int n, int* lane_count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = V.status[i];
+  V.computed[i] = 0;
+  if (st == ST_ALIVE || st == ST_NEW) atomicAdd(&lane_count[V.lane[i]], 1);
+}
+
+// exclusive scan of int32 (three launches: block scan, scan of block sums, add)
+constexpr int kScanB = 1024;
+__global__ void k_scan_block(const int* in, int* out, int* bsum, int n) {
+  __shared__ int sh[kScanB];
+  int i = blockIdx.x * kScanB + threadIdx.x;
+  int v = i < n ? in[i] : 0;
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 1; off < kScanB; off <<= 1) {
+    int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (i < n) out[i] = sh[threadIdx.x] - v;
+  if (threadIdx.x == kScanB - 1) bsum[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void k_scan_sums(int* bsum, int nb) {      // single block, serial over chunks of 1024
+  __shared__ int sh[kScanB];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += kScanB) {
+    int i = base + threadIdx.x;
+    int v = i < nb ? bsum[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < kScanB; off <<= 1) {
+      int t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) bsum[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[kScanB - 1];
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(int* out, const int* bsum, int n) {
+  int i = blockIdx.x * kScanB + threadIdx.x;
+  if (i < n) out[i] += bsum[blockIdx.x];
+}
+
+__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* order) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = V.status[i];
+  if (st != ST_ALIVE && st != ST_NEW) return;
+  int ln = V.lane[i];
+  int slot = lane_start[ln] + atomicAdd(&lane_fill[ln], 1);
+  order[slot] = i;
+}
+
+// in-lane order by (start-of-step position, id) + own-lane leader links + lane tail.
+// Replaces the per-query linear scans of Reseau::GetPrevVehicule (reseau.cpp:3650-3718) and
+// GetNearAvalVehicule (:3583-3640) over the id-ordered lane sets.
+__global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const int* lane_start, int* order,
+                             int* lane_tail, int* lane_done, long long* counters) {
+  int ln = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ln >= n_lanes) return;
+  int n = lane_count[ln];
+  lane_done[ln] = n == 0;
+  if (!n) { lane_tail[ln] = -1; return; }
+  int s = lane_start[ln];
+  for (int a = 1; a < n; a++) {
+    int x = order[s + a]; double px = snap_pos(V.pos[x]); int idx = V.id[x];
+    int j = a - 1;
+    while (j >= 0) {
+      int y = order[s + j]; double py = snap_pos(V.pos[y]);
+      if (py > px || (py == px && V.id[y] > idx)) { order[s + j + 1] = y; j--; } else break;
+    }
+    order[s + j + 1] = x;
+  }
+  int tail = -1; int ties = 0;
+  for (int a = 0; a < n; a++) {
+    int x = order[s + a]; double px = snap_pos(V.pos[x]);
+    if (tail < 0 && px >= 0) { tail = x; if (a + 1 < n && snap_pos(V.pos[order[s + a + 1]]) == px) ties++; }
+    double own = px <= SYM_UNDEF ? 0.0 : px;
+    bool eq_ok = V.status[x] == ST_NEW;           // GetPos(0) == UNDEF only before the first computation (reseau.cpp:3695)
+    int ld = -1;
+    for (int b = a + 1; b < n; b++) {
+      int y = order[s + b]; double pb = snap_pos(V.pos[y]);
+      if (pb > own || (eq_ok && pb == own)) { ld = y; if (b + 1 < n && snap_pos(V.pos[order[s + b + 1]]) == pb) ties++; break; }
+    }
+    V.ahead[x] = ld;
+  }
+  lane_tail[ln] = tail;
+  if (ties) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_TIES], (unsigned long long)ties);
+}
+
+__global__ void k_context(DevNet N, DevVeh V, int n, const int* lane_tail, unsigned* draws, int* overflow) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = V.status[i];
+  if (st != ST_ALIVE && st != ST_NEW) return;
+  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow);
+  if (d) atomicAdd(draws, (unsigned)d);
+}
+
+// One wavefront pass: every lane walks its vehicles front -> back; a lane head whose leader sits on another
+// lane waits for a later pass until that leader was computed in an EARLIER pass (stamp < pass).
+// stat[0] = lanes still pending after the pass, stat[1] = vehicles computed in the pass.
+__global__ void k_follow_pass(DevNet N, DevVeh V, DevLaneDyn LD, int n_lanes, const int* order, int* lane_done, int pass,
+                              double inst, int* stat) {
+  int ln = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ln >= n_lanes) return;
+  if (lane_done[ln]) return;
+  int n = LD.count[ln], s = LD.start[ln];
+  int done = 0, prog = 0;
+  bool pending = false;
+  for (int a = n - 1; a >= 0; a--) {
+    int x = order[s + a];
+    if (V.computed[x]) { done++; continue; }
+    int L = V.ctx_leader[x];
+    if (L >= 0) {
+      int cl = V.computed[L];
+      bool same_thread = (V.lane[L] == ln) && cl != 0;      // own-lane leader: computed by this thread just before
+      if (!(same_thread || (cl != 0 && cl < pass))) { pending = true; break; }
+    }
+    follow_one(cP, N, V, LD, x, true, inst);
+    V.computed[x] = pass;
+    done++; prog++;
+  }
+  if (!pending && done == n) lane_done[ln] = 1; else atomicAdd(&stat[0], 1);
+  if (prog) atomicAdd(&stat[1], prog);
+}
+
+// first not yet computed vehicle in list (slot) order
+__global__ void k_first_pending(DevVeh V, int n, int* first) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = V.status[i];
+  if ((st == ST_ALIVE || st == ST_NEW) && !V.computed[i]) atomicMin(first, i);
+}
+// Loop breaking exactly as the recursion of Vehicule::CalculTraficEx does it (vehicule.cpp:1198-1217, :1304-1309):
+// follow the leader chain from the first pending vehicle of m_LstVehicles; when the chain re-enters itself the
+// re-entered vehicle stays uncomputed and its follower uses the estimated leader speed
+// (NewellCarFollowing.cpp:217-230); then the chain unwinds leader first.
+__global__ void k_break_loop(DevNet N, DevVeh V, DevLaneDyn LD, const int* first, int* stack, int* visit, int stamp, int pass,
+                             double inst, long long* counters) {
+  if (blockIdx.x || threadIdx.x) return;
+  int x = *first;
+  if (x >= 0x7f7f7f7f) return;
+  int depth = 0; bool loop = false;
+  for (;;) {
+    stack[depth++] = x; visit[x] = stamp;
+    int L = V.ctx_leader[x];
+    if (L < 0 || V.computed[L]) break;
+    if (visit[L] == stamp) { loop = true; break; }
+    x = L;
+  }
+  if (loop && cP.cls[V.cls[stack[depth - 1]]].law == 0) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_LOOPS], 1ULL);
+  for (int d = depth - 1; d >= 0; d--) {
+    int y = stack[d];
+    follow_one(cP, N, V, LD, y, !(loop && d == depth - 1), inst);
+    V.computed[y] = pass;
+  }
+}
+
+// Origins, after the main update: ready vehicle inserted? then try the first waiting vehicle of the lane
+// (SymuViaTripNode::InsertionVehEnAttente, usage/SymuViaTripNode.cpp:1725-1812).  One thread per origin lane.
+struct EntryDesc { int lane, pret_slot, pool_slot, dst_slot; };
+__device__ inline void copy_row(const DevVeh& V, int src, int dst) {
+  V.id[dst] = V.id[src]; V.cls[dst] = V.cls[src]; V.route[dst] = V.route[src]; V.route_pos[dst] = V.route_pos[src];
+  V.lane[dst] = V.lane[src]; V.lane_n[dst] = V.lane_n[src]; V.prev_leader[dst] = V.prev_leader[src]; V.flags[dst] = V.flags[src];
+  V.oflags[dst] = V.oflags[src];
+  for (int k = 0; k < kMemo; k++) V.memo[dst * kMemo + k] = V.memo[src * kMemo + k];
+  V.pos[dst] = V.pos[src]; V.vit[dst] = V.vit[src]; V.acc[dst] = V.acc[src];
+  V.pos_n[dst] = V.pos_n[src]; V.vit_n[dst] = V.vit_n[src]; V.acc_n[dst] = V.acc_n[src];
+  V.dn[dst] = V.dn[src]; V.cpos[dst] = V.cpos[src]; V.tcre[dst] = V.tcre[src]; V.dstp[dst] = V.dstp[src];
+  V.hent[dst] = V.hent[src]; V.tsort[dst] = V.tsort[src];
+  V.ctx_leader[dst] = V.ctx_leader[src];
+}
+__global__ void k_entries(DevNet N, DevVeh V, DevLaneDyn LD, const EntryDesc* desc, int n_desc, int* result, double inst,
+                          unsigned* draws, int* overflow) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_desc) return;
+  EntryDesc d = desc[e];
+  int res = 0;                                   // bit0: ready vehicle inserted, bit1: waiting vehicle inserted
+  bool pret_ok = true;
+  if (d.pret_slot >= 0) { pret_ok = V.pos_n[d.pret_slot] > SYM_UNDEF; if (pret_ok) res |= 1; }
+  if (pret_ok && d.pool_slot >= 0) {
+    int w = d.pool_slot;
+    int own_leader = d.pret_slot >= 0 ? d.pret_slot : LD.tail[d.lane];
+    int dr = context_one(cP, N, V, LD.tail, w, own_leader, overflow);
+    if (dr) atomicAdd(draws, (unsigned)dr);
+    follow_one(cP, N, V, LD, w, true, inst);
+    if (V.pos_n[w] > SYM_UNDEF) {
+      copy_row(V, w, d.dst_slot);
+      V.status[d.dst_slot] = ST_NEW; V.status[w] = ST_DEAD; V.computed[d.dst_slot] = 1;
+      res |= 2;
+    } else {                                      // :1776-1783 the vehicle stays at the head of the queue
+      V.pos_n[w] = SYM_UNDEF; V.vit_n[w] = cP.cls[V.cls[w]].vx; V.lane_n[w] = d.lane; V.tcre[w] = 0.0;
+    }
+  }
+  result[e] = res;
+}
+
+// Vehicule::FinCalculTrafic (vehicule.cpp:4254-4583) + Reseau::SupprimeVehicules (reseau.cpp:3984-4216)
+struct ExitRow { int slot, id; double inst; };
+__global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* entre, int* sorti, ExitRow* exited, int* n_exited,
+                        int* exit_winner, int* n_alive, int* err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int st = V.status[i];
+  if (st != ST_ALIVE && st != ST_NEW) return;
+  if (!V.computed[i]) { atomicAdd(err, 1); return; }
+  int of = V.oflags[i];
+  int lane1 = V.lane[i], lane0 = V.lane_n[i];
+  int link1 = (of & O_LINK1NULL) ? -1 : N.lane_link[lane1];
+  int link0 = N.lane_link[lane0];
+  if (link1 < 0) V.dstp[i] = V.pos_n[i]; else V.dstp[i] += V.vit_n[i] * dt;              // :4328-4333
+  int c = V.cls[i];
+  if (link1 != link0) {                                                                    // :4337-4442
+    if (link1 >= 0 && N.link_brick[link1] < 0) atomicAdd(&sorti[link1 * ncls + c], 1);
+    if (N.link_brick[link0] < 0) atomicAdd(&entre[link0 * ncls + c], 1);
+    if (N.link_brick[link0] < 0) { int k = route_index(N, V.route[i], V.route_pos[i], link0); if (k >= 0) V.route_pos[i] = k; }
+  }
+  if (of & O_ENDLEG) {                                                                     // TripNode::VehiculeEnter TripNode.cpp:167-177
+    int k = atomicAdd(n_exited, 1);
+    exited[k].slot = i; exited[k].id = V.id[i]; exited[k].inst = V.tsort[i];
+    atomicMax(&exit_winner[lane0], i);
+    V.status[i] = ST_DEAD;
+  } else {
+    V.status[i] = ST_ALIVE;
+    atomicAdd(n_alive, 1);
+  }
+}
+// Sortie::VehiculeEnter + GetNextEnterInstant (sortie.cpp:60-130): the last vehicle of the list that left through
+// the lane sets the earliest exit instant of the next one.
+__global__ void k_exit_lanes(DevVeh V, const int* exit_lanes, const double* exit_cap, const int* exit_nl, int n_exit_lanes,
+                             int* exit_winner, double* next_sortie, double inst, double dt, double duree) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_exit_lanes) return;
+  int ln = exit_lanes[e];
+  int w = exit_winner[ln];
+  if (w < 0) return;
+  exit_winner[ln] = -1;
+  double cap = exit_cap[e];
+  double r;
+  if (cap < 0 || cap >= 9999) r = inst;
+  else {
+    double cum = 0, cump = 0, ti = V.tsort[w];
+    while (cum < 1 && ti <= duree) { cump = cum; cum += cap * dt / exit_nl[e]; ti += dt; }
+    r = cum < 1 ? -1.0 : (ti - dt) + (1 - cump) / (cum - cump) * dt;
+  }
+  next_sortie[ln] = r;
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+namespace {
+
+// RandManager (RandManager.cpp:5-30): boost::mt19937 + uniform_int<>(0, 0x7FFE)
+struct HostRng {
+  uint32_t mt[624]; int idx = 624; unsigned count = 0;
+  void seed(uint32_t s) { mt[0] = s; for (int i = 1; i < 624; i++) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i; idx = 624; count = 0; }
+  uint32_t raw() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; i++) { uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+      idx = 0; }
+    uint32_t y = mt[idx++]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18; return y;
+  }
+  int next() { count++; const uint32_t bucket = 0xFFFFFFFFu / 32767u; for (;;) { uint32_t r = raw() / bucket; if (r <= 32766u) return (int)r; } }
+  void skip(unsigned n) { for (unsigned i = 0; i < n; i++) next(); }
+};
+
+struct HostVeh { int id, cls, route, lane; double tcre, hent; };   // a generated vehicle not yet uploaded
+struct EntryLane { int lane; int pret_slot = -1; int pool_slot = -1; std::deque<HostVeh> queue; int pool_base; };
+struct HostEntry { int node, link; std::vector<std::pair<double, double>> demand; std::vector<int> dest_exit; std::vector<double> dest_coeff;
+  std::vector<std::vector<std::pair<int, double>>> dest_routes; std::vector<double> lane_coefs, type_coefs; bool exponential = false;
+  double crit = 0; std::vector<EntryLane> lanes; };
+
+template <class T> struct DBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) { n = count; if (!count) { p = nullptr; return cudaSuccess; } cudaError_t e = cudaMalloc(&p, count * sizeof(T)); if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T)); return e; }
+  cudaError_t upload(const std::vector<T>& h) { cudaError_t e = alloc(h.size()); if (e != cudaSuccess || h.empty()) return e; return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice); }
+  void free() { if (p) cudaFree(p); p = nullptr; }
+};
+
+}  // namespace
+
+struct symgpu_ctx {
+  FlatNet net; DevParams P; int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double t = 0; int n_alive = 0, n_slots = 0, cap = 0, pool_base = 0, n_pool = 0; int stamp = 0;
+  double last_ms = 0; long long launches = 0, passes = 0, created = 0;
+  HostRng rng; unsigned dev_draws_seen = 0;
+  // static tables
+  DBuf<int> lane_link, lane_num, lane_prev, lane_flags, succ_off, succ_key, succ_next, sl_off, sl_i, link_first, link_nl, link_up,
+      link_type, link_brick, route_off, route_links, ctrl_seq_off, ctrl_nseq, seq_sig_off, seq_nsig, sig_in, sig_out, exit_lanes, exit_nl;
+  DBuf<double> lane_len, sl_pos, link_len, link_vreg, ctrl_cycle, seq_len, sig_green, sig_amber, sig_delay, exit_cap;
+  // per step
+  DBuf<int> sl_col; DBuf<double> sl_prop;
+  DBuf<int> lane_count, lane_start, lane_fill, lane_tail, lane_done, exit_winner, bsum, order, entre, sorti, stat, visit, stack;
+  DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
+  // vehicles
+  DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
+      v_ctx_lane, v_ctx_leader, v_ctx_flags;
+  DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
+  DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
+  std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
+  int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
+};
+
+static void fill_dev_structs(symgpu_ctx* c) {
+  DevNet& n = c->dn;
+  n.lane_link = c->lane_link.p; n.lane_num = c->lane_num.p; n.lane_prev = c->lane_prev.p; n.lane_flags = c->lane_flags.p; n.lane_len = c->lane_len.p;
+  n.succ_off = c->succ_off.p; n.succ_key = c->succ_key.p; n.succ_next = c->succ_next.p;
+  n.sl_off = c->sl_off.p; n.sl_i = c->sl_i.p; n.sl_pos = c->sl_pos.p;
+  n.link_first = c->link_first.p; n.link_nl = c->link_nl.p; n.link_up = c->link_up.p; n.link_type = c->link_type.p; n.link_brick = c->link_brick.p;
+  n.link_len = c->link_len.p; n.link_vreg = c->link_vreg.p; n.route_off = c->route_off.p; n.route_links = c->route_links.p;
+  n.sl_col = c->sl_col.p; n.sl_prop = c->sl_prop.p; n.n_lanes = c->net.n_lanes(); n.n_links = c->net.n_links(); n.n_sl = c->net.n_sl();
+  DevVeh& v = c->dv;
+  v.status = c->v_status.p; v.id = c->v_id.p; v.cls = c->v_cls.p; v.route = c->v_route.p; v.route_pos = c->v_rpos.p; v.lane = c->v_lane.p;
+  v.lane_n = c->v_lane_n.p; v.prev_leader = c->v_pl.p; v.flags = c->v_flags.p; v.oflags = c->v_oflags.p; v.memo = c->v_memo.p;
+  v.pos = c->v_pos.p; v.vit = c->v_vit.p; v.acc = c->v_acc.p; v.pos_n = c->v_pos_n.p; v.vit_n = c->v_vit_n.p; v.acc_n = c->v_acc_n.p;
+  v.dn = c->v_dn.p; v.cpos = c->v_cpos.p; v.tcre = c->v_tcre.p; v.dstp = c->v_dstp.p; v.hent = c->v_hent.p; v.tsort = c->v_tsort.p;
+  v.ahead = c->v_ahead.p; v.computed = c->v_computed.p; v.ctx_nl = c->v_ctx_nl.p; v.ctx_lane = c->v_ctx_lane.p; v.ctx_leader = c->v_ctx_leader.p;
+  v.ctx_flags = c->v_ctx_flags.p; v.ctx_gap = c->v_ctx_gap.p; v.ctx_dn0 = c->v_ctx_dn0.p; v.ctx_dfree = c->v_ctx_dfree.p;
+  DevLaneDyn& l = c->dl;
+  l.count = c->lane_count.p; l.start = c->lane_start.p; l.fill = c->lane_fill.p; l.tail = c->lane_tail.p; l.head_done = c->lane_done.p;
+  l.next_sortie = c->next_sortie.p; l.exit_winner = c->exit_winner.p;
+  DevSig& s = c->ds;
+  s.ctrl_seq_off = c->ctrl_seq_off.p; s.ctrl_nseq = c->ctrl_nseq.p; s.ctrl_cycle = c->ctrl_cycle.p; s.seq_sig_off = c->seq_sig_off.p; s.seq_nsig = c->seq_nsig.p;
+  s.seq_len = c->seq_len.p; s.sig_in = c->sig_in.p; s.sig_out = c->sig_out.p; s.sig_green = c->sig_green.p; s.sig_amber = c->sig_amber.p; s.sig_delay = c->sig_delay.p;
+}
+
+template <class T> static std::vector<T> col(const std::vector<T>& v, int stride, int k) {
+  std::vector<T> o(v.size() / stride);
+  for (size_t i = 0; i < o.size(); i++) o[i] = v[i * stride + k];
+  return o;
+}
+
+struct HostRow { int status, id, cls, route, rpos, lane; double pos, vit, acc, tcre, hent; };
+static int upload_rows(symgpu_ctx* c, int slot0, const std::vector<HostRow>& rows) {
+  size_t n = rows.size();
+  if (!n) return SYMGPU_OK;
+  std::vector<int> st(n), id(n), cl(n), ro(n), rp(n), la(n), pl(n, -1), fl(n, 0), memo(n * kMemo, -1);
+  std::vector<double> po(n), vi(n), ac(n), dnv(n, 1.0), z(n, 0.0), tc(n), he(n);
+  for (size_t i = 0; i < n; i++) { const HostRow& r = rows[i]; st[i] = r.status; id[i] = r.id; cl[i] = r.cls; ro[i] = r.route; rp[i] = r.rpos; la[i] = r.lane;
+    po[i] = r.pos; vi[i] = r.vit; ac[i] = r.acc; tc[i] = r.tcre; he[i] = r.hent; }
+  auto I = [&](DBuf<int>& b, const std::vector<int>& h, int w = 1) { return cudaMemcpyAsync(b.p + (size_t)slot0 * w, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream); };
+  auto D = [&](DBuf<double>& b, const std::vector<double>& h) { return cudaMemcpyAsync(b.p + slot0, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream); };
+  CK(I(c->v_status, st)); CK(I(c->v_id, id)); CK(I(c->v_cls, cl)); CK(I(c->v_route, ro)); CK(I(c->v_rpos, rp)); CK(I(c->v_lane, la)); CK(I(c->v_lane_n, la));
+  CK(I(c->v_pl, pl)); CK(I(c->v_flags, fl)); CK(I(c->v_oflags, fl)); CK(I(c->v_memo, memo, kMemo));
+  CK(D(c->v_pos, po)); CK(D(c->v_vit, vi)); CK(D(c->v_acc, ac)); CK(D(c->v_pos_n, po)); CK(D(c->v_vit_n, vi)); CK(D(c->v_acc_n, ac));
+  CK(D(c->v_dn, dnv)); CK(D(c->v_cpos, z)); CK(D(c->v_tcre, tc)); CK(D(c->v_dstp, z)); CK(D(c->v_hent, he)); CK(D(c->v_tsort, z));
+  CK(cudaStreamSynchronize(c->stream));     // host vectors go out of scope
+  return SYMGPU_OK;
+}
+
+extern "C" const char* symgpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
+  if (!out || !path) return SYMGPU_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { g_err = "no usable CUDA device (this library has no CPU path)"; return SYMGPU_E_NODEVICE; }
+  CK(cudaSetDevice(device));
+  auto c = new symgpu_ctx(); c->device = device;
+  if (!c->net.load(path)) { g_err = c->net.error; delete c; return SYMGPU_E_LOAD; }
+  FlatNet& f = c->net;
+  const int T = f.n_cls(), L = f.n_lanes(), K = f.n_links();
+  if (T > kMaxCls) { g_err = "too many vehicle classes"; delete c; return SYMGPU_E_UNSUPPORTED; }
+  // every (lane, next link) movement must have a single target lane of rate >= 1 (see micro.cuh next_voie)
+  for (int l = 0; l < L; l++) for (int m = f.succ_off[l]; m < f.succ_off[l + 1]; m++) {
+    if (f.succ_f[m] < 1.0) { g_err = "movement with taux_utilisation < 1: multi-lane next-lane draws are not supported on the device yet"; delete c; return SYMGPU_E_UNSUPPORTED; }
+    for (int m2 = m + 1; m2 < f.succ_off[l + 1]; m2++) if (f.succ_i[3 * m2] == f.succ_i[3 * m]) { g_err = "movement with several target lanes is not supported on the device yet"; delete c; return SYMGPU_E_UNSUPPORTED; }
+  }
+  if (f.params[SYMFLAT_P_CHGTVOIE] != 0) { g_err = "chgtvoie=true (lane changing, row A9) is not implemented on the device yet"; delete c; return SYMGPU_E_UNSUPPORTED; }
+  DevParams& P = c->P; memset(&P, 0, sizeof(P));
+  P.dt = f.params[SYMFLAT_P_DT]; P.relax = f.params[SYMFLAT_P_RELAX]; P.duree = f.params[SYMFLAT_P_NSTEPS] * P.dt; P.bevel = 0;
+  P.accbornee = f.params[SYMFLAT_P_ACCBORNEE] != 0; P.ncls = T; P.min_kv = 999;
+  for (int i = 0; i < T; i++) { const double* r = &f.cls[i * SYMFLAT_CLS_STRIDE]; DevCls& k = P.cls[i];
+    k.w = r[0]; k.kx = r[1]; k.vx = r[2]; k.esp = r[3]; k.decel = r[4]; k.tau_lc = r[5]; k.pi_rab = r[6]; k.law = (int)r[7]; k.nplage = std::min(4, (int)r[8]);
+    for (int j = 0; j < k.nplage; j++) { k.ax[j] = r[9 + 2 * j]; k.vs[j] = r[10 + 2 * j]; }
+    double kv = -k.kx * k.w / (k.vx - k.w); if (kv < P.min_kv) P.min_kv = kv; }     // Reseau::GetMinKv reseau.cpp:9719-9737
+  CK(cudaMemcpyToSymbol(cP, &P, sizeof(P)));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+  CK(cudaMallocHost(&c->h_stat, 16 * sizeof(int)));
+  // static tables
+  CK(c->lane_link.upload(col(f.lane_i, 4, 0))); CK(c->lane_num.upload(col(f.lane_i, 4, 1))); CK(c->lane_prev.upload(col(f.lane_i, 4, 2)));
+  CK(c->lane_flags.upload(col(f.lane_i, 4, 3))); CK(c->lane_len.upload(f.lane_f));
+  CK(c->succ_off.upload(f.succ_off)); CK(c->succ_key.upload(col(f.succ_i, 3, 0))); CK(c->succ_next.upload(col(f.succ_i, 3, 1)));
+  CK(c->sl_off.upload(f.sl_off)); CK(c->sl_i.upload(f.sl_i)); CK(c->sl_pos.upload(f.sl_f));
+  CK(c->link_first.upload(col(f.link_i, 8, 0))); CK(c->link_nl.upload(col(f.link_i, 8, 1))); CK(c->link_up.upload(col(f.link_i, 8, 2)));
+  CK(c->link_type.upload(col(f.link_i, 8, 4))); CK(c->link_brick.upload(col(f.link_i, 8, 5)));
+  CK(c->link_len.upload(col(f.link_f, 2, 0))); CK(c->link_vreg.upload(col(f.link_f, 2, 1)));
+  CK(c->route_off.upload(f.route_off)); CK(c->route_links.upload(f.route_links));
+  CK(c->ctrl_seq_off.upload(col(f.ctrl_i, 2, 0))); CK(c->ctrl_nseq.upload(col(f.ctrl_i, 2, 1))); CK(c->ctrl_cycle.upload(f.ctrl_f));
+  CK(c->seq_sig_off.upload(col(f.seq_i, 2, 0))); CK(c->seq_nsig.upload(col(f.seq_i, 2, 1))); CK(c->seq_len.upload(f.seq_f));
+  CK(c->sig_in.upload(col(f.sig_i, 2, 0))); CK(c->sig_out.upload(col(f.sig_i, 2, 1)));
+  CK(c->sig_green.upload(col(f.sig_f, 3, 0))); CK(c->sig_amber.upload(col(f.sig_f, 3, 1))); CK(c->sig_delay.upload(col(f.sig_f, 3, 2)));
+  CK(c->sl_col.alloc(f.n_sl())); CK(c->sl_prop.alloc(f.n_sl()));
+  // exits
+  { std::vector<int> el, enl; std::vector<double> ec;
+    for (int x = 0; x < f.n_exits(); x++) { int link = f.exit_i[2 * x + 1]; for (int k = 0; k < f.link_i[8 * link + 1]; k++) { el.push_back(f.link_i[8 * link] + k); enl.push_back(f.link_i[8 * link + 1]); ec.push_back(f.exit_f[x]); } }
+    CK(c->exit_lanes.upload(el)); CK(c->exit_nl.upload(enl)); CK(c->exit_cap.upload(ec)); }
+  // origins
+  int n_entry_lanes = 0;
+  for (int e = 0; e < f.n_entries(); e++) { const int* r = &f.entry_i[8 * e]; HostEntry h; h.node = r[0]; h.link = r[1];
+    for (int d = r[2]; d < r[2] + r[3]; d++) h.demand.push_back({f.dem_f[2 * d], f.dem_f[2 * d + 1]});
+    for (int d = r[4]; d < r[4] + r[5]; d++) { h.dest_exit.push_back(f.dest_i[3 * d]); h.dest_coeff.push_back(f.dest_f[d]); std::vector<std::pair<int, double>> rr;
+      for (int q = f.dest_i[3 * d + 1]; q < f.dest_i[3 * d + 1] + f.dest_i[3 * d + 2]; q++) rr.push_back({f.droute_i[q], f.droute_f[q]}); h.dest_routes.push_back(rr); }
+    int nl = f.link_i[8 * h.link + 1]; h.exponential = (r[7] >> 30) & 1; int tco = r[7] & 0x3fffffff;
+    for (int k = 0; k < nl; k++) h.lane_coefs.push_back(f.lanecoef_f[r[6] + k]);
+    for (int k = 0; k < T; k++) h.type_coefs.push_back(f.typecoef_f[tco + k]);
+    for (int k = 0; k < nl; k++) { EntryLane el; el.lane = f.link_i[8 * h.link] + k; h.lanes.push_back(el); n_entry_lanes++; }
+    c->entries.push_back(std::move(h)); }
+  // capacity: initial vehicles + demand budget
+  double budget = 0;
+  for (auto& e : c->entries) { double tt = 0; for (auto& d : e.demand) { double dur = std::min(d.first, std::max(0.0, P.duree - tt)); budget += dur * d.second; tt += d.first; } }
+  c->n_pool = n_entry_lanes;
+  size_t cap = (size_t)f.n_init() + (size_t)(budget * 1.25) + 2 * (size_t)(P.duree / P.dt) * (size_t)n_entry_lanes / 4 + 4096 + n_entry_lanes;
+  if (const char* env = getenv("SYMGPU_CAPACITY")) cap = std::max(cap, (size_t)atoll(env));
+  c->cap = (int)cap; c->pool_base = c->cap - c->n_pool;
+  { int q = 0; for (auto& e : c->entries) for (auto& l : e.lanes) l.pool_base = c->pool_base + q++; }
+  // dynamic lane / link state
+  CK(c->lane_count.alloc(L)); CK(c->lane_start.alloc(L)); CK(c->lane_fill.alloc(L)); CK(c->lane_tail.alloc(L)); CK(c->lane_done.alloc(L));
+  CK(c->exit_winner.alloc(L)); CK(cudaMemset(c->exit_winner.p, 0xff, L * sizeof(int))); CK(c->next_sortie.alloc(L));
+  CK(c->bsum.alloc((L + kScanB - 1) / kScanB + 1)); CK(c->order.alloc(cap)); CK(c->entre.alloc((size_t)K * T)); CK(c->sorti.alloc((size_t)K * T));
+  CK(c->stat.alloc(16)); CK(c->visit.alloc(cap)); CK(c->stack.alloc(cap)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
+  CK(c->exited.alloc(cap)); CK(c->edesc.alloc(std::max(1, n_entry_lanes))); CK(c->eresult.alloc(std::max(1, n_entry_lanes)));
+  // vehicles
+  for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
+                       &c->v_computed, &c->v_ctx_nl, &c->v_ctx_leader, &c->v_ctx_flags}) CK(b->alloc(cap));
+  CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
+  for (DBuf<double>* b : {&c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre, &c->v_dstp, &c->v_hent,
+                          &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) CK(b->alloc(cap));
+  fill_dev_structs(c);
+  c->rng.seed((unsigned)f.params[SYMFLAT_P_SEED]);                    // reseau.cpp:983-995
+  // initial vehicles (reseau.cpp:1293-1340): already on the network, state at index 0
+  { std::vector<HostRow> rows(f.n_init());
+    for (int v = 0; v < f.n_init(); v++) { HostRow& r = rows[v]; r.status = ST_ALIVE; r.id = c->last_id++; r.cls = f.iv_i[4 * v]; r.lane = f.iv_i[4 * v + 1];
+      r.route = f.iv_i[4 * v + 2]; r.rpos = f.iv_i[4 * v + 3]; r.pos = f.iv_f[3 * v]; r.vit = f.iv_f[3 * v + 1]; r.acc = f.iv_f[3 * v + 2]; r.tcre = 0; r.hent = 0; }
+    int rc = upload_rows(c, 0, rows); if (rc != SYMGPU_OK) { delete c; return rc; }
+    c->n_slots = c->n_alive = f.n_init(); }
+  *out = c;
+  return SYMGPU_OK;
+}
+
+extern "C" void symgpu_destroy(symgpu_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (DBuf<int>* b : {&c->lane_link, &c->lane_num, &c->lane_prev, &c->lane_flags, &c->succ_off, &c->succ_key, &c->succ_next, &c->sl_off, &c->sl_i, &c->link_first,
+                       &c->link_nl, &c->link_up, &c->link_type, &c->link_brick, &c->route_off, &c->route_links, &c->ctrl_seq_off, &c->ctrl_nseq, &c->seq_sig_off,
+                       &c->seq_nsig, &c->sig_in, &c->sig_out, &c->exit_lanes, &c->exit_nl, &c->sl_col, &c->lane_count, &c->lane_start, &c->lane_fill, &c->lane_tail,
+                       &c->lane_done, &c->exit_winner, &c->bsum, &c->order, &c->entre, &c->sorti, &c->stat, &c->visit, &c->stack, &c->eresult, &c->v_status, &c->v_id,
+                       &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_memo, &c->v_ahead, &c->v_computed,
+                       &c->v_ctx_nl, &c->v_ctx_lane, &c->v_ctx_leader, &c->v_ctx_flags}) b->free();
+  for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
+                          &c->sl_prop, &c->next_sortie, &c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre,
+                          &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
+  c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free();
+  if (c->h_stat) cudaFreeHost(c->h_stat);
+  if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ---- origins (host): usage/SymuViaTripNode.cpp:847-955, :212-325, :331-840 ---------------------------
+static double demande_value(const HostEntry& e, double inst) {
+  double acc = 0; for (auto& d : e.demand) { acc += d.first; if (inst <= acc) return d.second; }
+  return e.demand.empty() ? 0.0 : e.demand.back().second;
+}
+static void update_crit(symgpu_ctx* c, HostEntry& e, double inst, bool due_to_creation, double max_debit) {
+  double dt = c->P.dt;
+  if (!e.exponential) { e.crit += demande_value(e, inst) * dt; return; }                           // :905-911
+  if (fabs(demande_value(e, inst) - demande_value(e, inst - dt)) > DBL_EPSILON || fabs(inst - dt) < DBL_EPSILON || due_to_creation) {
+    double niveau = demande_value(e, inst); if (niveau > max_debit) niveau = max_debit;
+    double r = 0; while (r <= 0) r = (double)c->rng.next() / 32767.0;
+    e.crit = niveau > 0 ? inst - log(r) * (1 - niveau / max_debit) / niveau + 1 / max_debit : DBL_MAX;   // :935-940
+  }
+}
+static double max_debit_max(const symgpu_ctx* c) { double m = 0; for (int i = 0; i < c->P.ncls; i++) { const DevCls& k = c->P.cls[i]; double q = k.w * k.kx / ((k.w / k.vx) - 1); if (q > m) m = q; } return m; }
+
+// returns rows to append to m_LstVehicles this step (ready vehicles), fills waiting queues
+static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::vector<EntryLane*>& new_row_lane) {
+  const double dt = c->P.dt, inst = c->t; const FlatNet& f = c->net; const double mdm = max_debit_max(c);
+  for (auto& e : c->entries) {
+    for (;;) {                                                                                      // CreationVehicules :212-325
+      bool creation; double tcre = 0;
+      if (e.exponential) { creation = e.crit <= inst; if (creation) { tcre = e.crit - (inst - dt); if (inst - dt + tcre >= 0) update_crit(c, e, inst - dt + tcre, true, mdm); } }
+      else { creation = e.crit >= 1; if (creation) { double q = demande_value(e, inst); if (q != 0.0) { tcre = dt - (e.crit - 1) * dt / (q * dt); e.crit -= 1; } } }
+      if (!creation) break;
+      // GenerateVehicle :331-840 — draw order: lane (:1966), type (RepartitionTypeVehicule.cpp:92), [law coefficient
+      // CarFollowingFactory.cpp:99], destination (:1288), itinerary (:515), Jorge class (vehicule.cpp:749)
+      int nl = (int)e.lanes.size(); int nv = 0;
+      { double r = c->rng.next() / 32767.0, sum = 0; for (; nv < nl; nv++) { double cf = e.lane_coefs[nv]; if (cf <= 0) continue; sum += cf; if (sum >= r) break; } if (nv >= nl) nv = nl - 1; }
+      int tv = -1;
+      { double r = c->rng.next() / 32767.0, sum = 0; int lastnn = -1; for (int i = 0; i < c->P.ncls; i++) { double cf = e.type_coefs[i]; if (cf <= 0) continue; lastnn = i; sum += cf; if (r <= sum) { tv = i; break; } } if (tv < 0) tv = lastnn; }
+      if (c->P.cls[tv].law != 0) c->rng.next();
+      int id = c->last_id++;
+      int d = -1;
+      { double r = (double)c->rng.next() / 32767.0, sum = 0; for (size_t i = 0; i < e.dest_coeff.size(); i++) { if (e.dest_coeff[i] <= 0) continue; sum += e.dest_coeff[i]; if (i == e.dest_coeff.size() - 1) sum = 1; if (r <= sum) { d = (int)i; break; } } }
+      if (d < 0) continue;
+      int route = e.dest_routes[d].back().first;
+      { double r = c->rng.next() / 32767.0, sum = 0; for (auto& q : e.dest_routes[d]) { sum += q.second; if (r <= sum) { route = q.first; break; } } }
+      c->rng.next();                                                                                // TirageJorge
+      c->created++;
+      EntryLane& el = e.lanes[nv];
+      HostVeh hv{id, tv, route, el.lane, tcre, inst - dt + tcre};
+      (void)f;
+      if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);   // :794-800
+      else { HostRow r{ST_NEW, id, tv, route, 0, el.lane, SYM_UNDEF, c->P.cls[tv].vx, 0.0, tcre, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el); }
+    }
+  }
+}
+
+#define LAUNCH(c) ((c)->launches++)
+
+static int do_step(symgpu_ctx* c) {
+  const int L = c->net.n_lanes(), T = c->net.n_cls(), K = c->net.n_links();
+  (void)K;
+  cudaStream_t s = c->stream;
+  const bool has_entries = !c->entries.empty();
+  c->t += c->P.dt;                                                                                  // reseau.cpp:2105
+  // origins: criterion update (reseau.cpp:2219-2223) and creation (:2255); the device draws of the previous step
+  // come first in the global random sequence
+  std::vector<HostRow> new_rows; std::vector<EntryLane*> new_row_lane;
+  std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane;
+  if (has_entries) {
+    const double mdm = max_debit_max(c);
+    for (auto& e : c->entries) update_crit(c, e, c->t, false, mdm);
+    create_vehicles(c, new_rows, new_row_lane);
+    if (c->n_slots + (int)new_rows.size() + c->n_pool > c->pool_base) { g_err = "vehicle capacity exhausted (set SYMGPU_CAPACITY)"; return SYMGPU_E_CAPACITY; }
+    for (size_t i = 0; i < new_rows.size(); i++) new_row_lane[i]->pret_slot = c->n_slots + (int)i;
+    int rc = upload_rows(c, c->n_slots, new_rows); if (rc != SYMGPU_OK) return rc;
+    c->n_slots += (int)new_rows.size();
+    // queue heads move to their pool slot (they keep their state between attempts)
+    std::vector<HostRow> one(1);
+    for (auto& e : c->entries) for (auto& el : e.lanes) {
+      if (el.pool_slot < 0 && !el.queue.empty()) {
+        HostVeh hv = el.queue.front(); el.queue.pop_front();
+        one[0] = HostRow{ST_POOL, hv.id, hv.cls, hv.route, 0, hv.lane, SYM_UNDEF, c->P.cls[hv.cls].vx, 0.0, hv.tcre, hv.hent};
+        rc = upload_rows(c, el.pool_base, one); if (rc != SYMGPU_OK) return rc;
+        el.pool_slot = el.pool_base;
+      }
+      if (el.pret_slot >= 0 || el.pool_slot >= 0) {
+        EntryDesc d{el.lane, el.pret_slot, el.pool_slot, -1};
+        if (el.pool_slot >= 0) d.dst_slot = c->n_slots++;
+        desc.push_back(d); desc_lane.push_back(&el);
+      }
+    }
+    if (!desc.empty()) CK(cudaMemcpyAsync(c->edesc.p, desc.data(), desc.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, s));
+  }
+  const int n = c->n_slots;
+  const int B = 256;
+  auto G = [&](int cnt) { return (cnt + B - 1) / B; };
+  CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
+  CK(cudaMemsetAsync(c->stat.p, 0, 16 * sizeof(int), s));
+  if (c->net.n_sl()) { k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); LAUNCH(c); }
+  if (n > 0) {
+    k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); LAUNCH(c);
+    int nb = (L + kScanB - 1) / kScanB;
+    k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
+    if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); LAUNCH(c); }
+    k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); LAUNCH(c);
+    k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->lane_done.p, c->counters.p); LAUNCH(c);
+    k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, n, c->lane_tail.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); LAUNCH(c);
+    // wavefront passes; stat is read back every `burst` passes
+    int pass = 1; const int burst = 4; int stall = 0;
+    for (;;) {
+      for (int b = 0; b < burst; b++) {
+        CK(cudaMemsetAsync(c->stat.p, 0, 2 * sizeof(int), s));
+        k_follow_pass<<<G(L), B, 0, s>>>(c->dn, c->dv, c->dl, L, c->order.p, c->lane_done.p, pass + 1, c->t, c->stat.p); LAUNCH(c);
+        pass++; c->passes++;
+      }
+      CK(cudaMemcpyAsync(c->h_stat, c->stat.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (c->h_stat[0] == 0) break;
+      if (c->h_stat[1] == 0) {                                       // no progress in the last pass: a leader loop
+        CK(cudaMemsetAsync(&c->stat.p[8], 0x7f, sizeof(int), s));
+        k_first_pending<<<G(n), B, 0, s>>>(c->dv, n, &c->stat.p[8]); LAUNCH(c);
+        k_break_loop<<<1, 32, 0, s>>>(c->dn, c->dv, c->dl, &c->stat.p[8], c->stack.p, c->visit.p, ++c->stamp, pass + 1, c->t, c->counters.p); LAUNCH(c);
+        pass++;
+        if (++stall > n + 8) { g_err = "follow passes do not terminate"; return SYMGPU_E_CUDA; }
+      }
+    }
+    if (!desc.empty()) { k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
+                                                                    (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); LAUNCH(c); }
+    CK(cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s));
+    k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6]); LAUNCH(c);
+    if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
+                                                                              c->next_sortie.p, c->t, c->P.dt, c->P.duree); LAUNCH(c); }
+  }
+  CK(cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(c->h_stat + 7, c->draws.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  std::vector<int> eres(desc.size());
+  if (!desc.empty()) CK(cudaMemcpyAsync(eres.data(), c->eresult.p, desc.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (c->h_stat[6]) { g_err = "internal error: vehicles left uncomputed"; return SYMGPU_E_CUDA; }
+  c->n_alive = n > 0 ? c->h_stat[5] : 0;
+  int nex = n > 0 ? c->h_stat[4] : 0;
+  c->last_exited.resize(nex);
+  if (nex) { CK(cudaMemcpy(c->last_exited.data(), c->exited.p, nex * sizeof(ExitRow), cudaMemcpyDeviceToHost));
+    std::sort(c->last_exited.begin(), c->last_exited.end(), [](const ExitRow& a, const ExitRow& b) { return a.slot < b.slot; }); }
+  // global random sequence: account for the draws made on the device during this step
+  unsigned dd = (unsigned)c->h_stat[7];
+  if (has_entries) c->rng.skip(dd - c->dev_draws_seen); else c->rng.count += dd - c->dev_draws_seen;
+  c->dev_draws_seen = dd;
+  for (size_t i = 0; i < desc.size(); i++) { EntryLane* el = desc_lane[i];
+    if (eres[i] & 1) el->pret_slot = -1;
+    if (eres[i] & 2) el->pool_slot = -1; }
+  // swap start/end-of-step buffers
+  std::swap(c->v_pos.p, c->v_pos_n.p); std::swap(c->v_vit.p, c->v_vit_n.p); std::swap(c->v_acc.p, c->v_acc_n.p); std::swap(c->v_lane.p, c->v_lane_n.p);
+  fill_dev_structs(c);
+  return c->n_alive;
+}
+
+extern "C" int symgpu_step(symgpu_ctx* c) {
+  if (!c) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int r = do_step(c);
+  if (r < 0) return r;
+  CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms;
+  return r;
+}
+extern "C" int symgpu_run(symgpu_ctx* c, int n_steps) {
+  if (!c) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int r = c->n_alive;
+  for (int k = 0; k < n_steps; k++) { r = do_step(c); if (r < 0) return r; }
+  CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms;
+  return r;
+}
+
+// list-order gather on the host (m_LstVehicles order = slot order)
+static int gather(symgpu_ctx* c, std::vector<int>& slots) {
+  std::vector<int> st(c->n_slots);
+  if (c->n_slots) CK(cudaMemcpy(st.data(), c->v_status.p, c->n_slots * sizeof(int), cudaMemcpyDeviceToHost));
+  slots.clear();
+  for (int i = 0; i < c->n_slots; i++) if (st[i] == ST_ALIVE) slots.push_back(i);
+  return SYMGPU_OK;
+}
+template <class T> static int fetch(symgpu_ctx* c, const T* dev, const std::vector<int>& slots, T* out, int cap, int width = 1) {
+  if (!out) return SYMGPU_OK;
+  std::vector<T> h((size_t)c->n_slots * width);
+  if (c->n_slots) CK(cudaMemcpy(h.data(), dev, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < slots.size() && (int)k < cap; k++) out[k] = h[(size_t)slots[k] * width];
+  return SYMGPU_OK;
+}
+extern "C" int symgpu_get_state(symgpu_ctx* c, int cap, int* id, int* lane, int* route_pos, int* flags, double* pos, double* vit, double* acc,
+                                double* deltaN, int* leader_id) {
+  if (!c) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  std::vector<int> slots; int rc = gather(c, slots); if (rc) return rc;
+  if ((rc = fetch(c, c->v_id.p, slots, id, cap))) return rc;
+  if ((rc = fetch(c, c->v_lane.p, slots, lane, cap))) return rc;
+  if ((rc = fetch(c, c->v_rpos.p, slots, route_pos, cap))) return rc;
+  if ((rc = fetch(c, c->v_pos.p, slots, pos, cap))) return rc;
+  if ((rc = fetch(c, c->v_vit.p, slots, vit, cap))) return rc;
+  if ((rc = fetch(c, c->v_acc.p, slots, acc, cap))) return rc;
+  if ((rc = fetch(c, c->v_dn.p, slots, deltaN, cap))) return rc;
+  if ((rc = fetch(c, c->v_pl.p, slots, leader_id, cap))) return rc;
+  if (flags) {
+    std::vector<int> of(slots.size()), cl(slots.size());
+    if ((rc = fetch(c, c->v_oflags.p, slots, of.data(), (int)of.size()))) return rc;
+    if ((rc = fetch(c, c->v_cls.p, slots, cl.data(), (int)cl.size()))) return rc;
+    for (size_t k = 0; k < slots.size() && (int)k < cap; k++) flags[k] = (of[k] & 7) | (cl[k] << 8);
+  }
+  return (int)slots.size();
+}
+extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc) {
+  int r = symgpu_step(c);
+  if (r < 0) return r;
+  return symgpu_get_state(c, cap, id, lane, nullptr, nullptr, pos, vit, acc, nullptr, nullptr);
+}
+extern "C" int symgpu_num_vehicles(symgpu_ctx* c) { return c ? c->n_alive : SYMGPU_E_ARG; }
+extern "C" double symgpu_time(symgpu_ctx* c) { return c ? c->t : 0.0; }
+extern "C" unsigned symgpu_rng_count(symgpu_ctx* c) { return c ? c->rng.count : 0; }
+extern "C" double symgpu_last_step_ms(symgpu_ctx* c) { return c ? c->last_ms : 0.0; }
+extern "C" int symgpu_num_links(symgpu_ctx* c) { return c ? c->net.n_links() : SYMGPU_E_ARG; }
+extern "C" int symgpu_num_classes(symgpu_ctx* c) { return c ? c->net.n_cls() : SYMGPU_E_ARG; }
+extern "C" int symgpu_waiting(symgpu_ctx* c) { if (!c) return SYMGPU_E_ARG; int n = 0; for (auto& e : c->entries) for (auto& l : e.lanes) n += (int)l.queue.size() + (l.pool_slot >= 0); return n; }
+extern "C" long symgpu_counter(symgpu_ctx* c, int which) {
+  if (!c) return SYMGPU_E_ARG;
+  if (which == SYMGPU_CNT_CREATED) return (long)c->created;
+  if (which == SYMGPU_CNT_PASSES) return (long)c->passes;
+  if (which == SYMGPU_CNT_LAUNCHES) return (long)c->launches;
+  if (which == SYMGPU_CNT_SLOTS) return c->n_slots;
+  long long h[16];
+  cudaSetDevice(c->device);
+  if (cudaMemcpy(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return SYMGPU_E_CUDA;
+  if (which == SYMGPU_CNT_CTX_OVERFLOW) return (long)(h[which] & 0xffffffff);
+  return which >= 0 && which < 16 ? (long)h[which] : SYMGPU_E_ARG;
+}
+extern "C" int symgpu_get_link_counts(symgpu_ctx* c, int* entre, int* sorti) {
+  if (!c) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  size_t n = (size_t)c->net.n_links() * c->net.n_cls();
+  if (entre) CK(cudaMemcpy(entre, c->entre.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (sorti) CK(cudaMemcpy(sorti, c->sorti.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+  return (int)n;
+}
+extern "C" int symgpu_get_exited(symgpu_ctx* c, int cap, int* id, double* instant) {
+  if (!c) return SYMGPU_E_ARG;
+  int n = (int)c->last_exited.size();
+  for (int k = 0; k < n && k < cap; k++) { if (id) id[k] = c->last_exited[k].id; if (instant) instant[k] = c->last_exited[k].inst; }
+  return n;
+}

@@ -1,0 +1,88 @@
+// flatnet.h — host-side flattened network tables (SYMFLAT1, include/symflat.h).
+// Replaces the object graph Reseau::LoadReseauXML builds (symuvia/src/reseau.cpp:4931-9612) by
+// dense arrays that can be uploaded to HBM as they are.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/symflat.h"
+
+namespace symb200 {
+
+struct FlatNet {
+  std::vector<double> params, cls, link_f, lane_f, succ_f, sl_f, ctrl_f, seq_f, sig_f, dem_f, dest_f, droute_f,
+      lanecoef_f, typecoef_f, exit_f, iv_f, link_geom;
+  std::vector<int> link_i, lane_i, succ_off, succ_i, sl_off, sl_i, ctrl_i, seq_i, sig_i, node_i, route_off, route_links,
+      entry_i, dest_i, droute_i, exit_i, iv_i;
+  std::vector<std::string> link_names, node_names, cls_names;
+  std::string error;
+
+  int n_links() const { return (int)link_i.size() / 8; }
+  int n_lanes() const { return (int)lane_i.size() / 4; }
+  int n_cls() const { return (int)cls.size() / SYMFLAT_CLS_STRIDE; }
+  int n_entries() const { return (int)entry_i.size() / 8; }
+  int n_exits() const { return (int)exit_i.size() / 2; }
+  int n_init() const { return (int)iv_i.size() / 4; }
+  int n_ctrl() const { return (int)ctrl_i.size() / 2; }
+  int n_sl() const { return (int)sl_i.size() / 6; }
+
+  static void split_names(const std::vector<unsigned char>& raw, std::vector<std::string>& out) {
+    std::string cur;
+    for (unsigned char c : raw) { if (c == 0) { out.push_back(cur); cur.clear(); } else cur.push_back((char)c); }
+  }
+
+  bool load(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { error = std::string("cannot open ") + path; return false; }
+    char magic[8]; uint32_t n = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, SYMFLAT_MAGIC, 8) != 0 || fread(&n, 4, 1, f) != 1) {
+      fclose(f); error = "bad SYMFLAT1 header"; return false; }
+    std::map<std::string, std::vector<int>*> im = {
+        {"link_i", &link_i}, {"lane_i", &lane_i}, {"succ_off", &succ_off}, {"succ_i", &succ_i}, {"sl_off", &sl_off},
+        {"sl_i", &sl_i}, {"ctrl_i", &ctrl_i}, {"seq_i", &seq_i}, {"sig_i", &sig_i}, {"node_i", &node_i},
+        {"route_off", &route_off}, {"route_links", &route_links}, {"entry_i", &entry_i}, {"dest_i", &dest_i},
+        {"droute_i", &droute_i}, {"exit_i", &exit_i}, {"iv_i", &iv_i}};
+    std::map<std::string, std::vector<double>*> dm = {
+        {"params", &params}, {"cls", &cls}, {"link_f", &link_f}, {"lane_f", &lane_f}, {"succ_f", &succ_f},
+        {"sl_f", &sl_f}, {"ctrl_f", &ctrl_f}, {"seq_f", &seq_f}, {"sig_f", &sig_f}, {"dem_f", &dem_f},
+        {"dest_f", &dest_f}, {"droute_f", &droute_f}, {"lanecoef_f", &lanecoef_f}, {"typecoef_f", &typecoef_f},
+        {"exit_f", &exit_f}, {"iv_f", &iv_f}, {"link_geom", &link_geom}};
+    for (uint32_t s = 0; s < n; s++) {
+      char name[25] = {0}; uint32_t dt; uint64_t cnt;
+      if (fread(name, 1, 24, f) != 24 || fread(&dt, 4, 1, f) != 1 || fread(&cnt, 8, 1, f) != 1) { fclose(f); error = "truncated section header"; return false; }
+      size_t isz = dt == 0 ? 4 : dt == 1 ? 8 : 1, bytes = cnt * isz;
+      std::string nm(name);
+      bool ok = true;
+      if (dt == 0 && im.count(nm)) { im[nm]->resize(cnt); ok = !cnt || fread(im[nm]->data(), 1, bytes, f) == bytes; }
+      else if (dt == 1 && dm.count(nm)) { dm[nm]->resize(cnt); ok = !cnt || fread(dm[nm]->data(), 1, bytes, f) == bytes; }
+      else {
+        std::vector<unsigned char> raw(bytes);
+        ok = !bytes || fread(raw.data(), 1, bytes, f) == bytes;
+        if (nm == "names_link") split_names(raw, link_names);
+        else if (nm == "names_node") split_names(raw, node_names);
+        else if (nm == "names_cls") split_names(raw, cls_names);
+      }
+      if (!ok) { fclose(f); error = "truncated section " + nm; return false; }
+      size_t pad = (8 - bytes % 8) % 8; char tmp[8];
+      if (pad && fread(tmp, 1, pad, f) != pad) { fclose(f); error = "truncated padding"; return false; }
+    }
+    fclose(f);
+    return validate();
+  }
+
+  bool validate() {
+    if (params.size() < SYMFLAT_P_COUNT) { error = "params missing"; return false; }
+    if (cls.empty() || cls.size() % SYMFLAT_CLS_STRIDE) { error = "cls table malformed"; return false; }
+    if (link_i.size() % 8 || link_f.size() != (size_t)n_links() * 2) { error = "link tables malformed"; return false; }
+    if (lane_i.size() % 4 || lane_f.size() != (size_t)n_lanes()) { error = "lane tables malformed"; return false; }
+    if (succ_off.size() != (size_t)n_lanes() + 1 || sl_off.size() != (size_t)n_lanes() + 1) { error = "CSR offsets malformed"; return false; }
+    if (route_off.empty()) route_off.push_back(0);
+    return true;
+  }
+};
+
+}  // namespace symb200
