@@ -139,3 +139,44 @@ class Engine:
         inst = np.zeros(cap, np.float64)
         n = self._chk(self.L.symgpu_get_exited(self.h, cap, _p(ids), _p(inst)))
         return ids[:n], inst[:n]
+
+
+class SymuVia:
+    """ctypes view of the SymuVia C exports (include/symuvia_exports.h) exactly as a user of the reference's
+    libSymuVia.so binds them (SymExpC.h:15-53): one global current network, caller-allocated XML buffer."""
+
+    def __init__(self, xml_buffer_bytes: int = 1 << 24):
+        self.L = lib()
+        L = self.L
+        L.SymLoadNetworkEx.argtypes = [C.c_char_p]
+        L.SymLoadNetworkEx.restype = C.c_int
+        L.SymRunEx.argtypes = [C.c_char_p]
+        L.SymRunEx.restype = C.c_int
+        L.SymRunNextStepEx.argtypes = [C.c_char_p, C.c_bool, C.POINTER(C.c_bool)]
+        L.SymRunNextStepEx.restype = C.c_bool
+        L.SymRunNextStepLiteEx.argtypes = [C.c_bool, C.POINTER(C.c_bool)]
+        L.SymRunNextStepLiteEx.restype = C.c_bool
+        L.SymCreateVehicleEx.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_double]
+        L.SymCreateVehicleEx.restype = C.c_int
+        L.SymUnloadCurrentNetworkEx.argtypes = []
+        self.buf = C.create_string_buffer(xml_buffer_bytes)
+
+    def load(self, path: str) -> bool:
+        return bool(self.L.SymLoadNetworkEx(path.encode()))
+
+    def run(self, path: str) -> int:
+        return self.L.SymRunEx(path.encode())
+
+    def step(self, lite: bool = False):
+        end = C.c_bool(False)
+        if lite:
+            ok = self.L.SymRunNextStepLiteEx(True, C.byref(end))
+            return bool(ok), bool(end.value), None
+        ok = self.L.SymRunNextStepEx(self.buf, True, C.byref(end))
+        return bool(ok), bool(end.value), (self.buf.value.decode() if ok else None)
+
+    def create_vehicle(self, typ: str, origin: str, dest: str, lane: int, dbt: float) -> int:
+        return self.L.SymCreateVehicleEx(typ.encode(), origin.encode(), dest.encode(), lane, dbt)
+
+    def unload(self):
+        self.L.SymUnloadCurrentNetworkEx()

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/symgpu.h"
+#include "engine_internal.h"
 #include "flatnet.h"
 #include "micro.cuh"
 
@@ -396,6 +397,8 @@ struct symgpu_ctx {
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
+  struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
+  std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
 };
 
@@ -447,6 +450,12 @@ static int upload_rows(symgpu_ctx* c, int slot0, const std::vector<HostRow>& row
 }
 
 extern "C" const char* symgpu_last_error(void) { return g_err.c_str(); }
+const symb200::FlatNet& symgpu_internal_net(symgpu_ctx* c) { return c->net; }
+int symgpu_internal_create_vehicle(symgpu_ctx* c, int cls, int entry, int dest, int lane, double dbt) {
+  int id = c->last_id++;                                             // IncLastIdVeh at request time
+  c->api_queue.push_back({id, cls, entry, dest, lane, dbt});
+  return id;
+}
 
 extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   if (!out || !path) return SYMGPU_E_ARG;
@@ -573,6 +582,28 @@ static void update_crit(symgpu_ctx* c, HostEntry& e, double inst, bool due_to_cr
 }
 static double max_debit_max(const symgpu_ctx* c) { double m = 0; for (int i = 0; i < c->P.ncls; i++) { const DevCls& k = c->P.cls[i]; double q = k.w * k.kx / ((k.w / k.vx) - 1); if (q > m) m = q; } return m; }
 
+// SymCreateVehicle path (reseau.cpp:13351 -> :2233-2240 -> GenerateVehicle with type, lane and destination imposed):
+// only the itinerary (:515), law-coefficient and Jorge draws remain; the vehicle joins m_LstVehicles BEFORE
+// InitVehicules, so it is shifted once (state at index 1, position still undefined) like an older ready vehicle.
+static void create_api_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::vector<EntryLane*>& new_row_lane) {
+  const double dt = c->P.dt, inst = c->t;
+  for (auto& a : c->api_queue) {
+    HostEntry& e = c->entries[a.entry];
+    int nl = (int)e.lanes.size(); int nv = a.lane;
+    if (nv < 0) { double r = c->rng.next() / 32767.0, sum = 0; for (nv = 0; nv < nl; nv++) { double cf = e.lane_coefs[nv]; if (cf <= 0) continue; sum += cf; if (sum >= r) break; } if (nv >= nl) nv = nl - 1; }
+    if (c->P.cls[a.cls].law != 0) c->rng.next();
+    int route = e.dest_routes[a.dest].back().first;
+    { double r = c->rng.next() / 32767.0, sum = 0; for (auto& q : e.dest_routes[a.dest]) { sum += q.second; if (r <= sum) { route = q.first; break; } } }
+    c->rng.next();
+    c->created++;
+    EntryLane& el = e.lanes[nv];
+    HostVeh hv{a.id, a.cls, route, el.lane, a.dbt, inst - dt + a.dbt};
+    if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);
+    else { HostRow r{ST_ALIVE, a.id, a.cls, route, 0, el.lane, SYM_UNDEF, c->P.cls[a.cls].vx, 0.0, a.dbt, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el); }
+  }
+  c->api_queue.clear();
+}
+
 // returns rows to append to m_LstVehicles this step (ready vehicles), fills waiting queues
 static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::vector<EntryLane*>& new_row_lane) {
   const double dt = c->P.dt, inst = c->t; const FlatNet& f = c->net; const double mdm = max_debit_max(c);
@@ -621,6 +652,7 @@ static int do_step(symgpu_ctx* c) {
   if (has_entries) {
     const double mdm = max_debit_max(c);
     for (auto& e : c->entries) update_crit(c, e, c->t, false, mdm);
+    create_api_vehicles(c, new_rows, new_row_lane);
     create_vehicles(c, new_rows, new_row_lane);
     if (c->n_slots + (int)new_rows.size() + c->n_pool > c->pool_base) { g_err = "vehicle capacity exhausted (set SYMGPU_CAPACITY)"; return SYMGPU_E_CAPACITY; }
     for (size_t i = 0; i < new_rows.size(); i++) new_row_lane[i]->pret_slot = c->n_slots + (int)i;

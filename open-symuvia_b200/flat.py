@@ -3,7 +3,7 @@
 The reference keeps the network as a pointer graph built by its XML loader
 (`symuvia/src/reseau.cpp:4931-9612`).  The B200 path needs flat tables; this module is the
 Python writer/reader of the binary container both the product (`csrc/host/flatnet.cpp`) and
-the oracle (`oracle/oracle.cpp`) load.  Layout (little endian):
+the CPU checker used by the tests load.  Layout (little endian):
 
     "SYMFLAT1" | u32 n_sections | { char name[24] | u32 dtype | u64 count | data, padded to 8 B }*
 

@@ -39,6 +39,7 @@ def lib():
         L.orc_link_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_exited.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_waiting.argtypes = [C.c_void_p]
+        L.orc_create_vehicle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.orc_rng_new.restype = C.c_void_p
         L.orc_rng_new.argtypes = [C.c_uint]
         L.orc_rng_next.argtypes = [C.c_void_p]
@@ -84,6 +85,9 @@ class Oracle:
 
     def counter(self, which: int) -> int:
         return self.L.orc_counter(self.h, which)
+
+    def create_vehicle(self, cls: int, entry: int, dest: int, lane: int, dbt: float) -> int:
+        return self.L.orc_create_vehicle(self.h, cls, entry, dest, lane, dbt)
 
     def waiting(self) -> int:
         return self.L.orc_waiting(self.h)

@@ -171,6 +171,8 @@ struct Sim {
   std::vector<Veh*> graveyard;
   double min_kv = 0, max_vit_max = 0, max_debit_max = 0;
   long n_ties = 0, n_loops = 0, n_created = 0;
+  struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
+  std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
 
   // ---------------------------------------------------------------------------------------------
   bool load(const char* path) {
@@ -725,6 +727,26 @@ struct Sim {
     else { e.pret[nv] = v->id; add_vehicule(v); }
     return v;
   }
+  // SymCreateVehicle: Reseau::CreateVehicle reseau.cpp:13351 queues, SimuTrafic :2233-2240 activates before
+  // InitVehicules: GenerateVehicle with type / lane / destination imposed (only itinerary, law and Jorge draws)
+  void activate_api_vehicles(double inst) {
+    for (auto& a : api_queue) {
+      Entry& e = entries[a.entry]; const Link& T = links[e.link];
+      int nv = a.lane;
+      if (nv < 0) { double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER; double sum = 0;
+        for (nv = 0; nv < T.n_lanes; nv++) { double cf = e.lane_coefs[nv]; if (cf <= 0) continue; sum += cf; if (sum >= r) break; }
+        if (nv >= T.n_lanes) nv = T.n_lanes - 1; }
+      Veh* v = new_vehicle(a.cls, a.id);
+      { double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER; double sum = 0; const Dest& D = e.dests[a.dest]; v->route = D.routes.back().route;
+        for (auto& q : D.routes) { sum += q.coeff; if (r <= sum) { v->route = q.route; break; } } }
+      v->route_pos = 0; v->lane[0] = T.first_lane + nv; v->link[0] = e.link;
+      v->inst_creation = a.dbt; v->heure_entree = inst - dt + a.dbt; v->vit_reg_tuy_act = T.vit_reg;
+      rnd.myRand(); n_created++;
+      if (e.pret[nv] != -1 || !e.attente[nv].empty()) e.attente[nv].push_back(v);
+      else { e.pret[nv] = v->id; add_vehicule(v); }
+    }
+    api_queue.clear();
+  }
   void creation_vehicules(Entry& e, double inst) {                                          // :212-325
     for (;;) {
       bool creation; double inst_creat = 0;
@@ -831,6 +853,7 @@ struct Sim {
   int step() {
     t += dt; ninst++;                                                                        // :2105-2106
     for (auto& e : entries) update_crit_creation_step(e);                                   // :2219-2223
+    activate_api_vehicles(t);                                                                // :2233-2240
     init_vehicules();                                                                        // :2250
     for (auto& e : entries) creation_vehicules(e, t);                                       // :2255 -> :14143
     // ChangementDeVoie :14181 (row A9, pending) ; ComputeFirstVehicules :14184 (only consumed by flux nodes)
@@ -872,6 +895,8 @@ void orc_link_counts(void* h, int* entre, int* sorti) { Sim* s = (Sim*)h; size_t
   memcpy(entre, s->nb_entre.data(), n * 4); memcpy(sorti, s->nb_sorti.data(), n * 4); }
 int orc_exited(void* h, int* ids, double* inst, int cap) { Sim* s = (Sim*)h; int n = 0;
   for (auto& e : s->exited) { if (n < cap) { ids[n] = e.id; inst[n] = e.inst; } n++; } return n; }
+int orc_create_vehicle(void* h, int cls, int entry, int dest, int lane, double dbt) { Sim* s = (Sim*)h; int id = s->last_id++;
+  s->api_queue.push_back({id, cls, entry, dest, lane, dbt}); return id; }
 int orc_waiting(void* h) { Sim* s = (Sim*)h; int n = 0; for (auto& e : s->entries) for (auto& q : e.attente) n += (int)q.size(); return n; }
 // raw RNG access for the known-answer test of the generator itself
 void* orc_rng_new(unsigned seed) { auto* r = new RandManager(); r->mySrand(seed); return r; }

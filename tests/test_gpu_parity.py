@@ -1,0 +1,125 @@
+"""Parity of the CUDA path (through the symgpu C-ABI) against the CPU oracle — needs a B200.
+
+Integer state (list order, ids, lanes, route cursor, regime flags, leader ids, link counters, exits, RNG count)
+must be bit-exact; fp64 state within 1e-9 relative (BASELINE.json north_star).  In practice the device arithmetic
+is contraction-free and ordered like the reference, so the tests also assert bit-exact fp64 (`worst == 0`).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+from tests.parity import run_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(stats, expect_loops=None):
+    assert stats["overflow"] == 0
+    assert stats["loops_gpu"] == stats["loops_oracle"]
+    assert stats["worst"] == 0.0, stats
+    if expect_loops:
+        assert stats["loops_gpu"] > 0
+
+
+def test_c1_single_link_full_hour(synth):
+    """BASELINE config C1: 2 km one-lane link, Newell, 1800 veh/h, 3600 steps of 1 s."""
+    s = run_parity(synth.config("C1"), 3600, check_every=1)
+    _check(s)
+    assert s["veh_steps"] > 100000
+
+
+def test_signalised_link(synth):
+    _check(run_parity(synth.single_link(n_steps=600, signal=(20, 3, 17), vit_reg=15.0, demand=0.4), 600))
+
+
+def test_saturated_origin_queue(synth):
+    """Origin above capacity: ready / waiting vehicle logic (usage/SymuViaTripNode.cpp:1642-1851)."""
+    s = run_parity(synth.single_link(length=1500.0, vit_reg=10.0, demand=0.9, n_steps=300), 300)
+    _check(s)
+
+
+def test_deceleration_at_red(synth):
+    cls = dict(synth.VL, decel=2.5)
+    _check(run_parity(synth.single_link(n_steps=400, signal=(15, 3, 22), vit_reg=18.0, demand=0.35, classes=[cls]), 400))
+
+
+def test_exit_capacity(synth):
+    _check(run_parity(synth.single_link(length=800.0, n_steps=400, vit_reg=20.0, demand=0.5, exit_capacity=0.3), 400))
+
+
+def test_accbornee(synth):
+    _check(run_parity(synth.single_link(length=800.0, n_steps=300, vit_reg=20.0, demand=0.4, accbornee=True,
+                                        signal=(20, 3, 17)), 300))
+
+
+@pytest.mark.parametrize("law", [1, 2])
+def test_gipps_idm(synth, law):
+    """pow/sqrt differ by <= 1 ulp between glibc and CUDA: tolerance 1e-9 relative, integers still exact."""
+    cls = dict(synth.VL, law=law, decel=3.0)
+    s = run_parity(synth.single_link(length=800.0, vit_reg=15.0, demand=0.4, n_steps=300, classes=[cls], signal=(10, 2, 28)), 300)
+    assert s["overflow"] == 0 and s["worst"] <= 1e-9
+
+
+def test_two_classes_on_a_link(synth):
+    s = run_parity(synth.single_link(length=1200.0, vit_reg=20.0, demand=0.5, n_steps=400, classes=[synth.VL, synth.PL],
+                                     type_coefs=[0.85, 0.15], signal=(20, 3, 17)), 400)
+    _check(s)
+
+
+def test_exponential_headways(synth):
+    _check(run_parity(synth.single_link(length=1200.0, vit_reg=20.0, demand=0.4, n_steps=400, exponential=True), 400))
+
+
+def test_grid_with_demand(synth):
+    """Small C2: 4x4 signalised grid, boundary demand, OD routes."""
+    _check(run_parity(synth.grid(n=4, n_steps=500, demand_per_lane=0.2, demand_duration=400), 500))
+
+
+def test_grid_saturated_demand(synth):
+    _check(run_parity(synth.grid(n=4, n_steps=400, demand_per_lane=0.45, demand_duration=600), 400))
+
+
+def test_grid_preseeded_shuffled_with_loops(synth):
+    """Pre-seeded congested grid, list order shuffled: exercises leader-recursion loop breaking."""
+    s = run_parity(synth.grid(n=6, n_steps=300, demand_per_lane=0.0, preseed_per_lane=12.6, shuffle=True), 300)
+    _check(s, expect_loops=True)
+
+
+def test_grid_rectangular_mixed(synth):
+    _check(run_parity(synth.grid(n=5, ny=3, n_steps=300, demand_per_lane=0.3, preseed_per_lane=8, shuffle=True), 300))
+
+
+def test_c2_config(synth):
+    """BASELINE config C2 (10x10 grid, ~20k vehicles at peak), first 400 steps."""
+    s = run_parity(synth.config("C2"), 400, check_every=10)
+    _check(s)
+
+
+def test_c4_full_size_prefix_and_invariants(synth, pkg):
+    """BASELINE config C4 at full size (100x100, ~1M vehicles): oracle parity on the first steps, then
+    size-independent invariants over a longer run: no follower passes its leader on a lane, positions stay
+    within the lane, the population only shrinks by exits."""
+    import os
+    import tempfile
+    b = synth.config("C4")
+    s = run_parity(b, 6, check_every=3)
+    _check(s)
+    fd, path = tempfile.mkstemp(suffix=".symflat")
+    os.close(fd)
+    b.write(path)
+    g = pkg.Engine(path)
+    os.unlink(path)
+    lane_len = np.asarray(b.lane_f)
+    n_prev = g.n
+    for _ in range(4):
+        n = g.run(5)
+        assert n <= n_prev
+        n_prev = n
+        st = g.state()
+        assert (st["pos"] >= 0).all() and (st["pos"] <= lane_len[st["lane"]] + 1e-9).all()
+        order = np.lexsort((st["pos"], st["lane"]))
+        same = st["lane"][order][1:] == st["lane"][order][:-1]
+        assert (np.diff(st["pos"][order])[same] >= 0).all()
+    assert g.counter(pkg.CNT_CTX_OVERFLOW) == 0
+    g.close()

@@ -22,6 +22,10 @@ elif case == "g6seed":
     b = synth.grid(n=6, n_steps=steps, demand_per_lane=0.0, preseed_per_lane=12.6, shuffle=True)
 elif case == "g6both":
     b = synth.grid(n=6, n_steps=steps, demand_per_lane=0.3, preseed_per_lane=8, shuffle=True)
+elif case == "c4":
+    b = synth.config("C4")
+elif case == "g30":
+    b = synth.grid(n=30, n_steps=steps, demand_per_lane=0.0, preseed_per_lane=12.6, shuffle=False)
 else:
     raise SystemExit("unknown case")
 t0 = time.time()
