@@ -1,0 +1,235 @@
+#!/usr/bin/env python
+"""bench.py — vehicle-steps/s of the per-time-step microscopic update on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W     the CPU oracle on the host cores (reference arm)
+
+A "step" is one simulated time step (Reseau::SimuTrafic, reseau.cpp:2028-2428) over every vehicle of the workload.
+Workload at N=1: BASELINE config C4 — 100x100 signalised grid, ~1M pre-seeded vehicles (synthetic, seed 42).
+`value`  : whole-job vehicle-steps/s, network + vehicles resident in HBM, timed with CUDA events on the step stream.
+`e2e`    : same metric through the host-facing call symgpu_step_traj(): every step ends with the device->host copy
+           of the trajectory rows (id, lane, pos, speed, acc) the XML writers consume; C4 has no origins, so the
+           per-step host->device input (created vehicles) is 0 bytes — stated, not hidden.
+`roofline`: dominant kernel, algorithmic bytes = 128 B per vehicle-step over its measured device time.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+B_ALG = 128.0   # algorithmic bytes per vehicle-step
+
+
+def make_workload(name: str, rank: int, path: str):
+    synth = importlib.import_module("open-symuvia_b200.synth")
+    if name == "C4":
+        b = synth.config("C4", seed=42 + rank)
+    elif name == "C4small":          # debugging only (not a bench line)
+        b = synth.grid(n=20, n_steps=300, demand_per_lane=0.0, preseed_per_lane=12.6, seed=42 + rank)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    b.write(path)
+    return dict(n_links=len(b.links), n_lanes=len(b.lanes), n_classes=len(b.classes), n_init=len(b.iv_i))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = max([int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()] or [0])
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_rate(path, info, steps, warmup=0):
+    from oracle.binding import Oracle
+    o = Oracle(path, info["n_links"], info["n_classes"])
+    for _ in range(warmup):
+        o.step()
+    tot = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tot += o.step()
+    dt = time.perf_counter() - t0
+    o.close()
+    return tot / dt, dt, tot
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--cpu-steps", type=int, default=10, help="oracle steps for cpu_baseline (bounded sample)")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warm = max(a.warmup, 3)
+    base_cfg = {"workload": f"{a.workload}: synthetic 100x100 signalised Manhattan grid, 200 m blocks, 2 lanes/dir, ~1M pre-seeded vehicles, "
+                            "Newell, dt=1 s, chgtvoie off (BASELINE.json configs[3])",
+                "working_set": "vehicle SoA + tables ~0.4 GB per GPU > 126 MB L2 (no L2 flush needed)"}
+    path = f"/tmp/symuvia_bench_{a.workload}_{rank}.symflat"
+
+    if a.impl == "reference":
+        # Reference arm: the reference's own CPU algorithm (oracle port; the C++ reference cannot be built here)
+        if rank != 0:
+            return
+        info = make_workload(a.workload, 0, path)
+        rate, dt, tot = cpu_oracle_rate(path, info, a.steps, warmup=min(warm, 3))
+        line = {"impl": "reference", "metric": "vehicle-steps/sec", "value": rate, "unit": "vehicle-steps/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": min(warm, 3), "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": dict(base_cfg, parallelism="1 host thread (the reference steps one network on one thread)"),
+                "cpu_baseline": {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port",
+                                 "sample": f"{a.steps} full time steps of {a.workload} ({tot} vehicle-steps)"},
+                "e2e": {"value": rate, "unit": "vehicle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("open-symuvia_b200")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    info = make_workload(a.workload, rank, path)
+    g = pkg.Engine(path, device=local)
+    L = g.L
+    L.symgpu_profile.argtypes = [g.h.__class__, pkg.C.c_int]
+    L.symgpu_kernel_ms.argtypes = [g.h.__class__, pkg.C.c_int]
+    L.symgpu_kernel_ms.restype = pkg.C.c_double
+    L.symgpu_kernel_launches.argtypes = [g.h.__class__, pkg.C.c_int]
+    L.symgpu_kernel_launches.restype = pkg.C.c_long
+    L.symgpu_kernel_name.restype = pkg.C.c_char_p
+    L.symgpu_vehicle_steps.argtypes = [g.h.__class__]
+    L.symgpu_vehicle_steps.restype = pkg.C.c_longlong
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    g.run(warm)
+    # ---- value: state resident in HBM, CUDA events around exactly K steps ------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.symgpu_profile(g.h, 1)
+    vs0, l0 = L.symgpu_vehicle_steps(g.h), g.counter(pkg.CNT_LAUNCHES)
+    barrier()
+    t0 = time.perf_counter()
+    g.run(a.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = g.last_step_ms
+    vsteps = L.symgpu_vehicle_steps(g.h) - vs0
+    launches = g.counter(pkg.CNT_LAUNCHES) - l0
+    kms = {L.symgpu_kernel_name(k).decode(): (L.symgpu_kernel_ms(g.h, k), L.symgpu_kernel_launches(g.h, k)) for k in range(L.symgpu_kernel_count())}
+    L.symgpu_profile(g.h, 0)
+    t_max = allmax(dev_ms / 1e3)
+    total_vsteps = allsum(float(vsteps))
+    value = total_vsteps / t_max
+    # ---- e2e: host-facing call, trajectory rows copied to host buffers every step ---------------------------------
+    cap = g.n + 1024
+    bufs = {"id": np.zeros(cap, np.int32), "lane": np.zeros(cap, np.int32), "pos": np.zeros(cap), "vit": np.zeros(cap), "acc": np.zeros(cap)}
+    e2e_steps = max(3, min(a.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    ev = 0
+    rows = 0
+    for _ in range(e2e_steps):
+        rows = g.step_traj(bufs)
+        ev += rows
+    barrier()
+    e2e_t = allmax(time.perf_counter() - t0)
+    e2e = allsum(float(ev)) / e2e_t
+    clocks = sampler.stop()
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
+    peak, peak_src = peak_hbm()
+    dom = max(kms, key=lambda k: kms[k][0])
+    dom_ms, dom_launches = kms[dom]
+    achieved = B_ALG * vsteps / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": peak_src, "launches_in_region": dom_launches, "avg_launch_ms": dom_ms / max(1, dom_launches),
+            "alg_bytes_per_vehicle_step": B_ALG, "whole_step_frac": B_ALG * vsteps / (dev_ms / 1e3) / 1e9 / peak,
+            "kernel_ms": {k: round(v[0], 3) for k, v in kms.items()}}
+    line = {"metric": "vehicle-steps/sec", "value": value, "unit": "vehicle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
+            "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": dict(base_cfg, parallelism=("1 GPU" if world == 1 else f"{world} independent grid partitions, one per GPU (boundary exchange not built yet)"),
+                           vehicles_per_gpu=info["n_init"], lanes_per_gpu=info["n_lanes"]),
+            "e2e": {"value": e2e, "unit": "vehicle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(rows) * 32,
+                    "steps": e2e_steps, "note": "C4 has no origins: per-step host input is empty; output = trajectory rows to host"},
+            "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks, "roofline": roof,
+            "loops_broken": g.counter(pkg.CNT_LOOPS), "follow_passes": g.counter(pkg.CNT_PASSES)}
+    if rank == 0 and world == 1 and a.cpu_steps > 0:
+        rate, dt, tot = cpu_oracle_rate(path, info, a.cpu_steps)
+        line["cpu_baseline"] = {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port",
+                                "sample": f"first {a.cpu_steps} time steps of the same {a.workload} input ({tot} vehicle-steps, {dt:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,14 @@ int symgpu_run(symgpu_ctx* c, int n_steps);
  * Vehicule::SortieTrafic (vehicule.cpp:1993-2176) hands to DocTrafic::AddTrajectoire.  Returns rows written. */
 int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
 
+/* Per-kernel device timing (CUDA events on the step stream) for roofline accounting. */
+int symgpu_profile(symgpu_ctx* c, int enable);
+int symgpu_kernel_count(void);
+const char* symgpu_kernel_name(int k);
+double symgpu_kernel_ms(symgpu_ctx* c, int k);
+long symgpu_kernel_launches(symgpu_ctx* c, int k);
+long long symgpu_vehicle_steps(symgpu_ctx* c);   /* sum over steps of vehicles on the network after the step */
+
 int symgpu_num_vehicles(symgpu_ctx* c);
 double symgpu_time(symgpu_ctx* c);
 unsigned symgpu_rng_count(symgpu_ctx* c);       /* RandManager::m_Count (RandManager.cpp:26-30) */

@@ -378,6 +378,7 @@ template <class T> struct DBuf {
 
 }  // namespace
 
+struct ProfRec { int kid; cudaEvent_t a, b; };
 struct symgpu_ctx {
   FlatNet net; DevParams P; int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double t = 0; int n_alive = 0, n_slots = 0, cap = 0, pool_base = 0, n_pool = 0; int stamp = 0;
@@ -399,6 +400,8 @@ struct symgpu_ctx {
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
+  bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
 };
 
@@ -599,7 +602,8 @@ static void create_api_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, s
     EntryLane& el = e.lanes[nv];
     HostVeh hv{a.id, a.cls, route, el.lane, a.dbt, inst - dt + a.dbt};
     if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);
-    else { HostRow r{ST_ALIVE, a.id, a.cls, route, 0, el.lane, SYM_UNDEF, c->P.cls[a.cls].vx, 0.0, a.dbt, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el); }
+    else { HostRow r{ST_ALIVE, a.id, a.cls, route, 0, el.lane, SYM_UNDEF, c->P.cls[a.cls].vx, 0.0, a.dbt, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el);
+      el.pret_slot = -2; /* ready vehicle registered, slot assigned at upload */ }
   }
   c->api_queue.clear();
 }
@@ -632,12 +636,32 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
       HostVeh hv{id, tv, route, el.lane, tcre, inst - dt + tcre};
       (void)f;
       if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);   // :794-800
-      else { HostRow r{ST_NEW, id, tv, route, 0, el.lane, SYM_UNDEF, c->P.cls[tv].vx, 0.0, tcre, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el); }
+      else { HostRow r{ST_NEW, id, tv, route, 0, el.lane, SYM_UNDEF, c->P.cls[tv].vx, 0.0, tcre, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el);
+        el.pret_slot = -2; /* ready vehicle registered, slot assigned at upload */ }
     }
   }
 }
 
+// per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
+enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_FOLLOW, KID_LOOP, KID_ENTRIES, KID_FINAL, KID_COUNT };
+static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_follow_pass",
+                                              "k_break_loop", "k_entries", "k_final"};
+static void prof_begin(symgpu_ctx* c, int kid);
+static void prof_end(symgpu_ctx* c);
 #define LAUNCH(c) ((c)->launches++)
+#define KBEGIN(c, kid) do { if ((c)->profile) prof_begin(c, kid); } while (0)
+#define KEND(c) do { LAUNCH(c); if ((c)->profile) prof_end(c); } while (0)
+
+static cudaEvent_t prof_event(symgpu_ctx* c) {
+  if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
+  return c->ev_pool[c->ev_used++];
+}
+static void prof_begin(symgpu_ctx* c, int kid) { ProfRec r{kid, prof_event(c), prof_event(c)}; cudaEventRecord(r.a, c->stream); c->prof_recs.push_back(r); }
+static void prof_end(symgpu_ctx* c) { cudaEventRecord(c->prof_recs.back().b, c->stream); }
+static void prof_collect(symgpu_ctx* c) {
+  for (auto& r : c->prof_recs) { float ms = 0; if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->k_ms[r.kid] += ms; c->k_launches[r.kid]++; } }
+  c->prof_recs.clear(); c->ev_used = 0;
+}
 
 static int do_step(symgpu_ctx* c) {
   const int L = c->net.n_lanes(), T = c->net.n_cls(), K = c->net.n_links();
@@ -680,21 +704,22 @@ static int do_step(symgpu_ctx* c) {
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
   CK(cudaMemsetAsync(c->stat.p, 0, 16 * sizeof(int), s));
-  if (c->net.n_sl()) { k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); LAUNCH(c); }
+  if (c->net.n_sl()) { KBEGIN(c, KID_SIGNALS); k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); KEND(c); }
   if (n > 0) {
-    k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); LAUNCH(c);
+    KBEGIN(c, KID_PREPARE); k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); KEND(c);
     int nb = (L + kScanB - 1) / kScanB;
-    k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
-    if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); LAUNCH(c); }
-    k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); LAUNCH(c);
-    k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->lane_done.p, c->counters.p); LAUNCH(c);
-    k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, n, c->lane_tail.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); LAUNCH(c);
+    KBEGIN(c, KID_SCAN); k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
+    if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
+    KEND(c);
+    KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
+    KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->lane_done.p, c->counters.p); KEND(c);
+    KBEGIN(c, KID_CONTEXT); k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, n, c->lane_tail.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c);
     // wavefront passes; stat is read back every `burst` passes
     int pass = 1; const int burst = 4; int stall = 0;
     for (;;) {
       for (int b = 0; b < burst; b++) {
         CK(cudaMemsetAsync(c->stat.p, 0, 2 * sizeof(int), s));
-        k_follow_pass<<<G(L), B, 0, s>>>(c->dn, c->dv, c->dl, L, c->order.p, c->lane_done.p, pass + 1, c->t, c->stat.p); LAUNCH(c);
+        KBEGIN(c, KID_FOLLOW); k_follow_pass<<<G(L), B, 0, s>>>(c->dn, c->dv, c->dl, L, c->order.p, c->lane_done.p, pass + 1, c->t, c->stat.p); KEND(c);
         pass++; c->passes++;
       }
       CK(cudaMemcpyAsync(c->h_stat, c->stat.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -702,26 +727,29 @@ static int do_step(symgpu_ctx* c) {
       if (c->h_stat[0] == 0) break;
       if (c->h_stat[1] == 0) {                                       // no progress in the last pass: a leader loop
         CK(cudaMemsetAsync(&c->stat.p[8], 0x7f, sizeof(int), s));
-        k_first_pending<<<G(n), B, 0, s>>>(c->dv, n, &c->stat.p[8]); LAUNCH(c);
-        k_break_loop<<<1, 32, 0, s>>>(c->dn, c->dv, c->dl, &c->stat.p[8], c->stack.p, c->visit.p, ++c->stamp, pass + 1, c->t, c->counters.p); LAUNCH(c);
+        KBEGIN(c, KID_LOOP); k_first_pending<<<G(n), B, 0, s>>>(c->dv, n, &c->stat.p[8]); LAUNCH(c);
+        k_break_loop<<<1, 32, 0, s>>>(c->dn, c->dv, c->dl, &c->stat.p[8], c->stack.p, c->visit.p, ++c->stamp, pass + 1, c->t, c->counters.p); KEND(c);
         pass++;
         if (++stall > n + 8) { g_err = "follow passes do not terminate"; return SYMGPU_E_CUDA; }
       }
     }
-    if (!desc.empty()) { k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
-                                                                    (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); LAUNCH(c); }
+    if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
+                                                                    (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     CK(cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s));
-    k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6]); LAUNCH(c);
+    KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6]); LAUNCH(c);
     if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
-                                                                              c->next_sortie.p, c->t, c->P.dt, c->P.duree); LAUNCH(c); }
+                                                                              c->next_sortie.p, c->t, c->P.dt, c->P.duree); }
+    KEND(c);
   }
   CK(cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(c->h_stat + 7, c->draws.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   std::vector<int> eres(desc.size());
   if (!desc.empty()) CK(cudaMemcpyAsync(eres.data(), c->eresult.p, desc.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  if (c->profile) prof_collect(c);
   if (c->h_stat[6]) { g_err = "internal error: vehicles left uncomputed"; return SYMGPU_E_CUDA; }
   c->n_alive = n > 0 ? c->h_stat[5] : 0;
+  c->veh_steps += c->n_alive;
   int nex = n > 0 ? c->h_stat[4] : 0;
   c->last_exited.resize(nex);
   if (nex) { CK(cudaMemcpy(c->last_exited.data(), c->exited.p, nex * sizeof(ExitRow), cudaMemcpyDeviceToHost));
@@ -801,6 +829,12 @@ extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, doub
   if (r < 0) return r;
   return symgpu_get_state(c, cap, id, lane, nullptr, nullptr, pos, vit, acc, nullptr, nullptr);
 }
+extern "C" int symgpu_profile(symgpu_ctx* c, int enable) { if (!c) return SYMGPU_E_ARG; c->profile = enable != 0; for (int k = 0; k < 16; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return SYMGPU_OK; }
+extern "C" int symgpu_kernel_count(void) { return KID_COUNT; }
+extern "C" const char* symgpu_kernel_name(int k) { return k >= 0 && k < KID_COUNT ? kKernelNames[k] : ""; }
+extern "C" double symgpu_kernel_ms(symgpu_ctx* c, int k) { return c && k >= 0 && k < KID_COUNT ? c->k_ms[k] : 0.0; }
+extern "C" long symgpu_kernel_launches(symgpu_ctx* c, int k) { return c && k >= 0 && k < KID_COUNT ? (long)c->k_launches[k] : 0; }
+extern "C" long long symgpu_vehicle_steps(symgpu_ctx* c) { return c ? c->veh_steps : 0; }
 extern "C" int symgpu_num_vehicles(symgpu_ctx* c) { return c ? c->n_alive : SYMGPU_E_ARG; }
 extern "C" double symgpu_time(symgpu_ctx* c) { return c ? c->t : 0.0; }
 extern "C" unsigned symgpu_rng_count(symgpu_ctx* c) { return c ? c->rng.count : 0; }
