@@ -36,6 +36,8 @@ static thread_local std::string g_err;
   do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return SYMGPU_E_CUDA; } } while (0)
 
 __constant__ DevParams cP;
+__device__ __forceinline__ const DevParams& cP_ref() { return cP; }
+#include "flow.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // device tables for signals
@@ -151,11 +153,10 @@ __global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill
 // Replaces the per-query linear scans of Reseau::GetPrevVehicule (reseau.cpp:3650-3718) and
 // GetNearAvalVehicule (:3583-3640) over the id-ordered lane sets.
 __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const int* lane_start, int* order,
-                             int* lane_tail, int* lane_done, long long* counters) {
+                             int* lane_tail, long long* counters) {
   int ln = blockIdx.x * blockDim.x + threadIdx.x;
   if (ln >= n_lanes) return;
   int n = lane_count[ln];
-  lane_done[ln] = n == 0;
   if (!n) { lane_tail[ln] = -1; return; }
   int s = lane_start[ln];
   for (int a = 1; a < n; a++) {
@@ -167,16 +168,37 @@ __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const
     }
     order[s + j + 1] = x;
   }
+  // Equal positions: Reseau::GetLastVehicule (reseau.cpp:14041-14081) returns the first candidate (id order) that is not
+  // the leader of another candidate; the candidates' leaders are read from their previous-step context (a candidate met
+  // while it has already rebuilt its context this step is counted in SYMGPU_CNT_TIES but not replayed).
+  auto pick = [&](int b0, int b1) -> int {          // group = order[s+b0 .. s+b1) at one position, id-ascending
+    if (b1 - b0 == 1) return order[s + b0];
+    for (int i = b0; i < b1; i++) {
+      int idi = V.id[order[s + i]]; bool fol = false;
+      for (int j = b0; j < b1 && !fol; j++) if (j != i && V.prev_leader[order[s + j]] == idi) fol = true;
+      if (!fol) return order[s + i];
+    }
+    return order[s + b1 - 1];
+  };
   int tail = -1; int ties = 0;
   for (int a = 0; a < n; a++) {
     int x = order[s + a]; double px = snap_pos(V.pos[x]);
-    if (tail < 0 && px >= 0) { tail = x; if (a + 1 < n && snap_pos(V.pos[order[s + a + 1]]) == px) ties++; }
+    if (tail < 0 && px >= 0) {
+      int b1 = a + 1; while (b1 < n && snap_pos(V.pos[order[s + b1]]) == px) b1++;
+      if (b1 - a > 1) ties++;
+      tail = pick(a, b1);
+    }
     double own = px <= SYM_UNDEF ? 0.0 : px;
     bool eq_ok = V.status[x] == ST_NEW;           // GetPos(0) == UNDEF only before the first computation (reseau.cpp:3695)
     int ld = -1;
     for (int b = a + 1; b < n; b++) {
       int y = order[s + b]; double pb = snap_pos(V.pos[y]);
-      if (pb > own || (eq_ok && pb == own)) { ld = y; if (b + 1 < n && snap_pos(V.pos[order[s + b + 1]]) == pb) ties++; break; }
+      if (pb > own || (eq_ok && pb == own)) {
+        int b1 = b + 1; while (b1 < n && snap_pos(V.pos[order[s + b1]]) == pb) b1++;
+        if (b1 - b > 1) ties++;
+        ld = pick(b, b1);
+        break;
+      }
     }
     V.ahead[x] = ld;
   }
@@ -191,66 +213,6 @@ __global__ void k_context(DevNet N, DevVeh V, int n, const int* lane_tail, unsig
   if (st != ST_ALIVE && st != ST_NEW) return;
   int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow);
   if (d) atomicAdd(draws, (unsigned)d);
-}
-
-// One wavefront pass: every lane walks its vehicles front -> back; a lane head whose leader sits on another
-// lane waits for a later pass until that leader was computed in an EARLIER pass (stamp < pass).
-// stat[0] = lanes still pending after the pass, stat[1] = vehicles computed in the pass.
-__global__ void k_follow_pass(DevNet N, DevVeh V, DevLaneDyn LD, int n_lanes, const int* order, int* lane_done, int pass,
-                              double inst, int* stat) {
-  int ln = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ln >= n_lanes) return;
-  if (lane_done[ln]) return;
-  int n = LD.count[ln], s = LD.start[ln];
-  int done = 0, prog = 0;
-  bool pending = false;
-  for (int a = n - 1; a >= 0; a--) {
-    int x = order[s + a];
-    if (V.computed[x]) { done++; continue; }
-    int L = V.ctx_leader[x];
-    if (L >= 0) {
-      int cl = V.computed[L];
-      bool same_thread = (V.lane[L] == ln) && cl != 0;      // own-lane leader: computed by this thread just before
-      if (!(same_thread || (cl != 0 && cl < pass))) { pending = true; break; }
-    }
-    follow_one(cP, N, V, LD, x, true, inst);
-    V.computed[x] = pass;
-    done++; prog++;
-  }
-  if (!pending && done == n) lane_done[ln] = 1; else atomicAdd(&stat[0], 1);
-  if (prog) atomicAdd(&stat[1], prog);
-}
-
-// first not yet computed vehicle in list (slot) order
-__global__ void k_first_pending(DevVeh V, int n, int* first) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int st = V.status[i];
-  if ((st == ST_ALIVE || st == ST_NEW) && !V.computed[i]) atomicMin(first, i);
-}
-// Loop breaking exactly as the recursion of Vehicule::CalculTraficEx does it (vehicule.cpp:1198-1217, :1304-1309):
-// follow the leader chain from the first pending vehicle of m_LstVehicles; when the chain re-enters itself the
-// re-entered vehicle stays uncomputed and its follower uses the estimated leader speed
-// (NewellCarFollowing.cpp:217-230); then the chain unwinds leader first.
-__global__ void k_break_loop(DevNet N, DevVeh V, DevLaneDyn LD, const int* first, int* stack, int* visit, int stamp, int pass,
-                             double inst, long long* counters) {
-  if (blockIdx.x || threadIdx.x) return;
-  int x = *first;
-  if (x >= 0x7f7f7f7f) return;
-  int depth = 0; bool loop = false;
-  for (;;) {
-    stack[depth++] = x; visit[x] = stamp;
-    int L = V.ctx_leader[x];
-    if (L < 0 || V.computed[L]) break;
-    if (visit[L] == stamp) { loop = true; break; }
-    x = L;
-  }
-  if (loop && cP.cls[V.cls[stack[depth - 1]]].law == 0) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_LOOPS], 1ULL);
-  for (int d = depth - 1; d >= 0; d--) {
-    int y = stack[d];
-    follow_one(cP, N, V, LD, y, !(loop && d == depth - 1), inst);
-    V.computed[y] = pass;
-  }
 }
 
 // Origins, after the main update: ready vehicle inserted? then try the first waiting vehicle of the lane
@@ -390,7 +352,9 @@ struct symgpu_ctx {
   DBuf<double> lane_len, sl_pos, link_len, link_vreg, ctrl_cycle, seq_len, sig_green, sig_amber, sig_delay, exit_cap;
   // per step
   DBuf<int> sl_col; DBuf<double> sl_prop;
-  DBuf<int> lane_count, lane_start, lane_fill, lane_tail, lane_done, exit_winner, bsum, order, entre, sorti, stat, visit, stack;
+  DBuf<int> lane_count, lane_start, lane_fill, lane_tail, exit_winner, bsum, order, entre, sorti, stat;
+  DBuf<int> f_posidx, f_isfront, f_seg_len, f_seg_dep, f_segpos, f_minslot, f_first_waiter, f_next_waiter, f_cut, f_queue, f_A, f_A2, f_Mn, f_Mn2, f_oncyc, f_cid;
+  DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DevFlow df; int flow_grid = 0; FlowCtl* h_ctl = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
@@ -421,8 +385,12 @@ static void fill_dev_structs(symgpu_ctx* c) {
   v.ahead = c->v_ahead.p; v.computed = c->v_computed.p; v.ctx_nl = c->v_ctx_nl.p; v.ctx_lane = c->v_ctx_lane.p; v.ctx_leader = c->v_ctx_leader.p;
   v.ctx_flags = c->v_ctx_flags.p; v.ctx_gap = c->v_ctx_gap.p; v.ctx_dn0 = c->v_ctx_dn0.p; v.ctx_dfree = c->v_ctx_dfree.p;
   DevLaneDyn& l = c->dl;
-  l.count = c->lane_count.p; l.start = c->lane_start.p; l.fill = c->lane_fill.p; l.tail = c->lane_tail.p; l.head_done = c->lane_done.p;
+  l.count = c->lane_count.p; l.start = c->lane_start.p; l.fill = c->lane_fill.p; l.tail = c->lane_tail.p; l.head_done = nullptr;
   l.next_sortie = c->next_sortie.p; l.exit_winner = c->exit_winner.p;
+  DevFlow& fl = c->df;
+  fl.order = c->order.p; fl.posidx = c->f_posidx.p; fl.isfront = c->f_isfront.p; fl.seg_len = c->f_seg_len.p; fl.seg_dep = c->f_seg_dep.p; fl.segpos = c->f_segpos.p;
+  fl.minslot = c->f_minslot.p; fl.first_waiter = c->f_first_waiter.p; fl.next_waiter = c->f_next_waiter.p; fl.cut = c->f_cut.p; fl.queue = c->f_queue.p;
+  fl.ctl = c->f_ctl.p; fl.A = c->f_A.p; fl.A2 = c->f_A2.p; fl.Mn = c->f_Mn.p; fl.Mn2 = c->f_Mn2.p; fl.oncyc = c->f_oncyc.p; fl.cid = c->f_cid.p; fl.rootkey = c->f_rootkey.p;
   DevSig& s = c->ds;
   s.ctrl_seq_off = c->ctrl_seq_off.p; s.ctrl_nseq = c->ctrl_nseq.p; s.ctrl_cycle = c->ctrl_cycle.p; s.seq_sig_off = c->seq_sig_off.p; s.seq_nsig = c->seq_nsig.p;
   s.seq_len = c->seq_len.p; s.sig_in = c->sig_in.p; s.sig_out = c->sig_out.p; s.sig_green = c->sig_green.p; s.sig_amber = c->sig_amber.p; s.sig_delay = c->sig_delay.p;
@@ -526,10 +494,16 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   c->cap = (int)cap; c->pool_base = c->cap - c->n_pool;
   { int q = 0; for (auto& e : c->entries) for (auto& l : e.lanes) l.pool_base = c->pool_base + q++; }
   // dynamic lane / link state
-  CK(c->lane_count.alloc(L)); CK(c->lane_start.alloc(L)); CK(c->lane_fill.alloc(L)); CK(c->lane_tail.alloc(L)); CK(c->lane_done.alloc(L));
+  CK(c->lane_count.alloc(L)); CK(c->lane_start.alloc(L)); CK(c->lane_fill.alloc(L)); CK(c->lane_tail.alloc(L));
   CK(c->exit_winner.alloc(L)); CK(cudaMemset(c->exit_winner.p, 0xff, L * sizeof(int))); CK(c->next_sortie.alloc(L));
   CK(c->bsum.alloc((L + kScanB - 1) / kScanB + 1)); CK(c->order.alloc(cap)); CK(c->entre.alloc((size_t)K * T)); CK(c->sorti.alloc((size_t)K * T));
-  CK(c->stat.alloc(16)); CK(c->visit.alloc(cap)); CK(c->stack.alloc(cap)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
+  CK(c->stat.alloc(16)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
+  for (DBuf<int>* b : {&c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_first_waiter, &c->f_next_waiter, &c->f_cut,
+                       &c->f_queue, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
+  CK(c->f_rootkey.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
+  { int nb = 0, sms = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow, 128, 0)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    c->flow_grid = std::max(1, nb) * std::max(1, sms); }
+  c->f_queue.free(); CK(c->f_queue.alloc(cap + (size_t)c->flow_grid * 4 + 64));   // one ticket per worker beyond the last segment
   CK(c->exited.alloc(cap)); CK(c->edesc.alloc(std::max(1, n_entry_lanes))); CK(c->eresult.alloc(std::max(1, n_entry_lanes)));
   // vehicles
   for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
@@ -556,13 +530,16 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   for (DBuf<int>* b : {&c->lane_link, &c->lane_num, &c->lane_prev, &c->lane_flags, &c->succ_off, &c->succ_key, &c->succ_next, &c->sl_off, &c->sl_i, &c->link_first,
                        &c->link_nl, &c->link_up, &c->link_type, &c->link_brick, &c->route_off, &c->route_links, &c->ctrl_seq_off, &c->ctrl_nseq, &c->seq_sig_off,
                        &c->seq_nsig, &c->sig_in, &c->sig_out, &c->exit_lanes, &c->exit_nl, &c->sl_col, &c->lane_count, &c->lane_start, &c->lane_fill, &c->lane_tail,
-                       &c->lane_done, &c->exit_winner, &c->bsum, &c->order, &c->entre, &c->sorti, &c->stat, &c->visit, &c->stack, &c->eresult, &c->v_status, &c->v_id,
+                       &c->exit_winner, &c->bsum, &c->order, &c->entre, &c->sorti, &c->stat, &c->eresult, &c->v_status, &c->v_id,
+                       &c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_first_waiter, &c->f_next_waiter, &c->f_cut,
+                       &c->f_queue, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid,
                        &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_memo, &c->v_ahead, &c->v_computed,
                        &c->v_ctx_nl, &c->v_ctx_lane, &c->v_ctx_leader, &c->v_ctx_flags}) b->free();
   for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
                           &c->sl_prop, &c->next_sortie, &c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre,
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
-  c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free();
+  c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free();
+  if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_stat) cudaFreeHost(c->h_stat);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -643,9 +620,9 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
 }
 
 // per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
-enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_FOLLOW, KID_LOOP, KID_ENTRIES, KID_FINAL, KID_COUNT };
-static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_follow_pass",
-                                              "k_break_loop", "k_entries", "k_final"};
+enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_SEG, KID_FOLLOW, KID_LOOP, KID_ENTRIES, KID_FINAL, KID_COUNT };
+static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_seg", "k_flow",
+                                              "k_cyc_loops", "k_entries", "k_final"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
 #define LAUNCH(c) ((c)->launches++)
@@ -700,6 +677,7 @@ static int do_step(symgpu_ctx* c) {
     if (!desc.empty()) CK(cudaMemcpyAsync(c->edesc.p, desc.data(), desc.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, s));
   }
   const int n = c->n_slots;
+  const int n_sorted = c->n_alive + (int)new_rows.size();   // vehicles that are members of a lane this step
   const int B = 256;
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
@@ -712,26 +690,38 @@ static int do_step(symgpu_ctx* c) {
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
     KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
-    KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->lane_done.p, c->counters.p); KEND(c);
+    KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->counters.p); KEND(c);
     KBEGIN(c, KID_CONTEXT); k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, n, c->lane_tail.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c);
-    // wavefront passes; stat is read back every `burst` passes
-    int pass = 1; const int burst = 4; int stall = 0;
-    for (;;) {
-      for (int b = 0; b < burst; b++) {
-        CK(cudaMemsetAsync(c->stat.p, 0, 2 * sizeof(int), s));
-        KBEGIN(c, KID_FOLLOW); k_follow_pass<<<G(L), B, 0, s>>>(c->dn, c->dv, c->dl, L, c->order.p, c->lane_done.p, pass + 1, c->t, c->stat.p); KEND(c);
-        pass++; c->passes++;
-      }
-      CK(cudaMemcpyAsync(c->h_stat, c->stat.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
+    if (n_sorted > 0) {
+    CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
+    KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p); KEND(c);
+    int seg_done = 0;
+    for (int round = 0;; round++) {
+      CK(cudaMemsetAsync(c->f_queue.p, 0xff, ((size_t)n_sorted + (size_t)c->flow_grid * 4 + 64) * sizeof(int), s));
+      CK(cudaMemsetAsync(c->f_ctl.p, 0, 4 * sizeof(int), s));          // q_head, n_pushed, n_started, n_completed
+      KBEGIN(c, KID_FOLLOW);
+      k_flow_reset<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted); LAUNCH(c);
+      k_flow_init<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted); LAUNCH(c);
+      k_flow<<<c->flow_grid, 128, 0, s>>>(c->dn, c->dv, c->dl, c->df, c->t);
+      KEND(c);
+      c->passes++;
+      CK(cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      if (c->h_stat[0] == 0) break;
-      if (c->h_stat[1] == 0) {                                       // no progress in the last pass: a leader loop
-        CK(cudaMemsetAsync(&c->stat.p[8], 0x7f, sizeof(int), s));
-        KBEGIN(c, KID_LOOP); k_first_pending<<<G(n), B, 0, s>>>(c->dv, n, &c->stat.p[8]); LAUNCH(c);
-        k_break_loop<<<1, 32, 0, s>>>(c->dn, c->dv, c->dl, &c->stat.p[8], c->stack.p, c->visit.p, ++c->stamp, pass + 1, c->t, c->counters.p); KEND(c);
-        pass++;
-        if (++stall > n + 8) { g_err = "follow passes do not terminate"; return SYMGPU_E_CUDA; }
-      }
+      seg_done += c->h_ctl->n_completed;
+      if (c->h_ctl->n_vehicles_done >= n_sorted) break;
+      if (round > n_sorted) { g_err = "follow rounds do not terminate"; return SYMGPU_E_CUDA; }
+      int R = std::max(2, c->h_ctl->n_segments - seg_done), Klev = 1;
+      while ((1 << Klev) < R) Klev++;
+      Klev++;
+      KBEGIN(c, KID_LOOP);
+      k_cyc_init<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted); LAUNCH(c);
+      int flip = 0;
+      for (int k = 0; k < Klev; k++) { k_cyc_double<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c); flip ^= 1; }
+      k_cyc_mark<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c);
+      k_cyc_break<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, c->counters.p);
+      KEND(c);
+    }
     }
     if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
                                                                     (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }

@@ -1,0 +1,206 @@
+// flow.cuh — dependency-ordered execution of the car-following update (rows A4/A5 of SURVEY.md §8a).
+//
+// The reference computes a vehicle's leader before the vehicle itself (Vehicule::CalculTraficEx recursion,
+// vehicule.cpp:1304-1309) because Newell's congested branch uses the leader's NEW speed
+// (NewellCarFollowing.cpp:213-216).  On the device the same order is obtained without recursion:
+//   * k_seg      cuts every lane (already ordered by position) into SEGMENTS: maximal runs in which each
+//                vehicle follows the vehicle directly ahead.  Only a segment's front vehicle can depend on
+//                a vehicle outside the segment (the tail of the next lane of its route).
+//   * k_flow     persistent dataflow kernel: one warp = one worker; ready segments are taken from a ticket
+//                queue, walked front -> back by lane 0, and on completion the segments waiting on them are
+//                released (first one handed to the same worker: no queue latency on the critical chain).
+//                No worker ever waits on unscheduled work: the only spin is on the queue, and it ends when
+//                every scheduled segment has completed.
+//   * k_cyc_*    when segments remain (a loop of leaders, "Infinite loop detected" vehicule.cpp:1201-1216):
+//                pointer-doubling on the segment graph finds every loop and its basin; the basin's first
+//                vehicle in m_LstVehicles order is the root the reference's recursion would start from, which
+//                fixes WHERE the loop is cut (the re-entered vehicle X stays uncomputed, its follower Y uses
+//                the estimated leader speed, NewellCarFollowing.cpp:217-230); then the flow restarts.
+#pragma once
+#include "micro.cuh"
+
+namespace symb200 {
+
+constexpr int kDone = -2;     // first_waiter value of a completed segment
+
+struct FlowCtl { int q_head, n_pushed, n_started, n_completed, n_segments, n_vehicles_done, pad0, pad1; };
+
+struct DevFlow {
+  int *order, *posidx, *isfront, *seg_len, *seg_dep, *segpos, *minslot, *first_waiter, *next_waiter, *cut, *queue;
+  FlowCtl* ctl;
+  // loop detection scratch (indexed by order position)
+  int *A, *A2, *Mn, *Mn2, *oncyc, *cid;
+  unsigned long long* rootkey;
+};
+
+// per lane: segments, front -> rear
+__global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, const int* lane_start) {
+  int ln = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ln >= n_lanes) return;
+  int n = lane_count[ln];
+  if (!n) return;
+  int s = lane_start[ln];
+  int cur = -1, nseg = 0, len = 0, mn = 0x7fffffff;
+  for (int a = n - 1; a >= 0; a--) {
+    int p = s + a; int x = F.order[p];
+    F.posidx[x] = p;
+    int d = V.ctx_leader[x];
+    bool front = (a == n - 1) || d != F.order[p + 1];
+    if (front) {
+      if (cur >= 0) { F.seg_len[cur] = len; F.minslot[cur] = mn; }
+      cur = p; len = 0; mn = 0x7fffffff; nseg++;
+      F.isfront[p] = 1; F.seg_dep[p] = d; F.first_waiter[p] = -1;
+    } else F.isfront[p] = 0;
+    F.segpos[x] = cur; F.cut[x] = 0;
+    len++; if (x < mn) mn = x;
+  }
+  F.seg_len[cur] = len; F.minslot[cur] = mn;
+  atomicAdd(&F.ctl->n_segments, nseg);
+}
+
+__device__ __forceinline__ void flow_push(const DevFlow& F, int seg) {
+  atomicAdd(&F.ctl->n_started, 1);
+  int slot = atomicAdd(&F.ctl->n_pushed, 1);
+  __threadfence();
+  *(volatile int*)&F.queue[slot] = seg;
+}
+
+// start of a round: forget the waiter lists of unfinished segments
+__global__ void k_flow_reset(DevFlow F, int n_sorted) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  if (F.isfront[p] && F.first_waiter[p] != kDone) F.first_waiter[p] = -1;
+}
+// schedule the segments that can start, register the others on the segment they wait for
+__global__ void k_flow_init(DevVeh V, DevFlow F, int n_sorted) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  if (!F.isfront[p] || F.first_waiter[p] == kDone) return;
+  int x = F.order[p];
+  int d = F.seg_dep[p];
+  if (d < 0 || F.cut[x] || V.computed[d]) { flow_push(F, p); return; }
+  int t = F.segpos[d];
+  for (;;) {
+    int h = *(volatile int*)&F.first_waiter[t];
+    if (h == kDone) { flow_push(F, p); return; }
+    F.next_waiter[p] = h;
+    __threadfence();
+    if (atomicCAS(&F.first_waiter[t], h, p) == h) return;
+  }
+}
+
+// persistent workers
+__global__ void __launch_bounds__(128) k_flow(DevNet N, DevVeh V, DevLaneDyn LD, DevFlow F, double inst) {
+  const int lane = threadIdx.x & 31;
+  int seg = -1;                                    // segment handed over by the previous one (lane 0 only)
+  for (;;) {
+    if (lane == 0 && seg < 0) {                    // take a ticket
+      int t = atomicAdd(&F.ctl->q_head, 1);
+      for (;;) {
+        int v = *(volatile int*)&F.queue[t];
+        if (v >= 0) { seg = v; break; }
+        int c = *(volatile int*)&F.ctl->n_completed;
+        int st = *(volatile int*)&F.ctl->n_started;
+        int q = *(volatile int*)&F.ctl->n_pushed;
+        if (c == st && t >= q) { seg = -1; break; }   // everything scheduled has completed: no work will ever come
+        __nanosleep(64);
+      }
+    }
+    seg = __shfl_sync(0xffffffffu, seg, 0);
+    if (seg < 0) return;
+    const int len = F.seg_len[seg];
+    // lanes 1..31 pull the rows of the next vehicles of the segment towards L2/L1 while lane 0 computes
+    if (lane > 0 && lane < len) {
+      int x = F.order[seg - lane];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_gap[x]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_dfree[x]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_dn0[x]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_lane[x * kMaxCtx]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.pos[x]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.vit[x]));
+    }
+    if (lane == 0) {
+      __threadfence();                             // acquire: state written by the segment we waited for
+      for (int k = 0; k < len; k++) {
+        int x = F.order[seg - k];
+        follow_one(cP_ref(), N, V, LD, x, !F.cut[x], inst);
+        V.computed[x] = 1;
+      }
+      __threadfence();                             // release
+      int h = atomicExch(&F.first_waiter[seg], kDone);
+      int mine = -1;
+      while (h >= 0) {
+        int nx = F.next_waiter[h];
+        if (mine < 0) { mine = h; atomicAdd(&F.ctl->n_started, 1); } else flow_push(F, h);
+        h = nx;
+      }
+      atomicAdd(&F.ctl->n_vehicles_done, len);
+      __threadfence();
+      atomicAdd(&F.ctl->n_completed, 1);
+      seg = mine;
+    }
+  }
+}
+
+// ---- loop detection on the remaining segments ----------------------------------------------------------------
+__global__ void k_cyc_init(DevFlow F, int n_sorted) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  F.oncyc[p] = 0; F.rootkey[p] = ~0ULL; F.cid[p] = -1;
+  if (!F.isfront[p] || F.first_waiter[p] == kDone) { F.A[p] = p; F.Mn[p] = p; return; }
+  F.A[p] = F.segpos[F.seg_dep[p]];                 // every remaining segment waits on a remaining segment
+  F.Mn[p] = p;
+}
+__global__ void k_cyc_double(DevFlow F, int n_sorted, int flip) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;
+  int* Ao = flip ? F.A : F.A2; int* Mo = flip ? F.Mn : F.Mn2;
+  int a = A[p];
+  Ao[p] = A[a];
+  int m = M[p], m2 = M[a];
+  Mo[p] = m2 < m ? m2 : m;
+}
+__global__ void k_cyc_mark(DevFlow F, int n_sorted, int flip) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  if (!F.isfront[p] || F.first_waiter[p] == kDone) return;
+  const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;
+  int c0 = A[p];                                   // a segment on the loop this one leads to
+  F.oncyc[c0] = 1;
+  int id = M[c0];                                  // smallest segment id of that loop
+  F.cid[p] = id;
+  unsigned long long key = ((unsigned long long)(unsigned)F.minslot[p] << 32) | (unsigned)p;
+  atomicMin(&F.rootkey[id], key);
+}
+// one thread per loop: cut it where the reference's recursion would
+__global__ void k_cyc_break(DevVeh V, DevFlow F, int n_sorted, long long* counters) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  if (!F.oncyc[p] || F.cid[p] != p) return;        // representative = smallest segment of the loop
+  unsigned long long key = F.rootkey[p];
+  int r = (int)(key >> 32), rs = (int)(key & 0xffffffffu);
+  // entry segment of the root's chain into the loop, and the vehicle it enters at
+  int e = rs, T = -1;
+  while (!F.oncyc[e]) { T = F.seg_dep[e]; e = F.segpos[T]; }
+  // predecessor of e on the loop
+  int q = e;
+  for (;;) { int nx = F.segpos[F.seg_dep[q]]; if (nx == e) break; q = nx; }
+  int Tloop = F.seg_dep[q];                        // vehicle at which the loop enters e (tail of e's lane)
+  int X, Y;
+  int cand = (e != rs) ? T : r;                   // first vehicle of the root's chain inside e
+  X = (F.posidx[cand] >= F.posidx[Tloop]) ? cand : Tloop;   // behind the loop's entry point: the chain joins the loop there
+  if (X == Tloop) Y = F.order[q];                  // front vehicle of the predecessor segment
+  else Y = F.order[F.posidx[X] - 1];               // the vehicle right behind X inside e
+  F.cut[Y] = 1;
+  if (cP_ref().cls[V.cls[Y]].law == 0) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_LOOPS], 1ULL);
+  int py = F.posidx[Y];
+  if (!F.isfront[py]) {                            // split e below X: [rear .. Y] becomes a segment of its own
+    int rear = e - F.seg_len[e] + 1;
+    F.isfront[py] = 1; F.seg_len[py] = py - rear + 1; F.seg_len[e] = e - py; F.seg_dep[py] = X; F.first_waiter[py] = -1;
+    for (int a = rear; a <= py; a++) F.segpos[F.order[a]] = py;
+    atomicAdd(&F.ctl->n_segments, 1);
+  }
+}
+
+}  // namespace symb200

@@ -251,7 +251,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
     if (L >= 0) {
       const DevCls& cl = P.cls[V.cls[L]];
       double vL;
-      if (leader_computed) vL = V.vit_n[L];                                            // NewellCarFollowing.cpp:213-216
+      if (leader_computed) vL = __ldcg(&V.vit_n[L]);   // NewellCarFollowing.cpp:213-216 (written by another SM in the same kernel: read through L2)
       else {                                                                           // :217-230
         double vreg_l = n.link_vreg[n.lane_link[V.lane[L]]];                           // GetVitRegTuyAct of the leader
         if (P.accbornee) vL = fmin(fmin(vreg_l, cl.vx), vL1 + acc_max(c, vL1) * P.dt);

@@ -170,7 +170,7 @@ struct Sim {
   std::vector<Exited> exited;                                      // removed this step
   std::vector<Veh*> graveyard;
   double min_kv = 0, max_vit_max = 0, max_debit_max = 0;
-  long n_ties = 0, n_loops = 0, n_created = 0;
+  long n_ties = 0, n_loops = 0, n_created = 0, max_depth = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
 
@@ -606,6 +606,7 @@ struct Sim {
     if (v->deja_calcule) return;
     for (int id : ids) if (id == v->id) { if (cls[v->cls].law == 0) n_loops++; return; }   // :1203-1216
     ids.push_back(v->id);
+    if ((long)ids.size() > max_depth) max_depth = (long)ids.size();
     int prevlane = v->lane[1];
     if (prevlane < 0) { prevlane = v->lane[0]; set_voie_ant(v, prevlane); }                 // :1220-1232
     bool created;
@@ -880,7 +881,7 @@ int orc_step(void* h) { return ((Sim*)h)->step(); }
 int orc_nveh(void* h) { return (int)((Sim*)h)->lst.size(); }
 double orc_time(void* h) { return ((Sim*)h)->t; }
 unsigned orc_rng_count(void* h) { return ((Sim*)h)->rnd.count; }
-long orc_counter(void* h, int which) { Sim* s = (Sim*)h; return which == 0 ? s->n_ties : which == 1 ? s->n_loops : s->n_created; }
+long orc_counter(void* h, int which) { Sim* s = (Sim*)h; return which == 0 ? s->n_ties : which == 1 ? s->n_loops : which == 2 ? s->n_created : s->max_depth; }
 // state of m_LstVehicles in list order after the step
 void orc_dump(void* h, int* id, int* lane, int* route_pos, int* flags, double* pos, double* vit, double* acc, double* deltaN) {
   Sim* s = (Sim*)h; size_t i = 0;
