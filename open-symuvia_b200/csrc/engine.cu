@@ -153,7 +153,7 @@ __global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill
 // Replaces the per-query linear scans of Reseau::GetPrevVehicule (reseau.cpp:3650-3718) and
 // GetNearAvalVehicule (:3583-3640) over the id-ordered lane sets.
 __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const int* lane_start, int* order,
-                             int* lane_tail, long long* counters) {
+                             int* lane_tail, int* posidx, long long* counters) {
   int ln = blockIdx.x * blockDim.x + threadIdx.x;
   if (ln >= n_lanes) return;
   int n = lane_count[ln];
@@ -201,17 +201,18 @@ __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const
       }
     }
     V.ahead[x] = ld;
+    posidx[x] = s + a;
   }
   lane_tail[ln] = tail;
   if (ties) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_TIES], (unsigned long long)ties);
 }
 
-__global__ void k_context(DevNet N, DevVeh V, int n, const int* lane_tail, unsigned* draws, int* overflow) {
+__global__ void k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n, const int* lane_tail, const int* posidx, double* rows, unsigned* draws, int* overflow) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int st = V.status[i];
   if (st != ST_ALIVE && st != ST_NEW) return;
-  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow);
+  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow, rows, posidx[i], &LD);
   if (d) atomicAdd(draws, (unsigned)d);
 }
 
@@ -354,6 +355,7 @@ struct symgpu_ctx {
   DBuf<int> sl_col; DBuf<double> sl_prop;
   DBuf<int> lane_count, lane_start, lane_fill, lane_tail, exit_winner, bsum, order, entre, sorti, stat;
   DBuf<int> f_posidx, f_isfront, f_seg_len, f_seg_dep, f_segpos, f_minslot, f_first_waiter, f_next_waiter, f_cut, f_queue, f_A, f_A2, f_Mn, f_Mn2, f_oncyc, f_cid;
+  DBuf<double> rows, b_goal; DBuf<int> b_flags;
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DevFlow df; int flow_grid = 0; FlowCtl* h_ctl = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
@@ -500,7 +502,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->stat.alloc(16)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
   for (DBuf<int>* b : {&c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_first_waiter, &c->f_next_waiter, &c->f_cut,
                        &c->f_queue, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
-  CK(c->f_rootkey.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
+  CK(c->f_rootkey.alloc(cap)); CK(c->rows.alloc((size_t)cap * kRowD)); CK(c->b_goal.alloc(cap)); CK(c->b_flags.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
   { int nb = 0, sms = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow, 128, 0)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     c->flow_grid = std::max(1, nb) * std::max(1, sms); }
   c->f_queue.free(); CK(c->f_queue.alloc(cap + (size_t)c->flow_grid * 4 + 64));   // one ticket per worker beyond the last segment
@@ -538,7 +540,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
                           &c->sl_prop, &c->next_sortie, &c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre,
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
-  c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free();
+  c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_stat) cudaFreeHost(c->h_stat);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
@@ -620,9 +622,9 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
 }
 
 // per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
-enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_SEG, KID_FOLLOW, KID_LOOP, KID_ENTRIES, KID_FINAL, KID_COUNT };
+enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_COUNT };
 static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_seg", "k_flow",
-                                              "k_cyc_loops", "k_entries", "k_final"};
+                                              "k_cyc_loops", "k_place", "k_entries", "k_final"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
 #define LAUNCH(c) ((c)->launches++)
@@ -690,8 +692,8 @@ static int do_step(symgpu_ctx* c) {
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
     KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
-    KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->counters.p); KEND(c);
-    KBEGIN(c, KID_CONTEXT); k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, n, c->lane_tail.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c);
+    KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); KEND(c);
+    KBEGIN(c, KID_CONTEXT); k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dl, n, c->lane_tail.p, c->f_posidx.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c);
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
@@ -703,7 +705,7 @@ static int do_step(symgpu_ctx* c) {
       KBEGIN(c, KID_FOLLOW);
       k_flow_reset<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted); LAUNCH(c);
       k_flow_init<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted); LAUNCH(c);
-      k_flow<<<c->flow_grid, 128, 0, s>>>(c->dn, c->dv, c->dl, c->df, c->t);
+      k_flow<<<c->flow_grid, 128, 0, s>>>(c->dn, c->dv, c->dl, c->df, c->rows.p, c->b_goal.p, c->b_flags.p, c->t);
       KEND(c);
       c->passes++;
       CK(cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s));
@@ -719,9 +721,10 @@ static int do_step(symgpu_ctx* c) {
       int flip = 0;
       for (int k = 0; k < Klev; k++) { k_cyc_double<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c); flip ^= 1; }
       k_cyc_mark<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c);
-      k_cyc_break<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, c->counters.p);
+      k_cyc_break<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, c->rows.p, n_sorted, c->counters.p);
       KEND(c);
     }
+    KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t); KEND(c);
     }
     if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
                                                                     (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }

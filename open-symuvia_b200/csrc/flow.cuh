@@ -18,6 +18,7 @@
 //                the estimated leader speed, NewellCarFollowing.cpp:217-230); then the flow restarts.
 #pragma once
 #include "micro.cuh"
+#include "rows.cuh"
 
 namespace symb200 {
 
@@ -43,7 +44,6 @@ __global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, c
   int cur = -1, nseg = 0, len = 0, mn = 0x7fffffff;
   for (int a = n - 1; a >= 0; a--) {
     int p = s + a; int x = F.order[p];
-    F.posidx[x] = p;
     int d = V.ctx_leader[x];
     bool front = (a == n - 1) || d != F.order[p + 1];
     if (front) {
@@ -89,57 +89,94 @@ __global__ void k_flow_init(DevVeh V, DevFlow F, int n_sorted) {
   }
 }
 
-// persistent workers
-__global__ void __launch_bounds__(128) k_flow(DevNet N, DevVeh V, DevLaneDyn LD, DevFlow F, double inst) {
-  const int lane = threadIdx.x & 31;
-  int seg = -1;                                    // segment handed over by the previous one (lane 0 only)
+// persistent workers.  Rows of a segment are contiguous (descending order position): the warp stages them in shared
+// memory with coalesced 256-byte loads and lane 0 runs phase B down the chain out of shared memory.  While lane 0
+// computes, lanes 1..31 already stage the rows of the first segment waiting on this one (the waiter lists are frozen
+// once k_flow_init has run), which the same worker continues with: along a dependency chain no queue, fence or
+// global-memory round trip sits between two segments.
+constexpr int kBufRows = 16;
+__global__ void __launch_bounds__(128) k_flow(DevNet N, DevVeh V, DevLaneDyn LD, DevFlow F, const double* __restrict__ rows,
+                                              double* b_goal, int* b_flags, double inst) {
+  __shared__ double srow[4][2][kBufRows][kRowD];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int seg = -1, len = 0, buf = 0;
+  bool loaded = false;
   for (;;) {
-    if (lane == 0 && seg < 0) {                    // take a ticket
-      int t = atomicAdd(&F.ctl->q_head, 1);
-      for (;;) {
-        int v = *(volatile int*)&F.queue[t];
-        if (v >= 0) { seg = v; break; }
-        int c = *(volatile int*)&F.ctl->n_completed;
-        int st = *(volatile int*)&F.ctl->n_started;
-        int q = *(volatile int*)&F.ctl->n_pushed;
-        if (c == st && t >= q) { seg = -1; break; }   // everything scheduled has completed: no work will ever come
-        __nanosleep(64);
+    if (seg < 0) {
+      if (lane == 0) {                             // take a ticket
+        int t = atomicAdd(&F.ctl->q_head, 1);
+        for (;;) {
+          int v = *(volatile int*)&F.queue[t];
+          if (v >= 0) { seg = v; break; }
+          int c = *(volatile int*)&F.ctl->n_completed;
+          int st = *(volatile int*)&F.ctl->n_started;
+          int q = *(volatile int*)&F.ctl->n_pushed;
+          if (c == st && t >= q) { seg = -1; break; }   // everything scheduled has completed: no work will ever come
+          __nanosleep(32);
+        }
       }
+      seg = __shfl_sync(0xffffffffu, seg, 0);
+      if (seg < 0) return;
+      loaded = false;
     }
-    seg = __shfl_sync(0xffffffffu, seg, 0);
-    if (seg < 0) return;
-    const int len = F.seg_len[seg];
-    // lanes 1..31 pull the rows of the next vehicles of the segment towards L2/L1 while lane 0 computes
-    if (lane > 0 && lane < len) {
-      int x = F.order[seg - lane];
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_gap[x]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_dfree[x]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_dn0[x]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.ctx_lane[x * kMaxCtx]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.pos[x]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&V.vit[x]));
+    if (!loaded) {
+      len = F.seg_len[seg];
+      const int cnt = min(len, kBufRows);
+      for (int j = 0; j < cnt; j++) srow[w][buf][j][lane] = __ldcg(&rows[(size_t)(seg - j) * kRowD + lane]);
+      __syncwarp();
     }
-    if (lane == 0) {
-      __threadfence();                             // acquire: state written by the segment we waited for
-      for (int k = 0; k < len; k++) {
-        int x = F.order[seg - k];
-        follow_one(cP_ref(), N, V, LD, x, !F.cut[x], inst);
+    int h = -1, hlen = 0;
+    if (lane != 0) {                               // stage the successor
+      h = F.first_waiter[seg];
+      if (h >= 0) {
+        hlen = F.seg_len[h];
+        const int cnt = min(hlen, kBufRows);
+        for (int j = 0; j < cnt; j++) {
+          srow[w][buf ^ 1][j][lane] = __ldcg(&rows[(size_t)(h - j) * kRowD + lane]);
+          if (lane == 1) srow[w][buf ^ 1][j][0] = __ldcg(&rows[(size_t)(h - j) * kRowD]);
+        }
+      }
+    } else {                                       // phase B down the segment
+      int prev_x = -1; double prev_v0 = 0;
+      for (int j = 0; j < len; j++) {
+        const int p = seg - j;
+        const double* r = j < kBufRows ? srow[w][buf][j] : rows + (size_t)p * kRowD;
+        const int hdr = hi32(r[R_I0]); const int x = lo32(r[R_I1]);
+        const bool uncomputed_leader = j == 0 && (hi32(r[R_I1]) & 1);
+        if (hdr & H_SLOW) {
+          follow_one(cP_ref(), N, V, LD, x, !uncomputed_leader, inst);
+          b_flags[p] = B_SLOWDONE; prev_x = x; prev_v0 = V.vit_n[x];
+        } else {
+          const int L = lo32(r[R_I0]);
+          double vL = 0;
+          if (L >= 0) vL = uncomputed_leader ? r[R_VLEST] : (L == prev_x ? prev_v0 : __ldcg(&V.vit_n[L]));
+          BOut o = phase_b(cP_ref(), r, vL, inst);
+          V.vit_n[x] = o.v0; b_goal[p] = o.goal; b_flags[p] = o.flags; V.dn[x] = o.dn_end; V.cpos[x] = o.cpos;
+          prev_x = x; prev_v0 = o.v0;
+        }
         V.computed[x] = 1;
       }
-      __threadfence();                             // release
-      int h = atomicExch(&F.first_waiter[seg], kDone);
-      int mine = -1;
-      while (h >= 0) {
-        int nx = F.next_waiter[h];
-        if (mine < 0) { mine = h; atomicAdd(&F.ctl->n_started, 1); } else flow_push(F, h);
-        h = nx;
-      }
-      atomicAdd(&F.ctl->n_vehicles_done, len);
-      __threadfence();
-      atomicAdd(&F.ctl->n_completed, 1);
-      seg = mine;
     }
+    __syncwarp();
+    h = __shfl_sync(0xffffffffu, h, 1); hlen = __shfl_sync(0xffffffffu, hlen, 1);
+    if (lane == 0) {
+      if (h >= 0) {
+        atomicAdd(&F.ctl->n_started, 1);           // the first waiter continues on this worker
+        int o = F.next_waiter[h];
+        while (o >= 0) { int nx = F.next_waiter[o]; flow_push(F, o); o = nx; }   // the others go through the queue (release inside)
+      }
+      F.first_waiter[seg] = kDone;
+      atomicAdd(&F.ctl->n_vehicles_done, len);
+      atomicAdd(&F.ctl->n_completed, 1);
+    }
+    seg = h; len = hlen; buf ^= 1; loaded = h >= 0;
   }
+}
+// phase C for every vehicle of a lane (parallel)
+__global__ void k_place(DevNet N, DevVeh V, const double* rows, const double* b_goal, const int* b_flags, int n_sorted, double inst) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  phase_c(cP_ref(), N, V, rows, b_goal, b_flags, p, inst);
 }
 
 // ---- loop detection on the remaining segments ----------------------------------------------------------------
@@ -174,7 +211,7 @@ __global__ void k_cyc_mark(DevFlow F, int n_sorted, int flip) {
   atomicMin(&F.rootkey[id], key);
 }
 // one thread per loop: cut it where the reference's recursion would
-__global__ void k_cyc_break(DevVeh V, DevFlow F, int n_sorted, long long* counters) {
+__global__ void k_cyc_break(DevVeh V, DevFlow F, double* rows, int n_sorted, long long* counters) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
   if (!F.oncyc[p] || F.cid[p] != p) return;        // representative = smallest segment of the loop
@@ -195,6 +232,7 @@ __global__ void k_cyc_break(DevVeh V, DevFlow F, int n_sorted, long long* counte
   F.cut[Y] = 1;
   if (cP_ref().cls[V.cls[Y]].law == 0) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_LOOPS], 1ULL);
   int py = F.posidx[Y];
+  ((int*)&rows[(size_t)py * kRowD + R_I1])[1] |= 1;   // row header: leader stays uncomputed (little endian: high int)
   if (!F.isfront[py]) {                            // split e below X: [rear .. Y] becomes a segment of its own
     int rear = e - F.seg_len[e] + 1;
     F.isfront[py] = 1; F.seg_len[py] = py - rear + 1; F.seg_len[e] = e - py; F.seg_dep[py] = X; F.first_waiter[py] = -1;

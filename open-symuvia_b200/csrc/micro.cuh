@@ -112,8 +112,13 @@ __device__ inline int memo_touch(int* memo, int lane) {
 // (NewellCarFollowing.cpp:70-111), and the CalculNextVoie side effects of Vehicule::CalculTraficFeux
 // (vehicule.cpp:1854-1874).  `own_leader` = nearest vehicle ahead on the own lane (-1 none).
 // Returns the number of random draws consumed.
+__device__ inline void build_row(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, double* rows, int p, int i,
+                                 const int* lanes, int nl, int L, double gap, double dn0, double dfree, bool created, double start,
+                                 double cpos, double dtv);
+// rows != nullptr: also pack the vehicle's phase-B row at order position p (rows.cuh); the per-vehicle ctx_* arrays are
+// then only written for contexts the row cannot hold (general path).
 __device__ inline int context_one(const DevParams& P, const DevNet& n, const DevVeh& V, const int* lane_tail, int i,
-                                  int own_leader, int* overflow) {
+                                  int own_leader, int* overflow, double* rows = nullptr, int p = -1, const DevLaneDyn* LD = nullptr) {
   const DevCls& c = P.cls[V.cls[i]];
   double p1 = snap_pos(V.pos[i]);
   bool created = p1 <= SYM_UNDEF;                                         // vehicule.cpp:1235
@@ -199,11 +204,15 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
     }
     dfree = trav;
   }
-  for (int k = 0; k < kMemo; k++) V.memo[i * kMemo + k] = memo[k];
-  V.ctx_nl[i] = nl;
-  for (int k = 0; k < nl; k++) V.ctx_lane[i * kMaxCtx + k] = lanes[k];
-  V.ctx_leader[i] = leader; V.ctx_gap[i] = gap; V.ctx_dn0[i] = dn0; V.ctx_dfree[i] = dfree;
-  V.ctx_flags[i] = created ? 1 : 0;
+  if (draws) for (int k = 0; k < kMemo; k++) V.memo[i * kMemo + k] = memo[k];
+  V.ctx_leader[i] = leader;
+  if (!rows || nl > 4) {
+    V.ctx_nl[i] = nl;
+    for (int k = 0; k < nl; k++) V.ctx_lane[i * kMaxCtx + k] = lanes[k];
+    V.ctx_gap[i] = gap; V.ctx_dn0[i] = dn0; V.ctx_dfree[i] = dfree;
+    V.ctx_flags[i] = created ? 1 : 0;
+  }
+  if (rows) build_row(P, n, V, *LD, rows, p, i, lanes, nl, leader, gap, dn0, dfree, created, start, cpos, dtv);
   return draws;
 }
 
