@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libSymuViaB200.so")
+LIB_PATH = os.environ.get("SYMB200_LIB", os.path.join(_HERE, "libSymuViaB200.so"))   # override only for A/B experiments
 _LIB = None
 
 CNT_TIES, CNT_LOOPS, CNT_CREATED, CNT_PASSES, CNT_LAUNCHES, CNT_SLOTS, CNT_CTX_OVERFLOW = range(7)

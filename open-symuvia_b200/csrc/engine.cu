@@ -454,6 +454,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
     k.w = r[0]; k.kx = r[1]; k.vx = r[2]; k.esp = r[3]; k.decel = r[4]; k.tau_lc = r[5]; k.pi_rab = r[6]; k.law = (int)r[7]; k.nplage = std::min(4, (int)r[8]);
     for (int j = 0; j < k.nplage; j++) { k.ax[j] = r[9 + 2 * j]; k.vs[j] = r[10 + 2 * j]; }
     double kv = -k.kx * k.w / (k.vx - k.w); if (kv < P.min_kv) P.min_kv = kv; }     // Reseau::GetMinKv reseau.cpp:9719-9737
+  for (int i = 0; i < T; i++) P.maxinf[i] = max_influence(P, P.cls[i]);
   CK(cudaMemcpyToSymbol(cP, &P, sizeof(P)));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));

@@ -95,7 +95,7 @@ __global__ void k_flow_init(DevVeh V, DevFlow F, int n_sorted) {
 // once k_flow_init has run), which the same worker continues with: along a dependency chain no queue, fence or
 // global-memory round trip sits between two segments.
 constexpr int kBufRows = 16;
-__global__ void __launch_bounds__(128) k_flow(DevNet N, DevVeh V, DevLaneDyn LD, DevFlow F, const double* __restrict__ rows,
+__global__ void __launch_bounds__(128, 3) k_flow(DevNet N, DevVeh V, DevLaneDyn LD, DevFlow F, const double* __restrict__ rows,
                                               double* b_goal, int* b_flags, double inst) {
   __shared__ double srow[4][2][kBufRows][kRowD];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

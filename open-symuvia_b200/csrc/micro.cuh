@@ -27,7 +27,7 @@ enum : int { F_HASCTX = 1, F_PREVFREE = 2 };
 enum : int { O_FLUIDE = 1, O_FEU = 2, O_CTXFREE = 4, O_ENDLEG = 16, O_CREATED = 32, O_LINK1NULL = 64 };
 
 struct DevCls { double w, kx, vx, esp, decel, tau_lc, pi_rab; int law, nplage; double ax[4], vs[4]; };
-struct DevParams { double dt, relax, duree, min_kv, bevel; int accbornee, ncls; DevCls cls[kMaxCls]; };
+struct DevParams { double dt, relax, duree, min_kv, bevel; int accbornee, ncls; DevCls cls[kMaxCls]; double maxinf[kMaxCls]; };
 
 struct DevNet {
   const int *lane_link, *lane_num, *lane_prev, *lane_flags; const double* lane_len;
@@ -52,14 +52,14 @@ struct DevLaneDyn { int *count, *start, *fill, *tail, *head_done; double* next_s
 __device__ __forceinline__ double snap_pos(double p) {           // vehicule.cpp:995-997
   return (p != SYM_UNDEF && fabs(p) < 0.00001) ? 0.0 : p;
 }
-__device__ __forceinline__ double acc_max(const DevCls& c, double v) {   // vehicule.cpp:157-175
+__host__ __device__ __forceinline__ double acc_max(const DevCls& c, double v) {   // vehicule.cpp:157-175
   for (int i = 0; i < c.nplage; i++) if (v <= c.vs[i] + 0.000001) return c.ax[i];
   return c.nplage ? c.ax[c.nplage - 1] : 0.0;
 }
 __device__ __forceinline__ double len_ex(const DevParams& P, const DevNet& n, int lane) {   // voie.cpp:1451-1457
   return (n.lane_flags[lane] & 1) ? n.lane_len[lane] - P.bevel : n.lane_len[lane];
 }
-__device__ __forceinline__ double max_influence(const DevParams& P, const DevCls& c) {
+__host__ __device__ __forceinline__ double max_influence(const DevParams& P, const DevCls& c) {
   if (c.law == 0) return 1.0 / P.min_kv;                                  // NewellCarFollowing.cpp:48-51
   if (c.law == 1) return 3 * c.vx * P.dt;                                 // GippsCarFollowing.cpp:45-48
   double dec = c.decel; if (dec == 0) dec = DBL_MAX;                      // IDMCarFollowing.cpp:49-59
@@ -206,7 +206,7 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
   }
   if (draws) for (int k = 0; k < kMemo; k++) V.memo[i * kMemo + k] = memo[k];
   V.ctx_leader[i] = leader;
-  if (!rows || nl > 4) {
+  if (!rows || nl > 3) {
     V.ctx_nl[i] = nl;
     for (int k = 0; k < nl; k++) V.ctx_lane[i * kMaxCtx + k] = lanes[k];
     V.ctx_gap[i] = gap; V.ctx_dn0[i] = dn0; V.ctx_dfree[i] = dfree;

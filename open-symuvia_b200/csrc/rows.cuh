@@ -19,12 +19,16 @@
 namespace symb200 {
 
 constexpr int kRowD = 32;          // doubles per row (256 B)
-constexpr int kRowLanes = 4;       // context lanes held inline
-enum { R_DN0 = 0, R_GAP, R_DFREE, R_DTV, R_V1, R_VL1, R_START, R_CPOS, R_VLEST, R_GOALLAW, R_I0, R_I1, R_REC = 12 };
+constexpr int kRowLanes = 3;       // context lanes held inline
+// R_T0 = dn0/Kv(v1_L) (Newell) or the law's distance (Gipps/IDM); R_A = -Kx_L*w_L; R_Q1 = (dn0/(-Kx_self*w_L))/dtv: the terms of
+// ComputeRelaxationEvolution / ComputeCongestedDistance (NewellCarFollowing.cpp:113-136, :358-395) that do not involve the
+// leader's new speed are evaluated in phase A with the same operations, so phase B only keeps the dependent ones.
+enum { R_DN0 = 0, R_GAP, R_DFREE, R_DTV, R_V1, R_VL1, R_START, R_CPOS, R_VLEST, R_T0, R_I0, R_I1, R_A, R_WL, R_Q1, R_ALPHA, R_SPARE, R_REC = 17 };
+constexpr int R_GOALLAW = R_T0;
 constexpr int kRecD = 5;           // llen, pf, prop, ts, ints(lane, flags)
 enum { RF_STOPEND = 1, RF_EXIT = 2, RF_SL = 4, RF_COLSHIFT = 4 };
 // packed header flags (R_I0 high int)
-enum { H_CREATED = 1 << 12, H_SLOW = 1 << 15, H_LAWFREE = 1 << 16, H_LINK1NULL = 1 << 17 };
+enum { H_CREATED = 1 << 12, H_FLAGA = 1 << 13, H_FLAGB = 1 << 14, H_SLOW = 1 << 15, H_LAWFREE = 1 << 16, H_LINK1NULL = 1 << 17 };
 // phase B result flags
 enum { B_FLUIDE = 1, B_FEU = 2, B_CTXFREE = 4, B_CANCEL = 8, B_SLOWDONE = 16 };
 
@@ -80,8 +84,21 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
     }
     if (ctx_free) hdr |= H_LAWFREE;
   }
+  double t0 = goal_law, A = 0, wl = 0, q1 = 0, alpha = 0;
+  if (c.law == 0 && L >= 0) {
+    const DevCls& cl = P.cls[lcls];
+    double kv = -cl.kx * cl.w / (vL1 - cl.w);                              // NewellCarFollowing.cpp:117
+    t0 = dn0 / kv; A = -cl.kx * cl.w; wl = cl.w;
+    double r_self = dn0 / (-c.kx * cl.w);                                 // :120
+    q1 = r_self / dtv;
+    if ((P.dt - r_self) >= -0.0001) hdr |= H_FLAGA;                       // :128
+    double rr = dn0 / (-cl.kx * cl.w);                                    // :309
+    if ((P.dt - rr) >= -0.0001) hdr |= H_FLAGB;                           // :361
+    else alpha = -cl.w * cl.kx * P.dt / dn0;                              // :375
+  }
   r[R_DN0] = dn0; r[R_GAP] = gap; r[R_DFREE] = dfree; r[R_DTV] = dtv; r[R_V1] = v1; r[R_VL1] = vL1; r[R_START] = start; r[R_CPOS] = cpos;
-  r[R_VLEST] = vlest; r[R_GOALLAW] = goal_law; r[R_I0] = pack2(L, hdr); r[R_I1] = pack2(i, 0);
+  r[R_VLEST] = vlest; r[R_T0] = t0; r[R_I0] = pack2(L, hdr); r[R_I1] = pack2(i, 0);
+  r[R_A] = A; r[R_WL] = wl; r[R_Q1] = q1; r[R_ALPHA] = alpha;
   if (nl > kRowLanes) return;
   const int route = V.route[i], rpos = V.route_pos[i];
   for (int k = 0; k < nl; k++) {
@@ -127,22 +144,19 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const double* r, dou
   if (c.law == 0) {
     goal = r[R_DFREE];
     if (L >= 0) {
-      const DevCls& cl = P.cls[(hdr >> 4) & 15];
-      double kv = -cl.kx * cl.w / (vL1 - cl.w);                           // ComputeRelaxationEvolution NewellCarFollowing.cpp:113-136
-      double kvfin = -cl.kx * cl.w / (vL - cl.w);
-      double r_self = dn0 / (-c.kx * cl.w);
+      const double A = r[R_A];
+      double kvfin = A / (vL - r[R_WL]);                                  // NewellCarFollowing.cpp:118, :310
       double res;
-      if ((P.dt - r_self) >= -0.0001) res = fmin(1.0, (dn0 / kv + fmin(r_self / dtv * (vL - vL1) + P.relax, vL) * P.dt) * kvfin);
-      else res = fmin(1.0, (dn0 / kv + fmin((vL - vL1) + P.relax, vL) * P.dt) * kvfin);
+      if (hdr & H_FLAGA) res = fmin(1.0, (r[R_T0] + fmin(r[R_Q1] * (vL - vL1) + P.relax, vL) * P.dt) * kvfin);
+      else res = fmin(1.0, (r[R_T0] + fmin((vL - vL1) + P.relax, vL) * P.dt) * kvfin);
       double dn1 = fmax(dn0, res);
       dn_end = dn1;
-      double rr = dn0 / (-cl.kx * cl.w);
       double pc;
-      if ((P.dt - rr) >= -0.0001) {                                       // :361-371
+      if (hdr & H_FLAGB) {                                                // :361-371
         pc = gap + vL * P.dt - dn1 / kvfin;
         if (pc <= 0.0001 && dn0 < 1) { dn_end = dn0; pc = gap + vL * P.dt - dn0 / kvfin; }
       } else {                                                            // :373-395
-        double alpha = -cl.w * cl.kx * P.dt / dn0;
+        double alpha = r[R_ALPHA];
         if (dtv < P.dt) pc = gap + vL * P.dt - dn1 / kvfin;
         else { pc = alpha * gap + vL * P.dt - alpha * dn1 / kvfin;
           if (pc <= 0.0001 && dn0 < 1) { dn_end = dn0; pc = alpha * gap + vL * P.dt - alpha * dn0 / kvfin; } }
@@ -159,7 +173,7 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const double* r, dou
     double mini = DBL_MAX; bool infl = false;
     if (ep > llen && (fl & RF_STOPEND)) { fluide = false; infl = true; mini = fmin(mini, trav + llen - sp); }   // :1602-1616
     if (fl & RF_EXIT) {                                                   // :1636-1666
-      double pcrit = llen - max_influence(P, c);
+      double pcrit = llen - P.maxinf[hdr & 15];
       if (ep > pcrit) {
         double ts = q[3];
         if (ts < 0) { infl = true; mini = fmin(mini, trav + pcrit - sp); }

@@ -852,6 +852,7 @@ struct Sim {
   // ------------------------------------------------------------------------------------------
   // Reseau::SimuTrafic reseau.cpp:2028-2428 + SimuTraficMicroMacro :14152-14470
   int step() {
+    max_depth = 0;
     t += dt; ninst++;                                                                        // :2105-2106
     for (auto& e : entries) update_crit_creation_step(e);                                   // :2219-2223
     activate_api_vehicles(t);                                                                // :2233-2240
