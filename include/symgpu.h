@@ -41,6 +41,12 @@ int symgpu_run(symgpu_ctx* c, int n_steps);
  * Vehicule::SortieTrafic (vehicule.cpp:1993-2176) hands to DocTrafic::AddTrajectoire.  Returns rows written. */
 int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
 
+/* Asynchronous form (north_star: "trajectory output is copied back asynchronously on a side stream"): bind two caller
+ * buffers once (they are page-locked in place), then alternate them; the copy of step k overlaps the computation of k+1. */
+int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
+int symgpu_step_traj_async(symgpu_ctx* c, int which);   /* returns rows, valid after symgpu_traj_wait(which) */
+int symgpu_traj_wait(symgpu_ctx* c, int which);
+
 /* Per-kernel device timing (CUDA events on the step stream) for roofline accounting. */
 int symgpu_profile(symgpu_ctx* c, int enable);
 int symgpu_kernel_count(void);

@@ -37,6 +37,9 @@ def lib():
         L.symgpu_step.argtypes = [vp]
         L.symgpu_run.argtypes = [vp, ci]
         L.symgpu_step_traj.argtypes = [vp, ci, vp, vp, vp, vp, vp]
+        L.symgpu_traj_bind.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
+        L.symgpu_step_traj_async.argtypes = [vp, ci]
+        L.symgpu_traj_wait.argtypes = [vp, ci]
         L.symgpu_num_vehicles.argtypes = [vp]
         L.symgpu_time.argtypes = [vp]
         L.symgpu_time.restype = cd
@@ -126,6 +129,19 @@ class Engine:
         """One step + trajectory rows into preallocated host arrays (id, lane, pos, vit, acc)."""
         return self._chk(self.L.symgpu_step_traj(self.h, len(bufs["id"]), _p(bufs["id"]), _p(bufs["lane"]), _p(bufs["pos"]),
                                                  _p(bufs["vit"]), _p(bufs["acc"])))
+
+    def traj_bind(self, which: int, bufs):
+        """Registers host arrays (id, lane, pos, vit, acc) as trajectory buffer 0 or 1 (page-locked in place)."""
+        self._keep = getattr(self, "_keep", {})
+        self._keep[which] = bufs
+        return self._chk(self.L.symgpu_traj_bind(self.h, which, len(bufs["id"]), _p(bufs["id"]), _p(bufs["lane"]), _p(bufs["pos"]),
+                                                 _p(bufs["vit"]), _p(bufs["acc"])))
+
+    def step_traj_async(self, which: int) -> int:
+        return self._chk(self.L.symgpu_step_traj_async(self.h, which))
+
+    def traj_wait(self, which: int):
+        self._chk(self.L.symgpu_traj_wait(self.h, which))
 
     def link_counts(self):
         n = self.L.symgpu_num_links(self.h) * self.L.symgpu_num_classes(self.h)

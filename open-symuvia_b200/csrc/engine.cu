@@ -306,6 +306,19 @@ __global__ void k_exit_lanes(DevVeh V, const int* exit_lanes, const double* exit
   next_sortie[ln] = r;
 }
 
+// Trajectory rows for the writers (Vehicule::SortieTrafic vehicule.cpp:1993-2176): alive vehicles in m_LstVehicles order,
+// packed contiguously so that one asynchronous copy per field brings them to the host.
+__global__ void k_alive_flags(const int* status, int n, int* flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = status[i] == ST_ALIVE;
+}
+__global__ void k_pack_traj(DevVeh V, int n, const int* flag, const int* off, int* o_id, int* o_lane, double* o_pos, double* o_vit, double* o_acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  int k = off[i];
+  o_id[k] = V.id[i]; o_lane[k] = V.lane[i]; o_pos[k] = V.pos[i]; o_vit[k] = V.vit[i]; o_acc[k] = V.acc[i];
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -366,6 +379,9 @@ struct symgpu_ctx {
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
+  // trajectory output: packed device rows + side stream + caller buffers registered for direct DMA (two in flight)
+  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr};
+  struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
@@ -458,6 +474,8 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(cudaMemcpyToSymbol(cP, &P, sizeof(P)));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->t_ready, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->t_done[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->t_done[1], cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_stat, 16 * sizeof(int)));
   // static tables
   CK(c->lane_link.upload(col(f.lane_i, 4, 0))); CK(c->lane_num.upload(col(f.lane_i, 4, 1))); CK(c->lane_prev.upload(col(f.lane_i, 4, 2)));
@@ -503,6 +521,8 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->stat.alloc(16)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
   for (DBuf<int>* b : {&c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_first_waiter, &c->f_next_waiter, &c->f_cut,
                        &c->f_queue, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
+  CK(c->t_flag.alloc(cap)); CK(c->t_off.alloc(cap)); CK(c->t_bsum.alloc(cap / kScanB + 2)); CK(c->t_id.alloc(cap)); CK(c->t_lane.alloc(cap));
+  CK(c->t_pos.alloc(cap)); CK(c->t_vit.alloc(cap)); CK(c->t_acc.alloc(cap));
   CK(c->f_rootkey.alloc(cap)); CK(c->rows.alloc((size_t)cap * kRowD)); CK(c->b_goal.alloc(cap)); CK(c->b_flags.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
   { int nb = 0, sms = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow, 128, 0)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     c->flow_grid = std::max(1, nb) * std::max(1, sms); }
@@ -541,6 +561,9 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
                           &c->sl_prop, &c->next_sortie, &c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre,
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
+  for (int k = 0; k < 2; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
+  c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
+  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); for (int k = 0; k < 2; k++) if (c->t_done[k]) cudaEventDestroy(c->t_done[k]);
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_stat) cudaFreeHost(c->h_stat);
@@ -818,10 +841,61 @@ extern "C" int symgpu_get_state(symgpu_ctx* c, int cap, int* id, int* lane, int*
   }
   return (int)slots.size();
 }
-extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc) {
+// Caller buffers for trajectory rows: page-locked in place so the device copies straight into them.
+extern "C" int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, double* pos, double* vit, double* acc) {
+  if (!c || which < 0 || which > 1 || cap <= 0 || !id || !lane || !pos || !vit || !acc) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  auto& b = c->tbuf[which];
+  if (b.registered) { cudaHostUnregister(b.id); cudaHostUnregister(b.lane); cudaHostUnregister(b.pos); cudaHostUnregister(b.vit); cudaHostUnregister(b.acc); b.registered = false; }
+  b.cap = cap; b.id = id; b.lane = lane; b.pos = pos; b.vit = vit; b.acc = acc;
+  bool ok = cudaHostRegister(id, (size_t)cap * 4, cudaHostRegisterDefault) == cudaSuccess && cudaHostRegister(lane, (size_t)cap * 4, cudaHostRegisterDefault) == cudaSuccess &&
+            cudaHostRegister(pos, (size_t)cap * 8, cudaHostRegisterDefault) == cudaSuccess && cudaHostRegister(vit, (size_t)cap * 8, cudaHostRegisterDefault) == cudaSuccess &&
+            cudaHostRegister(acc, (size_t)cap * 8, cudaHostRegisterDefault) == cudaSuccess;
+  cudaGetLastError();
+  b.registered = ok;          // not registered (already pinned by the caller, or refused): the copies still work, staged by the driver
+  return SYMGPU_OK;
+}
+// One step, then pack + copy the trajectory rows to bound buffer `which` on the side stream (returns rows; the rows are
+// valid after symgpu_traj_wait(which)).  The next step can run while the copy is in flight.
+extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
+  if (!c || which < 0 || which > 1 || !c->tbuf[which].id) return SYMGPU_E_ARG;
   int r = symgpu_step(c);
   if (r < 0) return r;
-  return symgpu_get_state(c, cap, id, lane, nullptr, nullptr, pos, vit, acc, nullptr, nullptr);
+  auto& b = c->tbuf[which];
+  const int n = c->n_slots; const int rows = c->n_alive;
+  if (rows > b.cap) { g_err = "trajectory buffer too small"; return SYMGPU_E_CAPACITY; }
+  if (n > 0) {
+    cudaStream_t s = c->stream; const int B = 256; int G = (n + B - 1) / B; int nb = (n + kScanB - 1) / kScanB;
+    k_alive_flags<<<G, B, 0, s>>>(c->v_status.p, n, c->t_flag.p); LAUNCH(c);
+    k_scan_block<<<nb, kScanB, 0, s>>>(c->t_flag.p, c->t_off.p, c->t_bsum.p, n); LAUNCH(c);
+    if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->t_bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->t_off.p, c->t_bsum.p, n); LAUNCH(c); }
+    CK(cudaStreamWaitEvent(s, c->t_done[which ^ 1], 0));        // the packed rows are reused: the previous copy must have left
+    k_pack_traj<<<G, B, 0, s>>>(c->dv, n, c->t_flag.p, c->t_off.p, c->t_id.p, c->t_lane.p, c->t_pos.p, c->t_vit.p, c->t_acc.p); LAUNCH(c);
+    CK(cudaEventRecord(c->t_ready, s));
+    CK(cudaStreamWaitEvent(c->side, c->t_ready, 0));
+    CK(cudaMemcpyAsync(b.id, c->t_id.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->side));
+    CK(cudaMemcpyAsync(b.lane, c->t_lane.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->side));
+    CK(cudaMemcpyAsync(b.pos, c->t_pos.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, c->side));
+    CK(cudaMemcpyAsync(b.vit, c->t_vit.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, c->side));
+    CK(cudaMemcpyAsync(b.acc, c->t_acc.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, c->side));
+  }
+  CK(cudaEventRecord(c->t_done[which], c->side));
+  return rows;
+}
+extern "C" int symgpu_traj_wait(symgpu_ctx* c, int which) {
+  if (!c || which < 0 || which > 1) return SYMGPU_E_ARG;
+  CK(cudaEventSynchronize(c->t_done[which]));
+  return SYMGPU_OK;
+}
+// Synchronous convenience form: step, copy the rows into the caller's (pageable or pinned) buffers, return rows.
+extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc) {
+  if (!c) return SYMGPU_E_ARG;
+  auto saved = c->tbuf[0];
+  c->tbuf[0] = symgpu_ctx::TrajBuf(); c->tbuf[0].cap = cap; c->tbuf[0].id = id; c->tbuf[0].lane = lane; c->tbuf[0].pos = pos; c->tbuf[0].vit = vit; c->tbuf[0].acc = acc;
+  int r = symgpu_step_traj_async(c, 0);
+  if (r >= 0) { int w = symgpu_traj_wait(c, 0); if (w < 0) r = w; }
+  c->tbuf[0] = saved;
+  return r;
 }
 extern "C" int symgpu_profile(symgpu_ctx* c, int enable) { if (!c) return SYMGPU_E_ARG; c->profile = enable != 0; for (int k = 0; k < 16; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return SYMGPU_OK; }
 extern "C" int symgpu_kernel_count(void) { return KID_COUNT; }

@@ -123,3 +123,28 @@ def test_c4_full_size_prefix_and_invariants(synth, pkg):
         assert (np.diff(st["pos"][order])[same] >= 0).all()
     assert g.counter(pkg.CNT_CTX_OVERFLOW) == 0
     g.close()
+
+
+def test_trajectory_rows_sync_and_async(synth, pkg, tmp_path):
+    """symgpu_step_traj / symgpu_step_traj_async deliver exactly the state rows, in m_LstVehicles order."""
+    b = synth.grid(n=4, n_steps=100, demand_per_lane=0.3, preseed_per_lane=6, shuffle=True)
+    p = str(tmp_path / "t.symflat")
+    b.write(p)
+    g = pkg.Engine(p)
+    cap = 20000
+    mk = lambda: {"id": np.zeros(cap, np.int32), "lane": np.zeros(cap, np.int32), "pos": np.zeros(cap), "vit": np.zeros(cap), "acc": np.zeros(cap)}
+    bufs = [mk(), mk()]
+    g.traj_bind(0, bufs[0]); g.traj_bind(1, bufs[1])
+    for k in range(40):
+        w = k & 1
+        rows = g.step_traj_async(w)
+        g.traj_wait(w)
+        st = g.state()
+        assert rows == len(st["id"])
+        for key in ("id", "lane", "pos", "vit", "acc"):
+            assert np.array_equal(bufs[w][key][:rows], st[key]), (k, key)
+    one = mk()
+    rows = g.step_traj(one)
+    st = g.state()
+    assert rows == len(st["id"]) and np.array_equal(one["pos"][:rows], st["pos"]) and np.array_equal(one["id"][:rows], st["id"])
+    g.close()
