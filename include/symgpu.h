@@ -47,6 +47,16 @@ int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, doub
 int symgpu_step_traj_async(symgpu_ctx* c, int which);   /* returns rows, valid after symgpu_traj_wait(which) */
 int symgpu_traj_wait(symgpu_ctx* c, int which);
 
+/* Partitioned runs: one process per GPU, network tables replicated, vehicles owned by the rank that owns their lane.
+ * The caller moves the device buffers between ranks (NCCL send/recv through torch.distributed in the Python mirror).
+ * A follower whose leader is the tail of a lane owned by another rank uses the reference's estimated leader speed
+ * (NewellCarFollowing.cpp:217-230) instead of the leader's new speed: see DESIGN.md "multi-GPU". */
+int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int* node_part);
+int symgpu_mp_sizes(symgpu_ctx* c, int* export_cnt, int* halo_cnt);                 /* tail records per peer (4 doubles each) */
+int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails);
+int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, double* send_rows, int cap_per_peer, int* send_counts);
+int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows);          /* rows of 16 doubles */
+
 /* Per-kernel device timing (CUDA events on the step stream) for roofline accounting. */
 int symgpu_profile(symgpu_ctx* c, int enable);
 int symgpu_kernel_count(void);

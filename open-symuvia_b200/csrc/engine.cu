@@ -319,6 +319,57 @@ __global__ void k_pack_traj(DevVeh V, int n, const int* flag, const int* off, in
   o_id[k] = V.id[i]; o_lane[k] = V.lane[i]; o_pos[k] = V.pos[i]; o_vit[k] = V.vit[i]; o_acc[k] = V.acc[i];
 }
 
+// ---- partitioned runs ------------------------------------------------------------------------------------------------
+// tails of the lanes this GPU owns and another GPU looks into (first vehicle a follower arriving from upstream would meet)
+__global__ void k_mp_pack_tails(DevVeh V, const int* export_lanes, int n, const int* lane_tail, double* out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int t = lane_tail[export_lanes[k]];
+  double* o = out + 4 * (size_t)k;
+  if (t < 0) { o[0] = __hiloint2double(0, -1); o[1] = 0; o[2] = 0; o[3] = 0; }
+  else { o[0] = __hiloint2double(V.cls[t], V.id[t]); o[1] = V.pos[t]; o[2] = V.vit[t]; o[3] = 0; }
+}
+__global__ void k_mp_unpack_ghosts(DevVeh V, const int* halo_lanes, int n, int ghost_base, int* lane_tail, const double* in) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double* o = in + 4 * (size_t)k;
+  int id = __double2loint(o[0]); int g = ghost_base + k; int ln = halo_lanes[k];
+  if (id < 0) { V.status[g] = ST_DEAD; lane_tail[ln] = -1; return; }
+  V.status[g] = ST_GHOST; V.id[g] = id; V.cls[g] = __double2hiint(o[0]); V.lane[g] = ln; V.pos[g] = o[1]; V.vit[g] = o[2];
+  lane_tail[ln] = g;
+}
+// vehicles that ended the step on a lane owned by another GPU leave with their whole state (16 doubles per row)
+constexpr int kMigD = 16;
+__global__ void k_mp_pack_migrants(DevVeh V, int n, const int* lane_owner, int rank, int cap_per_peer, int* count, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || V.status[i] != ST_ALIVE) return;
+  int q = lane_owner[V.lane[i]];
+  if (q == rank) return;
+  int k = atomicAdd(&count[q], 1);
+  if (k < cap_per_peer) {
+    double* o = out + ((size_t)q * cap_per_peer + k) * kMigD;
+    o[0] = __hiloint2double(V.cls[i], V.id[i]); o[1] = __hiloint2double(V.route_pos[i], V.route[i]); o[2] = __hiloint2double(V.prev_leader[i], V.lane[i]);
+    o[3] = __hiloint2double(V.oflags[i], V.flags[i]); o[4] = __hiloint2double(V.memo[i * kMemo + 1], V.memo[i * kMemo]); o[5] = __hiloint2double(V.memo[i * kMemo + 3], V.memo[i * kMemo + 2]);
+    o[6] = V.pos[i]; o[7] = V.vit[i]; o[8] = V.acc[i]; o[9] = V.dn[i]; o[10] = V.cpos[i]; o[11] = V.tcre[i]; o[12] = V.dstp[i]; o[13] = V.hent[i]; o[14] = V.tsort[i]; o[15] = 0;
+  }
+  V.status[i] = ST_DEAD;
+}
+__global__ void k_mp_unpack_migrants(DevVeh V, int slot0, int n, const double* in) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double* o = in + (size_t)k * kMigD; int i = slot0 + k;
+  V.status[i] = ST_ALIVE; V.id[i] = __double2loint(o[0]); V.cls[i] = __double2hiint(o[0]); V.route[i] = __double2loint(o[1]); V.route_pos[i] = __double2hiint(o[1]);
+  V.lane[i] = __double2loint(o[2]); V.lane_n[i] = V.lane[i]; V.prev_leader[i] = __double2hiint(o[2]); V.flags[i] = __double2loint(o[3]); V.oflags[i] = __double2hiint(o[3]);
+  V.memo[i * kMemo] = __double2loint(o[4]); V.memo[i * kMemo + 1] = __double2hiint(o[4]); V.memo[i * kMemo + 2] = __double2loint(o[5]); V.memo[i * kMemo + 3] = __double2hiint(o[5]);
+  V.pos[i] = o[6]; V.vit[i] = o[7]; V.acc[i] = o[8]; V.pos_n[i] = o[6]; V.vit_n[i] = o[7]; V.acc_n[i] = o[8];
+  V.dn[i] = o[9]; V.cpos[i] = o[10]; V.tcre[i] = o[11]; V.dstp[i] = o[12]; V.hent[i] = o[13]; V.tsort[i] = o[14];
+}
+__global__ void k_mp_drop_foreign(DevVeh V, int n, const int* lane_owner, int rank, int* kept) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || V.status[i] != ST_ALIVE) return;
+  if (lane_owner[V.lane[i]] != rank) V.status[i] = ST_DEAD; else atomicAdd(kept, 1);
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -384,6 +435,10 @@ struct symgpu_ctx {
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
+  struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
+  // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
+  struct Mp { bool on = false; int rank = 0, world = 1, ghost_base = 0, n_halo = 0, n_export = 0; std::vector<int> lane_owner, halo_lanes, halo_off, export_lanes, export_off;
+    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count; int mig_cap = 0; std::vector<int> h_mig_count; } mp;
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
 };
 
@@ -513,6 +568,8 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   size_t cap = (size_t)f.n_init() + (size_t)(budget * 1.25) + 2 * (size_t)(P.duree / P.dt) * (size_t)n_entry_lanes / 4 + 4096 + n_entry_lanes;
   if (const char* env = getenv("SYMGPU_CAPACITY")) cap = std::max(cap, (size_t)atoll(env));
   c->cap = (int)cap; c->pool_base = c->cap - c->n_pool;
+  const size_t ghost_reserve = std::min<size_t>((size_t)L, 65536);   // slots past `cap` for tail vehicles of lanes owned by other GPUs
+  c->mp.ghost_base = c->cap; cap += ghost_reserve;
   { int q = 0; for (auto& e : c->entries) for (auto& l : e.lanes) l.pool_base = c->pool_base + q++; }
   // dynamic lane / link state
   CK(c->lane_count.alloc(L)); CK(c->lane_start.alloc(L)); CK(c->lane_fill.alloc(L)); CK(c->lane_tail.alloc(L));
@@ -666,16 +723,17 @@ static void prof_collect(symgpu_ctx* c) {
   c->prof_recs.clear(); c->ev_used = 0;
 }
 
-static int do_step(symgpu_ctx* c) {
-  const int L = c->net.n_lanes(), T = c->net.n_cls(), K = c->net.n_links();
-  (void)K;
+// first half of a step: origins (host), signals, lane membership and in-lane order.  In a partitioned run the tails of
+// the boundary lanes are exchanged between the two halves.
+static int step_front(symgpu_ctx* c) {
+  const int L = c->net.n_lanes();
   cudaStream_t s = c->stream;
   const bool has_entries = !c->entries.empty();
+  auto& desc = c->ss.desc; auto& desc_lane = c->ss.desc_lane; desc.clear(); desc_lane.clear();
   c->t += c->P.dt;                                                                                  // reseau.cpp:2105
   // origins: criterion update (reseau.cpp:2219-2223) and creation (:2255); the device draws of the previous step
   // come first in the global random sequence
   std::vector<HostRow> new_rows; std::vector<EntryLane*> new_row_lane;
-  std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane;
   if (has_entries) {
     const double mdm = max_debit_max(c);
     for (auto& e : c->entries) update_crit(c, e, c->t, false, mdm);
@@ -717,11 +775,26 @@ static int do_step(symgpu_ctx* c) {
     KEND(c);
     KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
     KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); KEND(c);
+  }
+  c->ss.n = n; c->ss.n_sorted = n_sorted; c->ss.has_entries = has_entries;
+  return SYMGPU_OK;
+}
+
+// second half: context, dependency-ordered car following, placement, origins' queues, finalisation
+static int step_back(symgpu_ctx* c) {
+  const int L = c->net.n_lanes(), T = c->net.n_cls();
+  cudaStream_t s = c->stream;
+  auto& desc = c->ss.desc; auto& desc_lane = c->ss.desc_lane;
+  const int n = c->ss.n, n_sorted = c->ss.n_sorted; const bool has_entries = c->ss.has_entries;
+  const int B = 256;
+  auto G = [&](int cnt) { return (cnt + B - 1) / B; };
+  const int by_id = c->mp.on ? 1 : 0;
+  if (n > 0) {
     KBEGIN(c, KID_CONTEXT); k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dl, n, c->lane_tail.p, c->f_posidx.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c);
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
-    KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p); KEND(c);
+    KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
     int seg_done = 0;
     for (int round = 0;; round++) {
       CK(cudaMemsetAsync(c->f_queue.p, 0xff, ((size_t)n_sorted + (size_t)c->flow_grid * 4 + 64) * sizeof(int), s));
@@ -744,7 +817,7 @@ static int do_step(symgpu_ctx* c) {
       k_cyc_init<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted); LAUNCH(c);
       int flip = 0;
       for (int k = 0; k < Klev; k++) { k_cyc_double<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c); flip ^= 1; }
-      k_cyc_mark<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c);
+      k_cyc_mark<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, flip, by_id); LAUNCH(c);
       k_cyc_break<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, c->rows.p, n_sorted, c->counters.p);
       KEND(c);
     }
@@ -770,7 +843,7 @@ static int do_step(symgpu_ctx* c) {
   int nex = n > 0 ? c->h_stat[4] : 0;
   c->last_exited.resize(nex);
   if (nex) { CK(cudaMemcpy(c->last_exited.data(), c->exited.p, nex * sizeof(ExitRow), cudaMemcpyDeviceToHost));
-    std::sort(c->last_exited.begin(), c->last_exited.end(), [](const ExitRow& a, const ExitRow& b) { return a.slot < b.slot; }); }
+    std::sort(c->last_exited.begin(), c->last_exited.end(), [&](const ExitRow& a, const ExitRow& b) { return c->mp.on ? a.id < b.id : a.slot < b.slot; }); }
   // global random sequence: account for the draws made on the device during this step
   unsigned dd = (unsigned)c->h_stat[7];
   if (has_entries) c->rng.skip(dd - c->dev_draws_seen); else c->rng.count += dd - c->dev_draws_seen;
@@ -781,6 +854,98 @@ static int do_step(symgpu_ctx* c) {
   // swap start/end-of-step buffers
   std::swap(c->v_pos.p, c->v_pos_n.p); std::swap(c->v_vit.p, c->v_vit_n.p); std::swap(c->v_acc.p, c->v_acc_n.p); std::swap(c->v_lane.p, c->v_lane_n.p);
   fill_dev_structs(c);
+  return c->n_alive;
+}
+static int do_step(symgpu_ctx* c) {
+  if (c->mp.on) { g_err = "partitioned context: drive it with symgpu_mp_step_front / _back / _import"; return SYMGPU_E_ARG; }
+  int rc = step_front(c);
+  if (rc != SYMGPU_OK) return rc;
+  return step_back(c);
+}
+
+// ---- partitioned runs: one process per GPU, the caller moves the buffers between ranks (NCCL via torch.distributed) ----------
+// node_part[n_nodes]: owning rank of every node.  A lane belongs to the rank of the node it leads to (internal junction lanes:
+// their junction; exit stubs: the junction they leave), so a follower and the junction it crosses are on one GPU.
+extern "C" int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int* node_part) {
+  if (!c || !node_part || world < 1 || rank < 0 || rank >= world) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if (!c->entries.empty()) { g_err = "partitioned runs do not support origins yet (vehicle ids and the random sequence are global)"; return SYMGPU_E_UNSUPPORTED; }
+  const FlatNet& f = c->net; const int L = f.n_lanes();
+  auto& m = c->mp; m.on = true; m.rank = rank; m.world = world;
+  m.lane_owner.resize(L);
+  for (int l = 0; l < L; l++) { int link = f.lane_i[4 * l]; int brick = f.link_i[8 * link + 5]; int up = f.link_i[8 * link + 2], down = f.link_i[8 * link + 3];
+    int ta = f.link_i[8 * link + 4]; int node = brick >= 0 ? brick : ((ta == 'S' || ta == 'P') ? up : down); m.lane_owner[l] = node_part[node]; }
+  // halo of rank r: lanes owned by someone else that an owned lane leads into; export of r to q: lanes of r in q's halo
+  std::vector<std::vector<int>> halo(world), expo(world);
+  std::vector<char> seen(L, 0);
+  for (int l = 0; l < L; l++) for (int k = f.succ_off[l]; k < f.succ_off[l + 1]; k++) { int nx = f.succ_i[3 * k + 1]; int a = m.lane_owner[l], b = m.lane_owner[nx];
+    if (a == b) continue;
+    if (a == rank && !(seen[nx] & 1)) { seen[nx] |= 1; halo[b].push_back(nx); }
+    if (b == rank && !(seen[nx] & 2)) { /* per peer dedupe below */ } }
+  for (int q = 0; q < world; q++) { if (q == rank) continue; std::vector<char> s2(L, 0);
+    for (int l = 0; l < L; l++) if (m.lane_owner[l] == q) for (int k = f.succ_off[l]; k < f.succ_off[l + 1]; k++) { int nx = f.succ_i[3 * k + 1];
+      if (m.lane_owner[nx] == rank && !s2[nx]) { s2[nx] = 1; expo[q].push_back(nx); } } }
+  m.halo_lanes.clear(); m.export_lanes.clear(); m.halo_off.assign(world + 1, 0); m.export_off.assign(world + 1, 0);
+  std::vector<int> export_peer;
+  for (int q = 0; q < world; q++) { std::sort(halo[q].begin(), halo[q].end()); std::sort(expo[q].begin(), expo[q].end());
+    m.halo_lanes.insert(m.halo_lanes.end(), halo[q].begin(), halo[q].end()); m.halo_off[q + 1] = (int)m.halo_lanes.size();
+    m.export_lanes.insert(m.export_lanes.end(), expo[q].begin(), expo[q].end()); m.export_off[q + 1] = (int)m.export_lanes.size(); }
+  m.n_halo = (int)m.halo_lanes.size(); m.n_export = (int)m.export_lanes.size();
+  if ((size_t)m.n_halo > std::min<size_t>((size_t)L, 65536)) { g_err = "halo larger than the ghost reserve"; return SYMGPU_E_CAPACITY; }
+  CK(m.d_lane_owner.upload(m.lane_owner)); CK(m.d_halo_lanes.upload(m.halo_lanes)); CK(m.d_export_lanes.upload(m.export_lanes)); CK(m.d_mig_count.alloc(world));
+  m.h_mig_count.assign(world, 0);
+  // keep only the vehicles on owned lanes
+  CK(cudaMemset(c->stat.p, 0, sizeof(int)));
+  if (c->n_slots) { k_mp_drop_foreign<<<(c->n_slots + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, m.d_lane_owner.p, rank, c->stat.p); LAUNCH(c); }
+  CK(cudaMemcpyAsync(c->h_stat, c->stat.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+  c->n_alive = c->h_stat[0];
+  return c->n_alive;
+}
+// entries (tail records of 4 doubles) this rank sends to / receives from every peer each step
+extern "C" int symgpu_mp_sizes(symgpu_ctx* c, int* export_cnt, int* halo_cnt) {
+  if (!c || !c->mp.on) return SYMGPU_E_ARG;
+  for (int q = 0; q < c->mp.world; q++) { if (export_cnt) export_cnt[q] = c->mp.export_off[q + 1] - c->mp.export_off[q]; if (halo_cnt) halo_cnt[q] = c->mp.halo_off[q + 1] - c->mp.halo_off[q]; }
+  return SYMGPU_OK;
+}
+// first half of the step; writes the tails of the exported lanes (n_export x 4 doubles, peers in rank order) to device memory `send_tails`
+extern "C" int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails) {
+  if (!c || !c->mp.on) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  int rc = step_front(c); if (rc != SYMGPU_OK) return rc;
+  if (c->mp.n_export) {
+    if (c->ss.n == 0) CK(cudaMemsetAsync(c->lane_tail.p, 0xff, c->net.n_lanes() * sizeof(int), c->stream));
+    k_mp_pack_tails<<<(c->mp.n_export + 255) / 256, 256, 0, c->stream>>>(c->dv, c->mp.d_export_lanes.p, c->mp.n_export, c->lane_tail.p, send_tails); LAUNCH(c); }
+  CK(cudaStreamSynchronize(c->stream));
+  return SYMGPU_OK;
+}
+// second half: `recv_tails` (n_halo x 4 doubles, peers in rank order) become ghost leaders; then the rest of the step; vehicles that
+// ended on a foreign lane are packed into `send_rows` (world regions of cap_per_peer rows of 16 doubles), counts in send_counts[world]
+extern "C" int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, double* send_rows, int cap_per_peer, int* send_counts) {
+  if (!c || !c->mp.on || !send_counts) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  auto& m = c->mp;
+  if (c->ss.n == 0) CK(cudaMemsetAsync(c->lane_tail.p, 0xff, c->net.n_lanes() * sizeof(int), c->stream));
+  if (m.n_halo) { k_mp_unpack_ghosts<<<(m.n_halo + 255) / 256, 256, 0, c->stream>>>(c->dv, m.d_halo_lanes.p, m.n_halo, m.ghost_base, c->lane_tail.p, recv_tails); LAUNCH(c); }
+  int r = step_back(c); if (r < 0) return r;
+  CK(cudaMemsetAsync(m.d_mig_count.p, 0, m.world * sizeof(int), c->stream));
+  if (c->n_slots) { k_mp_pack_migrants<<<(c->n_slots + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, m.d_lane_owner.p, m.rank, cap_per_peer, m.d_mig_count.p, send_rows); LAUNCH(c); }
+  CK(cudaMemcpyAsync(m.h_mig_count.data(), m.d_mig_count.p, m.world * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int out = 0;
+  for (int q = 0; q < m.world; q++) { send_counts[q] = m.h_mig_count[q]; out += m.h_mig_count[q]; if (m.h_mig_count[q] > cap_per_peer) { g_err = "migration buffer too small"; return SYMGPU_E_CAPACITY; } }
+  c->n_alive -= out;
+  return c->n_alive;
+}
+// vehicles arriving from other ranks (n_rows x 16 doubles in device memory) join the end of the local list
+extern "C" int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows) {
+  if (!c || !c->mp.on || n_rows < 0) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if (c->n_slots + n_rows > c->pool_base) { g_err = "vehicle capacity exhausted (set SYMGPU_CAPACITY)"; return SYMGPU_E_CAPACITY; }
+  if (n_rows) { k_mp_unpack_migrants<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, n_rows, recv_rows); LAUNCH(c); }
+  c->n_slots += n_rows; c->n_alive += n_rows;
+  CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms;
   return c->n_alive;
 }
 

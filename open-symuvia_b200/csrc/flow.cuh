@@ -35,26 +35,30 @@ struct DevFlow {
 };
 
 // per lane: segments, front -> rear
-__global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, const int* lane_start) {
+// `by_id`: m_LstVehicles order is the slot order on one GPU; in a partitioned run slots are local, so the vehicle id is the key
+// (pre-seeded vehicles are listed in id order, reseau.cpp:1293-1340).
+__device__ __forceinline__ int list_key(const DevVeh& V, int x, int by_id) { return by_id ? V.id[x] : x; }
+__global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, const int* lane_start, int by_id) {
   int ln = blockIdx.x * blockDim.x + threadIdx.x;
   if (ln >= n_lanes) return;
   int n = lane_count[ln];
   if (!n) return;
   int s = lane_start[ln];
-  int cur = -1, nseg = 0, len = 0, mn = 0x7fffffff;
+  int cur = -1, nseg = 0, len = 0, mn = 0x7fffffff, mnx = -1;
   for (int a = n - 1; a >= 0; a--) {
     int p = s + a; int x = F.order[p];
     int d = V.ctx_leader[x];
     bool front = (a == n - 1) || d != F.order[p + 1];
+    if (d >= 0 && V.status[d] == ST_GHOST) d = -1;          // leader on another GPU: estimated speed, no dependency
     if (front) {
-      if (cur >= 0) { F.seg_len[cur] = len; F.minslot[cur] = mn; }
-      cur = p; len = 0; mn = 0x7fffffff; nseg++;
+      if (cur >= 0) { F.seg_len[cur] = len; F.minslot[cur] = mnx; }
+      cur = p; len = 0; mn = 0x7fffffff; mnx = -1; nseg++;
       F.isfront[p] = 1; F.seg_dep[p] = d; F.first_waiter[p] = -1;
     } else F.isfront[p] = 0;
     F.segpos[x] = cur; F.cut[x] = 0;
-    len++; if (x < mn) mn = x;
+    len++; { int k = list_key(V, x, by_id); if (k < mn) { mn = k; mnx = x; } }
   }
-  F.seg_len[cur] = len; F.minslot[cur] = mn;
+  F.seg_len[cur] = len; F.minslot[cur] = mnx;
   atomicAdd(&F.ctl->n_segments, nseg);
 }
 
@@ -198,7 +202,7 @@ __global__ void k_cyc_double(DevFlow F, int n_sorted, int flip) {
   int m = M[p], m2 = M[a];
   Mo[p] = m2 < m ? m2 : m;
 }
-__global__ void k_cyc_mark(DevFlow F, int n_sorted, int flip) {
+__global__ void k_cyc_mark(DevVeh V, DevFlow F, int n_sorted, int flip, int by_id) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
   if (!F.isfront[p] || F.first_waiter[p] == kDone) return;
@@ -207,7 +211,7 @@ __global__ void k_cyc_mark(DevFlow F, int n_sorted, int flip) {
   F.oncyc[c0] = 1;
   int id = M[c0];                                  // smallest segment id of that loop
   F.cid[p] = id;
-  unsigned long long key = ((unsigned long long)(unsigned)F.minslot[p] << 32) | (unsigned)p;
+  unsigned long long key = ((unsigned long long)(unsigned)list_key(V, F.minslot[p], by_id) << 32) | (unsigned)p;
   atomicMin(&F.rootkey[id], key);
 }
 // one thread per loop: cut it where the reference's recursion would
@@ -216,7 +220,7 @@ __global__ void k_cyc_break(DevVeh V, DevFlow F, double* rows, int n_sorted, lon
   if (p >= n_sorted) return;
   if (!F.oncyc[p] || F.cid[p] != p) return;        // representative = smallest segment of the loop
   unsigned long long key = F.rootkey[p];
-  int r = (int)(key >> 32), rs = (int)(key & 0xffffffffu);
+  int rs = (int)(key & 0xffffffffu); int r = F.minslot[rs];
   // entry segment of the root's chain into the loop, and the vehicle it enters at
   int e = rs, T = -1;
   while (!F.oncyc[e]) { T = F.seg_dep[e]; e = F.segpos[T]; }

@@ -20,7 +20,8 @@ constexpr int kMaxCls = 8;
 
 // vehicle slot status
 enum : int { ST_DEAD = 0, ST_ALIVE = 1, ST_NEW = 2 /* entered m_LstVehicles this step, never computed */,
-             ST_POOL = 3 /* head of an origin's waiting queue, not in m_LstVehicles */ };
+             ST_POOL = 3 /* head of an origin's waiting queue, not in m_LstVehicles */,
+             ST_GHOST = 4 /* read-only copy of the tail vehicle of a lane owned by another GPU (partitioned runs) */ };
 // persistent per-vehicle flags
 enum : int { F_HASCTX = 1, F_PREVFREE = 2 };
 // output flags (same packing as the oracle dump): bit0 regime fluide, bit1 arret au feu, bit2 context free-flow

@@ -97,7 +97,9 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
     else alpha = -cl.w * cl.kx * P.dt / dn0;                              // :375
   }
   r[R_DN0] = dn0; r[R_GAP] = gap; r[R_DFREE] = dfree; r[R_DTV] = dtv; r[R_V1] = v1; r[R_VL1] = vL1; r[R_START] = start; r[R_CPOS] = cpos;
-  r[R_VLEST] = vlest; r[R_T0] = t0; r[R_I0] = pack2(L, hdr); r[R_I1] = pack2(i, 0);
+  // a leader living on another GPU is never computed before its follower: the follower uses the estimated leader speed,
+  // exactly as when the reference breaks a leader loop (NewellCarFollowing.cpp:217-230)
+  r[R_VLEST] = vlest; r[R_T0] = t0; r[R_I0] = pack2(L, hdr); r[R_I1] = pack2(i, (L >= 0 && V.status[L] == ST_GHOST) ? 1 : 0);
   r[R_A] = A; r[R_WL] = wl; r[R_Q1] = q1; r[R_ALPHA] = alpha;
   if (nl > kRowLanes) return;
   const int route = V.route[i], rpos = V.route_pos[i];

@@ -39,6 +39,7 @@ def lib():
         L.orc_link_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_exited.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_waiting.argtypes = [C.c_void_p]
+        L.orc_set_partition.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_create_vehicle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.orc_rng_new.restype = C.c_void_p
         L.orc_rng_new.argtypes = [C.c_uint]
@@ -88,6 +89,10 @@ class Oracle:
 
     def create_vehicle(self, cls: int, entry: int, dest: int, lane: int, dbt: float) -> int:
         return self.L.orc_create_vehicle(self.h, cls, entry, dest, lane, dbt)
+
+    def set_partition(self, node_part):
+        part = np.ascontiguousarray(node_part, np.int32)
+        self.L.orc_set_partition(self.h, part.ctypes.data_as(C.c_void_p))
 
     def waiting(self) -> int:
         return self.L.orc_waiting(self.h)

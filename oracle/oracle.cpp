@@ -171,6 +171,11 @@ struct Sim {
   std::vector<Veh*> graveyard;
   double min_kv = 0, max_vit_max = 0, max_debit_max = 0;
   long n_ties = 0, n_loops = 0, n_created = 0, max_depth = 0;
+  // partitioned model (multi-GPU runs): a leader on a lane of another partition is never computed first; its follower uses the
+  // estimated leader speed of NewellCarFollowing.cpp:217-230 (the reference's own rule when a leader is not yet computed)
+  std::vector<int> lane_owner;
+  bool same_part(const Veh* a, const Veh* b) const { return lane_owner.empty() || lane_owner[a->lane[1]] == lane_owner[b->lane[1]]; }
+
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
 
@@ -441,7 +446,7 @@ struct Sim {
   }
   double newell_cong(Veh* v, double dtv, Ctx& c) {                                          // :204-398
     Veh* L = c.leader; double dist = c.leader_dist; double vL;
-    if (L->deja_calcule) vL = L->vit[0];
+    if (L->deja_calcule && same_part(v, L)) vL = L->vit[0];
     else {                                                                                   // :217-230 (at most one leader in the context)
       if (accbornee) vL = std::min<double>(std::min<double>(L->vit_reg_tuy_act, L->vit_max), L->vit[1] + cls[v->cls].acc_max(L->vit[1]) * dt);
       else vL = std::min<double>(L->vit_reg_tuy_act, L->vit_max);
@@ -618,7 +623,7 @@ struct Sim {
     double range = max_influence(v) + dtv * v->vit_max;                                     // :1299, :1710-1715
     build_context(v, range);                                                                 // :1302
     Ctx& c = *v->ctx;
-    if (c.leader) calcul_trafic_ex(c.leader, inst, ids);                                    // :1304-1309 leader first
+    if (c.leader && same_part(v, c.leader)) calcul_trafic_ex(c.leader, inst, ids);          // :1304-1309 leader first
     double goal = compute_law(v, dtv, c);                                                    // :1312
     v->regime_fluide = c.free_flow; v->regime_fluide_leader = v->regime_fluide;             // :1313-1315
     v->arret_au_feu = false;
@@ -899,6 +904,9 @@ int orc_exited(void* h, int* ids, double* inst, int cap) { Sim* s = (Sim*)h; int
   for (auto& e : s->exited) { if (n < cap) { ids[n] = e.id; inst[n] = e.inst; } n++; } return n; }
 int orc_create_vehicle(void* h, int cls, int entry, int dest, int lane, double dbt) { Sim* s = (Sim*)h; int id = s->last_id++;
   s->api_queue.push_back({id, cls, entry, dest, lane, dbt}); return id; }
+void orc_set_partition(void* h, const int* node_part) { Sim* s = (Sim*)h; s->lane_owner.resize(s->lanes.size());
+  for (size_t l = 0; l < s->lanes.size(); l++) { const Link& T = s->links[s->lanes[l].link];
+    int node = T.brick >= 0 ? T.brick : ((T.type_aval == 'S' || T.type_aval == 'P') ? T.up_node : T.down_node); s->lane_owner[l] = node_part[node]; } }
 int orc_waiting(void* h) { Sim* s = (Sim*)h; int n = 0; for (auto& e : s->entries) for (auto& q : e.attente) n += (int)q.size(); return n; }
 // raw RNG access for the known-answer test of the generator itself
 void* orc_rng_new(unsigned seed) { auto* r = new RandManager(); r->mySrand(seed); return r; }
