@@ -40,6 +40,7 @@ def lib():
         L.symgpu_traj_bind.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp]
         L.symgpu_step_traj_async.argtypes = [vp, ci]
         L.symgpu_traj_wait.argtypes = [vp, ci]
+        L.symgpu_traj_copy_async.argtypes = [vp, ci]
         L.symgpu_num_vehicles.argtypes = [vp]
         L.symgpu_time.argtypes = [vp]
         L.symgpu_time.restype = cd
@@ -139,6 +140,9 @@ class Engine:
 
     def step_traj_async(self, which: int) -> int:
         return self._chk(self.L.symgpu_step_traj_async(self.h, which))
+
+    def traj_copy_async(self, which: int) -> int:
+        return self._chk(self.L.symgpu_traj_copy_async(self.h, which))
 
     def traj_wait(self, which: int):
         self._chk(self.L.symgpu_traj_wait(self.h, which))

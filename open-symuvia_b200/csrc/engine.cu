@@ -595,7 +595,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   c->rng.seed((unsigned)f.params[SYMFLAT_P_SEED]);                    // reseau.cpp:983-995
   // initial vehicles (reseau.cpp:1293-1340): already on the network, state at index 0
   { std::vector<HostRow> rows(f.n_init());
-    for (int v = 0; v < f.n_init(); v++) { HostRow& r = rows[v]; r.status = ST_ALIVE; r.id = c->last_id++; r.cls = f.iv_i[4 * v]; r.lane = f.iv_i[4 * v + 1];
+    for (int v = 0; v < f.n_init(); v++) { HostRow& r = rows[v]; r.status = ST_ALIVE; r.id = f.iv_id.empty() ? c->last_id++ : f.iv_id[v]; if (!f.iv_id.empty()) c->last_id = std::max(c->last_id, r.id + 1); r.cls = f.iv_i[4 * v]; r.lane = f.iv_i[4 * v + 1];
       r.route = f.iv_i[4 * v + 2]; r.rpos = f.iv_i[4 * v + 3]; r.pos = f.iv_f[3 * v]; r.vit = f.iv_f[3 * v + 1]; r.acc = f.iv_f[3 * v + 2]; r.tcre = 0; r.hent = 0; }
     int rc = upload_rows(c, 0, rows); if (rc != SYMGPU_OK) { delete c; return rc; }
     c->n_slots = c->n_alive = f.n_init(); }
@@ -1022,10 +1022,11 @@ extern "C" int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int*
 }
 // One step, then pack + copy the trajectory rows to bound buffer `which` on the side stream (returns rows; the rows are
 // valid after symgpu_traj_wait(which)).  The next step can run while the copy is in flight.
-extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
+// pack + copy the CURRENT trajectory rows to bound buffer `which` on the side stream (no step): partitioned runs call it
+// after symgpu_mp_import
+extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
   if (!c || which < 0 || which > 1 || !c->tbuf[which].id) return SYMGPU_E_ARG;
-  int r = symgpu_step(c);
-  if (r < 0) return r;
+  CK(cudaSetDevice(c->device));
   auto& b = c->tbuf[which];
   const int n = c->n_slots; const int rows = c->n_alive;
   if (rows > b.cap) { g_err = "trajectory buffer too small"; return SYMGPU_E_CAPACITY; }
@@ -1046,6 +1047,12 @@ extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
   }
   CK(cudaEventRecord(c->t_done[which], c->side));
   return rows;
+}
+extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
+  if (!c || which < 0 || which > 1 || !c->tbuf[which].id) return SYMGPU_E_ARG;
+  int r = symgpu_step(c);
+  if (r < 0) return r;
+  return symgpu_traj_copy_async(c, which);
 }
 extern "C" int symgpu_traj_wait(symgpu_ctx* c, int which) {
   if (!c || which < 0 || which > 1) return SYMGPU_E_ARG;

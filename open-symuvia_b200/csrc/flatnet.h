@@ -17,7 +17,7 @@ struct FlatNet {
   std::vector<double> params, cls, link_f, lane_f, succ_f, sl_f, ctrl_f, seq_f, sig_f, dem_f, dest_f, droute_f,
       lanecoef_f, typecoef_f, exit_f, iv_f, link_geom;
   std::vector<int> link_i, lane_i, succ_off, succ_i, sl_off, sl_i, ctrl_i, seq_i, sig_i, node_i, route_off, route_links,
-      entry_i, dest_i, droute_i, exit_i, iv_i;
+      entry_i, dest_i, droute_i, exit_i, iv_i, iv_id;
   std::vector<std::string> link_names, node_names, cls_names;
   std::string error;
 
@@ -45,7 +45,7 @@ struct FlatNet {
         {"link_i", &link_i}, {"lane_i", &lane_i}, {"succ_off", &succ_off}, {"succ_i", &succ_i}, {"sl_off", &sl_off},
         {"sl_i", &sl_i}, {"ctrl_i", &ctrl_i}, {"seq_i", &seq_i}, {"sig_i", &sig_i}, {"node_i", &node_i},
         {"route_off", &route_off}, {"route_links", &route_links}, {"entry_i", &entry_i}, {"dest_i", &dest_i},
-        {"droute_i", &droute_i}, {"exit_i", &exit_i}, {"iv_i", &iv_i}};
+        {"droute_i", &droute_i}, {"exit_i", &exit_i}, {"iv_i", &iv_i}, {"iv_id", &iv_id}};
     std::map<std::string, std::vector<double>*> dm = {
         {"params", &params}, {"cls", &cls}, {"link_f", &link_f}, {"lane_f", &lane_f}, {"succ_f", &succ_f},
         {"sl_f", &sl_f}, {"ctrl_f", &ctrl_f}, {"seq_f", &seq_f}, {"sig_f", &sig_f}, {"dem_f", &dem_f},

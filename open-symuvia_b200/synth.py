@@ -447,3 +447,18 @@ def config(name: str, **kw) -> NetBuilder:
     if name == "C5":
         return grid(n=300, n_steps=100, demand_per_lane=0.0, preseed_per_lane=14.0, **kw)
     raise KeyError(name)
+
+
+def fast_grid(path: str, nx: int, ny: int, per_lane: float = 12.6, seed: int = 42, route_len: int = 24, n_steps: int = 300,
+              rank: int = 0, world: int = 1):
+    """C++ generator (csrc/gen_grid.cpp) of the pre-seeded grid: the whole network, the vehicles of strip `rank` of `world`
+    (global ids).  Returns (vehicles written, vehicles in the whole population)."""
+    import ctypes as C
+    import os
+    lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsymgen.so"))
+    lib.symgen_grid.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    tot = C.c_longlong(0)
+    n = lib.symgen_grid(path.encode(), nx, ny, per_lane, seed, route_len, n_steps, rank, world, C.byref(tot))
+    if n < 0:
+        raise RuntimeError(f"symgen_grid could not write {path}")
+    return n, int(tot.value)

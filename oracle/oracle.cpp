@@ -231,8 +231,9 @@ struct Sim {
       if (c.debit_max() > max_debit_max) max_debit_max = c.debit_max(); }
     rnd.mySrand(seed);                                              // reseau.cpp:983-995 (seed != 0)
     // initial vehicles: reseau.cpp:11680-11773 (load), :1293-1340 (copy into m_LstVehicles at InitSimuTrafic)
-    const int* ivi = f.I("iv_i"); const double* ivf = f.D("iv_f");
+    const int* ivi = f.I("iv_i"); const double* ivf = f.D("iv_f"); const int* ivid = f.N("iv_id") ? f.I("iv_id") : nullptr;
     for (size_t v = 0; v < f.N("iv_i") / 4; v++) {
+      if (ivid) last_id = ivid[v];
       Veh* p = new_vehicle(ivi[4 * v], last_id++, false);   // law object copied, no draw (vehicule.cpp:5246-5250)
       p->lane[0] = ivi[4 * v + 1]; p->link[0] = lanes[p->lane[0]].link; p->route = ivi[4 * v + 2]; p->route_pos = ivi[4 * v + 3];
       p->pos[0] = ivf[3 * v]; p->vit[0] = ivf[3 * v + 1]; p->acc[0] = ivf[3 * v + 2];
