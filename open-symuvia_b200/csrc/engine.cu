@@ -340,7 +340,7 @@ __global__ void k_mp_unpack_ghosts(DevVeh V, const int* halo_lanes, int n, int g
 }
 // vehicles that ended the step on a lane owned by another GPU leave with their whole state (16 doubles per row)
 constexpr int kMigD = 16;
-__global__ void k_mp_pack_migrants(DevVeh V, int n, const int* lane_owner, int rank, int cap_per_peer, int* count, double* out) {
+__global__ void k_mp_pack_migrants(DevVeh V, int n, const int* lane_owner, int rank, int cap_per_peer, int* count, double* out, int* free_slots, int free_base, int* free_cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || V.status[i] != ST_ALIVE) return;
   int q = lane_owner[V.lane[i]];
@@ -353,11 +353,12 @@ __global__ void k_mp_pack_migrants(DevVeh V, int n, const int* lane_owner, int r
     o[6] = V.pos[i]; o[7] = V.vit[i]; o[8] = V.acc[i]; o[9] = V.dn[i]; o[10] = V.cpos[i]; o[11] = V.tcre[i]; o[12] = V.dstp[i]; o[13] = V.hent[i]; o[14] = V.tsort[i]; o[15] = 0;
   }
   V.status[i] = ST_DEAD;
+  free_slots[free_base + atomicAdd(free_cnt, 1)] = i;          // the slot is reused by a later arrival
 }
-__global__ void k_mp_unpack_migrants(DevVeh V, int slot0, int n, const double* in) {
+__global__ void k_mp_unpack_migrants(DevVeh V, int slot0, int n, const double* in, const int* free_slots, int free_top, int n_reuse) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const double* o = in + (size_t)k * kMigD; int i = slot0 + k;
+  const double* o = in + (size_t)k * kMigD; int i = k < n_reuse ? free_slots[free_top - 1 - k] : slot0 + (k - n_reuse);
   V.status[i] = ST_ALIVE; V.id[i] = __double2loint(o[0]); V.cls[i] = __double2hiint(o[0]); V.route[i] = __double2loint(o[1]); V.route_pos[i] = __double2hiint(o[1]);
   V.lane[i] = __double2loint(o[2]); V.lane_n[i] = V.lane[i]; V.prev_leader[i] = __double2hiint(o[2]); V.flags[i] = __double2loint(o[3]); V.oflags[i] = __double2hiint(o[3]);
   V.memo[i * kMemo] = __double2loint(o[4]); V.memo[i * kMemo + 1] = __double2hiint(o[4]); V.memo[i * kMemo + 2] = __double2loint(o[5]); V.memo[i * kMemo + 3] = __double2hiint(o[5]);
@@ -438,7 +439,7 @@ struct symgpu_ctx {
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
   struct Mp { bool on = false; int rank = 0, world = 1, ghost_base = 0, n_halo = 0, n_export = 0; std::vector<int> lane_owner, halo_lanes, halo_off, export_lanes, export_off;
-    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count; int mig_cap = 0; std::vector<int> h_mig_count; } mp;
+    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count, d_free; int free_count = 0; int mig_cap = 0; std::vector<int> h_mig_count; } mp;
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
 };
 
@@ -892,7 +893,7 @@ extern "C" int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int
     m.export_lanes.insert(m.export_lanes.end(), expo[q].begin(), expo[q].end()); m.export_off[q + 1] = (int)m.export_lanes.size(); }
   m.n_halo = (int)m.halo_lanes.size(); m.n_export = (int)m.export_lanes.size();
   if ((size_t)m.n_halo > std::min<size_t>((size_t)L, 65536)) { g_err = "halo larger than the ghost reserve"; return SYMGPU_E_CAPACITY; }
-  CK(m.d_lane_owner.upload(m.lane_owner)); CK(m.d_halo_lanes.upload(m.halo_lanes)); CK(m.d_export_lanes.upload(m.export_lanes)); CK(m.d_mig_count.alloc(world));
+  CK(m.d_lane_owner.upload(m.lane_owner)); CK(m.d_halo_lanes.upload(m.halo_lanes)); CK(m.d_export_lanes.upload(m.export_lanes)); CK(m.d_mig_count.alloc(world + 1)); CK(m.d_free.alloc(c->cap));
   m.h_mig_count.assign(world, 0);
   // keep only the vehicles on owned lanes
   CK(cudaMemset(c->stat.p, 0, sizeof(int)));
@@ -928,22 +929,24 @@ extern "C" int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, doub
   if (c->ss.n == 0) CK(cudaMemsetAsync(c->lane_tail.p, 0xff, c->net.n_lanes() * sizeof(int), c->stream));
   if (m.n_halo) { k_mp_unpack_ghosts<<<(m.n_halo + 255) / 256, 256, 0, c->stream>>>(c->dv, m.d_halo_lanes.p, m.n_halo, m.ghost_base, c->lane_tail.p, recv_tails); LAUNCH(c); }
   int r = step_back(c); if (r < 0) return r;
-  CK(cudaMemsetAsync(m.d_mig_count.p, 0, m.world * sizeof(int), c->stream));
-  if (c->n_slots) { k_mp_pack_migrants<<<(c->n_slots + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, m.d_lane_owner.p, m.rank, cap_per_peer, m.d_mig_count.p, send_rows); LAUNCH(c); }
+  CK(cudaMemsetAsync(m.d_mig_count.p, 0, (m.world + 1) * sizeof(int), c->stream));
+  if (c->n_slots) { k_mp_pack_migrants<<<(c->n_slots + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, m.d_lane_owner.p, m.rank, cap_per_peer, m.d_mig_count.p, send_rows,
+                                                                                  m.d_free.p, m.free_count, &m.d_mig_count.p[m.world]); LAUNCH(c); }
   CK(cudaMemcpyAsync(m.h_mig_count.data(), m.d_mig_count.p, m.world * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   int out = 0;
   for (int q = 0; q < m.world; q++) { send_counts[q] = m.h_mig_count[q]; out += m.h_mig_count[q]; if (m.h_mig_count[q] > cap_per_peer) { g_err = "migration buffer too small"; return SYMGPU_E_CAPACITY; } }
-  c->n_alive -= out;
+  c->n_alive -= out; m.free_count += out;
   return c->n_alive;
 }
 // vehicles arriving from other ranks (n_rows x 16 doubles in device memory) join the end of the local list
 extern "C" int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows) {
   if (!c || !c->mp.on || n_rows < 0) return SYMGPU_E_ARG;
   CK(cudaSetDevice(c->device));
-  if (c->n_slots + n_rows > c->pool_base) { g_err = "vehicle capacity exhausted (set SYMGPU_CAPACITY)"; return SYMGPU_E_CAPACITY; }
-  if (n_rows) { k_mp_unpack_migrants<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, n_rows, recv_rows); LAUNCH(c); }
-  c->n_slots += n_rows; c->n_alive += n_rows;
+  const int reuse = std::min(n_rows, c->mp.free_count);
+  if (c->n_slots + (n_rows - reuse) > c->pool_base) { g_err = "vehicle capacity exhausted (set SYMGPU_CAPACITY)"; return SYMGPU_E_CAPACITY; }
+  if (n_rows) { k_mp_unpack_migrants<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, n_rows, recv_rows, c->mp.d_free.p, c->mp.free_count, reuse); LAUNCH(c); }
+  c->mp.free_count -= reuse; c->n_slots += n_rows - reuse; c->n_alive += n_rows;
   CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
   float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms;
   return c->n_alive;
