@@ -38,6 +38,7 @@ static thread_local std::string g_err;
 __constant__ DevParams cP;
 __device__ __forceinline__ const DevParams& cP_ref() { return cP; }
 #include "flow.cuh"
+#include "lanechange.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // device tables for signals
@@ -222,7 +223,7 @@ struct EntryDesc { int lane, pret_slot, pool_slot, dst_slot; };
 __device__ inline void copy_row(const DevVeh& V, int src, int dst) {
   V.id[dst] = V.id[src]; V.cls[dst] = V.cls[src]; V.route[dst] = V.route[src]; V.route_pos[dst] = V.route_pos[src];
   V.lane[dst] = V.lane[src]; V.lane_n[dst] = V.lane_n[src]; V.prev_leader[dst] = V.prev_leader[src]; V.flags[dst] = V.flags[src];
-  V.oflags[dst] = V.oflags[src];
+  V.oflags[dst] = V.oflags[src]; V.vdes[dst] = V.vdes[src];
   for (int k = 0; k < kMemo; k++) V.memo[dst * kMemo + k] = V.memo[src * kMemo + k];
   V.pos[dst] = V.pos[src]; V.vit[dst] = V.vit[src]; V.acc[dst] = V.acc[src];
   V.pos_n[dst] = V.pos_n[src]; V.vit_n[dst] = V.vit_n[src]; V.acc_n[dst] = V.acc_n[src];
@@ -424,6 +425,7 @@ struct symgpu_ctx {
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DevFlow df; int flow_grid = 0; FlowCtl* h_ctl = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
+  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
@@ -435,6 +437,7 @@ struct symgpu_ctx {
   DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  long long lane_changes = 0;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
@@ -453,6 +456,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   n.sl_col = c->sl_col.p; n.sl_prop = c->sl_prop.p; n.n_lanes = c->net.n_lanes(); n.n_links = c->net.n_links(); n.n_sl = c->net.n_sl();
   DevVeh& v = c->dv;
   v.status = c->v_status.p; v.id = c->v_id.p; v.cls = c->v_cls.p; v.route = c->v_route.p; v.route_pos = c->v_rpos.p; v.lane = c->v_lane.p;
+  v.vdes = c->v_vdes.p; n.link_down = c->link_down.p;
   v.lane_n = c->v_lane_n.p; v.prev_leader = c->v_pl.p; v.flags = c->v_flags.p; v.oflags = c->v_oflags.p; v.memo = c->v_memo.p;
   v.pos = c->v_pos.p; v.vit = c->v_vit.p; v.acc = c->v_acc.p; v.pos_n = c->v_pos_n.p; v.vit_n = c->v_vit_n.p; v.acc_n = c->v_acc_n.p;
   v.dn = c->v_dn.p; v.cpos = c->v_cpos.p; v.tcre = c->v_tcre.p; v.dstp = c->v_dstp.p; v.hent = c->v_hent.p; v.tsort = c->v_tsort.p;
@@ -465,6 +469,11 @@ static void fill_dev_structs(symgpu_ctx* c) {
   fl.order = c->order.p; fl.posidx = c->f_posidx.p; fl.isfront = c->f_isfront.p; fl.seg_len = c->f_seg_len.p; fl.seg_dep = c->f_seg_dep.p; fl.segpos = c->f_segpos.p;
   fl.minslot = c->f_minslot.p; fl.first_waiter = c->f_first_waiter.p; fl.next_waiter = c->f_next_waiter.p; fl.cut = c->f_cut.p; fl.queue = c->f_queue.p;
   fl.ctl = c->f_ctl.p; fl.A = c->f_A.p; fl.A2 = c->f_A2.p; fl.Mn = c->f_Mn.p; fl.Mn2 = c->f_Mn2.p; fl.oncyc = c->f_oncyc.p; fl.cid = c->f_cid.p; fl.rootkey = c->f_rootkey.p;
+  DevLc& lc = c->dlc;
+  lc.order = c->order.p; lc.lane_start = c->lane_start.p; lc.lane_count = c->lane_count.p; lc.vdes = c->v_vdes.p; lc.voies_ok = c->lc_voies_ok.p; lc.chgt = c->lc_chgt.p;
+  lc.delta_next = c->lc_delta_next.p; lc.link_delta_head = c->lc_link_head.p; lc.rng = c->lc_rng.p; lc.n_changes = c->lc_nchg.p;
+  lc.dst_chgtvoie = c->net.params[SYMFLAT_P_DSTCHGT]; lc.dst_force = c->net.params[SYMFLAT_P_DST_FORCE] > 0 ? c->net.params[SYMFLAT_P_DST_FORCE] : -1.0;
+  lc.phi_force = c->net.params[SYMFLAT_P_PHI_FORCE] > 0 ? c->net.params[SYMFLAT_P_PHI_FORCE] : 1.0; lc.ordre = 1;
   DevSig& s = c->ds;
   s.ctrl_seq_off = c->ctrl_seq_off.p; s.ctrl_nseq = c->ctrl_nseq.p; s.ctrl_cycle = c->ctrl_cycle.p; s.seq_sig_off = c->seq_sig_off.p; s.seq_nsig = c->seq_nsig.p;
   s.seq_len = c->seq_len.p; s.sig_in = c->sig_in.p; s.sig_out = c->sig_out.p; s.sig_green = c->sig_green.p; s.sig_amber = c->sig_amber.p; s.sig_delay = c->sig_delay.p;
@@ -487,7 +496,7 @@ static int upload_rows(symgpu_ctx* c, int slot0, const std::vector<HostRow>& row
   auto I = [&](DBuf<int>& b, const std::vector<int>& h, int w = 1) { return cudaMemcpyAsync(b.p + (size_t)slot0 * w, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream); };
   auto D = [&](DBuf<double>& b, const std::vector<double>& h) { return cudaMemcpyAsync(b.p + slot0, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream); };
   CK(I(c->v_status, st)); CK(I(c->v_id, id)); CK(I(c->v_cls, cl)); CK(I(c->v_route, ro)); CK(I(c->v_rpos, rp)); CK(I(c->v_lane, la)); CK(I(c->v_lane_n, la));
-  CK(I(c->v_pl, pl)); CK(I(c->v_flags, fl)); CK(I(c->v_oflags, fl)); CK(I(c->v_memo, memo, kMemo));
+  CK(I(c->v_vdes, pl)); CK(I(c->v_pl, pl)); CK(I(c->v_flags, fl)); CK(I(c->v_oflags, fl)); CK(I(c->v_memo, memo, kMemo));
   CK(D(c->v_pos, po)); CK(D(c->v_vit, vi)); CK(D(c->v_acc, ac)); CK(D(c->v_pos_n, po)); CK(D(c->v_vit_n, vi)); CK(D(c->v_acc_n, ac));
   CK(D(c->v_dn, dnv)); CK(D(c->v_cpos, z)); CK(D(c->v_tcre, tc)); CK(D(c->v_dstp, z)); CK(D(c->v_hent, he)); CK(D(c->v_tsort, z));
   CK(cudaStreamSynchronize(c->stream));     // host vectors go out of scope
@@ -518,7 +527,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
     if (f.succ_f[m] < 1.0) { g_err = "movement with taux_utilisation < 1: multi-lane next-lane draws are not supported on the device yet"; delete c; return SYMGPU_E_UNSUPPORTED; }
     for (int m2 = m + 1; m2 < f.succ_off[l + 1]; m2++) if (f.succ_i[3 * m2] == f.succ_i[3 * m]) { g_err = "movement with several target lanes is not supported on the device yet"; delete c; return SYMGPU_E_UNSUPPORTED; }
   }
-  if (f.params[SYMFLAT_P_CHGTVOIE] != 0) { g_err = "chgtvoie=true (lane changing, row A9) is not implemented on the device yet"; delete c; return SYMGPU_E_UNSUPPORTED; }
+  c->chgtvoie = f.params[SYMFLAT_P_CHGTVOIE] != 0;
   DevParams& P = c->P; memset(&P, 0, sizeof(P));
   P.dt = f.params[SYMFLAT_P_DT]; P.relax = f.params[SYMFLAT_P_RELAX]; P.duree = f.params[SYMFLAT_P_NSTEPS] * P.dt; P.bevel = 0;
   P.accbornee = f.params[SYMFLAT_P_ACCBORNEE] != 0; P.ncls = T; P.min_kv = 999;
@@ -539,6 +548,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->succ_off.upload(f.succ_off)); CK(c->succ_key.upload(col(f.succ_i, 3, 0))); CK(c->succ_next.upload(col(f.succ_i, 3, 1)));
   CK(c->sl_off.upload(f.sl_off)); CK(c->sl_i.upload(f.sl_i)); CK(c->sl_pos.upload(f.sl_f));
   CK(c->link_first.upload(col(f.link_i, 8, 0))); CK(c->link_nl.upload(col(f.link_i, 8, 1))); CK(c->link_up.upload(col(f.link_i, 8, 2)));
+  CK(c->link_down.upload(col(f.link_i, 8, 3)));
   CK(c->link_type.upload(col(f.link_i, 8, 4))); CK(c->link_brick.upload(col(f.link_i, 8, 5)));
   CK(c->link_len.upload(col(f.link_f, 2, 0))); CK(c->link_vreg.upload(col(f.link_f, 2, 1)));
   CK(c->route_off.upload(f.route_off)); CK(c->route_links.upload(f.route_links));
@@ -590,6 +600,8 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
                        &c->v_computed, &c->v_ctx_nl, &c->v_ctx_leader, &c->v_ctx_flags}) CK(b->alloc(cap));
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
+  CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
+  CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(1)); CK(c->lc_rng.alloc(1));
   for (DBuf<double>* b : {&c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre, &c->v_dstp, &c->v_hent,
                           &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) CK(b->alloc(cap));
   fill_dev_structs(c);
@@ -704,8 +716,8 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
 }
 
 // per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
-enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_COUNT };
-static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_seg", "k_flow",
+enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_LC, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_COUNT };
+static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_lane_change", "k_seg", "k_flow",
                                               "k_cyc_loops", "k_place", "k_entries", "k_final"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
@@ -776,6 +788,30 @@ static int step_front(symgpu_ctx* c) {
     KEND(c);
     KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
     KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); KEND(c);
+  }
+  // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
+  if (c->chgtvoie && n > 0) {
+    const int K = c->net.n_links();
+    KBEGIN(c, KID_LC);
+    k_lc_prepare<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c);
+    CK(cudaMemsetAsync(c->lc_link_head.p, 0xff, K * sizeof(int), s)); CK(cudaMemsetAsync(c->lc_nchg.p, 0, sizeof(int), s));
+    CK(cudaMemcpyAsync(c->lc_rng.p, &c->rng, sizeof(DevRng), cudaMemcpyHostToDevice, s));
+    k_lc_sequential<<<1, 32, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c);
+    KEND(c);
+    int nchg = 0;
+    CK(cudaMemcpyAsync(&c->rng, c->lc_rng.p, sizeof(DevRng), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&nchg, c->lc_nchg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->lane_changes += nchg;
+    if (nchg > 0) {
+      CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
+      k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); LAUNCH(c);
+      int nb = (L + kScanB - 1) / kScanB;
+      k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
+      if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); LAUNCH(c); }
+      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); LAUNCH(c);
+      k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); LAUNCH(c);
+    }
   }
   c->ss.n = n; c->ss.n_sorted = n_sorted; c->ss.has_entries = has_entries;
   return SYMGPU_OK;
@@ -870,6 +906,7 @@ static int do_step(symgpu_ctx* c) {
 extern "C" int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int* node_part) {
   if (!c || !node_part || world < 1 || rank < 0 || rank >= world) return SYMGPU_E_ARG;
   CK(cudaSetDevice(c->device));
+  if (c->chgtvoie) { g_err = "partitioned runs do not support lane changing yet (global random stream)"; return SYMGPU_E_UNSUPPORTED; }
   if (!c->entries.empty()) { g_err = "partitioned runs do not support origins yet (vehicle ids and the random sequence are global)"; return SYMGPU_E_UNSUPPORTED; }
   const FlatNet& f = c->net; const int L = f.n_lanes();
   auto& m = c->mp; m.on = true; m.rank = rank; m.world = world;
@@ -1091,6 +1128,7 @@ extern "C" long symgpu_counter(symgpu_ctx* c, int which) {
   if (which == SYMGPU_CNT_PASSES) return (long)c->passes;
   if (which == SYMGPU_CNT_LAUNCHES) return (long)c->launches;
   if (which == SYMGPU_CNT_SLOTS) return c->n_slots;
+  if (which == SYMGPU_CNT_LANE_CHANGES) return (long)c->lane_changes;
   long long h[16];
   cudaSetDevice(c->device);
   if (cudaMemcpy(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return SYMGPU_E_CUDA;

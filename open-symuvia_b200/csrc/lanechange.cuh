@@ -1,0 +1,253 @@
+// lanechange.cuh — lane changing.
+//
+// Reseau::ChangementDeVoie (reseau.cpp:4219-4330) is a sequential loop over m_LstVehicles: every acceptance test draws from the
+// one global random stream (AbstractCarFollowing.cpp:324) and a successful change moves the vehicle at once (vehicule.cpp:2674),
+// which changes the tests — and the number of draws — of the vehicles that come later in the list.  Bit-exact lane assignment
+// therefore needs the reference's order.  This first device version keeps that order literally: k_lc_prepare evaluates the
+// per-vehicle, order-independent part in parallel (CalculVoiesPossibles / CalculVoieDesiree, vehicule.cpp:4749-5038) and
+// k_lc_sequential walks the vehicle list with ONE thread, running MT19937 on the device.  (Next: epochs between successes
+// evaluated in parallel; successes are rare, so the serial part shrinks to the changes themselves.)
+#pragma once
+#include "micro.cuh"
+
+namespace symb200 {
+
+struct DevRng { unsigned mt[624]; int idx; unsigned count; };
+
+__device__ inline unsigned rng_raw(DevRng* r) {                        // boost::mt19937
+  if (r->idx >= 624) {
+    for (int i = 0; i < 624; i++) { unsigned y = (r->mt[i] & 0x80000000u) | (r->mt[(i + 1) % 624] & 0x7fffffffu);
+      r->mt[i] = r->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+    r->idx = 0; }
+  unsigned y = r->mt[r->idx++]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18; return y;
+}
+__device__ inline int rng_next(DevRng* r) {                            // RandManager::myRand RandManager.cpp:26-30
+  r->count++;
+  const unsigned bucket = 0xFFFFFFFFu / 32767u;
+  for (;;) { unsigned v = rng_raw(r) / bucket; if (v <= 32766u) return (int)v; }
+}
+
+struct DevLc {
+  const int *order, *lane_start, *lane_count;
+  int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head;
+  DevRng* rng; int* n_changes;
+  double dst_chgtvoie, dst_force, phi_force; int ordre;
+};
+
+// Vehicule::CalculVoiesPossibles + CalculVoieDesiree (vehicule.cpp:4749-5038), phase 6 of the step, per vehicle
+__global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  C.chgt[i] = 0; C.delta_next[i] = -1;
+  if (V.status[i] != ST_ALIVE) return;                                // vehicles created this step have no link at index 1 (reseau.cpp:3941)
+  int lane = V.lane[i]; int link = N.lane_link[lane]; int nl = N.link_nl[link]; int first = N.link_first[link];
+  double p1 = snap_pos(V.pos[i]);
+  int mask = 0;
+  bool zone = p1 > N.lane_len[lane] - C.dst_chgtvoie;
+  int ta = N.link_type[link];
+  if (zone && ta != 0 && N.link_brick[link] < 0) {
+    if (ta == 'S' || ta == 'P') mask = (1 << nl) - 1;
+    else {
+      // next link of the itinerary (Vehicule::CalculNextTuyau vehicule.cpp:2764-2826)
+      int route = V.route[i]; int o = N.route_off[route], e = N.route_off[route + 1];
+      int k = route_index(N, route, V.route_pos[i], link); int nxt = (k >= 0 && o + k + 1 < e) ? N.route_links[o + k + 1] : -1;
+      for (int q = 0; q < nl; q++) { int ln = first + q; bool ok = false;
+        if (nxt >= 0) for (int m = N.succ_off[ln]; m < N.succ_off[ln + 1]; m++) if (N.succ_key[m] == nxt) { ok = true; break; }
+        if (ok && !(N.lane_flags[ln] & 1)) mask |= 1 << q; }
+    }
+  } else for (int q = 0; q < nl; q++) if (!(N.lane_flags[first + q] & 1)) mask |= 1 << q;
+  C.voies_ok[i] = mask;
+  if (C.vdes[i] == -1) {
+    int nV = N.lane_num[lane];
+    if (!((mask >> nV) & 1)) {
+      int d = -1;
+      if (nV - 1 >= 0 && ((mask >> (nV - 1)) & 1)) d = nV - 1;
+      else if (nV + 1 < nl && ((mask >> (nV + 1)) & 1)) d = nV + 1;
+      else { for (int k = nV - 2; k >= 0 && d < 0; k--) if ((mask >> k) & 1) d = nV - 1;
+             for (int k = nV + 2; k < nl && d < 0; k++) if ((mask >> k) & 1) d = nV + 1; }
+      C.vdes[i] = d;
+    }
+  }
+}
+
+// ---- the sequential part (one thread) ----------------------------------------------------------------------------------
+struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; };
+constexpr int kTie = 8;
+
+// iterate the vehicles currently on `lane`: the lane's slice of the start-of-step order (minus those that left it) plus the
+// vehicles that changed to it during this step (per-link list)
+template <class F> __device__ inline void for_lane(const LcView& W, int lane, F f) {
+  int s = W.C.lane_start[lane], n = W.C.lane_count[lane];
+  for (int a = 0; a < n; a++) { int y = W.C.order[s + a]; if (W.V.lane[y] == lane && W.V.status[y] == ST_ALIVE) f(y); }   // vehicles created this step join their lane set later (vehicule.cpp:1224)
+  for (int y = W.C.link_delta_head[W.N.lane_link[lane]]; y >= 0; y = W.C.delta_next[y]) if (W.V.lane[y] == lane) f(y);
+}
+__device__ inline double p1of(const LcView& W, int y) { return snap_pos(W.V.pos[y]); }
+// Reseau::GetLastVehicule (reseau.cpp:14041-14081) over candidates collected in id order
+__device__ inline int pick_last(const LcView& W, int* c, int n) {
+  if (n == 0) return -1;
+  if (n == 1) return c[0];
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (W.V.id[c[j]] < W.V.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
+  for (int i = 0; i < n; i++) { bool fol = false; for (int j = 0; j < n && !fol; j++) if (i != j && W.V.prev_leader[c[j]] == W.V.id[c[i]]) fol = true; if (!fol) return c[i]; }
+  return c[n - 1];
+}
+// Reseau::GetFirstVehicule(list) (reseau.cpp:14084-14128)
+__device__ inline int pick_first(const LcView& W, int* c, int n) {
+  if (n == 0) return -1;
+  if (n == 1) return c[0];
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (W.V.id[c[j]] < W.V.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
+  for (int i = 0; i < n; i++) { int ld = W.V.prev_leader[c[i]]; if (ld < 0) return c[i];
+    bool found = false; for (int j = 0; j < n && !found; j++) if (i != j && W.V.id[c[j]] == ld) found = true; if (!found) return c[i]; }
+  return c[n - 1];
+}
+__device__ inline int near_aval(const LcView& W, int lane, double pos, int excl) {           // reseau.cpp:3583-3640
+  int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 0.00001;
+  for_lane(W, lane, [&](int y) { double p = p1of(W, y); if (p >= pos && p <= pv && y != excl) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } });
+  return pick_last(W, c, n);
+}
+__device__ inline int near_amont(const LcView& W, int lane, double pos, int excl) {          // reseau.cpp:3374-3436 (first stage; no previous lane in scope)
+  int c[kTie]; int n = 0; double pt = -99999;
+  for_lane(W, lane, [&](int y) { double p = p1of(W, y); if (pos > p && p >= pt && y != excl) { if (p == pt) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pt = p; } } });
+  if (n > 0 && (pos - pt) < 9999) return pick_first(W, c, n);
+  return -1;
+}
+__device__ inline int first_vehicule(const LcView& W, int lane) {                            // reseau.cpp:3255-3295 (last maximum in id order)
+  int r = -1; double p = 0; int rid = -1;
+  for_lane(W, lane, [&](int y) { double q = p1of(W, y); if (q > p || (q == p && (r < 0 || W.V.id[y] > rid))) { if (q >= p) { r = y; p = q; rid = W.V.id[y]; } } });
+  return r;
+}
+__device__ inline int prev_vehicule(const LcView& W, int v) {                                // reseau.cpp:3650-3718
+  int lane = W.V.lane[v]; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1; double own = p1of(W, v);
+  for_lane(W, lane, [&](int y) { double p = p1of(W, y); if (p > own && p <= pv && y != v) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } });
+  return pick_last(W, c, n);
+}
+__device__ inline double dist_veh(const LcView& W, int a, int b) {                           // reseau.cpp:4446-4560
+  if (a < 0 || b < 0) return 9999;
+  int la = W.N.lane_link[W.V.lane[a]], lb = W.N.lane_link[W.V.lane[b]];
+  if (la == lb) return fabs(p1of(W, b) - p1of(W, a));
+  if (W.N.link_down[la] == W.N.link_up[lb]) return W.N.lane_len[W.V.lane[a]] - p1of(W, a) + p1of(W, b);
+  if (W.N.link_down[lb] == W.N.link_up[la]) return W.N.lane_len[W.V.lane[b]] - p1of(W, b) + p1of(W, a);
+  return 9999;
+}
+__device__ inline double vit_eq(const DevCls& c, double conc) {                              // DiagFonda.cpp:116-172, :221-276
+  double kc = c.w * c.kx / (c.w - c.vx); double debit;
+  if (conc <= kc) { debit = c.vx * conc; if (fabs(debit) < DBL_EPSILON) debit = 0; }
+  else { debit = c.w * (conc - c.kx); if (fabs(debit) < DBL_EPSILON) debit = 0; }
+  if (fabs(debit) < DBL_EPSILON && fabs(conc) < DBL_EPSILON) return 0;
+  double vit = conc < DBL_EPSILON ? c.vx : debit / conc;
+  if (fabs(vit) < DBL_EPSILON) vit = 0;
+  return vit;
+}
+__device__ inline double debit_max(const DevCls& c) { return c.w * c.kx / ((c.w / c.vx) - 1); }
+__device__ inline double vreg_act(const LcView& W, int y) { return W.N.link_vreg[W.N.lane_link[W.V.lane[y]]]; }   // GetVitRegTuyAct (set at the end of the previous step)
+
+// the lane's memoised next-lane draw (Vehicule::GetTirage) consumed through CalculNextVoie
+__device__ inline int next_voie_draw(const LcView& W, int v, int lane) {
+  int tl; int nx = next_voie(W.N, W.V.route[v], W.V.route_pos[v], lane, &tl);
+  if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) rng_next(W.C.rng);
+  return nx;
+}
+__device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int v, int fol, int lead, int lead_orig, int tgt, bool force) {   // AbstractCarFollowing.cpp:61-329
+  const DevCls& c = P.cls[W.V.cls[v]]; double kc = c.w * c.kx / (c.w - c.vx);
+  double pv = p1of(W, v); int lane = W.V.lane[v]; int link = W.N.lane_link[lane];
+  double si;
+  if (lead_orig >= 0) si = p1of(W, lead_orig) - pv;
+  else if (force) si = fmax(1 / c.kx, W.N.lane_len[lane] - pv);
+  else si = 1 / kc;
+  double sf = (fol >= 0 && lead >= 0) ? dist_veh(W, lead, fol) : 1 / kc;
+  double vit = fmin(vreg_act(W, v), c.vx);
+  double dem_orig = fmin(vit / si, debit_max(c));
+  double dem_dest;
+  if (fol >= 0) { const DevCls& cf = P.cls[W.V.cls[fol]]; dem_dest = fmin(cf.vx / sf, debit_max(cf)); }
+  else dem_dest = fmin(vit / sf, debit_max(c));
+  double off_dest;
+  if (lead >= 0) { const DevCls& cl = P.cls[W.V.cls[lead]]; off_dest = fmin((cl.kx - (1 / sf)) * (-1) * cl.w, debit_max(cl)); }
+  else off_dest = debit_max(c);
+  double pi;
+  if (force) pi = 1 / P.dt;
+  else {
+    double vtgt;
+    if (sf > 0) { const DevCls& d = lead >= 0 ? P.cls[W.V.cls[lead]] : c; vtgt = vit_eq(d, 1 / sf); if (lead >= 0) vtgt = W.V.vit[lead]; } else vtgt = 0;
+    vtgt = fmin(vtgt, W.N.link_vreg[W.N.lane_link[tgt]]);
+    if (fol < 0 && lead >= 0) { vtgt = fmax(vtgt, W.V.vit[lead]); vtgt = fmin(vtgt, vreg_act(W, lead)); }
+    vtgt = fmin(vtgt, c.vx);
+    double vorg = DBL_MAX;
+    if (si > 0) { const DevCls& d = lead_orig >= 0 ? P.cls[W.V.cls[lead_orig]] : c; vorg = vit_eq(d, 1 / si);
+      if (c.law == 0 && (W.V.flags[v] & F_HASCTX) && W.V.dn[v] < 1 && lead_orig >= 0) vorg = W.V.vit[lead_orig]; }
+    else vorg = lead_orig >= 0 ? W.V.vit[lead_orig] : W.V.vit[v];
+    vorg = fmin(vorg, W.N.link_vreg[link]); vorg = fmin(vorg, c.vx);
+    pi = fmax(0., vtgt - vorg) / (W.N.link_vreg[link] * c.tau_lc);
+    if (pi < 0.000001) return false;
+  }
+  double phi;
+  if (force && W.N.link_len[link] - pv < W.C.dst_force) phi = W.C.phi_force;
+  else {
+    if (fol < 0 || lead < 0) dem_dest = 0;
+    if (dem_dest > 0) phi = fmin(1., off_dest / dem_dest) * pi * dem_orig / vit * P.dt * si;
+    else phi = pi * dem_orig / vit * P.dt * si;
+  }
+  double r = rng_next(W.C.rng) / 32767.0;
+  return r < phi;
+}
+__device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol) {            // vehicule.cpp:2657-2711
+  W.C.chgt[v] = 1;
+  int old = W.V.lane[v]; int link = W.N.lane_link[old];
+  double p = p1of(W, v) * W.N.lane_len[tgt] / W.N.lane_len[old];
+  W.V.lane[v] = tgt;
+  if (fol >= 0 && W.N.lane_link[W.V.lane[fol]] == link) p = fmax(p, p1of(W, fol));
+  W.V.pos[v] = p;
+  if (W.C.delta_next[v] == -1 && W.C.link_delta_head[link] != v) { W.C.delta_next[v] = W.C.link_delta_head[link]; W.C.link_delta_head[link] = v; }   // join the link's moved list once
+  W.C.vdes[v] = -1;
+  next_voie_draw(W, v, tgt);
+  atomicAdd(W.C.n_changes, 1);
+}
+__device__ inline bool calcul_changement_voie(const DevParams& P, const LcView& W, int v, int tgt_num, bool force) {   // vehicule.cpp:2248-2457
+  double p1 = p1of(W, v);
+  if (p1 <= SYM_UNDEF) return false;
+  if (W.C.chgt[v]) return false;
+  int lane = W.V.lane[v]; int link = W.N.lane_link[lane]; bool desired = W.C.vdes[v] != -1; bool oblig = W.N.lane_flags[lane] & 1;
+  if (first_vehicule(W, lane) == v && !oblig && !desired) return false;
+  int tgt = W.N.link_first[link] + tgt_num;
+  double ratio = W.N.lane_len[tgt] / W.N.lane_len[lane];
+  bool move_back = false;
+  int same = near_aval(W, tgt, ratio * p1 - 0.01, v);
+  if (same >= 0 && fabs(ratio * p1 - p1of(W, same)) < 0.01) {
+    if (fabs(p1 - W.N.lane_len[lane]) < 0.01) {
+      if (force && W.C.vdes[same] == W.N.lane_num[lane] && W.C.vdes[v] == W.N.lane_num[W.V.lane[same]] && W.V.vit[v] < 0.01 && W.V.vit[same] < 0.01) {
+        changement_voie(W, v, tgt, -1); changement_voie(W, same, lane, -1); return true;
+      }
+      W.V.pos[v] = p1 - 0.5; p1 = p1 - 0.5; move_back = true;
+    } else return false;
+  }
+  double q = ratio * p1 + 0.001;
+  int fol = near_amont(W, tgt, q, v);
+  int lead = near_aval(W, tgt, q, v);
+  if (lead < 0 && (oblig || desired)) { int nx = next_voie_draw(W, v, tgt); if (nx >= 0) lead = near_aval(W, nx, 0, -1); }
+  int lead_orig = prev_vehicule(W, v);
+  if (lead_orig < 0 && !oblig && !desired && !force) return false;   // vehicule.cpp:2440-2442 (the reference does not undo the move-back here)
+  if (test_lane_change(P, W, v, fol, lead, lead_orig, tgt, force)) { changement_voie(W, v, tgt, fol); return true; }
+  if (move_back) W.V.pos[v] = p1 + 0.5;
+  return false;
+}
+// Reseau::ChangementDeVoie (reseau.cpp:4219-4330): one thread, m_LstVehicles (slot) order
+__global__ void k_lc_sequential(DevNet N, DevVeh V, DevLc C, int n) {
+  if (blockIdx.x || threadIdx.x) return;
+  const DevParams& P = cP_ref();
+  LcView W{N, V, C};
+  for (int v = 0; v < n; v++) {                                       // mandatory pass
+    if (V.status[v] != ST_ALIVE) continue;
+    if (C.vdes[v] != -1) { bool ok = calcul_changement_voie(P, W, v, C.vdes[v], true); C.chgt[v] = 1; if (ok) C.vdes[v] = -1; }
+  }
+  for (int v = 0; v < n; v++) {                                       // discretionary pass
+    int st = V.status[v]; if (st != ST_ALIVE) continue;               // needs a link at index 1
+    if (C.chgt[v]) continue;
+    int lane = V.lane[v]; int link = N.lane_link[lane]; int nl = N.link_nl[link];
+    if (nl < 2) continue;
+    int nV = N.lane_num[lane]; int nVF = nV + 1, nVS = nV - 1;
+    if (C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
+    int mask = C.voies_ok[v];
+    if (nVF >= 0 && nVF < nl && ((mask >> nVF) & 1) && calcul_changement_voie(P, W, v, nVF, false)) continue;
+    if (nVS >= 0 && nVS < nl && ((mask >> nVS) & 1) && calcul_changement_voie(P, W, v, nVS, false)) continue;
+  }
+}
+
+}  // namespace symb200

@@ -34,14 +34,14 @@ struct DevNet {
   const int *lane_link, *lane_num, *lane_prev, *lane_flags; const double* lane_len;
   const int *succ_off, *succ_key, *succ_next;
   const int *sl_off, *sl_i; const double* sl_pos;              // sl_i stride 6
-  const int *link_first, *link_nl, *link_up, *link_type, *link_brick; const double *link_len, *link_vreg;
+  const int *link_first, *link_nl, *link_up, *link_down, *link_type, *link_brick; const double *link_len, *link_vreg;
   const int *route_off, *route_links;
   const int* sl_col; const double* sl_prop;                    // per stop line, refreshed every step (k_signals)
   int n_lanes, n_links, n_sl;
 };
 
 struct DevVeh {
-  int *status, *id, *cls, *route, *route_pos, *lane, *lane_n, *prev_leader, *flags, *oflags, *memo;
+  int *status, *id, *cls, *route, *route_pos, *lane, *lane_n, *prev_leader, *flags, *oflags, *memo, *vdes;
   double *pos, *vit, *acc, *pos_n, *vit_n, *acc_n, *dn, *cpos, *tcre, *dstp, *hent, *tsort;
   // per-step scratch
   int *ahead, *computed, *ctx_nl, *ctx_lane, *ctx_leader, *ctx_flags;
@@ -396,6 +396,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
     bool reached = ep > llen && ta == 'S' && n.route_links[re - 1] == link;            // TripLeg.cpp:91-117, Position.cpp:394-404
     if (reached) { dest_lane = ln; trav_dest = trav; }
     if (reached || ep <= llen) { lane0 = ln; pos0 = ep; break; }
+    V.vdes[i] = -1;                                                                  // :1505 the desired lane is forgotten when the lane is left
   }
   int of = (fluide ? O_FLUIDE : 0) | (feu ? O_FEU : 0) | (ctx_free ? O_CTXFREE : 0) | (created ? O_CREATED : 0);
   if (dest_lane >= 0) {                                                                // :1512-1527

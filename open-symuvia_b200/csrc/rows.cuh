@@ -240,6 +240,7 @@ __device__ inline void phase_c(const DevParams& P, const DevNet& n, const DevVeh
     bool reached = ep > llen && ta == 'S' && n.route_links[re - 1] == link;
     if (reached) { dest_lane = ln; trav_dest = trav; }
     if (reached || ep <= llen) { lane0 = ln; pos0 = ep; break; }
+    V.vdes[i] = -1;                                                   // vehicule.cpp:1505
   }
   int of = ((bf & B_FLUIDE) ? O_FLUIDE : 0) | (feu ? O_FEU : 0) | ((bf & B_CTXFREE) ? O_CTXFREE : 0) | (created ? O_CREATED : 0);
   if (dest_lane >= 0) {

@@ -436,6 +436,76 @@ def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, 
     return b
 
 
+# ---------------------------------------------------------------------------------------------
+# C3-style corridor: multi-lane, multi-class, lane changing, off-ramps reachable from the right lane only
+# ---------------------------------------------------------------------------------------------
+def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_steps=600, seed=42, classes=None, type_coefs=None,
+             offramp_every=0, offramp_share=0.1, preseed_density=0.0, chgtvoie=True, dst_chgtvoie=200.0, dst_force=0.0, phi_force=1.0,
+             slow_lane_speed=None, shuffle=False) -> NetBuilder:
+    """n_links consecutive links joined by pass-through distributors (lane k -> lane k).  Every `offramp_every` nodes a one-lane
+    off-ramp leaves from lane 0 only, so exiting vehicles must reach lane 0 in the mandatory zone (`chgtvoie_dstfin`).
+    Demand enters at the first link (lanes drawn uniformly); `preseed_density` (veh/m/lane) pre-seeds every lane.
+    The merges (on-ramp Convergents) of BASELINE config C3 are row A10 and not generated."""
+    rng = np.random.default_rng(seed)
+    b = NetBuilder(n_steps=n_steps, seed=seed, chgtvoie=chgtvoie, dst_chgtvoie=dst_chgtvoie)
+    b.params[F.P_PHI_FORCE] = phi_force
+    b.params[F.P_DST_FORCE] = dst_force
+    cl = classes or [VL, PL]
+    for c in cl:
+        b.add_class(c)
+    tc = type_coefs or ([0.85, 0.15] if len(cl) == 2 else None)
+    nodes = [b.add_node("E", "E0", (0.0, 0.0))]
+    for j in range(1, n_links):
+        nodes.append(b.add_node("R", f"R{j}", (j * length, 0.0)))
+    nodes.append(b.add_node("S", "S_end", (n_links * length, 0.0)))
+    main = []
+    for j in range(n_links):
+        main.append(b.add_link(f"M{j}", nodes[j], nodes[j + 1], n_lanes, length, vit_reg, "S" if j == n_links - 1 else "R",
+                               geom=(j * length, 0.0, (j + 1) * length, 0.0)))
+    ramps = {}
+    for j in range(1, n_links):
+        for k in range(n_lanes):
+            b.add_succ(b.lane_of(main[j - 1], k), main[j], b.lane_of(main[j], k), 1.0, 1)
+        if offramp_every and j % offramp_every == 0:
+            s = b.add_node("S", f"S{j}", (j * length, -100.0))
+            r = b.add_link(f"X{j}", nodes[j], s, 1, 150.0, vit_reg * 0.6, "S", geom=(j * length, 0.0, j * length + 100.0, -100.0))
+            b.add_succ(b.lane_of(main[j - 1], 0), r, b.lane_of(r, 0), 1.0, 1)
+            ramps[j] = (r, b.add_exit(s, r))
+    x_end = b.add_exit(nodes[-1], main[-1])
+    through = b.add_route(main)
+    dests = [(x_end, 1.0 - (offramp_share if ramps else 0.0), [(through, 1.0)])]
+    ramp_routes = {}
+    for j, (r, x) in ramps.items():
+        ramp_routes[j] = b.add_route(main[:j] + [r])
+        dests.append((x, offramp_share / len(ramps), [(ramp_routes[j], 1.0)]))
+    if demand > 0:
+        b.add_entry(nodes[0], main[0], [(1e12, demand)], dests, type_coefs=tc)
+    if preseed_density > 0:
+        seeds = []
+        for j, k in enumerate(main):
+            # routes starting at link j (through or a later ramp)
+            later = [jj for jj in ramps if jj > j]
+            for num in range(n_lanes):
+                m = max(0, int(preseed_density * length))
+                pos = np.sort(rng.random(m) * (length - 20.0) + 5.0)
+                pos = pos[np.concatenate(([True], np.diff(pos) > 13.0))] if m else pos
+                for q, p0 in enumerate(pos):
+                    c = int(rng.random() < 0.15) if len(cl) > 1 else 0
+                    if later and rng.random() < offramp_share:
+                        jj = later[int(rng.integers(len(later)))]
+                        rt = b.add_route(main[j:jj] + [ramps[jj][0]])
+                    else:
+                        rt = b.add_route(main[j:])
+                    nxt = pos[q + 1] - p0 if q + 1 < len(pos) else 1e9
+                    v = min(min(cl[c]["vx"], vit_reg), max(0.0, -cl[c]["w"] * (nxt * cl[c]["kx"] - 1.0)))
+                    seeds.append((c, b.lane_of(k, num), rt, float(p0), float(v)))
+        if shuffle:
+            seeds = [seeds[p] for p in rng.permutation(len(seeds))]
+        for (c, ln, rt, p0, v) in seeds:
+            b.add_init_vehicle(c, ln, rt, 0, p0, v)
+    return b
+
+
 def config(name: str, **kw) -> NetBuilder:
     """Named BASELINE.json configurations."""
     if name == "C1":

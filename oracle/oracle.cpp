@@ -143,7 +143,7 @@ struct Veh {
   double inst_creation = 0, creation_pos = 0, generation_pos = UNDEF_POSITION, heure_entree = 0, inst_sortie = -1;
   double inst_dest_reached = 0; int dest_enter_lane = -1;
   double dst_parcourue = 0, vit_reg_tuy_act = 0;
-  int voie_desiree = -1; int prev_lane = -1;
+  int voie_desiree = -1; int prev_lane = -1; bool b_chgt_voie = false; std::vector<char> voies_ok;
   std::vector<int> used_lanes; std::map<int, double> tirage;      // m_LstUsedLanes, m_NextVoieTirage
   std::vector<int> tuyaux_parcourus;
   std::unique_ptr<Ctx> ctx, prev_ctx;
@@ -157,7 +157,7 @@ struct Exited { int id; double inst; };
 struct Sim {
   // parameters
   double dt = 1, duree = 0; unsigned seed = 0; bool accbornee = false; double relax = 1; bool chgtvoie = false;
-  double dst_chgtvoie = 50; double bevel = 0;
+  double dst_chgtvoie = 50; double bevel = 0; double dst_chgtvoie_force = -1, phi_chgtvoie_force = 1; int ordre_chgtvoie = 1;
   std::vector<Cls> cls; std::vector<Link> links; std::vector<Lane> lanes; std::vector<Ctrl> ctrls;
   std::vector<std::vector<int>> routes; std::vector<Entry> entries; std::vector<Exit> exits;
   std::vector<int> node_type, node_ctrl;
@@ -184,7 +184,7 @@ struct Sim {
     Flat f; if (!f.load(path)) return false;
     const double* P = f.D("params");
     dt = P[0]; duree = P[1] * dt; seed = (unsigned)P[2]; accbornee = P[3] != 0; relax = P[4]; chgtvoie = P[5] != 0;
-    dst_chgtvoie = P[6];
+    dst_chgtvoie = P[6]; phi_chgtvoie_force = P[9] > 0 ? P[9] : 1.0; dst_chgtvoie_force = P[10] > 0 ? P[10] : -1.0;   // reseau.cpp:272-273, :5601-5604
     const double* C = f.D("cls"); size_t T = f.N("cls") / 24;
     for (size_t i = 0; i < T; i++) { const double* c = C + 24 * i; Cls k; k.w = c[0]; k.kx = c[1]; k.vx = c[2]; k.esp = c[3];
       k.decel = c[4]; k.tau_lc = c[5]; k.pi_rab = c[6]; k.law = (int)c[7];
@@ -379,6 +379,185 @@ struct Sim {
       if ((c->pos[1] > v->pos[1] || (v->pos[0] == UNDEF_POSITION && c->pos[1] == v->pos[1])) && c->pos[1] <= pv && c != v) {
         if (c->pos[1] == pv) l.push_back(c); else { l.resize(1); l[0] = c; pv = c->pos[1]; } } }
     return get_last_vehicule(l);
+  }
+
+
+  // ------------------------------------------------------------------------------------------
+  // lane changing (row A9): reseau.cpp:4219-4330, vehicule.cpp:2217-2456, :2657-2711, :4749-5039,
+  // carFollowing/AbstractCarFollowing.cpp:61-329, reseau.cpp:3255-3295, :3374-3520, :4446-4560, :14084-14128
+  bool mvt_autorise(int lane, int next_link) const { if (next_link < 0) return false; for (auto& q : lanes[lane].succ) if (q.key_link == next_link) return true; return false; }
+  void calcul_voies_possibles(Veh* v) {                                                      // vehicule.cpp:4749-4940
+    if (v->link[1] < 0 || v->lane[1] < 0) return;
+    const Link& T = links[v->link[1]]; v->voies_ok.assign(T.n_lanes, 0);
+    auto plain = [&]() { for (int i = 0; i < T.n_lanes; i++) v->voies_ok[i] = !chgt_voie_obligatoire(T.first_lane + i); };
+    if (v->pos[1] > lanes[v->lane[1]].length - dst_chgtvoie) {                               // :4805 mandatory-changing zone
+      bool has_cnx = T.type_aval != 0 && T.brick < 0;                                        // :4809-4830 (CAF downstream, or a simple connection)
+      if (has_cnx) {
+        if (T.type_aval == 'S' || T.type_aval == 'P') { for (int i = 0; i < T.n_lanes; i++) v->voies_ok[i] = 1; return; }   // :4835-4846
+        for (int i = 0; i < T.n_lanes; i++) v->voies_ok[i] = mvt_autorise(T.first_lane + i, v->next_link) && !chgt_voie_obligatoire(T.first_lane + i);   // :4892-4909
+      } else plain();
+    } else plain();
+  }
+  void calcul_voie_desiree(Veh* v) {                                                         // vehicule.cpp:4942-5038
+    if (v->voie_desiree != -1) return;
+    if (v->lane[1] < 0) { v->voie_desiree = -1; return; }
+    if (v->voies_ok.empty()) return;
+    int nV = lanes[v->lane[1]].num; int n = (int)v->voies_ok.size();
+    if (!v->voies_ok[nV]) {
+      if (nV - 1 >= 0 && v->voies_ok[nV - 1]) { v->voie_desiree = nV - 1; return; }
+      if (nV + 1 < n && v->voies_ok[nV + 1]) { v->voie_desiree = nV + 1; return; }
+      for (int k = nV - 2; k >= 0; k--) if (v->voies_ok[k]) { v->voie_desiree = nV - 1; return; }   // one lane per time step (no reserved lanes in scope)
+      for (int k = nV + 2; k < n; k++) if (v->voies_ok[k]) { v->voie_desiree = nV + 1; return; }
+    }
+  }
+  Veh* get_first_vehicule_lane(int lane) {                                                   // reseau.cpp:3255-3295
+    Veh* r = nullptr; double p = 0;
+    for (Veh* c : lane_set[lane]) if (p <= c->pos[1]) { r = c; p = c->pos[1]; }
+    return r;
+  }
+  Veh* get_first_vehicule(std::vector<Veh*>& l) {                                            // reseau.cpp:14084-14128
+    if (l.size() == 1) return l[0];
+    if (l.empty()) return nullptr;
+    n_ties++;
+    for (size_t i = 0; i < l.size(); i++) { Veh* ld = get_leader_of(l[i]); if (!ld) return l[i];
+      bool found = false; for (size_t j = 0; j < l.size() && !found; j++) if (i != j && ld->id == l[j]->id) found = true;
+      if (!found) return l[i]; }
+    return l.back();
+  }
+  Veh* get_near_amont_vehicule(int lane, double pos, double dstmax, Veh* excl) {             // reseau.cpp:3374-3520
+    std::vector<Veh*> l; if (lane < 0) return nullptr;
+    if (dstmax < 0) dstmax = 9999;
+    double ptmp = -99999;
+    for (Veh* c : lane_set[lane]) if (pos > c->pos[1] && c->pos[1] >= ptmp) { if (!excl || excl->id != c->id) {
+      if (c->pos[1] == ptmp) l.push_back(c); else { l.resize(1); l[0] = c; ptmp = c->pos[1]; } } }
+    if (dstmax > 0 && !l.empty() && (pos - ptmp) < dstmax) return get_first_vehicule(l);
+    dstmax -= pos; ptmp = -99999;
+    int pv = lanes[lane].prev_lane;                                                          // VoieMicro::GetPrevVoie
+    if (l.empty() && pv >= 0 && dstmax > 0) {
+      pos = lanes[pv].length + 0.001;
+      for (Veh* c : lane_set[pv]) if (pos >= c->pos[1] && c->pos[1] >= ptmp) { if (!excl || excl->id != c->id) {
+        if (c->pos[1] == ptmp) l.push_back(c); else { l.resize(1); l[0] = c; ptmp = c->pos[1]; } } }
+      lane = pv;
+    }
+    if (!l.empty()) { if ((pos - ptmp) < dstmax) return get_first_vehicule(l); else return nullptr; }
+    // :3486-3517 single upstream link with a single lane behind a punctual connection: not present in the flattened tables
+    return get_first_vehicule(l);
+  }
+  double distance_entre_vehicules(Veh* a, Veh* b) {                                          // reseau.cpp:4446-4560 (start of step)
+    if (!a || !b) return 9999;
+    if (a->link[1] == b->link[1]) return fabs(b->pos[1] - a->pos[1]);
+    if (a->link[1] < 0) { if (a->lane[1] == b->lane[1]) return b->pos[1];
+      if (links[lanes[a->lane[1]].link].down_node == links[b->link[1]].up_node) return lanes[a->lane[1]].length + b->pos[1]; return 9999; }
+    if (b->link[1] < 0) { if (b->lane[1] == a->lane[1]) return a->pos[1];
+      if (b->lane[1] >= 0 && links[lanes[b->lane[1]].link].down_node == links[a->link[1]].up_node) return lanes[b->lane[1]].length + a->pos[1]; return 9999; }
+    if (links[a->link[1]].down_node == links[b->link[1]].up_node) return lanes[a->lane[1]].length - a->pos[1] + b->pos[1];
+    if (links[b->link[1]].down_node == links[a->link[1]].up_node) return lanes[b->lane[1]].length - b->pos[1] + a->pos[1];
+    return 9999;
+  }
+  // CDiagrammeFondamental::CalculVitEqDiagrOrig(concentration) DiagFonda.cpp:116-172, :221-276 (bFluide = true)
+  static double vit_eq(double w, double kx, double vx, double conc) {
+    double kc = w * kx / (w - vx); double debit;
+    if (conc <= kc) { debit = vx * conc; if (fabs(debit) < DBL_EPSILON) debit = 0; }
+    else { debit = w * (conc - kx); if (fabs(debit) < DBL_EPSILON) debit = 0; }
+    if (fabs(debit) < DBL_EPSILON && fabs(conc) < DBL_EPSILON) return 0;
+    double vit = conc < DBL_EPSILON ? vx : debit / conc;
+    if (fabs(vit) < DBL_EPSILON) vit = 0;
+    return vit;
+  }
+  // AbstractCarFollowing::TestLaneChange AbstractCarFollowing.cpp:61-329 (no pull-back, no ghost, synchronous mandatory mode)
+  bool test_lane_change(Veh* v, Veh* fol, Veh* lead, Veh* lead_orig, int tgt_lane, bool force) {
+    const Cls& c = cls[v->cls]; double kc = c.k_crit();
+    double si;
+    if (lead_orig) si = lead_orig->pos[1] - v->pos[1];
+    else if (force) si = std::max<double>(1 / v->kx, lanes[v->lane[1]].length - v->pos[1]);
+    else si = 1 / kc;
+    double sf = (fol && lead) ? distance_entre_vehicules(lead, fol) : 1 / kc;
+    double vit = std::min<double>(v->vit_reg_tuy_act, v->vx);
+    double dem_orig = std::min<double>(vit / si, c.debit_max());                             // :130-146
+    double dem_dest;
+    if (fol) dem_dest = std::min<double>(fol->vx / sf, cls[fol->cls].debit_max());          // :149-153
+    else dem_dest = std::min<double>(vit / sf, c.debit_max());
+    double off_dest = lead ? std::min<double>((lead->kx - (1 / sf)) * (-1) * lead->w, cls[lead->cls].debit_max()) : c.debit_max();   // :158-161
+    double pi;
+    if (force) pi = 1 / dt;                                                                  // :168-173
+    else {
+      double vtgt;
+      if (sf > 0) { const Veh* d = lead ? lead : v; vtgt = vit_eq(d->w, d->kx, d->vx, 1 / sf); if (lead) vtgt = lead->vit[1]; } else vtgt = 0;   // :177-194
+      vtgt = std::min<double>(vtgt, links[lanes[tgt_lane].link].vit_reg);
+      if (!fol && lead) { vtgt = std::max<double>(vtgt, lead->vit[1]); vtgt = std::min<double>(vtgt, lead->vit_reg_tuy_act); }
+      vtgt = std::min<double>(vtgt, v->vit_max);
+      double vorg = DBL_MAX;
+      if (si > 0) { const Veh* d = lead_orig ? lead_orig : v; vorg = vit_eq(d->w, d->kx, d->vx, 1 / si);
+        if (c.law == 0 && v->ctx && v->ctx->deltaN < 1 && lead_orig) vorg = lead_orig->vit[1]; }   // :218-222
+      else vorg = lead_orig ? lead_orig->vit[1] : v->vit[1];
+      vorg = std::min<double>(vorg, links[v->link[1]].vit_reg); vorg = std::min<double>(vorg, v->vit_max);
+      pi = std::max<double>(0., vtgt - vorg) / (links[v->link[1]].vit_reg * c.tau_lc);        // :246
+      if (pi < 0.000001) return false;
+    }
+    double phi;
+    if (force && links[v->link[1]].length - v->pos[1] < dst_chgtvoie_force) phi = phi_chgtvoie_force;   // :254-257
+    else {
+      if (!fol || !lead) dem_dest = 0;                                                       // :260-261
+      if (dem_dest > 0) phi = std::min<double>(1., off_dest / dem_dest) * pi * dem_orig / vit * dt * si;
+      else phi = pi * dem_orig / vit * dt * si;
+    }
+    double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER;                                         // :324
+    return r < phi;
+  }
+  void changement_voie(Veh* v, int tgt_lane, Veh* fol) {                                    // vehicule.cpp:2657-2711
+    v->b_chgt_voie = true;
+    int old = v->lane[1];
+    set_voie_ant(v, tgt_lane);
+    v->pos[1] = v->pos[1] * lanes[tgt_lane].length / lanes[old].length;
+    if (fol && fol->link[1] == v->link[1]) v->pos[1] = std::max<double>(v->pos[1], fol->pos[1]);
+    v->voie_desiree = -1;
+    calcul_next_voie(v, v->lane[1]);                                                         // :2700 (consumes the lane's memoised draw)
+  }
+  bool calcul_changement_voie(Veh* v, int tgt_num, bool force) {                            // vehicule.cpp:2248-2457
+    if (v->pos[1] <= UNDEF_POSITION) return false;                                           // :2291
+    if (v->b_chgt_voie) return false;                                                        // :2297
+    int lane = v->lane[1]; bool desired = v->voie_desiree != -1;
+    if (get_first_vehicule_lane(lane) == v && !chgt_voie_obligatoire(lane) && !desired) return false;   // :2302-2307
+    int tgt = links[v->link[1]].first_lane + tgt_num;
+    double ratio_pos = lanes[tgt].length / lanes[lane].length * v->pos[1];
+    bool move_back = false;
+    Veh* same = get_near_aval_vehicule(tgt, ratio_pos - 0.01, v);                            // :2378
+    if (same && fabs(lanes[tgt].length / lanes[lane].length * v->pos[1] - same->pos[1]) < 0.01) {
+      if (fabs(v->pos[1] - lanes[lane].length) < 0.01) {
+        if (force && same->voie_desiree == lanes[lane].num && v->voie_desiree == lanes[same->lane[1]].num && v->vit[1] < 0.01 && same->vit[1] < 0.01) {
+          changement_voie(v, tgt, nullptr); changement_voie(same, lane, nullptr); return true;          // switch-switch :2383-2393
+        }
+        v->pos[1] = v->pos[1] - 0.5; move_back = true;
+      } else return false;
+    }
+    double q = lanes[tgt].length / lanes[lane].length * v->pos[1] + 0.001;
+    Veh* fol = get_near_amont_vehicule(tgt, q, -1.0, v);                                     // :2403
+    Veh* lead = get_near_aval_vehicule(tgt, q, v);                                           // :2404
+    if (!lead && (chgt_voie_obligatoire(lane) || desired)) {                                 // :2417-2434 (merge non-priority exception: row A10)
+      int nx = calcul_next_voie(v, tgt);
+      if (nx >= 0) lead = get_near_aval_vehicule(nx, 0, nullptr);
+    }
+    Veh* lead_orig = get_prev_vehicule(v);                                                   // :2439
+    if (!lead_orig && !chgt_voie_obligatoire(lane) && !desired && !force) return false;   // :2440-2442 (the reference returns here without undoing the 0.5 m move-back)
+    if (test_lane_change(v, fol, lead, lead_orig, tgt, force)) { changement_voie(v, tgt, fol); return true; }
+    if (move_back) v->pos[1] = v->pos[1] + 0.5;
+    return false;
+  }
+  void changement_de_voie() {                                                                // reseau.cpp:4219-4330
+    for (Veh* v : lst) v->b_chgt_voie = false;
+    for (Veh* v : lst) if (v->lane[1] >= 0 && v->voie_desiree != -1) {                       // mandatory pass
+      bool ok = calcul_changement_voie(v, v->voie_desiree, true);
+      v->b_chgt_voie = true;
+      if (ok) v->voie_desiree = -1;
+    }
+    for (Veh* v : lst) if (v->lane[1] >= 0 && !v->b_chgt_voie && v->link[1] >= 0) {          // discretionary pass
+      int nV = lanes[v->lane[1]].num, n = links[v->link[1]].n_lanes;
+      int nVF = nV + 1, nVS = nV - 1;
+      if (ordre_chgtvoie == 2) { nVF = nV - 1; nVS = nV + 1; }
+      if (nVF >= 0 && nVF < n && v->voies_ok[nVF] && calcul_changement_voie(v, nVF, false)) continue;
+      if (nVS >= 0 && nVS < n && v->voies_ok[nVS] && calcul_changement_voie(v, nVS, false)) continue;
+      // pull-back (:4320-4326) only from reserved lanes: none in scope
+    }
   }
 
   // ------------------------------------------------------------------------------------------
@@ -683,8 +862,8 @@ struct Sim {
       if (v->lane[1] >= 0) lane_set[v->lane[1]].insert(v);
       if (v->link[1] >= 0) {
         if (v->next_link < 0) v->next_link = calcul_next_tuyau(v, v->link[1]);
-        // CalculVoiesPossibles / CalculVoieDesiree (vehicule.cpp:4749-5039) only feed the lane-change
-        // procedure (row A9, pending); they draw no random numbers.
+        calcul_voies_possibles(v);                                                           // :3951
+        calcul_voie_desiree(v);                                                              // :3953
       }
     }
   }
@@ -864,7 +1043,7 @@ struct Sim {
     activate_api_vehicles(t);                                                                // :2233-2240
     init_vehicules();                                                                        // :2250
     for (auto& e : entries) creation_vehicules(e, t);                                       // :2255 -> :14143
-    // ChangementDeVoie :14181 (row A9, pending) ; ComputeFirstVehicules :14184 (only consumed by flux nodes)
+    if (chgtvoie) changement_de_voie();                                                      // :14181 (ComputeFirstVehicules :14184 only feeds flux nodes)
     for (size_t i = 0; i < lst.size(); i++) { std::vector<int> ids; calcul_trafic_ex(lst[i], t, ids); }   // MiseAJourVehicules :3827-3865
     for (auto& e : entries) insertion_veh_en_attente(e, t);                                 // :14293-14296
     // Convergent::CalculInsertion :14310-14314 (row A10, pending)

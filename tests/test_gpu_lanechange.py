@@ -1,0 +1,47 @@
+"""Row A9 — lane changing (Reseau::ChangementDeVoie reseau.cpp:4219-4330, Vehicule::CalculChangementVoie vehicule.cpp:2384-2760):
+the CUDA path against the oracle on multi-lane corridors.  Lane assignment, list order and draw count bit-exact."""
+import importlib
+
+import pytest
+
+from tests.parity import run_parity
+
+synth = importlib.import_module("open-symuvia_b200.synth")
+pkg = importlib.import_module("open-symuvia_b200")
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "plain3": dict(n_links=4, length=400.0, n_lanes=3, demand=1.0, n_steps=300),
+    "offramps": dict(n_links=6, length=500.0, n_lanes=3, demand=1.2, offramp_every=2, preseed_density=0.03, shuffle=True, n_steps=300),
+    "two_lanes_dense": dict(n_links=5, length=300.0, n_lanes=2, demand=0.9, offramp_every=1, offramp_share=0.25, preseed_density=0.06, n_steps=300),
+    "forced": dict(n_links=6, length=400.0, n_lanes=3, demand=1.4, offramp_every=3, offramp_share=0.3, preseed_density=0.08,
+                   dst_force=80.0, phi_force=3.0, shuffle=True, n_steps=300),
+    "four_lanes": dict(n_links=4, length=600.0, n_lanes=4, demand=1.6, offramp_every=2, preseed_density=0.05, n_steps=240),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_lane_change_parity(name):
+    kw = dict(CASES[name])
+    b = synth.corridor(**kw)
+    st = run_parity(b, kw["n_steps"], check_every=1)
+    assert st["worst"] == 0.0
+    assert st["overflow"] == 0
+
+
+def test_lane_changes_happen():
+    """the parity above would be vacuous without changes: the corridor with off-ramps must produce them"""
+    import os
+    import tempfile
+    b = synth.corridor(n_links=6, length=500.0, n_lanes=3, demand=1.2, offramp_every=2, preseed_density=0.03, shuffle=True, n_steps=200)
+    fd, path = tempfile.mkstemp(suffix=".symflat")
+    os.close(fd)
+    try:
+        b.write(path)
+        g = pkg.Engine(path)
+        for _ in range(200):
+            g.step()
+        assert g.counter(pkg.CNT_LANE_CHANGES) > 20
+        g.close()
+    finally:
+        os.unlink(path)
