@@ -214,6 +214,7 @@ __global__ void k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n, const int* l
   int st = V.status[i];
   if (st != ST_ALIVE && st != ST_NEW) return;
   int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow, rows, posidx[i], &LD);
+  V.vit_n[i] = V.vit[i];                           // initial guess of the relaxation (flow.cuh)
   if (d) atomicAdd(draws, (unsigned)d);
 }
 
@@ -244,7 +245,7 @@ __global__ void k_entries(DevNet N, DevVeh V, DevLaneDyn LD, const EntryDesc* de
     int own_leader = d.pret_slot >= 0 ? d.pret_slot : LD.tail[d.lane];
     int dr = context_one(cP, N, V, LD.tail, w, own_leader, overflow);
     if (dr) atomicAdd(draws, (unsigned)dr);
-    follow_one(cP, N, V, LD, w, true, inst);
+    follow_one(cP, N, V, LD, w, true, inst, V.cpos[w]);
     if (V.pos_n[w] > SYM_UNDEF) {
       copy_row(V, w, d.dst_slot);
       V.status[d.dst_slot] = ST_NEW; V.status[w] = ST_DEAD; V.computed[d.dst_slot] = 1;
@@ -420,9 +421,9 @@ struct symgpu_ctx {
   // per step
   DBuf<int> sl_col; DBuf<double> sl_prop;
   DBuf<int> lane_count, lane_start, lane_fill, lane_tail, exit_winner, bsum, order, entre, sorti, stat;
-  DBuf<int> f_posidx, f_isfront, f_seg_len, f_seg_dep, f_segpos, f_minslot, f_first_waiter, f_next_waiter, f_cut, f_queue, f_A, f_A2, f_Mn, f_Mn2, f_oncyc, f_cid;
+  DBuf<int> f_posidx, f_isfront, f_seg_len, f_seg_dep, f_segpos, f_minslot, f_cut, f_fronts, rl_lead, f_A, f_A2, f_Mn, f_Mn2, f_oncyc, f_cid;
   DBuf<double> rows, b_goal; DBuf<int> b_flags;
-  DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DevFlow df; int flow_grid = 0; FlowCtl* h_ctl = nullptr;
+  DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DBuf<double> vl_used; DevFlow df; FlowCtl* h_ctl = nullptr; FlowCtl* h_ctl_seed = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
   DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
@@ -437,7 +438,7 @@ struct symgpu_ctx {
   DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
-  long long lane_changes = 0;
+  long long lane_changes = 0; int n_sms = 148;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
@@ -467,7 +468,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   l.next_sortie = c->next_sortie.p; l.exit_winner = c->exit_winner.p;
   DevFlow& fl = c->df;
   fl.order = c->order.p; fl.posidx = c->f_posidx.p; fl.isfront = c->f_isfront.p; fl.seg_len = c->f_seg_len.p; fl.seg_dep = c->f_seg_dep.p; fl.segpos = c->f_segpos.p;
-  fl.minslot = c->f_minslot.p; fl.first_waiter = c->f_first_waiter.p; fl.next_waiter = c->f_next_waiter.p; fl.cut = c->f_cut.p; fl.queue = c->f_queue.p;
+  fl.minslot = c->f_minslot.p; fl.cut = c->f_cut.p; fl.fronts = c->f_fronts.p;
   fl.ctl = c->f_ctl.p; fl.A = c->f_A.p; fl.A2 = c->f_A2.p; fl.Mn = c->f_Mn.p; fl.Mn2 = c->f_Mn2.p; fl.oncyc = c->f_oncyc.p; fl.cid = c->f_cid.p; fl.rootkey = c->f_rootkey.p;
   DevLc& lc = c->dlc;
   lc.order = c->order.p; lc.lane_start = c->lane_start.p; lc.lane_count = c->lane_count.p; lc.vdes = c->v_vdes.p; lc.voies_ok = c->lc_voies_ok.p; lc.chgt = c->lc_chgt.p;
@@ -587,14 +588,13 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->exit_winner.alloc(L)); CK(cudaMemset(c->exit_winner.p, 0xff, L * sizeof(int))); CK(c->next_sortie.alloc(L));
   CK(c->bsum.alloc((L + kScanB - 1) / kScanB + 1)); CK(c->order.alloc(cap)); CK(c->entre.alloc((size_t)K * T)); CK(c->sorti.alloc((size_t)K * T));
   CK(c->stat.alloc(16)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
-  for (DBuf<int>* b : {&c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_first_waiter, &c->f_next_waiter, &c->f_cut,
-                       &c->f_queue, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
+  for (DBuf<int>* b : {&c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_cut,
+                       &c->f_fronts, &c->rl_lead, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
   CK(c->t_flag.alloc(cap)); CK(c->t_off.alloc(cap)); CK(c->t_bsum.alloc(cap / kScanB + 2)); CK(c->t_id.alloc(cap)); CK(c->t_lane.alloc(cap));
   CK(c->t_pos.alloc(cap)); CK(c->t_vit.alloc(cap)); CK(c->t_acc.alloc(cap));
-  CK(c->f_rootkey.alloc(cap)); CK(c->rows.alloc((size_t)cap * kRowD)); CK(c->b_goal.alloc(cap)); CK(c->b_flags.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
-  { int nb = 0, sms = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_flow, 128, 0)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    c->flow_grid = std::max(1, nb) * std::max(1, sms); }
-  c->f_queue.free(); CK(c->f_queue.alloc(cap + (size_t)c->flow_grid * 4 + 64));   // one ticket per worker beyond the last segment
+  CK(c->f_rootkey.alloc(cap)); CK(c->rows.alloc(((size_t)cap + 32) * kRowD)); CK(c->b_goal.alloc(cap)); CK(c->b_flags.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
+  CK(c->vl_used.alloc(cap)); CK(cudaMallocHost(&c->h_ctl_seed, sizeof(FlowCtl))); memset(c->h_ctl_seed, 0, sizeof(FlowCtl)); c->h_ctl_seed->changed[0] = 1;
+  { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)); c->n_sms = std::max(1, sms); }
   CK(c->exited.alloc(cap)); CK(c->edesc.alloc(std::max(1, n_entry_lanes))); CK(c->eresult.alloc(std::max(1, n_entry_lanes)));
   // vehicles
   for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
@@ -624,8 +624,8 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
                        &c->link_nl, &c->link_up, &c->link_type, &c->link_brick, &c->route_off, &c->route_links, &c->ctrl_seq_off, &c->ctrl_nseq, &c->seq_sig_off,
                        &c->seq_nsig, &c->sig_in, &c->sig_out, &c->exit_lanes, &c->exit_nl, &c->sl_col, &c->lane_count, &c->lane_start, &c->lane_fill, &c->lane_tail,
                        &c->exit_winner, &c->bsum, &c->order, &c->entre, &c->sorti, &c->stat, &c->eresult, &c->v_status, &c->v_id,
-                       &c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_first_waiter, &c->f_next_waiter, &c->f_cut,
-                       &c->f_queue, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid,
+                       &c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_cut,
+                       &c->f_fronts, &c->rl_lead, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid,
                        &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_memo, &c->v_ahead, &c->v_computed,
                        &c->v_ctx_nl, &c->v_ctx_lane, &c->v_ctx_leader, &c->v_ctx_flags}) b->free();
   for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
@@ -636,6 +636,8 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); for (int k = 0; k < 2; k++) if (c->t_done[k]) cudaEventDestroy(c->t_done[k]);
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
+  if (c->h_ctl_seed) cudaFreeHost(c->h_ctl_seed);
+  c->vl_used.free();
   if (c->h_stat) cudaFreeHost(c->h_stat);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -717,13 +719,14 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
 
 // per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
 enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_LC, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_COUNT };
-static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_lane_change", "k_seg", "k_flow",
+static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_lane_change", "k_seg", "k_relax",
                                               "k_cyc_loops", "k_place", "k_entries", "k_final"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
 #define LAUNCH(c) ((c)->launches++)
 #define KBEGIN(c, kid) do { if ((c)->profile) prof_begin(c, kid); } while (0)
 #define KEND(c) do { LAUNCH(c); if ((c)->profile) prof_end(c); } while (0)
+#define KEND0(c) do { if ((c)->profile) prof_end(c); } while (0)
 
 static cudaEvent_t prof_event(symgpu_ctx* c) {
   if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
@@ -832,32 +835,33 @@ static int step_back(symgpu_ctx* c) {
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
     KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
-    int seg_done = 0;
-    for (int round = 0;; round++) {
-      CK(cudaMemsetAsync(c->f_queue.p, 0xff, ((size_t)n_sorted + (size_t)c->flow_grid * 4 + 64) * sizeof(int), s));
-      CK(cudaMemsetAsync(c->f_ctl.p, 0, 4 * sizeof(int), s));          // q_head, n_pushed, n_started, n_completed
-      KBEGIN(c, KID_FOLLOW);
-      k_flow_reset<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted); LAUNCH(c);
-      k_flow_init<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted); LAUNCH(c);
-      k_flow<<<c->flow_grid, 128, 0, s>>>(c->dn, c->dv, c->dl, c->df, c->rows.p, c->b_goal.p, c->b_flags.p, c->t);
-      KEND(c);
-      c->passes++;
+    // leader loops: always looked for (the segment graph is small), cut where the reference's recursion would cut them
+    { int Klev = 1; while ((1LL << (2 * Klev)) < (long long)std::max(4, n_sorted)) Klev++;
+      Klev++;
+      const int Gs = std::min(G(n_sorted), c->n_sms * 8);
+      KBEGIN(c, KID_LOOP);
+      k_cyc_init<<<Gs, B, 0, s>>>(c->df); LAUNCH(c);
+      int flip = 0;
+      for (int k = 0; k < Klev; k++) { k_cyc_jump<<<Gs, B, 0, s>>>(c->df, flip); LAUNCH(c); flip ^= 1; }
+      k_cyc_mark<<<Gs, B, 0, s>>>(c->dv, c->df, flip, by_id); LAUNCH(c);
+      k_cyc_break<<<Gs, B, 0, s>>>(c->dv, c->df, c->rows.p, c->counters.p);
+      KEND(c); }
+    // relaxation sweeps until one changes nothing (flow.cuh)
+    KBEGIN(c, KID_FOLLOW);
+    for (int sweep = 0;;) {
+      int* ch = c->f_ctl.p->changed;                                     // device address arithmetic only
+      if (sweep > 0) CK(cudaMemcpyAsync(ch, c->h_ctl_seed->changed, sizeof(int) * (kRelaxBatch + 1), cudaMemcpyHostToDevice, s));
+      for (int j = 0; j < kRelaxBatch; j++, sweep++) {
+        k_relax<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, sweep == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
+      }
       CK(cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
-      seg_done += c->h_ctl->n_completed;
-      if (c->h_ctl->n_vehicles_done >= n_sorted) break;
-      if (round > n_sorted) { g_err = "follow rounds do not terminate"; return SYMGPU_E_CUDA; }
-      int R = std::max(2, c->h_ctl->n_segments - seg_done), Klev = 1;
-      while ((1 << Klev) < R) Klev++;
-      Klev++;
-      KBEGIN(c, KID_LOOP);
-      k_cyc_init<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted); LAUNCH(c);
-      int flip = 0;
-      for (int k = 0; k < Klev; k++) { k_cyc_double<<<G(n_sorted), B, 0, s>>>(c->df, n_sorted, flip); LAUNCH(c); flip ^= 1; }
-      k_cyc_mark<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, flip, by_id); LAUNCH(c);
-      k_cyc_break<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, c->rows.p, n_sorted, c->counters.p);
-      KEND(c);
+      bool done = false;
+      for (int j = 1; j <= kRelaxBatch && !done; j++) { if (c->h_ctl->changed[j] == 0) done = true; else c->passes++; }
+      if (done) break;
+      if (sweep > n_sorted + kRelaxBatch) { g_err = "relaxation does not terminate (leader loop left uncut)"; return SYMGPU_E_CUDA; }
     }
+    KEND0(c);
     KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t); KEND(c);
     }
     if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,

@@ -25,7 +25,7 @@ enum : int { ST_DEAD = 0, ST_ALIVE = 1, ST_NEW = 2 /* entered m_LstVehicles this
 // persistent per-vehicle flags
 enum : int { F_HASCTX = 1, F_PREVFREE = 2 };
 // output flags (same packing as the oracle dump): bit0 regime fluide, bit1 arret au feu, bit2 context free-flow
-enum : int { O_FLUIDE = 1, O_FEU = 2, O_CTXFREE = 4, O_ENDLEG = 16, O_CREATED = 32, O_LINK1NULL = 64 };
+enum : int { O_FLUIDE = 1, O_FEU = 2, O_CTXFREE = 4, O_ENDLEG = 16, O_CREATED = 32, O_LINK1NULL = 64, O_VDESRESET = 128 };
 
 struct DevCls { double w, kx, vx, esp, decel, tau_lc, pi_rab; int law, nplage; double ax[4], vs[4]; };
 struct DevParams { double dt, relax, duree, min_kv, bevel; int accbornee, ncls; DevCls cls[kMaxCls]; double maxinf[kMaxCls]; };
@@ -238,13 +238,17 @@ __device__ inline double decel_limit(const DevParams& P, const DevCls& c, bool c
 // Vehicule::CalculTraficEx (vehicule.cpp:1299-1574), NewellCarFollowing.cpp:53-68,113-136,204-398,
 // GippsCarFollowing.cpp:50-122, IDMCarFollowing.cpp:61-211, Vehicule::CheckNetworkInfluence (:1591-1708),
 // Vehicule::CalculTraficFeux (:1799-1945).
+// `defer` (relaxation sweeps, flow.cuh): the call may be repeated with another leader speed, so nothing it reads is
+// overwritten — creation position from `cpos_in`, creation instant kept, new speed returned through v0_out, the
+// desired-lane reset left to phase C (O_VDESRESET).  vL_in: the leader's new speed the caller looked up.
 __device__ inline void follow_one(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, int i,
-                                  bool leader_computed, double inst) {
+                                  bool leader_computed, double inst, double cpos_in, bool defer = false,
+                                  const double* vL_in = nullptr, double* v0_out = nullptr) {
   const DevCls& c = P.cls[V.cls[i]];
   const bool created = V.ctx_flags[i] & 1;
   double p1 = snap_pos(V.pos[i]); if (p1 <= SYM_UNDEF) p1 = 0.0;
   const double v1 = V.vit[i];
-  double cpos = created ? V.cpos[i] : 0.0;
+  double cpos = created ? cpos_in : 0.0;
   const double dtv = P.dt - fmax(0.0, V.tcre[i]);
   const int nl = V.ctx_nl[i];
   int lanes[kMaxCtx];
@@ -261,7 +265,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
     if (L >= 0) {
       const DevCls& cl = P.cls[V.cls[L]];
       double vL;
-      if (leader_computed) vL = __ldcg(&V.vit_n[L]);   // NewellCarFollowing.cpp:213-216 (written by another SM in the same kernel: read through L2)
+      if (leader_computed) vL = vL_in ? *vL_in : __ldcg(&V.vit_n[L]);   // NewellCarFollowing.cpp:213-216 (written by another SM in the same kernel: read through L2)
       else {                                                                           // :217-230
         double vreg_l = n.link_vreg[n.lane_link[V.lane[L]]];                           // GetVitRegTuyAct of the leader
         if (P.accbornee) vL = fmin(fmin(vreg_l, cl.vx), vL1 + acc_max(c, vL1) * P.dt);
@@ -385,7 +389,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
   double a0 = created ? 0.0 : (dtv != 0 ? (v0 - v1) / dtv : 0.0);                      // :1368-1375
   if (fabs(a0) < 0.000001) a0 = 0;                                                     // vehicule.h:501
   // ---- placement: vehicule.cpp:1377-1527 ------------------------------------------------------------
-  trav = 0; int lane0 = lanes[0]; double pos0 = start; int dest_lane = -1; double trav_dest = 0;
+  trav = 0; int lane0 = lanes[0]; double pos0 = start; int dest_lane = -1; double trav_dest = 0; bool left = false;
   const int ro = n.route_off[route], re = n.route_off[route + 1];
   for (int k = 0; k < nl; k++) {
     int ln = lanes[k]; double sp = k == 0 ? start : 0.0; double llen = len_ex(P, n, ln); double ep = goal - trav + sp;
@@ -396,16 +400,18 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
     bool reached = ep > llen && ta == 'S' && n.route_links[re - 1] == link;            // TripLeg.cpp:91-117, Position.cpp:394-404
     if (reached) { dest_lane = ln; trav_dest = trav; }
     if (reached || ep <= llen) { lane0 = ln; pos0 = ep; break; }
-    V.vdes[i] = -1;                                                                  // :1505 the desired lane is forgotten when the lane is left
+    left = true;                                                                     // :1505 the desired lane is forgotten when the lane is left
   }
   int of = (fluide ? O_FLUIDE : 0) | (feu ? O_FEU : 0) | (ctx_free ? O_CTXFREE : 0) | (created ? O_CREATED : 0);
+  if (left) { if (defer) of |= O_VDESRESET; else V.vdes[i] = -1; }
   if (dest_lane >= 0) {                                                                // :1512-1527
     double ti = goal > 0.0001 ? inst - dtv + dtv * (trav_dest / goal) : inst - dtv;
     V.tsort[i] = ti; of |= O_ENDLEG;
   }
   if (cancel) pos0 = SYM_UNDEF;                                                        // :1567-1571
-  V.pos_n[i] = pos0; V.vit_n[i] = v0; V.acc_n[i] = a0; V.lane_n[i] = lane0;
-  V.cpos[i] = cpos; V.tcre[i] = 0.0;                                                   // :1574
+  V.pos_n[i] = pos0; V.acc_n[i] = a0; V.lane_n[i] = lane0;
+  if (v0_out) *v0_out = v0; else V.vit_n[i] = v0;
+  V.cpos[i] = cpos; if (!defer) V.tcre[i] = 0.0;                                       // :1574
   V.dn[i] = c.law == 0 ? dn_end : 1.0;
   V.prev_leader[i] = L >= 0 ? V.id[L] : -1;
   V.flags[i] = F_HASCTX | (ctx_free ? F_PREVFREE : 0);

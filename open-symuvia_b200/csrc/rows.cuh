@@ -32,6 +32,15 @@ enum { H_CREATED = 1 << 12, H_FLAGA = 1 << 13, H_FLAGB = 1 << 14, H_SLOW = 1 << 
 // phase B result flags
 enum { B_FLUIDE = 1, B_FEU = 2, B_CTXFREE = 4, B_CANCEL = 8, B_SLOWDONE = 16 };
 
+// Rows live in tiles of 32 consecutive order positions, field-major inside a tile (AoSoA): field k of position p is at
+// tile*32*kRowD + k*32 + (p & 31), so a warp reading field k of its 32 vehicles touches one 256-byte line.
+struct Row {
+  double* b;
+  __device__ __forceinline__ double& operator[](int k) const { return b[k * 32]; }
+  __device__ __forceinline__ Row operator+(int k) const { return Row{b + k * 32}; }
+};
+__device__ __forceinline__ Row row_at(const double* rows, int p) { return Row{const_cast<double*>(rows) + (size_t)(p >> 5) * (32 * kRowD) + (p & 31)}; }
+
 __device__ __forceinline__ double pack2(int lo, int hi) { return __hiloint2double(hi, lo); }
 __device__ __forceinline__ int lo32(double d) { return __double2loint(d); }
 __device__ __forceinline__ int hi32(double d) { return __double2hiint(d); }
@@ -40,7 +49,7 @@ __device__ __forceinline__ int hi32(double d) { return __double2hiint(d); }
 __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, double* rows, int p, int i,
                                  const int* lanes, int nl, int L, double gap, double dn0, double dfree, bool created, double start,
                                  double cpos, double dtv) {
-  double* r = rows + (size_t)p * kRowD;
+  const Row r = row_at(rows, p);
   const DevCls& c = P.cls[V.cls[i]];
   const double v1 = V.vit[i];
   double vL1 = 0, vlest = 0; int lcls = 0;
@@ -128,7 +137,7 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
         }
       }
     }
-    double* q = r + R_REC + kRecD * k;
+    const Row q = r + (R_REC + kRecD * k);
     q[0] = llen; q[1] = pf; q[2] = prop; q[3] = ts; q[4] = pack2(ln, fl);
   }
 }
@@ -136,7 +145,7 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
 struct BOut { double goal, v0, dn_end, cpos; int flags; };
 
 // phase B: r = the vehicle's row (shared or global memory), vL = leader's new speed (ignored when no leader / non-Newell).
-__device__ __forceinline__ BOut phase_b(const DevParams& P, const double* r, double vL, double inst) {
+__device__ __forceinline__ BOut phase_b(const DevParams& P, const Row r, double vL, double inst) {
   const int hdr = hi32(r[R_I0]); const int L = lo32(r[R_I0]);
   const DevCls& c = P.cls[hdr & 15];
   const int nl = (hdr >> 8) & 15; const bool created = hdr & H_CREATED;
@@ -169,7 +178,7 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const double* r, dou
   bool fluide = ctx_free, feu = false;
   double mgoal = goal + 1, trav = 0;                                      // vehicule.cpp:1317-1343
   for (int k = 0; k < nl; k++) {
-    const double* q = r + R_REC + kRecD * k;
+    const Row q = r + (R_REC + kRecD * k);
     const double llen = q[0]; const int fl = hi32(q[4]);
     double sp = k == 0 ? start : 0.0; double ep = goal - trav + sp;
     double mini = DBL_MAX; bool infl = false;
@@ -217,10 +226,12 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const double* r, dou
 // phase C: acceleration, placement, destination, bookkeeping (vehicule.cpp:1367-1527, :1567-1574)
 __device__ inline void phase_c(const DevParams& P, const DevNet& n, const DevVeh& V, const double* rows, const double* b_goal,
                                const int* b_flags, int p, double inst) {
-  const double* r = rows + (size_t)p * kRowD;
+  const Row r = row_at(rows, p);
   const int bf = b_flags[p];
-  if (bf & B_SLOWDONE) return;
   const int hdr = hi32(r[R_I0]); const int L = lo32(r[R_I0]); const int i = lo32(r[R_I1]);
+  if (bf & B_SLOWDONE) {                                              // placed by follow_one (deferred form): finish its bookkeeping
+    V.tcre[i] = 0.0; if (V.oflags[i] & O_VDESRESET) V.vdes[i] = -1;
+    return; }
   const int nl = (hdr >> 8) & 15; const bool created = hdr & H_CREATED;
   const double dtv = r[R_DTV], v1 = r[R_V1], start = r[R_START];
   const double goal = b_goal[p];
@@ -231,7 +242,7 @@ __device__ inline void phase_c(const DevParams& P, const DevNet& n, const DevVeh
   double trav = 0; int lane0 = lo32(r[R_REC + 4]); double pos0 = start; int dest_lane = -1; double trav_dest = 0;
   const int route = V.route[i]; const int re = n.route_off[route + 1];
   for (int k = 0; k < nl; k++) {
-    const double* q = r + R_REC + kRecD * k;
+    const Row q = r + (R_REC + kRecD * k);
     int ln = lo32(q[4]); double sp = k == 0 ? start : 0.0; double llen = q[0]; double ep = goal - trav + sp;
     trav += fmin(ep, llen) - sp;
     int link = n.lane_link[ln]; int ta = n.link_type[link];
