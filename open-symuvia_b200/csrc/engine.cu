@@ -208,12 +208,13 @@ __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const
   if (ties) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_TIES], (unsigned long long)ties);
 }
 
-__global__ void k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n, const int* lane_tail, const int* posidx, double* rows, unsigned* draws, int* overflow) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int st = V.status[i];
-  if (st != ST_ALIVE && st != ST_NEW) return;
-  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow, rows, posidx[i], &LD);
+// one thread per position of the lane order: neighbouring threads are neighbours on a lane, so they walk the same context
+// lanes, stop lines and movements (little divergence, table reads shared through L1) and their rows are written coalesced
+__global__ void k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  int i = order[p];
+  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow, rows, p, &LD);
   V.vit_n[i] = V.vit[i];                           // initial guess of the relaxation (flow.cuh)
   if (d) atomicAdd(draws, (unsigned)d);
 }
@@ -830,7 +831,7 @@ static int step_back(symgpu_ctx* c) {
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
   if (n > 0) {
-    KBEGIN(c, KID_CONTEXT); k_context<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dl, n, c->lane_tail.p, c->f_posidx.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c);
+    if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT); k_context<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
