@@ -3,10 +3,17 @@
 // Reseau::ChangementDeVoie (reseau.cpp:4219-4330) is a sequential loop over m_LstVehicles: every acceptance test draws from the
 // one global random stream (AbstractCarFollowing.cpp:324) and a successful change moves the vehicle at once (vehicule.cpp:2674),
 // which changes the tests — and the number of draws — of the vehicles that come later in the list.  Bit-exact lane assignment
-// therefore needs the reference's order.  This first device version keeps that order literally: k_lc_prepare evaluates the
-// per-vehicle, order-independent part in parallel (CalculVoiesPossibles / CalculVoieDesiree, vehicule.cpp:4749-5038) and
-// k_lc_sequential walks the vehicle list with ONE thread, running MT19937 on the device.  (Next: epochs between successes
-// evaluated in parallel; successes are rare, so the serial part shrinks to the changes themselves.)
+// therefore needs the reference's order.  The device keeps that order exactly but only serialises what is order-dependent:
+//   k_lc_prepare   per vehicle, parallel: CalculVoiesPossibles / CalculVoieDesiree (vehicule.cpp:4749-5038)
+//   k_lc_eval      per vehicle, parallel, no side effects: everything CalculChangementVoie and TestLaneChange do up to the
+//                  random draw — neighbours on both lanes, supply/demand, the acceptance probability phi — stored as one
+//                  record per (vehicle, pass, candidate lane).  A record is valid as long as nothing changed on its link.
+//   k_lc_walk      one block: thread 0 walks the events in list order through the records (skipping, 256 at a time, the
+//                  events that neither draw nor change anything), draws from MT19937 on the device, commits the accepted
+//                  changes; after every commit the block re-evaluates, in parallel, the later records of the link concerned
+//                  (and of the links leading into it).  Events with the reference's rare side effects on failure (the
+//                  0.5 m move-back, the lane swap of two stopped vehicles) run the literal sequential code.
+//   k_lc_sequential  the literal one-thread version (SYMGPU_LC=seq), kept as the device-side cross-check.
 #pragma once
 #include "micro.cuh"
 
@@ -32,7 +39,10 @@ struct DevLc {
   int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head;
   DevRng* rng; int* n_changes;
   double dst_chgtvoie, dst_force, phi_force; int ordre;
+  // records of k_lc_eval: stage 0 = mandatory pass, 1 / 2 = first / second candidate lane of the discretionary pass
+  unsigned char *kind, *code; int *tl_pre, *rfol, *rtgt, *had_mand; double* phi;
 };
+enum : int { LC_FAIL = 0, LC_TEST = 1, LC_SLOW = 2 };
 
 // Vehicule::CalculVoiesPossibles + CalculVoieDesiree (vehicule.cpp:4749-5038), phase 6 of the step, per vehicle
 __global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
@@ -146,9 +156,10 @@ __device__ inline int next_voie_draw(const LcView& W, int v, int lane) {
   if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) rng_next(W.C.rng);
   return nx;
 }
-__device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int v, int fol, int lead, int lead_orig, int tgt, bool force) {   // AbstractCarFollowing.cpp:61-329
+// everything of TestLaneChange before the draw; false = refused without a draw
+__device__ inline bool lane_change_phi(const DevParams& P, const LcView& W, int v, double pv, int fol, int lead, int lead_orig, int tgt, bool force, double* phi_out) {   // AbstractCarFollowing.cpp:61-323
   const DevCls& c = P.cls[W.V.cls[v]]; double kc = c.w * c.kx / (c.w - c.vx);
-  double pv = p1of(W, v); int lane = W.V.lane[v]; int link = W.N.lane_link[lane];
+  int lane = W.V.lane[v]; int link = W.N.lane_link[lane];
   double si;
   if (lead_orig >= 0) si = p1of(W, lead_orig) - pv;
   else if (force) si = fmax(1 / c.kx, W.N.lane_len[lane] - pv);
@@ -185,7 +196,13 @@ __device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int
     if (dem_dest > 0) phi = fmin(1., off_dest / dem_dest) * pi * dem_orig / vit * P.dt * si;
     else phi = pi * dem_orig / vit * P.dt * si;
   }
-  double r = rng_next(W.C.rng) / 32767.0;
+  *phi_out = phi;
+  return true;
+}
+__device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int v, int fol, int lead, int lead_orig, int tgt, bool force) {
+  double phi;
+  if (!lane_change_phi(P, W, v, p1of(W, v), fol, lead, lead_orig, tgt, force, &phi)) return false;
+  double r = rng_next(W.C.rng) / 32767.0;                            // AbstractCarFollowing.cpp:324-328
   return r < phi;
 }
 __device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol) {            // vehicule.cpp:2657-2711
@@ -227,6 +244,158 @@ __device__ inline bool calcul_changement_voie(const DevParams& P, const LcView& 
   if (test_lane_change(P, W, v, fol, lead, lead_orig, tgt, force)) { changement_voie(W, v, tgt, fol); return true; }
   if (move_back) W.V.pos[v] = p1 + 0.5;
   return false;
+}
+// ---- parallel evaluation / ordered commit -------------------------------------------------------------------------------
+// CalculChangementVoie without side effects: what the event (v, candidate lane) will do when its turn comes, provided
+// nothing changes on its link before.
+__device__ inline void lc_eval_stage(const DevParams& P, const LcView& W, int v, int tgt_num, bool force, int slot) {
+  unsigned char code = LC_FAIL; int tl_pre = -1, rf = -1, rt = -1; double phi = 0;
+  do {
+    double p1 = p1of(W, v);
+    if (p1 <= SYM_UNDEF || W.C.chgt[v]) break;
+    int lane = W.V.lane[v]; int link = W.N.lane_link[lane]; bool desired = W.C.vdes[v] != -1; bool oblig = W.N.lane_flags[lane] & 1;
+    if (first_vehicule(W, lane) == v && !oblig && !desired) break;
+    int tgt = W.N.link_first[link] + tgt_num;
+    double ratio = W.N.lane_len[tgt] / W.N.lane_len[lane];
+    int same = near_aval(W, tgt, ratio * p1 - 0.01, v);
+    if (same >= 0 && fabs(ratio * p1 - p1of(W, same)) < 0.01) {
+      if (fabs(p1 - W.N.lane_len[lane]) < 0.01) code = LC_SLOW;       // move-back / swap: literal code at commit time
+      break;
+    }
+    double q = ratio * p1 + 0.001;
+    int fol = near_amont(W, tgt, q, v);
+    int lead = near_aval(W, tgt, q, v);
+    if (lead < 0 && (oblig || desired)) {
+      int tl; int nx = next_voie(W.N, W.V.route[v], W.V.route_pos[v], tgt, &tl);
+      tl_pre = tl;
+      if (nx >= 0) lead = near_aval(W, nx, 0, -1);
+    }
+    int lead_orig = prev_vehicule(W, v);
+    if (lead_orig < 0 && !oblig && !desired && !force) break;
+    if (!lane_change_phi(P, W, v, p1, fol, lead, lead_orig, tgt, force, &phi)) break;
+    code = LC_TEST; rf = fol; rt = tgt;
+  } while (0);
+  W.C.code[slot] = code; W.C.tl_pre[slot] = tl_pre; W.C.rfol[slot] = rf; W.C.rtgt[slot] = rt; W.C.phi[slot] = phi;
+}
+// records of vehicle v for the passes >= from_pass; n = number of slots
+__device__ inline void lc_eval_vehicle(const DevParams& P, const LcView& W, int v, int n, int from_pass) {
+  const bool alive = W.V.status[v] == ST_ALIVE;
+  if (from_pass == 0) {
+    unsigned char k = 0;
+    if (alive && W.C.vdes[v] != -1) { lc_eval_stage(P, W, v, W.C.vdes[v], true, v); k = (W.C.code[v] != LC_FAIL || W.C.tl_pre[v] >= 0) ? 1 : 2; }
+    W.C.kind[v] = k;                                                  // 2: only marks the vehicle as handled (m_bDejaCalcule)
+  }
+  unsigned char k = 0;
+  if (alive && !W.C.chgt[v] && !W.C.had_mand[v]) {
+    int lane = W.V.lane[v]; int link = W.N.lane_link[lane]; int nl = W.N.link_nl[link];
+    if (nl >= 2) {
+      int nV = W.N.lane_num[lane]; int nVF = nV + 1, nVS = nV - 1;
+      if (W.C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
+      int mask = W.C.voies_ok[v];
+      W.C.code[n + v] = LC_FAIL; W.C.code[2 * n + v] = LC_FAIL; W.C.tl_pre[n + v] = -1; W.C.tl_pre[2 * n + v] = -1;
+      if (nVF >= 0 && nVF < nl && ((mask >> nVF) & 1)) lc_eval_stage(P, W, v, nVF, false, n + v);
+      if (nVS >= 0 && nVS < nl && ((mask >> nVS) & 1)) lc_eval_stage(P, W, v, nVS, false, 2 * n + v);
+      if (W.C.code[n + v] != LC_FAIL || W.C.tl_pre[n + v] >= 0 || W.C.code[2 * n + v] != LC_FAIL || W.C.tl_pre[2 * n + v] >= 0) k = 1;
+    }
+  }
+  W.C.kind[n + v] = k;
+}
+__global__ void k_lc_eval(DevNet N, DevVeh V, DevLc C, int n) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  LcView W{N, V, C};
+  C.had_mand[v] = (V.status[v] == ST_ALIVE && C.vdes[v] != -1) ? 1 : 0;
+  lc_eval_vehicle(cP_ref(), W, v, n, 0);
+}
+// what a commit invalidates: the records of the vehicles whose neighbour queries can reach the moved vehicle's old or new
+// place, i.e. those between its strict neighbours on the lane it left and on the lane it joined (normalised abscissa x =
+// pos / lane length, which the lane-to-lane projection of vehicule.cpp:2300 preserves); `full`: the whole link;
+// `preds`: also the links leading into this one (their vehicles look at the first vehicle of the next lane, :2408-2420).
+struct LcDirty { bool dirty, full, preds; double xlo, xhi; };
+__device__ inline void lc_window(const LcView& W, int lane, double pos, int excl, LcDirty* d) {
+  double lo = -1, hi = -1;
+  for_lane(W, lane, [&](int y) { if (y == excl) return; double p = p1of(W, y); if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } });
+  const double len = W.N.lane_len[lane];
+  if (lo < 0) { d->preds = true; d->xlo = -1; } else d->xlo = fmin(d->xlo, lo / len);
+  d->xhi = hi < 0 ? 2.0 : fmax(d->xhi, hi / len);
+}
+// one stage of an event at its turn (thread 0 of k_lc_walk)
+__device__ inline bool lc_run_stage(const DevParams& P, const LcView& W, int v, int slot, int tgt_num, bool force, LcDirty* d) {
+  const int code = W.C.code[slot];
+  if (code == LC_SLOW) { d->dirty = d->full = d->preds = true; return calcul_changement_voie(P, W, v, tgt_num, force); }
+  const int tl = W.C.tl_pre[slot];
+  if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) rng_next(W.C.rng);
+  if (code != LC_TEST) return false;
+  double r = rng_next(W.C.rng) / 32767.0;
+  if (!(r < W.C.phi[slot])) return false;
+  d->dirty = true;
+  lc_window(W, W.V.lane[v], p1of(W, v), v, d);
+  changement_voie(W, v, W.C.rtgt[slot], W.C.rfol[slot]);
+  lc_window(W, W.V.lane[v], p1of(W, v), v, d);
+  return true;
+}
+constexpr int kLcBlock = 256;
+__global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc C, int n) {
+  const DevParams& P = cP_ref();
+  LcView W{N, V, C};
+  __shared__ unsigned s_mask[kLcBlock / 32];
+  __shared__ int s_next, s_dirty_link, s_cur, s_full, s_preds; __shared__ double s_xlo, s_xhi;
+  const int tid = threadIdx.x; const int E = 2 * n;
+  int base = 0;
+  while (base < E) {
+    const int e = base + tid;
+    const unsigned m = __ballot_sync(0xffffffffu, e < E && C.kind[e] == 1);   // 0 / 2: neither draws nor changes anything
+    if ((tid & 31) == 0) s_mask[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+      int dirty_link = -1, next = base + kLcBlock, cur = -1;
+      for (int w = 0; w < kLcBlock / 32 && dirty_link < 0; w++) {
+        unsigned mm = s_mask[w];
+        while (mm && dirty_link < 0) {
+          const int b = __ffs(mm) - 1; mm &= mm - 1;
+          const int ev = base + w * 32 + b; const int pass = ev >= n; const int v = pass ? ev - n : ev;
+          LcDirty d{false, false, false, 3.0, -1.0};
+          const int link = N.lane_link[V.lane[v]];
+          if (!pass) {                                                // mandatory pass (reseau.cpp:4238-4262)
+            if (C.vdes[v] != -1) {
+              bool ok = lc_run_stage(P, W, v, v, C.vdes[v], true, &d);
+              C.chgt[v] = 1; if (ok) C.vdes[v] = -1;
+            }
+          } else if (!C.chgt[v]) {                                    // discretionary pass (:4264-4327)
+            const int nV = N.lane_num[V.lane[v]]; int nVF = nV + 1, nVS = nV - 1;
+            if (C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
+            bool ok = lc_run_stage(P, W, v, n + v, nVF, false, &d);
+            if (!ok && !d.dirty) ok = lc_run_stage(P, W, v, 2 * n + v, nVS, false, &d);
+            else if (!ok && d.dirty) {                                  // the first candidate left side effects: the second one is evaluated on the spot
+              const int nl = N.link_nl[link];
+              if (nVS >= 0 && nVS < nl && ((C.voies_ok[v] >> nVS) & 1)) calcul_changement_voie(P, W, v, nVS, false);
+            }
+          }
+          if (d.dirty) { dirty_link = link; next = ev + 1; cur = ev; s_full = d.full; s_preds = d.preds; s_xlo = d.xlo; s_xhi = d.xhi; }
+        }
+      }
+      s_dirty_link = dirty_link; s_next = next; s_cur = cur;
+    }
+    __syncthreads();
+    const int K = s_dirty_link; const int cur = s_cur; base = s_next;
+    if (K >= 0) {                                                     // re-evaluate the later events of link K and of the links that lead into it
+      const int from_pass = cur >= n; const int vcur = from_pass ? cur - n : cur;
+      const int upn = N.link_up[K]; const bool full = s_full, preds = s_preds;
+      const double margin = 0.05 / N.link_len[K]; const double xlo = s_xlo - margin, xhi = s_xhi + margin;
+      for (int k = preds ? 0 : K; k < (preds ? N.n_links : K + 1); k++) {
+        if (k != K && N.link_down[k] != upn) continue;
+        const int l0 = N.link_first[k], l1 = l0 + N.link_nl[k] - 1;
+        const int a = C.lane_start[l0], b = C.lane_start[l1] + C.lane_count[l1];
+        for (int q = a + tid; q < b; q += kLcBlock) {
+          const int y = C.order[q];
+          if (k == K && !full) { const double x = p1of(W, y) / N.lane_len[V.lane[y]]; if (x < xlo || x > xhi) continue; }
+          if (from_pass == 0) lc_eval_vehicle(P, W, y, n, y > vcur ? 0 : 1);
+          else if (y > vcur) lc_eval_vehicle(P, W, y, n, 1);
+        }
+      }
+      __syncthreads();
+    }
+  }
 }
 // Reseau::ChangementDeVoie (reseau.cpp:4219-4330): one thread, m_LstVehicles (slot) order
 __global__ void k_lc_sequential(DevNet N, DevVeh V, DevLc C, int n) {

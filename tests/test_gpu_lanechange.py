@@ -20,13 +20,28 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("mode", ["walk", "seq"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_lane_change_parity(name):
+def test_lane_change_parity(name, mode, monkeypatch):
+    """walk = parallel evaluation + ordered commit (k_lc_eval / k_lc_walk, the default); seq = the literal one-thread kernel"""
+    if mode == "seq":
+        monkeypatch.setenv("SYMGPU_LC", "seq")
+    else:
+        monkeypatch.delenv("SYMGPU_LC", raising=False)
     kw = dict(CASES[name])
     b = synth.corridor(**kw)
     st = run_parity(b, kw["n_steps"], check_every=1)
     assert st["worst"] == 0.0
     assert st["overflow"] == 0
+
+
+def test_lane_change_parity_large():
+    """~4000 vehicles, several accepted changes per step: exercises the re-evaluation after every commit"""
+    b = synth.corridor(n_links=24, length=800.0, n_lanes=3, demand=1.5, offramp_every=3, offramp_share=0.15, preseed_density=0.07,
+                       shuffle=True, n_steps=120)
+    st = run_parity(b, 120, check_every=1)
+    assert st["worst"] == 0.0
+    assert st["n_final"] > 1000
 
 
 def test_lane_changes_happen():
