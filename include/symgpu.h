@@ -27,7 +27,9 @@ enum { SYMGPU_CNT_TIES = 0,      /* equal-position leader candidates met (reseau
        SYMGPU_CNT_LAUNCHES = 4,  /* kernels launched since creation */
        SYMGPU_CNT_SLOTS = 5,     /* vehicle slots in use (alive + holes) */
        SYMGPU_CNT_CTX_OVERFLOW = 6, /* context lane list longer than the device bound (must stay 0) */
-       SYMGPU_CNT_LANE_CHANGES = 7  /* successful lane changes (Vehicule::ChangementVoie) */ };
+       SYMGPU_CNT_LANE_CHANGES = 7, /* successful lane changes (Vehicule::ChangementVoie) */
+       SYMGPU_CNT_LC_EVENTS = 8,    /* lane-change events that drew or changed something (walked one by one) */
+       SYMGPU_CNT_LC_REEVAL = 9     /* acceptance-test records re-evaluated after a commit */ };
 
 /* Replaces Reseau::LoadReseauXML + InitSimuTrafic for an already flattened network (include/symflat.h). */
 int symgpu_create(const char* symflat_path, int device, symgpu_ctx** out);

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SYMB200_LIB", os.path.join(_HERE, "libSymuViaB200.so"))   # override only for A/B experiments
 _LIB = None
 
-CNT_TIES, CNT_LOOPS, CNT_CREATED, CNT_PASSES, CNT_LAUNCHES, CNT_SLOTS, CNT_CTX_OVERFLOW, CNT_LANE_CHANGES = range(8)
+CNT_TIES, CNT_LOOPS, CNT_CREATED, CNT_PASSES, CNT_LAUNCHES, CNT_SLOTS, CNT_CTX_OVERFLOW, CNT_LANE_CHANGES, CNT_LC_EVENTS, CNT_LC_REEVAL = range(10)
 
 
 class SymGpuError(RuntimeError):

@@ -474,7 +474,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   DevLc& lc = c->dlc;
   lc.order = c->order.p; lc.lane_start = c->lane_start.p; lc.lane_count = c->lane_count.p; lc.vdes = c->v_vdes.p; lc.voies_ok = c->lc_voies_ok.p; lc.chgt = c->lc_chgt.p;
   lc.delta_next = c->lc_delta_next.p; lc.link_delta_head = c->lc_link_head.p; lc.rng = c->lc_rng.p; lc.n_changes = c->lc_nchg.p;
-  lc.kind = c->lc_kind.p; lc.code = c->lc_code.p; lc.tl_pre = c->lc_tl_pre.p; lc.rfol = c->lc_rfol.p; lc.rtgt = c->lc_rtgt.p; lc.had_mand = c->lc_had_mand.p; lc.phi = c->lc_phi.p;
+  lc.counters = c->counters.p; lc.kind = c->lc_kind.p; lc.code = c->lc_code.p; lc.tl_pre = c->lc_tl_pre.p; lc.rfol = c->lc_rfol.p; lc.rtgt = c->lc_rtgt.p; lc.had_mand = c->lc_had_mand.p; lc.phi = c->lc_phi.p;
   lc.dst_chgtvoie = c->net.params[SYMFLAT_P_DSTCHGT]; lc.dst_force = c->net.params[SYMFLAT_P_DST_FORCE] > 0 ? c->net.params[SYMFLAT_P_DST_FORCE] : -1.0;
   lc.phi_force = c->net.params[SYMFLAT_P_PHI_FORCE] > 0 ? c->net.params[SYMFLAT_P_PHI_FORCE] : 1.0; lc.ordre = 1;
   DevSig& s = c->ds;
@@ -603,7 +603,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
                        &c->v_computed, &c->v_ctx_nl, &c->v_ctx_leader, &c->v_ctx_flags}) CK(b->alloc(cap));
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
-  CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(1)); CK(c->lc_rng.alloc(1));
+  CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
     CK(c->lc_phi.alloc(3 * cap)); CK(c->lc_had_mand.alloc(cap)); const char* e = getenv("SYMGPU_LC"); c->lc_seq = e && !strcmp(e, "seq"); }
   for (DBuf<double>* b : {&c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre, &c->v_dstp, &c->v_hent,
@@ -801,15 +801,17 @@ static int step_front(symgpu_ctx* c) {
     const int K = c->net.n_links();
     KBEGIN(c, KID_LC);
     k_lc_prepare<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c);
-    CK(cudaMemsetAsync(c->lc_link_head.p, 0xff, K * sizeof(int), s)); CK(cudaMemsetAsync(c->lc_nchg.p, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(c->lc_link_head.p, 0xff, K * sizeof(int), s)); CK(cudaMemsetAsync(c->lc_nchg.p, 0, 2 * sizeof(int), s));
     CK(cudaMemcpyAsync(c->lc_rng.p, &c->rng, sizeof(DevRng), cudaMemcpyHostToDevice, s));
     if (c->lc_seq) { k_lc_sequential<<<1, 32, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); }
     else { k_lc_eval<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); k_lc_walk<<<1, kLcBlock, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); }
     KEND(c);
-    int nchg = 0;
-    CK(cudaMemcpyAsync(&c->rng, c->lc_rng.p, sizeof(DevRng), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&nchg, c->lc_nchg.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int nchg2[2] = {0, 0};
+    if (c->lc_seq) CK(cudaMemcpyAsync(&c->rng, c->lc_rng.p, sizeof(DevRng), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nchg2, c->lc_nchg.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (!c->lc_seq) c->rng.skip((unsigned)nchg2[1]);                     // the walk drew through a look-ahead buffer: advance the host's copy of the stream
+    const int nchg = nchg2[0];
     c->lane_changes += nchg;
     if (nchg > 0) {
       CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));

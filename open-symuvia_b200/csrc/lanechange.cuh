@@ -37,10 +37,11 @@ __device__ inline int rng_next(DevRng* r) {                            // RandMa
 struct DevLc {
   const int *order, *lane_start, *lane_count;
   int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head;
-  DevRng* rng; int* n_changes;
+  DevRng* rng; int* n_changes;      // n_changes[1]: draws consumed by k_lc_walk (the host advances its own stream)
   double dst_chgtvoie, dst_force, phi_force; int ordre;
   // records of k_lc_eval: stage 0 = mandatory pass, 1 / 2 = first / second candidate lane of the discretionary pass
   unsigned char *kind, *code; int *tl_pre, *rfol, *rtgt, *had_mand; double* phi;
+  long long* counters;
 };
 enum : int { LC_FAIL = 0, LC_TEST = 1, LC_SLOW = 2 };
 
@@ -81,7 +82,23 @@ __global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
 }
 
 // ---- the sequential part (one thread) ----------------------------------------------------------------------------------
-struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; };
+// rb..srng: k_lc_walk draws through a buffer of upcoming values kept in shared memory (all null elsewhere: direct draws)
+struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; int* rb = nullptr; int* rb_pos = nullptr; int* rb_fill = nullptr; int* rb_base = nullptr; DevRng* srng = nullptr; };
+constexpr int kRb = 2048;
+// make at least `need` upcoming draws available in the buffer (one thread)
+__device__ inline void lc_fill(const LcView& W, int need) {
+  int pos = *W.rb_pos, fill = *W.rb_fill;
+  if (fill - pos >= need) return;
+  for (int k = pos; k < fill; k++) W.rb[k - pos] = W.rb[k];
+  *W.rb_base += pos; fill -= pos; pos = 0;
+  while (fill < kRb) W.rb[fill++] = rng_next(W.srng);
+  *W.rb_pos = pos; *W.rb_fill = fill;
+}
+__device__ inline int lc_draw(const LcView& W) {                       // RandManager::myRand in list order
+  if (!W.rb) return rng_next(W.C.rng);
+  lc_fill(W, 1);
+  return W.rb[(*W.rb_pos)++];
+}
 constexpr int kTie = 8;
 
 // iterate the vehicles currently on `lane`: the lane's slice of the start-of-step order (minus those that left it) plus the
@@ -153,7 +170,7 @@ __device__ inline double vreg_act(const LcView& W, int y) { return W.N.link_vreg
 // the lane's memoised next-lane draw (Vehicule::GetTirage) consumed through CalculNextVoie
 __device__ inline int next_voie_draw(const LcView& W, int v, int lane) {
   int tl; int nx = next_voie(W.N, W.V.route[v], W.V.route_pos[v], lane, &tl);
-  if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) rng_next(W.C.rng);
+  if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) lc_draw(W);
   return nx;
 }
 // everything of TestLaneChange before the draw; false = refused without a draw
@@ -202,7 +219,7 @@ __device__ inline bool lane_change_phi(const DevParams& P, const LcView& W, int 
 __device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int v, int fol, int lead, int lead_orig, int tgt, bool force) {
   double phi;
   if (!lane_change_phi(P, W, v, p1of(W, v), fol, lead, lead_orig, tgt, force, &phi)) return false;
-  double r = rng_next(W.C.rng) / 32767.0;                            // AbstractCarFollowing.cpp:324-328
+  double r = lc_draw(W) / 32767.0;                                   // AbstractCarFollowing.cpp:324-328
   return r < phi;
 }
 __device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol) {            // vehicule.cpp:2657-2711
@@ -324,9 +341,9 @@ __device__ inline bool lc_run_stage(const DevParams& P, const LcView& W, int v, 
   const int code = W.C.code[slot];
   if (code == LC_SLOW) { d->dirty = d->full = d->preds = true; return calcul_changement_voie(P, W, v, tgt_num, force); }
   const int tl = W.C.tl_pre[slot];
-  if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) rng_next(W.C.rng);
+  if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) lc_draw(W);
   if (code != LC_TEST) return false;
-  double r = rng_next(W.C.rng) / 32767.0;
+  double r = lc_draw(W) / 32767.0;
   if (!(r < W.C.phi[slot])) return false;
   d->dirty = true;
   lc_window(W, W.V.lane[v], p1of(W, v), v, d);
@@ -335,51 +352,93 @@ __device__ inline bool lc_run_stage(const DevParams& P, const LcView& W, int v, 
   return true;
 }
 constexpr int kLcBlock = 256;
+// one event at its turn, literally (thread 0): the stop event of a chunk — an accepted change or an event with side effects
+__device__ inline void lc_run_event(const DevParams& P, const LcView& W, int ev, int n, LcDirty* d) {
+  const DevNet& N = W.N; const DevVeh& V = W.V; const DevLc& C = W.C;
+  const int pass = ev >= n; const int v = pass ? ev - n : ev;
+  if (!pass) {                                                        // mandatory pass (reseau.cpp:4238-4262)
+    if (C.vdes[v] != -1) { bool ok = lc_run_stage(P, W, v, v, C.vdes[v], true, d); C.chgt[v] = 1; if (ok) C.vdes[v] = -1; }
+  } else if (!C.chgt[v]) {                                            // discretionary pass (:4264-4327)
+    const int link = N.lane_link[V.lane[v]];
+    const int nV = N.lane_num[V.lane[v]]; int nVF = nV + 1, nVS = nV - 1;
+    if (C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
+    bool ok = lc_run_stage(P, W, v, n + v, nVF, false, d);
+    if (!ok && !d->dirty) ok = lc_run_stage(P, W, v, 2 * n + v, nVS, false, d);
+    else if (!ok && d->dirty) {                                       // the first candidate left side effects: the second one is evaluated on the spot
+      const int nl = N.link_nl[link];
+      if (nVS >= 0 && nVS < nl && ((C.voies_ok[v] >> nVS) & 1)) calcul_changement_voie(P, W, v, nVS, false);
+    }
+  }
+}
 __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc C, int n) {
   const DevParams& P = cP_ref();
-  LcView W{N, V, C};
-  __shared__ unsigned s_mask[kLcBlock / 32];
-  __shared__ int s_next, s_dirty_link, s_cur, s_full, s_preds; __shared__ double s_xlo, s_xhi;
-  const int tid = threadIdx.x; const int E = 2 * n;
-  int base = 0;
+  __shared__ DevRng srng; __shared__ int rb[kRb]; __shared__ int rb_pos, rb_fill, rb_base;
+  __shared__ int s_wsum[kLcBlock / 32], s_stop, s_stop_off, s_total, s_dirty_link, s_full, s_preds; __shared__ double s_xlo, s_xhi;
+  LcView W{N, V, C, rb, &rb_pos, &rb_fill, &rb_base, &srng};
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5; const int E = 2 * n;
+  for (int k = tid; k < 624; k += kLcBlock) srng.mt[k] = C.rng->mt[k];
+  if (tid == 0) { srng.idx = C.rng->idx; srng.count = 0; rb_pos = rb_fill = rb_base = 0; }
+  __syncthreads();
+  int base = 0; long long walked = 0;
   while (base < E) {
+    if (tid == 0) { lc_fill(W, 4 * kLcBlock + 8); s_stop = 0x7fffffff; }
+    __syncthreads();
+    // every thread: its event under the assumption that all tests before it (and its own) are refused
     const int e = base + tid;
-    const unsigned m = __ballot_sync(0xffffffffu, e < E && C.kind[e] == 1);   // 0 / 2: neither draws nor changes anything
-    if ((tid & 31) == 0) s_mask[tid >> 5] = m;
+    int cnt = 0, nt = 0, toff[2]; double tphi[2]; bool hard = false, live = false;
+    int memo_l[kMemo]; int v = 0, pass = 0;
+    if (e < E && C.kind[e] == 1) {
+      pass = e >= n; v = pass ? e - n : e;
+      int slots[2], ns = 0;
+      if (!pass) { if (C.vdes[v] != -1) slots[ns++] = v; }
+      else if (!C.chgt[v]) { slots[ns++] = n + v; slots[ns++] = 2 * n + v; }
+      live = ns > 0;
+      for (int k = 0; k < kMemo; k++) memo_l[k] = V.memo[v * kMemo + k];
+      for (int q = 0; q < ns && !hard; q++) {
+        const int code = C.code[slots[q]];
+        if (code == LC_SLOW) { hard = true; break; }
+        const int tl = C.tl_pre[slots[q]];
+        if (tl >= 0) cnt += memo_touch(memo_l, tl);
+        if (code == LC_TEST) { toff[nt] = cnt; tphi[nt] = C.phi[slots[q]]; nt++; cnt++; }
+      }
+    }
+    // exclusive prefix sum of the draw counts over the chunk
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    int woff = 0; for (int w = 0; w < wid; w++) woff += s_wsum[w];
+    const int off = woff + inc - cnt;
+    if (tid == kLcBlock - 1) s_total = woff + inc;
+    bool stop = hard;
+    for (int t = 0; t < nt && !stop; t++) { double r = rb[rb_pos + off + toff[t]] / 32767.0; if (r < tphi[t]) stop = true; }
+    if (live && stop) atomicMin(&s_stop, e);
+    __syncthreads();
+    const int st = s_stop;
+    if (live && e < st) {                                             // refused without side effects: keep the memo, mark the vehicle handled
+      for (int k = 0; k < kMemo; k++) V.memo[v * kMemo + k] = memo_l[k];
+      if (!pass) C.chgt[v] = 1;
+      walked++;
+    }
+    if (e == st) s_stop_off = off;
     __syncthreads();
     if (tid == 0) {
-      int dirty_link = -1, next = base + kLcBlock, cur = -1;
-      for (int w = 0; w < kLcBlock / 32 && dirty_link < 0; w++) {
-        unsigned mm = s_mask[w];
-        while (mm && dirty_link < 0) {
-          const int b = __ffs(mm) - 1; mm &= mm - 1;
-          const int ev = base + w * 32 + b; const int pass = ev >= n; const int v = pass ? ev - n : ev;
-          LcDirty d{false, false, false, 3.0, -1.0};
-          const int link = N.lane_link[V.lane[v]];
-          if (!pass) {                                                // mandatory pass (reseau.cpp:4238-4262)
-            if (C.vdes[v] != -1) {
-              bool ok = lc_run_stage(P, W, v, v, C.vdes[v], true, &d);
-              C.chgt[v] = 1; if (ok) C.vdes[v] = -1;
-            }
-          } else if (!C.chgt[v]) {                                    // discretionary pass (:4264-4327)
-            const int nV = N.lane_num[V.lane[v]]; int nVF = nV + 1, nVS = nV - 1;
-            if (C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
-            bool ok = lc_run_stage(P, W, v, n + v, nVF, false, &d);
-            if (!ok && !d.dirty) ok = lc_run_stage(P, W, v, 2 * n + v, nVS, false, &d);
-            else if (!ok && d.dirty) {                                  // the first candidate left side effects: the second one is evaluated on the spot
-              const int nl = N.link_nl[link];
-              if (nVS >= 0 && nVS < nl && ((C.voies_ok[v] >> nVS) & 1)) calcul_changement_voie(P, W, v, nVS, false);
-            }
-          }
-          if (d.dirty) { dirty_link = link; next = ev + 1; cur = ev; s_full = d.full; s_preds = d.preds; s_xlo = d.xlo; s_xhi = d.xhi; }
-        }
+      s_dirty_link = -1;
+      if (st == 0x7fffffff) rb_pos += s_total;
+      else {
+        rb_pos += s_stop_off;
+        LcDirty d{false, false, false, 3.0, -1.0};
+        const int vv = st >= n ? st - n : st; const int link = N.lane_link[V.lane[vv]];
+        lc_run_event(P, W, st, n, &d);
+        if (d.dirty) { s_dirty_link = link; s_full = d.full; s_preds = d.preds; s_xlo = d.xlo; s_xhi = d.xhi; }
       }
-      s_dirty_link = dirty_link; s_next = next; s_cur = cur;
     }
     __syncthreads();
-    const int K = s_dirty_link; const int cur = s_cur; base = s_next;
-    if (K >= 0) {                                                     // re-evaluate the later events of link K and of the links that lead into it
-      const int from_pass = cur >= n; const int vcur = from_pass ? cur - n : cur;
+    if (st == 0x7fffffff) { base += kLcBlock; continue; }
+    base = st + 1;
+    const int K = s_dirty_link;
+    if (K >= 0) {                                                     // re-evaluate the later events of link K (window) and, if needed, of the links that lead into it
+      const int from_pass = st >= n; const int vcur = from_pass ? st - n : st;
       const int upn = N.link_up[K]; const bool full = s_full, preds = s_preds;
       const double margin = 0.05 / N.link_len[K]; const double xlo = s_xlo - margin, xhi = s_xhi + margin;
       for (int k = preds ? 0 : K; k < (preds ? N.n_links : K + 1); k++) {
@@ -391,11 +450,15 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
           if (k == K && !full) { const double x = p1of(W, y) / N.lane_len[V.lane[y]]; if (x < xlo || x > xhi) continue; }
           if (from_pass == 0) lc_eval_vehicle(P, W, y, n, y > vcur ? 0 : 1);
           else if (y > vcur) lc_eval_vehicle(P, W, y, n, 1);
+          else continue;
+          atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_REEVAL], 1ULL);
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
   }
+  if (walked) atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_EVENTS], (unsigned long long)walked);
+  if (tid == 0) C.n_changes[1] = rb_base + rb_pos;
 }
 // Reseau::ChangementDeVoie (reseau.cpp:4219-4330): one thread, m_LstVehicles (slot) order
 __global__ void k_lc_sequential(DevNet N, DevVeh V, DevLc C, int n) {

@@ -30,6 +30,7 @@ t0 = time.time()
 for _ in range(steps):
     n = g.step()
 dt = time.time() - t0
-print(f"n={n} steps={steps} {dt / steps * 1e3:.2f} ms/step, lane changes/step {(g.counter(pkg.CNT_LANE_CHANGES) - c0) / steps:.1f}")
+print(f"n={n} steps={steps} {dt / steps * 1e3:.2f} ms/step, lane changes/step {(g.counter(pkg.CNT_LANE_CHANGES) - c0) / steps:.1f}, "
+      f"events walked/step {g.counter(pkg.CNT_LC_EVENTS) / (steps + 5):.0f}, records re-evaluated/step {g.counter(pkg.CNT_LC_REEVAL) / (steps + 5):.0f}")
 print({L.symgpu_kernel_name(k).decode(): round(L.symgpu_kernel_ms(g.h, k) / (steps + 5), 3) for k in range(L.symgpu_kernel_count())})
 os.unlink(path)
