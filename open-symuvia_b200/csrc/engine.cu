@@ -358,6 +358,11 @@ __global__ void k_mp_pack_migrants(DevVeh V, int n, const int* lane_owner, int r
   V.status[i] = ST_DEAD;
   free_slots[free_base + atomicAdd(free_cnt, 1)] = i;          // the slot is reused by a later arrival
 }
+// the number of rows of every per-peer region rides in the spare double of its first row, so the receiver needs no separate count exchange
+__global__ void k_mp_row_counts(const int* count, double* out, int cap_per_peer, int world) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < world) out[(size_t)q * cap_per_peer * kMigD + 15] = (double)count[q];
+}
 __global__ void k_mp_unpack_migrants(DevVeh V, int slot0, int n, const double* in, const int* free_slots, int free_top, int n_reuse) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -980,6 +985,7 @@ extern "C" int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, doub
   CK(cudaMemsetAsync(m.d_mig_count.p, 0, (m.world + 1) * sizeof(int), c->stream));
   if (c->n_slots) { k_mp_pack_migrants<<<(c->n_slots + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, m.d_lane_owner.p, m.rank, cap_per_peer, m.d_mig_count.p, send_rows,
                                                                                   m.d_free.p, m.free_count, &m.d_mig_count.p[m.world]); LAUNCH(c); }
+  k_mp_row_counts<<<1, 64, 0, c->stream>>>(m.d_mig_count.p, send_rows, cap_per_peer, m.world); LAUNCH(c);
   CK(cudaMemcpyAsync(m.h_mig_count.data(), m.d_mig_count.p, m.world * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   int out = 0;

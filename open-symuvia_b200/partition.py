@@ -66,6 +66,7 @@ class RankEngine:
         self.recv_tails = torch.zeros(max(1, int(self.halo_cnt.sum())) * TAIL_D, dtype=torch.float64, device=dev)
         self.send_rows = torch.zeros(world * cap_per_peer * ROW_D, dtype=torch.float64, device=dev)
         self.recv_rows = torch.zeros(world * cap_per_peer * ROW_D, dtype=torch.float64, device=dev)
+        self.recv_regions = torch.zeros(world * cap_per_peer * ROW_D, dtype=torch.float64, device=dev)
         self.send_counts = np.zeros(world, np.int32)
 
     def front(self):
@@ -115,6 +116,21 @@ def exchange_rows_dist(dist, torch, send_rows, recv_rows, send_counts, cap, rank
     return off // ROW_D
 
 
+def exchange_rows_fixed(dist, torch, send_rows, recv_regions, recv_rows, cap, rank, world):
+    """One fixed-size all_to_all of the per-peer regions; the row count of a region travels in the spare double (index 15) of
+    its first row (k_mp_row_counts), so no count exchange is needed.  Returns rows received (packed at the front of recv_rows)."""
+    dist.all_to_all_single(recv_regions, send_rows)
+    cnt = [int(x) for x in recv_regions.view(world, cap * ROW_D)[:, 15].cpu()]
+    off = 0
+    for q in range(world):
+        c = cnt[q]
+        if q == rank or c <= 0:
+            continue
+        recv_rows[off: off + c * ROW_D].copy_(recv_regions[q * cap * ROW_D: (q * cap + c) * ROW_D])
+        off += c * ROW_D
+    return off // ROW_D
+
+
 class DistributedRun:
     """The run as seen by one rank of a torch.distributed job (bench.py --gpus N, torchrun)."""
 
@@ -131,8 +147,7 @@ class DistributedRun:
         exchange_tails_dist(dist, r.send_tails, r.recv_tails, r.export_cnt, r.halo_cnt)
         torch.cuda.synchronize()
         r.back()
-        n = exchange_rows_dist(dist, torch, r.send_rows, r.recv_rows, r.send_counts, r.cap, self.rank, self.world)
-        torch.cuda.synchronize()
+        n = exchange_rows_fixed(dist, torch, r.send_rows, r.recv_regions, r.recv_rows, r.cap, self.rank, self.world)
         return r.import_rows(n)
 
 

@@ -50,6 +50,19 @@ def _worker(rank, world, port, q):
         ok = ok and n == 3 and bool(torch.equal(recv_rows[: 3 * R], torch.arange(3 * R, dtype=torch.float64) + 7))
     else:
         ok = ok and n == 0
+    # same rows through the single fixed-size all_to_all (count in the spare double of the region's first row)
+    send2 = send_rows.clone()
+    for peer in range(world):
+        send2[peer * cap * R + 15] = float(counts[peer])
+    regions = torch.zeros(world * cap * R, dtype=torch.float64)
+    recv2 = torch.zeros(world * cap * R, dtype=torch.float64)
+    n2 = part.exchange_rows_fixed(dist, torch, send2, regions, recv2, cap, rank, world)
+    if rank == 1:
+        want = torch.arange(3 * R, dtype=torch.float64) + 7
+        want[15] = 3.0
+        ok = ok and n2 == 3 and bool(torch.equal(recv2[: 3 * R], want))
+    else:
+        ok = ok and n2 == 0
     q.put((rank, ok))
     dist.destroy_process_group()
 
