@@ -49,6 +49,7 @@ int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, do
 int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
 int symgpu_step_traj_async(symgpu_ctx* c, int which);   /* returns rows, valid after symgpu_traj_wait(which) */
 int symgpu_traj_wait(symgpu_ctx* c, int which);
+double symgpu_traj_copy_ms(symgpu_ctx* c, int which);    /* device->host copy time of the rows last waited for (side stream, CUDA events) */
 int symgpu_traj_copy_async(symgpu_ctx* c, int which);   /* the copy alone (current state), e.g. after symgpu_mp_import */
 
 /* Partitioned runs: one process per GPU, network tables replicated, vehicles owned by the rank that owns their lane.

@@ -441,7 +441,7 @@ struct symgpu_ctx {
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
   // trajectory output: packed device rows + side stream + caller buffers registered for direct DMA (two in flight)
-  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr};
+  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   long long lane_changes = 0; int n_sms = 148;
@@ -548,7 +548,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
   CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->t_ready, cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&c->t_done[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->t_done[1], cudaEventDisableTiming));
+  for (int k = 0; k < 2; k++) { CK(cudaEventCreate(&c->t_done[k])); CK(cudaEventCreate(&c->t_begin[k])); }
   CK(cudaMallocHost(&c->h_stat, 16 * sizeof(int)));
   // static tables
   CK(c->lane_link.upload(col(f.lane_i, 4, 0))); CK(c->lane_num.upload(col(f.lane_i, 4, 1))); CK(c->lane_prev.upload(col(f.lane_i, 4, 2)));
@@ -642,7 +642,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
   for (int k = 0; k < 2; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
   c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
-  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); for (int k = 0; k < 2; k++) if (c->t_done[k]) cudaEventDestroy(c->t_done[k]);
+  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); for (int k = 0; k < 2; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_ctl_seed) cudaFreeHost(c->h_ctl_seed);
@@ -1096,6 +1096,7 @@ extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
     k_pack_traj<<<G, B, 0, s>>>(c->dv, n, c->t_flag.p, c->t_off.p, c->t_id.p, c->t_lane.p, c->t_pos.p, c->t_vit.p, c->t_acc.p); LAUNCH(c);
     CK(cudaEventRecord(c->t_ready, s));
     CK(cudaStreamWaitEvent(c->side, c->t_ready, 0));
+    CK(cudaEventRecord(c->t_begin[which], c->side));
     CK(cudaMemcpyAsync(b.id, c->t_id.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->side));
     CK(cudaMemcpyAsync(b.lane, c->t_lane.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->side));
     CK(cudaMemcpyAsync(b.pos, c->t_pos.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, c->side));
@@ -1114,6 +1115,7 @@ extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
 extern "C" int symgpu_traj_wait(symgpu_ctx* c, int which) {
   if (!c || which < 0 || which > 1) return SYMGPU_E_ARG;
   CK(cudaEventSynchronize(c->t_done[which]));
+  float ms = 0; if (cudaEventElapsedTime(&ms, c->t_begin[which], c->t_done[which]) == cudaSuccess) c->t_copy_ms[which] = ms; else cudaGetLastError();
   return SYMGPU_OK;
 }
 // Synchronous convenience form: step, copy the rows into the caller's (pageable or pinned) buffers, return rows.
@@ -1126,6 +1128,7 @@ extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, doub
   c->tbuf[0] = saved;
   return r;
 }
+extern "C" double symgpu_traj_copy_ms(symgpu_ctx* c, int which) { return c && which >= 0 && which < 2 ? c->t_copy_ms[which] : 0.0; }
 extern "C" int symgpu_profile(symgpu_ctx* c, int enable) { if (!c) return SYMGPU_E_ARG; c->profile = enable != 0; for (int k = 0; k < 16; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return SYMGPU_OK; }
 extern "C" int symgpu_kernel_count(void) { return KID_COUNT; }
 extern "C" const char* symgpu_kernel_name(int k) { return k >= 0 && k < KID_COUNT ? kKernelNames[k] : ""; }
