@@ -432,7 +432,7 @@ struct symgpu_ctx {
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DBuf<double> vl_used; DevFlow df; FlowCtl* h_ctl = nullptr; FlowCtl* h_ctl_seed = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
-  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi; bool lc_seq = false; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
+  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, lc_spos; DBuf<int> lc_moved; bool lc_seq = false; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
@@ -479,7 +479,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   DevLc& lc = c->dlc;
   lc.order = c->order.p; lc.lane_start = c->lane_start.p; lc.lane_count = c->lane_count.p; lc.vdes = c->v_vdes.p; lc.voies_ok = c->lc_voies_ok.p; lc.chgt = c->lc_chgt.p;
   lc.delta_next = c->lc_delta_next.p; lc.link_delta_head = c->lc_link_head.p; lc.rng = c->lc_rng.p; lc.n_changes = c->lc_nchg.p;
-  lc.counters = c->counters.p; lc.kind = c->lc_kind.p; lc.code = c->lc_code.p; lc.tl_pre = c->lc_tl_pre.p; lc.rfol = c->lc_rfol.p; lc.rtgt = c->lc_rtgt.p; lc.had_mand = c->lc_had_mand.p; lc.phi = c->lc_phi.p;
+  lc.moved = c->lc_moved.p; lc.posidx = c->f_posidx.p; lc.spos = c->lc_spos.p; lc.counters = c->counters.p; lc.kind = c->lc_kind.p; lc.code = c->lc_code.p; lc.tl_pre = c->lc_tl_pre.p; lc.rfol = c->lc_rfol.p; lc.rtgt = c->lc_rtgt.p; lc.had_mand = c->lc_had_mand.p; lc.phi = c->lc_phi.p;
   lc.dst_chgtvoie = c->net.params[SYMFLAT_P_DSTCHGT]; lc.dst_force = c->net.params[SYMFLAT_P_DST_FORCE] > 0 ? c->net.params[SYMFLAT_P_DST_FORCE] : -1.0;
   lc.phi_force = c->net.params[SYMFLAT_P_PHI_FORCE] > 0 ? c->net.params[SYMFLAT_P_PHI_FORCE] : 1.0; lc.ordre = 1;
   DevSig& s = c->ds;
@@ -610,7 +610,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
-    CK(c->lc_phi.alloc(3 * cap)); CK(c->lc_had_mand.alloc(cap)); const char* e = getenv("SYMGPU_LC"); c->lc_seq = e && !strcmp(e, "seq"); }
+    CK(c->lc_phi.alloc(3 * cap)); CK(c->lc_had_mand.alloc(cap)); CK(c->lc_spos.alloc(cap)); CK(c->lc_moved.alloc(cap)); const char* e = getenv("SYMGPU_LC"); c->lc_seq = e && !strcmp(e, "seq"); }
   for (DBuf<double>* b : {&c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre, &c->v_dstp, &c->v_hent,
                           &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) CK(b->alloc(cap));
   fill_dev_structs(c);

@@ -36,7 +36,7 @@ __device__ inline int rng_next(DevRng* r) {                            // RandMa
 
 struct DevLc {
   const int *order, *lane_start, *lane_count;
-  int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head;
+  int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head, *moved; const int* posidx; double* spos;
   DevRng* rng; int* n_changes;      // n_changes[1]: draws consumed by k_lc_walk (the host advances its own stream)
   double dst_chgtvoie, dst_force, phi_force; int ordre;
   // records of k_lc_eval: stage 0 = mandatory pass, 1 / 2 = first / second candidate lane of the discretionary pass
@@ -49,7 +49,8 @@ enum : int { LC_FAIL = 0, LC_TEST = 1, LC_SLOW = 2 };
 __global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  C.chgt[i] = 0; C.delta_next[i] = -1;
+  C.chgt[i] = 0; C.delta_next[i] = -1; C.moved[i] = 0;
+  if (V.status[i] == ST_ALIVE || V.status[i] == ST_NEW) C.spos[C.posidx[i]] = snap_pos(V.pos[i]);   // the keys k_sort_lanes ordered the lane by
   if (V.status[i] != ST_ALIVE) return;                                // vehicles created this step have no link at index 1 (reseau.cpp:3941)
   int lane = V.lane[i]; int link = N.lane_link[lane]; int nl = N.link_nl[link]; int first = N.link_first[link];
   double p1 = snap_pos(V.pos[i]);
@@ -101,12 +102,46 @@ __device__ inline int lc_draw(const LcView& W) {                       // RandMa
 }
 constexpr int kTie = 8;
 
-// iterate the vehicles currently on `lane`: the lane's slice of the start-of-step order (minus those that left it) plus the
-// vehicles that changed to it during this step (per-link list)
-template <class F> __device__ inline void for_lane(const LcView& W, int lane, F f) {
-  int s = W.C.lane_start[lane], n = W.C.lane_count[lane];
-  for (int a = 0; a < n; a++) { int y = W.C.order[s + a]; if (W.V.lane[y] == lane && W.V.status[y] == ST_ALIVE) f(y); }   // vehicles created this step join their lane set later (vehicule.cpp:1224)
+// The vehicles currently on `lane` = the lane's slice of the start-of-phase order (sorted by position; `spos` keeps the sort
+// keys), minus those that left it or were displaced since (`moved`), plus the link's list of displaced vehicles.  Queries
+// bracket the slice by binary search and only visit the few entries that can matter; the displaced list is short.
+__device__ __forceinline__ bool slice_ok(const LcView& W, int lane, int y) { return W.V.lane[y] == lane && !W.C.moved[y] && W.V.status[y] == ST_ALIVE; }   // vehicles created this step join their lane set later (vehicule.cpp:1224)
+template <class F> __device__ inline void for_slice(const LcView& W, int lane, int q0, int q1, F f) {
+  for (int q = q0; q < q1; q++) { int y = W.C.order[q]; if (slice_ok(W, lane, y)) f(y); }
+}
+template <class F> __device__ inline void for_moved(const LcView& W, int lane, F f) {
   for (int y = W.C.link_delta_head[W.N.lane_link[lane]]; y >= 0; y = W.C.delta_next[y]) if (W.V.lane[y] == lane) f(y);
+}
+__device__ inline int slice_lb(const LcView& W, int lane, double pos) {             // first order position of the lane with key >= pos
+  int lo = W.C.lane_start[lane], hi = lo + W.C.lane_count[lane];
+  while (lo < hi) { int m = (lo + hi) >> 1; if (W.C.spos[m] < pos) lo = m + 1; else hi = m; }
+  return lo;
+}
+__device__ inline int slice_ub(const LcView& W, int lane, double pos) {             // first order position of the lane with key > pos
+  int lo = W.C.lane_start[lane], hi = lo + W.C.lane_count[lane];
+  while (lo < hi) { int m = (lo + hi) >> 1; if (W.C.spos[m] <= pos) lo = m + 1; else hi = m; }
+  return lo;
+}
+// [q0, end of the group of equal keys that holds the first usable entry at or after q0)
+__device__ inline int slice_group_fwd(const LcView& W, int lane, int q0, int excl) {
+  const int e = W.C.lane_start[lane] + W.C.lane_count[lane];
+  int q = q0; while (q < e) { int y = W.C.order[q]; if (y != excl && slice_ok(W, lane, y)) break; q++; }
+  if (q >= e) return e;
+  const double k = W.C.spos[q]; while (q < e && W.C.spos[q] == k) q++;
+  return q;
+}
+// [start of the group of equal keys that holds the last usable entry before q1, q1)
+__device__ inline int slice_group_bwd(const LcView& W, int lane, int q1, int excl) {
+  const int b = W.C.lane_start[lane];
+  int q = q1 - 1; while (q >= b) { int y = W.C.order[q]; if (y != excl && slice_ok(W, lane, y)) break; q--; }
+  if (q < b) return b;
+  const double k = W.C.spos[q]; while (q >= b && W.C.spos[q] == k) q--;
+  return q + 1;
+}
+__device__ inline void lc_mark_moved(const LcView& W, int v) {                       // v no longer sits where the sorted slice says
+  W.C.moved[v] = 1;
+  const int link = W.N.lane_link[W.V.lane[v]];
+  if (W.C.delta_next[v] == -1 && W.C.link_delta_head[link] != v) { W.C.delta_next[v] = W.C.link_delta_head[link]; W.C.link_delta_head[link] = v; }
 }
 __device__ inline double p1of(const LcView& W, int y) { return snap_pos(W.V.pos[y]); }
 // Reseau::GetLastVehicule (reseau.cpp:14041-14081) over candidates collected in id order
@@ -128,23 +163,31 @@ __device__ inline int pick_first(const LcView& W, int* c, int n) {
 }
 __device__ inline int near_aval(const LcView& W, int lane, double pos, int excl) {           // reseau.cpp:3583-3640
   int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 0.00001;
-  for_lane(W, lane, [&](int y) { double p = p1of(W, y); if (p >= pos && p <= pv && y != excl) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } });
+  auto f = [&](int y) { double p = p1of(W, y); if (p >= pos && p <= pv && y != excl) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } };
+  const int q0 = slice_lb(W, lane, pos);
+  for_slice(W, lane, q0, slice_group_fwd(W, lane, q0, excl), f); for_moved(W, lane, f);
   return pick_last(W, c, n);
 }
 __device__ inline int near_amont(const LcView& W, int lane, double pos, int excl) {          // reseau.cpp:3374-3436 (first stage; no previous lane in scope)
   int c[kTie]; int n = 0; double pt = -99999;
-  for_lane(W, lane, [&](int y) { double p = p1of(W, y); if (pos > p && p >= pt && y != excl) { if (p == pt) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pt = p; } } });
+  auto f = [&](int y) { double p = p1of(W, y); if (pos > p && p >= pt && y != excl) { if (p == pt) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pt = p; } } };
+  const int q1 = slice_lb(W, lane, pos);
+  for_slice(W, lane, slice_group_bwd(W, lane, q1, excl), q1, f); for_moved(W, lane, f);
   if (n > 0 && (pos - pt) < 9999) return pick_first(W, c, n);
   return -1;
 }
 __device__ inline int first_vehicule(const LcView& W, int lane) {                            // reseau.cpp:3255-3295 (last maximum in id order)
   int r = -1; double p = 0; int rid = -1;
-  for_lane(W, lane, [&](int y) { double q = p1of(W, y); if (q > p || (q == p && (r < 0 || W.V.id[y] > rid))) { if (q >= p) { r = y; p = q; rid = W.V.id[y]; } } });
+  auto f = [&](int y) { double q = p1of(W, y); if (q > p || (q == p && (r < 0 || W.V.id[y] > rid))) { if (q >= p) { r = y; p = q; rid = W.V.id[y]; } } };
+  const int q1 = W.C.lane_start[lane] + W.C.lane_count[lane];
+  for_slice(W, lane, slice_group_bwd(W, lane, q1, -1), q1, f); for_moved(W, lane, f);
   return r;
 }
 __device__ inline int prev_vehicule(const LcView& W, int v) {                                // reseau.cpp:3650-3718
   int lane = W.V.lane[v]; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1; double own = p1of(W, v);
-  for_lane(W, lane, [&](int y) { double p = p1of(W, y); if (p > own && p <= pv && y != v) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } });
+  auto f = [&](int y) { double p = p1of(W, y); if (p > own && p <= pv && y != v) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } };
+  const int q0 = slice_ub(W, lane, own);
+  for_slice(W, lane, q0, slice_group_fwd(W, lane, q0, v), f); for_moved(W, lane, f);
   return pick_last(W, c, n);
 }
 __device__ inline double dist_veh(const LcView& W, int a, int b) {                           // reseau.cpp:4446-4560
@@ -229,7 +272,7 @@ __device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol)
   W.V.lane[v] = tgt;
   if (fol >= 0 && W.N.lane_link[W.V.lane[fol]] == link) p = fmax(p, p1of(W, fol));
   W.V.pos[v] = p;
-  if (W.C.delta_next[v] == -1 && W.C.link_delta_head[link] != v) { W.C.delta_next[v] = W.C.link_delta_head[link]; W.C.link_delta_head[link] = v; }   // join the link's moved list once
+  lc_mark_moved(W, v);
   W.C.vdes[v] = -1;
   next_voie_draw(W, v, tgt);
   atomicAdd(W.C.n_changes, 1);
@@ -249,7 +292,7 @@ __device__ inline bool calcul_changement_voie(const DevParams& P, const LcView& 
       if (force && W.C.vdes[same] == W.N.lane_num[lane] && W.C.vdes[v] == W.N.lane_num[W.V.lane[same]] && W.V.vit[v] < 0.01 && W.V.vit[same] < 0.01) {
         changement_voie(W, v, tgt, -1); changement_voie(W, same, lane, -1); return true;
       }
-      W.V.pos[v] = p1 - 0.5; p1 = p1 - 0.5; move_back = true;
+      W.V.pos[v] = p1 - 0.5; p1 = p1 - 0.5; move_back = true; lc_mark_moved(W, v);
     } else return false;
   }
   double q = ratio * p1 + 0.001;
@@ -331,7 +374,9 @@ __global__ void k_lc_eval(DevNet N, DevVeh V, DevLc C, int n) {
 struct LcDirty { bool dirty, full, preds; double xlo, xhi; };
 __device__ inline void lc_window(const LcView& W, int lane, double pos, int excl, LcDirty* d) {
   double lo = -1, hi = -1;
-  for_lane(W, lane, [&](int y) { if (y == excl) return; double p = p1of(W, y); if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } });
+  auto f = [&](int y) { if (y == excl) return; double p = p1of(W, y); if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } };
+  const int qa = slice_lb(W, lane, pos), qb = slice_ub(W, lane, pos);
+  for_slice(W, lane, slice_group_bwd(W, lane, qa, excl), qa, f); for_slice(W, lane, qb, slice_group_fwd(W, lane, qb, excl), f); for_moved(W, lane, f);
   const double len = W.N.lane_len[lane];
   if (lo < 0) { d->preds = true; d->xlo = -1; } else d->xlo = fmin(d->xlo, lo / len);
   d->xhi = hi < 0 ? 2.0 : fmax(d->xhi, hi / len);
