@@ -50,6 +50,25 @@ struct DevVeh {
 
 struct DevLaneDyn { int *count, *start, *fill, *tail, *head_done; double* next_sortie; int* exit_winner; };
 
+// std::pow with the three exponents the laws use (GippsCarFollowing.cpp:75 gamma = 0.5, IDMCarFollowing.cpp:148 alpha = 4 and
+// :175 beta = 1.5), correctly rounded: the host libm the reference links (glibc) returns the correctly rounded value for all
+// but ~1e-5 of the arguments, CUDA's pow() is allowed 2 ulp — and the car-following feedback amplifies one ulp beyond the
+// 1e-9 gate within a few hundred steps.  Evaluated in double-double (error-free products through fma), rounded once.
+__device__ __forceinline__ double pow_half(double x) { return sqrt(x); }
+__device__ __forceinline__ double pow_four(double x) {
+  double p1 = x * x, e1 = fma(x, x, -p1);            // x^2 = p1 + e1 exactly
+  double p2 = p1 * p1, e2 = fma(p1, p1, -p2);        // p1^2 = p2 + e2 exactly
+  e2 = e2 + 2.0 * p1 * e1;                           // (p1 + e1)^2 = p2 + e2 + 2 p1 e1 (+ e1^2 ~ 2^-106)
+  return p2 + e2;
+}
+__device__ __forceinline__ double pow_three_halves(double z) {
+  if (!(z > 0.0) || z > DBL_MAX) return pow(z, 1.5);
+  double s = sqrt(z); double r = fma(-s, s, z);      // z = s^2 + r exactly
+  double c = r / (2.0 * s);                          // sqrt(z) = s + c (1 + O(2^-52))
+  double p = z * s, e = fma(z, s, -p);               // z s = p + e exactly
+  e = e + z * c;
+  return p + e;
+}
 __device__ __forceinline__ double snap_pos(double p) {           // vehicule.cpp:995-997
   return (p != SYM_UNDEF && fabs(p) < 0.00001) ? 0.0 : p;
 }
@@ -297,7 +316,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
   } else {
     double vmaxl = fmin(c.vx, n.link_vreg[n.lane_link[lanes[0]]]);
     if (c.law == 1) {                                                                  // Gipps
-      double vf = v1 + 2.5 * acc_max(c, v1) * dtv * (1 - v1 / vmaxl) * pow(0.025 + v1 / vmaxl, 0.5);
+      double vf = v1 + 2.5 * acc_max(c, v1) * dtv * (1 - v1 / vmaxl) * pow_half(0.025 + v1 / vmaxl);
       if (L >= 0) {
         const DevCls& cl = P.cls[V.cls[L]];
         double dmax = -c.decel; if (dmax == 0) dmax = -DBL_MAX;
@@ -318,7 +337,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
       if (relpos <= 0) z = 2;
       else { double dsp = c.esp + fmax(1 * v1 + (v1 * relsp) / (2.0 * sqrt(amax * dec)), 0.0); z = dsp / relpos; }
       ctx_free = z < 1;
-      double a = amax * (1.0 - pow(v1 / vmaxl, 4.0) - pow(z, 1.5));
+      double a = amax * (1.0 - pow_four(v1 / vmaxl) - pow_three_halves(z));
       goal = v1 * dtv + 0.5 * a * dtv * dtv;                                           // :700-703
     }
   }

@@ -67,7 +67,7 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
     bool ctx_free = true;
     double vmaxl = fmin(c.vx, n.link_vreg[n.lane_link[lanes[0]]]);
     if (c.law == 1) {                                                     // GippsCarFollowing.cpp:50-122
-      double vf = v1 + 2.5 * acc_max(c, v1) * dtv * (1 - v1 / vmaxl) * pow(0.025 + v1 / vmaxl, 0.5);
+      double vf = v1 + 2.5 * acc_max(c, v1) * dtv * (1 - v1 / vmaxl) * pow_half(0.025 + v1 / vmaxl);
       if (L >= 0) {
         const DevCls& cl = P.cls[lcls];
         double dmax = -c.decel; if (dmax == 0) dmax = -DBL_MAX;
@@ -88,7 +88,7 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
       if (relpos <= 0) z = 2;
       else { double dsp = c.esp + fmax(1 * v1 + (v1 * relsp) / (2.0 * sqrt(amax * dec)), 0.0); z = dsp / relpos; }
       ctx_free = z < 1;
-      double a = amax * (1.0 - pow(v1 / vmaxl, 4.0) - pow(z, 1.5));
+      double a = amax * (1.0 - pow_four(v1 / vmaxl) - pow_three_halves(z));
       goal_law = v1 * dtv + 0.5 * a * dtv * dtv;
     }
     if (ctx_free) hdr |= H_LAWFREE;

@@ -441,13 +441,14 @@ def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, 
 # ---------------------------------------------------------------------------------------------
 def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_steps=600, seed=42, classes=None, type_coefs=None,
              offramp_every=0, offramp_share=0.1, preseed_density=0.0, chgtvoie=True, dst_chgtvoie=200.0, dst_force=0.0, phi_force=1.0,
-             slow_lane_speed=None, shuffle=False) -> NetBuilder:
+             slow_lane_speed=None, shuffle=False, accbornee=False, relax=1.0, signal=None, signal_at=None, exponential=False) -> NetBuilder:
     """n_links consecutive links joined by pass-through distributors (lane k -> lane k).  Every `offramp_every` nodes a one-lane
     off-ramp leaves from lane 0 only, so exiting vehicles must reach lane 0 in the mandatory zone (`chgtvoie_dstfin`).
     Demand enters at the first link (lanes drawn uniformly); `preseed_density` (veh/m/lane) pre-seeds every lane.
-    The merges (on-ramp Convergents) of BASELINE config C3 are row A10 and not generated."""
+    The merges (on-ramp Convergents) of BASELINE config C3 are row A10 and not generated.
+    `signal=(green, amber, red)` puts a fixed-time stop line on every lane at the end of link `signal_at` (default: the middle)."""
     rng = np.random.default_rng(seed)
-    b = NetBuilder(n_steps=n_steps, seed=seed, chgtvoie=chgtvoie, dst_chgtvoie=dst_chgtvoie)
+    b = NetBuilder(n_steps=n_steps, seed=seed, chgtvoie=chgtvoie, dst_chgtvoie=dst_chgtvoie, accbornee=accbornee, relax=relax)
     b.params[F.P_PHI_FORCE] = phi_force
     b.params[F.P_DST_FORCE] = dst_force
     cl = classes or [VL, PL]
@@ -455,8 +456,10 @@ def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_st
         b.add_class(c)
     tc = type_coefs or ([0.85, 0.15] if len(cl) == 2 else None)
     nodes = [b.add_node("E", "E0", (0.0, 0.0))]
+    sig_j = (signal_at if signal_at is not None else n_links // 2) if signal else -1
+    ctrl = b.add_ctrl(sum(signal), [dict(len=sum(signal), signals=[])]) if signal else -1
     for j in range(1, n_links):
-        nodes.append(b.add_node("R", f"R{j}", (j * length, 0.0)))
+        nodes.append(b.add_node("R", f"R{j}", (j * length, 0.0), ctrl=ctrl if j == sig_j else -1))
     nodes.append(b.add_node("S", "S_end", (n_links * length, 0.0)))
     main = []
     for j in range(n_links):
@@ -466,6 +469,10 @@ def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_st
     for j in range(1, n_links):
         for k in range(n_lanes):
             b.add_succ(b.lane_of(main[j - 1], k), main[j], b.lane_of(main[j], k), 1.0, 1)
+        if j == sig_j:
+            b.ctrl[ctrl]["seqs"][0]["signals"].append((main[j - 1], main[j], signal[0], signal[1], 0.0))
+            for k in range(n_lanes):
+                b.add_stopline(b.lane_of(main[j - 1], k), length, ctrl, main[j - 1], k, main[j], k)
         if offramp_every and j % offramp_every == 0:
             s = b.add_node("S", f"S{j}", (j * length, -100.0))
             r = b.add_link(f"X{j}", nodes[j], s, 1, 150.0, vit_reg * 0.6, "S", geom=(j * length, 0.0, j * length + 100.0, -100.0))
@@ -479,7 +486,7 @@ def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_st
         ramp_routes[j] = b.add_route(main[:j] + [r])
         dests.append((x, offramp_share / len(ramps), [(ramp_routes[j], 1.0)]))
     if demand > 0:
-        b.add_entry(nodes[0], main[0], [(1e12, demand)], dests, type_coefs=tc)
+        b.add_entry(nodes[0], main[0], [(1e12, demand)], dests, type_coefs=tc, exponential=exponential)
     if preseed_density > 0:
         seeds = []
         for j, k in enumerate(main):

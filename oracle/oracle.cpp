@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -652,6 +653,18 @@ struct Sim {
     return pc;
   }
   // Gipps: GippsCarFollowing.cpp:50-122 ; IDM: IDMCarFollowing.cpp:61-211 ; distance AbstractCarFollowing.cpp:692-716
+  // std::pow is the host libm's (glibc: within 0.52 ulp, i.e. not the correctly rounded value for ~0.08 % of the arguments; another
+  // platform's libm differs again).  ORACLE_POW=cr swaps in the correctly rounded value of the three powers the laws use, the
+  // same double-double evaluation as the device (csrc/micro.cuh), so that the tests can separate the engine's logic (bit-exact
+  // under identical arithmetic) from the libm sensitivity of Gipps / IDM (1 ulp, amplified by the car-following feedback).
+  bool pow_cr = [] { const char* e = getenv("ORACLE_POW"); return e && !strcmp(e, "cr"); }();   // read when the simulation is created
+  double pow_law(double x, double y) const {
+    if (!pow_cr) return pow(x, y);
+    if (y == 0.5) return sqrt(x);
+    if (y == 4) { double p1 = x * x, e1 = std::fma(x, x, -p1); double p2 = p1 * p1, e2 = std::fma(p1, p1, -p2); e2 = e2 + 2.0 * p1 * e1; return p2 + e2; }
+    if (y == 1.5 && x > 0 && x <= DBL_MAX) { double r0 = sqrt(x); double r = std::fma(-r0, r0, x); double c = r / (2.0 * r0); double p = x * r0, e = std::fma(x, r0, -p); e = e + x * c; return p + e; }
+    return pow(x, y);
+  }
   double compute_law(Veh* v, double dtv, Ctx& c) {
     const Cls& k = cls[v->cls];
     if (k.law == 0) {                                                                        // Newell InternalCompute :53-68
@@ -663,7 +676,7 @@ struct Sim {
     if (k.law == 1) {
       const double A = 2.5, B = 0.025, G = 0.5, TH = 1;
       bool ff = true;
-      double vf = v->vit[1] + A * k.acc_max(v->vit[1]) * dtv * (1 - v->vit[1] / vmaxl) * pow(B + v->vit[1] / vmaxl, G);
+      double vf = v->vit[1] + A * k.acc_max(v->vit[1]) * dtv * (1 - v->vit[1] / vmaxl) * pow_law(B + v->vit[1] / vmaxl, G);
       if (c.leader) { Veh* L = c.leader;
         double dmax = -k.decel; if (dmax == 0) dmax = -DBL_MAX;
         double dlmax = -cls[L->cls].decel; if (dlmax == 0) dlmax = -DBL_MAX;
@@ -682,7 +695,7 @@ struct Sim {
     if (relpos <= 0) z = 2;
     else { double dsp = k.esp + std::max<double>(1 * sp + (sp * relsp) / (2.0 * sqrt(amax * dec)), 0); z = dsp / relpos; }
     c.free_flow = z < 1;
-    double a = amax * (1.0 - pow(sp / vmaxl, 4) - pow(z, 1.5));
+    double a = amax * (1.0 - pow_law(sp / vmaxl, 4) - pow_law(z, 1.5));
     return v->vit[1] * dtv + 0.5 * a * dtv * dtv;
   }
 

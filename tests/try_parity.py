@@ -26,6 +26,12 @@ elif case == "c4":
     b = synth.config("C4")
 elif case == "g30":
     b = synth.grid(n=30, n_steps=steps, demand_per_lane=0.0, preseed_per_lane=12.6, shuffle=False)
+elif case.startswith("lc:"):
+    from tests.test_gpu_lanechange import CASES
+    kw = dict(CASES[case.split(":")[1]])
+    if case.endswith(":seq"):
+        os.environ["SYMGPU_LC"] = "seq"
+    b = synth.corridor(**kw)
 else:
     raise SystemExit("unknown case")
 t0 = time.time()
