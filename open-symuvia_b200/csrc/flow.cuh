@@ -43,10 +43,8 @@ struct DevFlow {
 __device__ __forceinline__ int list_key(const DevVeh& V, int x, int by_id) { return by_id ? V.id[x] : x; }
 __global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, const int* lane_start, int by_id) {
   int ln = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ln >= n_lanes) return;
-  int n = lane_count[ln];
-  if (!n) return;
-  int s = lane_start[ln];
+  int n = ln < n_lanes ? lane_count[ln] : 0;
+  int s = n ? lane_start[ln] : 0;
   int cur = -1, nseg = 0, len = 0, mn = 0x7fffffff, mnx = -1;
   for (int a = n - 1; a >= 0; a--) {
     int p = s + a; int x = F.order[p];
@@ -61,8 +59,14 @@ __global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, c
     F.segpos[x] = cur; F.cut[x] = 0;
     len++; { int k = list_key(V, x, by_id); if (k < mn) { mn = k; mnx = x; } }
   }
-  F.seg_len[cur] = len; F.minslot[cur] = mnx;
-  int base = atomicAdd(&F.ctl->n_segments, nseg);                 // compact list of the segment fronts (any order)
+  if (n) { F.seg_len[cur] = len; F.minslot[cur] = mnx; }
+  // compact list of the segment fronts (any order): one atomic per warp
+  const int lane = threadIdx.x & 31;
+  int inc = nseg;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  int base = 0;
+  if (lane == 31 && inc) base = atomicAdd(&F.ctl->n_segments, inc);
+  base = __shfl_sync(0xffffffffu, base, 31) + inc - nseg;
   for (int a = n - 1; a >= 0; a--) if (F.isfront[s + a]) F.fronts[base++] = s + a;
 }
 
