@@ -444,7 +444,7 @@ struct symgpu_ctx {
   DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
-  long long lane_changes = 0; int n_sms = 148;
+  long long lane_changes = 0; int n_sms = 148; int relax_batch = kRelaxBatch;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
@@ -863,13 +863,16 @@ static int step_back(symgpu_ctx* c) {
     for (int sweep = 0;;) {
       int* ch = c->f_ctl.p->changed;                                     // device address arithmetic only
       if (sweep > 0) CK(cudaMemcpyAsync(ch, c->h_ctl_seed->changed, sizeof(int) * (kRelaxBatch + 1), cudaMemcpyHostToDevice, s));
-      for (int j = 0; j < kRelaxBatch; j++, sweep++) {
+      const int nb = sweep == 0 ? c->relax_batch : kRelaxBatch;          // first batch: what the previous step needed, plus the sweep that proves it
+      for (int j = 0; j < nb; j++, sweep++) {
         k_relax<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, sweep == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
       }
       CK(cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
       bool done = false;
-      for (int j = 1; j <= kRelaxBatch && !done; j++) { if (c->h_ctl->changed[j] == 0) done = true; else c->passes++; }
+      int used = 0;
+      for (int j = 1; j <= nb && !done; j++) { used = j; if (c->h_ctl->changed[j] == 0) done = true; else c->passes++; }
+      if (done && sweep == nb) c->relax_batch = std::min(kRelaxBatch, std::max(2, used + 1)); else if (!done) c->relax_batch = kRelaxBatch;
       if (done) break;
       if (sweep > n_sorted + kRelaxBatch) { g_err = "relaxation does not terminate (leader loop left uncut)"; return SYMGPU_E_CUDA; }
     }
