@@ -427,7 +427,7 @@ struct symgpu_ctx {
   // per step
   DBuf<int> sl_col; DBuf<double> sl_prop;
   DBuf<int> lane_count, lane_start, lane_fill, lane_tail, exit_winner, bsum, order, entre, sorti, stat;
-  DBuf<int> f_posidx, f_isfront, f_seg_len, f_seg_dep, f_segpos, f_minslot, f_cut, f_fronts, rl_lead, f_A, f_A2, f_Mn, f_Mn2, f_oncyc, f_cid;
+  DBuf<int> f_posidx, f_isfront, f_seg_len, f_seg_dep, f_segpos, f_minslot, f_cut, f_fronts, f_ulist, rl_lead, f_A, f_A2, f_Mn, f_Mn2, f_oncyc, f_cid;
   DBuf<double> rows, b_goal; DBuf<int> b_flags;
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DBuf<double> vl_used; DevFlow df; FlowCtl* h_ctl = nullptr; FlowCtl* h_ctl_seed = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
@@ -474,7 +474,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   l.next_sortie = c->next_sortie.p; l.exit_winner = c->exit_winner.p;
   DevFlow& fl = c->df;
   fl.order = c->order.p; fl.posidx = c->f_posidx.p; fl.isfront = c->f_isfront.p; fl.seg_len = c->f_seg_len.p; fl.seg_dep = c->f_seg_dep.p; fl.segpos = c->f_segpos.p;
-  fl.minslot = c->f_minslot.p; fl.cut = c->f_cut.p; fl.fronts = c->f_fronts.p;
+  fl.minslot = c->f_minslot.p; fl.cut = c->f_cut.p; fl.fronts = c->f_fronts.p; fl.ulist = c->f_ulist.p;
   fl.ctl = c->f_ctl.p; fl.A = c->f_A.p; fl.A2 = c->f_A2.p; fl.Mn = c->f_Mn.p; fl.Mn2 = c->f_Mn2.p; fl.oncyc = c->f_oncyc.p; fl.cid = c->f_cid.p; fl.rootkey = c->f_rootkey.p;
   DevLc& lc = c->dlc;
   lc.order = c->order.p; lc.lane_start = c->lane_start.p; lc.lane_count = c->lane_count.p; lc.vdes = c->v_vdes.p; lc.voies_ok = c->lc_voies_ok.p; lc.chgt = c->lc_chgt.p;
@@ -596,7 +596,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->bsum.alloc((L + kScanB - 1) / kScanB + 1)); CK(c->order.alloc(cap)); CK(c->entre.alloc((size_t)K * T)); CK(c->sorti.alloc((size_t)K * T));
   CK(c->stat.alloc(16)); CK(c->counters.alloc(16)); CK(c->draws.alloc(1));
   for (DBuf<int>* b : {&c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_cut,
-                       &c->f_fronts, &c->rl_lead, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
+                       &c->f_fronts, &c->f_ulist, &c->rl_lead, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid}) CK(b->alloc(cap));
   CK(c->t_flag.alloc(cap)); CK(c->t_off.alloc(cap)); CK(c->t_bsum.alloc(cap / kScanB + 2)); CK(c->t_id.alloc(cap)); CK(c->t_lane.alloc(cap));
   CK(c->t_pos.alloc(cap)); CK(c->t_vit.alloc(cap)); CK(c->t_acc.alloc(cap));
   CK(c->f_rootkey.alloc(cap)); CK(c->rows.alloc(((size_t)cap + 32) * kRowD)); CK(c->b_goal.alloc(cap)); CK(c->b_flags.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
@@ -634,7 +634,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
                        &c->seq_nsig, &c->sig_in, &c->sig_out, &c->exit_lanes, &c->exit_nl, &c->sl_col, &c->lane_count, &c->lane_start, &c->lane_fill, &c->lane_tail,
                        &c->exit_winner, &c->bsum, &c->order, &c->entre, &c->sorti, &c->stat, &c->eresult, &c->v_status, &c->v_id,
                        &c->f_posidx, &c->f_isfront, &c->f_seg_len, &c->f_seg_dep, &c->f_segpos, &c->f_minslot, &c->f_cut,
-                       &c->f_fronts, &c->rl_lead, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid,
+                       &c->f_fronts, &c->f_ulist, &c->rl_lead, &c->f_A, &c->f_A2, &c->f_Mn, &c->f_Mn2, &c->f_oncyc, &c->f_cid,
                        &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_memo, &c->v_ahead, &c->v_computed,
                        &c->v_ctx_nl, &c->v_ctx_lane, &c->v_ctx_leader, &c->v_ctx_flags}) b->free();
   for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
@@ -848,15 +848,15 @@ static int step_back(symgpu_ctx* c) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
     KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
     // leader loops: always looked for (the segment graph is small), cut where the reference's recursion would cut them
-    { int Klev = 1; while ((1LL << (2 * Klev)) < (long long)std::max(4, n_sorted)) Klev++;
+    { int Klev = 1; while ((1LL << (2 * Klev)) * kCycWalk < (long long)std::max(4, n_sorted)) Klev++;   // 4^K * walk >= longest possible chain
       Klev++;
-      const int Gs = std::min(G(n_sorted), c->n_sms * 8);
+      const int Gs = std::min(G(n_sorted), c->n_sms * 8), Gu = std::min(G(n_sorted), c->n_sms);
       KBEGIN(c, KID_LOOP);
-      k_cyc_init<<<Gs, B, 0, s>>>(c->df); LAUNCH(c);
+      k_cyc_walk<<<Gs, B, 0, s>>>(c->df); LAUNCH(c);
       int flip = 0;
-      for (int k = 0; k < Klev; k++) { k_cyc_jump<<<Gs, B, 0, s>>>(c->df, flip); LAUNCH(c); flip ^= 1; }
-      k_cyc_mark<<<Gs, B, 0, s>>>(c->dv, c->df, flip, by_id); LAUNCH(c);
-      k_cyc_break<<<Gs, B, 0, s>>>(c->dv, c->df, c->rows.p, c->counters.p);
+      for (int k = 0; k < Klev; k++) { k_cyc_jump<<<Gu, B, 0, s>>>(c->df, flip); LAUNCH(c); flip ^= 1; }
+      k_cyc_mark<<<Gu, B, 0, s>>>(c->dv, c->df, flip, by_id); LAUNCH(c);
+      k_cyc_break<<<Gu, B, 0, s>>>(c->dv, c->df, c->rows.p, c->counters.p);
       KEND(c); }
     // relaxation sweeps until one changes nothing (flow.cuh)
     KBEGIN(c, KID_FOLLOW);

@@ -9,7 +9,8 @@
 //   * k_seg      cuts every lane (already ordered by position) into SEGMENTS: maximal runs in which each vehicle follows
 //                the vehicle directly ahead.  Only a segment's front vehicle can depend on a vehicle outside it, so leader
 //                loops ("Infinite loop detected", vehicule.cpp:1201-1216) are loops of the much smaller segment graph.
-//   * k_cyc_*    pointer jumping (4 steps per round) on the segment graph finds every loop and its basin; the basin's first
+//   * k_cyc_*    a short walk per segment, then pointer jumping (4 steps per round) for the chains still open, finds every loop
+//                and its basin on the segment graph; the basin's first
 //                vehicle in m_LstVehicles order is the root the reference's recursion would start from, which fixes WHERE
 //                the loop is cut: the re-entered vehicle X is computed last, its follower Y uses the estimated leader speed
 //                (NewellCarFollowing.cpp:217-230).  After the cuts the leader graph is acyclic.
@@ -27,10 +28,10 @@ namespace symb200 {
 
 constexpr int kRelaxBatch = 8;   // sweeps launched between two looks at the change counters
 
-struct FlowCtl { int n_segments, pad0, pad1, pad2; int changed[kRelaxBatch + 1]; int pad3[3]; };
+struct FlowCtl { int n_segments, n_unres, pad1, pad2; int changed[kRelaxBatch + 1]; int pad3[3]; };
 
 struct DevFlow {
-  int *order, *posidx, *isfront, *seg_len, *seg_dep, *segpos, *minslot, *cut, *fronts;
+  int *order, *posidx, *isfront, *seg_len, *seg_dep, *segpos, *minslot, *cut, *fronts, *ulist;
   FlowCtl* ctl;
   // loop detection scratch (indexed by order position)
   int *A, *A2, *Mn, *Mn2, *oncyc, *cid;
@@ -125,32 +126,47 @@ __global__ void k_place(DevNet N, DevVeh V, const double* rows, const double* b_
   phase_c(cP_ref(), N, V, rows, b_goal, b_flags, p, inst);
 }
 
-// ---- leader loops: pointer jumping on the segment graph (threads stride over the compact list of fronts) ----------------
-__global__ void k_cyc_init(DevFlow F) {
+// ---- leader loops: pointer jumping on the segment graph ---------------------------------------------------------------
+// Most chains end within a few segments (a vehicle without leader, a cut, a ghost): every front first walks kCycWalk steps on
+// its own; the fronts that have not reached a terminal by then (long chains, loops and their basins) go to a short list and
+// only they take part in the pointer jumping.  A[p] of a resolved front points straight at its terminal (in both buffers).
+constexpr int kCycWalk = 8;
+__global__ void k_cyc_walk(DevFlow F) {
   const int ns = F.ctl->n_segments;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
-    int p = F.fronts[t];
-    F.oncyc[p] = 0; F.rootkey[p] = ~0ULL; F.cid[p] = -1; F.Mn[p] = p;
-    int d = F.seg_dep[p];
-    F.A[p] = d >= 0 ? F.segpos[d] : p;             // a segment without dependency is a terminal (fixed point of the jump)
+  for (int t0 = blockIdx.x * blockDim.x; t0 < ns; t0 += gridDim.x * blockDim.x) {      // whole warps stay together for the ballot
+    const int t = t0 + threadIdx.x;
+    bool unres = false; int p = -1;
+    if (t < ns) {
+      p = F.fronts[t];
+      int q = p, mn = p; bool term = false;
+      for (int h = 0; h < kCycWalk; h++) { int d = F.seg_dep[q]; if (d < 0) { term = true; break; } q = F.segpos[d]; if (h + 1 < kCycWalk && q < mn) mn = q; }
+      F.A[p] = q; F.A2[p] = q; F.Mn[p] = mn; F.Mn2[p] = mn;
+      unres = !term;
+      if (unres) { F.oncyc[p] = 0; F.rootkey[p] = ~0ULL; F.cid[p] = -1; }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, unres);
+    if (m) { const int lane = threadIdx.x & 31; int base = 0;
+      if (lane == 0) base = atomicAdd(&F.ctl->n_unres, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (unres) F.ulist[base + __popc(m & ((1u << lane) - 1))] = p; }
   }
 }
-__global__ void k_cyc_jump(DevFlow F, int flip) {  // A <- A^4, Mn <- min over the four segments stepped over
-  const int ns = F.ctl->n_segments;
+__global__ void k_cyc_jump(DevFlow F, int flip) {  // A <- A^4, Mn <- min over the segments stepped over
+  const int ns = F.ctl->n_unres;
   const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;
   int* Ao = flip ? F.A : F.A2; int* Mo = flip ? F.Mn : F.Mn2;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
-    int p = F.fronts[t];
+    int p = F.ulist[t];
     int a = A[p], a1 = A[a], a2 = A[a1];
     Ao[p] = A[a2];
     Mo[p] = min(min(M[p], M[a]), min(M[a1], M[a2]));
   }
 }
 __global__ void k_cyc_mark(DevVeh V, DevFlow F, int flip, int by_id) {
-  const int ns = F.ctl->n_segments;
+  const int ns = F.ctl->n_unres;
   const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
-    int p = F.fronts[t];
+    int p = F.ulist[t];
     int c0 = A[p];                                 // where this segment's chain ends up: a terminal, or a segment on a loop
     if (F.seg_dep[c0] < 0) continue;
     F.oncyc[c0] = 1;
@@ -162,9 +178,9 @@ __global__ void k_cyc_mark(DevVeh V, DevFlow F, int flip, int by_id) {
 }
 // one thread per loop: cut it where the reference's recursion would
 __global__ void k_cyc_break(DevVeh V, DevFlow F, double* rows, long long* counters) {
-  const int ns = F.ctl->n_segments;
+  const int ns = F.ctl->n_unres;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
-  int p = F.fronts[t];
+  int p = F.ulist[t];
   if (!F.oncyc[p] || F.cid[p] != p) continue;      // representative = smallest segment of the loop
   unsigned long long key = F.rootkey[p];
   int rs = (int)(key & 0xffffffffu); int r = F.minslot[rs];
