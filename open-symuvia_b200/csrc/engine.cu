@@ -210,7 +210,10 @@ __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const
 
 // one thread per position of the lane order: neighbouring threads are neighbours on a lane, so they walk the same context
 // lanes, stop lines and movements (little divergence, table reads shared through L1) and their rows are written coalesced
-__global__ void k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
+#ifndef SYM_CTX_BLOCKS
+#define SYM_CTX_BLOCKS 8   // 32 registers: the kernel waits on dependent table look-ups, so resident warps matter more than spills (C4: 3 blocks/SM 0.40 ms, 4: 0.33, 6: 0.30, 8: 0.296)
+#endif
+__global__ void __launch_bounds__(256, SYM_CTX_BLOCKS) k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
   int i = order[p];

@@ -76,7 +76,10 @@ __global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, c
 // Leaders are mostly the neighbour in the lane order, i.e. in the same thread block: the block repeats its part until
 // nothing in it changes (kLocalIters at most), so a global sweep carries a change down whole segments, not one vehicle.
 constexpr int kLocalIters = 48;
-__global__ void __launch_bounds__(256) k_relax(DevNet N, DevVeh V, DevLaneDyn LD, const double* __restrict__ rows, double* b_goal, int* b_flags,
+#ifndef SYM_RELAX_BLOCKS
+#define SYM_RELAX_BLOCKS 5   // 48 registers (C4: 3 blocks/SM 0.38 ms, 4: 0.324, 5: 0.321, 6: 0.334)
+#endif
+__global__ void __launch_bounds__(256, SYM_RELAX_BLOCKS) k_relax(DevNet N, DevVeh V, DevLaneDyn LD, const double* __restrict__ rows, double* b_goal, int* b_flags,
                                                double* vl_used, int* rl_lead, int n_sorted, int first, const int* prev, int* changed, double inst) {
   if (!first && *prev == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
