@@ -868,7 +868,7 @@ static int step_back(symgpu_ctx* c) {
       if (sweep > 0) CK(cudaMemcpyAsync(ch, c->h_ctl_seed->changed, sizeof(int) * (kRelaxBatch + 1), cudaMemcpyHostToDevice, s));
       const int nb = sweep == 0 ? c->relax_batch : kRelaxBatch;          // first batch: what the previous step needed, plus the sweep that proves it
       for (int j = 0; j < nb; j++, sweep++) {
-        k_relax<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, sweep == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
+        k_relax<<<(n_sorted + SYM_RELAX_THREADS - 1) / SYM_RELAX_THREADS, SYM_RELAX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, sweep == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
       }
       CK(cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));

@@ -77,9 +77,12 @@ __global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, c
 // nothing in it changes (kLocalIters at most), so a global sweep carries a change down whole segments, not one vehicle.
 constexpr int kLocalIters = 48;
 #ifndef SYM_RELAX_BLOCKS
-#define SYM_RELAX_BLOCKS 5   // 48 registers (C4: 3 blocks/SM 0.38 ms, 4: 0.324, 5: 0.321, 6: 0.334)
+#define SYM_RELAX_BLOCKS 8   // 128 threads x 8 blocks per SM, 64 registers (C4, ms per step: 256x3 0.38, 256x5 0.32, 128x10 0.30, 128x8 0.297, 512x2 0.35)
 #endif
-__global__ void __launch_bounds__(256, SYM_RELAX_BLOCKS) k_relax(DevNet N, DevVeh V, DevLaneDyn LD, const double* __restrict__ rows, double* b_goal, int* b_flags,
+#ifndef SYM_RELAX_THREADS
+#define SYM_RELAX_THREADS 128
+#endif
+__global__ void __launch_bounds__(SYM_RELAX_THREADS, SYM_RELAX_BLOCKS) k_relax(DevNet N, DevVeh V, DevLaneDyn LD, const double* __restrict__ rows, double* b_goal, int* b_flags,
                                                double* vl_used, int* rl_lead, int n_sorted, int first, const int* prev, int* changed, double inst) {
   if (!first && *prev == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
