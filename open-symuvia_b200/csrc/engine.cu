@@ -153,6 +153,9 @@ __global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill
 // in-lane order by (start-of-step position, id) + own-lane leader links + lane tail.
 // Replaces the per-query linear scans of Reseau::GetPrevVehicule (reseau.cpp:3650-3718) and
 // GetNearAvalVehicule (:3583-3640) over the id-ordered lane sets.
+#ifndef SYM_LANE_THREADS
+#define SYM_LANE_THREADS 256   // one thread per lane (k_sort_lanes, k_seg)
+#endif
 __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const int* lane_start, int* order,
                              int* lane_tail, int* posidx, long long* counters) {
   int ln = blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,7 +216,10 @@ __global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const
 #ifndef SYM_CTX_BLOCKS
 #define SYM_CTX_BLOCKS 8   // 32 registers: the kernel waits on dependent table look-ups, so resident warps matter more than spills (C4: 3 blocks/SM 0.40 ms, 4: 0.33, 6: 0.30, 8: 0.296)
 #endif
-__global__ void __launch_bounds__(256, SYM_CTX_BLOCKS) k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
+#ifndef SYM_CTX_THREADS
+#define SYM_CTX_THREADS 256
+#endif
+__global__ void __launch_bounds__(SYM_CTX_THREADS, SYM_CTX_BLOCKS) k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
   int i = order[p];
@@ -802,7 +808,7 @@ static int step_front(symgpu_ctx* c) {
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
     KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
-    KBEGIN(c, KID_SORT); k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); KEND(c);
+    KBEGIN(c, KID_SORT); k_sort_lanes<<<(L + SYM_LANE_THREADS - 1) / SYM_LANE_THREADS, SYM_LANE_THREADS, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); KEND(c);
   }
   // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
   if (c->chgtvoie && n > 0) {
@@ -845,11 +851,11 @@ static int step_back(symgpu_ctx* c) {
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
   if (n > 0) {
-    if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT); k_context<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
+    if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT); k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
-    KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
+    KBEGIN(c, KID_SEG); k_seg<<<(L + SYM_LANE_THREADS - 1) / SYM_LANE_THREADS, SYM_LANE_THREADS, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
     // leader loops: always looked for (the segment graph is small), cut where the reference's recursion would cut them
     { int Klev = 1; while ((1LL << (2 * Klev)) * kCycWalk < (long long)std::max(4, n_sorted)) Klev++;   // 4^K * walk >= longest possible chain
       Klev++;
