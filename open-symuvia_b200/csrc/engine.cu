@@ -6,7 +6,7 @@
 // Step pipeline (all on one stream, no host round trip unless the network has origins):
 //   k_signals      A8   per stop line: colour + green fraction of this step (ControleurDeFeux.cpp:96-148)
 //   k_prepare      A2   per vehicle : lane membership histogram          (reseau.cpp:3901-3976)
-//   scan + k_scatter + k_sort_lanes  A3: counting sort by lane, in-lane order by (position, id), own-lane
+//   scan + k_scatter + k_lane_rank/links  A3: counting sort by lane, in-lane order by (position, id), own-lane
 //                       leader links, lane tail                          (reseau.cpp:3583-3820)
 //   k_context      A3/A5/A12 per vehicle: context lanes, leader, deltaN, free-flow distance
 //   k_follow_pass  A4-A7 per lane  : ordered chain front -> back (leader first, vehicule.cpp:1304-1309);
@@ -140,74 +140,71 @@ __global__ void k_scan_add(int* out, const int* bsum, int n) {
   if (i < n) out[i] += bsum[blockIdx.x];
 }
 
-__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* order) {
+__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* uorder, double* ukey, int* uid, int* ulane) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int st = V.status[i];
   if (st != ST_ALIVE && st != ST_NEW) return;
   int ln = V.lane[i];
   int slot = lane_start[ln] + atomicAdd(&lane_fill[ln], 1);
-  order[slot] = i;
+  uorder[slot] = i; ukey[slot] = snap_pos(V.pos[i]); uid[slot] = V.id[i]; ulane[slot] = ln;     // the lane's slice, in arrival order, with its sort keys
 }
 
 // in-lane order by (start-of-step position, id) + own-lane leader links + lane tail.
 // Replaces the per-query linear scans of Reseau::GetPrevVehicule (reseau.cpp:3650-3718) and
 // GetNearAvalVehicule (:3583-3640) over the id-ordered lane sets.
-#ifndef SYM_LANE_THREADS
-#define SYM_LANE_THREADS 256   // one thread per lane (k_sort_lanes, k_seg)
-#endif
-__global__ void k_sort_lanes(DevVeh V, int n_lanes, const int* lane_count, const int* lane_start, int* order,
-                             int* lane_tail, int* posidx, long long* counters) {
-  int ln = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ln >= n_lanes) return;
-  int n = lane_count[ln];
-  if (!n) { lane_tail[ln] = -1; return; }
-  int s = lane_start[ln];
-  for (int a = 1; a < n; a++) {
-    int x = order[s + a]; double px = snap_pos(V.pos[x]); int idx = V.id[x];
-    int j = a - 1;
-    while (j >= 0) {
-      int y = order[s + j]; double py = snap_pos(V.pos[y]);
-      if (py > px || (py == px && V.id[y] > idx)) { order[s + j + 1] = y; j--; } else break;
-    }
-    order[s + j + 1] = x;
-  }
+// Two fully parallel kernels, one thread per vehicle (lanes are short: a vehicle's rank is a scan of its lane's slice, which its
+// lane mates read too and L1 serves):
+//   k_lane_rank   rank of (position, id) among the lane's keys -> position in the lane order; keys and lane stored in that order
+//   k_lane_links  nearest vehicle ahead with the reference's rule for equal positions, lane tail
+__global__ void k_lane_rank(int n_sorted, const int* lane_start, const int* lane_count, const int* uorder, const double* ukey, const int* uid, const int* ulane,
+                            int* order, double* skey, int* sid, int* slane, int* posidx) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_sorted) return;
+  const int ln = ulane[u]; const int s = lane_start[ln], n = lane_count[ln];
+  const double k = ukey[u]; const int id = uid[u];
+  int r = 0;
+  for (int a = 0; a < n; a++) { double ka = ukey[s + a]; r += (ka < k || (ka == k && uid[s + a] < id)) ? 1 : 0; }
+  const int p = s + r; const int x = uorder[u];
+  order[p] = x; skey[p] = k; sid[p] = id; slane[p] = ln; posidx[x] = p;
+}
+__global__ void k_lane_links(DevVeh V, int n_sorted, const int* lane_start, const int* lane_count, const int* order, const double* skey, const int* sid,
+                             const int* slane, int* lane_tail, long long* counters) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_sorted) return;
+  const int ln = slane[p]; const int s = lane_start[ln], n = lane_count[ln]; const int a = p - s;
   // Equal positions: Reseau::GetLastVehicule (reseau.cpp:14041-14081) returns the first candidate (id order) that is not
   // the leader of another candidate; the candidates' leaders are read from their previous-step context (a candidate met
   // while it has already rebuilt its context this step is counted in SYMGPU_CNT_TIES but not replayed).
   auto pick = [&](int b0, int b1) -> int {          // group = order[s+b0 .. s+b1) at one position, id-ascending
     if (b1 - b0 == 1) return order[s + b0];
     for (int i = b0; i < b1; i++) {
-      int idi = V.id[order[s + i]]; bool fol = false;
+      int idi = sid[s + i]; bool fol = false;
       for (int j = b0; j < b1 && !fol; j++) if (j != i && V.prev_leader[order[s + j]] == idi) fol = true;
       if (!fol) return order[s + i];
     }
     return order[s + b1 - 1];
   };
-  int tail = -1; int ties = 0;
-  for (int a = 0; a < n; a++) {
-    int x = order[s + a]; double px = snap_pos(V.pos[x]);
-    if (tail < 0 && px >= 0) {
-      int b1 = a + 1; while (b1 < n && snap_pos(V.pos[order[s + b1]]) == px) b1++;
-      if (b1 - a > 1) ties++;
-      tail = pick(a, b1);
-    }
-    double own = px <= SYM_UNDEF ? 0.0 : px;
-    bool eq_ok = V.status[x] == ST_NEW;           // GetPos(0) == UNDEF only before the first computation (reseau.cpp:3695)
-    int ld = -1;
-    for (int b = a + 1; b < n; b++) {
-      int y = order[s + b]; double pb = snap_pos(V.pos[y]);
-      if (pb > own || (eq_ok && pb == own)) {
-        int b1 = b + 1; while (b1 < n && snap_pos(V.pos[order[s + b1]]) == pb) b1++;
-        if (b1 - b > 1) ties++;
-        ld = pick(b, b1);
-        break;
-      }
-    }
-    V.ahead[x] = ld;
-    posidx[x] = s + a;
+  const int x = order[p]; const double px = skey[p];
+  int ties = 0;
+  if (px >= 0 && (a == 0 || skey[p - 1] < 0)) {     // first vehicle with a position: its group holds the lane's tail (GetLastVehicule)
+    int b1 = a + 1; while (b1 < n && skey[s + b1] == px) b1++;
+    if (b1 - a > 1) ties++;
+    lane_tail[ln] = pick(a, b1);
   }
-  lane_tail[ln] = tail;
+  const double own = px <= SYM_UNDEF ? 0.0 : px;
+  const bool eq_ok = V.status[x] == ST_NEW;         // GetPos(0) == UNDEF only before the first computation (reseau.cpp:3695)
+  int ld = -1;
+  for (int b = a + 1; b < n; b++) {
+    double pb = skey[s + b];
+    if (pb > own || (eq_ok && pb == own)) {
+      int b1 = b + 1; while (b1 < n && skey[s + b1] == pb) b1++;
+      if (b1 - b > 1) ties++;
+      ld = pick(b, b1);
+      break;
+    }
+  }
+  V.ahead[x] = ld;
   if (ties) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_TIES], (unsigned long long)ties);
 }
 
@@ -441,7 +438,7 @@ struct symgpu_ctx {
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DBuf<double> vl_used; DevFlow df; FlowCtl* h_ctl = nullptr; FlowCtl* h_ctl_seed = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
-  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, lc_spos; DBuf<int> lc_moved; bool lc_seq = false; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
+  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, u_key, s_key; DBuf<int> lc_moved, u_order, u_id, u_lane, s_id, s_lane; bool lc_seq = false; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
@@ -488,7 +485,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   DevLc& lc = c->dlc;
   lc.order = c->order.p; lc.lane_start = c->lane_start.p; lc.lane_count = c->lane_count.p; lc.vdes = c->v_vdes.p; lc.voies_ok = c->lc_voies_ok.p; lc.chgt = c->lc_chgt.p;
   lc.delta_next = c->lc_delta_next.p; lc.link_delta_head = c->lc_link_head.p; lc.rng = c->lc_rng.p; lc.n_changes = c->lc_nchg.p;
-  lc.moved = c->lc_moved.p; lc.posidx = c->f_posidx.p; lc.spos = c->lc_spos.p; lc.counters = c->counters.p; lc.kind = c->lc_kind.p; lc.code = c->lc_code.p; lc.tl_pre = c->lc_tl_pre.p; lc.rfol = c->lc_rfol.p; lc.rtgt = c->lc_rtgt.p; lc.had_mand = c->lc_had_mand.p; lc.phi = c->lc_phi.p;
+  lc.moved = c->lc_moved.p; lc.posidx = c->f_posidx.p; lc.spos = c->s_key.p; lc.counters = c->counters.p; lc.kind = c->lc_kind.p; lc.code = c->lc_code.p; lc.tl_pre = c->lc_tl_pre.p; lc.rfol = c->lc_rfol.p; lc.rtgt = c->lc_rtgt.p; lc.had_mand = c->lc_had_mand.p; lc.phi = c->lc_phi.p;
   lc.dst_chgtvoie = c->net.params[SYMFLAT_P_DSTCHGT]; lc.dst_force = c->net.params[SYMFLAT_P_DST_FORCE] > 0 ? c->net.params[SYMFLAT_P_DST_FORCE] : -1.0;
   lc.phi_force = c->net.params[SYMFLAT_P_PHI_FORCE] > 0 ? c->net.params[SYMFLAT_P_PHI_FORCE] : 1.0; lc.ordre = 1;
   DevSig& s = c->ds;
@@ -609,7 +606,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->t_flag.alloc(cap)); CK(c->t_off.alloc(cap)); CK(c->t_bsum.alloc(cap / kScanB + 2)); CK(c->t_id.alloc(cap)); CK(c->t_lane.alloc(cap));
   CK(c->t_pos.alloc(cap)); CK(c->t_vit.alloc(cap)); CK(c->t_acc.alloc(cap));
   CK(c->f_rootkey.alloc(cap)); CK(c->rows.alloc(((size_t)cap + 32) * kRowD)); CK(c->b_goal.alloc(cap)); CK(c->b_flags.alloc(cap)); CK(c->f_ctl.alloc(1)); CK(cudaMallocHost(&c->h_ctl, sizeof(FlowCtl)));
-  CK(c->vl_used.alloc(cap)); CK(cudaMallocHost(&c->h_ctl_seed, sizeof(FlowCtl))); memset(c->h_ctl_seed, 0, sizeof(FlowCtl)); c->h_ctl_seed->changed[0] = 1;
+  CK(c->vl_used.alloc(cap)); CK(c->u_key.alloc(cap)); CK(c->s_key.alloc(cap)); for (DBuf<int>* b : {&c->u_order, &c->u_id, &c->u_lane, &c->s_id, &c->s_lane}) CK(b->alloc(cap)); CK(cudaMallocHost(&c->h_ctl_seed, sizeof(FlowCtl))); memset(c->h_ctl_seed, 0, sizeof(FlowCtl)); c->h_ctl_seed->changed[0] = 1;
   { int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device)); c->n_sms = std::max(1, sms); }
   CK(c->exited.alloc(cap)); CK(c->edesc.alloc(std::max(1, n_entry_lanes))); CK(c->eresult.alloc(std::max(1, n_entry_lanes)));
   // vehicles
@@ -619,7 +616,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
-    CK(c->lc_phi.alloc(3 * cap)); CK(c->lc_had_mand.alloc(cap)); CK(c->lc_spos.alloc(cap)); CK(c->lc_moved.alloc(cap)); const char* e = getenv("SYMGPU_LC"); c->lc_seq = e && !strcmp(e, "seq"); }
+    CK(c->lc_phi.alloc(3 * cap)); CK(c->lc_had_mand.alloc(cap)); CK(c->lc_moved.alloc(cap)); const char* e = getenv("SYMGPU_LC"); c->lc_seq = e && !strcmp(e, "seq"); }
   for (DBuf<double>* b : {&c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre, &c->v_dstp, &c->v_hent,
                           &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) CK(b->alloc(cap));
   fill_dev_structs(c);
@@ -655,7 +652,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_ctl_seed) cudaFreeHost(c->h_ctl_seed);
-  c->vl_used.free();
+  c->vl_used.free(); c->u_key.free(); c->s_key.free(); for (DBuf<int>* b : {&c->u_order, &c->u_id, &c->u_lane, &c->s_id, &c->s_lane}) b->free();
   if (c->h_stat) cudaFreeHost(c->h_stat);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -737,7 +734,7 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
 
 // per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
 enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_LC, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_COUNT };
-static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_sort_lanes", "k_context", "k_lane_change", "k_seg", "k_relax",
+static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_lane_order", "k_context", "k_lane_change", "k_seg", "k_relax",
                                               "k_cyc_loops", "k_place", "k_entries", "k_final"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
@@ -807,8 +804,10 @@ static int step_front(symgpu_ctx* c) {
     KBEGIN(c, KID_SCAN); k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
-    KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); KEND(c);
-    KBEGIN(c, KID_SORT); k_sort_lanes<<<(L + SYM_LANE_THREADS - 1) / SYM_LANE_THREADS, SYM_LANE_THREADS, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); KEND(c);
+    KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); KEND(c);
+    KBEGIN(c, KID_SORT); CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
+      if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
+        k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } KEND(c);
   }
   // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
   if (c->chgtvoie && n > 0) {
@@ -833,8 +832,10 @@ static int step_front(symgpu_ctx* c) {
       int nb = (L + kScanB - 1) / kScanB;
       k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
       if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); LAUNCH(c); }
-      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->order.p); LAUNCH(c);
-      k_sort_lanes<<<G(L), B, 0, s>>>(c->dv, L, c->lane_count.p, c->lane_start.p, c->order.p, c->lane_tail.p, c->f_posidx.p, c->counters.p); LAUNCH(c);
+      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); LAUNCH(c);
+      CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
+      if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
+        k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } LAUNCH(c);
     }
   }
   c->ss.n = n; c->ss.n_sorted = n_sorted; c->ss.has_entries = has_entries;
@@ -855,7 +856,7 @@ static int step_back(symgpu_ctx* c) {
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
-    KBEGIN(c, KID_SEG); k_seg<<<(L + SYM_LANE_THREADS - 1) / SYM_LANE_THREADS, SYM_LANE_THREADS, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
+    KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
     // leader loops: always looked for (the segment graph is small), cut where the reference's recursion would cut them
     { int Klev = 1; while ((1LL << (2 * Klev)) * kCycWalk < (long long)std::max(4, n_sorted)) Klev++;   // 4^K * walk >= longest possible chain
       Klev++;

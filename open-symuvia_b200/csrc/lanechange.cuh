@@ -36,7 +36,7 @@ __device__ inline int rng_next(DevRng* r) {                            // RandMa
 
 struct DevLc {
   const int *order, *lane_start, *lane_count;
-  int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head, *moved; const int* posidx; double* spos;
+  int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head, *moved; const int* posidx; const double* spos;   // spos: the lane order's sort keys (k_lane_rank)
   DevRng* rng; int* n_changes;      // n_changes[1]: draws consumed by k_lc_walk (the host advances its own stream)
   double dst_chgtvoie, dst_force, phi_force; int ordre;
   // records of k_lc_eval: stage 0 = mandatory pass, 1 / 2 = first / second candidate lane of the discretionary pass
@@ -50,7 +50,6 @@ __global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   C.chgt[i] = 0; C.delta_next[i] = -1; C.moved[i] = 0;
-  if (V.status[i] == ST_ALIVE || V.status[i] == ST_NEW) C.spos[C.posidx[i]] = snap_pos(V.pos[i]);   // the keys k_sort_lanes ordered the lane by
   if (V.status[i] != ST_ALIVE) return;                                // vehicles created this step have no link at index 1 (reseau.cpp:3941)
   int lane = V.lane[i]; int link = N.lane_link[lane]; int nl = N.link_nl[link]; int first = N.link_first[link];
   double p1 = snap_pos(V.pos[i]);
