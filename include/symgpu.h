@@ -61,6 +61,11 @@ int symgpu_mp_sizes(symgpu_ctx* c, int* export_cnt, int* halo_cnt);             
 int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails);
 int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, double* send_rows, int cap_per_peer, int* send_counts);
 int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows);          /* rows of 16 doubles */
+/* Origins in a partitioned run: every rank replays the creation draws of all origins (same seed, same ids) and keeps the vehicles of
+   the entry lanes it owns; the device's own draws of the step are summed over the ranks by the caller and committed on every rank. */
+int symgpu_mp_has_origins(symgpu_ctx* c);
+long symgpu_mp_local_draws(symgpu_ctx* c);
+int symgpu_mp_commit_draws(symgpu_ctx* c, long total_over_ranks);
 
 /* Per-kernel device timing (CUDA events on the step stream) for roofline accounting. */
 int symgpu_profile(symgpu_ctx* c, int enable);

@@ -455,7 +455,7 @@ struct symgpu_ctx {
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
   struct Mp { bool on = false; int rank = 0, world = 1, ghost_base = 0, n_halo = 0, n_export = 0; std::vector<int> lane_owner, halo_lanes, halo_off, export_lanes, export_off;
-    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count, d_free; int free_count = 0; int mig_cap = 0; std::vector<int> h_mig_count; } mp;
+    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count, d_free; int free_count = 0; int mig_cap = 0; std::vector<int> h_mig_count; unsigned draw_delta = 0; } mp;
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
 };
 
@@ -678,6 +678,10 @@ static double max_debit_max(const symgpu_ctx* c) { double m = 0; for (int i = 0;
 // SymCreateVehicle path (reseau.cpp:13351 -> :2233-2240 -> GenerateVehicle with type, lane and destination imposed):
 // only the itinerary (:515), law-coefficient and Jorge draws remain; the vehicle joins m_LstVehicles BEFORE
 // InitVehicules, so it is shifted once (state at index 1, position still undefined) like an older ready vehicle.
+// partitioned runs: every rank replays the creation of ALL origins (same seed, same draws, same vehicle ids) and keeps the
+// vehicles whose entry lane it owns, so the global random sequence and the ids need no exchange
+static inline bool owns_lane(symgpu_ctx* c, int lane) { return !c->mp.on || c->mp.lane_owner[lane] == c->mp.rank; }
+
 static void create_api_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::vector<EntryLane*>& new_row_lane) {
   const double dt = c->P.dt, inst = c->t;
   for (auto& a : c->api_queue) {
@@ -688,8 +692,9 @@ static void create_api_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, s
     int route = e.dest_routes[a.dest].back().first;
     { double r = c->rng.next() / 32767.0, sum = 0; for (auto& q : e.dest_routes[a.dest]) { sum += q.second; if (r <= sum) { route = q.first; break; } } }
     c->rng.next();
-    c->created++;
     EntryLane& el = e.lanes[nv];
+    if (!owns_lane(c, el.lane)) continue;
+    c->created++;
     HostVeh hv{a.id, a.cls, route, el.lane, a.dbt, inst - dt + a.dbt};
     if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);
     else { HostRow r{ST_ALIVE, a.id, a.cls, route, 0, el.lane, SYM_UNDEF, c->P.cls[a.cls].vx, 0.0, a.dbt, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el);
@@ -721,8 +726,9 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
       int route = e.dest_routes[d].back().first;
       { double r = c->rng.next() / 32767.0, sum = 0; for (auto& q : e.dest_routes[d]) { sum += q.second; if (r <= sum) { route = q.first; break; } } }
       c->rng.next();                                                                                // TirageJorge
-      c->created++;
       EntryLane& el = e.lanes[nv];
+      if (!owns_lane(c, el.lane)) continue;
+      c->created++;
       HostVeh hv{id, tv, route, el.lane, tcre, inst - dt + tcre};
       (void)f;
       if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);   // :794-800
@@ -912,7 +918,8 @@ static int step_back(symgpu_ctx* c) {
     std::sort(c->last_exited.begin(), c->last_exited.end(), [&](const ExitRow& a, const ExitRow& b) { return c->mp.on ? a.id < b.id : a.slot < b.slot; }); }
   // global random sequence: account for the draws made on the device during this step
   unsigned dd = (unsigned)c->h_stat[7];
-  if (has_entries) c->rng.skip(dd - c->dev_draws_seen); else c->rng.count += dd - c->dev_draws_seen;
+  if (c->mp.on && has_entries) c->mp.draw_delta = dd - c->dev_draws_seen;      // committed with the other ranks' draws (symgpu_mp_commit_draws)
+  else if (has_entries) c->rng.skip(dd - c->dev_draws_seen); else c->rng.count += dd - c->dev_draws_seen;
   c->dev_draws_seen = dd;
   for (size_t i = 0; i < desc.size(); i++) { EntryLane* el = desc_lane[i];
     if (eres[i] & 1) el->pret_slot = -1;
@@ -936,7 +943,6 @@ extern "C" int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int
   if (!c || !node_part || world < 1 || rank < 0 || rank >= world) return SYMGPU_E_ARG;
   CK(cudaSetDevice(c->device));
   if (c->chgtvoie) { g_err = "partitioned runs do not support lane changing yet (global random stream)"; return SYMGPU_E_UNSUPPORTED; }
-  if (!c->entries.empty()) { g_err = "partitioned runs do not support origins yet (vehicle ids and the random sequence are global)"; return SYMGPU_E_UNSUPPORTED; }
   const FlatNet& f = c->net; const int L = f.n_lanes();
   auto& m = c->mp; m.on = true; m.rank = rank; m.world = world;
   m.lane_owner.resize(L);
@@ -1005,6 +1011,15 @@ extern "C" int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, doub
   for (int q = 0; q < m.world; q++) { send_counts[q] = m.h_mig_count[q]; out += m.h_mig_count[q]; if (m.h_mig_count[q] > cap_per_peer) { g_err = "migration buffer too small"; return SYMGPU_E_CAPACITY; } }
   c->n_alive -= out; m.free_count += out;
   return c->n_alive;
+}
+// origins in a partitioned run: the draws the device made this step (next-lane memo) are part of the one global random sequence;
+// the caller sums symgpu_mp_local_draws over the ranks and hands the total to every rank before the next step
+extern "C" int symgpu_mp_has_origins(symgpu_ctx* c) { return c ? (c->entries.empty() ? 0 : 1) : SYMGPU_E_ARG; }
+extern "C" long symgpu_mp_local_draws(symgpu_ctx* c) { return c && c->mp.on ? (long)c->mp.draw_delta : (long)SYMGPU_E_ARG; }
+extern "C" int symgpu_mp_commit_draws(symgpu_ctx* c, long total) {
+  if (!c || !c->mp.on || total < 0) return SYMGPU_E_ARG;
+  c->rng.skip((unsigned)total); c->mp.draw_delta = 0;
+  return SYMGPU_OK;
 }
 // vehicles arriving from other ranks (n_rows x 16 doubles in device memory) join the end of the local list
 extern "C" int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows) {

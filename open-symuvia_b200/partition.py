@@ -42,6 +42,10 @@ def bind_mp(L):
     L.symgpu_mp_step_front.argtypes = [vp, vp]
     L.symgpu_mp_step_back.argtypes = [vp, vp, vp, ci, vp]
     L.symgpu_mp_import.argtypes = [vp, vp, ci]
+    L.symgpu_mp_has_origins.argtypes = [vp]
+    L.symgpu_mp_local_draws.argtypes = [vp]
+    L.symgpu_mp_local_draws.restype = C.c_long
+    L.symgpu_mp_commit_draws.argtypes = [vp, C.c_long]
 
 
 class RankEngine:
@@ -68,6 +72,7 @@ class RankEngine:
         self.recv_rows = torch.zeros(world * cap_per_peer * ROW_D, dtype=torch.float64, device=dev)
         self.recv_regions = torch.zeros(world * cap_per_peer * ROW_D, dtype=torch.float64, device=dev)
         self.send_counts = np.zeros(world, np.int32)
+        self.has_origins = self.L.symgpu_mp_has_origins(self.e.h) == 1
 
     def front(self):
         self.e._chk(self.L.symgpu_mp_step_front(self.e.h, C.c_void_p(self.send_tails.data_ptr())))
@@ -75,6 +80,12 @@ class RankEngine:
     def back(self) -> int:
         return self.e._chk(self.L.symgpu_mp_step_back(self.e.h, C.c_void_p(self.recv_tails.data_ptr()), C.c_void_p(self.send_rows.data_ptr()),
                                                       self.cap, self.send_counts.ctypes.data_as(C.c_void_p)))
+
+    def local_draws(self) -> int:
+        return int(self.L.symgpu_mp_local_draws(self.e.h))
+
+    def commit_draws(self, total: int):
+        self.e._chk(self.L.symgpu_mp_commit_draws(self.e.h, int(total)))
 
     def import_rows(self, n_rows: int) -> int:
         return self.e._chk(self.L.symgpu_mp_import(self.e.h, C.c_void_p(self.recv_rows.data_ptr()), n_rows))
@@ -148,6 +159,10 @@ class DistributedRun:
         torch.cuda.synchronize()
         r.back()
         n = exchange_rows_fixed(dist, torch, r.send_rows, r.recv_regions, r.recv_rows, r.cap, self.rank, self.world)
+        if r.has_origins:                             # one global random sequence: the ranks' device draws of this step, summed
+            t = torch.tensor([r.local_draws()], dtype=torch.int64, device=r.send_rows.device)
+            dist.all_reduce(t)
+            r.commit_draws(int(t.item()))
         return r.import_rows(n)
 
 
@@ -178,6 +193,10 @@ class LocalGroup:
         torch.cuda.synchronize()
         for r in self.ranks:
             r.back()
+        if self.ranks[0].has_origins:
+            draws = sum(r.local_draws() for r in self.ranks)
+            for r in self.ranks:
+                r.commit_draws(draws)
         total = 0
         for dst in self.ranks:
             off = 0
@@ -200,6 +219,10 @@ class LocalGroup:
         return {k: v[order] for k, v in out.items()}
 
     def rng_count(self) -> int:
+        if self.ranks[0].has_origins:                 # every rank carries the whole sequence
+            counts = {r.e.rng_count for r in self.ranks}
+            assert len(counts) == 1, counts
+            return counts.pop()
         return sum(r.e.rng_count for r in self.ranks)
 
     def link_counts(self):

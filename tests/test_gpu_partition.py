@@ -62,3 +62,13 @@ def test_partition_of_one_is_the_plain_engine(pkg, synth, tmp_path):
         so, sg = o.state(), g.state()
         assert np.array_equal(so["id"], sg["id"]) and np.array_equal(so["pos"], sg["pos"]) and np.array_equal(so["lane"], sg["lane"])
     g.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_grid_with_origins(pkg, synth, tmp_path, world):
+    """Boundary demand (deterministic creation, queues at the origins, draws per created vehicle) in a partitioned run: every
+    rank replays all origins' draws and keeps the vehicles of its own entry lanes; the device draws are summed over the ranks."""
+    b = synth.grid(n=8, ny=4, n_steps=300, demand_per_lane=0.25, demand_duration=200, preseed_per_lane=4.0, shuffle=False)
+    migrated, loops_gpu, loops_oracle = _run(pkg, synth, tmp_path, b, world, 220)
+    assert migrated > 50
+    assert loops_gpu == loops_oracle
