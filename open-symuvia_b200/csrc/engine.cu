@@ -240,7 +240,8 @@ __device__ inline void copy_row(const DevVeh& V, int src, int dst) {
   V.ctx_leader[dst] = V.ctx_leader[src];
 }
 __global__ void k_entries(DevNet N, DevVeh V, DevLaneDyn LD, const EntryDesc* desc, int n_desc, int* result, double inst,
-                          unsigned* draws, int* overflow) {
+                          unsigned* draws, int* overflow, const int* guard) {
+  if (guard && *guard == 0) return;              // launched ahead of the convergence check (step_back): nothing to do yet
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_desc) return;
   EntryDesc d = desc[e];
@@ -267,7 +268,8 @@ __global__ void k_entries(DevNet N, DevVeh V, DevLaneDyn LD, const EntryDesc* de
 // Vehicule::FinCalculTrafic (vehicule.cpp:4254-4583) + Reseau::SupprimeVehicules (reseau.cpp:3984-4216)
 struct ExitRow { int slot, id; double inst; };
 __global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* entre, int* sorti, ExitRow* exited, int* n_exited,
-                        int* exit_winner, int* n_alive, int* err) {
+                        int* exit_winner, int* n_alive, int* err, const int* guard) {
+  if (guard && *guard == 0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int st = V.status[i];
@@ -297,7 +299,8 @@ __global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* ent
 // Sortie::VehiculeEnter + GetNextEnterInstant (sortie.cpp:60-130): the last vehicle of the list that left through
 // the lane sets the earliest exit instant of the next one.
 __global__ void k_exit_lanes(DevVeh V, const int* exit_lanes, const double* exit_cap, const int* exit_nl, int n_exit_lanes,
-                             int* exit_winner, double* next_sortie, double inst, double dt, double duree) {
+                             int* exit_winner, double* next_sortie, double inst, double dt, double duree, const int* guard) {
+  if (guard && *guard == 0) return;
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_exit_lanes) return;
   int ln = exit_lanes[e];
@@ -874,40 +877,62 @@ static int step_back(symgpu_ctx* c) {
       k_cyc_mark<<<Gu, B, 0, s>>>(c->dv, c->df, flip, by_id); LAUNCH(c);
       k_cyc_break<<<Gu, B, 0, s>>>(c->dv, c->df, c->rows.p, c->counters.p);
       KEND(c); }
-    // relaxation sweeps until one changes nothing (flow.cuh)
-    KBEGIN(c, KID_FOLLOW);
-    for (int sweep = 0;;) {
-      int* ch = c->f_ctl.p->changed;                                     // device address arithmetic only
-      if (sweep > 0) CK(cudaMemcpyAsync(ch, c->h_ctl_seed->changed, sizeof(int) * (kRelaxBatch + 1), cudaMemcpyHostToDevice, s));
-      const int nb = sweep == 0 ? c->relax_batch : kRelaxBatch;          // first batch: what the previous step needed, plus the sweep that proves it
-      for (int j = 0; j < nb; j++, sweep++) {
-        k_relax<<<(n_sorted + SYM_RELAX_THREADS - 1) / SYM_RELAX_THREADS, SYM_RELAX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, sweep == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
-      }
-      CK(cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s));
-      CK(cudaStreamSynchronize(s));
-      bool done = false;
-      int used = 0;
-      for (int j = 1; j <= nb && !done; j++) { used = j; if (c->h_ctl->changed[j] == 0) done = true; else c->passes++; }
-      if (done && sweep == nb) c->relax_batch = std::min(kRelaxBatch, std::max(2, used + 1)); else if (!done) c->relax_batch = kRelaxBatch;
-      if (done) break;
-      if (sweep > n_sorted + kRelaxBatch) { g_err = "relaxation does not terminate (leader loop left uncut)"; return SYMGPU_E_CUDA; }
     }
-    KEND0(c);
-    KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t); KEND(c);
-    }
-    if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
-                                                                    (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
-    CK(cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s));
-    KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6]); LAUNCH(c);
-    if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
-                                                                              c->next_sortie.p, c->t, c->P.dt, c->P.duree); }
-    KEND(c);
   }
-  CK(cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(c->h_stat + 7, c->draws.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  // relaxation sweeps until one changes nothing (flow.cuh), then placement / origins' queues / finalisation.  The first batch of
+  // sweeps is sized by what the previous step needed; the kernels after it are launched at once, guarded by the device-side
+  // verdict of that batch (k_relax_done), so the common case has ONE host synchronisation per step.  If the batch did not reach
+  // the fixed point the guarded kernels did nothing: more sweeps follow, then the same kernels unguarded.
   std::vector<int> eres(desc.size());
-  if (!desc.empty()) CK(cudaMemcpyAsync(eres.data(), c->eresult.p, desc.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  auto sweeps = [&](int nb, bool first) {
+    int* ch = c->f_ctl.p->changed;                                       // device address arithmetic only
+    if (!first) cudaMemcpyAsync(ch, c->h_ctl_seed->changed, sizeof(int) * (kRelaxBatch + 1), cudaMemcpyHostToDevice, s);
+    for (int j = 0; j < nb; j++) {
+      k_relax<<<(n_sorted + SYM_RELAX_THREADS - 1) / SYM_RELAX_THREADS, SYM_RELAX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, first && j == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
+    }
+    k_relax_done<<<1, 32, 0, s>>>(c->f_ctl.p, nb); LAUNCH(c);
+    cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s);
+  };
+  auto finish = [&](const int* guard) {
+    if (n > 0) {
+      if (n_sorted > 0) { KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t, guard); KEND(c); }
+      if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
+                                                                      (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW], guard); KEND(c); }
+      cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s);
+      KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6], guard); LAUNCH(c);
+      if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
+                                                                                c->next_sortie.p, c->t, c->P.dt, c->P.duree, guard); }
+      KEND(c);
+    }
+    cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(c->h_stat + 7, c->draws.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+    if (!desc.empty()) cudaMemcpyAsync(eres.data(), c->eresult.p, desc.size() * sizeof(int), cudaMemcpyDeviceToHost, s);
+  };
+  auto tally = [&](int nb, bool first_batch) -> bool {                   // counts the sweeps that changed something; true when one changed nothing
+    bool done = false; int used = 0;
+    for (int j = 1; j <= nb && !done; j++) { used = j; if (c->h_ctl->changed[j] == 0) done = true; else c->passes++; }
+    if (done && first_batch) c->relax_batch = std::min(kRelaxBatch, std::max(2, used + 1)); else if (!done) c->relax_batch = kRelaxBatch;
+    return done;
+  };
+  const bool relax = n > 0 && n_sorted > 0;
+  if (relax) {
+    const int nb = c->relax_batch;
+    KBEGIN(c, KID_FOLLOW); sweeps(nb, true); KEND0(c);
+    finish(&c->f_ctl.p->converged);
+    CK(cudaStreamSynchronize(s));
+    if (!tally(nb, true)) {
+      for (int sweep = nb;;) {
+        KBEGIN(c, KID_FOLLOW); sweeps(kRelaxBatch, false); KEND0(c);
+        CK(cudaStreamSynchronize(s));
+        sweep += kRelaxBatch;
+        if (tally(kRelaxBatch, false)) break;
+        if (sweep > n_sorted + kRelaxBatch) { g_err = "relaxation does not terminate (leader loop left uncut)"; return SYMGPU_E_CUDA; }
+      }
+      finish(nullptr);
+      CK(cudaStreamSynchronize(s));
+    }
+  } else { finish(nullptr); CK(cudaStreamSynchronize(s)); }
+  CK(cudaGetLastError());
   if (c->profile) prof_collect(c);
   if (c->h_stat[6]) { g_err = "internal error: vehicles left uncomputed"; return SYMGPU_E_CUDA; }
   c->n_alive = n > 0 ? c->h_stat[5] : 0;

@@ -28,7 +28,7 @@ namespace symb200 {
 
 constexpr int kRelaxBatch = 8;   // sweeps launched between two looks at the change counters
 
-struct FlowCtl { int n_segments, n_unres, pad1, pad2; int changed[kRelaxBatch + 1]; int pad3[3]; };
+struct FlowCtl { int n_segments, n_unres, converged, pad2; int changed[kRelaxBatch + 1]; int pad3[3]; };
 
 struct DevFlow {
   int *order, *posidx, *isfront, *seg_len, *seg_dep, *segpos, *minslot, *cut, *fronts, *ulist;
@@ -126,7 +126,14 @@ __global__ void __launch_bounds__(SYM_RELAX_THREADS, SYM_RELAX_BLOCKS) k_relax(D
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(changed, __popc(m));
 }
 // phase C for every vehicle of a lane (parallel)
-__global__ void k_place(DevNet N, DevVeh V, const double* rows, const double* b_goal, const int* b_flags, int n_sorted, double inst) {
+// verdict of a batch of sweeps: did one of them change nothing?
+__global__ void k_relax_done(FlowCtl* ctl, int nb) {
+  if (threadIdx.x || blockIdx.x) return;
+  int ok = 0; for (int j = 1; j <= nb; j++) if (ctl->changed[j] == 0) ok = 1;
+  ctl->converged = ok;
+}
+__global__ void k_place(DevNet N, DevVeh V, const double* rows, const double* b_goal, const int* b_flags, int n_sorted, double inst, const int* guard) {
+  if (guard && *guard == 0) return;              // launched ahead of the convergence check (engine.cu: step_back)
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
   phase_c(cP_ref(), N, V, rows, b_goal, b_flags, p, inst);
