@@ -416,6 +416,8 @@ struct HostEntry { int node, link; std::vector<std::pair<double, double>> demand
 
 template <class T> struct DBuf {
   T* p = nullptr; size_t n = 0;
+  DBuf() = default; DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { free(); }                               // every device buffer of a context goes with it (symgpu_destroy)
   cudaError_t alloc(size_t count) { n = count; if (!count) { p = nullptr; return cudaSuccess; } cudaError_t e = cudaMalloc(&p, count * sizeof(T)); if (e == cudaSuccess) e = cudaMemset(p, 0, count * sizeof(T)); return e; }
   cudaError_t upload(const std::vector<T>& h) { cudaError_t e = alloc(h.size()); if (e != cudaSuccess || h.empty()) return e; return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice); }
   void free() { if (p) cudaFree(p); p = nullptr; }
