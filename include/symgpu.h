@@ -63,6 +63,7 @@ int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, double* send_ro
 int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows);          /* rows of 16 doubles */
 /* Origins in a partitioned run: every rank replays the creation draws of all origins (same seed, same ids) and keeps the vehicles of
    the entry lanes it owns; the device's own draws of the step are summed over the ranks by the caller and committed on every rank. */
+int symgpu_set_stream(symgpu_ctx* c, void* cuda_stream);   /* run on the caller's stream (cudaStream_t), e.g. the one its collectives are ordered on */
 int symgpu_mp_has_origins(symgpu_ctx* c);
 long symgpu_mp_local_draws(symgpu_ctx* c);
 int symgpu_mp_commit_draws(symgpu_ctx* c, long total_over_ranks);

@@ -455,7 +455,7 @@ struct symgpu_ctx {
   DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
-  long long lane_changes = 0; int n_sms = 148; int relax_batch = kRelaxBatch;
+  long long lane_changes = 0; int n_sms = 148; int relax_batch = kRelaxBatch; bool ext_stream = false;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
@@ -660,7 +660,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   c->vl_used.free(); c->u_key.free(); c->s_key.free(); for (DBuf<int>* b : {&c->u_order, &c->u_id, &c->u_lane, &c->s_id, &c->s_lane}) b->free();
   if (c->h_stat) cudaFreeHost(c->h_stat);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream && !c->ext_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -1016,7 +1016,7 @@ extern "C" int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails) {
   if (c->mp.n_export) {
     if (c->ss.n == 0) CK(cudaMemsetAsync(c->lane_tail.p, 0xff, c->net.n_lanes() * sizeof(int), c->stream));
     k_mp_pack_tails<<<(c->mp.n_export + 255) / 256, 256, 0, c->stream>>>(c->dv, c->mp.d_export_lanes.p, c->mp.n_export, c->lane_tail.p, send_tails); LAUNCH(c); }
-  CK(cudaStreamSynchronize(c->stream));
+  if (!c->ext_stream) CK(cudaStreamSynchronize(c->stream));   // on the caller's stream the collective that follows is ordered after the pack
   return SYMGPU_OK;
 }
 // second half: `recv_tails` (n_halo x 4 doubles, peers in rank order) become ghost leaders; then the rest of the step; vehicles that
@@ -1041,6 +1041,16 @@ extern "C" int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, doub
 }
 // origins in a partitioned run: the draws the device made this step (next-lane memo) are part of the one global random sequence;
 // the caller sums symgpu_mp_local_draws over the ranks and hands the total to every rank before the next step
+// run on the caller's stream (e.g. torch's current stream, on which its NCCL collectives are ordered): the exchanges of a partitioned
+// step then need no host synchronisation between the engine's kernels and the collectives
+extern "C" int symgpu_set_stream(symgpu_ctx* c, void* stream) {
+  if (!c) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->stream && !c->ext_stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)stream; c->ext_stream = true;
+  return SYMGPU_OK;
+}
 extern "C" int symgpu_mp_has_origins(symgpu_ctx* c) { return c ? (c->entries.empty() ? 0 : 1) : SYMGPU_E_ARG; }
 extern "C" long symgpu_mp_local_draws(symgpu_ctx* c) { return c && c->mp.on ? (long)c->mp.draw_delta : (long)SYMGPU_E_ARG; }
 extern "C" int symgpu_mp_commit_draws(symgpu_ctx* c, long total) {

@@ -42,6 +42,7 @@ def bind_mp(L):
     L.symgpu_mp_step_front.argtypes = [vp, vp]
     L.symgpu_mp_step_back.argtypes = [vp, vp, vp, ci, vp]
     L.symgpu_mp_import.argtypes = [vp, vp, ci]
+    L.symgpu_set_stream.argtypes = [vp, vp]
     L.symgpu_mp_has_origins.argtypes = [vp]
     L.symgpu_mp_local_draws.argtypes = [vp]
     L.symgpu_mp_local_draws.restype = C.c_long
@@ -151,12 +152,13 @@ class DistributedRun:
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.r = RankEngine(pkg, flat_path, self.rank, self.world, node_part, device, cap_per_peer)
+        # the engine runs on torch's current stream: its kernels and the NCCL collectives are ordered on the device, no host sync between them
+        self.r.e._chk(self.r.L.symgpu_set_stream(self.r.e.h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
 
     def step(self) -> int:
         r, torch, dist = self.r, self.torch, self.dist
         r.front()
         exchange_tails_dist(dist, r.send_tails, r.recv_tails, r.export_cnt, r.halo_cnt)
-        torch.cuda.synchronize()
         r.back()
         n = exchange_rows_fixed(dist, torch, r.send_rows, r.recv_regions, r.recv_rows, r.cap, self.rank, self.world)
         if r.has_origins:                             # one global random sequence: the ranks' device draws of this step, summed
