@@ -140,14 +140,29 @@ __global__ void k_scan_add(int* out, const int* bsum, int n) {
   if (i < n) out[i] += bsum[blockIdx.x];
 }
 
-__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* uorder, double* ukey, int* uid, int* ulane) {
+__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* uorder, double* ukey, int* uid, int* ulane, int* cc_list, int* cc_cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int st = V.status[i];
-  if (st != ST_ALIVE && st != ST_NEW) return;
-  int ln = V.lane[i];
-  int slot = lane_start[ln] + atomicAdd(&lane_fill[ln], 1);
-  uorder[slot] = i; ukey[slot] = snap_pos(V.pos[i]); uid[slot] = V.id[i]; ulane[slot] = ln;     // the lane's slice, in arrival order, with its sort keys
+  bool stale = false;
+  if (i < n) {
+    int st = V.status[i];
+    if (st == ST_ALIVE || st == ST_NEW) {
+      int ln = V.lane[i]; int id = V.id[i];
+      int slot = lane_start[ln] + atomicAdd(&lane_fill[ln], 1);
+      uorder[slot] = i; ukey[slot] = snap_pos(V.pos[i]); uid[slot] = id; ulane[slot] = ln;     // the lane's slice, in arrival order, with its sort keys
+      if (cc_list) stale = V.cc_lane[i] != ln || V.cc_id[i] != id;                               // changed lane (or a new vehicle in the slot): its context memo is rebuilt
+    }
+  }
+  if (cc_list) {                                                                                 // list of the stale vehicles, one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, stale);
+    if (m) { const int lane = threadIdx.x & 31; int base = 0;
+      if (lane == 0) base = atomicAdd(cc_cnt, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (stale) cc_list[base + __popc(m & ((1u << lane) - 1))] = i; }
+  }
+}
+__global__ void k_ctx_fill(DevNet N, DevVeh V, const int* cc_list, const int* cc_cnt) {
+  const int cnt = *cc_cnt;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) ctx_cache_fill(N, V, cc_list[t]);
 }
 
 // in-lane order by (start-of-step position, id) + own-lane leader links + lane tail.
@@ -447,6 +462,7 @@ struct symgpu_ctx {
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
+  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
@@ -474,7 +490,7 @@ static void fill_dev_structs(symgpu_ctx* c) {
   n.sl_col = c->sl_col.p; n.sl_prop = c->sl_prop.p; n.n_lanes = c->net.n_lanes(); n.n_links = c->net.n_links(); n.n_sl = c->net.n_sl();
   DevVeh& v = c->dv;
   v.status = c->v_status.p; v.id = c->v_id.p; v.cls = c->v_cls.p; v.route = c->v_route.p; v.route_pos = c->v_rpos.p; v.lane = c->v_lane.p;
-  v.vdes = c->v_vdes.p; n.link_down = c->link_down.p;
+  v.vdes = c->v_vdes.p; n.link_down = c->link_down.p; v.cc_lane = c->cc_lane.p; v.cc_id = c->cc_id.p; v.cc = c->cc.p;
   v.lane_n = c->v_lane_n.p; v.prev_leader = c->v_pl.p; v.flags = c->v_flags.p; v.oflags = c->v_oflags.p; v.memo = c->v_memo.p;
   v.pos = c->v_pos.p; v.vit = c->v_vit.p; v.acc = c->v_acc.p; v.pos_n = c->v_pos_n.p; v.vit_n = c->v_vit_n.p; v.acc_n = c->v_acc_n.p;
   v.dn = c->v_dn.p; v.cpos = c->v_cpos.p; v.tcre = c->v_tcre.p; v.dstp = c->v_dstp.p; v.hent = c->v_hent.p; v.tsort = c->v_tsort.p;
@@ -618,6 +634,9 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
                        &c->v_computed, &c->v_ctx_nl, &c->v_ctx_leader, &c->v_ctx_flags}) CK(b->alloc(cap));
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
+  { const char* e = getenv("SYMGPU_CTXCACHE"); c->use_cc = !(e && !strcmp(e, "0")); }                    // SYMGPU_CTXCACHE=0: every vehicle walks the tables every step (cross-check)
+  if (c->use_cc) { CK(c->cc_lane.alloc(cap)); CK(cudaMemset(c->cc_lane.p, 0xff, cap * sizeof(int))); CK(c->cc_id.alloc(cap)); CK(cudaMemset(c->cc_id.p, 0xff, cap * sizeof(int)));
+    CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); }
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
@@ -815,7 +834,8 @@ static int step_front(symgpu_ctx* c) {
     KBEGIN(c, KID_SCAN); k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
-    KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); KEND(c);
+    KBEGIN(c, KID_SCATTER); if (c->use_cc) CK(cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s));
+    k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->cc_list.p, c->cc_cnt.p); KEND(c);
     KBEGIN(c, KID_SORT); CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
       if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
         k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } KEND(c);
@@ -843,7 +863,8 @@ static int step_front(symgpu_ctx* c) {
       int nb = (L + kScanB - 1) / kScanB;
       k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
       if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); LAUNCH(c); }
-      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); LAUNCH(c);
+      if (c->use_cc) CK(cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s));
+      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
       CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
       if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
         k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } LAUNCH(c);
@@ -863,7 +884,9 @@ static int step_back(symgpu_ctx* c) {
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
   if (n > 0) {
-    if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT); k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
+    if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
+      if (c->use_cc) { k_ctx_fill<<<std::min(G(n_sorted), c->n_sms * 8), B, 0, s>>>(c->dn, c->dv, c->cc_list.p, c->cc_cnt.p); LAUNCH(c); }
+      k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));

@@ -73,7 +73,7 @@ __global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, c
 
 // one relaxation sweep.  first: every vehicle, and the dependency (order position -> leader slot, -1 = none / cut / ghost)
 // is cached; later sweeps only look at the leader's speed again.  `prev` = changes counted by the sweep before.
-// Leaders are mostly the neighbour in the lane order, i.e. in the same thread block: the block repeats its part until
+// Leaders are mostly the neighbour in the lane order, i.e. in the same warp: every warp repeats its part until
 // nothing in it changes (kLocalIters at most), so a global sweep carries a change down whole segments, not one vehicle.
 constexpr int kLocalIters = 48;
 #ifndef SYM_RELAX_BLOCKS
@@ -117,7 +117,11 @@ __global__ void __launch_bounds__(SYM_RELAX_THREADS, SYM_RELAX_BLOCKS) k_relax(D
       if (__double_as_longlong(v0) != __double_as_longlong(V.vit_n[x])) { V.vit_n[x] = v0; ch = true; }
     }
     nch += ch;
-    if (!__syncthreads_or(ch) || it == kLocalIters) break;
+#ifdef SYM_RELAX_BLOCKLOOP
+    if (!__syncthreads_or(ch) || it == kLocalIters) break;             // whole block in step (C4: relax 0.316 ms)
+#else
+    if (!__any_sync(0xffffffffu, ch) || it == kLocalIters) break;     // every warp on its own: no barrier, other warps' changes arrive through L2 (0.293 ms)
+#endif
     need = false;
     if (dep >= 0) { vL = __ldcg(&V.vit_n[dep]); need = __double_as_longlong(vL) != __double_as_longlong(vl_last); }
   }

@@ -40,7 +40,24 @@ struct DevNet {
   int n_lanes, n_links, n_sl;
 };
 
+// Per-vehicle memo of the table walks of phase A that only depend on (vehicle, lane): the next lanes of the itinerary from the
+// vehicle's lane (Vehicule::CalculNextVoie applied 4 times, with the lane whose draw each application consults), which of them
+// are junction-internal, and for the first three context lanes THE stop line of the vehicle's movement (CalculTraficFeux,
+// vehicule.cpp:1829-1883: upstream lane and downstream lane both match).  Valid while the vehicle stays on `lane`; rebuilt by
+// k_ctx_fill for the vehicles that changed lane (a few per cent per step), so k_context walks no table for the others.
+struct CtxCache {
+  int lane, id;          // key
+  int chain[4];          // chain[h] = CalculNextVoie^(h+1)(lane), -1 from the first failure on
+  int tl[4];             // lane whose memoised draw hop h consults (-1 none)
+  int slm[3];            // context lane k: first stop line matching the movement, -1 none, -2 downstream lane beyond the memo
+  int bits;              // bit k (k=1,2): lane k has a stop line of its upstream lane at pos >= 0; bit 8+h: chain[h] is internal;
+                         // bit 16+k: more than one matching stop line on lane k
+  double slu0;           // lane 0: largest position of a stop line of its upstream lane (-DBL_MAX none)
+};
+static_assert(sizeof(CtxCache) == 64, "CtxCache is one 64-byte record");
+
 struct DevVeh {
+  int *cc_lane, *cc_id; CtxCache* cc;     // cc_lane / cc_id: the cache key again, struct-of-arrays, for the staleness test of k_scatter
   int *status, *id, *cls, *route, *route_pos, *lane, *lane_n, *prev_leader, *flags, *oflags, *memo, *vdes;
   double *pos, *vit, *acc, *pos_n, *vit_n, *acc_n, *dn, *cpos, *tcre, *dstp, *hent, *tsort;
   // per-step scratch
@@ -134,7 +151,39 @@ __device__ inline int memo_touch(int* memo, int lane) {
 // Returns the number of random draws consumed.
 __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, double* rows, int p, int i,
                                  const int* lanes, int nl, int L, double gap, double dn0, double dfree, bool created, double start,
-                                 double cpos, double dtv);
+                                 double cpos, double dtv, const int* slm);
+
+// rebuilds the memo of vehicle i (k_ctx_fill)
+__device__ inline void ctx_cache_fill(const DevNet& n, const DevVeh& V, int i) {
+  CtxCache c;
+  const int lane = V.lane[i], route = V.route[i], rpos = V.route_pos[i];
+  c.lane = lane; c.id = V.id[i]; c.bits = 0; c.slu0 = -DBL_MAX;
+  int cur = lane;
+  for (int h = 0; h < 4; h++) {
+    int nx = -1, tl = -1;
+    if (cur >= 0) nx = next_voie(n, route, rpos, cur, &tl);
+    c.chain[h] = nx; c.tl[h] = tl;
+    if (nx >= 0 && n.link_brick[n.lane_link[nx]] >= 0) c.bits |= 1 << (8 + h);
+    cur = nx;
+  }
+  for (int k = 0; k < 3; k++) {
+    const int ln = k == 0 ? lane : c.chain[k - 1];
+    c.slm[k] = -1;
+    if (ln < 0) continue;
+    const int am = n.link_brick[n.lane_link[ln]] >= 0 ? n.lane_prev[ln] : ln;
+    int aval = -1; bool unknown = false;               // first lane after k that is not junction-internal (vehicule.cpp:1854-1874)
+    { int q = k; for (; q < 4; q++) { if (c.chain[q] < 0) break; if (!((c.bits >> (8 + q)) & 1)) { aval = c.chain[q]; break; } } unknown = q == 4; }
+    int nmatch = 0;
+    for (int s = n.sl_off[ln]; s < n.sl_off[ln + 1]; s++) {
+      if (!(am >= 0 && n.sl_i[6 * s + 1] == n.lane_link[am] && n.sl_i[6 * s + 2] == n.lane_num[am])) continue;
+      if (k == 0) c.slu0 = fmax(c.slu0, n.sl_pos[s]); else if (n.sl_pos[s] >= 0.0) c.bits |= 1 << k;
+      if (unknown) { c.slm[k] = -2; continue; }
+      if (aval >= 0 && n.sl_i[6 * s + 3] == n.lane_link[aval] && n.sl_i[6 * s + 4] == n.lane_num[aval]) { if (nmatch == 0) c.slm[k] = s; nmatch++; }
+    }
+    if (nmatch > 1) c.bits |= 1 << (16 + k);
+  }
+  V.cc[i] = c; V.cc_lane[i] = lane; V.cc_id[i] = c.id;
+}
 // rows != nullptr: also pack the vehicle's phase-B row at order position p (rows.cuh); the per-vehicle ctx_* arrays are
 // then only written for contexts the row cannot hold (general path).
 __device__ inline int context_one(const DevParams& P, const DevNet& n, const DevVeh& V, const int* lane_tail, int i,
@@ -154,6 +203,43 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
   int lane = V.lane[i];
   lanes[0] = lane;
   double start = p1 + cpos;
+  int slm[3] = {-1, -1, -1}; bool fast = false;
+  if (rows && V.cc) {                                                     // same hops, same memo touches, read from the vehicle's memo (CtxCache)
+    const CtxCache cc = V.cc[i];
+    if (cc.lane == lane && cc.id == V.id[i]) {
+      int m[kMemo]; for (int k = 0; k < kMemo; k++) m[k] = memo[k];
+      int d = 0, h = 0; bool ok = true;
+      double dist = len_ex(P, n, lane) - start;
+      while (dist < range) {
+        if (h > 3) { ok = false; break; }
+        const int nx = cc.chain[h], tl = cc.tl[h]; h++;
+        if (tl >= 0) d += memo_touch(m, tl);
+        if (nx < 0) break;
+        if (nl == 3) { ok = false; break; }                               // longer contexts take the general path
+        lanes[nl++] = nx; dist += len_ex(P, n, nx);
+      }
+      for (int k = 0; k < nl && ok; k++) {
+        const bool need = k == 0 ? cc.slu0 >= start : (cc.bits >> k) & 1;
+        if (need) {
+          bool found = false;
+          for (int q = k + 1; q < nl; q++) if (!((cc.bits >> (8 + q - 1)) & 1)) found = true;
+          for (int hh = nl - 1; !found; hh++) {
+            if (hh > 3) { ok = false; break; }
+            const int av = cc.chain[hh], tl = cc.tl[hh];
+            if (tl >= 0) d += memo_touch(m, tl);
+            if (!(av >= 0 && ((cc.bits >> (8 + hh)) & 1))) break;
+          }
+        }
+        int s = cc.slm[k];
+        if (s == -2) ok = false;
+        else if (s >= 0 && !(n.sl_pos[s] >= (k == 0 ? start : 0.0))) { if ((cc.bits >> (16 + k)) & 1) ok = false; else s = -1; }
+        slm[k] = s;
+      }
+      if (ok) { fast = true; draws = d; for (int k = 0; k < kMemo; k++) memo[k] = m[k]; }
+      else nl = 1;
+    }
+  }
+  if (!fast) {
   double dist = len_ex(P, n, lane) - start;                               // CarFollowingContext.cpp:118
   while (dist < range) {                                                  // :121-125
     int tl; int nx = next_voie(n, route, rpos, lane, &tl);
@@ -161,6 +247,7 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
     if (nx < 0) break;
     if (nl == kMaxCtx) { atomicAdd(overflow, 1); break; }
     lanes[nl++] = nx; dist += len_ex(P, n, nx); lane = nx;
+  }
   }
   // leader: SearchLeaders :128-170 (stops at the first vehicle met, accepted or not)
   int leader = -1; double gap = 0;
@@ -178,7 +265,7 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
   }
   // stop-line bookkeeping: CalculTraficFeux resolves the downstream lane of the movement with CalculNextVoie,
   // which may consume the memoised draw of a lane beyond the context (vehicule.cpp:1854-1874)
-  for (int k = 0; k < nl; k++) {
+  for (int k = 0; k < nl && !fast; k++) {
     int ln = lanes[k];
     double s0 = k == 0 ? start : 0.0;
     bool need = false;
@@ -232,7 +319,7 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
     V.ctx_gap[i] = gap; V.ctx_dn0[i] = dn0; V.ctx_dfree[i] = dfree;
     V.ctx_flags[i] = created ? 1 : 0;
   }
-  if (rows) build_row(P, n, V, *LD, rows, p, i, lanes, nl, leader, gap, dn0, dfree, created, start, cpos, dtv);
+  if (rows) build_row(P, n, V, *LD, rows, p, i, lanes, nl, leader, gap, dn0, dfree, created, start, cpos, dtv, fast ? slm : nullptr);
   return draws;
 }
 

@@ -48,7 +48,7 @@ __device__ __forceinline__ int hi32(double d) { return __double2hiint(d); }
 // phase A tail: called by k_context once lanes / leader / gap / dn0 / dfree are known for vehicle i at order position p.
 __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, double* rows, int p, int i,
                                  const int* lanes, int nl, int L, double gap, double dn0, double dfree, bool created, double start,
-                                 double cpos, double dtv) {
+                                 double cpos, double dtv, const int* slm) {
   const Row r = row_at(rows, p);
   const DevCls& c = P.cls[V.cls[i]];
   const double v1 = V.vit[i];
@@ -118,8 +118,12 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
     int fl = 0; double pf = -1, prop = 0, ts = 0;
     if ((n.lane_flags[ln] & 1) || ((k == nl - 1) && ta != 'S' && ta != 'P')) fl |= RF_STOPEND;        // vehicule.cpp:1607-1608
     if (ta == 'S' || ta == 'P') { fl |= RF_EXIT; ts = LD.next_sortie[ln]; }                          // :1636-1642
+    if (slm) {                                                                                        // the movement's stop line from the vehicle's memo (CtxCache)
+      const int s = slm[k];
+      if (s >= 0) { fl |= RF_SL | (n.sl_col[s] << RF_COLSHIFT); pf = n.sl_pos[s]; prop = n.sl_prop[s]; }
+    }
     int aval = -2;                                                                                    // CalculTraficFeux :1829-1883
-    for (int s = n.sl_off[ln]; s < n.sl_off[ln + 1]; s++) {
+    for (int s = slm ? n.sl_off[ln + 1] : n.sl_off[ln]; s < n.sl_off[ln + 1]; s++) {
       double f = n.sl_pos[s];
       if (f >= sp) {
         int am = n.link_brick[link] >= 0 ? n.lane_prev[ln] : ln;
