@@ -140,26 +140,17 @@ __global__ void k_scan_add(int* out, const int* bsum, int n) {
   if (i < n) out[i] += bsum[blockIdx.x];
 }
 
-__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* uorder, double* ukey, int* uid, int* ulane, int* cc_list, int* cc_cnt) {
+__global__ void k_scatter(DevVeh V, int n, const int* lane_start, int* lane_fill, int* uorder, double* ukey, int* uid, int* ulane) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool stale = false;
-  if (i < n) {
-    int st = V.status[i];
-    if (st == ST_ALIVE || st == ST_NEW) {
-      int ln = V.lane[i]; int id = V.id[i];
-      int slot = lane_start[ln] + atomicAdd(&lane_fill[ln], 1);
-      uorder[slot] = i; ukey[slot] = snap_pos(V.pos[i]); uid[slot] = id; ulane[slot] = ln;     // the lane's slice, in arrival order, with its sort keys
-      if (cc_list) stale = V.cc_lane[i] != ln || V.cc_id[i] != id;                               // changed lane (or a new vehicle in the slot): its context memo is rebuilt
-    }
-  }
-  if (cc_list) {                                                                                 // list of the stale vehicles, one atomic per warp
-    const unsigned m = __ballot_sync(0xffffffffu, stale);
-    if (m) { const int lane = threadIdx.x & 31; int base = 0;
-      if (lane == 0) base = atomicAdd(cc_cnt, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (stale) cc_list[base + __popc(m & ((1u << lane) - 1))] = i; }
-  }
+  if (i >= n) return;
+  int st = V.status[i];
+  if (st != ST_ALIVE && st != ST_NEW) return;
+  int ln = V.lane[i];
+  int slot = lane_start[ln] + atomicAdd(&lane_fill[ln], 1);
+  uorder[slot] = i; ukey[slot] = snap_pos(V.pos[i]); uid[slot] = V.id[i]; ulane[slot] = ln;     // the lane's slice, in arrival order, with its sort keys
 }
+// context memos (micro.cuh: CtxCache) of the vehicles k_final listed (they changed lane or are new): runs on a side stream beside the
+// first kernels of the next step
 __global__ void k_ctx_fill(DevNet N, DevVeh V, const int* cc_list, const int* cc_cnt) {
   const int cnt = *cc_cnt;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt; t += gridDim.x * blockDim.x) ctx_cache_fill(N, V, cc_list[t]);
@@ -283,13 +274,14 @@ __global__ void k_entries(DevNet N, DevVeh V, DevLaneDyn LD, const EntryDesc* de
 // Vehicule::FinCalculTrafic (vehicule.cpp:4254-4583) + Reseau::SupprimeVehicules (reseau.cpp:3984-4216)
 struct ExitRow { int slot, id; double inst; };
 __global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* entre, int* sorti, ExitRow* exited, int* n_exited,
-                        int* exit_winner, int* n_alive, int* err, const int* guard) {
+                        int* exit_winner, int* n_alive, int* err, const int* guard, int* cc_list, int* cc_cnt) {
   if (guard && *guard == 0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int st = V.status[i];
-  if (st != ST_ALIVE && st != ST_NEW) return;
-  if (!V.computed[i]) { atomicAdd(err, 1); return; }
+  bool stale = false;
+  int st = i < n ? V.status[i] : ST_DEAD;
+  if (st == ST_ALIVE || st == ST_NEW) {
+  if (!V.computed[i]) atomicAdd(err, 1);
+  else {
   int of = V.oflags[i];
   int lane1 = V.lane[i], lane0 = V.lane_n[i];
   int link1 = (of & O_LINK1NULL) ? -1 : N.lane_link[lane1];
@@ -309,6 +301,18 @@ __global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* ent
   } else {
     V.status[i] = ST_ALIVE;
     atomicAdd(n_alive, 1);
+    if (cc_list) { int id = V.id[i];                                                       // the vehicle's context memo is for another lane (or another vehicle):
+      stale = V.cc_lane[i] != lane0 || V.cc_id[i] != id;                                   // listed for k_ctx_fill, key set now so that it is listed once
+      if (stale) { V.cc_lane[i] = lane0; V.cc_id[i] = id; } }
+  }
+  }
+  }
+  if (cc_list) {                                                                           // one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, stale);
+    if (m) { const int lane = threadIdx.x & 31; int base = 0;
+      if (lane == 0) base = atomicAdd(cc_cnt, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (stale) cc_list[base + __popc(m & ((1u << lane) - 1))] = i; }
   }
 }
 // Sortie::VehiculeEnter + GetNextEnterInstant (sortie.cpp:60-130): the last vehicle of the list that left through
@@ -462,7 +466,7 @@ struct symgpu_ctx {
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
-  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
+  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_pending = false, dbg_sync = false, dbg_failed = false; cudaStream_t aux = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
@@ -634,9 +638,11 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
                        &c->v_computed, &c->v_ctx_nl, &c->v_ctx_leader, &c->v_ctx_flags}) CK(b->alloc(cap));
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
+  { const char* e = getenv("SYMGPU_DEBUG_SYNC"); c->dbg_sync = e && !strcmp(e, "1"); }
   { const char* e = getenv("SYMGPU_CTXCACHE"); c->use_cc = !(e && !strcmp(e, "0")); }                    // SYMGPU_CTXCACHE=0: every vehicle walks the tables every step (cross-check)
   if (c->use_cc) { CK(c->cc_lane.alloc(cap)); CK(cudaMemset(c->cc_lane.p, 0xff, cap * sizeof(int))); CK(c->cc_id.alloc(cap)); CK(cudaMemset(c->cc_id.p, 0xff, cap * sizeof(int)));
-    CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); }
+    CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); CK(cudaMemset(c->cc.p, 0xff, cap * sizeof(CtxCache)));   // key (-1, -1): matches no vehicle
+    CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->cc_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->cc_done, cudaEventDisableTiming)); }
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
@@ -672,6 +678,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
   for (int k = 0; k < 2; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
   c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
+  if (c->aux) cudaStreamDestroy(c->aux); if (c->cc_go) cudaEventDestroy(c->cc_go); if (c->cc_done) cudaEventDestroy(c->cc_done);
   if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); for (int k = 0; k < 2; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
@@ -768,7 +775,8 @@ static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan"
                                               "k_cyc_loops", "k_place", "k_entries", "k_final"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
-#define LAUNCH(c) ((c)->launches++)
+static void dbg_sync(symgpu_ctx* c, int line);
+#define LAUNCH(c) do { (c)->launches++; if ((c)->dbg_sync) dbg_sync(c, __LINE__); } while (0)
 #define KBEGIN(c, kid) do { if ((c)->profile) prof_begin(c, kid); } while (0)
 #define KEND(c) do { LAUNCH(c); if ((c)->profile) prof_end(c); } while (0)
 #define KEND0(c) do { if ((c)->profile) prof_end(c); } while (0)
@@ -786,6 +794,11 @@ static void prof_collect(symgpu_ctx* c) {
 
 // first half of a step: origins (host), signals, lane membership and in-lane order.  In a partitioned run the tails of
 // the boundary lanes are exchanged between the two halves.
+// SYMGPU_DEBUG_SYNC=1: wait for the device after every launch and name the line of the first one that failed (bring-up aid)
+static void dbg_sync(symgpu_ctx* c, int line) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess && !c->dbg_failed) { c->dbg_failed = true; fprintf(stderr, "symgpu: launch before engine.cu:%d failed: %s\n", line, cudaGetErrorString(e)); }
+}
 static int step_front(symgpu_ctx* c) {
   const int L = c->net.n_lanes();
   cudaStream_t s = c->stream;
@@ -825,6 +838,14 @@ static int step_front(symgpu_ctx* c) {
   const int n_sorted = c->n_alive + (int)new_rows.size();   // vehicles that are members of a lane this step
   const int B = 256;
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
+  // context memos of the vehicles the last step listed: on a side stream, beside this step's lane ordering; k_context waits for them
+  // (before the lane-change phase when there is one: it moves vehicles to other lanes)
+  if (c->use_cc && c->cc_pending) {
+    CK(cudaEventRecord(c->cc_go, s)); CK(cudaStreamWaitEvent(c->aux, c->cc_go, 0));
+    k_ctx_fill<<<c->n_sms * 16, 64, 0, c->aux>>>(c->dn, c->dv, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
+    CK(cudaEventRecord(c->cc_done, c->aux));
+    if (c->chgtvoie) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->cc_pending = false; }
+  }
   CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
   CK(cudaMemsetAsync(c->stat.p, 0, 16 * sizeof(int), s));
   if (c->net.n_sl()) { KBEGIN(c, KID_SIGNALS); k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); KEND(c); }
@@ -834,8 +855,7 @@ static int step_front(symgpu_ctx* c) {
     KBEGIN(c, KID_SCAN); k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
-    KBEGIN(c, KID_SCATTER); if (c->use_cc) CK(cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s));
-    k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->cc_list.p, c->cc_cnt.p); KEND(c);
+    KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); KEND(c);
     KBEGIN(c, KID_SORT); CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
       if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
         k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } KEND(c);
@@ -863,8 +883,7 @@ static int step_front(symgpu_ctx* c) {
       int nb = (L + kScanB - 1) / kScanB;
       k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
       if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); LAUNCH(c); }
-      if (c->use_cc) CK(cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s));
-      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
+      k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); LAUNCH(c);
       CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
       if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
         k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } LAUNCH(c);
@@ -883,9 +902,9 @@ static int step_back(symgpu_ctx* c) {
   const int B = 256;
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
+  if (c->use_cc && c->cc_pending) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->cc_pending = false; }
   if (n > 0) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
-      if (c->use_cc) { k_ctx_fill<<<std::min(G(n_sorted), c->n_sms * 8), B, 0, s>>>(c->dn, c->dv, c->cc_list.p, c->cc_cnt.p); LAUNCH(c); }
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
@@ -923,8 +942,8 @@ static int step_back(symgpu_ctx* c) {
       if (n_sorted > 0) { KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t, guard); KEND(c); }
       if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
                                                                       (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW], guard); KEND(c); }
-      cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s);
-      KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6], guard); LAUNCH(c);
+      cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s); if (c->use_cc) cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s);
+      KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6], guard, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
       if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
                                                                                 c->next_sortie.p, c->t, c->P.dt, c->P.duree, guard); }
       KEND(c);
@@ -960,7 +979,7 @@ static int step_back(symgpu_ctx* c) {
   CK(cudaGetLastError());
   if (c->profile) prof_collect(c);
   if (c->h_stat[6]) { g_err = "internal error: vehicles left uncomputed"; return SYMGPU_E_CUDA; }
-  c->n_alive = n > 0 ? c->h_stat[5] : 0;
+  c->n_alive = n > 0 ? c->h_stat[5] : 0; c->cc_pending = c->use_cc && n > 0;
   c->veh_steps += c->n_alive;
   int nex = n > 0 ? c->h_stat[4] : 0;
   c->last_exited.resize(nex);
