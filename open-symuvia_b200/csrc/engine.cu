@@ -466,7 +466,7 @@ struct symgpu_ctx {
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
-  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_pending = false, dbg_sync = false, dbg_failed = false; cudaStream_t aux = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
+  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_fill = false /* k_final listed vehicles for k_ctx_fill */, aux_wait = false /* the step has work on the side stream */, dbg_sync = false, dbg_failed = false, coop_loops = true; cudaStream_t aux = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
@@ -638,11 +638,12 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   for (DBuf<int>* b : {&c->v_status, &c->v_id, &c->v_cls, &c->v_route, &c->v_rpos, &c->v_lane, &c->v_lane_n, &c->v_pl, &c->v_flags, &c->v_oflags, &c->v_ahead,
                        &c->v_computed, &c->v_ctx_nl, &c->v_ctx_leader, &c->v_ctx_flags}) CK(b->alloc(cap));
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
+  { const char* e = getenv("SYMGPU_COOP_LOOPS"); int co = 0; cudaDeviceGetAttribute(&co, cudaDevAttrCooperativeLaunch, device); c->coop_loops = co && !(e && !strcmp(e, "0")); }
   { const char* e = getenv("SYMGPU_DEBUG_SYNC"); c->dbg_sync = e && !strcmp(e, "1"); }
   { const char* e = getenv("SYMGPU_CTXCACHE"); c->use_cc = !(e && !strcmp(e, "0")); }                    // SYMGPU_CTXCACHE=0: every vehicle walks the tables every step (cross-check)
   if (c->use_cc) { CK(c->cc_lane.alloc(cap)); CK(cudaMemset(c->cc_lane.p, 0xff, cap * sizeof(int))); CK(c->cc_id.alloc(cap)); CK(cudaMemset(c->cc_id.p, 0xff, cap * sizeof(int)));
-    CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); CK(cudaMemset(c->cc.p, 0xff, cap * sizeof(CtxCache)));   // key (-1, -1): matches no vehicle
-    CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->cc_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->cc_done, cudaEventDisableTiming)); }
+    CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); CK(cudaMemset(c->cc.p, 0xff, cap * sizeof(CtxCache))); }   // key (-1, -1): matches no vehicle
+  CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->cc_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->cc_done, cudaEventDisableTiming));
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
@@ -838,17 +839,19 @@ static int step_front(symgpu_ctx* c) {
   const int n_sorted = c->n_alive + (int)new_rows.size();   // vehicles that are members of a lane this step
   const int B = 256;
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
-  // context memos of the vehicles the last step listed: on a side stream, beside this step's lane ordering; k_context waits for them
-  // (before the lane-change phase when there is one: it moves vehicles to other lanes)
-  if (c->use_cc && c->cc_pending) {
+  // side stream, beside this step's lane ordering: the signal states of the step (read from k_context on) and the context memos
+  // of the vehicles the last step listed; step_back waits for both (the lane-change phase too: it moves vehicles to other lanes)
+  const bool side_sig = c->net.n_sl() > 0 && !c->profile;                 // per-kernel timing (profile) keeps everything on one stream
+  if (side_sig || c->cc_fill) {
     CK(cudaEventRecord(c->cc_go, s)); CK(cudaStreamWaitEvent(c->aux, c->cc_go, 0));
-    k_ctx_fill<<<c->n_sms * 16, 64, 0, c->aux>>>(c->dn, c->dv, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
-    CK(cudaEventRecord(c->cc_done, c->aux));
-    if (c->chgtvoie) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->cc_pending = false; }
+    if (side_sig) { k_signals<<<G(c->net.n_sl()), B, 0, c->aux>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); LAUNCH(c); }
+    if (c->cc_fill) { k_ctx_fill<<<c->n_sms * 16, 64, 0, c->aux>>>(c->dn, c->dv, c->cc_list.p, c->cc_cnt.p); LAUNCH(c); c->cc_fill = false; }
+    CK(cudaEventRecord(c->cc_done, c->aux)); c->aux_wait = true;
+    if (c->chgtvoie) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->aux_wait = false; }
   }
   CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
   CK(cudaMemsetAsync(c->stat.p, 0, 16 * sizeof(int), s));
-  if (c->net.n_sl()) { KBEGIN(c, KID_SIGNALS); k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); KEND(c); }
+  if (c->net.n_sl() && !side_sig) { KBEGIN(c, KID_SIGNALS); k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); KEND(c); }
   if (n > 0) {
     KBEGIN(c, KID_PREPARE); k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); KEND(c);
     int nb = (L + kScanB - 1) / kScanB;
@@ -902,7 +905,7 @@ static int step_back(symgpu_ctx* c) {
   const int B = 256;
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
-  if (c->use_cc && c->cc_pending) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->cc_pending = false; }
+  if (c->aux_wait) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->aux_wait = false; }
   if (n > 0) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
@@ -916,10 +919,16 @@ static int step_back(symgpu_ctx* c) {
       const int Gs = std::min(G(n_sorted), c->n_sms * 8), Gu = std::min(G(n_sorted), c->n_sms);
       KBEGIN(c, KID_LOOP);
       k_cyc_walk<<<Gs, B, 0, s>>>(c->df); LAUNCH(c);
+      if (c->coop_loops) {                                                  // jump rounds + mark + cut in one cooperative launch
+        DevVeh dv = c->dv; DevFlow df = c->df; double* rp = c->rows.p; long long* cp = c->counters.p; int kl = Klev, bi = by_id;
+        void* args[] = {&dv, &df, &rp, &cp, &kl, &bi};
+        CK(cudaLaunchCooperativeKernel((void*)k_cyc_rest, dim3(c->n_sms), dim3(256), args, 0, s)); LAUNCH(c);
+      } else {
       int flip = 0;
       for (int k = 0; k < Klev; k++) { k_cyc_jump<<<Gu, B, 0, s>>>(c->df, flip); LAUNCH(c); flip ^= 1; }
       k_cyc_mark<<<Gu, B, 0, s>>>(c->dv, c->df, flip, by_id); LAUNCH(c);
       k_cyc_break<<<Gu, B, 0, s>>>(c->dv, c->df, c->rows.p, c->counters.p);
+      }
       KEND(c); }
     }
   }
@@ -979,7 +988,7 @@ static int step_back(symgpu_ctx* c) {
   CK(cudaGetLastError());
   if (c->profile) prof_collect(c);
   if (c->h_stat[6]) { g_err = "internal error: vehicles left uncomputed"; return SYMGPU_E_CUDA; }
-  c->n_alive = n > 0 ? c->h_stat[5] : 0; c->cc_pending = c->use_cc && n > 0;
+  c->n_alive = n > 0 ? c->h_stat[5] : 0; c->cc_fill = c->use_cc && n > 0;
   c->veh_steps += c->n_alive;
   int nex = n > 0 ? c->h_stat[4] : 0;
   c->last_exited.resize(nex);

@@ -28,7 +28,7 @@ namespace symb200 {
 
 constexpr int kRelaxBatch = 8;   // sweeps launched between two looks at the change counters
 
-struct FlowCtl { int n_segments, n_unres, converged, pad2; int changed[kRelaxBatch + 1]; int pad3[3]; };
+struct FlowCtl { int n_segments, n_unres, converged; unsigned gbar; int changed[kRelaxBatch + 1]; int pad3[3]; };
 
 struct DevFlow {
   int *order, *posidx, *isfront, *seg_len, *seg_dep, *segpos, *minslot, *cut, *fronts, *ulist;
@@ -217,6 +217,70 @@ __global__ void k_cyc_break(DevVeh V, DevFlow F, double* rows, long long* counte
   if (cP_ref().cls[V.cls[Y]].law == 0) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_LOOPS], 1ULL);
   int py = F.posidx[Y];
   ((int*)&row_at(rows, py)[R_I1])[1] |= 1;          // row header: leader stays uncomputed (little endian: high int)
+  }
+}
+
+// The pointer-jumping rounds, the marking and the cutting in ONE launch (cooperative: all blocks resident, barriers between the
+// phases on a counter in FlowCtl): the open chains are few, so the separate launches (K + 2 of them) only cost their latency.
+// Data another block wrote in an earlier phase is read through L2 (__ldcg): the L1 of this SM may hold the line from before.
+__device__ __forceinline__ void grid_barrier(unsigned* count, unsigned nblocks, unsigned& phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    phase++;
+    __threadfence();
+    atomicAdd(count, 1u);
+    const unsigned target = phase * nblocks;
+    while (*(volatile unsigned*)count < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) k_cyc_rest(DevVeh V, DevFlow F, double* rows, long long* counters, int klev, int by_id) {
+  unsigned phase = 0; const unsigned nb = gridDim.x;
+  const int ns = __ldcg(&F.ctl->n_unres);
+  if (ns == 0) return;                                   // every block sees the same count: no chain left open
+  int flip = 0;
+  for (int k = 0; k < klev; k++) {                     // A <- A^4, Mn <- min over the segments stepped over
+    const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;
+    int* Ao = flip ? F.A : F.A2; int* Mo = flip ? F.Mn : F.Mn2;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
+      int p = F.ulist[t];
+      int a = __ldcg(&A[p]), a1 = __ldcg(&A[a]), a2 = __ldcg(&A[a1]);
+      Ao[p] = __ldcg(&A[a2]);
+      Mo[p] = min(min(__ldcg(&M[p]), __ldcg(&M[a])), min(__ldcg(&M[a1]), __ldcg(&M[a2])));
+    }
+    flip ^= 1;
+    grid_barrier(&F.ctl->gbar, nb, phase);
+  }
+  { const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;          // mark (k_cyc_mark)
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {
+      int p = F.ulist[t];
+      int c0 = __ldcg(&A[p]);
+      if (F.seg_dep[c0] < 0) continue;
+      F.oncyc[c0] = 1;
+      int id = __ldcg(&M[c0]);
+      F.cid[p] = id;
+      unsigned long long key = ((unsigned long long)(unsigned)list_key(V, F.minslot[p], by_id) << 32) | (unsigned)p;
+      atomicMin(&F.rootkey[id], key);
+    } }
+  grid_barrier(&F.ctl->gbar, nb, phase);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ns; t += gridDim.x * blockDim.x) {   // cut (k_cyc_break)
+    int p = F.ulist[t];
+    if (!__ldcg(&F.oncyc[p]) || __ldcg(&F.cid[p]) != p) continue;
+    unsigned long long key = __ldcg(&F.rootkey[p]);
+    int rs = (int)(key & 0xffffffffu); int r = F.minslot[rs];
+    int e = rs, T = -1;
+    while (!__ldcg(&F.oncyc[e])) { T = F.seg_dep[e]; e = F.segpos[T]; }
+    int q = e;
+    for (;;) { int nx = F.segpos[F.seg_dep[q]]; if (nx == e) break; q = nx; }
+    int Tloop = F.seg_dep[q];
+    int cand = (e != rs) ? T : r;
+    int X = (F.posidx[cand] >= F.posidx[Tloop]) ? cand : Tloop;
+    int Y = (X == Tloop) ? F.order[q] : F.order[F.posidx[X] - 1];
+    F.cut[Y] = 1;
+    if (cP_ref().cls[V.cls[Y]].law == 0) atomicAdd((unsigned long long*)&counters[SYMGPU_CNT_LOOPS], 1ULL);
+    int py = F.posidx[Y];
+    ((int*)&row_at(rows, py)[R_I1])[1] |= 1;
   }
 }
 

@@ -155,3 +155,10 @@ def test_trajectory_rows_sync_and_async(synth, pkg, tmp_path):
     st = g.state()
     assert rows == len(st["id"]) and np.array_equal(one["pos"][:rows], st["pos"]) and np.array_equal(one["id"][:rows], st["id"])
     g.close()
+
+
+def test_grid_without_context_memo(synth, monkeypatch):
+    """SYMGPU_CTXCACHE=0: every vehicle walks the itinerary / movement / stop-line tables every step (the path the per-vehicle
+    memo of micro.cuh: CtxCache replaces for the vehicles that stayed on their lane); same bits against the oracle."""
+    monkeypatch.setenv("SYMGPU_CTXCACHE", "0")
+    _check(run_parity(synth.grid(n=4, n_steps=150, demand_per_lane=0.3, preseed_per_lane=6, shuffle=True), 150))
