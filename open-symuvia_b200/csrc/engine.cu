@@ -217,10 +217,11 @@ __global__ void k_lane_links(DevVeh V, int n_sorted, const int* lane_start, cons
 // one thread per position of the lane order: neighbouring threads are neighbours on a lane, so they walk the same context
 // lanes, stop lines and movements (little divergence, table reads shared through L1) and their rows are written coalesced
 #ifndef SYM_CTX_BLOCKS
-#define SYM_CTX_BLOCKS 8   // 32 registers: the kernel waits on dependent table look-ups, so resident warps matter more than spills (C4: 3 blocks/SM 0.40 ms, 4: 0.33, 6: 0.30, 8: 0.296)
+#define SYM_CTX_BLOCKS 8   // 128 threads x 8 blocks = 64 registers.  With the per-vehicle context memo the kernel moves 870 B per vehicle at ~60 % of the HBM
+                           // peak, so spill traffic costs more than the lost warps (C4, 256-thread blocks at 32 / 40 / 48 / 64 / 80 registers: 0.227 / 0.200 / 0.193 / 0.184 / 0.20 ms; 128 x 8: 0.184)
 #endif
 #ifndef SYM_CTX_THREADS
-#define SYM_CTX_THREADS 256
+#define SYM_CTX_THREADS 128
 #endif
 __global__ void __launch_bounds__(SYM_CTX_THREADS, SYM_CTX_BLOCKS) k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
