@@ -278,7 +278,7 @@ __global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* ent
                         int* exit_winner, int* n_alive, int* err, const int* guard, int* cc_list, int* cc_cnt) {
   if (guard && *guard == 0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool stale = false;
+  bool stale = false, alive = false;
   int st = i < n ? V.status[i] : ST_DEAD;
   if (st == ST_ALIVE || st == ST_NEW) {
   if (!V.computed[i]) atomicAdd(err, 1);
@@ -301,13 +301,15 @@ __global__ void k_final(DevNet N, DevVeh V, int n, int ncls, double dt, int* ent
     V.status[i] = ST_DEAD;
   } else {
     V.status[i] = ST_ALIVE;
-    atomicAdd(n_alive, 1);
+    alive = true;
     if (cc_list) { int id = V.id[i];                                                       // the vehicle's context memo is for another lane (or another vehicle):
       stale = V.cc_lane[i] != lane0 || V.cc_id[i] != id;                                   // listed for k_ctx_fill, key set now so that it is listed once
       if (stale) { V.cc_lane[i] = lane0; V.cc_id[i] = id; } }
   }
   }
   }
+  { const unsigned ma = __ballot_sync(0xffffffffu, alive);                                 // vehicles left on the network: one atomic per warp
+    if (ma && (threadIdx.x & 31) == 0) atomicAdd(n_alive, __popc(ma)); }
   if (cc_list) {                                                                           // one atomic per warp
     const unsigned m = __ballot_sync(0xffffffffu, stale);
     if (m) { const int lane = threadIdx.x & 31; int base = 0;
