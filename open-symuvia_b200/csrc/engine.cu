@@ -88,6 +88,13 @@ __global__ void k_signals(DevSig S, const int* sl_i, int n_sl, double inst, int*
 }
 
 // ------------------------------------------------------------------------------------------------
+// start of a step: per-lane counters, lane tails, step statistics and the relaxation's control block in one launch
+__global__ void k_reset(int L, int* lane_count, int* lane_fill, int* lane_tail, int* stat, int* flow_ctl, int ctl_words) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) { lane_count[i] = 0; lane_fill[i] = 0; lane_tail[i] = -1; }
+  if (i < 16) stat[i] = 0;
+  if (i < ctl_words) flow_ctl[i] = 0;
+}
 __global__ void k_prepare(DevVeh V, int n, int* lane_count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -842,27 +849,26 @@ static int step_front(symgpu_ctx* c) {
   const int n_sorted = c->n_alive + (int)new_rows.size();   // vehicles that are members of a lane this step
   const int B = 256;
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
+  k_reset<<<G(std::max(L, 32)), B, 0, s>>>(L, c->lane_count.p, c->lane_fill.p, c->lane_tail.p, c->stat.p, (int*)c->f_ctl.p, (int)(sizeof(FlowCtl) / sizeof(int))); LAUNCH(c);
+  if (n > 0) { KBEGIN(c, KID_PREPARE); k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); KEND(c); }
   // side stream, beside this step's lane ordering: the signal states of the step (read from k_context on) and the context memos
   // of the vehicles the last step listed; step_back waits for both (the lane-change phase too: it moves vehicles to other lanes)
   const bool side_sig = c->net.n_sl() > 0 && !c->profile;                 // per-kernel timing (profile) keeps everything on one stream
   if (side_sig || c->cc_fill) {
-    CK(cudaEventRecord(c->cc_go, s)); CK(cudaStreamWaitEvent(c->aux, c->cc_go, 0));
+    if (c->mp.on || c->ext_stream) { CK(cudaEventRecord(c->cc_go, s)); CK(cudaStreamWaitEvent(c->aux, c->cc_go, 0)); }   // else: the host waited for the last step, nothing is in flight
     if (side_sig) { k_signals<<<G(c->net.n_sl()), B, 0, c->aux>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); LAUNCH(c); }
     if (c->cc_fill) { k_ctx_fill<<<c->n_sms * 16, 64, 0, c->aux>>>(c->dn, c->dv, c->cc_list.p, c->cc_cnt.p); LAUNCH(c); c->cc_fill = false; }
     CK(cudaEventRecord(c->cc_done, c->aux)); c->aux_wait = true;
     if (c->chgtvoie) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->aux_wait = false; }
   }
-  CK(cudaMemsetAsync(c->lane_count.p, 0, L * sizeof(int), s)); CK(cudaMemsetAsync(c->lane_fill.p, 0, L * sizeof(int), s));
-  CK(cudaMemsetAsync(c->stat.p, 0, 16 * sizeof(int), s));
   if (c->net.n_sl() && !side_sig) { KBEGIN(c, KID_SIGNALS); k_signals<<<G(c->net.n_sl()), B, 0, s>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); KEND(c); }
   if (n > 0) {
-    KBEGIN(c, KID_PREPARE); k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); KEND(c);
     int nb = (L + kScanB - 1) / kScanB;
     KBEGIN(c, KID_SCAN); k_scan_block<<<nb, kScanB, 0, s>>>(c->lane_count.p, c->lane_start.p, c->bsum.p, L); LAUNCH(c);
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->lane_start.p, c->bsum.p, L); }
     KEND(c);
     KBEGIN(c, KID_SCATTER); k_scatter<<<G(n), B, 0, s>>>(c->dv, n, c->lane_start.p, c->lane_fill.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p); KEND(c);
-    KBEGIN(c, KID_SORT); CK(cudaMemsetAsync(c->lane_tail.p, 0xff, L * sizeof(int), s));
+    KBEGIN(c, KID_SORT);
       if (n_sorted > 0) { k_lane_rank<<<G(n_sorted), B, 0, s>>>(n_sorted, c->lane_start.p, c->lane_count.p, c->u_order.p, c->u_key.p, c->u_id.p, c->u_lane.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->f_posidx.p); LAUNCH(c);
         k_lane_links<<<G(n_sorted), B, 0, s>>>(c->dv, n_sorted, c->lane_start.p, c->lane_count.p, c->order.p, c->s_key.p, c->s_id.p, c->s_lane.p, c->lane_tail.p, c->counters.p); } KEND(c);
   }
@@ -914,7 +920,6 @@ static int step_back(symgpu_ctx* c) {
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
-    CK(cudaMemsetAsync(c->f_ctl.p, 0, sizeof(FlowCtl), s));
     KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
     // leader loops: always looked for (the segment graph is small), cut where the reference's recursion would cut them
     { int Klev = 1; while ((1LL << (2 * Klev)) * kCycWalk < (long long)std::max(4, n_sorted)) Klev++;   // 4^K * walk >= longest possible chain
@@ -954,7 +959,7 @@ static int step_back(symgpu_ctx* c) {
       if (n_sorted > 0) { KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t, guard); KEND(c); }
       if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
                                                                       (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW], guard); KEND(c); }
-      cudaMemsetAsync(&c->stat.p[4], 0, 3 * sizeof(int), s); if (c->use_cc) cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s);
+      if (c->use_cc) cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s);
       KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6], guard, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
       if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
                                                                                 c->next_sortie.p, c->t, c->P.dt, c->P.duree, guard); }
