@@ -484,7 +484,7 @@ struct symgpu_ctx {
   // trajectory output: packed device rows + side stream + caller buffers registered for direct DMA (two in flight)
   DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
-  bool profile = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  int profile = 0; bool prof_open = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   long long lane_changes = 0; int n_sms = 148; int relax_batch = kRelaxBatch; bool ext_stream = false;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
@@ -788,9 +788,11 @@ static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
 static void dbg_sync(symgpu_ctx* c, int line);
 #define LAUNCH(c) do { (c)->launches++; if ((c)->dbg_sync) dbg_sync(c, __LINE__); } while (0)
-#define KBEGIN(c, kid) do { if ((c)->profile) prof_begin(c, kid); } while (0)
-#define KEND(c) do { LAUNCH(c); if ((c)->profile) prof_end(c); } while (0)
-#define KEND0(c) do { if ((c)->profile) prof_end(c); } while (0)
+// profile 1: every kernel group is bracketed by events (per-kernel breakdown); 2: only the relaxation sweeps (the dominant kernel,
+// timed inside the measured region without the other groups' event records)
+#define KBEGIN(c, kid) do { if ((c)->profile == 1 || ((c)->profile == 2 && (kid) == KID_FOLLOW)) { prof_begin(c, kid); (c)->prof_open = true; } } while (0)
+#define KEND(c) do { LAUNCH(c); if ((c)->prof_open) { prof_end(c); (c)->prof_open = false; } } while (0)
+#define KEND0(c) do { if ((c)->prof_open) { prof_end(c); (c)->prof_open = false; } } while (0)
 
 static cudaEvent_t prof_event(symgpu_ctx* c) {
   if (c->ev_used == c->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->ev_pool.push_back(e); }
@@ -853,7 +855,7 @@ static int step_front(symgpu_ctx* c) {
   if (n > 0) { KBEGIN(c, KID_PREPARE); k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); KEND(c); }
   // side stream, beside this step's lane ordering: the signal states of the step (read from k_context on) and the context memos
   // of the vehicles the last step listed; step_back waits for both (the lane-change phase too: it moves vehicles to other lanes)
-  const bool side_sig = c->net.n_sl() > 0 && !c->profile;                 // per-kernel timing (profile) keeps everything on one stream
+  const bool side_sig = c->net.n_sl() > 0 && c->profile != 1;                 // per-kernel timing (profile) keeps everything on one stream
   if (side_sig || c->cc_fill) {
     if (c->mp.on || c->ext_stream) { CK(cudaEventRecord(c->cc_go, s)); CK(cudaStreamWaitEvent(c->aux, c->cc_go, 0)); }   // else: the host waited for the last step, nothing is in flight
     if (side_sig) { k_signals<<<G(c->net.n_sl()), B, 0, c->aux>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); LAUNCH(c); }
@@ -1253,7 +1255,7 @@ extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, doub
   return r;
 }
 extern "C" double symgpu_traj_copy_ms(symgpu_ctx* c, int which) { return c && which >= 0 && which < 2 ? c->t_copy_ms[which] : 0.0; }
-extern "C" int symgpu_profile(symgpu_ctx* c, int enable) { if (!c) return SYMGPU_E_ARG; c->profile = enable != 0; for (int k = 0; k < 16; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return SYMGPU_OK; }
+extern "C" int symgpu_profile(symgpu_ctx* c, int enable) { if (!c) return SYMGPU_E_ARG; c->profile = enable; for (int k = 0; k < 16; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return SYMGPU_OK; }
 extern "C" int symgpu_kernel_count(void) { return KID_COUNT; }
 extern "C" const char* symgpu_kernel_name(int k) { return k >= 0 && k < KID_COUNT ? kKernelNames[k] : ""; }
 extern "C" double symgpu_kernel_ms(symgpu_ctx* c, int k) { return c && k >= 0 && k < KID_COUNT ? c->k_ms[k] : 0.0; }
