@@ -482,7 +482,7 @@ struct symgpu_ctx {
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
   // trajectory output: packed device rows + side stream + caller buffers registered for direct DMA (two in flight)
-  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
+  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_packed = nullptr; bool pack_wait = false; cudaEvent_t t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
   struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
   int profile = 0; bool prof_open = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   long long lane_changes = 0; int n_sms = 148; int relax_batch = kRelaxBatch; bool ext_stream = false;
@@ -588,7 +588,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(cudaMemcpyToSymbol(cP, &P, sizeof(P)));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
-  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->t_ready, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->t_ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->t_packed, cudaEventDisableTiming));
   for (int k = 0; k < 2; k++) { CK(cudaEventCreate(&c->t_done[k])); CK(cudaEventCreate(&c->t_begin[k])); }
   CK(cudaMallocHost(&c->h_stat, 16 * sizeof(int)));
   // static tables
@@ -690,7 +690,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   for (int k = 0; k < 2; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
   c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
   if (c->aux) cudaStreamDestroy(c->aux); if (c->cc_go) cudaEventDestroy(c->cc_go); if (c->cc_done) cudaEventDestroy(c->cc_done);
-  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); for (int k = 0; k < 2; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
+  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); if (c->t_packed) cudaEventDestroy(c->t_packed); for (int k = 0; k < 2; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_ctl_seed) cudaFreeHost(c->h_ctl_seed);
@@ -876,6 +876,7 @@ static int step_front(symgpu_ctx* c) {
   }
   // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
   if (c->chgtvoie && n > 0) {
+    if (c->pack_wait) { CK(cudaStreamWaitEvent(s, c->t_packed, 0)); c->pack_wait = false; }
     const int K = c->net.n_links();
     KBEGIN(c, KID_LC);
     k_lc_prepare<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c);
@@ -957,6 +958,7 @@ static int step_back(symgpu_ctx* c) {
     cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s);
   };
   auto finish = [&](const int* guard) {
+    if (c->pack_wait) { cudaStreamWaitEvent(s, c->t_packed, 0); c->pack_wait = false; }      // trajectory rows of the last step are packed: status may change
     if (n > 0) {
       if (n_sorted > 0) { KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t, guard); KEND(c); }
       if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
@@ -1214,14 +1216,15 @@ extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
   const int n = c->n_slots; const int rows = c->n_alive;
   if (rows > b.cap) { g_err = "trajectory buffer too small"; return SYMGPU_E_CAPACITY; }
   if (n > 0) {
-    cudaStream_t s = c->stream; const int B = 256; int G = (n + B - 1) / B; int nb = (n + kScanB - 1) / kScanB;
+    // packing and copies on the side stream, beside the next step: it only reads the start-of-step arrays of that step (id, lane,
+    // pos, vit, acc) and the status, which the next step leaves alone until its lane-change phase / k_final — they wait for t_packed
+    cudaStream_t s = c->side; const int B = 256; int G = (n + B - 1) / B; int nb = (n + kScanB - 1) / kScanB;
+    if (c->mp.on || c->ext_stream) { CK(cudaEventRecord(c->t_ready, c->stream)); CK(cudaStreamWaitEvent(s, c->t_ready, 0)); }   // else the host waited for the step
     k_alive_flags<<<G, B, 0, s>>>(c->v_status.p, n, c->t_flag.p); LAUNCH(c);
     k_scan_block<<<nb, kScanB, 0, s>>>(c->t_flag.p, c->t_off.p, c->t_bsum.p, n); LAUNCH(c);
     if (nb > 1) { k_scan_sums<<<1, kScanB, 0, s>>>(c->t_bsum.p, nb); LAUNCH(c); k_scan_add<<<nb, kScanB, 0, s>>>(c->t_off.p, c->t_bsum.p, n); LAUNCH(c); }
-    CK(cudaStreamWaitEvent(s, c->t_done[which ^ 1], 0));        // the packed rows are reused: the previous copy must have left
     k_pack_traj<<<G, B, 0, s>>>(c->dv, n, c->t_flag.p, c->t_off.p, c->t_id.p, c->t_lane.p, c->t_pos.p, c->t_vit.p, c->t_acc.p); LAUNCH(c);
-    CK(cudaEventRecord(c->t_ready, s));
-    CK(cudaStreamWaitEvent(c->side, c->t_ready, 0));
+    CK(cudaEventRecord(c->t_packed, s)); c->pack_wait = true;
     CK(cudaEventRecord(c->t_begin[which], c->side));
     CK(cudaMemcpyAsync(b.id, c->t_id.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->side));
     CK(cudaMemcpyAsync(b.lane, c->t_lane.p, (size_t)rows * 4, cudaMemcpyDeviceToHost, c->side));
