@@ -46,6 +46,8 @@ int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, do
 
 /* Asynchronous form (north_star: "trajectory output is copied back asynchronously on a side stream"): bind two caller
  * buffers once (they are page-locked in place), then alternate them; the copy of step k overlaps the computation of k+1. */
+/* `which` = 0..3: two buffers let the consumer lag one step (the copy must then end inside the next step); three in rotation let
+   it lag two, so that a copy never stalls the stepping loop. */
 int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
 int symgpu_step_traj_async(symgpu_ctx* c, int which);   /* returns rows, valid after symgpu_traj_wait(which) */
 int symgpu_traj_wait(symgpu_ctx* c, int which);

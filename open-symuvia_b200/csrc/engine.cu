@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <deque>
@@ -420,6 +421,7 @@ __global__ void k_mp_drop_foreign(DevVeh V, int n, const int* lane_owner, int ra
 // ================================================================================================
 // host side
 // ================================================================================================
+constexpr int kTrajBufs = 4;   // caller buffers for trajectory rows: with three in rotation the consumer lags two steps and a copy never has to end inside its step
 namespace {
 
 // RandManager (RandManager.cpp:5-30): boost::mt19937 + uniform_int<>(0, 0x7FFE)
@@ -482,8 +484,8 @@ struct symgpu_ctx {
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
   // trajectory output: packed device rows + side stream + caller buffers registered for direct DMA (two in flight)
-  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_packed = nullptr; bool pack_wait = false; cudaEvent_t t_done[2] = {nullptr, nullptr}, t_begin[2] = {nullptr, nullptr}; double t_copy_ms[2] = {0, 0};
-  struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[2];
+  DBuf<int> t_flag, t_off, t_bsum, t_id, t_lane; DBuf<double> t_pos, t_vit, t_acc; cudaStream_t side = nullptr; cudaEvent_t t_ready = nullptr, t_packed = nullptr; bool pack_wait = false; int traj_req = -1, traj_req_n = 0, traj_req_rows = 0; double traj_host_us = 0; long traj_host_n = 0; cudaEvent_t t_done[kTrajBufs] = {}, t_begin[kTrajBufs] = {}; double t_copy_ms[kTrajBufs] = {};
+  struct TrajBuf { int cap = 0; int* id = nullptr; int* lane = nullptr; double* pos = nullptr; double* vit = nullptr; double* acc = nullptr; bool registered = false; } tbuf[kTrajBufs];
   int profile = 0; bool prof_open = false; std::vector<ProfRec> prof_recs; std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   long long lane_changes = 0; int n_sms = 148; int relax_batch = kRelaxBatch; bool ext_stream = false;
   double k_ms[16] = {0}; long long k_launches[16] = {0}; long long veh_steps = 0;
@@ -589,7 +591,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
   CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->t_ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->t_packed, cudaEventDisableTiming));
-  for (int k = 0; k < 2; k++) { CK(cudaEventCreate(&c->t_done[k])); CK(cudaEventCreate(&c->t_begin[k])); }
+  for (int k = 0; k < kTrajBufs; k++) { CK(cudaEventCreate(&c->t_done[k])); CK(cudaEventCreate(&c->t_begin[k])); }
   CK(cudaMallocHost(&c->h_stat, 16 * sizeof(int)));
   // static tables
   CK(c->lane_link.upload(col(f.lane_i, 4, 0))); CK(c->lane_num.upload(col(f.lane_i, 4, 1))); CK(c->lane_prev.upload(col(f.lane_i, 4, 2)));
@@ -673,6 +675,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
 }
 
 extern "C" void symgpu_destroy(symgpu_ctx* c) {
+  if (c && c->traj_host_n && getenv("SYMGPU_TIMING")) fprintf(stderr, "symgpu: trajectory enqueue %.1f us of host time per call (%ld calls)\n", c->traj_host_us / c->traj_host_n, c->traj_host_n);
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
@@ -687,10 +690,10 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
   for (DBuf<double>* b : {&c->lane_len, &c->sl_pos, &c->link_len, &c->link_vreg, &c->ctrl_cycle, &c->seq_len, &c->sig_green, &c->sig_amber, &c->sig_delay, &c->exit_cap,
                           &c->sl_prop, &c->next_sortie, &c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre,
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
-  for (int k = 0; k < 2; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
+  for (int k = 0; k < kTrajBufs; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
   c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
   if (c->aux) cudaStreamDestroy(c->aux); if (c->cc_go) cudaEventDestroy(c->cc_go); if (c->cc_done) cudaEventDestroy(c->cc_done);
-  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); if (c->t_packed) cudaEventDestroy(c->t_packed); for (int k = 0; k < 2; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
+  if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); if (c->t_packed) cudaEventDestroy(c->t_packed); for (int k = 0; k < kTrajBufs; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
   if (c->h_ctl) cudaFreeHost(c->h_ctl);
   if (c->h_ctl_seed) cudaFreeHost(c->h_ctl_seed);
@@ -787,6 +790,7 @@ static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan"
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
 static void dbg_sync(symgpu_ctx* c, int line);
+static int traj_enqueue(symgpu_ctx* c);
 #define LAUNCH(c) do { (c)->launches++; if ((c)->dbg_sync) dbg_sync(c, __LINE__); } while (0)
 // profile 1: every kernel group is bracketed by events (per-kernel breakdown); 2: only the relaxation sweeps (the dominant kernel,
 // timed inside the measured region without the other groups' event records)
@@ -876,6 +880,7 @@ static int step_front(symgpu_ctx* c) {
   }
   // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
   if (c->chgtvoie && n > 0) {
+    if (c->traj_req >= 0) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }   // before vehicles move to other lanes
     if (c->pack_wait) { CK(cudaStreamWaitEvent(s, c->t_packed, 0)); c->pack_wait = false; }
     const int K = c->net.n_links();
     KBEGIN(c, KID_LC);
@@ -921,6 +926,9 @@ static int step_back(symgpu_ctx* c) {
   if (n > 0) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
+    // trajectory rows of the last step: packed and copied on the side stream beside this one.  Enqueued here because k_context keeps
+    // the device busy long enough for the ~13 API calls (behind the short kernels of the lane ordering they would stall the queue)
+    if (c->traj_req >= 0) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
@@ -1193,7 +1201,7 @@ extern "C" int symgpu_get_state(symgpu_ctx* c, int cap, int* id, int* lane, int*
 }
 // Caller buffers for trajectory rows: page-locked in place so the device copies straight into them.
 extern "C" int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, double* pos, double* vit, double* acc) {
-  if (!c || which < 0 || which > 1 || cap <= 0 || !id || !lane || !pos || !vit || !acc) return SYMGPU_E_ARG;
+  if (!c || which < 0 || which >= kTrajBufs || cap <= 0 || !id || !lane || !pos || !vit || !acc) return SYMGPU_E_ARG;
   CK(cudaSetDevice(c->device));
   auto& b = c->tbuf[which];
   if (b.registered) { cudaHostUnregister(b.id); cudaHostUnregister(b.lane); cudaHostUnregister(b.pos); cudaHostUnregister(b.vit); cudaHostUnregister(b.acc); b.registered = false; }
@@ -1209,15 +1217,19 @@ extern "C" int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int*
 // valid after symgpu_traj_wait(which)).  The next step can run while the copy is in flight.
 // pack + copy the CURRENT trajectory rows to bound buffer `which` on the side stream (no step): partitioned runs call it
 // after symgpu_mp_import
-extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
-  if (!c || which < 0 || which > 1 || !c->tbuf[which].id) return SYMGPU_E_ARG;
-  CK(cudaSetDevice(c->device));
+// pack + copies of the rows requested by symgpu_traj_copy_async.  On one GPU the request is only noted and this runs from the next
+// step's step_front, once its first kernels are in the queue: the ~13 API calls then cost no device time (the device is busy), and the
+// side stream works beside that step.  symgpu_traj_wait (or another request) flushes a request that no step has picked up.
+static int traj_enqueue(symgpu_ctx* c) {
+  const int which = c->traj_req; if (which < 0) return SYMGPU_OK;
+  struct Timer { symgpu_ctx* c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~Timer() { c->traj_host_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); c->traj_host_n++; } } timer{c};
+  c->traj_req = -1;
   auto& b = c->tbuf[which];
-  const int n = c->n_slots; const int rows = c->n_alive;
-  if (rows > b.cap) { g_err = "trajectory buffer too small"; return SYMGPU_E_CAPACITY; }
+  const int n = c->traj_req_n; const int rows = c->traj_req_rows;
   if (n > 0) {
-    // packing and copies on the side stream, beside the next step: it only reads the start-of-step arrays of that step (id, lane,
-    // pos, vit, acc) and the status, which the next step leaves alone until its lane-change phase / k_final — they wait for t_packed
+    // the side stream only reads the start-of-step arrays of the next step (id, lane, pos, vit, acc) and the status, which that step
+    // leaves alone until its lane-change phase / k_final — they wait for t_packed
     cudaStream_t s = c->side; const int B = 256; int G = (n + B - 1) / B; int nb = (n + kScanB - 1) / kScanB;
     if (c->mp.on || c->ext_stream) { CK(cudaEventRecord(c->t_ready, c->stream)); CK(cudaStreamWaitEvent(s, c->t_ready, 0)); }   // else the host waited for the step
     k_alive_flags<<<G, B, 0, s>>>(c->v_status.p, n, c->t_flag.p); LAUNCH(c);
@@ -1233,16 +1245,27 @@ extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
     CK(cudaMemcpyAsync(b.acc, c->t_acc.p, (size_t)rows * 8, cudaMemcpyDeviceToHost, c->side));
   }
   CK(cudaEventRecord(c->t_done[which], c->side));
+  return SYMGPU_OK;
+}
+extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
+  if (!c || which < 0 || which >= kTrajBufs || !c->tbuf[which].id) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  if (c->traj_req >= 0) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }
+  const int rows = c->n_alive;
+  if (rows > c->tbuf[which].cap) { g_err = "trajectory buffer too small"; return SYMGPU_E_CAPACITY; }
+  c->traj_req = which; c->traj_req_n = c->n_slots; c->traj_req_rows = rows;
+  if (c->mp.on || c->ext_stream) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }   // partitioned runs: arrivals may reuse slots before the next step
   return rows;
 }
 extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
-  if (!c || which < 0 || which > 1 || !c->tbuf[which].id) return SYMGPU_E_ARG;
+  if (!c || which < 0 || which >= kTrajBufs || !c->tbuf[which].id) return SYMGPU_E_ARG;
   int r = symgpu_step(c);
   if (r < 0) return r;
   return symgpu_traj_copy_async(c, which);
 }
 extern "C" int symgpu_traj_wait(symgpu_ctx* c, int which) {
-  if (!c || which < 0 || which > 1) return SYMGPU_E_ARG;
+  if (!c || which < 0 || which >= kTrajBufs) return SYMGPU_E_ARG;
+  if (c->traj_req == which) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }
   CK(cudaEventSynchronize(c->t_done[which]));
   float ms = 0; if (cudaEventElapsedTime(&ms, c->t_begin[which], c->t_done[which]) == cudaSuccess) c->t_copy_ms[which] = ms; else cudaGetLastError();
   return SYMGPU_OK;
@@ -1257,7 +1280,7 @@ extern "C" int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, doub
   c->tbuf[0] = saved;
   return r;
 }
-extern "C" double symgpu_traj_copy_ms(symgpu_ctx* c, int which) { return c && which >= 0 && which < 2 ? c->t_copy_ms[which] : 0.0; }
+extern "C" double symgpu_traj_copy_ms(symgpu_ctx* c, int which) { return c && which >= 0 && which < kTrajBufs ? c->t_copy_ms[which] : 0.0; }
 extern "C" int symgpu_profile(symgpu_ctx* c, int enable) { if (!c) return SYMGPU_E_ARG; c->profile = enable; for (int k = 0; k < 16; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return SYMGPU_OK; }
 extern "C" int symgpu_kernel_count(void) { return KID_COUNT; }
 extern "C" const char* symgpu_kernel_name(int k) { return k >= 0 && k < KID_COUNT ? kKernelNames[k] : ""; }

@@ -157,6 +157,38 @@ def test_trajectory_rows_sync_and_async(synth, pkg, tmp_path):
     g.close()
 
 
+@pytest.mark.parametrize("nbuf", [2, 3])
+def test_trajectory_rows_pipelined(synth, pkg, tmp_path, nbuf):
+    """The bench's pattern: the rows of step k are picked up while step k+1 runs (the pack and the copies are enqueued from the
+    next step, on the side stream) — they must still be the state at the end of step k, exits and arrivals included."""
+    b = synth.grid(n=4, n_steps=100, demand_per_lane=0.3, preseed_per_lane=6, shuffle=True)
+    p = str(tmp_path / "t.symflat")
+    b.write(p)
+    g, ref = pkg.Engine(p), pkg.Engine(p)
+    cap = 20000
+    mk = lambda: {"id": np.zeros(cap, np.int32), "lane": np.zeros(cap, np.int32), "pos": np.zeros(cap), "vit": np.zeros(cap), "acc": np.zeros(cap)}
+    bufs = [mk() for _ in range(nbuf)]
+    for w in range(nbuf):
+        g.traj_bind(w, bufs[w])
+    states, counts = [], []
+
+    def check(j):
+        g.traj_wait(j % nbuf)
+        st, rows = states[j], counts[j]
+        assert rows == len(st["id"])
+        for key in ("id", "lane", "pos", "vit", "acc"):
+            assert np.array_equal(bufs[j % nbuf][key][:rows], st[key]), (j, key)
+
+    for k in range(60):
+        counts.append(g.step_traj_async(k % nbuf))
+        ref.step(); states.append(ref.state())
+        if k >= nbuf - 1:
+            check(k - (nbuf - 1))
+    for j in range(60 - (nbuf - 1), 60):
+        check(j)
+    g.close(); ref.close()
+
+
 def test_grid_without_context_memo(synth, monkeypatch):
     """SYMGPU_CTXCACHE=0: every vehicle walks the itinerary / movement / stop-line tables every step (the path the per-vehicle
     memo of micro.cuh: CtxCache replaces for the vehicles that stayed on their lane); same bits against the oracle."""
