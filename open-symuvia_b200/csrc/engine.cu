@@ -880,7 +880,6 @@ static int step_front(symgpu_ctx* c) {
   }
   // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
   if (c->chgtvoie && n > 0) {
-    if (c->traj_req >= 0) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }   // before vehicles move to other lanes
     if (c->pack_wait) { CK(cudaStreamWaitEvent(s, c->t_packed, 0)); c->pack_wait = false; }
     const int K = c->net.n_links();
     KBEGIN(c, KID_LC);
@@ -926,9 +925,6 @@ static int step_back(symgpu_ctx* c) {
   if (n > 0) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
-    // trajectory rows of the last step: packed and copied on the side stream beside this one.  Enqueued here because k_context keeps
-    // the device busy long enough for the ~13 API calls (behind the short kernels of the lane ordering they would stall the queue)
-    if (c->traj_req >= 0) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
@@ -1217,9 +1213,9 @@ extern "C" int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int*
 // valid after symgpu_traj_wait(which)).  The next step can run while the copy is in flight.
 // pack + copy the CURRENT trajectory rows to bound buffer `which` on the side stream (no step): partitioned runs call it
 // after symgpu_mp_import
-// pack + copies of the rows requested by symgpu_traj_copy_async.  On one GPU the request is only noted and this runs from the next
-// step's step_front, once its first kernels are in the queue: the ~13 API calls then cost no device time (the device is busy), and the
-// side stream works beside that step.  symgpu_traj_wait (or another request) flushes a request that no step has picked up.
+// pack + copies of the rows requested by symgpu_traj_copy_async, on the side stream beside the next step.  (Enqueuing them later —
+// from the next step's step_front, or behind its k_context launch, with two or three caller buffers — was measured: 0.95 / 0.97 /
+// 1.02 ms per step end to end against 0.95 here; what the copy costs the stepping loop is device-side, not the ~30 us of API calls.)
 static int traj_enqueue(symgpu_ctx* c) {
   const int which = c->traj_req; if (which < 0) return SYMGPU_OK;
   struct Timer { symgpu_ctx* c; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -1254,7 +1250,7 @@ extern "C" int symgpu_traj_copy_async(symgpu_ctx* c, int which) {
   const int rows = c->n_alive;
   if (rows > c->tbuf[which].cap) { g_err = "trajectory buffer too small"; return SYMGPU_E_CAPACITY; }
   c->traj_req = which; c->traj_req_n = c->n_slots; c->traj_req_rows = rows;
-  if (c->mp.on || c->ext_stream) { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }   // partitioned runs: arrivals may reuse slots before the next step
+  { int rc = traj_enqueue(c); if (rc != SYMGPU_OK) return rc; }
   return rows;
 }
 extern "C" int symgpu_step_traj_async(symgpu_ctx* c, int which) {
