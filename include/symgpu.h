@@ -63,6 +63,7 @@ int symgpu_mp_sizes(symgpu_ctx* c, int* export_cnt, int* halo_cnt);             
 int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails);
 int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, double* send_rows, int cap_per_peer, int* send_counts);
 int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows);          /* rows of 16 doubles */
+int symgpu_mp_import_regions(symgpu_ctx* c, const double* recv_regions, int cap_per_peer);   /* the receive buffer of the fixed-size all_to_all as it is (world regions of cap_per_peer rows) */
 /* Origins in a partitioned run: every rank replays the creation draws of all origins (same seed, same ids) and keeps the vehicles of
    the entry lanes it owns; the device's own draws of the step are summed over the ranks by the caller and committed on every rank. */
 int symgpu_set_stream(symgpu_ctx* c, void* cuda_stream);   /* run on the caller's stream (cudaStream_t), e.g. the one its collectives are ordered on */

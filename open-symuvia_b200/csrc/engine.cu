@@ -1126,6 +1126,29 @@ extern "C" int symgpu_mp_commit_draws(symgpu_ctx* c, long total) {
   return SYMGPU_OK;
 }
 // vehicles arriving from other ranks (n_rows x 16 doubles in device memory) join the end of the local list
+// arrivals straight from the per-peer regions of the fixed-size all_to_all (the row count of a region rides in the spare double of
+// its first row, k_mp_row_counts): one strided copy brings the counts to the host, one unpack launch per non-empty region
+extern "C" int symgpu_mp_import_regions(symgpu_ctx* c, const double* recv_regions, int cap_per_peer) {
+  if (!c || !c->mp.on || !recv_regions || cap_per_peer <= 0) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  const int W = c->mp.world;
+  std::vector<double> cnt(W, 0.0);
+  CK(cudaMemcpy2DAsync(cnt.data(), sizeof(double), recv_regions + 15, (size_t)cap_per_peer * kMigD * sizeof(double), sizeof(double), W, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int q = 0; q < W; q++) {
+    if (q == c->mp.rank) continue;
+    const int n_rows = (int)cnt[q];
+    if (n_rows <= 0) continue;
+    if (n_rows > cap_per_peer) { g_err = "migration region overflow"; return SYMGPU_E_CAPACITY; }
+    const int reuse = std::min(n_rows, c->mp.free_count);
+    if (c->n_slots + (n_rows - reuse) > c->pool_base) { g_err = "vehicle capacity exhausted (set SYMGPU_CAPACITY)"; return SYMGPU_E_CAPACITY; }
+    k_mp_unpack_migrants<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, n_rows, recv_regions + (size_t)q * cap_per_peer * kMigD, c->mp.d_free.p, c->mp.free_count, reuse); LAUNCH(c);
+    c->mp.free_count -= reuse; c->n_slots += n_rows - reuse; c->n_alive += n_rows;
+  }
+  CK(cudaEventRecord(c->ev1, c->stream)); CK(cudaEventSynchronize(c->ev1));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms;
+  return c->n_alive;
+}
 extern "C" int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows) {
   if (!c || !c->mp.on || n_rows < 0) return SYMGPU_E_ARG;
   CK(cudaSetDevice(c->device));

@@ -42,6 +42,7 @@ def bind_mp(L):
     L.symgpu_mp_step_front.argtypes = [vp, vp]
     L.symgpu_mp_step_back.argtypes = [vp, vp, vp, ci, vp]
     L.symgpu_mp_import.argtypes = [vp, vp, ci]
+    L.symgpu_mp_import_regions.argtypes = [vp, vp, ci]
     L.symgpu_set_stream.argtypes = [vp, vp]
     L.symgpu_mp_has_origins.argtypes = [vp]
     L.symgpu_mp_local_draws.argtypes = [vp]
@@ -87,6 +88,9 @@ class RankEngine:
 
     def commit_draws(self, total: int):
         self.e._chk(self.L.symgpu_mp_commit_draws(self.e.h, int(total)))
+
+    def import_regions(self) -> int:
+        return self.e._chk(self.L.symgpu_mp_import_regions(self.e.h, C.c_void_p(self.recv_regions.data_ptr()), self.cap))
 
     def import_rows(self, n_rows: int) -> int:
         return self.e._chk(self.L.symgpu_mp_import(self.e.h, C.c_void_p(self.recv_rows.data_ptr()), n_rows))
@@ -154,18 +158,21 @@ class DistributedRun:
         self.r = RankEngine(pkg, flat_path, self.rank, self.world, node_part, device, cap_per_peer)
         # the engine runs on torch's current stream: its kernels and the NCCL collectives are ordered on the device, no host sync between them
         self.r.e._chk(self.r.L.symgpu_set_stream(self.r.e.h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        self._tail_in = [int(c) * TAIL_D for c in self.r.export_cnt]
+        self._tail_out = [int(c) * TAIL_D for c in self.r.halo_cnt]
+        self._tail_in_n, self._tail_out_n = sum(self._tail_in), sum(self._tail_out)
 
     def step(self) -> int:
         r, torch, dist = self.r, self.torch, self.dist
         r.front()
-        exchange_tails_dist(dist, r.send_tails, r.recv_tails, r.export_cnt, r.halo_cnt)
+        dist.all_to_all_single(r.recv_tails[: self._tail_out_n], r.send_tails[: self._tail_in_n], output_split_sizes=self._tail_out, input_split_sizes=self._tail_in)
         r.back()
-        n = exchange_rows_fixed(dist, torch, r.send_rows, r.recv_regions, r.recv_rows, r.cap, self.rank, self.world)
+        dist.all_to_all_single(r.recv_regions, r.send_rows)     # per-peer regions of migrating vehicles, row counts inside (k_mp_row_counts)
         if r.has_origins:                             # one global random sequence: the ranks' device draws of this step, summed
             t = torch.tensor([r.local_draws()], dtype=torch.int64, device=r.send_rows.device)
             dist.all_reduce(t)
             r.commit_draws(int(t.item()))
-        return r.import_rows(n)
+        return r.import_regions()
 
 
 class LocalGroup:
