@@ -66,6 +66,12 @@ int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows);       
 int symgpu_mp_import_regions(symgpu_ctx* c, const double* recv_regions, int cap_per_peer);   /* the receive buffer of the fixed-size all_to_all as it is (world regions of cap_per_peer rows) */
 /* Origins in a partitioned run: every rank replays the creation draws of all origins (same seed, same ids) and keeps the vehicles of
    the entry lanes it owns; the device's own draws of the step are summed over the ranks by the caller and committed on every rank. */
+/* Tail exchange over peer memory (NVLink, CUDA IPC) instead of a collective: _handle returns this rank's 64-byte IPC handle (and its
+   halo size); _connect takes the world's handles, and per peer q the offset (in records) of this rank's lanes inside q's halo and q's
+   halo size.  Afterwards symgpu_mp_step_front stores the tails into the peers and symgpu_mp_step_back waits for theirs on the device;
+   send_tails / recv_tails are ignored. */
+int symgpu_mp_p2p_handle(symgpu_ctx* c, void* handle64);
+int symgpu_mp_p2p_connect(symgpu_ctx* c, const void* handles, const int* peer_halo_off, const int* peer_n_halo);
 int symgpu_set_stream(symgpu_ctx* c, void* cuda_stream);   /* run on the caller's stream (cudaStream_t), e.g. the one its collectives are ordered on */
 int symgpu_mp_has_origins(symgpu_ctx* c);
 long symgpu_mp_local_draws(symgpu_ctx* c);

@@ -371,6 +371,41 @@ __global__ void k_mp_pack_tails(DevVeh V, const int* export_lanes, int n, const 
   if (t < 0) { o[0] = __hiloint2double(0, -1); o[1] = 0; o[2] = 0; o[3] = 0; }
   else { o[0] = __hiloint2double(V.cls[t], V.id[t]); o[1] = V.pos[t]; o[2] = V.vit[t]; o[3] = 0; }
 }
+// Tail exchange over peer memory (NVLink): the pack kernel stores every record straight into the halo area of the GPU that looks into
+// the lane (exp_dst[k], opened through CUDA IPC) and the last block to finish publishes the step's sequence number in that GPU's flag
+// slot (system-scope fence by every thread before the block counts itself done, release store of the flag) — no collective, no host.
+__global__ void k_mp_pack_tails_p2p(DevVeh V, const int* export_lanes, int n, const int* lane_tail, double* const* exp_dst, unsigned* done_ctr,
+                                    unsigned long long* const* flag_dst, int world, unsigned long long seq) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) {
+    int t = lane_tail[export_lanes[k]];
+    double* o = exp_dst[k];
+    if (t < 0) { o[0] = __hiloint2double(0, -1); o[1] = 0; o[2] = 0; o[3] = 0; }
+    else { o[0] = __hiloint2double(V.cls[t], V.id[t]); o[1] = V.pos[t]; o[2] = V.vit[t]; o[3] = 0; }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(done_ctr, 1u);
+    if (t == gridDim.x - 1) {
+      *done_ctr = 0;
+      __threadfence_system();
+      for (int q = 0; q < world; q++) if (flag_dst[q]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag_dst[q]), "l"(seq) : "memory");
+    }
+  }
+}
+// the GPU that looks into the lanes: waits until every peer it has a halo from has published this step (bounded: ~2 s, then an error)
+__global__ void k_mp_wait_tails(const unsigned long long* flags, const int* halo_off, int world, unsigned long long seq, int* err) {
+  int q = threadIdx.x;
+  if (q >= world || halo_off[q + 1] == halo_off[q]) return;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + q) : "memory");
+    if (v >= seq) break;
+    if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1); break; }
+  }
+}
 __global__ void k_mp_unpack_ghosts(DevVeh V, const int* halo_lanes, int n, int ghost_base, int* lane_tail, const double* in) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -492,7 +527,10 @@ struct symgpu_ctx {
   struct StepScratch { std::vector<EntryDesc> desc; std::vector<EntryLane*> desc_lane; int n = 0, n_sorted = 0; bool has_entries = false; } ss;
   // partitioned runs (one process per GPU): lane ownership, halo (ghost tail vehicles) and migration lists
   struct Mp { bool on = false; int rank = 0, world = 1, ghost_base = 0, n_halo = 0, n_export = 0; std::vector<int> lane_owner, halo_lanes, halo_off, export_lanes, export_off;
-    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count, d_free; int free_count = 0; int mig_cap = 0; std::vector<int> h_mig_count; unsigned draw_delta = 0; } mp;
+    DBuf<int> d_lane_owner, d_halo_lanes, d_export_lanes, d_export_peer, d_mig_count, d_free; int free_count = 0; int mig_cap = 0; std::vector<int> h_mig_count; unsigned draw_delta = 0;
+    // tail exchange over peer memory: halo area (n_halo records of 4 doubles) + one flag per peer, exported through CUDA IPC
+    struct P2p { bool on = false; DBuf<unsigned long long> area; std::vector<void*> peer; DBuf<double*> exp_dst; DBuf<unsigned long long*> flag_dst; DBuf<unsigned> done; DBuf<int> d_halo_off, err;
+      unsigned long long seq = 0; } p2p; } mp;
   int* h_stat = nullptr;   // pinned: [0..3] stat, [4] n_exited, [5] n_alive, [6] err, [7] draws, [8] first
 };
 
@@ -675,6 +713,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
 }
 
 extern "C" void symgpu_destroy(symgpu_ctx* c) {
+  if (c) for (void* p : c->mp.p2p.peer) if (p) cudaIpcCloseMemHandle(p);
   if (c && c->traj_host_n && getenv("SYMGPU_TIMING")) fprintf(stderr, "symgpu: trajectory enqueue %.1f us of host time per call (%ld calls)\n", c->traj_host_us / c->traj_host_n, c->traj_host_n);
   if (!c) return;
   cudaSetDevice(c->device);
@@ -1069,6 +1108,38 @@ extern "C" int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int
   return c->n_alive;
 }
 // entries (tail records of 4 doubles) this rank sends to / receives from every peer each step
+// tail exchange over peer memory, set-up: (1) every rank allocates its halo area + flags and hands out a CUDA IPC handle (64 bytes);
+// (2) the caller gathers the handles and, per peer q, where this rank's records start inside q's area (q's halo offset of this rank)
+// and q's halo size; the engine opens the peers' areas and precomputes the destination of every exported record.
+extern "C" int symgpu_mp_p2p_handle(symgpu_ctx* c, void* handle64) {
+  if (!c || !c->mp.on || !handle64) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  auto& m = c->mp; auto& pp = m.p2p;
+  CK(pp.area.alloc(4 * (size_t)m.n_halo + m.world + 1));
+  cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, pp.area.p));
+  static_assert(sizeof(h) == 64, "CUDA IPC handle is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return m.n_halo;
+}
+extern "C" int symgpu_mp_p2p_connect(symgpu_ctx* c, const void* handles, const int* peer_halo_off, const int* peer_n_halo) {
+  if (!c || !c->mp.on || !handles || !peer_halo_off || !peer_n_halo || !c->mp.p2p.area.p) return SYMGPU_E_ARG;
+  CK(cudaSetDevice(c->device));
+  auto& m = c->mp; auto& pp = m.p2p;
+  pp.peer.assign(m.world, nullptr);
+  std::vector<double*> dst(std::max(1, m.n_export), nullptr); std::vector<unsigned long long*> fl(m.world, nullptr);
+  for (int q = 0; q < m.world; q++) {
+    const int ne = m.export_off[q + 1] - m.export_off[q];
+    if (q == m.rank || ne == 0) continue;
+    cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + 64 * (size_t)q, 64);
+    CK(cudaIpcOpenMemHandle(&pp.peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+    double* base = (double*)pp.peer[q];
+    for (int j = 0; j < ne; j++) dst[m.export_off[q] + j] = base + 4 * ((size_t)peer_halo_off[q] + j);
+    fl[q] = (unsigned long long*)pp.peer[q] + 4 * (size_t)peer_n_halo[q] + m.rank;
+  }
+  CK(pp.exp_dst.upload(dst)); CK(pp.flag_dst.upload(fl)); CK(pp.done.alloc(1)); CK(pp.err.alloc(1)); CK(pp.d_halo_off.upload(m.halo_off));
+  pp.on = true;
+  return SYMGPU_OK;
+}
 extern "C" int symgpu_mp_sizes(symgpu_ctx* c, int* export_cnt, int* halo_cnt) {
   if (!c || !c->mp.on) return SYMGPU_E_ARG;
   for (int q = 0; q < c->mp.world; q++) { if (export_cnt) export_cnt[q] = c->mp.export_off[q + 1] - c->mp.export_off[q]; if (halo_cnt) halo_cnt[q] = c->mp.halo_off[q + 1] - c->mp.halo_off[q]; }
@@ -1082,7 +1153,10 @@ extern "C" int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails) {
   int rc = step_front(c); if (rc != SYMGPU_OK) return rc;
   if (c->mp.n_export) {
     if (c->ss.n == 0) CK(cudaMemsetAsync(c->lane_tail.p, 0xff, c->net.n_lanes() * sizeof(int), c->stream));
-    k_mp_pack_tails<<<(c->mp.n_export + 255) / 256, 256, 0, c->stream>>>(c->dv, c->mp.d_export_lanes.p, c->mp.n_export, c->lane_tail.p, send_tails); LAUNCH(c); }
+    if (c->mp.p2p.on) { auto& pp = c->mp.p2p; pp.seq++;
+      k_mp_pack_tails_p2p<<<(c->mp.n_export + 255) / 256, 256, 0, c->stream>>>(c->dv, c->mp.d_export_lanes.p, c->mp.n_export, c->lane_tail.p, pp.exp_dst.p, pp.done.p, pp.flag_dst.p, c->mp.world, pp.seq); LAUNCH(c); }
+    else { k_mp_pack_tails<<<(c->mp.n_export + 255) / 256, 256, 0, c->stream>>>(c->dv, c->mp.d_export_lanes.p, c->mp.n_export, c->lane_tail.p, send_tails); LAUNCH(c); } }
+  else if (c->mp.p2p.on) c->mp.p2p.seq++;
   if (!c->ext_stream) CK(cudaStreamSynchronize(c->stream));   // on the caller's stream the collective that follows is ordered after the pack
   return SYMGPU_OK;
 }
@@ -1093,8 +1167,12 @@ extern "C" int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, doub
   CK(cudaSetDevice(c->device));
   auto& m = c->mp;
   if (c->ss.n == 0) CK(cudaMemsetAsync(c->lane_tail.p, 0xff, c->net.n_lanes() * sizeof(int), c->stream));
+  if (m.n_halo && m.p2p.on) {
+    k_mp_wait_tails<<<1, 32, 0, c->stream>>>(m.p2p.area.p + 4 * (size_t)m.n_halo, m.p2p.d_halo_off.p, m.world, m.p2p.seq, m.p2p.err.p); LAUNCH(c);
+    recv_tails = (const double*)m.p2p.area.p; }
   if (m.n_halo) { k_mp_unpack_ghosts<<<(m.n_halo + 255) / 256, 256, 0, c->stream>>>(c->dv, m.d_halo_lanes.p, m.n_halo, m.ghost_base, c->lane_tail.p, recv_tails); LAUNCH(c); }
   int r = step_back(c); if (r < 0) return r;
+  if (m.p2p.on) { int e = 0; CK(cudaMemcpy(&e, m.p2p.err.p, sizeof(int), cudaMemcpyDeviceToHost)); if (e) { g_err = "tail exchange over peer memory timed out"; return SYMGPU_E_CUDA; } }
   CK(cudaMemsetAsync(m.d_mig_count.p, 0, (m.world + 1) * sizeof(int), c->stream));
   if (c->n_slots) { k_mp_pack_migrants<<<(c->n_slots + 255) / 256, 256, 0, c->stream>>>(c->dv, c->n_slots, m.d_lane_owner.p, m.rank, cap_per_peer, m.d_mig_count.p, send_rows,
                                                                                   m.d_free.p, m.free_count, &m.d_mig_count.p[m.world]); LAUNCH(c); }

@@ -17,6 +17,7 @@ estimated leader speed (NewellCarFollowing.cpp:217-230); the oracle has the same
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Sequence
 
 import numpy as np
@@ -44,6 +45,8 @@ def bind_mp(L):
     L.symgpu_mp_import.argtypes = [vp, vp, ci]
     L.symgpu_mp_import_regions.argtypes = [vp, vp, ci]
     L.symgpu_set_stream.argtypes = [vp, vp]
+    L.symgpu_mp_p2p_handle.argtypes = [vp, vp]
+    L.symgpu_mp_p2p_connect.argtypes = [vp, vp, vp, vp]
     L.symgpu_mp_has_origins.argtypes = [vp]
     L.symgpu_mp_local_draws.argtypes = [vp]
     L.symgpu_mp_local_draws.restype = C.c_long
@@ -158,6 +161,31 @@ class DistributedRun:
         self.r = RankEngine(pkg, flat_path, self.rank, self.world, node_part, device, cap_per_peer)
         # the engine runs on torch's current stream: its kernels and the NCCL collectives are ordered on the device, no host sync between them
         self.r.e._chk(self.r.L.symgpu_set_stream(self.r.e.h, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        # SYMGPU_P2P=1: tails travel over peer memory (NVLink) instead of an NCCL all_to_all: every rank exports its halo area through
+        # CUDA IPC, the pack kernel of a peer stores straight into it and raises a flag (engine.cu: k_mp_pack_tails_p2p /
+        # k_mp_wait_tails).  Bit-identical state (tests/try_mp_timing.py: exact state hash, N=2) and the same step time as the collective
+        # (N=2 0.97 vs 0.97 ms, N=4 1.09 vs 1.06): on the caller's stream the collective's latency already hides behind the lane
+        # ordering, so the collective stays the default until the migration exchange goes over peer memory too.
+        self.p2p = os.environ.get("SYMGPU_P2P", "0") == "1" and self.world > 1
+        if self.p2p:
+            r = self.r
+            h = C.create_string_buffer(64)
+            ok = r.L.symgpu_mp_p2p_handle(r.e.h, h) >= 0
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (h.raw, [int(c) for c in r.halo_cnt], ok))
+            if all(g[2] for g in gathered):
+                handles = b"".join(g[0] for g in gathered)
+                peer_off = np.array([sum(g[1][: self.rank]) for g in gathered], np.int32)   # where this rank's lanes start in peer q's halo
+                peer_n = np.array([sum(g[1]) for g in gathered], np.int32)
+                ok = r.L.symgpu_mp_p2p_connect(r.e.h, handles, peer_off.ctypes.data_as(C.c_void_p), peer_n.ctypes.data_as(C.c_void_p)) >= 0
+            else:
+                ok = False
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok)
+            if not all(flags):                         # a peer could not be mapped (no peer access between two GPUs): everybody uses the collective
+                raise pkg.SymGpuError("tail exchange over peer memory could not be set up on every rank (set SYMGPU_P2P=0 to use the NCCL all_to_all): "
+                                      + r.L.symgpu_last_error().decode())
+            dist.barrier()
         self._tail_in = [int(c) * TAIL_D for c in self.r.export_cnt]
         self._tail_out = [int(c) * TAIL_D for c in self.r.halo_cnt]
         self._tail_in_n, self._tail_out_n = sum(self._tail_in), sum(self._tail_out)
@@ -165,7 +193,8 @@ class DistributedRun:
     def step(self) -> int:
         r, torch, dist = self.r, self.torch, self.dist
         r.front()
-        dist.all_to_all_single(r.recv_tails[: self._tail_out_n], r.send_tails[: self._tail_in_n], output_split_sizes=self._tail_out, input_split_sizes=self._tail_in)
+        if not self.p2p:
+            dist.all_to_all_single(r.recv_tails[: self._tail_out_n], r.send_tails[: self._tail_in_n], output_split_sizes=self._tail_out, input_split_sizes=self._tail_in)
         r.back()
         dist.all_to_all_single(r.recv_regions, r.send_rows)     # per-peer regions of migrating vehicles, row counts inside (k_mp_row_counts)
         if r.has_origins:                             # one global random sequence: the ranks' device draws of this step, summed

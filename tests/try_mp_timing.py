@@ -55,6 +55,14 @@ print(f"rank {rank}: max rows to one peer {MAXC}; {1e3 * tot / steps:.3f} ms/ste
 st = r.e.state()
 chk = torch.tensor([float(len(st["id"])), float(st["id"].astype("float64").sum()), float(st["pos"].sum()), float(st["vit"].sum())], dtype=torch.float64, device="cuda")
 dist.all_reduce(chk)
+import numpy as np
+key = (2 * st["id"].astype(np.int64) + 1)
+hx = int(np.bitwise_xor.reduce(st["vit"].view(np.int64) * key)) ^ int(np.bitwise_xor.reduce(st["pos"].view(np.int64) * key)) if len(key) else 0
+allh = [None] * world
+dist.all_gather_object(allh, hx)
 if rank == 0:
-    print("rank 0 checksum", [repr(float(x)) for x in chk], flush=True)
+    tot = 0
+    for v in allh:
+        tot ^= v
+    print("rank 0 checksum", [repr(float(x)) for x in chk], "exact state hash", hex(tot & 0xffffffffffffffff), flush=True)
 dist.destroy_process_group()
