@@ -236,17 +236,13 @@ class LocalGroup:
             for r in self.ranks:
                 r.commit_draws(draws)
         total = 0
-        for dst in self.ranks:
-            off = 0
+        for dst in self.ranks:                       # migrating vehicles: the sender's region for dst -> dst's region for the sender, as the
+            W = dst.cap * ROW_D                      # fixed-size all_to_all delivers them (row counts inside); imported like DistributedRun does
             for src in self.ranks:
-                if src is dst:
-                    continue
-                k = int(src.send_counts[dst.rank])
-                if k:
-                    dst.recv_rows[off: off + k * ROW_D].copy_(src.send_rows[dst.rank * src.cap * ROW_D: (dst.rank * src.cap + k) * ROW_D])
-                    off += k * ROW_D
+                if src is not dst:
+                    dst.recv_regions[src.rank * W: (src.rank + 1) * W].copy_(src.send_rows[dst.rank * W: (dst.rank + 1) * W])
             torch.cuda.synchronize()
-            total += dst.import_rows(off // ROW_D)
+            total += dst.import_regions()
         return total
 
     def state(self):
