@@ -966,7 +966,7 @@ static int step_back(symgpu_ctx* c) {
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
-    KBEGIN(c, KID_SEG); k_seg<<<G(L), B, 0, s>>>(c->dv, c->df, L, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
+    KBEGIN(c, KID_SEG); k_seg<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, c->s_lane.p, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
     // leader loops: always looked for (the segment graph is small), cut where the reference's recursion would cut them
     { int Klev = 1; while ((1LL << (2 * Klev)) * kCycWalk < (long long)std::max(4, n_sorted)) Klev++;   // 4^K * walk >= longest possible chain
       Klev++;

@@ -38,44 +38,50 @@ struct DevFlow {
   unsigned long long* rootkey;
 };
 
-// per lane: segments, front -> rear
 // `by_id`: m_LstVehicles order is the slot order on one GPU; in a partitioned run slots are local, so the vehicle id is the key
 // (pre-seeded vehicles are listed in id order, reseau.cpp:1293-1340).
 __device__ __forceinline__ int list_key(const DevVeh& V, int x, int by_id) { return by_id ? V.id[x] : x; }
-__global__ void k_seg(DevVeh V, DevFlow F, int n_lanes, const int* lane_count, const int* lane_start, int by_id) {
-  int ln = blockIdx.x * blockDim.x + threadIdx.x;
-  int n = ln < n_lanes ? lane_count[ln] : 0;
-  int s = n ? lane_start[ln] : 0;
-  int cur = -1, nseg = 0, len = 0, mn = 0x7fffffff, mnx = -1;
-  for (int a = n - 1; a >= 0; a--) {
-    int p = s + a; int x = F.order[p];
+// One thread per position of the lane order.  A position is a segment FRONT when it is the last of its lane or its vehicle does not
+// follow the vehicle directly ahead; the front's thread then walks its segment towards the rear (a handful of vehicles), gives every
+// member the segment's position and finds the member that comes first in m_LstVehicles (the loop-cutting rule needs it).
+__global__ void k_seg(DevVeh V, DevFlow F, int n_sorted, const int* slane, const int* lane_count, const int* lane_start, int by_id) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool front = false;
+  if (p < n_sorted) {
+    const int ln = slane[p]; const int s = lane_start[ln]; const int last = s + lane_count[ln] - 1;
+    const int x = F.order[p];
     int d = V.ctx_leader[x];
-    bool front = (a == n - 1) || d != F.order[p + 1];
-    if (d >= 0 && V.status[d] == ST_GHOST) d = -1;          // leader on another GPU: estimated speed, no dependency
+    front = p == last || d != F.order[p + 1];
     if (front) {
-      if (cur >= 0) { F.seg_len[cur] = len; F.minslot[cur] = mnx; }
-      cur = p; len = 0; mn = 0x7fffffff; mnx = -1; nseg++;
-      F.isfront[p] = 1; F.seg_dep[p] = d;
-    } else F.isfront[p] = 0;
-    F.segpos[x] = cur; F.cut[x] = 0;
-    len++; { int k = list_key(V, x, by_id); if (k < mn) { mn = k; mnx = x; } }
+      if (d >= 0 && V.status[d] == ST_GHOST) d = -1;          // leader on another GPU: estimated speed, no dependency
+      F.seg_dep[p] = d;
+      int mn = list_key(V, x, by_id), mnx = x;
+      F.segpos[x] = p;
+      for (int q = p - 1; q >= s; q--) {                      // members: positions below the front whose vehicle follows the one directly ahead
+        const int y = F.order[q];
+        if (V.ctx_leader[y] != F.order[q + 1]) break;
+        F.segpos[y] = p;
+        const int k = list_key(V, y, by_id); if (k < mn) { mn = k; mnx = y; }
+      }
+      F.minslot[p] = mnx;
+    }
   }
-  if (n) { F.seg_len[cur] = len; F.minslot[cur] = mnx; }
   // compact list of the segment fronts (any order): one atomic per warp
-  const int lane = threadIdx.x & 31;
-  int inc = nseg;
-  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-  int base = 0;
-  if (lane == 31 && inc) base = atomicAdd(&F.ctl->n_segments, inc);
-  base = __shfl_sync(0xffffffffu, base, 31) + inc - nseg;
-  for (int a = n - 1; a >= 0; a--) if (F.isfront[s + a]) F.fronts[base++] = s + a;
+  const unsigned m = __ballot_sync(0xffffffffu, front);
+  if (m) { const int lane = threadIdx.x & 31; int base = 0;
+    if (lane == 0) base = atomicAdd(&F.ctl->n_segments, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (front) F.fronts[base + __popc(m & ((1u << lane) - 1))] = p; }
 }
 
 // one relaxation sweep.  first: every vehicle, and the dependency (order position -> leader slot, -1 = none / cut / ghost)
 // is cached; later sweeps only look at the leader's speed again.  `prev` = changes counted by the sweep before.
 // Leaders are mostly the neighbour in the lane order, i.e. in the same warp: every warp repeats its part until
 // nothing in it changes (kLocalIters at most), so a global sweep carries a change down whole segments, not one vehicle.
-constexpr int kLocalIters = 48;
+#ifndef SYM_LOCAL_ITERS
+#define SYM_LOCAL_ITERS 48
+#endif
+constexpr int kLocalIters = SYM_LOCAL_ITERS;
 #ifndef SYM_RELAX_BLOCKS
 #define SYM_RELAX_BLOCKS 8   // 128 threads x 8 blocks per SM, 64 registers (C4, ms per step: 256x3 0.38, 256x5 0.32, 128x10 0.30, 128x8 0.297, 512x2 0.35)
 #endif
