@@ -44,10 +44,9 @@ int symgpu_run(symgpu_ctx* c, int n_steps);
  * Vehicule::SortieTrafic (vehicule.cpp:1993-2176) hands to DocTrafic::AddTrajectoire.  Returns rows written. */
 int symgpu_step_traj(symgpu_ctx* c, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
 
-/* Asynchronous form (north_star: "trajectory output is copied back asynchronously on a side stream"): bind two caller
- * buffers once (they are page-locked in place), then alternate them; the copy of step k overlaps the computation of k+1. */
-/* `which` = 0..3: two buffers let the consumer lag one step (the copy must then end inside the next step); three in rotation let
-   it lag two, so that a copy never stalls the stepping loop. */
+/* Asynchronous form (north_star: "trajectory output is copied back asynchronously on a side stream"): bind caller buffers once
+ * (they are page-locked in place), then rotate them; the rows of step k are packed and copied on a side stream beside step k+1.
+ * `which` = 0..3: two buffers let the consumer lag one step, three in rotation two. */
 int symgpu_traj_bind(symgpu_ctx* c, int which, int cap, int* id, int* lane, double* pos, double* vit, double* acc);
 int symgpu_step_traj_async(symgpu_ctx* c, int which);   /* returns rows, valid after symgpu_traj_wait(which) */
 int symgpu_traj_wait(symgpu_ctx* c, int which);
@@ -64,8 +63,6 @@ int symgpu_mp_step_front(symgpu_ctx* c, double* send_tails);
 int symgpu_mp_step_back(symgpu_ctx* c, const double* recv_tails, double* send_rows, int cap_per_peer, int* send_counts);
 int symgpu_mp_import(symgpu_ctx* c, const double* recv_rows, int n_rows);          /* rows of 16 doubles */
 int symgpu_mp_import_regions(symgpu_ctx* c, const double* recv_regions, int cap_per_peer);   /* the receive buffer of the fixed-size all_to_all as it is (world regions of cap_per_peer rows) */
-/* Origins in a partitioned run: every rank replays the creation draws of all origins (same seed, same ids) and keeps the vehicles of
-   the entry lanes it owns; the device's own draws of the step are summed over the ranks by the caller and committed on every rank. */
 /* Tail exchange over peer memory (NVLink, CUDA IPC) instead of a collective: _handle returns this rank's 64-byte IPC handle (and its
    halo size); _connect takes the world's handles, and per peer q the offset (in records) of this rank's lanes inside q's halo and q's
    halo size.  Afterwards symgpu_mp_step_front stores the tails into the peers and symgpu_mp_step_back waits for theirs on the device;
@@ -73,11 +70,14 @@ int symgpu_mp_import_regions(symgpu_ctx* c, const double* recv_regions, int cap_
 int symgpu_mp_p2p_handle(symgpu_ctx* c, void* handle64);
 int symgpu_mp_p2p_connect(symgpu_ctx* c, const void* handles, const int* peer_halo_off, const int* peer_n_halo);
 int symgpu_set_stream(symgpu_ctx* c, void* cuda_stream);   /* run on the caller's stream (cudaStream_t), e.g. the one its collectives are ordered on */
+/* Origins in a partitioned run: every rank replays the creation draws of all origins (same seed, same ids) and keeps the vehicles of
+   the entry lanes it owns; the device's own draws of the step are summed over the ranks by the caller and committed on every rank. */
 int symgpu_mp_has_origins(symgpu_ctx* c);
 long symgpu_mp_local_draws(symgpu_ctx* c);
 int symgpu_mp_commit_draws(symgpu_ctx* c, long total_over_ranks);
 
-/* Per-kernel device timing (CUDA events on the step stream) for roofline accounting. */
+/* Per-kernel device timing (CUDA events on the step stream) for roofline accounting.  enable = 1: every kernel group of a step is
+   bracketed (breakdown); 2: only the relaxation sweeps (the dominant kernel, timed inside a measured region); 0: off. */
 int symgpu_profile(symgpu_ctx* c, int enable);
 int symgpu_kernel_count(void);
 const char* symgpu_kernel_name(int k);
