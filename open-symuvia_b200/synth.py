@@ -60,6 +60,11 @@ class NetBuilder:
         self.exits: List[Tuple[int, int, float]] = []
         self.iv_i: List[List[int]] = []
         self.iv_f: List[List[float]] = []
+        # merge points (row A10): Convergent objects in Reseau::Liste_convergents order (std::map by id, reseau.h:201)
+        self.cvgs: List[dict] = []
+        self.caf_mvts: List[Tuple[int, int, int, List[int]]] = []   # CarrefourAFeuxEx::m_LstMouvements: node, entry link, exit link, internal links
+        self.link_cam: Dict[int, List[int]] = {}   # link -> m_LstTuyAm of its upstream connection (reference order)
+        self.link_cav: Dict[int, List[int]] = {}   # link -> m_LstTuyAv of its downstream connection
 
     # -- topology ---------------------------------------------------------------------------
     def add_class(self, c: dict) -> int:
@@ -119,6 +124,16 @@ class NetBuilder:
     def add_exit(self, node: int, link: int, capacity=-1.0) -> int:
         self.exits.append((node, link, capacity))
         return len(self.exits) - 1
+
+    def add_convergent(self, name: str, node: int, down_link: int, am_links: List[int], points: List[dict], tagreg=30.0, gamma=1.0,
+                       mu=1.0, pos_cpt_av=5.0, tf: Optional[List[float]] = None) -> dict:
+        """One `Convergent` (convergent.cpp:159-255): `points` = one dict per lane of the downstream link,
+        {down_lane, vam: [(upstream lane, reference priority level)]} in `m_LstVAm` order; `am_links` = `m_LstTuyAm` order
+        (one ponctual sensor each at length - 5, FinInit :230-255); sensor of the downstream link at `pos_cpt_av`."""
+        c = dict(name=name, node=node, down_link=down_link, am_links=list(am_links), points=points, tagreg=tagreg, gamma=gamma, mu=mu,
+                 pos_cpt_av=pos_cpt_av, tf=tf)
+        self.cvgs.append(c)
+        return c
 
     def add_init_vehicle(self, cls: int, lane: int, route: int, route_pos: int, pos: float, v: float,
                          a: float = 0.0):
@@ -191,7 +206,40 @@ class NetBuilder:
         def names(lst):
             return np.frombuffer(("\0".join(lst) + "\0").encode(), np.uint8)
 
-        return {
+        # merge points: convergents sorted by id like std::map<std::string, Convergent*> (reseau.cpp:14310)
+        cv = sorted(self.cvgs, key=lambda c: c["name"].encode())
+        cvg_i, cvg_f, cvg_tf, cvgam, pt_i, ptam_i = [], [], [], [], [], []
+        for ci, c in enumerate(cv):
+            cvg_i.append([c["node"], c["down_link"], len(pt_i), len(c["points"]), len(cvgam), len(c["am_links"]), 0, 0])
+            cvg_f.append([c["tagreg"], c["gamma"], c["mu"], c["pos_cpt_av"]])
+            cvg_tf.extend(c["tf"] or [0.0] * T)
+            cvgam.extend(c["am_links"])
+            for pt in c["points"]:
+                pt_i.append([ci, pt["down_lane"], len(ptam_i), len(pt["vam"])])
+                ptam_i.extend([[ln, niv] for (ln, niv) in pt["vam"]])
+        mv_i, mv_l = [], []
+        for (node, a, o, tl) in self.caf_mvts:
+            mv_i.append([node, a, o, len(mv_l), len(tl)])
+            mv_l.extend(tl)
+        K = len(self.links)
+
+        def csr(d):
+            off = np.zeros(K + 1, np.int32)
+            flat: List[int] = []
+            for k in range(K):
+                flat.extend(d.get(k, []))
+                off[k + 1] = len(flat)
+            return off, np.asarray(flat, np.int32)
+        lcam_off, lcam = csr(self.link_cam)
+        lcav_off, lcav = csr(self.link_cav)
+        merge = {}
+        if cv or self.link_cam or self.link_cav:
+            merge = {"cvg_i": I(cvg_i, 8), "cvg_f": D(cvg_f, 4), "cvg_tf": D(cvg_tf), "cvgam_i": np.asarray(cvgam, np.int32),
+                     "pt_i": I(pt_i, 4), "ptam_i": I(ptam_i, 2), "cafmvt_i": I(mv_i, 5), "cafmvt_links": np.asarray(mv_l, np.int32),
+                     "lcam_off": lcam_off, "lcam_links": lcam, "lcav_off": lcav_off, "lcav_links": lcav,
+                     "names_cvg": names([c["name"] for c in cv])}
+
+        return {**merge,
             "params": self.params, "cls": cls,
             "link_i": I(self.links, F.LINK_I), "link_f": D(self.link_f, F.LINK_F),
             "link_geom": D(self.link_geom, 4),
@@ -264,13 +312,15 @@ _DNAME = "ENWS"
 def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, green=30.0, amber=3.0,
          n_steps=1800, dt=1.0, seed=42, demand_per_lane=0.2, demand_duration=1e12,
          preseed_per_lane=0.0, shuffle=False, classes=None, offsets=False, law=F.LAW_NEWELL,
-         ny: Optional[int] = None) -> NetBuilder:
+         ny: Optional[int] = None, merges=True) -> NetBuilder:
     """n x ny grid of CAF junctions (BASELINE configs C2/C4/C5).
 
     Every approach lane k may go straight / right / left into exit lane k (no U-turn);
     signals: sequence 0 serves the E/W-bound approaches, sequence 1 the N/S-bound ones.
     `preseed_per_lane` > 0 places that many vehicles on every non-stub external lane with
     staircase routes to the boundary (C4/C5: no demand, population steady over the run).
+    `merges`: every exit link fed by more than one internal link gets its `Convergent` (<CAF>_C0_<exit link>,
+    CarrefourAFeuxEx.cpp:489-919) with one merge point per exit lane — row A10; False reproduces the round-1 tables.
     """
     ny = n if ny is None else ny
     rng = np.random.default_rng(seed)
@@ -339,11 +389,21 @@ def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, 
                     continue
                 moves.append((node, i, j, a, o, din))
                 exit_in_count[o] = exit_in_count.get(o, 0) + n_lanes
+    # Signal plan entries per (entry link, exit link); internal links in the creation order of CarrefourAFeuxEx::Init
+    # (CarrefourAFeuxEx.cpp:331-480: m_mapMvtAutorises is ordered by entry-LANE label "<link>V<num+1>", then exit-link label, then
+    # exit lane), which fixes m_LstMouvements, Divergent::m_LstTuyAv, Convergent::m_LstTuyAm and PointDeConvergence::m_LstVAm order.
     for (node, i, j, a, o, din) in moves:
         ctrl = b.nodes[node][1]
         seq = 0 if din in (0, 2) else 1
         b.ctrl[ctrl]["seqs"][seq]["signals"].append((a, o, green, amber, 0.0))
+    by_node: Dict[int, list] = {}
+    for (node, i, j, a, o, din) in moves:
         for k in range(n_lanes):
+            by_node.setdefault(node, []).append((f"{b.link_names[a]}V{k + 1}", b.link_names[o], k, a, o, din))
+    for node in sorted(by_node):
+        ctrl = b.nodes[node][1]
+        feeds: Dict[int, List[Tuple[int, int]]] = {}        # exit link -> [(internal link, exit lane num)] in creation order
+        for (_, _, k, a, o, din) in sorted(by_node[node], key=lambda t: (t[0].encode(), t[1].encode(), t[2])):
             ax, ay = lane_pt(a, k, True)
             ox, oy = lane_pt(o, k, False)
             ln = math.hypot(ox - ax, oy - ay)
@@ -355,6 +415,40 @@ def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, 
             b.add_succ(ent_lane, o, b.lane_of(il, 0), 1.0, 1)
             b.add_succ(b.lane_of(il, 0), o, b.lane_of(o, k), 1.0, 1)
             b.add_stopline(ent_lane, b.lane_f[ent_lane], ctrl, a, k, o, k)
+            feeds.setdefault(o, []).append((il, k))
+            b.caf_mvts.append((node, a, o, [il]))
+            b.link_cam[il] = [a]                              # Divergent <CAF>_D0_<entry link>: one upstream link (:379-391)
+            b.link_cav.setdefault(a, []).append(il)           # pDiv->AddEltAval(pT) (:707)
+            b.link_cav[il] = [o]
+        if not merges:
+            continue
+        for o, lst in feeds.items():
+            b.link_cam[o] = [il for (il, _) in lst]           # pCvg->AddEltAmont(pT) (:708)
+            if len(lst) < 2:
+                continue                                      # one upstream link: converted to a Repartiteur (:860-905)
+            points = []
+            for kk in range(n_lanes):
+                vam = [b.lane_of(il, 0) for (il, k) in lst if k == kk]
+                # reference priority levels from the geometry (:1129-1166): upstream links sorted by AngleOfView seen from the
+                # exit lane's upstream end (exit lane's downstream end as first point), smallest angle = level n (lowest)
+                vx0, vy0 = lane_pt(o, kk, False)
+                vx1, vy1 = lane_pt(o, kk, True)
+                ang = {}
+                for ln_ in vam:
+                    gx0, gy0, _, _ = b.link_geom[b.lanes[ln_][0]]
+                    a1, a2, b1, b2 = vx1 - vx0, vy1 - vy0, gx0 - vx0, gy0 - vy0
+                    t = math.atan2(a1 * b2 - a2 * b1, a1 * b1 + a2 * b2) if (a1 * a1 + a2 * a2) and (b1 * b1 + b2 * b2) else 0.0
+                    if t < 0:
+                        t += 2 * math.pi
+                    assert t not in ang, "two upstream links seen under the same angle: std::map insert would drop one"
+                    ang[t] = ln_
+                niv = {}
+                lev = len(ang)
+                for t in sorted(ang):
+                    niv[ang[t]] = lev
+                    lev -= 1
+                points.append(dict(down_lane=b.lane_of(o, kk), vam=[(ln_, niv[ln_]) for ln_ in vam]))
+            b.add_convergent(f"{b.node_names[node]}_C0_{b.link_names[o]}", node, o, [il for (il, _) in lst], points)
 
     # routing helpers on the (link -> link) graph without U-turns
     nxt: Dict[int, List[int]] = {}

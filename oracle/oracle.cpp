@@ -126,11 +126,21 @@ struct Entry { int node, link; std::vector<std::pair<double, double>> demand; st
   std::vector<int> pret;                                           // m_mapVehPret[link][lane] (-1 none)
   std::vector<std::deque<Veh*>> attente; };                        // m_mapVehEnAttente[link][lane]
 struct Exit { int node, link; double capacity; };
+// ---- merge points (row A10): convergent.h, sensors/PonctualSensor.h, sensors/SensorsManager.h ----
+struct DesVoieAmont { int lane, niv, niv_ref; };                   // convergent.h DesVoieAmont
+struct PtCvg { int cvg, down_lane; std::vector<DesVoieAmont> vam;  // PointDeConvergence
+  double inst_last_passage = 0; int rand_numbers = 0; bool free_flow = true, insertion = false; };
+struct Capteur { int link; double pos; std::vector<double> cnt; }; // PonctualSensor::m_Data.pNbTypeVehInst [cls][lane][window]
+struct Cvg { int node, down_link; double tagreg, gamma, mu, pos_cpt_av; std::vector<double> tf; std::vector<int> pts, am_links;
+  std::vector<Capteur> cpt; int nb_inst = -1, last_ind = 0, window = 0;                      // SensorsManager::m_nNbInst (-1 at construction)
+  std::vector<Veh*> ins_veh; };                                    // ConnectionPonctuel::m_LstInsVeh
+struct CafMvt { int node, ent_link, exit_link; std::vector<int> tl; };   // CarrefourAFeuxEx MvtCAFEx (entry, exit, lstTMvt)
 
 // ---- car-following context: carFollowing/CarFollowingContext.h, NewellContext.h ---------------
 struct Ctx {
   std::vector<int> lanes; Veh* leader = nullptr; int leader_id = -1; double leader_dist = 0;
   double start_pos = 0; bool free_flow = true; double deltaN = 1; bool contraction = false;
+  bool post = false;                                               // CarFollowingContext::m_bIsPostProcessing
 };
 
 // ---- vehicle: vehicule.h:310-420 --------------------------------------------------------------
@@ -149,6 +159,8 @@ struct Veh {
   std::vector<int> tuyaux_parcourus;
   std::unique_ptr<Ctx> ctx, prev_ctx;
   bool in_list = false; int dead = 0;
+  int next_voie = -1;                                              // m_pNextVoie: set by ChangementVoie (vehicule.cpp:2700) and CalculVitesseLeader (convergent.cpp:1146), never reset
+  double res_tir_foll_int = -1;                                    // m_dbResTirFollInt (AbstractCarFollowing.cpp:484-497)
 };
 struct LessId { bool operator()(const Veh* a, const Veh* b) const { return a->id < b->id; } };   // tools.h:67-74
 
@@ -162,6 +174,12 @@ struct Sim {
   std::vector<Cls> cls; std::vector<Link> links; std::vector<Lane> lanes; std::vector<Ctrl> ctrls;
   std::vector<std::vector<int>> routes; std::vector<Entry> entries; std::vector<Exit> exits;
   std::vector<int> node_type, node_ctrl;
+  std::vector<Cvg> cvgs; std::vector<PtCvg> pts; std::vector<CafMvt> caf_mvts;              // Reseau::Liste_convergents in std::map (id) order
+  std::vector<int> link_cvg_aval;                                   // link -> Convergent that is its downstream connection (-1)
+  std::vector<std::vector<std::pair<int, int>>> link_capteurs;      // Tuyau::getListeCapteursConvergents: (cvg, sensor)
+  std::vector<std::vector<int>> lcam, lcav;                         // m_LstTuyAm of a link's upstream connection / m_LstTuyAv of its downstream one
+  long n_insertions = 0, n_refus = 0, n_pins = 0, n_cong = 0; double inst_cur = 0;
+  bool trace_ties = getenv("ORACLE_TRACE_TIES") != nullptr, trace_merge = getenv("ORACLE_TRACE_MERGE") != nullptr;
   // dynamic
   double t = 0; int ninst = 0; int last_id = 0; RandManager rnd;
   std::vector<Veh*> lst;                                           // m_LstVehicles (order is part of the contract)
@@ -226,6 +244,32 @@ struct Sim {
       x.pret.assign(nl, -1); x.attente.resize(nl);
       entries.push_back(std::move(x)); }
     lane_set.resize(lanes.size()); nb_entre.assign(links.size() * T, 0); nb_sorti.assign(links.size() * T, 0);
+    // merge points: Convergent::Init / FinInit (convergent.cpp:208-255), CarrefourAFeuxEx::Init (:489-919, :1129-1166)
+    link_cvg_aval.assign(links.size(), -1); link_capteurs.resize(links.size()); lcam.resize(links.size()); lcav.resize(links.size());
+    if (f.N("cvg_i")) {
+      const int* ci2 = f.I("cvg_i"); const double* cf2 = f.D("cvg_f"); const double* ctf = f.D("cvg_tf"); const int* cam = f.I("cvgam_i");
+      const int* pi = f.I("pt_i"); const int* pam = f.I("ptam_i");
+      for (size_t p = 0; p < f.N("pt_i") / 4; p++) { PtCvg x; x.cvg = pi[4 * p]; x.down_lane = pi[4 * p + 1];
+        for (int m = pi[4 * p + 2]; m < pi[4 * p + 2] + pi[4 * p + 3]; m++) x.vam.push_back({pam[2 * m], pam[2 * m + 1], pam[2 * m + 1]});
+        pts.push_back(std::move(x)); }
+      for (size_t c = 0; c < f.N("cvg_i") / 8; c++) { const int* r = ci2 + 8 * c; Cvg x; x.node = r[0]; x.down_link = r[1];
+        x.tagreg = cf2[4 * c]; x.gamma = cf2[4 * c + 1]; x.mu = cf2[4 * c + 2]; x.pos_cpt_av = cf2[4 * c + 3];
+        for (size_t t = 0; t < T; t++) x.tf.push_back(ctf[c * T + t]);
+        for (int p = r[2]; p < r[2] + r[3]; p++) x.pts.push_back(p);
+        for (int a = r[4]; a < r[4] + r[5]; a++) x.am_links.push_back(cam[a]);
+        x.window = (int)(x.tagreg / dt);                                                       // PonctualSensor::InitData :131
+        auto add = [&](int link, double pos) { Capteur k; k.link = link; k.pos = pos; k.cnt.assign(T * links[link].n_lanes * x.window, 0.0);
+          link_capteurs[link].push_back({(int)c, (int)x.cpt.size()}); x.cpt.push_back(std::move(k)); };
+        add(x.down_link, x.pos_cpt_av);                                                        // "CptTav"
+        for (int a : x.am_links) { add(a, links[a].length - 5); link_cvg_aval[a] = (int)c; }   // "CptAm" at length - 5
+        cvgs.push_back(std::move(x)); }
+      const int* mi = f.I("cafmvt_i"); const int* ml = f.I("cafmvt_links");
+      for (size_t m = 0; m < f.N("cafmvt_i") / 5; m++) { CafMvt x{mi[5 * m], mi[5 * m + 1], mi[5 * m + 2], {}};
+        for (int q = mi[5 * m + 3]; q < mi[5 * m + 3] + mi[5 * m + 4]; q++) x.tl.push_back(ml[q]);
+        caf_mvts.push_back(std::move(x)); }
+    }
+    if (f.N("lcam_off")) { const int* o = f.I("lcam_off"); const int* l = f.I("lcam_links"); for (size_t k = 0; k < links.size(); k++) lcam[k].assign(l + o[k], l + o[k + 1]); }
+    if (f.N("lcav_off")) { const int* o = f.I("lcav_off"); const int* l = f.I("lcav_links"); for (size_t k = 0; k < links.size(); k++) lcav[k].assign(l + o[k], l + o[k + 1]); }
     // Reseau::GetMinKv reseau.cpp:9719-9737, GetMaxVitMax :9700-9715, m_dbMaxDebitMax :5915
     min_kv = 999; max_vit_max = 0; max_debit_max = 0;
     for (auto& c : cls) { double kv = -c.kx * c.w / (c.vx - c.w); if (kv < min_kv) min_kv = kv; if (c.vx > max_vit_max) max_vit_max = c.vx;
@@ -360,6 +404,7 @@ struct Sim {
     if (l.size() == 1) return l[0];
     if (l.empty()) return nullptr;
     n_ties++;
+    if (trace_ties) { fprintf(stderr, "tie t=%g lane %d (link %d brick %d):", t, l[0]->lane[1], lanes[l[0]->lane[1]].link, links[lanes[l[0]->lane[1]].link].brick); for (Veh* q : l) fprintf(stderr, " id %d pos %.6f v1 %.4f", q->id, q->pos[1], q->vit[1]); fprintf(stderr, " len %.4f\n", lanes[l[0]->lane[1]].length); }
     for (size_t i = 0; i < l.size(); i++) { bool fol = false;
       for (size_t j = 0; j < l.size() && !fol; j++) if (i != j) { Veh* ld = get_leader_of(l[j]); if (ld && ld->id == l[i]->id) fol = true; }
       if (!fol) return l[i]; }
@@ -427,6 +472,7 @@ struct Sim {
   }
   Veh* get_near_amont_vehicule(int lane, double pos, double dstmax, Veh* excl) {             // reseau.cpp:3374-3520
     std::vector<Veh*> l; if (lane < 0) return nullptr;
+    const int lane0 = lane;                                                                  // pTuyau = parent of the lane the search started on (:3411)
     if (dstmax < 0) dstmax = 9999;
     double ptmp = -99999;
     for (Veh* c : lane_set[lane]) if (pos > c->pos[1] && c->pos[1] >= ptmp) { if (!excl || excl->id != c->id) {
@@ -441,7 +487,14 @@ struct Sim {
       lane = pv;
     }
     if (!l.empty()) { if ((pos - ptmp) < dstmax) return get_first_vehicule(l); else return nullptr; }
-    // :3486-3517 single upstream link with a single lane behind a punctual connection: not present in the flattened tables
+    // :3479-3517 the upstream connection has a single upstream link with a single lane (lcam = its m_LstTuyAm; empty without a connection)
+    int link0 = lanes[lane0].link;
+    dstmax -= pos;
+    if (dstmax > 0 && lcam[link0].size() == 1 && links[lcam[link0][0]].n_lanes == 1) {
+      int up = links[lcam[link0][0]].first_lane; pos = lanes[up].length + 0.001; ptmp = -99999;
+      for (Veh* c : lane_set[up]) if (pos >= c->pos[1] && c->pos[1] >= ptmp) { if (!excl || excl->id != c->id) {
+        if (c->pos[1] == ptmp) l.push_back(c); else { l.resize(1); l[0] = c; ptmp = c->pos[1]; } } }
+    }
     return get_first_vehicule(l);
   }
   double distance_entre_vehicules(Veh* a, Veh* b) {                                          // reseau.cpp:4446-4560 (start of step)
@@ -512,7 +565,7 @@ struct Sim {
     v->pos[1] = v->pos[1] * lanes[tgt_lane].length / lanes[old].length;
     if (fol && fol->link[1] == v->link[1]) v->pos[1] = std::max<double>(v->pos[1], fol->pos[1]);
     v->voie_desiree = -1;
-    calcul_next_voie(v, v->lane[1]);                                                         // :2700 (consumes the lane's memoised draw)
+    v->next_voie = calcul_next_voie(v, v->lane[1]);                                          // :2700 (consumes the lane's memoised draw; m_pNextVoie is kept)
   }
   bool calcul_changement_voie(Veh* v, int tgt_num, bool force) {                            // vehicule.cpp:2248-2457
     if (v->pos[1] <= UNDEF_POSITION) return false;                                           // :2291
@@ -634,7 +687,17 @@ struct Sim {
     }
     // :233-263 red-light correction: the inner `ControleurDeFeux *pCDF` declarations shadow the outer
     // NULL pointer, so the branch never fires — nothing to restate.
-    // :266-298 non-priority merge-branch leader correction: part of row A10 (merge points), see oracle/README.md.
+    // :266-298 the leader heads a non-priority merge branch: worst case, it does not insert
+    if (!c.post && L->link[1] >= 0 && links[L->link[1]].type_aval == 'C' && link_cvg_aval[L->link[1]] >= 0) {
+      const Cvg& cv = cvgs[link_cvg_aval[L->link[1]]];
+      if (cv.am_links.size() >= 1 && get_prev_vehicule(L) == nullptr && voie_amont_non_prioritaire(cv, L->lane[1])) {
+        double vit = -1;
+        if (!L->deja_calcule) vit = calcul_vitesse_leader(cv, L, inst_cur, dtv); else vit = L->vit[0];
+        const double borne = std::min<double>(L->vit[1] + cls[L->cls].acc_max(v->vit[1]) * dtv, L->vit_reg_tuy_act);   // sic: the leader's table at the follower's speed
+        if (vit == -1) vit = borne; else vit = std::min<double>(vit, borne);
+        if (L->pos[1] + vit * dtv > lanes[L->lane[1]].length) vL = (lanes[L->lane[1]].length - L->pos[1]) / dtv;
+      }
+    }
     double dn0 = c.deltaN;
     double dn1 = newell_relax(dn0, v, L, vL, dtv, c);
     c.deltaN = dn1;
@@ -770,7 +833,11 @@ struct Sim {
         else if (ts > inst - dtv) { double vv = (trav + llen - start) / (ts - (inst - dtv)); infl = true; mini = std::min<double>(mini, vv * dtv); }
       }
     }
-    // 3 - downstream punctual connection (Convergent::ComputeTraffic convergent.cpp:1368-1403): row A10, pending.
+    // 3 - downstream punctual connection: Convergent::ComputeTraffic convergent.cpp:1368-1403 (vehicule.cpp:1668-1677)
+    { int cv = link_cvg_aval[lanes[lane].link];
+      if (cv >= 0 && lane == v->lane[1] && voie_amont_non_prioritaire(cvgs[cv], lane) && get_prev_vehicule(v) == nullptr) {
+        double mc = calcul_vitesse_leader(cvgs[cv], v, inst, dtv) * dtv;
+        if (mc < goal) { infl = true; mini = std::min<double>(mini, mc); } } }
     // 4 - signals :1680-1705
     double ml = goal + 1; bool arret = false;
     if (calcul_trafic_feux(v, inst, dtv, trav, start, end, goal, lane, ilane, lst, ml, arret)) {
@@ -815,7 +882,7 @@ struct Sim {
     double dtv = dt - std::max<double>(0, v->inst_creation);                                // :1278
     double range = max_influence(v) + dtv * v->vit_max;                                     // :1299, :1710-1715
     build_context(v, range);                                                                 // :1302
-    Ctx& c = *v->ctx;
+    Ctx& c = *v->ctx; inst_cur = inst;
     if (c.leader && same_part(v, c.leader)) calcul_trafic_ex(c.leader, inst, ids);          // :1304-1309 leader first
     double goal = compute_law(v, dtv, c);                                                    // :1312
     v->regime_fluide = c.free_flow; v->regime_fluide_leader = v->regime_fluide;             // :1313-1315
@@ -845,7 +912,7 @@ struct Sim {
       if (reached) { dest_lane = ln; trav_dest = trav; }
       if (reached) { v->link[0] = lanes[ln].link; v->lane[0] = ln; v->pos[0] = ep; break; }  // :1417-1423
       else if (ep <= llen) { v->link[0] = lanes[ln].link; v->lane[0] = ln; v->pos[0] = ep; break; }   // :1425-1431
-      // :1485-1496 AddInsVeh on the downstream punctual connection: consumed by row A10 (merge points), pending.
+      { int cv = link_cvg_aval[lanes[ln].link]; if (cv >= 0 && ta != 'E' && ta != 'S') cvgs[cv].ins_veh.push_back(v); }   // :1485-1496 AddInsVeh
       if (i > 0) v->used_lanes.push_back(ln);                                                // :1499-1502
       v->voie_desiree = -1;                                                                  // :1505
     }
@@ -1047,21 +1114,370 @@ struct Sim {
     }
   }
 
+
+  // ==========================================================================================
+  // Merge points (row A10)
+  // convergent.cpp:77-100, :310-329, :333-990, :1087-1403 ; carFollowing/AbstractCarFollowing.cpp:336-664 ;
+  // CarrefourAFeuxEx.cpp:1386-1593 ; reseau.cpp:2432-2600, :9614-9690 ; sensors/SensorsManager.cpp:462-700 ;
+  // vehicule.cpp:4060-4160 (IsItineraire), :4615-4660 (CalculPosition)
+  // ==========================================================================================
+  static double min_d(double a, double b) { return (b < a) ? b : a; }                       // std::min<double> (matters when an operand is NaN)
+  double cvg_tf(const Cvg& c, int k) const { return std::max<double>(c.tf[k], 1 / cls[k].debit_max()); }   // Convergent::GetTf :310-329 (every type is listed)
+  int pt_of_upstream_lane(const Cvg& c, int lane) const {                                  // GetPointDeConvergence(VoieMicro*) :1340-1353
+    for (int p : c.pts) for (auto& a : pts[p].vam) if (a.lane == lane) return p;
+    return -1; }
+  bool voie_amont_non_prioritaire(const Cvg& c, int lane) const {                          // :1230-1258
+    int p = pt_of_upstream_lane(c, lane); int niv = 0, nmin = INT32_MAX;
+    if (p >= 0) for (auto& a : pts[p].vam) { if (a.lane == lane) niv = a.niv; if (nmin > a.niv) nmin = a.niv; }
+    return niv > nmin && niv > 1; }
+  double inst_last_passage(const Cvg& c, int down_lane) const {                            // :1170-1184 (UNDEF_INSTANT when the lane is not a point of this merge)
+    for (int p : c.pts) if (pts[p].down_lane == down_lane) return pts[p].inst_last_passage;
+    return -DBL_MIN; }
+  double calcul_vitesse_leader(const Cvg& c, Veh* L, double inst, double pas) {            // :1121-1168
+    if (L->next_voie < 0) L->next_voie = calcul_next_voie(L, L->lane[1]);
+    double tl = inst_last_passage(c, L->next_voie);
+    double t0 = tl >= 0 ? tl + cvg_tf(c, L->cls) - (inst - pas) : 0;
+    double p1 = L->pos[1] <= UNDEF_POSITION ? 0 : L->pos[1];
+    if (t0 > 0) return (lanes[L->lane[1]].length - p1) / t0;
+    return L->vit_max; }
+  Veh* vehicule_en_attente(const Cvg& c, int lane) const {                                 // GetVehiculeEnAttente :1087-1116
+    for (Veh* v : c.ins_veh) { if (v->lane[1] == lane && v->lane[0] != lane) return v;
+      for (int u : v->used_lanes) if (u == lane && v->lane[0] != lane) return v; }
+    return nullptr; }
+  // a vehicle that does not insert stays at the end of its upstream lane (:405-412, :433-438, :635-644, :819-827, :972-987)
+  void immobilise(Veh* v, int lane, bool acc_sic) {
+    v->pos[0] = lanes[lane].length - 0.0001; v->link[0] = lanes[lane].link; v->lane[0] = lane;
+    v->vit[0] = dst_parcourue_ex(v) / dt;
+    set_acc(v, acc_sic ? v->vit[1] / dt : (v->vit[0] - v->vit[1]) / dt);
+    update_used_lanes(v); n_pins++; }
+  // sensors of a merge: SensorsManager::GetDebitMoyen / GetNbVehTotal / GetRatioTypeVehicule (:551-700)
+  int capteur_of(const Cvg& c, int link) const { if (link == c.down_link) return 0;       // Convergent::GetCapteur :1000-1014
+    for (size_t k = 0; k < c.cpt.size(); k++) if (c.cpt[k].link == link) return (int)k;
+    return -1; }
+  double cpt_somme(const Cvg& c, int k, int nvoie, int type /* -1 = all */) const {
+    const Capteur& q = c.cpt[k]; int nl = links[q.link].n_lanes; if (nvoie < 0 || nvoie >= nl) return 0;
+    int kmax = std::min(c.nb_inst, c.window); double s = 0;
+    for (size_t t = 0; t < cls.size(); t++) if (type < 0 || (int)t == type) for (int j = 0; j < kmax; j++) s += q.cnt[(t * nl + nvoie) * c.window + j];
+    return s; }
+  double debit_moyen(const Cvg& c, int k, int nvoie) const { if (k < 0) return 0; return cpt_somme(c, k, nvoie, -1) / (std::min(c.nb_inst, c.window) * dt); }
+  double nb_veh_total(const Cvg& c, int k, int nvoie) const { if (k < 0) return 0; return cpt_somme(c, k, nvoie, -1); }
+  double ratio_type(const Cvg& c, int k, int nvoie, int type) const { if (k < 0) return 0; double tot = cpt_somme(c, k, nvoie, -1);
+    return tot > 0 ? cpt_somme(c, k, nvoie, type) / tot : 0; }
+  // Vehicule::IsItineraire vehicule.cpp:4060-4160 ('iti' mode; itineraries hold external links only)
+  bool is_itineraire(const Veh* v, int link) const {
+    const auto& r = routes[v->route];
+    for (int k : r) if (k == link) return true;
+    int br = links[link].brick;
+    if (br >= 0) for (size_t i = 0; i + 1 < r.size(); i++) if (links[r[i]].down_node == br) {
+      for (auto& m : caf_mvts) if (m.node == br && m.ent_link == r[i] && m.exit_link == r[i + 1]) for (int t : m.tl) if (t == link) return true; }
+    return false; }
+  // Reseau::GetVehiculeAmont reseau.cpp:9638-9690 (first lane of every link only)
+  Veh* get_vehicule_amont(int link, double dst, double cum) {
+    Veh* veh = get_near_amont_vehicule(links[link].first_lane, links[link].length, -1.0, nullptr);
+    if (veh) return veh;
+    if (dst < cum) return nullptr;
+    if (node_type[links[link].up_node] == 'E' || node_type[links[link].up_node] == 'S' || node_type[links[link].up_node] == 'P') return nullptr;
+    for (int am : lcam[link]) {
+      veh = get_vehicule_amont(am, dst, cum + links[link].length);
+      if (veh && dst > cum + links[link].length - veh->pos[1] && calcul_next_voie(veh, veh->lane[1]) == links[link].first_lane) return veh; }
+    return nullptr; }
+  double max_rap_vit_sur_qx(int link) const { return std::min(links[link].vit_reg, cls[0].vx); }   // TuyauMicro::GetMaxRapVitSurQx tuyau.cpp:1944-1958
+  // Reseau::GetPrevVehicule(pVeh, bSearchNextVoie = true) reseau.cpp:3650-3820
+  Veh* get_prev_vehicule_next(Veh* v) {
+    int lane = v->lane[1]; if (lane < 0) return nullptr;
+    Veh* r = get_prev_vehicule(v); if (r) return r;
+    std::vector<Veh*> l; int nvoie = lanes[lane].num; int next_link = -1; int voie = lane;
+    char ta = links[v->link[1]].type_aval;
+    if (ta != 'S' && ta != 'P') next_link = v->link[1];
+    auto scan = [&](int ln) { double pv = lanes[ln].length + 1;
+      for (Veh* c : lane_set[ln]) if (c->pos[1] <= pv && c->pos[1] >= 0 && c != v) { if (c->pos[1] == pv) l.push_back(c); else { l.resize(1); l[0] = c; pv = c->pos[1]; } } };
+    if (ta == 'C' && !lcav[v->link[1]].empty()) {                                          // :3726-3768
+      next_link = lcav[v->link[1]].front();
+      voie = calcul_next_voie(v, voie);
+      if (voie < 0) voie = links[next_link].first_lane + std::min(nvoie, links[next_link].n_lanes - 1);
+      scan(voie);
+    }
+    if (l.empty() && next_link >= 0) for (int nn : lcav[next_link]) if (is_itineraire(v, nn)) {   // :3771-3815
+      voie = calcul_next_voie(v, voie);
+      if (voie < 0) voie = links[nn].first_lane + std::min(nvoie, links[nn].n_lanes - 1);
+      scan(voie);
+    }
+    return get_last_vehicule(l); }
+  // Vehicule::CalculPosition vehicule.cpp:4615-4760
+  double calcul_position(const Veh* v, double tr, int lane) const {
+    double p = v->pos[1] + v->vit[0] * tr;
+    if (lanes[lane].link == lanes[v->lane[1]].link) return p;
+    std::vector<int> iti; const auto& r = routes[v->route];                                // Reseau::ComputeItineraireComplet reseau.cpp:14002-14032
+    for (size_t i = 0; i < r.size(); i++) { if (i > 0 && links[r[i - 1]].type_aval != 'S') {
+        int br = links[r[i - 1]].down_node;
+        if (node_type[br] == 'C' && links[r[i]].up_node == br) {                            // CarrefourAFeuxEx::GetTuyauxInternes :1598-1660: first lane pair that has a movement
+          bool found = false;
+          for (int a = 0; a < links[r[i - 1]].n_lanes && !found; a++) for (int b2 = 0; b2 < links[r[i]].n_lanes && !found; b2++)
+            for (auto& m : caf_mvts) if (m.node == br && m.ent_link == r[i - 1] && m.exit_link == r[i] && !m.tl.empty() &&
+                lanes[links[m.tl.front()].first_lane].prev_lane == links[r[i - 1]].first_lane + a) {
+              int last = links[m.tl.back()].first_lane; bool to_b = false; for (auto& q : lanes[last].succ) if (q.next_lane == links[r[i]].first_lane + b2) to_b = true;
+              if (to_b) { for (int t : m.tl) iti.push_back(t); found = true; break; } } } }
+      iti.push_back(r[i]); }
+    int idx = -1; for (size_t k = 0; k < iti.size(); k++) if (iti[k] == lanes[v->lane[1]].link) { idx = (int)k; break; }
+    if (idx != -1) { p = -(lanes[v->lane[1]].length - p);
+      for (size_t j = idx + 1; j < iti.size(); j++) { if (iti[j] == lanes[lane].link) return p; p -= links[iti[j]].length; } }
+    return 9999; }
+
+  // AbstractCarFollowing::TestConvergentInsertion carFollowing/AbstractCarFollowing.cpp:336-664 (no roundabout, calcul_tq_convergent off)
+  bool test_convergent_insertion(Veh* v, PtCvg& P, Cvg& C, int TAmP, int VAmP, int VAmNP, int nVoieGir, double inst, int j,
+                                 double demande1, double demande2, double offre, Veh* leader, Veh* follower, double& tr, double& ta) {
+    bool res = false;
+    if (!P.free_flow) {                                                                     // :343-377
+      double q2g = C.gamma * offre / (1 + C.gamma);
+      if (demande2 < q2g) { res = true; P.rand_numbers = 0; }
+      else { double proba = q2g * dt; res = false; n_cong++;
+        rnd.myRand();                                                                       // one draw, unused
+        for (int k = 0; k < P.rand_numbers; k++) { double r = rnd.myRand() / MAXIMUM_RANDOM_NUMBER; P.rand_numbers = P.rand_numbers - 1;
+          if (r < proba) { res = true; break; } } }
+      return res;
+    }
+    P.rand_numbers = 0;                                                                     // :381
+    const Cls& k = cls[v->cls];
+    const double tmin = std::max<double>(cvg_tf(C, v->cls), 1 / k.debit_max());
+    if (!(inst - P.inst_last_passage >= tmin)) return false;                                 // :385-391 downstream condition
+    const int TAv = C.down_link;
+    if (follower) {                                                                          // :395-461
+      if (node_type[links[TAmP].up_node] == 'C' && links[TAmP].brick >= 0) {                 // get_Type_amont() == 'D': internal link behind a CAF divergent
+        int ent = lcam[TAmP].empty() ? -1 : lcam[TAmP].front();
+        if (ent >= 0 && lcav[ent].size() > 1) {                                              // m_LstVoiesSvt only ever holds results of CalculNextVoie: no entry lane, the search fails
+          calcul_next_voie(follower, links[ent].first_lane);                                 // :432 (may consume the memoised draw of that lane)
+        }
+      } else if (!is_itineraire(follower, TAv)) { follower = nullptr; res = true; }         // :455-459
+    }
+    Veh* foll_int = nullptr;                                                                 // :472-500
+    if (links[TAmP].n_lanes > 1 && links[TAv].n_lanes > 1 && nVoieGir == 0) {
+      foll_int = get_near_amont_vehicule(links[TAmP].first_lane + nVoieGir + 1, lanes[VAmP].length, -1.0, nullptr);
+      if (foll_int) { if (foll_int->res_tir_foll_int == -1) foll_int->res_tir_foll_int = (double)rnd.myRand() / MAXIMUM_RANDOM_NUMBER;
+        foll_int->res_tir_foll_int = -1; foll_int = nullptr; }                               // not a roundabout: never in the way
+    }
+    const int TNP = lanes[VAmNP].link;
+    double tfbar = 0;                                                                        // :505-513
+    if (nb_veh_total(C, capteur_of(C, TNP), j) == 0) tfbar = cvg_tf(C, v->cls);
+    else for (size_t i = 0; i < cls.size(); i++) tfbar += ratio_type(C, capteur_of(C, TNP), j, (int)i) * cvg_tf(C, (int)i);
+    double tmbar = 0;
+    for (size_t i = 0; i < cls.size(); i++) tmbar += ratio_type(C, capteur_of(C, TAmP), 0, (int)i) * (1 / cls[i].debit_max());
+    double q1mu = 1 / ((tfbar * C.mu) + tmbar);
+    double vit_am;                                                                           // :520-525
+    { Veh* w = get_vehicule_amont(TAmP, max_rap_vit_sur_qx(TAmP), 0);
+      if (w && w->link[1] >= 0) vit_am = std::min<double>(w->vit_max, vit_reg(w->link[1]));
+      else vit_am = std::min<double>(max_vit_max, vit_reg(TAmP)); }
+    double dlag;
+    if (demande1 <= q1mu) dlag = (-k.w + vit_am) / (-k.kx * k.w);
+    else { double eta = (demande1 - q1mu) / (1 / tmbar - q1mu); dlag = (-k.w + vit_am) / (-k.kx * k.w) * (1 - eta); }   // :537-538 (the first assignment is dead)
+    if (VAmNP == v->lane[1]) tr = dt * (lanes[v->lane[1]].length - v->pos[1]) / dst_parcourue_ex(v);            // :544-547
+    else tr = dt * (lanes[v->lane[1]].length - v->pos[1] + lanes[VAmNP].length) / dst_parcourue_ex(v);
+    const double plim = lanes[VAmP].length - dlag;
+    if (inst - dt + tr > P.inst_last_passage + tmin) {                                       // :550-587
+      if (follower || foll_int) {
+        double pf = 9999; if (follower) pf = calcul_position(follower, tr, VAmP);
+        if (pf <= plim) { res = true; ta = dt - tr; } else res = false;
+      } else { res = true; ta = dt - tr; }
+    } else {                                                                                 // :589-628
+      tr = dt - (inst - (P.inst_last_passage + tmin));
+      if (!follower && !foll_int) { ta = dt - tr; res = true; }
+      else { double pf = 9999; if (follower) pf = calcul_position(follower, tr, VAmP);
+        if (pf <= plim) { ta = dt - tr; res = true; } else res = false; }
+    }
+    return res;
+  }
+
+  // PointDeConvergence::CalculInsertion convergent.cpp:333-990
+  void calcul_insertion(int pi, double inst) {
+    PtCvg& P = pts[pi]; Cvg& C = cvgs[P.cvg];
+    P.rand_numbers++;                                                                       // :366
+    if (P.vam.empty()) return;
+    int VAmP = -1; { int nt = INT32_MAX; for (auto& a : P.vam) if (a.niv < nt) { VAmP = a.lane; nt = a.niv; } }   // GetVoieAmontPrioritaire :77-100
+    int niv_prio = -1; for (auto& a : P.vam) if (a.lane == VAmP) { niv_prio = a.niv; break; }
+    int niv = 999; Veh* att = nullptr; int VAmNP = -1; int att_lane = -1; bool have = false;   // LstVehEnAttente holds at most one entry (the Tmp list is cleared per lane, :447)
+    for (size_t i = 0; i < P.vam.size(); i++) if (P.vam[i].niv > niv_prio) {                // :376-449
+      int VAm = P.vam[i].lane;
+      Veh* w = vehicule_en_attente(C, VAm);
+      if (!(w && w->vit[0] > 0)) w = nullptr;
+      if (w) {
+        if (P.vam[i].niv < niv) {
+          if (have && att) immobilise(att, att_lane, true);                                 // :399-413 (acc = vit[1]/dt, sic)
+          att = w; att_lane = VAm; have = true; VAmNP = VAm; niv = P.vam[i].niv;
+        } else immobilise(w, VAm, true);                                                    // :425-442
+      }
+    }
+    if (!att) return;                                                                        // :452-460
+    Veh* follower = get_near_amont_vehicule(VAmP, lanes[VAmP].length + 0.01, dt * max_vit_max, nullptr);   // :463
+    int TAmP = lanes[VAmP].link; int nVoieGir = lanes[VAmP].num;
+    auto drop = [&](Veh*& f) { if (f) { if (f->link[1] < 0) f = nullptr; else if (f->arret_au_feu) f = nullptr; else if (!f->ctx) f = nullptr; } };
+    drop(follower);                                                                          // :469-483
+    if (!follower) for (size_t i = 0; i < P.vam.size(); i++) if (P.vam[i].niv < niv && P.vam[i].niv > 1) {   // :486-504
+      follower = get_near_amont_vehicule(P.vam[i].lane, lanes[P.vam[i].lane].length, -1.0, nullptr);
+      if (follower && !follower->arret_au_feu) { niv = P.vam[i].niv; VAmP = P.vam[i].lane; TAmP = lanes[VAmP].link; nVoieGir = lanes[VAmP].num; }
+      else follower = nullptr; }
+    drop(follower);                                                                          // :507-521
+    if (follower && !is_itineraire(follower, TAmP)) follower = nullptr;                     // :525-528
+    Veh* leader = get_near_aval_vehicule(P.down_lane, 0, nullptr);                          // :531-533
+    if (!leader && att->link[1] >= 0) leader = get_prev_vehicule_next(att);
+    { Veh* w = get_near_amont_vehicule(P.down_lane, C.pos_cpt_av, -1.0, nullptr);           // :538-550
+      if (w && w->lane[1] != P.down_lane) w = nullptr;
+      P.free_flow = w ? w->regime_fluide : true; }
+    if (!P.free_flow && !get_vehicule_amont(TAmP, max_rap_vit_sur_qx(TAmP), 0)) P.free_flow = true;   // :554-556
+    double offre = 0, demande1 = 0, demande2 = 0;
+    if (!P.free_flow) {                                                                      // :560-583
+      offre = min_d(max_debit_max, debit_moyen(C, capteur_of(C, C.down_link), nVoieGir));
+      int TNP = lanes[VAmNP].link; bool np_free;
+      Veh* w = get_vehicule_amont(TNP, max_rap_vit_sur_qx(TNP), 0);
+      if (w) np_free = !(w->vit[1] < std::min<double>(w->vit_max, vit_reg(TNP))); else np_free = true;
+      if (np_free) demande2 = min_d(max_debit_max, debit_moyen(C, capteur_of(C, TNP), std::min<int>(lanes[VAmNP].num, nVoieGir)));
+      else demande2 = max_debit_max;
+    } else demande1 = min_d(max_debit_max, debit_moyen(C, capteur_of(C, TAmP), nVoieGir));  // :586
+    double tr = 0, ta = 0;
+    bool ins = test_convergent_insertion(att, P, C, TAmP, VAmP, VAmNP, nVoieGir, inst, 0, demande1, demande2, offre, leader, follower, tr, ta);   // :590-600
+    // TestConvergentInsertion drops its own copy of the follower only (pVehFollower is passed by value)
+    P.insertion = ins;
+    if (trace_merge) fprintf(stderr, "merge t=%g pt %d down %d: att %d (lane %d niv %d) prio lane %d (niv %d) follower %d leader %d free %d ins %d tr %g ta %g d1 %g\n", inst, pi, P.down_lane, att->id, VAmNP, niv, VAmP, niv_prio, follower ? follower->id : -1, leader ? leader->id : -1, (int)P.free_flow, (int)ins, tr, ta, demande1);
+    if (!ins) { immobilise(att, VAmNP, false); n_refus++; return; }                          // :967-987
+    if (P.free_flow) {                                                                       // :656-836
+      Ctx ic; ic.post = true; ic.start_pos = 0;
+      if (leader && leader->link[1] >= 0) { double pl = leader->pos[1] + (dt - ta) * leader->vit[0];
+        if (P.down_lane != leader->lane[1]) pl += lanes[P.down_lane].length;
+        ic.leader = leader; ic.leader_id = leader->id; ic.leader_dist = pl; }
+      { bool add = false; for (int ln : att->ctx->lanes) { if (lanes[ln].link == lanes[P.down_lane].link) add = true; if (add) ic.lanes.push_back(ln); } }
+      double pos_att = ic.lanes.empty() ? 0.0 : compute_law(att, ta, ic);
+      if (pos_att > 0) {
+        double dfol = 0; 
+        if (follower) {                                                                      // :704-749
+          Ctx fc; fc.post = true;
+          double ptr = follower->pos[1] + (dt - ta) * follower->vit[0];
+          std::vector<int> lf = follower->ctx->lanes;
+          while (lf.size() > 1 && ptr > links[lanes[lf.front()].link].length) { ptr -= links[lanes[lf.front()].link].length; lf.erase(lf.begin()); }
+          double dconv = 0;
+          for (size_t i = 0; i < lf.size(); i++) { if (i == 0) dconv = lanes[lf[i]].length - ptr; else dconv += lanes[lf[i]].length; if (lanes[lf[i]].link == TAmP) break; }
+          fc.leader = att; fc.leader_id = att->id; fc.leader_dist = dconv; fc.lanes = lf; fc.start_pos = ptr;
+          fc.deltaN = follower->ctx->deltaN; fc.contraction = follower->ctx->contraction;
+          dfol = compute_law(follower, ta, fc);
+          dfol = std::min<double>(dst_parcourue_ex(follower), (dt - ta) * follower->vit[0] + dfol);
+        }
+        if (!follower || dfol >= 0) {
+          bool dont_move = false; double trav = 0;                                          // :753-786
+          for (size_t i = 0; i < ic.lanes.size(); i++) { int ln = ic.lanes[i]; double llen = len_ex(ln); double ep = pos_att - trav;
+            if (ln == att->lane[0] && ep > att->pos[0]) { dont_move = true; break; }
+            else if (ep <= llen) { att->link[0] = lanes[ln].link; att->lane[0] = ln; att->pos[0] = ep; update_used_lanes(att); break; }
+            trav += std::min<double>(ep, llen); }
+          if (!dont_move) { att->vit[0] = (pos_att + (dt - ta) * att->vit[0]) / dt; set_acc(att, (att->vit[0] - att->vit[1]) / dt); }
+          if (follower) {                                                                    // :788-816
+            trav = 0; const std::vector<int>& lf2 = follower->ctx->lanes;
+            for (size_t i = 0; i < lf2.size(); i++) { int ln = lf2[i]; double sp = i == 0 ? follower->pos[1] : 0; double llen = len_ex(ln); double ep = dfol - trav + sp;
+              if (ep <= llen) { follower->link[0] = lanes[ln].link; follower->lane[0] = ln; follower->pos[0] = ep; update_used_lanes(follower); break; }
+              trav += std::min<double>(ep, llen) - sp; }
+            follower->vit[0] = (dfol + (dt - ta) * follower->vit[0]) / dt; set_acc(follower, (follower->vit[0] - follower->vit[1]) / dt);
+          }
+          P.inst_last_passage = inst - dt + tr; n_insertions++;
+          return;
+        }
+      }
+      immobilise(att, VAmNP, false);                                                         // :819-830
+      for (auto it = C.ins_veh.begin(); it != C.ins_veh.end(); ++it) if (*it == att) { C.ins_veh.erase(it); break; }   // DelInsVeh
+      return;
+    }
+    // congested :838-966
+    if (!leader) return;                                                                     // the reference dereferences the leader here; a congested downstream lane always has one
+    double dconv = att->link[1] == lanes[VAmNP].link ? lanes[VAmNP].length - att->pos[1]
+                                                     : lanes[VAmNP].length + lanes[att->lane[1]].length - att->pos[1];
+    Ctx ic; ic.post = true;
+    double pl = leader->pos[1]; if (P.down_lane != leader->lane[1]) pl += lanes[P.down_lane].length;
+    pl += dconv;
+    ic.leader = leader; ic.leader_id = leader->id; ic.leader_dist = pl; ic.lanes = att->ctx->lanes; ic.start_pos = att->pos[1];   // deltaN = 1 (ComputeDeltaN without a previous context)
+    double d = compute_law(att, dt, ic);
+    d = std::min<double>(dst_parcourue_ex(att), d);
+    if (!(d >= dconv)) return;                                                               // :962-965 "PAS NORMAL"
+    { double trav = 0; const std::vector<int>& ll = ic.lanes;                               // :880-899
+      for (size_t i = 0; i < ll.size(); i++) { int ln = ll[i]; double sp = i == 0 ? att->pos[1] : 0; double llen = len_ex(ln); double ep = d - trav + sp;
+        if (ep <= llen) { att->link[0] = lanes[ln].link; att->lane[0] = ln; att->pos[0] = ep; update_used_lanes(att); break; }
+        trav += std::min<double>(ep, llen) - sp; }
+      att->vit[0] = d / dt; set_acc(att, (att->vit[0] - att->vit[1]) / dt); }
+    P.inst_last_passage = inst - dt; n_insertions++;
+    if (follower) {                                                                          // :908-958
+      double pos = follower->link[1] == TAmP ? lanes[VAmP].length - follower->pos[1]
+                                             : lanes[VAmP].length + lanes[follower->lane[1]].length - follower->pos[1];
+      Ctx fc; fc.post = true; fc.leader = att; fc.leader_id = att->id; fc.leader_dist = pos; fc.lanes = follower->ctx->lanes; fc.start_pos = follower->pos[1];
+      double dfol = std::max<double>(0, compute_law(follower, dt, fc));
+      if (dst_parcourue_ex(follower) > dfol) {
+        double trav = 0;
+        for (size_t i = 0; i < fc.lanes.size(); i++) { int ln = fc.lanes[i]; double sp = i == 0 ? follower->pos[1] : 0; double llen = len_ex(ln); double ep = dfol - trav + sp;
+          if (ep <= llen) { follower->link[0] = lanes[ln].link; follower->lane[0] = ln; follower->pos[0] = ep; update_used_lanes(follower); break; }
+          trav += std::min<double>(ep, llen) - sp; }
+        follower->vit[0] = dfol / dt; set_acc(follower, (follower->vit[0] - follower->vit[1]) / dt);
+      }
+    }
+  }
+
+  // CarrefourAFeuxEx::UpdateConvergents CarrefourAFeuxEx.cpp:1386-1593 (start of the step, reseau.cpp:2225-2229)
+  void caf_update_convergents(double inst) {
+    if (cvgs.empty()) return;
+    std::vector<char> occ(lanes.size(), 0);                                                // Reseau::HasVehicule :9614-9635: lane at the end of the previous step
+    for (Veh* v : lst) if (v->lane[0] >= 0) occ[v->lane[0]] = 1;
+    for (auto& C : cvgs) { if (C.node < 0 || node_ctrl[C.node] < 0) continue;               // :1406-1407 no controller: priorities stay
+      for (int p : C.pts) for (auto& a : pts[p].vam) a.niv = a.niv_ref; }
+    for (auto& C : cvgs) { if (C.node < 0 || node_ctrl[C.node] < 0) continue;
+      for (int p : C.pts) { PtCvg& P = pts[p];
+        if (P.vam.size() == 0) break;
+        if (P.vam.size() == 1) { P.vam[0].niv = 1; break; }
+        std::vector<const CafMvt*> g1, g2, g3; std::vector<int> tmv;                        // :1437-1497
+        for (auto& m : caf_mvts) if (m.node == C.node) {
+          int tm = -1; for (int t : m.tl) { for (auto& a : P.vam) if (lanes[a.lane].link == t) { tm = t; break; } if (tm >= 0) break; }
+          if (tm < 0) continue;
+          double pr = 0;
+          if (statut_couleur(node_ctrl[C.node], inst, m.ent_link, m.exit_link, &pr) == 1) g2.push_back(&m);
+          else { bool veh = false; for (int t : m.tl) { if (occ[links[t].first_lane]) { veh = true; break; } if (t == tm) break; }
+            if (veh) g1.push_back(&m); else g3.push_back(&m); } }
+        const int n = (int)P.vam.size();
+        auto bump = [&](const CafMvt* m, int add) { for (int t : m->tl) for (auto& a : P.vam) if (lanes[a.lane].link == t) { a.niv = a.niv_ref + add; break; } };
+        if (g1.empty()) { for (auto* m : g3) bump(m, n + 1); }                               // :1499-1525
+        else { for (auto* m : g2) bump(m, n + 1); for (auto* m : g3) bump(m, 2 * n + 1); }   // :1527-1588
+      } }
+  }
+  // SensorsManager::UpdateTabNbVeh sensors/SensorsManager.cpp:462-527 (Convergent::UpdateCapteurs, reseau.cpp:14425-14428)
+  void update_tab_nb_veh(Cvg& C) {
+    int last = C.window - 1;
+    if (C.nb_inst < last) { C.nb_inst++; last = C.nb_inst; }
+    else for (auto& q : C.cpt) { size_t rows = q.cnt.size() / (size_t)std::max(1, C.window);
+      for (size_t r = 0; r < rows; r++) { double* a = &q.cnt[r * C.window]; for (int j = 0; j + 1 < C.window; j++) a[j] = a[j + 1]; if (C.window > 0) a[C.window - 1] = 0; } }
+    C.last_ind = last; }
+  // Reseau::UpdateConvergents reseau.cpp:2432-2600 (offre_aval_convergent_deltaN off: integer counts)
+  void update_convergents_capteurs() {
+    const size_t T = cls.size();
+    auto hit = [&](const std::pair<int, int>& k, int cl, int lane) { Cvg& C = cvgs[k.first]; Capteur& q = C.cpt[k.second]; int nl = links[q.link].n_lanes;
+      if (C.last_ind >= 0 && C.last_ind < C.window) q.cnt[((size_t)cl * nl + lanes[lane].num) * C.window + C.last_ind] += 1; (void)T; };
+    for (Veh* v : lst) { double p0 = v->pos[0];
+      if (!(v->vit[0] > 0 && p0 >= 0)) continue;
+      int t0 = v->link[0], t1 = v->link[1]; double p1 = v->pos[1];
+      if (t1 >= 0) for (auto& k : link_capteurs[t1]) { double x = cvgs[k.first].cpt[k.second].pos;
+        if (p1 < x && (p0 >= x || t1 != t0) && v->lane[1] >= 0) hit(k, v->cls, v->lane[1]); }
+      if (t1 != t0) {
+        if (t0 >= 0) for (auto& k : link_capteurs[t0]) { if (p0 >= cvgs[k.first].cpt[k.second].pos && v->lane[0] >= 0) hit(k, v->cls, v->lane[0]); }
+        for (int u : v->used_lanes) for (auto& k : link_capteurs[lanes[u].link]) hit(k, v->cls, u); }
+    }
+  }
+
   // ------------------------------------------------------------------------------------------
   // Reseau::SimuTrafic reseau.cpp:2028-2428 + SimuTraficMicroMacro :14152-14470
   int step() {
     max_depth = 0;
     t += dt; ninst++;                                                                        // :2105-2106
     for (auto& e : entries) update_crit_creation_step(e);                                   // :2219-2223
+    caf_update_convergents(t);                                                               // :2225-2229
     activate_api_vehicles(t);                                                                // :2233-2240
     init_vehicules();                                                                        // :2250
     for (auto& e : entries) creation_vehicules(e, t);                                       // :2255 -> :14143
     if (chgtvoie) changement_de_voie();                                                      // :14181 (ComputeFirstVehicules :14184 only feeds flux nodes)
     for (size_t i = 0; i < lst.size(); i++) { std::vector<int> ids; calcul_trafic_ex(lst[i], t, ids); }   // MiseAJourVehicules :3827-3865
     for (auto& e : entries) insertion_veh_en_attente(e, t);                                 // :14293-14296
-    // Convergent::CalculInsertion :14310-14314 (row A10, pending)
+    for (auto& C : cvgs) { for (int p : C.pts) calcul_insertion(p, t); C.ins_veh.clear(); }  // :14310-14314 (Liste_convergents: std::map order)
     for (Veh* v : lst) fin_calcul_trafic(v, t);                                             // :14364 -> :3871
     supprime_vehicules();                                                                    // :14418
+    for (auto& C : cvgs) update_tab_nb_veh(C);                                              // :14425-14428
+    update_convergents_capteurs();                                                           // :14458
     for (Veh* v : lst) if (v->link[0] >= 0 && v->lane[0] >= 0) v->vit_reg_tuy_act = links[v->link[0]].vit_reg;   // UpdateVitessesReg :2606-2627
     return (int)lst.size();
   }
@@ -1080,7 +1496,11 @@ int orc_step(void* h) { return ((Sim*)h)->step(); }
 int orc_nveh(void* h) { return (int)((Sim*)h)->lst.size(); }
 double orc_time(void* h) { return ((Sim*)h)->t; }
 unsigned orc_rng_count(void* h) { return ((Sim*)h)->rnd.count; }
-long orc_counter(void* h, int which) { Sim* s = (Sim*)h; return which == 0 ? s->n_ties : which == 1 ? s->n_loops : which == 2 ? s->n_created : s->max_depth; }
+long orc_counter(void* h, int which) { Sim* s = (Sim*)h; return which == 0 ? s->n_ties : which == 1 ? s->n_loops : which == 2 ? s->n_created : which == 3 ? s->max_depth :
+  which == 4 ? s->n_insertions : which == 5 ? s->n_refus : which == 6 ? s->n_pins : which == 7 ? s->n_cong : 0; }
+// merge points: last passage instant and draw counter of every point, window sums of every sensor (test access)
+int orc_merge_state(void* h, double* inst_last, int* rand_numbers, int cap) { Sim* s = (Sim*)h; int n = (int)s->pts.size();
+  for (int p = 0; p < n && p < cap; p++) { if (inst_last) inst_last[p] = s->pts[p].inst_last_passage; if (rand_numbers) rand_numbers[p] = s->pts[p].rand_numbers; } return n; }
 // state of m_LstVehicles in list order after the step
 void orc_dump(void* h, int* id, int* lane, int* route_pos, int* flags, double* pos, double* vit, double* acc, double* deltaN) {
   Sim* s = (Sim*)h; size_t i = 0;
