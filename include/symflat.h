@@ -36,7 +36,17 @@
  * lanecoef_f   f64                   REP_VOIE coefficients ; typecoef_f: type repartition
  * exit_i/f     i32 X x 2 / f64 X     node link / capacity veh/s (<0 = unlimited, sortie.cpp:60-118)
  * iv_i/f       i32 N0 x 4 / f64 x 3  class lane route route_pos / pos vit acc  (INIT/TRAJS, reseau.cpp:11680-11773)
- * names_link / names_node / names_cls   u8 '\0'-separated labels (XML output)
+ * merge points (row A10; all optional — a network without Convergent objects has none):
+ * cvg_i        i32   V x 8           node(CAF brick | -1) down_link pt_off n_pts am_off n_am 0 0   (Convergent, convergent.cpp:159-255;
+ *                                    rows in Reseau::Liste_convergents order = std::map by id, reseau.h:201)
+ * cvg_f        f64   V x 4           Tagreg gamma mu pos_cpt_aval ; cvg_tf f64 V x T: insertion time per vehicle type (GetTf)
+ * cvgam_i      i32                   upstream links (m_LstTuyAm order): one sensor each at length - 5
+ * pt_i         i32   P x 4           cvg down_lane vam_off n_vam                     (PointDeConvergence: one per downstream lane)
+ * ptam_i       i32   * x 2           upstream lane, reference priority level (m_LstVAm order; 1 = highest)
+ * cafmvt_i     i32   * x 5           node entry_link exit_link tl_off n_tl ; cafmvt_links: internal links (MvtCAFEx::lstTMvt)
+ * lcam_off/links  i32 K+1 / *        upstream links of a link's upstream connection (m_LstTuyAm), lcav_*: downstream links of
+ *                                    its downstream connection (m_LstTuyAv), both in the reference's order
+ * names_link / names_node / names_cls / names_cvg   u8 '\0'-separated labels (XML output)
  * link_geom    f64   K x 4           x0 y0 x1 y1 (abs/ord of <TRAJ>)
  */
 #ifndef SYMFLAT_H

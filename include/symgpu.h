@@ -23,13 +23,17 @@ enum { SYMGPU_OK = 0, SYMGPU_E_NODEVICE = -1, SYMGPU_E_LOAD = -2, SYMGPU_E_CUDA 
 enum { SYMGPU_CNT_TIES = 0,      /* equal-position leader candidates met (reseau.cpp:14041-14128 tie-break not replayed) */
        SYMGPU_CNT_LOOPS = 1,     /* leader-recursion loops broken (vehicule.cpp:1201-1216) */
        SYMGPU_CNT_CREATED = 2,   /* vehicles generated at origins */
-       SYMGPU_CNT_PASSES = 3,    /* follow passes launched (dependency wavefronts) */
+       SYMGPU_CNT_PASSES = 3,    /* relaxation sweeps that changed at least one speed (flow.cuh) */
        SYMGPU_CNT_LAUNCHES = 4,  /* kernels launched since creation */
        SYMGPU_CNT_SLOTS = 5,     /* vehicle slots in use (alive + holes) */
        SYMGPU_CNT_CTX_OVERFLOW = 6, /* context lane list longer than the device bound (must stay 0) */
        SYMGPU_CNT_LANE_CHANGES = 7, /* successful lane changes (Vehicule::ChangementVoie) */
        SYMGPU_CNT_LC_EVENTS = 8,    /* lane-change events that drew or changed something (walked one by one) */
-       SYMGPU_CNT_LC_REEVAL = 9     /* acceptance-test records re-evaluated after a commit */ };
+       SYMGPU_CNT_LC_REEVAL = 9,    /* acceptance-test records re-evaluated after a commit */
+       SYMGPU_CNT_MRG_INS = 10,     /* merge points: insertions (PointDeConvergence::CalculInsertion accepted) */
+       SYMGPU_CNT_MRG_REFUS = 11,   /* merge points: insertions refused (vehicle held at the end of its branch) */
+       SYMGPU_CNT_MRG_SERIAL = 12,  /* merge points processed one by one because they shared a vehicle with another point */
+       SYMGPU_CNT_MRG_VALUES = 13   /* merge points whose decision consumed values of the random stream (congested branch) */ };
 
 /* Replaces Reseau::LoadReseauXML + InitSimuTrafic for an already flattened network (include/symflat.h). */
 int symgpu_create(const char* symflat_path, int device, symgpu_ctx** out);
@@ -101,6 +105,9 @@ int symgpu_get_exited(symgpu_ctx* c, int cap, int* id, double* instant);
 int symgpu_num_links(symgpu_ctx* c);
 int symgpu_num_classes(symgpu_ctx* c);
 int symgpu_waiting(symgpu_ctx* c);              /* vehicles queued at origins (m_mapVehEnAttente) */
+/* Merge points (PointDeConvergence, convergent.h) in Reseau::Liste_convergents order: m_dbInstLastPassage and m_nRandNumbers.
+   Returns the number of points; fills at most `cap`. */
+int symgpu_get_merge_state(symgpu_ctx* c, int cap, double* inst_last_passage, int* rand_numbers);
 
 #ifdef __cplusplus
 }

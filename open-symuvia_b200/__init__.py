@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SYMB200_LIB", os.path.join(_HERE, "libSymuViaB200.so"))   # override only for A/B experiments
 _LIB = None
 
-CNT_TIES, CNT_LOOPS, CNT_CREATED, CNT_PASSES, CNT_LAUNCHES, CNT_SLOTS, CNT_CTX_OVERFLOW, CNT_LANE_CHANGES, CNT_LC_EVENTS, CNT_LC_REEVAL = range(10)
+(CNT_TIES, CNT_LOOPS, CNT_CREATED, CNT_PASSES, CNT_LAUNCHES, CNT_SLOTS, CNT_CTX_OVERFLOW, CNT_LANE_CHANGES, CNT_LC_EVENTS, CNT_LC_REEVAL,
+ CNT_MRG_INS, CNT_MRG_REFUS, CNT_MRG_SERIAL, CNT_MRG_VALUES) = range(14)
 
 
 class SymGpuError(RuntimeError):
@@ -56,6 +57,7 @@ def lib():
         L.symgpu_num_links.argtypes = [vp]
         L.symgpu_num_classes.argtypes = [vp]
         L.symgpu_waiting.argtypes = [vp]
+        L.symgpu_get_merge_state.argtypes = [vp, ci, vp, vp]
         _LIB = L
     return _LIB
 
@@ -153,6 +155,15 @@ class Engine:
         s = np.zeros(n, np.int32)
         self._chk(self.L.symgpu_get_link_counts(self.h, _p(e), _p(s)))
         return e, s
+
+    def merge_state(self):
+        """(last passage instant, draw counter) of every merge point, in Liste_convergents order."""
+        n = self._chk(self.L.symgpu_get_merge_state(self.h, 0, None, None))
+        t = np.zeros(n, np.float64)
+        r = np.zeros(n, np.int32)
+        if n:
+            self._chk(self.L.symgpu_get_merge_state(self.h, n, _p(t), _p(r)))
+        return t, r
 
     def exited(self, cap: int = 4096):
         ids = np.zeros(cap, np.int32)

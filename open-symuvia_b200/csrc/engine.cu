@@ -22,7 +22,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <deque>
+#include <climits>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/symgpu.h"
@@ -38,8 +40,9 @@ static thread_local std::string g_err;
 
 __constant__ DevParams cP;
 __device__ __forceinline__ const DevParams& cP_ref() { return cP; }
-#include "flow.cuh"
 #include "lanechange.cuh"
+#include "merge.cuh"
+#include "flow.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // device tables for signals
@@ -231,11 +234,12 @@ __global__ void k_lane_links(DevVeh V, int n_sorted, const int* lane_start, cons
 #ifndef SYM_CTX_THREADS
 #define SYM_CTX_THREADS 128
 #endif
-__global__ void __launch_bounds__(SYM_CTX_THREADS, SYM_CTX_BLOCKS) k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow) {
+__global__ void __launch_bounds__(SYM_CTX_THREADS, SYM_CTX_BLOCKS) k_context(DevNet N, DevVeh V, DevLaneDyn LD, int n_sorted, const int* order, const int* lane_tail, double* rows, unsigned* draws, int* overflow,
+                                                                               const DevMrg* M, double inst) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
   int i = order[p];
-  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow, rows, p, &LD);
+  int d = context_one(cP, N, V, lane_tail, i, V.ahead[i], overflow, rows, p, &LD, M, inst);
   V.vit_n[i] = V.vit[i];                           // initial guess of the relaxation (flow.cuh)
   if (d) atomicAdd(draws, (unsigned)d);
 }
@@ -515,6 +519,13 @@ struct symgpu_ctx {
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
   DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_fill = false /* k_final listed vehicles for k_ctx_fill */, aux_wait = false /* the step has work on the side stream */, dbg_sync = false, dbg_failed = false, coop_loops = true; cudaStream_t aux = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
+  // merge points (merge.cuh): static tables, per-point state, sensors, per-step records; the device copy of the struct for the kernels that take a pointer
+  struct Mrg { bool on = false; int n_upd = 0, n_rows = 0; DevMrg h; DBuf<DevMrg> d;
+    DBuf<int> link_cvg, cvg_node, cvg_down, cvg_pt0, cvg_npt, cvg_am0, cvg_nam, cvg_win, cvg_sens0, cvg_am, pt_cvg, pt_down, pt_vam0, pt_nvam, pt_mode, pt_pm0, vam_lane, vam_ref, vam_niv,
+        pm_vam, pm_sl, pm_occ0, pm_occ, lane_pt, lane_vam, sens_link, sens_cnt0, sens_win, cnt, lsens0, lsens, lcam0, lcam, lcav0, lcav, lmv0, lmv_ent, lmv_exit, fm0, fm_exit, fm_tl0, fm_ntl, fm_tl,
+        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, nused, nvoie, row_sens, flag, out;
+    DBuf<double> cvg_gamma, cvg_mu, cvg_poscpt, cvg_tf, sens_pos, pt_last, proba, mrgx; DBuf<unsigned> seen; } mg;
+  bool host_rng_fresh = true;                                      // the host copy of the random stream equals the device's
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
@@ -592,6 +603,8 @@ static int upload_rows(symgpu_ctx* c, int slot0, const std::vector<HostRow>& row
   return SYMGPU_OK;
 }
 
+static int build_merge(symgpu_ctx* c);
+static double max_debit_max(const symgpu_ctx* c);
 extern "C" const char* symgpu_last_error(void) { return g_err.c_str(); }
 const symb200::FlatNet& symgpu_internal_net(symgpu_ctx* c) { return c->net; }
 int symgpu_internal_create_vehicle(symgpu_ctx* c, int cls, int entry, int dest, int lane, double dbt) {
@@ -701,7 +714,9 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   for (DBuf<double>* b : {&c->v_pos, &c->v_vit, &c->v_acc, &c->v_pos_n, &c->v_vit_n, &c->v_acc_n, &c->v_dn, &c->v_cpos, &c->v_tcre, &c->v_dstp, &c->v_hent,
                           &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) CK(b->alloc(cap));
   fill_dev_structs(c);
+  { int rc = build_merge(c); if (rc != SYMGPU_OK) { delete c; return rc; } }
   c->rng.seed((unsigned)f.params[SYMFLAT_P_SEED]);                    // reseau.cpp:983-995
+  CK(cudaMemcpy(c->lc_rng.p, &c->rng, sizeof(DevRng), cudaMemcpyHostToDevice));   // the stream lives on the device; the host copy is refreshed when the origins draw
   // initial vehicles (reseau.cpp:1293-1340): already on the network, state at index 0
   { std::vector<HostRow> rows(f.n_init());
     for (int v = 0; v < f.n_init(); v++) { HostRow& r = rows[v]; r.status = ST_ALIVE; r.id = f.iv_id.empty() ? c->last_id++ : f.iv_id[v]; if (!f.iv_id.empty()) c->last_id = std::max(c->last_id, r.id + 1); r.cls = f.iv_i[4 * v]; r.lane = f.iv_i[4 * v + 1];
@@ -758,6 +773,121 @@ static void update_crit(symgpu_ctx* c, HostEntry& e, double inst, bool due_to_cr
   }
 }
 static double max_debit_max(const symgpu_ctx* c) { double m = 0; for (int i = 0; i < c->P.ncls; i++) { const DevCls& k = c->P.cls[i]; double q = k.w * k.kx / ((k.w / k.vx) - 1); if (q > m) m = q; } return m; }
+
+
+// ---- merge points: tables of merge.cuh from the SYMFLAT1 sections (Convergent::Init / FinInit convergent.cpp:208-255, the loader's
+// CarrefourAFeuxEx::Init :489-919) --------------------------------------------------------------------------------------------
+static int build_merge(symgpu_ctx* c) {
+  const FlatNet& f = c->net; auto& g = c->mg; DevMrg& h = g.h; memset(&h, 0, sizeof(h));
+  const int K = f.n_links(), L = f.n_lanes(), T = f.n_cls(), nc = f.n_cvg(), np = f.n_pt();
+  g.on = nc > 0;
+  std::vector<int> link_cvg(K, -1), cvg_node(nc), cvg_down(nc), cvg_pt0(nc), cvg_npt(nc), cvg_am0(nc), cvg_nam(nc), cvg_win(nc), cvg_sens0(nc), cvg_am;
+  std::vector<double> cvg_gamma(nc), cvg_mu(nc), cvg_poscpt(nc), sens_pos; std::vector<int> sens_link, sens_cnt0, sens_win, row_sens;
+  size_t cnt_total = 0;
+  for (int k = 0; k < nc; k++) { const int* r = &f.cvg_i[8 * k]; cvg_node[k] = r[0]; cvg_down[k] = r[1]; cvg_pt0[k] = r[2]; cvg_npt[k] = r[3]; cvg_am0[k] = r[4]; cvg_nam[k] = r[5];
+    cvg_gamma[k] = f.cvg_f[4 * k + 1]; cvg_mu[k] = f.cvg_f[4 * k + 2]; cvg_poscpt[k] = f.cvg_f[4 * k + 3];
+    cvg_win[k] = (int)(f.cvg_f[4 * k] / c->P.dt);                                          // PonctualSensor::InitData sensors/PonctualSensor.cpp:131
+    if (cvg_win[k] < 1) { g_err = "merge sensor window shorter than one time step"; return SYMGPU_E_UNSUPPORTED; }
+    cvg_sens0[k] = (int)sens_link.size();
+    auto add = [&](int link, double pos) { const int nl = f.link_i[8 * link + 1]; const int s = (int)sens_link.size();
+      sens_link.push_back(link); sens_pos.push_back(pos); sens_win.push_back(cvg_win[k]); sens_cnt0.push_back((int)cnt_total);
+      for (int q = 0; q < T * nl; q++) { row_sens.push_back(s); row_sens.push_back(q); }
+      cnt_total += (size_t)T * nl * cvg_win[k]; };
+    add(cvg_down[k], cvg_poscpt[k]);                                                       // "CptTav" (FinInit :239)
+    for (int a = r[4]; a < r[4] + r[5]; a++) { const int am = f.cvgam_i[a]; add(am, f.link_f[2 * am] - 5); link_cvg[am] = k; }   // "CptAm" at length - 5 (:247)
+  }
+  cvg_am = f.cvgam_i;
+  if (cnt_total > 0x7fffffffULL) { g_err = "merge sensor storage too large"; return SYMGPU_E_CAPACITY; }
+  std::vector<int> lsens0(K + 1, 0), lsens(sens_link.size());
+  for (int s : sens_link) lsens0[s + 1]++;
+  for (int k = 0; k < K; k++) lsens0[k + 1] += lsens0[k];
+  { std::vector<int> fill(lsens0.begin(), lsens0.end() - 1); for (size_t s = 0; s < sens_link.size(); s++) lsens[fill[sens_link[s]]++] = (int)s; }
+  // points and their upstream lanes
+  std::vector<int> pt_cvg(np), pt_down(np), pt_vam0(np), pt_nvam(np), pt_mode(np, 2), vam_lane(f.ptam_i.size() / 2), vam_ref(vam_lane.size()), lane_pt(L, -1), lane_vam(L, -1);
+  for (int p = 0; p < np; p++) { pt_cvg[p] = f.pt_i[4 * p]; pt_down[p] = f.pt_i[4 * p + 1]; pt_vam0[p] = f.pt_i[4 * p + 2]; pt_nvam[p] = f.pt_i[4 * p + 3]; }
+  for (size_t a = 0; a < vam_lane.size(); a++) { vam_lane[a] = f.ptam_i[2 * a]; vam_ref[a] = f.ptam_i[2 * a + 1]; }
+  for (int k = 0; k < nc; k++) for (int p = cvg_pt0[k]; p < cvg_pt0[k] + cvg_npt[k]; p++) for (int a = pt_vam0[p]; a < pt_vam0[p] + pt_nvam[p]; a++)
+    if (lane_pt[vam_lane[a]] < 0) { lane_pt[vam_lane[a]] = p; lane_vam[vam_lane[a]] = a; }
+  // junction movements through every point whose priorities follow the signals (CarrefourAFeuxEx::UpdateConvergents :1386-1593)
+  const int nm = (int)f.cafmvt_i.size() / 5;
+  std::vector<int> pt_pm0(np + 1, 0), pm_vam, pm_sl, pm_occ0(1, 0), pm_occ;
+  std::vector<std::vector<int>> node_mvts(f.n_nodes());
+  for (int m = 0; m < nm; m++) node_mvts[f.cafmvt_i[5 * m]].push_back(m);
+  for (int k = 0; k < nc; k++) { const int node = cvg_node[k]; const bool ctl = node >= 0 && f.node_i[4 * node + 1] >= 0;
+    bool stop = !ctl;
+    for (int p = cvg_pt0[k]; p < cvg_pt0[k] + cvg_npt[k]; p++) {
+      if (stop) { pt_mode[p] = 2; continue; }
+      if (pt_nvam[p] == 0) { pt_mode[p] = 2; stop = true; continue; }                       // :1428-1429 leaves the loop over the points
+      if (pt_nvam[p] == 1) { pt_mode[p] = 1; stop = true; continue; }                       // :1431-1435
+      pt_mode[p] = 0;
+    } }
+  std::unordered_map<unsigned long long, int> sl_of;                                       // (entry link, exit link) -> first stop line of the movement
+  for (int s2 = f.n_sl() - 1; s2 >= 0; s2--) sl_of[((unsigned long long)(unsigned)f.sl_i[6 * s2 + 1] << 32) | (unsigned)f.sl_i[6 * s2 + 3]] = s2;
+  for (int p = 0; p < np; p++) { pt_pm0[p] = (int)pm_vam.size();
+    if (pt_mode[p] == 0) { const int node = cvg_node[pt_cvg[p]]; const int ctrl = f.node_i[4 * node + 1];
+      for (int m : node_mvts[node]) { const int* r = &f.cafmvt_i[5 * m]; const int ent = r[1], ex = r[2];
+        int tm = -1;                                                                       // first internal link of the movement that leads into the point
+        for (int q = r[3]; q < r[3] + r[4] && tm < 0; q++) for (int a = pt_vam0[p]; a < pt_vam0[p] + pt_nvam[p]; a++) if (f.lane_i[4 * vam_lane[a]] == f.cafmvt_links[q]) { tm = q; break; }
+        if (tm < 0) continue;
+        int sl = -1; { auto it = sl_of.find(((unsigned long long)(unsigned)ent << 32) | (unsigned)ex); if (it != sl_of.end() && f.sl_i[6 * it->second] == ctrl) sl = it->second; }
+        if (sl < 0) { g_err = "merge point inside a signalised junction: movement without a stop line (signal colour unknown)"; return SYMGPU_E_UNSUPPORTED; }
+        for (int q = r[3]; q < r[3] + r[4]; q++) for (int a = pt_vam0[p]; a < pt_vam0[p] + pt_nvam[p]; a++) if (f.lane_i[4 * vam_lane[a]] == f.cafmvt_links[q]) {
+          pm_vam.push_back(a); pm_sl.push_back(sl);
+          for (int q2 = r[3]; q2 <= tm; q2++) pm_occ.push_back(f.link_i[8 * f.cafmvt_links[q2]]);
+          pm_occ0.push_back((int)pm_occ.size()); break; }
+      } } }
+  pt_pm0[np] = (int)pm_vam.size();
+  // movements an internal link belongs to; first movement (lane-pair order) between an entry link and an exit link
+  std::vector<int> lmv0(K + 1, 0), lmv_ent, lmv_exit, fm0(K + 1, 0), fm_exit, fm_tl0, fm_ntl, fm_tl;
+  { std::vector<std::vector<std::pair<int, int>>> per(K);
+    for (int m = 0; m < nm; m++) { const int* r = &f.cafmvt_i[5 * m]; for (int q = r[3]; q < r[3] + r[4]; q++) per[f.cafmvt_links[q]].push_back({r[1], r[2]}); }
+    for (int k = 0; k < K; k++) { for (auto& e : per[k]) { lmv_ent.push_back(e.first); lmv_exit.push_back(e.second); } lmv0[k + 1] = (int)lmv_ent.size(); }
+    struct Fm { int ex, a, b, m; };
+    std::vector<std::vector<Fm>> pe(K);
+    for (int m = 0; m < nm; m++) { const int* r = &f.cafmvt_i[5 * m]; if (r[4] <= 0) continue;
+      const int first_il = f.cafmvt_links[r[3]], last_il = f.cafmvt_links[r[3] + r[4] - 1];
+      const int ent_lane = f.lane_i[4 * f.link_i[8 * first_il] + 2]; const int a = ent_lane >= 0 ? f.lane_i[4 * ent_lane + 1] : 0;
+      const int ll = f.link_i[8 * last_il]; int b = 0; for (int q = f.succ_off[ll]; q < f.succ_off[ll + 1]; q++) if (f.succ_i[3 * q] == r[2]) { b = f.lane_i[4 * f.succ_i[3 * q + 1] + 1]; break; }
+      auto& v = pe[r[1]]; bool seen = false;
+      for (auto& e : v) if (e.ex == r[2]) { seen = true; if (a < e.a || (a == e.a && b < e.b)) { e.a = a; e.b = b; e.m = m; } }
+      if (!seen) v.push_back({r[2], a, b, m}); }
+    for (int k = 0; k < K; k++) { for (auto& e : pe[k]) { const int* r = &f.cafmvt_i[5 * e.m]; fm_exit.push_back(e.ex); fm_tl0.push_back((int)fm_tl.size()); fm_ntl.push_back(r[4]);
+        for (int q = r[3]; q < r[3] + r[4]; q++) fm_tl.push_back(f.cafmvt_links[q]); }
+      fm0[k + 1] = (int)fm_exit.size(); } }
+  std::vector<int> node_type(f.n_nodes()); for (int n = 0; n < f.n_nodes(); n++) node_type[n] = f.node_i[4 * n];
+  auto one = [](std::vector<int>& v) { if (v.empty()) v.push_back(0); };
+  one(cvg_am); one(pm_vam); one(pm_sl); one(pm_occ); one(lmv_ent); one(lmv_exit); one(fm_exit); one(fm_tl0); one(fm_ntl); one(fm_tl); one(lsens); one(row_sens);
+  std::vector<int> lcam_l = f.lcam_links, lcav_l = f.lcav_links; one(lcam_l); one(lcav_l);
+  CK(g.link_cvg.upload(link_cvg)); CK(g.cvg_node.upload(cvg_node)); CK(g.cvg_down.upload(cvg_down)); CK(g.cvg_pt0.upload(cvg_pt0)); CK(g.cvg_npt.upload(cvg_npt)); CK(g.cvg_am0.upload(cvg_am0));
+  CK(g.cvg_nam.upload(cvg_nam)); CK(g.cvg_win.upload(cvg_win)); CK(g.cvg_sens0.upload(cvg_sens0)); CK(g.cvg_am.upload(cvg_am)); CK(g.cvg_gamma.upload(cvg_gamma)); CK(g.cvg_mu.upload(cvg_mu));
+  CK(g.cvg_poscpt.upload(cvg_poscpt)); CK(g.cvg_tf.upload(f.cvg_tf)); CK(g.pt_cvg.upload(pt_cvg)); CK(g.pt_down.upload(pt_down)); CK(g.pt_vam0.upload(pt_vam0)); CK(g.pt_nvam.upload(pt_nvam));
+  CK(g.pt_mode.upload(pt_mode)); CK(g.pt_pm0.upload(pt_pm0)); CK(g.vam_lane.upload(vam_lane)); CK(g.vam_ref.upload(vam_ref)); CK(g.vam_niv.upload(vam_ref)); CK(g.pm_vam.upload(pm_vam)); CK(g.pm_sl.upload(pm_sl));
+  CK(g.pm_occ0.upload(pm_occ0)); CK(g.pm_occ.upload(pm_occ)); CK(g.lane_pt.upload(lane_pt)); CK(g.lane_vam.upload(lane_vam)); CK(g.sens_link.upload(sens_link)); CK(g.sens_cnt0.upload(sens_cnt0));
+  CK(g.sens_win.upload(sens_win)); CK(g.sens_pos.upload(sens_pos)); CK(g.cnt.alloc(std::max<size_t>(1, cnt_total))); CK(g.lsens0.upload(lsens0)); CK(g.lsens.upload(lsens));
+  CK(g.lcam0.upload(f.lcam_off)); CK(g.lcam.upload(lcam_l)); CK(g.lcav0.upload(f.lcav_off)); CK(g.lcav.upload(lcav_l)); CK(g.lmv0.upload(lmv0)); CK(g.lmv_ent.upload(lmv_ent)); CK(g.lmv_exit.upload(lmv_exit));
+  CK(g.fm0.upload(fm0)); CK(g.fm_exit.upload(fm_exit)); CK(g.fm_tl0.upload(fm_tl0)); CK(g.fm_ntl.upload(fm_ntl)); CK(g.fm_tl.upload(fm_tl)); CK(g.node_type.upload(node_type)); CK(g.row_sens.upload(row_sens));
+  g.n_rows = (int)row_sens.size() / 2; if (sens_link.empty()) g.n_rows = 0;
+  const size_t cap = c->v_status.n;
+  CK(g.pt_last.alloc(std::max(1, np))); CK(g.pt_rand.alloc(std::max(1, np))); CK(g.pt_free.alloc(std::max(1, np))); CK(g.cand_up.alloc(L)); CK(cudaMemset(g.cand_up.p, 0xff, L * sizeof(int)));
+  { std::vector<int> mx(cap, INT_MAX), mn(cap, -1); CK(g.own_min.upload(mx)); CK(g.own_max.upload(mn)); }
+  for (DBuf<int>* b : {&g.st, &g.ninv, &g.pre, &g.kmax, &g.decide, &g.ndraw}) CK(b->alloc(std::max(1, np)));
+  CK(g.inv.alloc((size_t)std::max(1, np) * kMrgInv)); CK(g.proba.alloc(std::max(1, np))); CK(g.nused.alloc(cap)); CK(g.nvoie.alloc(cap)); CK(cudaMemset(g.nvoie.p, 0xff, cap * sizeof(int)));
+  CK(g.mrgx.alloc(((size_t)cap + 32) * kMrgX)); CK(g.flag.alloc(1)); CK(g.out.alloc(1)); CK(g.seen.alloc(1));
+  h.n_cvg = nc; h.n_pt = np; h.n_sens = (int)sens_link.size(); h.n_cls = T;
+  h.max_debit_max = max_debit_max(c); h.max_vit_max = 0; for (int i = 0; i < T; i++) h.max_vit_max = std::max(h.max_vit_max, c->P.cls[i].vx); h.vx0 = c->P.cls[0].vx;
+  h.link_cvg = g.link_cvg.p; h.cvg_node = g.cvg_node.p; h.cvg_down = g.cvg_down.p; h.cvg_pt0 = g.cvg_pt0.p; h.cvg_npt = g.cvg_npt.p; h.cvg_am0 = g.cvg_am0.p; h.cvg_nam = g.cvg_nam.p; h.cvg_win = g.cvg_win.p;
+  h.cvg_sens0 = g.cvg_sens0.p; h.cvg_am = g.cvg_am.p; h.cvg_gamma = g.cvg_gamma.p; h.cvg_mu = g.cvg_mu.p; h.cvg_poscpt = g.cvg_poscpt.p; h.cvg_tf = g.cvg_tf.p;
+  h.pt_cvg = g.pt_cvg.p; h.pt_down = g.pt_down.p; h.pt_vam0 = g.pt_vam0.p; h.pt_nvam = g.pt_nvam.p; h.pt_mode = g.pt_mode.p; h.pt_pm0 = g.pt_pm0.p; h.vam_lane = g.vam_lane.p; h.vam_ref = g.vam_ref.p; h.vam_niv = g.vam_niv.p;
+  h.pm_vam = g.pm_vam.p; h.pm_sl = g.pm_sl.p; h.pm_occ0 = g.pm_occ0.p; h.pm_occ = g.pm_occ.p; h.lane_pt = g.lane_pt.p; h.lane_vam = g.lane_vam.p;
+  h.sens_link = g.sens_link.p; h.sens_cnt0 = g.sens_cnt0.p; h.sens_pos = g.sens_pos.p; h.cnt = g.cnt.p; h.sens_win = g.sens_win.p; h.lsens0 = g.lsens0.p; h.lsens = g.lsens.p;
+  h.lcam0 = g.lcam0.p; h.lcam = g.lcam.p; h.lcav0 = g.lcav0.p; h.lcav = g.lcav.p; h.lmv0 = g.lmv0.p; h.lmv_ent = g.lmv_ent.p; h.lmv_exit = g.lmv_exit.p;
+  h.fm0 = g.fm0.p; h.fm_exit = g.fm_exit.p; h.fm_tl0 = g.fm_tl0.p; h.fm_ntl = g.fm_ntl.p; h.fm_tl = g.fm_tl.p; h.node_type = g.node_type.p;
+  h.pt_last = g.pt_last.p; h.pt_rand = g.pt_rand.p; h.pt_free = g.pt_free.p; h.cand_up = g.cand_up.p; h.own_min = g.own_min.p; h.own_max = g.own_max.p;
+  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.proba = g.proba.p;
+  h.nused = g.nused.p; h.nvoie = g.nvoie.p; h.mrgx = g.mrgx.p; h.rng = c->lc_rng.p; h.draws = c->draws.p; h.counters = c->counters.p;
+  std::vector<DevMrg> one_h(1, h); CK(g.d.upload(one_h));
+  return SYMGPU_OK;
+}
 
 // SymCreateVehicle path (reseau.cpp:13351 -> :2233-2240 -> GenerateVehicle with type, lane and destination imposed):
 // only the itinerary (:515), law-coefficient and Jorge draws remain; the vehicle joins m_LstVehicles BEFORE
@@ -823,9 +953,9 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
 }
 
 // per-kernel device timing (CUDA events on the step stream), enabled by symgpu_profile(); bench.py uses it for the roofline
-enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_LC, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_COUNT };
+enum { KID_SIGNALS = 0, KID_PREPARE, KID_SCAN, KID_SCATTER, KID_SORT, KID_CONTEXT, KID_LC, KID_SEG, KID_FOLLOW, KID_LOOP, KID_PLACE, KID_ENTRIES, KID_FINAL, KID_MERGE, KID_COUNT };
 static const char* kKernelNames[KID_COUNT] = {"k_signals", "k_prepare", "k_scan", "k_scatter", "k_lane_order", "k_context", "k_lane_change", "k_seg", "k_relax",
-                                              "k_cyc_loops", "k_place", "k_entries", "k_final"};
+                                              "k_cyc_loops", "k_place", "k_entries", "k_final", "k_merge"};
 static void prof_begin(symgpu_ctx* c, int kid);
 static void prof_end(symgpu_ctx* c);
 static void dbg_sync(symgpu_ctx* c, int line);
@@ -864,6 +994,9 @@ static int step_front(symgpu_ctx* c) {
   // origins: criterion update (reseau.cpp:2219-2223) and creation (:2255); the device draws of the previous step
   // come first in the global random sequence
   std::vector<HostRow> new_rows; std::vector<EntryLane*> new_row_lane;
+  if ((has_entries || !c->api_queue.empty()) && !c->mp.on && !c->host_rng_fresh) {      // the origins draw on the host: bring the stream back (2.5 KB, the device is idle)
+    CK(cudaMemcpy(&c->rng, c->lc_rng.p, sizeof(DevRng), cudaMemcpyDeviceToHost)); c->host_rng_fresh = true; }
+  const unsigned host_count0 = c->rng.count;
   if (has_entries) {
     const double mdm = max_debit_max(c);
     for (auto& e : c->entries) update_crit(c, e, c->t, false, mdm);
@@ -890,6 +1023,7 @@ static int step_front(symgpu_ctx* c) {
     }
     if (!desc.empty()) CK(cudaMemcpyAsync(c->edesc.p, desc.data(), desc.size() * sizeof(EntryDesc), cudaMemcpyHostToDevice, s));
   }
+  if (!c->mp.on && c->rng.count != host_count0) CK(cudaMemcpyAsync(c->lc_rng.p, &c->rng, sizeof(DevRng), cudaMemcpyHostToDevice, s));   // ... and forth when it drew
   const int n = c->n_slots;
   const int n_sorted = c->n_alive + (int)new_rows.size();   // vehicles that are members of a lane this step
   const int B = 256;
@@ -924,15 +1058,13 @@ static int step_front(symgpu_ctx* c) {
     KBEGIN(c, KID_LC);
     k_lc_prepare<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c);
     CK(cudaMemsetAsync(c->lc_link_head.p, 0xff, K * sizeof(int), s)); CK(cudaMemsetAsync(c->lc_nchg.p, 0, 2 * sizeof(int), s));
-    CK(cudaMemcpyAsync(c->lc_rng.p, &c->rng, sizeof(DevRng), cudaMemcpyHostToDevice, s));
     if (c->lc_seq) { k_lc_sequential<<<1, 32, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); }
-    else { k_lc_eval<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); k_lc_walk<<<1, kLcBlock, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); }
+    else { k_lc_eval<<<G(n), B, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c); k_lc_walk<<<1, kLcBlock, 0, s>>>(c->dn, c->dv, c->dlc, n); LAUNCH(c);
+      k_rng_skip<<<1, 256, 0, s>>>(c->lc_rng.p, &c->lc_nchg.p[1], 0); LAUNCH(c); }   // the walk drew through a look-ahead buffer: advance the stream by what it consumed
     KEND(c);
     int nchg2[2] = {0, 0};
-    if (c->lc_seq) CK(cudaMemcpyAsync(&c->rng, c->lc_rng.p, sizeof(DevRng), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(nchg2, c->lc_nchg.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (!c->lc_seq) c->rng.skip((unsigned)nchg2[1]);                     // the walk drew through a look-ahead buffer: advance the host's copy of the stream
     const int nchg = nchg2[0];
     c->lane_changes += nchg;
     if (nchg > 0) {
@@ -961,9 +1093,13 @@ static int step_back(symgpu_ctx* c) {
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
   if (c->aux_wait) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->aux_wait = false; }
+  if (c->mg.on) {                                                         // merge points: candidates of the step, priority levels from this step's signal colours
+    KBEGIN(c, KID_MERGE); CK(cudaMemsetAsync(c->mg.cand_up.p, 0xff, L * sizeof(int), s));
+    k_mrg_rank<<<G(c->mg.h.n_pt), B, 0, s>>>(c->mg.h, c->sl_col.p, c->lane_count.p); KEND(c); }
   if (n > 0) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
-      k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW]); KEND(c); }
+      k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW],
+                                                                                             c->mg.on ? c->mg.d.p : nullptr, c->t); KEND(c); }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     KBEGIN(c, KID_SEG); k_seg<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, c->s_lane.p, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
@@ -995,7 +1131,7 @@ static int step_back(symgpu_ctx* c) {
     int* ch = c->f_ctl.p->changed;                                       // device address arithmetic only
     if (!first) cudaMemcpyAsync(ch, c->h_ctl_seed->changed, sizeof(int) * (kRelaxBatch + 1), cudaMemcpyHostToDevice, s);
     for (int j = 0; j < nb; j++) {
-      k_relax<<<(n_sorted + SYM_RELAX_THREADS - 1) / SYM_RELAX_THREADS, SYM_RELAX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, first && j == 0, ch + j, ch + j + 1, c->t); LAUNCH(c);
+      k_relax<<<(n_sorted + SYM_RELAX_THREADS - 1) / SYM_RELAX_THREADS, SYM_RELAX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, c->rows.p, c->b_goal.p, c->b_flags.p, c->vl_used.p, c->rl_lead.p, n_sorted, first && j == 0, ch + j, ch + j + 1, c->t, c->mg.on ? c->mg.d.p : nullptr, c->mg.mrgx.p); LAUNCH(c);
     }
     k_relax_done<<<1, 32, 0, s>>>(c->f_ctl.p, nb); LAUNCH(c);
     cudaMemcpyAsync(c->h_ctl, c->f_ctl.p, sizeof(FlowCtl), cudaMemcpyDeviceToHost, s);
@@ -1003,14 +1139,25 @@ static int step_back(symgpu_ctx* c) {
   auto finish = [&](const int* guard) {
     if (c->pack_wait) { cudaStreamWaitEvent(s, c->t_packed, 0); c->pack_wait = false; }      // trajectory rows of the last step are packed: status may change
     if (n > 0) {
-      if (n_sorted > 0) { KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t, guard); KEND(c); }
+      if (n_sorted > 0) { KBEGIN(c, KID_PLACE); k_place<<<G(n_sorted), B, 0, s>>>(c->dn, c->dv, c->rows.p, c->b_goal.p, c->b_flags.p, n_sorted, c->t, guard, c->mg.on ? c->mg.d.p : nullptr); KEND(c); }
       if (!desc.empty()) { KBEGIN(c, KID_ENTRIES); k_entries<<<G((int)desc.size()), B, 0, s>>>(c->dn, c->dv, c->dl, c->edesc.p, (int)desc.size(), c->eresult.p, c->t, c->draws.p,
                                                                       (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW], guard); KEND(c); }
+      // merge points (merge.cuh), after the origins' queues like reseau.cpp:14290-14314; the stream first passes this step's count-only draws
+      if (c->mg.on && n_sorted > 0) { auto& g = c->mg; const int Gp = G(g.h.n_pt);
+        KBEGIN(c, KID_MERGE); cudaMemsetAsync(g.flag.p, 0, sizeof(int), s);
+        k_mrg_probe<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        k_mrg_eval<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, g.flag.p, guard); LAUNCH(c);
+        k_mrg_walk<<<1, 256, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, g.flag.p, g.seen.p, g.out.p, guard); LAUNCH(c);
+        k_mrg_apply<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); KEND(c); }
+      else if (!c->mp.on) { k_rng_ctx<<<1, 256, 0, s>>>(c->lc_rng.p, c->draws.p, c->mg.seen.p, guard); LAUNCH(c); }
       if (c->use_cc) cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s);
       KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6], guard, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);
       if (c->exit_lanes.n) { k_exit_lanes<<<G((int)c->exit_lanes.n), B, 0, s>>>(c->dv, c->exit_lanes.p, c->exit_cap.p, c->exit_nl.p, (int)c->exit_lanes.n, c->exit_winner.p,
                                                                                 c->next_sortie.p, c->t, c->P.dt, c->P.duree, guard); }
       KEND(c);
+      if (c->mg.on && c->mg.h.n_sens > 0) { auto& g = c->mg;                  // merge sensors (reseau.cpp:14425-14458): rotate the windows, count the crossings of the step
+        KBEGIN(c, KID_MERGE); k_mrg_rotate<<<G(g.n_rows), B, 0, s>>>(g.h, g.n_upd + 1, g.n_rows, g.row_sens.p, guard); LAUNCH(c);
+        k_mrg_sensors<<<G(n), B, 0, s>>>(c->dn, c->dv, g.h, n, c->f_posidx.p, c->order.p, c->rows.p, g.n_upd + 1, guard); KEND(c); }
     }
     cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(c->h_stat + 7, c->draws.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s);
@@ -1051,9 +1198,11 @@ static int step_back(symgpu_ctx* c) {
     std::sort(c->last_exited.begin(), c->last_exited.end(), [&](const ExitRow& a, const ExitRow& b) { return c->mp.on ? a.id < b.id : a.slot < b.slot; }); }
   // global random sequence: account for the draws made on the device during this step
   unsigned dd = (unsigned)c->h_stat[7];
-  if (c->mp.on && has_entries) c->mp.draw_delta = dd - c->dev_draws_seen;      // committed with the other ranks' draws (symgpu_mp_commit_draws)
-  else if (has_entries) c->rng.skip(dd - c->dev_draws_seen); else c->rng.count += dd - c->dev_draws_seen;
-  c->dev_draws_seen = dd;
+  if (c->mp.on) {                                                              // partitioned runs: the host owns the stream (no device draws with values there)
+    if (has_entries) c->mp.draw_delta = dd - c->dev_draws_seen;               // committed with the other ranks' draws (symgpu_mp_commit_draws)
+    else c->rng.count += dd - c->dev_draws_seen; }
+  else c->host_rng_fresh = false;                                              // the stream advanced on the device (next-lane memos, lane changes, merge points)
+  c->dev_draws_seen = dd; c->mg.n_upd++;
   for (size_t i = 0; i < desc.size(); i++) { EntryLane* el = desc_lane[i];
     if (eres[i] & 1) el->pret_slot = -1;
     if (eres[i] & 2) el->pool_slot = -1; }
@@ -1386,7 +1535,20 @@ extern "C" long symgpu_kernel_launches(symgpu_ctx* c, int k) { return c && k >= 
 extern "C" long long symgpu_vehicle_steps(symgpu_ctx* c) { return c ? c->veh_steps : 0; }
 extern "C" int symgpu_num_vehicles(symgpu_ctx* c) { return c ? c->n_alive : SYMGPU_E_ARG; }
 extern "C" double symgpu_time(symgpu_ctx* c) { return c ? c->t : 0.0; }
-extern "C" unsigned symgpu_rng_count(symgpu_ctx* c) { return c ? c->rng.count : 0; }
+extern "C" unsigned symgpu_rng_count(symgpu_ctx* c) {
+  if (!c) return 0;
+  if (!c->mp.on && !c->host_rng_fresh) { cudaSetDevice(c->device); if (cudaMemcpy(&c->rng, c->lc_rng.p, sizeof(DevRng), cudaMemcpyDeviceToHost) == cudaSuccess) c->host_rng_fresh = true; }
+  return c->rng.count;
+}
+// merge points: last passage instant and draw counter of every point, in Liste_convergents order (test access)
+extern "C" int symgpu_get_merge_state(symgpu_ctx* c, int cap, double* inst_last, int* rand_numbers) {
+  if (!c) return SYMGPU_E_ARG;
+  const int np = c->mg.on ? c->mg.h.n_pt : 0; const int m = std::min(np, cap);
+  CK(cudaSetDevice(c->device));
+  if (m > 0 && inst_last) CK(cudaMemcpy(inst_last, c->mg.pt_last.p, m * sizeof(double), cudaMemcpyDeviceToHost));
+  if (m > 0 && rand_numbers) CK(cudaMemcpy(rand_numbers, c->mg.pt_rand.p, m * sizeof(int), cudaMemcpyDeviceToHost));
+  return np;
+}
 extern "C" double symgpu_last_step_ms(symgpu_ctx* c) { return c ? c->last_ms : 0.0; }
 extern "C" int symgpu_num_links(symgpu_ctx* c) { return c ? c->net.n_links() : SYMGPU_E_ARG; }
 extern "C" int symgpu_num_classes(symgpu_ctx* c) { return c ? c->net.n_cls() : SYMGPU_E_ARG; }

@@ -17,7 +17,9 @@ struct FlatNet {
   std::vector<double> params, cls, link_f, lane_f, succ_f, sl_f, ctrl_f, seq_f, sig_f, dem_f, dest_f, droute_f,
       lanecoef_f, typecoef_f, exit_f, iv_f, link_geom;
   std::vector<int> link_i, lane_i, succ_off, succ_i, sl_off, sl_i, ctrl_i, seq_i, sig_i, node_i, route_off, route_links,
-      entry_i, dest_i, droute_i, exit_i, iv_i, iv_id;
+      entry_i, dest_i, droute_i, exit_i, iv_i, iv_id,
+      cvg_i, cvgam_i, pt_i, ptam_i, cafmvt_i, cafmvt_links, lcam_off, lcam_links, lcav_off, lcav_links;   // merge points (row A10)
+  std::vector<double> cvg_f, cvg_tf;
   std::vector<std::string> link_names, node_names, cls_names;
   std::string error;
 
@@ -29,6 +31,9 @@ struct FlatNet {
   int n_init() const { return (int)iv_i.size() / 4; }
   int n_ctrl() const { return (int)ctrl_i.size() / 2; }
   int n_sl() const { return (int)sl_i.size() / 6; }
+  int n_cvg() const { return (int)cvg_i.size() / 8; }
+  int n_pt() const { return (int)pt_i.size() / 4; }
+  int n_nodes() const { return (int)node_i.size() / 4; }
 
   static void split_names(const std::vector<unsigned char>& raw, std::vector<std::string>& out) {
     std::string cur;
@@ -45,12 +50,14 @@ struct FlatNet {
         {"link_i", &link_i}, {"lane_i", &lane_i}, {"succ_off", &succ_off}, {"succ_i", &succ_i}, {"sl_off", &sl_off},
         {"sl_i", &sl_i}, {"ctrl_i", &ctrl_i}, {"seq_i", &seq_i}, {"sig_i", &sig_i}, {"node_i", &node_i},
         {"route_off", &route_off}, {"route_links", &route_links}, {"entry_i", &entry_i}, {"dest_i", &dest_i},
-        {"droute_i", &droute_i}, {"exit_i", &exit_i}, {"iv_i", &iv_i}, {"iv_id", &iv_id}};
+        {"droute_i", &droute_i}, {"exit_i", &exit_i}, {"iv_i", &iv_i}, {"iv_id", &iv_id},
+        {"cvg_i", &cvg_i}, {"cvgam_i", &cvgam_i}, {"pt_i", &pt_i}, {"ptam_i", &ptam_i}, {"cafmvt_i", &cafmvt_i}, {"cafmvt_links", &cafmvt_links},
+        {"lcam_off", &lcam_off}, {"lcam_links", &lcam_links}, {"lcav_off", &lcav_off}, {"lcav_links", &lcav_links}};
     std::map<std::string, std::vector<double>*> dm = {
         {"params", &params}, {"cls", &cls}, {"link_f", &link_f}, {"lane_f", &lane_f}, {"succ_f", &succ_f},
         {"sl_f", &sl_f}, {"ctrl_f", &ctrl_f}, {"seq_f", &seq_f}, {"sig_f", &sig_f}, {"dem_f", &dem_f},
         {"dest_f", &dest_f}, {"droute_f", &droute_f}, {"lanecoef_f", &lanecoef_f}, {"typecoef_f", &typecoef_f},
-        {"exit_f", &exit_f}, {"iv_f", &iv_f}, {"link_geom", &link_geom}};
+        {"exit_f", &exit_f}, {"iv_f", &iv_f}, {"link_geom", &link_geom}, {"cvg_f", &cvg_f}, {"cvg_tf", &cvg_tf}};
     for (uint32_t s = 0; s < n; s++) {
       char name[25] = {0}; uint32_t dt; uint64_t cnt;
       if (fread(name, 1, 24, f) != 24 || fread(&dt, 4, 1, f) != 1 || fread(&cnt, 8, 1, f) != 1) { fclose(f); error = "truncated section header"; return false; }
@@ -81,6 +88,9 @@ struct FlatNet {
     if (lane_i.size() % 4 || lane_f.size() != (size_t)n_lanes()) { error = "lane tables malformed"; return false; }
     if (succ_off.size() != (size_t)n_lanes() + 1 || sl_off.size() != (size_t)n_lanes() + 1) { error = "CSR offsets malformed"; return false; }
     if (route_off.empty()) route_off.push_back(0);
+    if (lcam_off.size() != (size_t)n_links() + 1) { lcam_off.assign(n_links() + 1, 0); lcam_links.clear(); }
+    if (lcav_off.size() != (size_t)n_links() + 1) { lcav_off.assign(n_links() + 1, 0); lcav_links.clear(); }
+    if (cvg_f.size() != (size_t)n_cvg() * 4 || cvg_tf.size() != (size_t)n_cvg() * n_cls()) { error = "merge tables malformed"; return false; }
     return true;
   }
 };

@@ -89,7 +89,7 @@ constexpr int kLocalIters = SYM_LOCAL_ITERS;
 #define SYM_RELAX_THREADS 128
 #endif
 __global__ void __launch_bounds__(SYM_RELAX_THREADS, SYM_RELAX_BLOCKS) k_relax(DevNet N, DevVeh V, DevLaneDyn LD, const double* __restrict__ rows, double* b_goal, int* b_flags,
-                                               double* vl_used, int* rl_lead, int n_sorted, int first, const int* prev, int* changed, double inst) {
+                                               double* vl_used, int* rl_lead, int n_sorted, int first, const int* prev, int* changed, double inst, const DevMrg* M, const double* mrgx) {
   if (!first && *prev == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const Row r = row_at(rows, p < n_sorted ? p : 0);
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(SYM_RELAX_THREADS, SYM_RELAX_BLOCKS) k_relax(D
     } else {
       dep = rl_lead[p];
       if (dep >= 0) { vL = __ldcg(&V.vit_n[dep]); vl_last = vl_used[p]; need = __double_as_longlong(vL) != __double_as_longlong(vl_last); }
+      cutl = false;                                  // a cut leader is no dependency (dep = -1): later sweeps never recompute such a vehicle
     }
   }
   int nch = 0;
@@ -113,10 +114,10 @@ __global__ void __launch_bounds__(SYM_RELAX_THREADS, SYM_RELAX_BLOCKS) k_relax(D
       vl_last = vL; touched = true;
       double v0;
       if (hdr & H_SLOW) {                           // context longer than the row holds: general path (idempotent form)
-        follow_one(cP_ref(), N, V, LD, x, !cutl, inst, r[R_CPOS], true, dep >= 0 ? &vL : nullptr, &v0);
+        follow_one(cP_ref(), N, V, LD, x, !cutl, inst, r[R_CPOS], true, dep >= 0 ? &vL : nullptr, &v0, M, p, hdr);
         b_flags[p] = B_SLOWDONE;
       } else {
-        BOut o = phase_b(cP_ref(), r, vL, inst);
+        BOut o = phase_b(cP_ref(), r, vL, inst, mrgx + (size_t)p * 6, cutl);
         b_goal[p] = o.goal; b_flags[p] = o.flags; V.dn[x] = o.dn_end; V.cpos[x] = o.cpos; v0 = o.v0;
       }
       if (first && it == 0) V.computed[x] = 1;
@@ -142,11 +143,11 @@ __global__ void k_relax_done(FlowCtl* ctl, int nb) {
   int ok = 0; for (int j = 1; j <= nb; j++) if (ctl->changed[j] == 0) ok = 1;
   ctl->converged = ok;
 }
-__global__ void k_place(DevNet N, DevVeh V, const double* rows, const double* b_goal, const int* b_flags, int n_sorted, double inst, const int* guard) {
+__global__ void k_place(DevNet N, DevVeh V, const double* rows, const double* b_goal, const int* b_flags, int n_sorted, double inst, const int* guard, const DevMrg* M) {
   if (guard && *guard == 0) return;              // launched ahead of the convergence check (engine.cu: step_back)
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_sorted) return;
-  phase_c(cP_ref(), N, V, rows, b_goal, b_flags, p, inst);
+  phase_c(cP_ref(), N, V, rows, b_goal, b_flags, p, inst, M);
 }
 
 // ---- leader loops: pointer jumping on the segment graph ---------------------------------------------------------------

@@ -1,0 +1,779 @@
+// merge.cuh — merge points: Convergent / PointDeConvergence on the device.
+//
+// Reference: PointDeConvergence::CalculInsertion (convergent.cpp:333-990), Convergent::ComputeTraffic / CalculVitesseLeader
+// (:1121-1168, :1368-1403), AbstractCarFollowing::TestConvergentInsertion (carFollowing/AbstractCarFollowing.cpp:336-664),
+// CarrefourAFeuxEx::UpdateConvergents (CarrefourAFeuxEx.cpp:1386-1593), the merge sensors (reseau.cpp:2432-2600,
+// sensors/SensorsManager.cpp:462-700) and the leader-speed correction of NewellCarFollowing.cpp:266-298.
+//
+// In the reference the merge points are post-processed one after the other (Liste_convergents is a std::map: id order) after
+// every vehicle has been computed; a point only reads and rewrites a handful of vehicles (the vehicle waiting on a non-priority
+// branch, the follower on the priority branch, the leader downstream), and some points draw from the global random stream.
+// On the device:
+//   k_mrg_rank    per point, start of the step: priority levels of the points inside signalised junctions from this step's
+//                 signal colours and the occupancy of the internal lanes at the end of the previous step
+//   (phase A/B)   rows.cuh: the speed imposed on the head of a non-priority branch and the pessimistic leader speed
+//   k_mrg_probe   per point, parallel, read-only: which vehicles the point would touch -> ownership marks (min / max point)
+//   k_mrg_eval    per point, parallel: points whose vehicles no other point touches ("clean") are processed at once, unless
+//                 their decision needs VALUES of the random stream (congested branch, AbstractCarFollowing.cpp:357-375)
+//   k_mrg_walk    one block, points in id order: stream offsets of every point from the draw counts, the draws of the points
+//                 that need values, and the few points that share a vehicle with another one, literally in order
+//   k_mrg_apply   per point, parallel: the clean points whose decision the walk has just made
+//   k_mrg_sensors per vehicle, end of the step: merge sensor counts (integer atomics)
+// Every arithmetic expression is the reference's, in its order (fp64, no contraction).
+#pragma once
+#include "lanechange.cuh"
+#include "micro.cuh"
+#include "rows.cuh"
+
+namespace symb200 {
+
+constexpr int kMrgInv = 12;       // vehicles one merge point may touch (waiting candidates, followers, leader, upstream memo misses)
+constexpr int kMrgLanes = kMaxCtx;
+enum : int { MS_NONE = 0, MS_DONE = 1, MS_VALUES = 2, MS_DIRTY = 3, MS_OVERFLOW = 4 };
+enum : int { MM_PROBE = 0, MM_EVAL = 1, MM_DECIDED = 2, MM_SERIAL = 3 };
+
+struct DevMrg {
+  int n_cvg, n_pt, n_sens, n_cls;
+  double max_debit_max, max_vit_max, vx0;
+  const int* link_cvg;                                                     // link -> Convergent at its downstream end (-1)
+  const int *cvg_node, *cvg_down, *cvg_pt0, *cvg_npt, *cvg_am0, *cvg_nam, *cvg_win, *cvg_sens0, *cvg_am;
+  const double *cvg_gamma, *cvg_mu, *cvg_poscpt, *cvg_tf;
+  const int *pt_cvg, *pt_down, *pt_vam0, *pt_nvam, *pt_mode, *pt_pm0;
+  const int *vam_lane, *vam_ref; int* vam_niv;
+  const int *pm_vam, *pm_sl, *pm_occ0, *pm_occ;                            // movements of the junction that pass through a point
+  const int *lane_pt, *lane_vam;                                           // upstream lane -> its point (first in cvg order) and entry
+  const int *sens_link, *sens_cnt0; const double* sens_pos; int* cnt;      // ponctual sensors; cnt: [type][lane][window] ring per sensor
+  const int *sens_win;
+  const int *lsens0, *lsens;                                               // link -> sensors (Tuyau::getListeCapteursConvergents)
+  const int *lcam0, *lcam, *lcav0, *lcav;                                  // connections: m_LstTuyAm / m_LstTuyAv
+  const int *lmv0, *lmv_ent, *lmv_exit;                                    // internal link -> (entry link, exit link) of its movements
+  const int *fm0, *fm_exit, *fm_tl0, *fm_ntl, *fm_tl;                      // entry link -> per exit link: internal links of the FIRST movement
+  const int* node_type;
+  double* pt_last; int *pt_rand, *pt_free;                                 // m_dbInstLastPassage, m_nRandNumbers, m_bFreeFlow
+  int* cand_up;                                                            // upstream lane -> first vehicle that crossed it entirely this step
+  int *own_min, *own_max;                                                  // per vehicle slot: lowest / highest point that touches it
+  int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw; double* proba;       // per point, this step
+  int *nused, *nvoie;                                                      // per vehicle: intermediate lanes used this step; m_pNextVoie (sticky)
+  double* mrgx;                                                            // per order position: phase A -> phase B side record (6 doubles)
+  DevRng* rng; unsigned* draws;                                            // the stream (device copy) and the cumulative count of count-only draws
+  long long* counters;
+};
+enum { MX_OWN = 0, MX_POSL, MX_LENL, MX_BORNE, MX_REPL, MX_VUNC, kMrgX = 6 };
+
+struct MrgView { const DevParams& P; const DevNet& N; const DevVeh& V; const DevMrg& M; const int* order; const double* skey; const int* lane_start;
+                 const int* lane_count; const int* posidx; const double* rows; double inst; int n_upd; };
+
+__device__ __forceinline__ double min_std(double a, double b) { return (b < a) ? b : a; }      // std::min<double>, also for NaN operands
+__device__ __forceinline__ double mkey(const MrgView& W, int q) { double k = W.skey[q]; return k <= SYM_UNDEF ? 0.0 : k; }
+__device__ __forceinline__ double mpos1(const MrgView& W, int x) { double p = snap_pos(W.V.pos[x]); return p <= SYM_UNDEF ? 0.0 : p; }
+__device__ __forceinline__ int mlink1(const MrgView& W, int x) { return (W.V.oflags[x] & O_LINK1NULL) ? -1 : W.N.lane_link[W.V.lane[x]]; }
+__device__ __forceinline__ double cvg_tf(const MrgView& W, int c, int k) { return fmax(W.M.cvg_tf[c * W.M.n_cls + k], 1 / debit_max(W.P.cls[k])); }
+
+// Reseau::GetFirstVehicule / GetLastVehicule over a group of equal positions [g0, g1) of the lane order (id ascending), with the
+// leaders of THIS step's contexts (every vehicle has been computed when the merge points are processed)
+__device__ inline int grp_first(const MrgView& W, int g0, int g1) {                            // reseau.cpp:14084-14128
+  if (g1 - g0 == 1) return W.order[g0];
+  for (int i = g0; i < g1; i++) { int ld = W.V.ctx_leader[W.order[i]]; if (ld < 0) return W.order[i];
+    bool found = false; for (int j = g0; j < g1 && !found; j++) if (j != i && W.order[j] == ld) found = true;
+    if (!found) return W.order[i]; }
+  return W.order[g1 - 1];
+}
+__device__ inline int grp_last(const MrgView& W, int g0, int g1) {                             // reseau.cpp:14041-14081
+  if (g1 - g0 == 1) return W.order[g0];
+  for (int i = g0; i < g1; i++) { bool fol = false;
+    for (int j = g0; j < g1 && !fol; j++) if (j != i && W.V.ctx_leader[W.order[j]] == W.order[i]) fol = true;
+    if (!fol) return W.order[i]; }
+  return W.order[g1 - 1];
+}
+// largest key < pos (strict) or <= pos: [g0, g1) of that group, false when none
+__device__ inline bool grp_below(const MrgView& W, int lane, double pos, bool strict, int* g0, int* g1, double* key) {
+  const int s = W.lane_start[lane]; int lo = s, hi = s + W.lane_count[lane];
+  while (lo < hi) { int m = (lo + hi) >> 1; double k = mkey(W, m); if (strict ? (k < pos) : (k <= pos)) lo = m + 1; else hi = m; }
+  if (lo == s) return false;
+  const double k = mkey(W, lo - 1); int a = lo - 1; while (a - 1 >= s && mkey(W, a - 1) == k) a--;
+  *g0 = a; *g1 = lo; *key = k; return true;
+}
+// Reseau::GetNearAmontVehicule reseau.cpp:3374-3520
+__device__ inline int near_amont_m(const MrgView& W, int lane, double pos, double dstmax) {
+  if (lane < 0) return -1;
+  const int link0 = W.N.lane_link[lane];
+  if (dstmax < 0) dstmax = 9999;
+  int g0, g1; double pt;
+  bool have = grp_below(W, lane, pos, true, &g0, &g1, &pt);
+  if (dstmax > 0 && have && (pos - pt) < dstmax) return grp_first(W, g0, g1);
+  dstmax -= pos;
+  if (have) return -1;                                                                     // :3469-3473 with dbPosTmp reset to -99999
+  const int pv = W.N.lane_prev[lane];
+  if (pv >= 0 && dstmax > 0) {
+    pos = W.N.lane_len[pv] + 0.001;
+    if (grp_below(W, pv, pos, false, &g0, &g1, &pt)) return (pos - pt) < dstmax ? grp_first(W, g0, g1) : -1;
+  }
+  dstmax -= pos;
+  if (dstmax > 0 && W.M.lcam0[link0 + 1] - W.M.lcam0[link0] == 1) {
+    const int ul = W.M.lcam[W.M.lcam0[link0]];
+    if (W.N.link_nl[ul] == 1) { const int up = W.N.link_first[ul]; pos = W.N.lane_len[up] + 0.001;
+      if (grp_below(W, up, pos, false, &g0, &g1, &pt)) return grp_first(W, g0, g1); }
+  }
+  return -1;
+}
+// Reseau::GetNearAvalVehicule reseau.cpp:3583-3640
+__device__ inline int near_aval_m(const MrgView& W, int lane, double pos) {
+  if (lane < 0) return -1;
+  const int s = W.lane_start[lane], e = s + W.lane_count[lane]; int lo = s, hi = e;
+  while (lo < hi) { int m = (lo + hi) >> 1; if (mkey(W, m) < pos) lo = m + 1; else hi = m; }
+  if (lo == e) return -1;
+  const double k = mkey(W, lo); if (!(k <= W.N.lane_len[lane] + 0.00001)) return -1;
+  int b = lo + 1; while (b < e && mkey(W, b) == k) b++;
+  return grp_last(W, lo, b);
+}
+// nearest vehicle with pos >= 0 on a lane (second and third stage of GetPrevVehicule, reseau.cpp:3740-3815), excluding `excl`
+__device__ inline int first_from_zero(const MrgView& W, int lane, int excl) {
+  const int s = W.lane_start[lane], e = s + W.lane_count[lane];
+  int a = s; while (a < e && (W.order[a] == excl || !(mkey(W, a) >= 0))) a++;
+  if (a == e || !(mkey(W, a) <= W.N.lane_len[lane] + 1)) return -1;
+  const double k = mkey(W, a); int c[kTie]; int n = 0;
+  for (int b = a; b < e && mkey(W, b) == k; b++) if (W.order[b] != excl && n < kTie) c[n++] = W.order[b];
+  if (n == 1) return c[0];
+  for (int i = 0; i < n; i++) { bool fol = false; for (int j = 0; j < n && !fol; j++) if (j != i && W.V.ctx_leader[c[j]] == c[i]) fol = true; if (!fol) return c[i]; }
+  return c[n - 1];
+}
+// the context lanes of a vehicle (row of phase A, or the per-vehicle arrays for long contexts and the origins' queue heads)
+__device__ inline int ctx_lanes_of(const MrgView& W, int x, int* lanes) {
+  const int st = W.V.status[x];
+  if (st == ST_ALIVE || st == ST_NEW) { const int p = W.posidx[x];
+    if (W.order[p] == x) { const Row r = row_at(W.rows, p); const int nl = (hi32(r[R_I0]) >> 8) & 15;
+      if (nl <= kRowLanes) { for (int k = 0; k < nl; k++) lanes[k] = lo32(r[R_REC + kRecD * k + 4]); return nl; } } }
+  const int nl = W.V.ctx_nl[x]; for (int k = 0; k < nl; k++) lanes[k] = W.V.ctx_lane[x * kMaxCtx + k];
+  return nl;
+}
+// Vehicule::GetDstParcourueEx vehicule.cpp:3879-3915 (m_LstUsedLanes = the first `nused` context lanes after the start lane)
+__device__ inline double dst_ex(const MrgView& W, int x) {
+  const int l1 = W.V.lane[x], l0 = W.V.lane_n[x]; const int k1 = mlink1(W, x), k0 = W.N.lane_link[l0];
+  if (k0 == k1) return W.V.pos_n[x] - mpos1(W, x);
+  if (k1 < 0 && l1 == l0) return W.V.pos_n[x];
+  double d = W.N.lane_len[l1] - mpos1(W, x);
+  const int nu = W.M.nused[x];
+  if (nu > 0) { int lanes[kMrgLanes]; ctx_lanes_of(W, x, lanes); for (int k = 1; k <= nu; k++) if (l0 != lanes[k]) d += W.N.lane_len[lanes[k]]; }
+  return d + W.V.pos_n[x];
+}
+// Vehicule::UpdateLstUsedLanes vehicule.cpp:1751-1775 after the end lane has been rewritten
+__device__ inline void update_used(const MrgView& W, int x) {
+  int nu = W.M.nused[x]; if (nu <= 0) return;
+  int lanes[kMrgLanes]; ctx_lanes_of(W, x, lanes);
+  const int l0 = W.V.lane_n[x];
+  for (int k = 1; k <= nu; k++) if (lanes[k] == l0) { nu = k - 1; break; }
+  if (W.N.lane_link[l0] == mlink1(W, x)) nu = 0;
+  W.M.nused[x] = nu;
+}
+__device__ inline void set_acc_m(const MrgView& W, int x, double a) { if (fabs(a) < 0.000001) a = 0; W.V.acc_n[x] = a; }
+// a vehicle that does not insert waits at the end of its upstream lane (convergent.cpp:405-412, :433-438, :819-827, :972-987)
+__device__ inline void immobilise(const MrgView& W, int x, int lane, bool acc_sic) {
+  W.V.pos_n[x] = W.N.lane_len[lane] - 0.0001; W.V.lane_n[x] = lane;
+  W.V.vit_n[x] = dst_ex(W, x) / W.P.dt;
+  set_acc_m(W, x, acc_sic ? W.V.vit[x] / W.P.dt : (W.V.vit_n[x] - W.V.vit[x]) / W.P.dt);
+  update_used(W, x);
+}
+// Vehicule::IsItineraire vehicule.cpp:4060-4160
+__device__ inline bool is_itineraire(const MrgView& W, int x, int link) {
+  const int ro = W.N.route_off[W.V.route[x]], re = W.N.route_off[W.V.route[x] + 1];
+  for (int k = ro; k < re; k++) if (W.N.route_links[k] == link) return true;
+  const int br = W.N.link_brick[link];
+  if (br >= 0) for (int k = ro; k + 1 < re; k++) if (W.N.link_down[W.N.route_links[k]] == br)
+    for (int m = W.M.lmv0[link]; m < W.M.lmv0[link + 1]; m++) if (W.M.lmv_ent[m] == W.N.route_links[k] && W.M.lmv_exit[m] == W.N.route_links[k + 1]) return true;
+  return false;
+}
+// Vehicule::CalculPosition vehicule.cpp:4615-4760 over Reseau::ComputeItineraireComplet (reseau.cpp:14002-14032)
+__device__ inline double calcul_position(const MrgView& W, int x, double tr, int lane) {
+  double p = mpos1(W, x) + W.V.vit_n[x] * tr;
+  const int l1 = W.V.lane[x]; const int k1 = W.N.lane_link[l1], kt = W.N.lane_link[lane];
+  if (kt == k1) return p;
+  const int ro = W.N.route_off[W.V.route[x]], re = W.N.route_off[W.V.route[x] + 1];
+  bool started = false;
+  for (int k = ro; k < re; k++) {
+    const int cur = W.N.route_links[k];
+    if (k > ro) {                                                                          // internal links of the first movement between route[k-1] and route[k]
+      const int prev = W.N.route_links[k - 1];
+      for (int f = W.M.fm0[prev]; f < W.M.fm0[prev + 1]; f++) if (W.M.fm_exit[f] == cur) {
+        for (int t = W.M.fm_tl0[f]; t < W.M.fm_tl0[f] + W.M.fm_ntl[f]; t++) { const int il = W.M.fm_tl[t];
+          if (started) { if (il == kt) return p; p -= W.N.link_len[il]; }
+          else if (il == k1) { started = true; p = -(W.N.lane_len[l1] - p); } }
+        break; }
+    }
+    if (started) { if (cur == kt) return p; p -= W.N.link_len[cur]; }
+    else if (cur == k1) { started = true; p = -(W.N.lane_len[l1] - p); }
+  }
+  return 9999;
+}
+// Vehicule::CalculNextVoie with its memoised draw (GetTirage, vehicule.cpp:1779-1795).  probe: nothing is written, a miss is
+// reported through *miss.  Returns the next lane; *ndraw is incremented when a draw is consumed.
+__device__ inline int next_voie_m(const MrgView& W, int x, int lane, bool probe, int* ndraw, bool* miss) {
+  int tl; const int nx = next_voie(W.N, W.V.route[x], W.V.route_pos[x], lane, &tl);
+  if (tl >= 0) { int* memo = &W.V.memo[x * kMemo]; bool hit = false; for (int k = 0; k < kMemo; k++) if (memo[k] == tl) hit = true;
+    if (!hit) { (*ndraw)++; if (miss) *miss = true; if (!probe) memo_touch(memo, tl); } }
+  return nx;
+}
+struct MrgAcc { int inv[kMrgInv]; int ninv; int ndraw; bool probe; bool overflow; };
+__device__ inline void touch(MrgAcc& A, int x) { if (x < 0) return; for (int k = 0; k < A.ninv; k++) if (A.inv[k] == x) return; if (A.ninv < kMrgInv) A.inv[A.ninv++] = x; else A.overflow = true; }
+// Reseau::GetVehiculeAmont reseau.cpp:9638-9690: depth-first over the upstream connections, first lane of every link
+__device__ inline int vehicule_amont(const MrgView& W, MrgAcc& A, int link, double dst) {
+  struct Fr { int link, it; double cum; } stk[6]; int sp = 0;
+  stk[0] = {link, -1, 0.0};
+  while (sp >= 0) {
+    Fr& f = stk[sp];
+    if (f.it < 0) {                                                                        // entering the link
+      const int v = near_amont_m(W, W.N.link_first[f.link], W.N.link_len[f.link], -1.0);
+      if (v >= 0) {                                                                        // found: unwind through the callers' tests (:9679-9683)
+        int res = v; int lvl = sp - 1;
+        while (lvl >= 0 && res >= 0) { const Fr& c = stk[lvl]; bool ok = false;
+          if (dst > c.cum + W.N.link_len[c.link] - mpos1(W, res)) { bool miss = false; int nd = 0;
+            const int nx = next_voie_m(W, res, W.V.lane[res], A.probe, &nd, &miss); A.ndraw += nd; if (miss) touch(A, res);
+            ok = nx == W.N.link_first[c.link]; }
+          if (ok) lvl--; else break; }
+        if (lvl < 0) return res;
+        sp = lvl; continue;                                                                // the caller at `lvl` goes on with its next upstream link
+      }
+      const int nt = W.M.node_type[W.N.link_up[f.link]];
+      if (dst < f.cum || nt == 'E' || nt == 'S' || nt == 'P' || sp == 5) { sp--; continue; }
+      f.it = 0;
+    }
+    const int a0 = W.M.lcam0[f.link];
+    if (a0 + f.it >= W.M.lcam0[f.link + 1]) { sp--; continue; }
+    const int am = W.M.lcam[a0 + f.it]; f.it++;
+    stk[sp + 1] = {am, -1, f.cum + W.N.link_len[f.link]}; sp++;
+  }
+  return -1;
+}
+// sensors: SensorsManager::GetDebitMoyen / GetNbVehTotal / GetRatioTypeVehicule (sensors/SensorsManager.cpp:551-700).
+// The reference shifts its per-step arrays; here a ring: logical slot j of update count n sits at (max(0, n - W) + j) % W.
+__device__ inline int capteur_of(const MrgView& W, int c, int link) {                          // Convergent::GetCapteur :1000-1014
+  if (link == W.M.cvg_down[c]) return W.M.cvg_sens0[c];
+  for (int k = 0; k <= W.M.cvg_nam[c]; k++) if (W.M.sens_link[W.M.cvg_sens0[c] + k] == link) return W.M.cvg_sens0[c] + k;
+  return -1;
+}
+__device__ inline int nb_inst_of(int n_upd, int win) { return n_upd == 0 ? -1 : min(n_upd - 1, win - 1); }
+__device__ inline double cpt_somme(const MrgView& W, int s, int nvoie, int type) {
+  const int link = W.M.sens_link[s]; const int nl = W.N.link_nl[link]; if (nvoie < 0 || nvoie >= nl) return 0;
+  const int win = W.M.sens_win[s]; const int kmax = min(nb_inst_of(W.n_upd, win), win); const int head = max(0, W.n_upd - win) % max(1, win);
+  double sum = 0;
+  for (int t = 0; t < W.M.n_cls; t++) if (type < 0 || t == type) { const int* a = W.M.cnt + W.M.sens_cnt0[s] + (t * nl + nvoie) * win;
+    for (int j = 0; j < kmax; j++) sum += (double)a[(head + j) % win]; }
+  return sum;
+}
+__device__ inline double debit_moyen(const MrgView& W, int s, int nvoie) { if (s < 0) return 0; const int win = W.M.sens_win[s];
+  return cpt_somme(W, s, nvoie, -1) / (min(nb_inst_of(W.n_upd, win), win) * W.P.dt); }
+__device__ inline double ratio_type(const MrgView& W, int s, int nvoie, int type) { if (s < 0) return 0; const double tot = cpt_somme(W, s, nvoie, -1);
+  return tot > 0 ? cpt_somme(W, s, nvoie, type) / tot : 0; }
+
+// AbstractCarFollowing::Compute on a post-processing context (leader already computed, no leader corrections):
+// NewellCarFollowing.cpp:53-136, :204-398 ; GippsCarFollowing.cpp:50-122 ; IDMCarFollowing.cpp:61-211 ; AbstractCarFollowing.cpp:692-716
+__device__ inline double law_dist(const MrgView& W, int x, double dtv, const int* lanes, int nl, double start, int L, double dist, double dn0) {
+  const DevParams& P = W.P; const DevNet& n = W.N; const DevCls& c = P.cls[W.V.cls[x]]; const double v1 = W.V.vit[x];
+  if (c.law == 0) {
+    double trav = 0, rem = dtv;                                                            // ComputeFreeFlowDistance :70-111
+    for (int k = 0; k < nl; k++) { const int ln = lanes[k]; const double sp = k == 0 ? start : 0.0; const double lex = len_ex(P, n, ln);
+      double vdes = fmin(c.vx, n.link_vreg[n.lane_link[ln]]);
+      if (P.accbornee) vdes = fmin(vdes, v1 + acc_max(c, v1) * dtv);
+      const double tt = (n.lane_len[ln] - sp) / vdes;
+      if (tt >= rem || k == nl - 1) { trav += rem * vdes; break; }
+      trav += lex - sp; rem -= tt; }
+    double d = trav;
+    if (L >= 0) {                                                                          // ComputeCongestedDistance :204-398 (leader computed)
+      const DevCls& cl = P.cls[W.V.cls[L]]; const double vL1 = W.V.vit[L]; const double vL = W.V.vit_n[L];
+      const double kv = -cl.kx * cl.w / (vL1 - cl.w), kvfin = -cl.kx * cl.w / (vL - cl.w);
+      const double r_self = dn0 / (-c.kx * cl.w);
+      double res;
+      if ((P.dt - r_self) >= -0.0001) res = fmin(1.0, (dn0 / kv + fmin(r_self / dtv * (vL - vL1) + P.relax, vL) * P.dt) * kvfin);
+      else res = fmin(1.0, (dn0 / kv + fmin((vL - vL1) + P.relax, vL) * P.dt) * kvfin);
+      const double dn1 = fmax(dn0, res);
+      const double r = dn0 / (-cl.kx * cl.w);
+      double pc;
+      if ((P.dt - r) >= -0.0001) { pc = dist + vL * P.dt - dn1 / kvfin; if (pc <= 0.0001 && dn0 < 1) pc = dist + vL * P.dt - dn0 / kvfin; }
+      else { const double alpha = -cl.w * cl.kx * P.dt / dn0;
+        if (dtv < P.dt) pc = dist + vL * P.dt - dn1 / kvfin;
+        else { pc = alpha * dist + vL * P.dt - alpha * dn1 / kvfin; if (pc <= 0.0001 && dn0 < 1) pc = alpha * dist + vL * P.dt - alpha * dn0 / kvfin; } }
+      if (pc < d) d = pc;
+    }
+    return d;
+  }
+  const double vmaxl = fmin(c.vx, n.link_vreg[n.lane_link[lanes[0]]]);
+  if (c.law == 1) {
+    double vf = v1 + 2.5 * acc_max(c, v1) * dtv * (1 - v1 / vmaxl) * pow_half(0.025 + v1 / vmaxl);
+    if (L >= 0) { const DevCls& cl = P.cls[W.V.cls[L]]; const double vL1 = W.V.vit[L];
+      double dmax = -c.decel; if (dmax == 0) dmax = -DBL_MAX; double dlmax = -cl.decel; if (dlmax == 0) dlmax = -DBL_MAX;
+      const double fac = dmax * (dtv / 2.0 + 1); const double lenL = 1 / cl.kx - cl.esp;
+      const double sq = fac * fac - dmax * (2.0 * (dist - (lenL + c.esp)) - v1 * dtv - vL1 * vL1 / dlmax);
+      const double vc = sq >= 0 ? fac + sqrt(sq) : 0.0; if (vc < vf) vf = vc; }
+    return vf * dtv;
+  }
+  double relpos, relsp;
+  if (L >= 0) { const DevCls& cl = P.cls[W.V.cls[L]]; relpos = dist - (1 / cl.kx - cl.esp); relsp = v1 - W.V.vit[L]; } else { relpos = DBL_MAX; relsp = v1; }
+  const double amax = acc_max(c, v1); double dec = c.decel; if (dec == 0) dec = DBL_MAX;
+  double z; if (relpos <= 0) z = 2; else { const double dsp = c.esp + fmax(1 * v1 + (v1 * relsp) / (2.0 * sqrt(amax * dec)), 0.0); z = dsp / relpos; }
+  const double a = amax * (1.0 - pow_four(v1 / vmaxl) - pow_three_halves(z));
+  return v1 * dtv + 0.5 * a * dtv * dtv;
+}
+
+// priority of an upstream lane at its point: Convergent::IsVoieAmontNonPrioritaire convergent.cpp:1230-1258
+__device__ inline bool non_prioritaire(const DevMrg& M, int lane) {
+  const int p = M.lane_pt[lane]; if (p < 0) return false;
+  int niv = 0, nmin = INT_MAX;
+  for (int a = M.pt_vam0[p]; a < M.pt_vam0[p] + M.pt_nvam[p]; a++) { if (M.vam_lane[a] == lane) niv = M.vam_niv[a]; if (nmin > M.vam_niv[a]) nmin = M.vam_niv[a]; }
+  return niv > nmin && niv > 1;
+}
+// Convergent::CalculVitesseLeader convergent.cpp:1121-1168.  `nv` = the vehicle's sticky next lane (m_pNextVoie), already resolved.
+__device__ inline double vitesse_leader(const DevParams& P, const DevNet& N, const DevMrg& M, int c, int cls, int lane1, double pos1, int nv, double inst, double pas) {
+  double tl = -DBL_MIN;                                                                     // GetInstLastPassage :1170-1184 (UNDEF_INSTANT when not a point of this merge)
+  for (int p = M.cvg_pt0[c]; p < M.cvg_pt0[c] + M.cvg_npt[c]; p++) if (M.pt_down[p] == nv) { tl = M.pt_last[p]; break; }
+  const double tf = fmax(M.cvg_tf[c * M.n_cls + cls], 1 / debit_max(P.cls[cls]));
+  const double t0 = tl >= 0 ? tl + tf - (inst - pas) : 0;
+  if (t0 > 0) return (N.lane_len[lane1] - pos1) / t0;
+  return P.cls[cls].vx;
+}
+
+// ---- phase A hooks (declared in micro.cuh) --------------------------------------------------------------------------------
+// own: Convergent::ComputeTraffic (convergent.cpp:1368-1403, called from Vehicule::CheckNetworkInfluence vehicule.cpp:1668-1677): the head of
+//      a non-priority branch is held to the speed that brings it to the merge when the follow-up time has elapsed;
+// lead: NewellCarFollowing.cpp:266-298: the follower of such a head assumes it will not insert.
+// Returns the draws consumed (the head's next lane is resolved once and kept: Vehicule::m_pNextVoie is never reset).
+__device__ inline int mrg_phase_a(const DevParams& P, const DevNet& n, const DevVeh& V, const DevMrg* M, int i, int lane1, int L, double p1, double dtv,
+                                  double inst, int* memo, MrgA* out) {
+  int draws = 0;
+  const int cv = M->link_cvg[n.lane_link[lane1]];
+  if (cv >= 0 && V.ahead[i] < 0 && non_prioritaire(*M, lane1)) {
+    int nv = M->nvoie[i];
+    if (nv < 0) { int tl; nv = next_voie(n, V.route[i], V.route_pos[i], lane1, &tl); if (tl >= 0) draws += memo_touch(memo, tl); M->nvoie[i] = nv; }
+    out->own = true; out->mc = vitesse_leader(P, n, *M, cv, V.cls[i], lane1, p1, nv, inst, dtv) * dtv;
+  }
+  if (L >= 0 && P.cls[V.cls[i]].law == 0 && V.status[L] == ST_ALIVE) {                     // the leader has a link at index 1
+    const int ll = V.lane[L]; const int kl = n.lane_link[ll]; const int cl = M->link_cvg[kl];
+    if (n.link_type[kl] == 'C' && cl >= 0 && M->cvg_nam[cl] >= 1 && V.ahead[L] < 0 && non_prioritaire(*M, ll)) {
+      const DevCls& kc = P.cls[V.cls[L]]; const double pl = snap_pos(V.pos[L]); const double vl1 = V.vit[L];
+      int nvl = M->nvoie[L]; if (nvl < 0) { int tl; nvl = next_voie(n, V.route[L], V.route_pos[L], ll, &tl); }   // the leader's own thread stores it and counts the draw
+      out->lead = true; out->posl = pl; out->lenl = n.lane_len[ll];
+      const double a = vl1 + acc_max(kc, V.vit[i]) * dtv, b = n.link_vreg[kl];            // sic: the leader's acceleration table at the follower's speed
+      out->borne = (b < a) ? b : a;
+      out->repl = (n.lane_len[ll] - pl) / dtv;
+      out->vunc = vitesse_leader(P, n, *M, cl, V.cls[L], ll, pl <= SYM_UNDEF ? 0.0 : pl, nvl, inst, dtv);
+    }
+  }
+  return draws;
+}
+__device__ inline void mrg_store(const DevMrg* M, int p, const MrgA& a) {
+  if (!a.own && !a.lead) return;
+  double* x = M->mrgx + (size_t)p * kMrgX;
+  if (a.own) x[MX_OWN] = a.mc;
+  if (a.lead) { x[MX_POSL] = a.posl; x[MX_LENL] = a.lenl; x[MX_BORNE] = a.borne; x[MX_REPL] = a.repl; x[MX_VUNC] = a.vunc; }
+}
+__device__ inline void mrg_load(const DevMrg* M, int p, int hdr, MrgA* a) {
+  a->own = hdr & H_MRGOWN; a->lead = hdr & H_MRGLEAD;
+  if (!a->own && !a->lead) return;
+  const double* x = M->mrgx + (size_t)p * kMrgX;
+  if (a->own) a->mc = x[MX_OWN];
+  if (a->lead) { a->posl = x[MX_POSL]; a->lenl = x[MX_LENL]; a->borne = x[MX_BORNE]; a->repl = x[MX_REPL]; a->vunc = x[MX_VUNC]; }
+}
+// end of the placement loop (vehicule.cpp:1485-1502): the lanes before index kf were left during the step.  m_LstUsedLanes = the
+// intermediate ones; a vehicle that crossed a whole upstream lane of a merge is the lane's candidate "from upstream" (the vehicles that
+// started the step ON the lane are found in its slice, vehicule_en_attente).
+__device__ inline void mrg_register(const DevNet& n, const DevMrg* M, int i, int p, const int* lanes, int kf) {
+  M->nused[i] = kf > 0 ? kf - 1 : 0;
+  if (p < 0) return;
+  for (int k = 1; k < kf; k++) if (M->link_cvg[n.lane_link[lanes[k]]] >= 0) atomicMax(&M->cand_up[lanes[k]], p);
+}
+
+// first vehicle registered at the merge (ConnectionPonctuel::m_LstInsVeh: computation order, leader first) that went through
+// upstream lane `lane` and does not end the step on it: Convergent::GetVehiculeEnAttente convergent.cpp:1087-1116
+__device__ inline int vehicule_en_attente(const MrgView& W, int lane) {
+  const int s = W.lane_start[lane]; const double lim = W.N.lane_len[lane] - W.M.max_vit_max * W.P.dt - 1.0;   // a vehicle further upstream cannot have left the lane
+  for (int q = s + W.lane_count[lane] - 1; q >= s; q--) { if (mkey(W, q) < lim) break;
+    const int y = W.order[q]; if (W.V.lane_n[y] != lane) return y; }
+  const int k = W.M.cand_up[lane];
+  if (k >= 0) { const int y = W.order[k]; if (W.V.lane_n[y] != lane) return y; }
+  return -1;
+}
+
+struct MrgDraw { DevRng* rng; };   // serial mode: the positioned stream
+
+// PointDeConvergence::CalculInsertion convergent.cpp:333-990 + AbstractCarFollowing::TestConvergentInsertion (:336-664).
+// mode MM_PROBE   : nothing written; A collects the vehicles the point reads at index 0 or writes, and the count-only draws
+//      MM_EVAL    : processed completely unless the decision needs values of the stream -> MS_VALUES (nothing written)
+//      MM_DECIDED : as MM_EVAL, the congested test's outcome is M.decide[p]
+//      MM_SERIAL  : literal, drawing from the positioned stream `rng` (count-only draws are consumed from it as well)
+__device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, DevRng* rng) {
+  const DevMrg& M = W.M; const DevParams& P = W.P; const DevNet& N = W.N; const DevVeh& V = W.V;
+  const bool probe = mode == MM_PROBE; A.probe = probe;
+  const int c = M.pt_cvg[p]; const int v0 = M.pt_vam0[p], nv = M.pt_nvam[p]; const int down = M.pt_down[p];
+  if (nv == 0) return MS_NONE;
+  int VAmP = -1; int niv_prio = INT_MAX;
+  for (int a = v0; a < v0 + nv; a++) if (M.vam_niv[a] < niv_prio) { VAmP = M.vam_lane[a]; niv_prio = M.vam_niv[a]; }      // GetVoieAmontPrioritaire :77-100
+  int niv = 999, att = -1, att_lane = -1, VAmNP = -1;
+  for (int a = v0; a < v0 + nv; a++) if (M.vam_niv[a] > niv_prio) {                                                        // :376-449
+    const int lane = M.vam_lane[a];
+    int w = vehicule_en_attente(W, lane);
+    if (w >= 0) touch(A, w);
+    if (!(w >= 0 && V.vit_n[w] > 0)) w = -1;
+    if (w >= 0) {
+      if (M.vam_niv[a] < niv) { if (att >= 0 && !probe) immobilise(W, att, att_lane, true); att = w; att_lane = lane; VAmNP = lane; niv = M.vam_niv[a]; }
+      else if (!probe) immobilise(W, w, lane, true);
+    }
+  }
+  if (att < 0) return A.ninv ? MS_DONE : MS_NONE;
+  int fol = near_amont_m(W, VAmP, N.lane_len[VAmP] + 0.01, P.dt * M.max_vit_max);                                         // :463
+  int TAmP = N.lane_link[VAmP]; int nVoieGir = N.lane_num[VAmP];
+  auto drop = [&](int f) { if (f >= 0 && ((V.oflags[f] & O_LINK1NULL) || (V.oflags[f] & O_FEU))) return -1; return f; };  // :469-483 (every listed vehicle has a context)
+  fol = drop(fol);
+  if (fol < 0) for (int a = v0; a < v0 + nv; a++) if (M.vam_niv[a] < niv && M.vam_niv[a] > 1) {                           // :486-504
+    fol = near_amont_m(W, M.vam_lane[a], N.lane_len[M.vam_lane[a]], -1.0);
+    if (fol >= 0 && !(V.oflags[fol] & O_FEU)) { niv = M.vam_niv[a]; VAmP = M.vam_lane[a]; TAmP = N.lane_link[VAmP]; nVoieGir = N.lane_num[VAmP]; }
+    else fol = -1; }
+  fol = drop(fol);
+  if (fol >= 0 && !is_itineraire(W, fol, TAmP)) fol = -1;                                                                  // :525-528
+  touch(A, fol);
+  int lead = near_aval_m(W, down, 0.0);                                                                                   // :531-533
+  if (lead < 0 && !(V.oflags[att] & O_LINK1NULL)) {                                                                       // GetPrevVehicule(waiting, true) reseau.cpp:3650-3820
+    lead = V.ahead[att];
+    if (lead < 0) { const int k1 = N.lane_link[V.lane[att]]; const int ta = N.link_type[k1]; int voie = V.lane[att]; const int nvoie = N.lane_num[voie];
+      int next_link = (ta != 'S' && ta != 'P') ? k1 : -1;
+      if (ta == 'C' && M.lcav0[k1 + 1] > M.lcav0[k1]) { next_link = M.lcav[M.lcav0[k1]];
+        voie = next_voie_m(W, att, voie, probe, &A.ndraw, nullptr);
+        if (voie < 0) voie = N.link_first[next_link] + min(nvoie, N.link_nl[next_link] - 1);
+        lead = first_from_zero(W, voie, att); }
+      if (lead < 0 && next_link >= 0) for (int q = M.lcav0[next_link]; q < M.lcav0[next_link + 1]; q++) { const int nn = M.lcav[q];
+        if (!is_itineraire(W, att, nn)) continue;
+        voie = next_voie_m(W, att, voie, probe, &A.ndraw, nullptr);
+        if (voie < 0) voie = N.link_first[nn] + min(nvoie, N.link_nl[nn] - 1);
+        const int l2 = first_from_zero(W, voie, att); if (l2 >= 0) lead = l2; }
+    }
+  }
+  touch(A, lead);
+  bool free_flow;                                                                                                           // :538-556
+  { int w = near_amont_m(W, down, M.cvg_poscpt[c], -1.0); if (w >= 0 && V.lane[w] != down) w = -1;
+    free_flow = w >= 0 ? (V.oflags[w] & O_FLUIDE) != 0 : true; }
+  if (!free_flow && vehicule_amont(W, A, TAmP, fmin(N.link_vreg[TAmP], M.vx0)) < 0) free_flow = true;
+  double offre = 0, demande1 = 0, demande2 = 0;
+  const int TNP = N.lane_link[VAmNP];
+  if (!free_flow) {                                                                                                         // :560-583
+    offre = min_std(M.max_debit_max, debit_moyen(W, capteur_of(W, c, M.cvg_down[c]), nVoieGir));
+    const int w = vehicule_amont(W, A, TNP, fmin(N.link_vreg[TNP], M.vx0));
+    const bool np_free = w >= 0 ? !(V.vit[w] < fmin(P.cls[V.cls[w]].vx, N.link_vreg[TNP])) : true;
+    demande2 = np_free ? min_std(M.max_debit_max, debit_moyen(W, capteur_of(W, c, TNP), min(N.lane_num[VAmNP], nVoieGir))) : M.max_debit_max;
+  } else demande1 = min_std(M.max_debit_max, debit_moyen(W, capteur_of(W, c, TAmP), nVoieGir));
+  // ---- TestConvergentInsertion -----------------------------------------------------------------------------------------
+  bool ins = false; double tr = 0, ta = 0; int rand_numbers = M.pt_rand[p];
+  int drawn = 0;                                                                          // serial mode: count-only draws consumed from the stream so far
+  auto flush = [&]() { if (mode == MM_SERIAL) { for (; drawn < A.ndraw; drawn++) rng_next(rng); } };
+  if (!free_flow) {                                                                                                         // :343-377
+    const double q2g = M.cvg_gamma[c] * offre / (1 + M.cvg_gamma[c]);
+    if (demande2 < q2g) { ins = true; rand_numbers = 0; }
+    else {
+      const double proba = q2g * P.dt;
+      if (probe) { M.pre[p] = A.ndraw; M.kmax[p] = rand_numbers; M.proba[p] = proba; return MS_VALUES; }   // decided by k_mrg_walk from the stream's values
+      if (mode == MM_EVAL) return MS_OVERFLOW;                                                                              // unreachable: the probe saw the same state
+      if (mode == MM_DECIDED) { const int d = M.decide[p]; ins = d >> 16; rand_numbers -= d & 0xffff; }
+      else { flush(); rng_next(rng);                                                                                       // one draw, unused; the loop bound is re-read after every decrement (:362-374)
+        for (int k = 0; k < rand_numbers; k++) { const double r = rng_next(rng) / 32767.0; rand_numbers--; if (r < proba) { ins = true; break; } } }
+    }
+  } else {
+    rand_numbers = 0;                                                                                                       // :381
+    const DevCls& k = P.cls[V.cls[att]];
+    const double tmin = fmax(cvg_tf(W, c, V.cls[att]), 1 / debit_max(k));
+    int f2 = fol; bool cond = W.inst - M.pt_last[p] >= tmin;
+    if (cond) {
+      if (f2 >= 0) {                                                                                                        // :395-461
+        if (N.link_brick[TAmP] >= 0 && M.node_type[N.link_up[TAmP]] == 'C') {                                               // get_Type_amont() == 'D'
+          const int ent = M.lcam0[TAmP + 1] > M.lcam0[TAmP] ? M.lcam[M.lcam0[TAmP]] : -1;
+          if (ent >= 0 && M.lcav0[ent + 1] - M.lcav0[ent] > 1) next_voie_m(W, f2, N.link_first[ent], probe, &A.ndraw, nullptr);   // :432
+        } else if (!is_itineraire(W, f2, M.cvg_down[c])) { f2 = -1; ins = true; }
+      }
+      if (N.link_nl[TAmP] > 1 && N.link_nl[M.cvg_down[c]] > 1 && nVoieGir == 0) {                                           // :472-500 (not a roundabout: one draw, then ignored)
+        const int fi = near_amont_m(W, N.link_first[TAmP] + nVoieGir + 1, N.lane_len[VAmP], -1.0);
+        if (fi >= 0) A.ndraw++;
+      }
+      const int sNP = capteur_of(W, c, TNP), sP = capteur_of(W, c, TAmP);
+      double tfbar = 0;                                                                                                     // :505-513 (lane index j = 0)
+      if ((sNP < 0 ? 0.0 : cpt_somme(W, sNP, 0, -1)) == 0) tfbar = cvg_tf(W, c, V.cls[att]);
+      else for (int i = 0; i < M.n_cls; i++) tfbar += ratio_type(W, sNP, 0, i) * cvg_tf(W, c, i);
+      double tmbar = 0;
+      for (int i = 0; i < M.n_cls; i++) tmbar += ratio_type(W, sP, 0, i) * (1 / debit_max(P.cls[i]));
+      const double q1mu = 1 / ((tfbar * M.cvg_mu[c]) + tmbar);
+      double vit_am;                                                                                                        // :520-525
+      { const int w = vehicule_amont(W, A, TAmP, fmin(N.link_vreg[TAmP], M.vx0));
+        if (w >= 0 && !(V.oflags[w] & O_LINK1NULL)) vit_am = fmin(P.cls[V.cls[w]].vx, N.link_vreg[N.lane_link[V.lane[w]]]);
+        else vit_am = fmin(M.max_vit_max, N.link_vreg[TAmP]); }
+      double dlag;
+      if (demande1 <= q1mu) dlag = (-k.w + vit_am) / (-k.kx * k.w);
+      else { const double eta = (demande1 - q1mu) / (1 / tmbar - q1mu); dlag = (-k.w + vit_am) / (-k.kx * k.w) * (1 - eta); }
+      const int l1 = V.lane[att];
+      if (VAmNP == l1) tr = P.dt * (N.lane_len[l1] - mpos1(W, att)) / dst_ex(W, att);                                       // :544-547
+      else tr = P.dt * (N.lane_len[l1] - mpos1(W, att) + N.lane_len[VAmNP]) / dst_ex(W, att);
+      const double plim = N.lane_len[VAmP] - dlag;
+      if (W.inst - P.dt + tr > M.pt_last[p] + tmin) {                                                                       // :550-587
+        if (f2 >= 0) { const double pf = calcul_position(W, f2, tr, VAmP); if (pf <= plim) { ins = true; ta = P.dt - tr; } else ins = false; }
+        else { ins = true; ta = P.dt - tr; }
+      } else {                                                                                                              // :589-628
+        tr = P.dt - (W.inst - (M.pt_last[p] + tmin));
+        if (f2 < 0) { ta = P.dt - tr; ins = true; }
+        else { const double pf = calcul_position(W, f2, tr, VAmP); if (pf <= plim) { ta = P.dt - tr; ins = true; } else ins = false; }
+      }
+    } else ins = false;
+  }
+  if (probe) return MS_DONE;
+  flush();                                                                                // count-only draws (values unused: every movement has one target lane)
+  M.pt_rand[p] = rand_numbers; M.pt_free[p] = free_flow;
+  if (!ins) { immobilise(W, att, VAmNP, false); atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_REFUS], 1ULL); return MS_DONE; }   // :967-987
+  int la[kMrgLanes]; const int nla = ctx_lanes_of(W, att, la);
+  if (free_flow) {                                                                                                          // :656-836
+    int L2 = -1; double pl = 0;
+    if (lead >= 0 && !(V.oflags[lead] & O_LINK1NULL)) { pl = mpos1(W, lead) + (P.dt - ta) * V.vit_n[lead]; if (down != V.lane[lead]) pl += N.lane_len[down]; L2 = lead; }
+    int li[kMrgLanes]; int nli = 0; { bool add = false; for (int k = 0; k < nla; k++) { if (N.lane_link[la[k]] == N.lane_link[down]) add = true; if (add) li[nli++] = la[k]; } }
+    const double pos_att = nli ? law_dist(W, att, ta, li, nli, 0.0, L2, pl, 1.0) : 0.0;
+    if (pos_att > 0) {
+      double dfol = 0; int lf[kMrgLanes]; int nlf = 0;
+      if (fol >= 0) {                                                                                                       // :704-749
+        nlf = ctx_lanes_of(W, fol, lf);
+        double ptr = mpos1(W, fol) + (P.dt - ta) * V.vit_n[fol];
+        int o = 0; while (nlf - o > 1 && ptr > N.link_len[N.lane_link[lf[o]]]) { ptr -= N.link_len[N.lane_link[lf[o]]]; o++; }
+        double dconv = 0;
+        for (int i = o; i < nlf; i++) { if (i == o) dconv = N.lane_len[lf[i]] - ptr; else dconv += N.lane_len[lf[i]]; if (N.lane_link[lf[i]] == TAmP) break; }
+        dfol = law_dist(W, fol, ta, lf + o, nlf - o, ptr, att, dconv, V.dn[fol]);
+        dfol = fmin(dst_ex(W, fol), (P.dt - ta) * V.vit_n[fol] + dfol);
+      }
+      if (fol < 0 || dfol >= 0) {
+        bool dont_move = false; double trav = 0;                                                                            // :753-786
+        for (int i = 0; i < nli; i++) { const int ln = li[i]; const double llen = len_ex(P, N, ln); const double ep = pos_att - trav;
+          if (ln == V.lane_n[att] && ep > V.pos_n[att]) { dont_move = true; break; }
+          else if (ep <= llen) { V.lane_n[att] = ln; V.pos_n[att] = ep; update_used(W, att); break; }
+          trav += fmin(ep, llen); }
+        if (!dont_move) { V.vit_n[att] = (pos_att + (P.dt - ta) * V.vit_n[att]) / P.dt; set_acc_m(W, att, (V.vit_n[att] - V.vit[att]) / P.dt); }
+        if (fol >= 0) {                                                                                                     // :788-816
+          trav = 0;
+          for (int i = 0; i < nlf; i++) { const int ln = lf[i]; const double sp = i == 0 ? mpos1(W, fol) : 0.0; const double llen = len_ex(P, N, ln); const double ep = dfol - trav + sp;
+            if (ep <= llen) { V.lane_n[fol] = ln; V.pos_n[fol] = ep; update_used(W, fol); break; }
+            trav += fmin(ep, llen) - sp; }
+          V.vit_n[fol] = (dfol + (P.dt - ta) * V.vit_n[fol]) / P.dt; set_acc_m(W, fol, (V.vit_n[fol] - V.vit[fol]) / P.dt);
+        }
+        M.pt_last[p] = W.inst - P.dt + tr;
+        atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_INS], 1ULL);
+        return MS_DONE;
+      }
+    }
+    immobilise(W, att, VAmNP, false);                                                                                       // :819-830
+    return MS_DONE;
+  }
+  if (lead < 0) return MS_DONE;                                                                                             // congested :838-966
+  const double dconv = mlink1(W, att) == TNP ? N.lane_len[VAmNP] - mpos1(W, att) : N.lane_len[VAmNP] + N.lane_len[V.lane[att]] - mpos1(W, att);
+  double pl = mpos1(W, lead); if (down != V.lane[lead]) pl += N.lane_len[down];
+  pl += dconv;
+  double d = law_dist(W, att, P.dt, la, nla, mpos1(W, att), lead, pl, 1.0);
+  d = fmin(dst_ex(W, att), d);
+  if (!(d >= dconv)) return MS_DONE;                                                                                        // :962-965
+  { double trav = 0;
+    for (int i = 0; i < nla; i++) { const int ln = la[i]; const double sp = i == 0 ? mpos1(W, att) : 0.0; const double llen = len_ex(P, N, ln); const double ep = d - trav + sp;
+      if (ep <= llen) { V.lane_n[att] = ln; V.pos_n[att] = ep; update_used(W, att); break; }
+      trav += fmin(ep, llen) - sp; }
+    V.vit_n[att] = d / P.dt; set_acc_m(W, att, (V.vit_n[att] - V.vit[att]) / P.dt); }
+  M.pt_last[p] = W.inst - P.dt;
+  atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_INS], 1ULL);
+  if (fol >= 0) {                                                                                                           // :908-958
+    const double pos = mlink1(W, fol) == TAmP ? N.lane_len[VAmP] - mpos1(W, fol) : N.lane_len[VAmP] + N.lane_len[V.lane[fol]] - mpos1(W, fol);
+    int lf[kMrgLanes]; const int nlf = ctx_lanes_of(W, fol, lf);
+    const double dfol = fmax(0.0, law_dist(W, fol, P.dt, lf, nlf, mpos1(W, fol), att, pos, 1.0));
+    if (dst_ex(W, fol) > dfol) { double trav = 0;
+      for (int i = 0; i < nlf; i++) { const int ln = lf[i]; const double sp = i == 0 ? mpos1(W, fol) : 0.0; const double llen = len_ex(P, N, ln); const double ep = dfol - trav + sp;
+        if (ep <= llen) { V.lane_n[fol] = ln; V.pos_n[fol] = ep; update_used(W, fol); break; }
+        trav += fmin(ep, llen) - sp; }
+      V.vit_n[fol] = dfol / P.dt; set_acc_m(W, fol, (V.vit_n[fol] - V.vit[fol]) / P.dt); }
+  }
+  return MS_DONE;
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------------------------------
+// CarrefourAFeuxEx::UpdateConvergents CarrefourAFeuxEx.cpp:1386-1593.  pt_mode: 0 = re-ranked from the colours, 1 = single upstream
+// lane (level 1), 2 = left at the reference levels (no controller, or behind the `break` of :1428-1436).
+__global__ void k_mrg_rank(DevMrg M, const int* sl_col, const int* lane_count) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_pt) return;
+  M.pt_rand[p]++;                                                                          // convergent.cpp:366, every point, every step (nothing reads it before CalculInsertion)
+  const int v0 = M.pt_vam0[p], n = M.pt_nvam[p]; const int mode = M.pt_mode[p];
+  for (int a = v0; a < v0 + n; a++) M.vam_niv[a] = M.vam_ref[a];
+  if (mode == 1) { M.vam_niv[v0] = 1; return; }
+  if (mode != 0) return;
+  bool g1 = false;
+  for (int m = M.pt_pm0[p]; m < M.pt_pm0[p + 1] && !g1; m++) { if (sl_col[M.pm_sl[m]] == 1) continue;
+    for (int q = M.pm_occ0[m]; q < M.pm_occ0[m + 1]; q++) if (lane_count[M.pm_occ[q]] > 0) { g1 = true; break; } }
+  for (int m = M.pt_pm0[p]; m < M.pt_pm0[p + 1]; m++) {
+    const bool green = sl_col[M.pm_sl[m]] == 1; int grp = 2;
+    if (!green) { grp = 3; for (int q = M.pm_occ0[m]; q < M.pm_occ0[m + 1]; q++) if (lane_count[M.pm_occ[q]] > 0) { grp = 1; break; } }
+    const int a = M.pm_vam[m];
+    if (!g1) { if (grp == 3) M.vam_niv[a] = M.vam_ref[a] + (n + 1); }
+    else { if (grp == 2) M.vam_niv[a] = M.vam_ref[a] + (n + 1); else if (grp == 3) M.vam_niv[a] = M.vam_ref[a] + (2 * n + 1); }
+  }
+}
+__global__ void k_mrg_probe(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
+                            const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_pt) return;
+  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+  MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
+  int st = merge_point(W, p, MM_PROBE, A, nullptr);
+  if (A.overflow) st = MS_OVERFLOW;
+  M.st[p] = st; M.ninv[p] = A.ninv; M.ndraw[p] = 0;
+  for (int k = 0; k < A.ninv; k++) { M.inv[p * kMrgInv + k] = A.inv[k]; atomicMin(&M.own_min[A.inv[k]], p); atomicMax(&M.own_max[A.inv[k]], p); }
+}
+__global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
+                           const int* posidx, const double* rows, double inst, int n_upd, int* n_flag, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_pt) return;
+  int st = M.st[p];
+  if (st == MS_NONE) return;
+  bool clean = st != MS_OVERFLOW;
+  for (int k = 0; k < M.ninv[p] && clean; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p) clean = false; }
+  if (!clean) { M.st[p] = MS_DIRTY; atomicAdd(n_flag, 1); return; }
+  if (st == MS_VALUES) { atomicAdd(n_flag, 1); return; }                                   // decided by the walk, applied by k_mrg_apply
+  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+  MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
+  st = merge_point(W, p, MM_EVAL, A, nullptr);
+  M.st[p] = st; M.ndraw[p] = A.ndraw;
+  if (A.ndraw) atomicAdd(n_flag, 1);
+}
+// advance the stream by `n` accepted draws (RandManager::myRand = mt19937 + bucket rejection), one block of 256 threads
+__device__ inline void rng_skip_block(DevRng* r, unsigned n, unsigned* sh_new, int* sh_rej) {
+  const int tid = threadIdx.x; const int B = blockDim.x;
+  unsigned left = n;
+  while (left > 0) {
+    __syncthreads();
+    if (r->idx >= 624) {                                                                   // twist, four dependency phases
+      for (int ph = 0; ph < 4; ph++) {
+        const int a = ph == 0 ? 0 : ph == 1 ? 227 : ph == 2 ? 454 : 623, b = ph == 0 ? 227 : ph == 1 ? 454 : ph == 2 ? 623 : 624;
+        for (int i = a + tid; i < b; i += B) { const unsigned y = (r->mt[i] & 0x80000000u) | (r->mt[(i + 1) % 624] & 0x7fffffffu);
+          sh_new[i] = r->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        __syncthreads();
+        for (int i = a + tid; i < b; i += B) r->mt[i] = sh_new[i];
+        __syncthreads();
+      }
+      if (tid == 0) r->idx = 0;
+      __syncthreads();
+    }
+    const int idx = r->idx; const unsigned m = min(left, (unsigned)(624 - idx));
+    if (tid == 0) *sh_rej = 0;
+    __syncthreads();
+    int rej = 0;
+    for (unsigned k = tid; k < m; k += B) { unsigned y = r->mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+      if (y / (0xFFFFFFFFu / 32767u) > 32766u) rej++; }
+    if (rej) atomicAdd(sh_rej, rej);
+    __syncthreads();
+    left -= m - (unsigned)*sh_rej;
+    __syncthreads();
+    if (tid == 0) { r->idx = idx + (int)m; }
+  }
+  __syncthreads();
+  if (tid == 0) r->count += n;
+  __syncthreads();
+}
+__global__ void k_rng_skip(DevRng* r, const int* n_ptr, int n_imm) {
+  __shared__ unsigned sh_new[624]; __shared__ int sh_rej;
+  const unsigned n = n_ptr ? (unsigned)*n_ptr : (unsigned)n_imm;
+  rng_skip_block(r, n, sh_new, &sh_rej);
+}
+// networks without merge points: the count-only draws of the step's car-following phase (next-lane memos) still advance the stream
+__global__ void k_rng_ctx(DevRng* r, const unsigned* draws, unsigned* seen, const int* guard) {
+  __shared__ unsigned sh_new[624]; __shared__ int sh_rej;
+  if (guard && *guard == 0) return;
+  const unsigned now = *draws; const unsigned n = now - *seen;
+  rng_skip_block(r, n, sh_new, &sh_rej);
+  if (threadIdx.x == 0) *seen = now;
+}
+// The points in Liste_convergents order: stream offsets, the draws that need values, the points that share vehicles.
+// `ctx_draws` - `*seen` = count-only draws of this step's car-following phase (next-lane memos), which precede the merge phase
+// in the stream.  out[0] = draws consumed by the merge phase.
+__global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start,
+                                                  const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const int* n_flag,
+                                                  unsigned* seen, int* out, const int* guard) {
+  __shared__ unsigned sh_new[624]; __shared__ int sh_rej; __shared__ int sh_list[256]; __shared__ int sh_n;
+  if (guard && *guard == 0) return;
+  const int tid = threadIdx.x;
+  const unsigned now = *M.draws; const unsigned pre = now - *seen;
+  rng_skip_block(M.rng, pre, sh_new, &sh_rej);
+  if (tid == 0) { *seen = now; out[0] = 0; }
+  if (*n_flag == 0) return;                                                               // no point draws or shares a vehicle this step
+  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+  int total = 0;
+  for (int base = 0; base < M.n_pt; base += 256) {
+    __syncthreads();
+    if (tid == 0) sh_n = 0;
+    __syncthreads();
+    const int p = base + tid; bool f = false;
+    if (p < M.n_pt) { const int st = M.st[p]; f = st == MS_VALUES || st == MS_DIRTY || M.ndraw[p] > 0; }
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    __shared__ int wbase[8];
+    if ((tid & 31) == 0) wbase[tid >> 5] = __popc(m);
+    __syncthreads();
+    if (tid == 0) { int s = 0; for (int w = 0; w < 8; w++) { int t = wbase[w]; wbase[w] = s; s += t; } sh_n = s; }
+    __syncthreads();
+    if (f) sh_list[wbase[tid >> 5] + __popc(m & ((1u << (tid & 31)) - 1))] = p;
+    __syncthreads();
+    if (tid == 0) for (int k = 0; k < sh_n; k++) {
+      const int q = sh_list[k]; const int st = M.st[q];
+      if (st == MS_DIRTY) { MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; const unsigned c0 = M.rng->count;
+        // literal order: count-only draws interleave with the test's draws exactly as merge_point issues them in serial mode
+        merge_point(W, q, MM_SERIAL, A, M.rng); total += (int)(M.rng->count - c0); M.st[q] = MS_DONE; M.counters[SYMGPU_CNT_MRG_SERIAL]++; }
+      else if (st == MS_VALUES) {
+        for (int d = 0; d < M.pre[q]; d++) rng_next(M.rng);
+        rng_next(M.rng); int used = 0; bool ins = false; const double proba = M.proba[q];
+        int rn = M.kmax[q];
+        for (int d = 0; d < rn; d++) { const double r = rng_next(M.rng) / 32767.0; rn--; used++; if (r < proba) { ins = true; break; } }
+        M.decide[q] = ((int)ins << 16) | used; total += M.pre[q] + 1 + used; M.counters[SYMGPU_CNT_MRG_VALUES]++; }
+      else { for (int d = 0; d < M.ndraw[q]; d++) rng_next(M.rng); total += M.ndraw[q]; }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) out[0] = total;
+}
+__global__ void k_mrg_apply(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
+                            const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_pt) return;
+  if (M.st[p] == MS_VALUES) { const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+    MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; merge_point(W, p, MM_DECIDED, A, nullptr); }
+  for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; M.own_min[x] = INT_MAX; M.own_max[x] = -1; }   // marks back to idle for the next step
+}
+// Reseau::UpdateConvergents reseau.cpp:2432-2600 (integer counts) after SensorsManager::UpdateTabNbVeh (:462-527): the slot the
+// rotation exposes is cleared first (k_mrg_rotate), then every vehicle left on the network counts where it crossed a sensor.
+__global__ void k_mrg_rotate(DevMrg M, int n_upd_after, int n_rows, const int* row_sens, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int s = row_sens[2 * r]; const int win = M.sens_win[s];
+  if (n_upd_after > win) M.cnt[M.sens_cnt0[s] + row_sens[2 * r + 1] * win + (n_upd_after - win - 1) % win] = 0;
+}
+__device__ inline void sens_hit(const DevNet& N, const DevMrg& M, int s, int cls, int lane, int n_upd_after) {
+  const int win = M.sens_win[s]; const int nl = N.link_nl[M.sens_link[s]];
+  const int last = min(n_upd_after - 1, win - 1); const int head = max(0, n_upd_after - win) % max(1, win);
+  if (last >= 0) atomicAdd(&M.cnt[M.sens_cnt0[s] + (cls * nl + N.lane_num[lane]) * win + (head + last) % win], 1);
+}
+__global__ void k_mrg_sensors(DevNet N, DevVeh V, DevMrg M, int n, const int* posidx, const int* order, const double* rows, int n_upd_after, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n || V.status[x] != ST_ALIVE) return;                                           // after k_final: the vehicles still on the network; index n = end of this step
+  const double p0 = V.pos_n[x];
+  if (!(V.vit_n[x] > 0 && p0 >= 0)) return;
+  const int l1 = V.lane[x], l0 = V.lane_n[x]; const int k1 = (V.oflags[x] & O_LINK1NULL) ? -1 : N.lane_link[l1]; const int k0 = N.lane_link[l0];
+  double p1 = snap_pos(V.pos[x]);
+  const int cls = V.cls[x];
+  if (k1 >= 0) for (int q = M.lsens0[k1]; q < M.lsens0[k1 + 1]; q++) { const int s = M.lsens[q]; const double xs = M.sens_pos[s];
+    if (p1 < xs && (p0 >= xs || k1 != k0)) sens_hit(N, M, s, cls, l1, n_upd_after); }
+  if (k1 != k0) {
+    for (int q = M.lsens0[k0]; q < M.lsens0[k0 + 1]; q++) { const int s = M.lsens[q]; if (p0 >= M.sens_pos[s]) sens_hit(N, M, s, cls, l0, n_upd_after); }
+    const int nu = M.nused[x];
+    if (nu > 0) { int lanes[kMrgLanes]; int nl = 0;
+      const int p = posidx[x]; const Row r = row_at(rows, p); const int hn = (hi32(r[R_I0]) >> 8) & 15;
+      if (order[p] == x && hn <= kRowLanes) { nl = hn; for (int k = 0; k < nl; k++) lanes[k] = lo32(r[R_REC + kRecD * k + 4]); }
+      else { nl = V.ctx_nl[x]; for (int k = 0; k < nl; k++) lanes[k] = V.ctx_lane[x * kMaxCtx + k]; }
+      for (int k = 1; k <= nu && k < nl; k++) { const int kk = N.lane_link[lanes[k]];
+        for (int q = M.lsens0[kk]; q < M.lsens0[kk + 1]; q++) sens_hit(N, M, M.lsens[q], cls, lanes[k], n_upd_after); } }
+  }
+}
+
+}  // namespace symb200

@@ -66,6 +66,13 @@ struct DevVeh {
 };
 
 struct DevLaneDyn { int *count, *start, *fill, *tail, *head_done; double* next_sortie; int* exit_winner; };
+struct DevMrg;                                                   // merge points (merge.cuh)
+struct MrgA { bool own = false, lead = false; double mc = 0, posl = 0, lenl = 0, borne = 0, repl = 0, vunc = 0; };   // phase A results for the merge hooks
+__device__ inline int mrg_phase_a(const DevParams& P, const DevNet& n, const DevVeh& V, const DevMrg* M, int i, int lane1, int L, double p1, double dtv,
+                                  double inst, int* memo, MrgA* out);
+__device__ inline void mrg_store(const DevMrg* M, int p, const MrgA& a);
+__device__ inline void mrg_load(const DevMrg* M, int p, int hdr, MrgA* a);
+__device__ inline void mrg_register(const DevNet& n, const DevMrg* M, int i, int p, const int* lanes, int kf);
 
 // std::pow with the three exponents the laws use (GippsCarFollowing.cpp:75 gamma = 0.5, IDMCarFollowing.cpp:148 alpha = 4 and
 // :175 beta = 1.5), correctly rounded: the host libm the reference links (glibc) returns the correctly rounded value for all
@@ -151,7 +158,7 @@ __device__ inline int memo_touch(int* memo, int lane) {
 // Returns the number of random draws consumed.
 __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, double* rows, int p, int i,
                                  const int* lanes, int nl, int L, double gap, double dn0, double dfree, bool created, double start,
-                                 double cpos, double dtv, const int* slm);
+                                 double cpos, double dtv, const int* slm, const MrgA& ma);
 
 // rebuilds the memo of vehicle i (k_ctx_fill)
 __device__ inline void ctx_cache_fill(const DevNet& n, const DevVeh& V, int i) {
@@ -187,7 +194,8 @@ __device__ inline void ctx_cache_fill(const DevNet& n, const DevVeh& V, int i) {
 // rows != nullptr: also pack the vehicle's phase-B row at order position p (rows.cuh); the per-vehicle ctx_* arrays are
 // then only written for contexts the row cannot hold (general path).
 __device__ inline int context_one(const DevParams& P, const DevNet& n, const DevVeh& V, const int* lane_tail, int i,
-                                  int own_leader, int* overflow, double* rows = nullptr, int p = -1, const DevLaneDyn* LD = nullptr) {
+                                  int own_leader, int* overflow, double* rows = nullptr, int p = -1, const DevLaneDyn* LD = nullptr,
+                                  const DevMrg* M = nullptr, double inst = 0.0) {
   const DevCls& c = P.cls[V.cls[i]];
   double p1 = snap_pos(V.pos[i]);
   bool created = p1 <= SYM_UNDEF;                                         // vehicule.cpp:1235
@@ -311,6 +319,9 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
     }
     dfree = trav;
   }
+  // merge points: speed imposed on the head of a non-priority branch, pessimistic speed of such a leader (merge.cuh)
+  MrgA ma;
+  if (M && p >= 0) { draws += mrg_phase_a(P, n, V, M, i, lanes[0], leader, p1, dtv, inst, memo, &ma); mrg_store(M, p, ma); }
   if (draws) for (int k = 0; k < kMemo; k++) V.memo[i * kMemo + k] = memo[k];
   V.ctx_leader[i] = leader;
   if (!rows || nl > 3) {
@@ -319,7 +330,7 @@ __device__ inline int context_one(const DevParams& P, const DevNet& n, const Dev
     V.ctx_gap[i] = gap; V.ctx_dn0[i] = dn0; V.ctx_dfree[i] = dfree;
     V.ctx_flags[i] = created ? 1 : 0;
   }
-  if (rows) build_row(P, n, V, *LD, rows, p, i, lanes, nl, leader, gap, dn0, dfree, created, start, cpos, dtv, fast ? slm : nullptr);
+  if (rows) build_row(P, n, V, *LD, rows, p, i, lanes, nl, leader, gap, dn0, dfree, created, start, cpos, dtv, fast ? slm : nullptr, ma);
   return draws;
 }
 
@@ -349,7 +360,7 @@ __device__ inline double decel_limit(const DevParams& P, const DevCls& c, bool c
 // desired-lane reset left to phase C (O_VDESRESET).  vL_in: the leader's new speed the caller looked up.
 __device__ inline void follow_one(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, int i,
                                   bool leader_computed, double inst, double cpos_in, bool defer = false,
-                                  const double* vL_in = nullptr, double* v0_out = nullptr) {
+                                  const double* vL_in = nullptr, double* v0_out = nullptr, const DevMrg* M = nullptr, int p = -1, int hdr = 0) {
   const DevCls& c = P.cls[V.cls[i]];
   const bool created = V.ctx_flags[i] & 1;
   double p1 = snap_pos(V.pos[i]); if (p1 <= SYM_UNDEF) p1 = 0.0;
@@ -377,6 +388,8 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
         if (P.accbornee) vL = fmin(fmin(vreg_l, cl.vx), vL1 + acc_max(c, vL1) * P.dt);
         else vL = fmin(vreg_l, cl.vx);
       }
+      if (M && p >= 0) { MrgA ma; mrg_load(M, p, hdr, &ma);                                // NewellCarFollowing.cpp:266-298
+        if (ma.lead) { double vit = leader_computed ? vL : ma.vunc; vit = (ma.borne < vit) ? ma.borne : vit; if (ma.posl + vit * dtv > ma.lenl) vL = ma.repl; } }
       const double dn0 = V.ctx_dn0[i];
       // ComputeRelaxationEvolution :113-136 (contraction flag is only set by the aggressiveness procedure: off)
       double kv = -cl.kx * cl.w / (vL1 - cl.w);
@@ -449,6 +462,8 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
         else if (ts > inst - dtv) { double vv = (trav + llen - sp) / (ts - (inst - dtv)); infl = true; mini = fmin(mini, vv * dtv); }
       }
     }
+    if (k == 0 && M && p >= 0) { MrgA ma; mrg_load(M, p, hdr, &ma);                     // 3 - Convergent::ComputeTraffic convergent.cpp:1368-1403
+      if (ma.own && ma.mc < goal) { infl = true; mini = fmin(mini, ma.mc); } }
     // 4 - signals :1680-1705, CalculTraficFeux :1799-1945
     {
       double ml = goal + 1; bool arret = false, has = false; int aval = -2;
@@ -495,7 +510,7 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
   double a0 = created ? 0.0 : (dtv != 0 ? (v0 - v1) / dtv : 0.0);                      // :1368-1375
   if (fabs(a0) < 0.000001) a0 = 0;                                                     // vehicule.h:501
   // ---- placement: vehicule.cpp:1377-1527 ------------------------------------------------------------
-  trav = 0; int lane0 = lanes[0]; double pos0 = start; int dest_lane = -1; double trav_dest = 0; bool left = false;
+  trav = 0; int lane0 = lanes[0]; double pos0 = start; int dest_lane = -1; double trav_dest = 0; bool left = false; int kf = 0;
   const int ro = n.route_off[route], re = n.route_off[route + 1];
   for (int k = 0; k < nl; k++) {
     int ln = lanes[k]; double sp = k == 0 ? start : 0.0; double llen = len_ex(P, n, ln); double ep = goal - trav + sp;
@@ -505,9 +520,10 @@ __device__ inline void follow_one(const DevParams& P, const DevNet& n, const Dev
     if ((last && !is_exit && ep > llen) || (feu && ep > llen && ep < llen + 0.00001)) ep = llen;   // :1397-1403
     bool reached = ep > llen && ta == 'S' && n.route_links[re - 1] == link;            // TripLeg.cpp:91-117, Position.cpp:394-404
     if (reached) { dest_lane = ln; trav_dest = trav; }
-    if (reached || ep <= llen) { lane0 = ln; pos0 = ep; break; }
+    if (reached || ep <= llen) { lane0 = ln; pos0 = ep; kf = k; break; }
     left = true;                                                                     // :1505 the desired lane is forgotten when the lane is left
   }
+  if (M) mrg_register(n, M, i, p, lanes, kf);                                          // :1485-1502 AddInsVeh, m_LstUsedLanes
   int of = (fluide ? O_FLUIDE : 0) | (feu ? O_FEU : 0) | (ctx_free ? O_CTXFREE : 0) | (created ? O_CREATED : 0);
   if (left) { if (defer) of |= O_VDESRESET; else V.vdes[i] = -1; }
   if (dest_lane >= 0) {                                                                // :1512-1527

@@ -28,7 +28,8 @@ constexpr int R_GOALLAW = R_T0;
 constexpr int kRecD = 5;           // llen, pf, prop, ts, ints(lane, flags)
 enum { RF_STOPEND = 1, RF_EXIT = 2, RF_SL = 4, RF_COLSHIFT = 4 };
 // packed header flags (R_I0 high int)
-enum { H_CREATED = 1 << 12, H_FLAGA = 1 << 13, H_FLAGB = 1 << 14, H_SLOW = 1 << 15, H_LAWFREE = 1 << 16, H_LINK1NULL = 1 << 17 };
+enum { H_CREATED = 1 << 12, H_FLAGA = 1 << 13, H_FLAGB = 1 << 14, H_SLOW = 1 << 15, H_LAWFREE = 1 << 16, H_LINK1NULL = 1 << 17,
+       H_MRGOWN = 1 << 18 /* head of a non-priority merge branch: imposed speed */, H_MRGLEAD = 1 << 19 /* the leader is one */ };
 // phase B result flags
 enum { B_FLUIDE = 1, B_FEU = 2, B_CTXFREE = 4, B_CANCEL = 8, B_SLOWDONE = 16 };
 
@@ -48,7 +49,7 @@ __device__ __forceinline__ int hi32(double d) { return __double2hiint(d); }
 // phase A tail: called by k_context once lanes / leader / gap / dn0 / dfree are known for vehicle i at order position p.
 __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevVeh& V, const DevLaneDyn& LD, double* rows, int p, int i,
                                  const int* lanes, int nl, int L, double gap, double dn0, double dfree, bool created, double start,
-                                 double cpos, double dtv, const int* slm) {
+                                 double cpos, double dtv, const int* slm, const MrgA& ma) {
   const Row r = row_at(rows, p);
   const DevCls& c = P.cls[V.cls[i]];
   const double v1 = V.vit[i];
@@ -61,7 +62,7 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
     else vlest = fmin(vreg_l, cl.vx);
   }
   int hdr = V.cls[i] | (lcls << 4) | (nl << 8) | (created ? H_CREATED : 0) | (nl > kRowLanes ? H_SLOW : 0) |
-            ((V.status[i] == ST_NEW || V.status[i] == ST_POOL) ? H_LINK1NULL : 0);
+            ((V.status[i] == ST_NEW || V.status[i] == ST_POOL) ? H_LINK1NULL : 0) | (ma.own ? H_MRGOWN : 0) | (ma.lead ? H_MRGLEAD : 0);
   double goal_law = 0;
   if (c.law != 0) {                                                       // Gipps / IDM: no dependency on the leader's new state
     bool ctx_free = true;
@@ -149,7 +150,8 @@ __device__ inline void build_row(const DevParams& P, const DevNet& n, const DevV
 struct BOut { double goal, v0, dn_end, cpos; int flags; };
 
 // phase B: r = the vehicle's row (shared or global memory), vL = leader's new speed (ignored when no leader / non-Newell).
-__device__ __forceinline__ BOut phase_b(const DevParams& P, const Row r, double vL, double inst) {
+// mx: the merge side record of the position (merge.cuh; read only when the header says so); cutl: the leader stays uncomputed
+__device__ __forceinline__ BOut phase_b(const DevParams& P, const Row r, double vL, double inst, const double* mx = nullptr, bool cutl = false) {
   const int hdr = hi32(r[R_I0]); const int L = lo32(r[R_I0]);
   const DevCls& c = P.cls[hdr & 15];
   const int nl = (hdr >> 8) & 15; const bool created = hdr & H_CREATED;
@@ -159,6 +161,9 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const Row r, double 
   if (c.law == 0) {
     goal = r[R_DFREE];
     if (L >= 0) {
+      if (hdr & H_MRGLEAD) {                                              // NewellCarFollowing.cpp:266-298: the leader heads a non-priority merge branch
+        double vit = cutl ? mx[5] : vL; vit = (mx[3] < vit) ? mx[3] : vit;
+        if (mx[1] + vit * dtv > mx[2]) vL = mx[4]; }
       const double A = r[R_A];
       double kvfin = A / (vL - r[R_WL]);                                  // NewellCarFollowing.cpp:118, :310
       double res;
@@ -195,6 +200,7 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const Row r, double 
         else if (ts > inst - dtv) { double vv = (trav + llen - sp) / (ts - (inst - dtv)); infl = true; mini = fmin(mini, vv * dtv); }
       }
     }
+    if (k == 0 && (hdr & H_MRGOWN)) { const double mc = mx[0]; if (mc < goal) { infl = true; mini = fmin(mini, mc); } }   // Convergent::ComputeTraffic convergent.cpp:1368-1403
     if (fl & RF_SL) {                                                     // :1680-1705, :1884-1938
       double ml = goal + 1; bool arret = false, has = false;
       const int col = (fl >> RF_COLSHIFT) & 3; const double p = q[2]; const double pf = q[1];
@@ -229,7 +235,7 @@ __device__ __forceinline__ BOut phase_b(const DevParams& P, const Row r, double 
 
 // phase C: acceleration, placement, destination, bookkeeping (vehicule.cpp:1367-1527, :1567-1574)
 __device__ inline void phase_c(const DevParams& P, const DevNet& n, const DevVeh& V, const double* rows, const double* b_goal,
-                               const int* b_flags, int p, double inst) {
+                               const int* b_flags, int p, double inst, const DevMrg* M = nullptr) {
   const Row r = row_at(rows, p);
   const int bf = b_flags[p];
   const int hdr = hi32(r[R_I0]); const int L = lo32(r[R_I0]); const int i = lo32(r[R_I1]);
@@ -243,7 +249,7 @@ __device__ inline void phase_c(const DevParams& P, const DevNet& n, const DevVeh
   const bool feu = bf & B_FEU;
   double a0 = created ? 0.0 : (dtv != 0 ? (v0 - v1) / dtv : 0.0);
   if (fabs(a0) < 0.000001) a0 = 0;
-  double trav = 0; int lane0 = lo32(r[R_REC + 4]); double pos0 = start; int dest_lane = -1; double trav_dest = 0;
+  double trav = 0; int lane0 = lo32(r[R_REC + 4]); double pos0 = start; int dest_lane = -1; double trav_dest = 0; int kf = 0;
   const int route = V.route[i]; const int re = n.route_off[route + 1];
   for (int k = 0; k < nl; k++) {
     const Row q = r + (R_REC + kRecD * k);
@@ -254,9 +260,11 @@ __device__ inline void phase_c(const DevParams& P, const DevNet& n, const DevVeh
     if ((last && !is_exit && ep > llen) || (feu && ep > llen && ep < llen + 0.00001)) ep = llen;
     bool reached = ep > llen && ta == 'S' && n.route_links[re - 1] == link;
     if (reached) { dest_lane = ln; trav_dest = trav; }
-    if (reached || ep <= llen) { lane0 = ln; pos0 = ep; break; }
+    if (reached || ep <= llen) { lane0 = ln; pos0 = ep; kf = k; break; }
     V.vdes[i] = -1;                                                   // vehicule.cpp:1505
   }
+  if (M) { int lanes[kRowLanes]; for (int k = 0; k < nl && k < kRowLanes; k++) lanes[k] = lo32(r[R_REC + kRecD * k + 4]);
+    mrg_register(n, M, i, p, lanes, kf); }                            // :1485-1502 AddInsVeh, m_LstUsedLanes
   int of = ((bf & B_FLUIDE) ? O_FLUIDE : 0) | (feu ? O_FEU : 0) | ((bf & B_CTXFREE) ? O_CTXFREE : 0) | (created ? O_CREATED : 0);
   if (dest_lane >= 0) {
     double ti = goal > 0.0001 ? inst - dtv + dtv * (trav_dest / goal) : inst - dtv;

@@ -39,6 +39,7 @@ def lib():
         L.orc_link_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_exited.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_waiting.argtypes = [C.c_void_p]
+        L.orc_merge_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_set_partition.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_create_vehicle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]
         L.orc_rng_new.restype = C.c_void_p
@@ -96,6 +97,14 @@ class Oracle:
 
     def waiting(self) -> int:
         return self.L.orc_waiting(self.h)
+
+    def merge_state(self):
+        n = self.L.orc_merge_state(self.h, None, None, 0)
+        t = np.zeros(n, np.float64)
+        r = np.zeros(n, np.int32)
+        if n:
+            self.L.orc_merge_state(self.h, t.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), n)
+        return t, r
 
     def state(self):
         n = self.n

@@ -587,9 +587,10 @@ struct Sim {
     double q = lanes[tgt].length / lanes[lane].length * v->pos[1] + 0.001;
     Veh* fol = get_near_amont_vehicule(tgt, q, -1.0, v);                                     // :2403
     Veh* lead = get_near_aval_vehicule(tgt, q, v);                                           // :2404
-    if (!lead && (chgt_voie_obligatoire(lane) || desired)) {                                 // :2417-2434 (merge non-priority exception: row A10)
-      int nx = calcul_next_voie(v, tgt);
-      if (nx >= 0) lead = get_near_aval_vehicule(nx, 0, nullptr);
+    if (!lead && (chgt_voie_obligatoire(lane) || desired)) {                                 // :2417-2434
+      bool cont = true;                                                                      // non-priority branch of a merge: no leader looked for downstream
+      if (links[v->link[1]].type_aval == 'C' && link_cvg_aval[v->link[1]] >= 0 && voie_amont_non_prioritaire(cvgs[link_cvg_aval[v->link[1]]], lane)) cont = false;
+      if (cont) { int nx = calcul_next_voie(v, tgt); if (nx >= 0) lead = get_near_aval_vehicule(nx, 0, nullptr); }
     }
     Veh* lead_orig = get_prev_vehicule(v);                                                   // :2439
     if (!lead_orig && !chgt_voie_obligatoire(lane) && !desired && !force) return false;   // :2440-2442 (the reference returns here without undoing the 0.5 m move-back)

@@ -50,7 +50,8 @@ def run_parity(builder, n_steps, check_every=1, verbose=False):
                     raise AssertionError(f"step {k + 1}: {key} rel err {e:.3e} at row {bad} id {so['id'][bad]}: "
                                          f"oracle {so[key][bad]!r} gpu {sg[key][bad]!r}")
                 worst = max(worst, e)
-            assert o.rng_count == g.rng_count, f"step {k + 1}: rng count oracle {o.rng_count} gpu {g.rng_count}"
+            assert o.rng_count == g.rng_count, (f"step {k + 1}: rng count oracle {o.rng_count} gpu {g.rng_count} (merge insertions oracle {o.counter(4)} gpu "
+                                                f"{g.counter(pkg.CNT_MRG_INS)}, refusals {o.counter(5)} / {g.counter(pkg.CNT_MRG_REFUS)}, congested tests {o.counter(7)} / {g.counter(pkg.CNT_MRG_VALUES)})")
             eo, xo = o.link_counts()
             eg, xg = g.link_counts()
             assert np.array_equal(eo, eg) and np.array_equal(xo, xg), f"step {k + 1}: link counters differ"
@@ -59,11 +60,15 @@ def run_parity(builder, n_steps, check_every=1, verbose=False):
             assert np.array_equal(io, ig), f"step {k + 1}: exited ids differ {io} {ig}"
             assert _close(to, tg) <= RTOL, f"step {k + 1}: exit instants differ"
             assert o.waiting() == g.waiting(), f"step {k + 1}: waiting queues differ {o.waiting()} {g.waiting()}"
+            (mo_t, mo_r), (mg_t, mg_r) = o.merge_state(), g.merge_state()
+            assert np.array_equal(mo_r, mg_r) and np.array_equal(mo_t, mg_t), f"step {k + 1}: merge point state differs at {np.nonzero((mo_r != mg_r) | (mo_t != mg_t))[0][:5]}"
             if verbose and (k + 1) % 50 == 0:
                 print(f"step {k + 1}: n={no} worst={worst:.2e} rng={o.rng_count} passes={g.counter(pkg.CNT_PASSES)}")
         stats = dict(worst=worst, veh_steps=veh_steps, ties_gpu=g.counter(pkg.CNT_TIES), ties_oracle=o.counter(0),
                      loops_gpu=g.counter(pkg.CNT_LOOPS), loops_oracle=o.counter(1), passes=g.counter(pkg.CNT_PASSES),
-                     overflow=g.counter(pkg.CNT_CTX_OVERFLOW), n_final=no)
+                     overflow=g.counter(pkg.CNT_CTX_OVERFLOW), n_final=no, merge_ins=g.counter(pkg.CNT_MRG_INS), merge_ins_oracle=o.counter(4),
+                     merge_refus=g.counter(pkg.CNT_MRG_REFUS), merge_serial=g.counter(pkg.CNT_MRG_SERIAL), merge_values=g.counter(pkg.CNT_MRG_VALUES),
+                     merge_cong_oracle=o.counter(7))
         g.close()
         o.close()
         return stats
