@@ -1225,6 +1225,7 @@ extern "C" int symgpu_mp_configure(symgpu_ctx* c, int rank, int world, const int
   if (!c || !node_part || world < 1 || rank < 0 || rank >= world) return SYMGPU_E_ARG;
   CK(cudaSetDevice(c->device));
   if (c->chgtvoie) { g_err = "partitioned runs do not support lane changing yet (global random stream)"; return SYMGPU_E_UNSUPPORTED; }
+  if (c->mg.on) { g_err = "partitioned runs do not support merge points yet (their draws are ordered over the whole network)"; return SYMGPU_E_UNSUPPORTED; }
   const FlatNet& f = c->net; const int L = f.n_lanes();
   auto& m = c->mp; m.on = true; m.rank = rank; m.world = world;
   m.lane_owner.resize(L);

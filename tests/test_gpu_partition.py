@@ -43,7 +43,7 @@ def _run(pkg, synth, tmp_path, builder, world, steps):
 
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_partitioned_grid_matches_partitioned_oracle(pkg, synth, tmp_path, world):
-    b = synth.grid(n=8, ny=4, n_steps=200, demand_per_lane=0.0, preseed_per_lane=9.0, shuffle=False)
+    b = synth.grid(n=8, ny=4, n_steps=200, demand_per_lane=0.0, preseed_per_lane=9.0, shuffle=False, merges=False)
     migrated, loops_gpu, loops_oracle = _run(pkg, synth, tmp_path, b, world, 150)
     assert migrated > 50            # vehicles did cross the cuts
     assert loops_gpu == loops_oracle
@@ -52,7 +52,7 @@ def test_partitioned_grid_matches_partitioned_oracle(pkg, synth, tmp_path, world
 def test_partition_of_one_is_the_plain_engine(pkg, synth, tmp_path):
     """world = 1: no halo, no migration — must reproduce the unpartitioned oracle."""
     part_mod = importlib.import_module("open-symuvia_b200.partition")
-    b = synth.grid(n=4, n_steps=100, demand_per_lane=0.0, preseed_per_lane=10.0)
+    b = synth.grid(n=4, n_steps=100, demand_per_lane=0.0, preseed_per_lane=10.0, merges=False)
     p = str(tmp_path / "p.symflat")
     b.write(p)
     o = Oracle(p, len(b.links))
@@ -68,7 +68,7 @@ def test_partition_of_one_is_the_plain_engine(pkg, synth, tmp_path):
 def test_partitioned_grid_with_origins(pkg, synth, tmp_path, world):
     """Boundary demand (deterministic creation, queues at the origins, draws per created vehicle) in a partitioned run: every
     rank replays all origins' draws and keeps the vehicles of its own entry lanes; the device draws are summed over the ranks."""
-    b = synth.grid(n=8, ny=4, n_steps=300, demand_per_lane=0.25, demand_duration=200, preseed_per_lane=4.0, shuffle=False)
+    b = synth.grid(n=8, ny=4, n_steps=300, demand_per_lane=0.25, demand_duration=200, preseed_per_lane=4.0, shuffle=False, merges=False)
     migrated, loops_gpu, loops_oracle = _run(pkg, synth, tmp_path, b, world, 220)
     assert migrated > 50
     assert loops_gpu == loops_oracle
