@@ -27,8 +27,8 @@ struct Writer { FILE* f; int n = 0; long npos;
 const int DX[4] = {1, 0, -1, 0}, DY[4] = {0, 1, 0, -1};
 }  // namespace
 
-extern "C" int symgen_grid(const char* path, int nx, int ny, double per_lane, int seed, int route_len, int n_steps, int rank, int world,
-                           long long* n_vehicles_total) {
+extern "C" int symgen_grid2(const char* path, int nx, int ny, double per_lane, int seed, int route_len, int n_steps, int rank, int world,
+                            long long* n_vehicles_total, int merges) {
   const double block = 200.0, setback = 12.0, lane_w = 3.0, vit_reg = 13.89, green = 30.0, amber = 3.0;
   const int NL = 2;
   const double w = -5.8823, kx = 0.17, vx = 25.0;
@@ -38,6 +38,9 @@ extern "C" int symgen_grid(const char* path, int nx, int ny, double per_lane, in
   for (int i = 0; i < nx; i++) for (int j = 0; j < ny; j++) { node_i.insert(node_i.end(), {(int)'C', J(i, j), 0, 0}); node_xy.push_back(i * block); node_xy.push_back(j * block); }
   std::vector<int> link_i, lane_i; std::vector<double> link_f, link_geom, lane_f;
   std::vector<int> link_dir, link_kind;                      // kind: 0 'L' junction->junction, 1 exit stub, 2 entry stub, 3 internal
+  std::vector<std::string> link_name;                        // labels as in synth.py: they fix the creation order inside a junction and the order of the merges
+  const char DN[5] = "ENWS";
+  auto nm = [&](char pre, int i, int j, int d) { return std::string(1, pre) + std::to_string(i) + "_" + std::to_string(j) + std::string(1, DN[d]); };
   std::vector<int> out_link((size_t)nx * ny * 4, -1), in_link((size_t)nx * ny * 4, -1);
   std::vector<int> exit_i; std::vector<double> exit_f;
   auto add_link = [&](int up, int down, int nl, double len, char ta, int brick, int prev_lane, double x0, double y0, double x1, double y1, int dir, int kind) {
@@ -51,15 +54,15 @@ extern "C" int symgen_grid(const char* path, int nx, int ny, double per_lane, in
     for (int d = 0; d < 4; d++) {
       int i2 = i + DX[d], j2 = j + DY[d]; double gx0 = x0 + DX[d] * setback, gy0 = y0 + DY[d] * setback;
       if (i2 >= 0 && i2 < nx && j2 >= 0 && j2 < ny) {
-        int k = add_link(J(i, j), J(i2, j2), NL, L, 'D', -1, -1, gx0, gy0, i2 * block - DX[d] * setback, j2 * block - DY[d] * setback, d, 0);
+        int k = add_link(J(i, j), J(i2, j2), NL, L, 'D', -1, -1, gx0, gy0, i2 * block - DX[d] * setback, j2 * block - DY[d] * setback, d, 0); link_name.push_back(nm('L', i, j, d));
         out_link[(size_t)J(i, j) * 4 + d] = k; in_link[(size_t)J(i2, j2) * 4 + d] = k;
       } else {
         int s = (int)node_i.size() / 4; node_i.insert(node_i.end(), {(int)'S', -1, 0, 0}); node_xy.push_back(x0 + DX[d] * block); node_xy.push_back(y0 + DY[d] * block);
-        int k = add_link(J(i, j), s, NL, L, 'S', -1, -1, gx0, gy0, x0 + DX[d] * (block - setback), y0 + DY[d] * (block - setback), d, 1);
+        int k = add_link(J(i, j), s, NL, L, 'S', -1, -1, gx0, gy0, x0 + DX[d] * (block - setback), y0 + DY[d] * (block - setback), d, 1); link_name.push_back(nm('X', i, j, d));
         out_link[(size_t)J(i, j) * 4 + d] = k; exit_i.push_back(s); exit_i.push_back(k); exit_f.push_back(-1.0);
         int e = (int)node_i.size() / 4; node_i.insert(node_i.end(), {(int)'E', -1, 0, 0}); node_xy.push_back(x0 + DX[d] * block); node_xy.push_back(y0 + DY[d] * block);
         int din = (d + 2) % 4;
-        int k2 = add_link(e, J(i, j), NL, L, 'D', -1, -1, x0 + DX[d] * (block - setback), y0 + DY[d] * (block - setback), gx0, gy0, din, 2);
+        int k2 = add_link(e, J(i, j), NL, L, 'D', -1, -1, x0 + DX[d] * (block - setback), y0 + DY[d] * (block - setback), gx0, gy0, din, 2); link_name.push_back(nm('N', i, j, d));
         in_link[(size_t)J(i, j) * 4 + din] = k2;
       } } }
   const int n_ext_links = (int)link_i.size() / 8;
@@ -75,15 +78,46 @@ extern "C" int symgen_grid(const char* path, int nx, int ny, double per_lane, in
   std::vector<int> int_succ_key, int_succ_next;                       // internal lanes in creation order
   std::vector<std::vector<int>> sl_rows((size_t)n_ext_lanes);          // (ctrl, up_link, up_num, down_link, down_num)
   std::vector<std::vector<int>> sig_in((size_t)nx * ny * 2), sig_out((size_t)nx * ny * 2);
-  for (auto& m : moves) {
-    int seq = (m.din == 0 || m.din == 2) ? 0 : 1; sig_in[(size_t)m.node * 2 + seq].push_back(m.a); sig_out[(size_t)m.node * 2 + seq].push_back(m.o);
-    for (int k = 0; k < NL; k++) { double ax, ay, ox, oy; lane_pt(m.a, k, true, ax, ay); lane_pt(m.o, k, false, ox, oy); double len = std::hypot(ox - ax, oy - ay);
-      int ent = link_i[8 * (size_t)m.a] + k;
-      int il = add_link(m.node, m.node, 1, len, exit_in_count[m.o] > 1 ? 'C' : 'R', m.node, ent, ax, ay, ox, oy, m.din, 3);
-      int ilane = link_i[8 * (size_t)il];
-      succ_rows[ent].push_back(m.o); succ_rows[ent].push_back(ilane);
-      int_succ_key.push_back(m.o); int_succ_next.push_back(link_i[8 * (size_t)m.o] + k);
-      sl_rows[ent].insert(sl_rows[ent].end(), {m.node, m.a, k, m.o, k}); } }
+  for (auto& m : moves) { int seq = (m.din == 0 || m.din == 2) ? 0 : 1; sig_in[(size_t)m.node * 2 + seq].push_back(m.a); sig_out[(size_t)m.node * 2 + seq].push_back(m.o); }
+  // internal links in the creation order of CarrefourAFeuxEx::Init (CarrefourAFeuxEx.cpp:331-480): entry-lane label, exit-link label, exit lane;
+  // one Convergent per exit link fed by several internal links (:489-919), reference priority levels from the geometry (:1129-1166)
+  struct Cv { std::string name; int node, down; std::vector<int> am; std::vector<std::vector<std::pair<int, int>>> vam; };
+  std::vector<Cv> cvs; std::vector<int> mv_i, mv_l; std::vector<std::vector<int>> lcam((size_t)n_ext_links), lcav((size_t)n_ext_links);
+  std::vector<std::vector<int>> int_cam;                                // upstream link of every internal link (its entry link)
+  { size_t m0 = 0;
+    while (m0 < moves.size()) { size_t m1 = m0; while (m1 < moves.size() && moves[m1].node == moves[m0].node) m1++;
+      struct E { std::string ka, ko; int k, a, o, din; };
+      std::vector<E> es;
+      for (size_t q = m0; q < m1; q++) for (int k = 0; k < NL; k++) es.push_back({link_name[moves[q].a] + "V" + std::to_string(k + 1), link_name[moves[q].o], k, moves[q].a, moves[q].o, moves[q].din});
+      std::sort(es.begin(), es.end(), [](const E& x, const E& y) { if (x.ka != y.ka) return x.ka < y.ka; if (x.ko != y.ko) return x.ko < y.ko; return x.k < y.k; });
+      std::vector<int> exits; std::vector<std::vector<std::pair<int, int>>> feeds;
+      const int node = moves[m0].node;
+      for (auto& e : es) { double ax, ay, ox, oy; lane_pt(e.a, e.k, true, ax, ay); lane_pt(e.o, e.k, false, ox, oy); double len = std::hypot(ox - ax, oy - ay);
+        int ent = link_i[8 * (size_t)e.a] + e.k;
+        int il = add_link(node, node, 1, len, exit_in_count[e.o] > 1 ? 'C' : 'R', node, ent, ax, ay, ox, oy, e.din, 3);
+        int ilane = link_i[8 * (size_t)il];
+        succ_rows[ent].push_back(e.o); succ_rows[ent].push_back(ilane);
+        int_succ_key.push_back(e.o); int_succ_next.push_back(link_i[8 * (size_t)e.o] + e.k);
+        sl_rows[ent].insert(sl_rows[ent].end(), {node, e.a, e.k, e.o, e.k});
+        size_t xi = 0; while (xi < exits.size() && exits[xi] != e.o) xi++;
+        if (xi == exits.size()) { exits.push_back(e.o); feeds.emplace_back(); }
+        feeds[xi].push_back({il, e.k});
+        mv_i.insert(mv_i.end(), {node, e.a, e.o, (int)mv_l.size(), 1}); mv_l.push_back(il);
+        int_cam.push_back({e.a}); lcav[e.a].push_back(il); }
+      for (size_t xi = 0; xi < exits.size(); xi++) { const int o = exits[xi]; for (auto& fd : feeds[xi]) lcam[o].push_back(fd.first);
+        if (feeds[xi].size() < 2) continue;
+        Cv cv; cv.name = "J" + std::to_string(node / ny) + "_" + std::to_string(node % ny) + "_C0_" + link_name[o]; cv.node = node; cv.down = o;
+        for (auto& fd : feeds[xi]) cv.am.push_back(fd.first);
+        for (int kk = 0; kk < NL; kk++) { std::vector<std::pair<double, int>> ang; double vx0, vy0, vx1, vy1; lane_pt(o, kk, false, vx0, vy0); lane_pt(o, kk, true, vx1, vy1);
+          std::vector<int> lanes_kk;
+          for (auto& fd : feeds[xi]) if (fd.second == kk) { const int ln = link_i[8 * (size_t)fd.first]; lanes_kk.push_back(ln); const double* g = &link_geom[4 * (size_t)fd.first];
+            double a1 = vx1 - vx0, a2 = vy1 - vy0, b1 = g[0] - vx0, b2 = g[1] - vy0; double t = std::atan2(a1 * b2 - a2 * b1, a1 * b1 + a2 * b2); if (t < 0) t += 2 * 3.14159265358979323846;
+            ang.push_back({t, ln}); }
+          std::sort(ang.begin(), ang.end());
+          std::vector<std::pair<int, int>> v; for (int ln : lanes_kk) { int lev = 0; for (size_t q = 0; q < ang.size(); q++) if (ang[q].second == ln) lev = (int)ang.size() - (int)q; v.push_back({ln, lev}); }
+          cv.vam.push_back(v); }
+        cvs.push_back(std::move(cv)); }
+      m0 = m1; } }
   const int n_lanes = (int)lane_i.size() / 4;
   std::vector<int> succ_off(n_lanes + 1, 0), succ_i, sl_off(n_lanes + 1, 0), sl_i; std::vector<double> succ_f, sl_f;
   for (int l = 0; l < n_lanes; l++) {
@@ -134,6 +168,24 @@ extern "C" int symgen_grid(const char* path, int nx, int ny, double per_lane, in
   W.I("ctrl_i", ctrl_i); W.D("ctrl_f", ctrl_f); W.I("seq_i", seq_i); W.D("seq_f", seq_f); W.I("sig_i", sig_i); W.D("sig_f", sig_f);
   W.I("node_i", node_i); W.D("node_xy", node_xy); W.I("route_off", route_off); W.I("route_links", route_links);
   W.I("exit_i", exit_i); W.D("exit_f", exit_f); W.I("iv_i", iv_i); W.D("iv_f", iv_f); W.I("iv_id", iv_id);
+  if (merges) {
+    std::sort(cvs.begin(), cvs.end(), [](const Cv& x, const Cv& y) { return x.name < y.name; });      // Reseau::Liste_convergents: std::map by id
+    std::vector<int> cvg_i, cvgam, pt_i, ptam; std::vector<double> cvg_f, cvg_tf;
+    for (size_t ci = 0; ci < cvs.size(); ci++) { const Cv& c = cvs[ci];
+      cvg_i.insert(cvg_i.end(), {c.node, c.down, (int)pt_i.size() / 4, (int)c.vam.size(), (int)cvgam.size(), (int)c.am.size(), 0, 0});
+      cvg_f.insert(cvg_f.end(), {30.0, 1.0, 1.0, 5.0}); cvg_tf.push_back(0.0); cvgam.insert(cvgam.end(), c.am.begin(), c.am.end());
+      for (size_t kk = 0; kk < c.vam.size(); kk++) { pt_i.insert(pt_i.end(), {(int)ci, link_i[8 * (size_t)c.down] + (int)kk, (int)ptam.size() / 2, (int)c.vam[kk].size()});
+        for (auto& a : c.vam[kk]) { ptam.push_back(a.first); ptam.push_back(a.second); } } }
+    const int K = (int)link_i.size() / 8; std::vector<int> cam_off(K + 1, 0), cam_l, cav_off(K + 1, 0), cav_l;
+    for (int k = 0; k < K; k++) { const std::vector<int>& a = k < n_ext_links ? lcam[k] : int_cam[k - n_ext_links]; cam_l.insert(cam_l.end(), a.begin(), a.end()); cam_off[k + 1] = (int)cam_l.size();
+      if (k < n_ext_links) cav_l.insert(cav_l.end(), lcav[k].begin(), lcav[k].end()); else cav_l.push_back(int_succ_key[k - n_ext_links]);
+      cav_off[k + 1] = (int)cav_l.size(); }
+    W.I("cvg_i", cvg_i); W.D("cvg_f", cvg_f); W.D("cvg_tf", cvg_tf); W.I("cvgam_i", cvgam); W.I("pt_i", pt_i); W.I("ptam_i", ptam); W.I("cafmvt_i", mv_i); W.I("cafmvt_links", mv_l);
+    W.I("lcam_off", cam_off); W.I("lcam_links", cam_l); W.I("lcav_off", cav_off); W.I("lcav_links", cav_l);
+  }
   const char cn[] = "VL"; W.sec("names_cls", 2, cn, 3);
   return W.close() ? (int)(iv_id.size()) : -1;
+}
+extern "C" int symgen_grid(const char* path, int nx, int ny, double per_lane, int seed, int route_len, int n_steps, int rank, int world, long long* n_vehicles_total) {
+  return symgen_grid2(path, nx, ny, per_lane, seed, route_len, n_steps, rank, world, n_vehicles_total, 1);
 }

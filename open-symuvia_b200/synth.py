@@ -621,15 +621,15 @@ def config(name: str, **kw) -> NetBuilder:
 
 
 def fast_grid(path: str, nx: int, ny: int, per_lane: float = 12.6, seed: int = 42, route_len: int = 24, n_steps: int = 300,
-              rank: int = 0, world: int = 1):
+              rank: int = 0, world: int = 1, merges: bool = True):
     """C++ generator (csrc/gen_grid.cpp) of the pre-seeded grid: the whole network, the vehicles of strip `rank` of `world`
     (global ids).  Returns (vehicles written, vehicles in the whole population)."""
     import ctypes as C
     import os
     lib = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsymgen.so"))
-    lib.symgen_grid.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
+    lib.symgen_grid2.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.c_int]
     tot = C.c_longlong(0)
-    n = lib.symgen_grid(path.encode(), nx, ny, per_lane, seed, route_len, n_steps, rank, world, C.byref(tot))
+    n = lib.symgen_grid2(path.encode(), nx, ny, per_lane, seed, route_len, n_steps, rank, world, C.byref(tot), int(merges))
     if n < 0:
         raise RuntimeError(f"symgen_grid could not write {path}")
     return n, int(tot.value)

@@ -178,6 +178,7 @@ struct Sim {
   std::vector<int> link_cvg_aval;                                   // link -> Convergent that is its downstream connection (-1)
   std::vector<std::vector<std::pair<int, int>>> link_capteurs;      // Tuyau::getListeCapteursConvergents: (cvg, sensor)
   std::vector<std::vector<int>> lcam, lcav;                         // m_LstTuyAm of a link's upstream connection / m_LstTuyAv of its downstream one
+  std::vector<std::vector<int>> node_mvts;                          // CarrefourAFeuxEx::m_LstMouvements per junction (indices into caf_mvts, reference order)
   long n_insertions = 0, n_refus = 0, n_pins = 0, n_cong = 0; double inst_cur = 0;
   bool trace_ties = getenv("ORACLE_TRACE_TIES") != nullptr, trace_merge = getenv("ORACLE_TRACE_MERGE") != nullptr;
   // dynamic
@@ -267,6 +268,8 @@ struct Sim {
       for (size_t m = 0; m < f.N("cafmvt_i") / 5; m++) { CafMvt x{mi[5 * m], mi[5 * m + 1], mi[5 * m + 2], {}};
         for (int q = mi[5 * m + 3]; q < mi[5 * m + 3] + mi[5 * m + 4]; q++) x.tl.push_back(ml[q]);
         caf_mvts.push_back(std::move(x)); }
+      node_mvts.resize(node_type.size());
+      for (size_t m = 0; m < caf_mvts.size(); m++) node_mvts[caf_mvts[m].node].push_back((int)m);
     }
     if (f.N("lcam_off")) { const int* o = f.I("lcam_off"); const int* l = f.I("lcam_links"); for (size_t k = 0; k < links.size(); k++) lcam[k].assign(l + o[k], l + o[k + 1]); }
     if (f.N("lcav_off")) { const int* o = f.I("lcav_off"); const int* l = f.I("lcav_links"); for (size_t k = 0; k < links.size(); k++) lcav[k].assign(l + o[k], l + o[k + 1]); }
@@ -1170,7 +1173,7 @@ struct Sim {
     for (int k : r) if (k == link) return true;
     int br = links[link].brick;
     if (br >= 0) for (size_t i = 0; i + 1 < r.size(); i++) if (links[r[i]].down_node == br) {
-      for (auto& m : caf_mvts) if (m.node == br && m.ent_link == r[i] && m.exit_link == r[i + 1]) for (int t : m.tl) if (t == link) return true; }
+      for (int mi : node_mvts[br]) { const CafMvt& m = caf_mvts[mi]; if (m.ent_link == r[i] && m.exit_link == r[i + 1]) for (int t : m.tl) if (t == link) return true; } }
     return false; }
   // Reseau::GetVehiculeAmont reseau.cpp:9638-9690 (first lane of every link only)
   Veh* get_vehicule_amont(int link, double dst, double cum) {
@@ -1214,10 +1217,10 @@ struct Sim {
         if (node_type[br] == 'C' && links[r[i]].up_node == br) {                            // CarrefourAFeuxEx::GetTuyauxInternes :1598-1660: first lane pair that has a movement
           bool found = false;
           for (int a = 0; a < links[r[i - 1]].n_lanes && !found; a++) for (int b2 = 0; b2 < links[r[i]].n_lanes && !found; b2++)
-            for (auto& m : caf_mvts) if (m.node == br && m.ent_link == r[i - 1] && m.exit_link == r[i] && !m.tl.empty() &&
+            for (int mi : node_mvts[br]) { const CafMvt& m = caf_mvts[mi]; if (m.ent_link == r[i - 1] && m.exit_link == r[i] && !m.tl.empty() &&
                 lanes[links[m.tl.front()].first_lane].prev_lane == links[r[i - 1]].first_lane + a) {
               int last = links[m.tl.back()].first_lane; bool to_b = false; for (auto& q : lanes[last].succ) if (q.next_lane == links[r[i]].first_lane + b2) to_b = true;
-              if (to_b) { for (int t : m.tl) iti.push_back(t); found = true; break; } } } }
+              if (to_b) { for (int t : m.tl) iti.push_back(t); found = true; break; } } } } }
       iti.push_back(r[i]); }
     int idx = -1; for (size_t k = 0; k < iti.size(); k++) if (iti[k] == lanes[v->lane[1]].link) { idx = (int)k; break; }
     if (idx != -1) { p = -(lanes[v->lane[1]].length - p);
@@ -1425,7 +1428,7 @@ struct Sim {
         if (P.vam.size() == 0) break;
         if (P.vam.size() == 1) { P.vam[0].niv = 1; break; }
         std::vector<const CafMvt*> g1, g2, g3; std::vector<int> tmv;                        // :1437-1497
-        for (auto& m : caf_mvts) if (m.node == C.node) {
+        for (int mi : node_mvts[C.node]) { const CafMvt& m = caf_mvts[mi];
           int tm = -1; for (int t : m.tl) { for (auto& a : P.vam) if (lanes[a.lane].link == t) { tm = t; break; } if (tm >= 0) break; }
           if (tm < 0) continue;
           double pr = 0;
