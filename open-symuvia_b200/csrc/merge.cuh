@@ -52,7 +52,7 @@ struct DevMrg {
   double* pt_last; int *pt_rand, *pt_free;                                 // m_dbInstLastPassage, m_nRandNumbers, m_bFreeFlow
   int* cand_up;                                                            // upstream lane -> first vehicle that crossed it entirely this step
   int *own_min, *own_max;                                                  // per vehicle slot: lowest / highest point that touches it
-  int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw; double* proba;       // per point, this step
+  int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw, *flist; double* proba;   // per point, this step; flist: the points the walk must visit (unordered)
   int *nused, *nvoie;                                                      // per vehicle: intermediate lanes used this step; m_pNextVoie (sticky)
   double* mrgx;                                                            // per order position: phase A -> phase B side record (6 doubles)
   DevRng* rng; unsigned* draws;                                            // the stream (device copy) and the cumulative count of count-only draws
@@ -629,13 +629,13 @@ __global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const
   if (st == MS_NONE) return;
   bool clean = st != MS_OVERFLOW;
   for (int k = 0; k < M.ninv[p] && clean; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p) clean = false; }
-  if (!clean) { M.st[p] = MS_DIRTY; atomicAdd(n_flag, 1); return; }
-  if (st == MS_VALUES) { atomicAdd(n_flag, 1); return; }                                   // decided by the walk, applied by k_mrg_apply
+  if (!clean) { M.st[p] = MS_DIRTY; M.flist[atomicAdd(n_flag, 1)] = p; return; }
+  if (st == MS_VALUES) { M.flist[atomicAdd(n_flag, 1)] = p; return; }                      // decided by the walk, applied by k_mrg_apply
   const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
   MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
   st = merge_point(W, p, MM_EVAL, A, nullptr);
   M.st[p] = st; M.ndraw[p] = A.ndraw;
-  if (A.ndraw) atomicAdd(n_flag, 1);
+  if (A.ndraw) M.flist[atomicAdd(n_flag, 1)] = p;
 }
 // advance the stream by `n` accepted draws (RandManager::myRand = mt19937 + bucket rejection), one block of 256 threads
 __device__ inline void rng_skip_block(DevRng* r, unsigned n, unsigned* sh_new, int* sh_rej) {
@@ -690,45 +690,57 @@ __global__ void k_rng_ctx(DevRng* r, const unsigned* draws, unsigned* seen, cons
 __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start,
                                                   const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const int* n_flag,
                                                   unsigned* seen, int* out, const int* guard) {
-  __shared__ unsigned sh_new[624]; __shared__ int sh_rej; __shared__ int sh_list[256]; __shared__ int sh_n;
+  constexpr int kList = 2048;
+  __shared__ unsigned sh_new[624]; __shared__ int sh_rej; __shared__ int sh_list[kList]; __shared__ int sh_sorted[kList]; __shared__ DevRng srng;
   if (guard && *guard == 0) return;
   const int tid = threadIdx.x;
+  for (int k = tid; k < 624; k += 256) srng.mt[k] = M.rng->mt[k];                          // the stream works in shared memory and goes back at the end
+  if (tid == 0) { srng.idx = M.rng->idx; srng.count = M.rng->count; }
+  __syncthreads();
   const unsigned now = *M.draws; const unsigned pre = now - *seen;
-  rng_skip_block(M.rng, pre, sh_new, &sh_rej);
-  if (tid == 0) { *seen = now; out[0] = 0; }
-  if (*n_flag == 0) return;                                                               // no point draws or shares a vehicle this step
-  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+  rng_skip_block(&srng, pre, sh_new, &sh_rej);
+  const int nf = *n_flag;
   int total = 0;
-  for (int base = 0; base < M.n_pt; base += 256) {
-    __syncthreads();
-    if (tid == 0) sh_n = 0;
-    __syncthreads();
-    const int p = base + tid; bool f = false;
-    if (p < M.n_pt) { const int st = M.st[p]; f = st == MS_VALUES || st == MS_DIRTY || M.ndraw[p] > 0; }
-    const unsigned m = __ballot_sync(0xffffffffu, f);
-    __shared__ int wbase[8];
-    if ((tid & 31) == 0) wbase[tid >> 5] = __popc(m);
-    __syncthreads();
-    if (tid == 0) { int s = 0; for (int w = 0; w < 8; w++) { int t = wbase[w]; wbase[w] = s; s += t; } sh_n = s; }
-    __syncthreads();
-    if (f) sh_list[wbase[tid >> 5] + __popc(m & ((1u << (tid & 31)) - 1))] = p;
-    __syncthreads();
-    if (tid == 0) for (int k = 0; k < sh_n; k++) {
-      const int q = sh_list[k]; const int st = M.st[q];
-      if (st == MS_DIRTY) { MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; const unsigned c0 = M.rng->count;
-        // literal order: count-only draws interleave with the test's draws exactly as merge_point issues them in serial mode
-        merge_point(W, q, MM_SERIAL, A, M.rng); total += (int)(M.rng->count - c0); M.st[q] = MS_DONE; M.counters[SYMGPU_CNT_MRG_SERIAL]++; }
+  if (nf > 0) {
+    const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+    auto visit = [&](int q) {
+      const int st = M.st[q];
+      if (st == MS_DIRTY) { MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; const unsigned c0 = srng.count;
+        merge_point(W, q, MM_SERIAL, A, &srng); total += (int)(srng.count - c0); M.st[q] = MS_DONE; M.counters[SYMGPU_CNT_MRG_SERIAL]++; }
       else if (st == MS_VALUES) {
-        for (int d = 0; d < M.pre[q]; d++) rng_next(M.rng);
-        rng_next(M.rng); int used = 0; bool ins = false; const double proba = M.proba[q];
+        for (int d = 0; d < M.pre[q]; d++) rng_next(&srng);
+        rng_next(&srng); int used = 0; bool ins = false; const double proba = M.proba[q];
         int rn = M.kmax[q];
-        for (int d = 0; d < rn; d++) { const double r = rng_next(M.rng) / 32767.0; rn--; used++; if (r < proba) { ins = true; break; } }
+        for (int d = 0; d < rn; d++) { const double r = rng_next(&srng) / 32767.0; rn--; used++; if (r < proba) { ins = true; break; } }
         M.decide[q] = ((int)ins << 16) | used; total += M.pre[q] + 1 + used; M.counters[SYMGPU_CNT_MRG_VALUES]++; }
-      else { for (int d = 0; d < M.ndraw[q]; d++) rng_next(M.rng); total += M.ndraw[q]; }
+      else { for (int d = 0; d < M.ndraw[q]; d++) rng_next(&srng); total += M.ndraw[q]; }
+    };
+    if (nf <= kList) {                                                                     // the usual case: a short list, ordered by a rank sort in shared memory
+      for (int k = tid; k < nf; k += 256) sh_list[k] = M.flist[k];
+      __syncthreads();
+      for (int k = tid; k < nf; k += 256) { const int v = sh_list[k]; int r = 0; for (int j = 0; j < nf; j++) r += sh_list[j] < v; sh_sorted[r] = v; }
+      __syncthreads();
+      if (tid == 0) for (int k = 0; k < nf; k++) visit(sh_sorted[k]);
+    } else {                                                                               // many: scan the points 256 at a time
+      __shared__ int wbase[8]; __shared__ int sh_n;
+      for (int base = 0; base < M.n_pt; base += 256) {
+        __syncthreads();
+        const int p = base + tid; bool f = false;
+        if (p < M.n_pt) { const int st = M.st[p]; f = st == MS_VALUES || st == MS_DIRTY || M.ndraw[p] > 0; }
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if ((tid & 31) == 0) wbase[tid >> 5] = __popc(m);
+        __syncthreads();
+        if (tid == 0) { int s2 = 0; for (int w = 0; w < 8; w++) { int t = wbase[w]; wbase[w] = s2; s2 += t; } sh_n = s2; }
+        __syncthreads();
+        if (f) sh_list[wbase[tid >> 5] + __popc(m & ((1u << (tid & 31)) - 1))] = p;
+        __syncthreads();
+        if (tid == 0) for (int k = 0; k < sh_n; k++) visit(sh_list[k]);
+      }
     }
   }
   __syncthreads();
-  if (tid == 0) out[0] = total;
+  for (int k = tid; k < 624; k += 256) M.rng->mt[k] = srng.mt[k];
+  if (tid == 0) { M.rng->idx = srng.idx; M.rng->count = srng.count; *seen = now; out[0] = total; }
 }
 __global__ void k_mrg_apply(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
                             const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {

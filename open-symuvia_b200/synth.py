@@ -535,11 +535,14 @@ def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, 
 # ---------------------------------------------------------------------------------------------
 def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_steps=600, seed=42, classes=None, type_coefs=None,
              offramp_every=0, offramp_share=0.1, preseed_density=0.0, chgtvoie=True, dst_chgtvoie=200.0, dst_force=0.0, phi_force=1.0,
-             slow_lane_speed=None, shuffle=False, accbornee=False, relax=1.0, signal=None, signal_at=None, exponential=False) -> NetBuilder:
+             slow_lane_speed=None, shuffle=False, accbornee=False, relax=1.0, signal=None, signal_at=None, exponential=False,
+             onramp_every=0, onramp_demand=0.15, onramp_length=250.0, onramp_tf=0.0, onramp_exponential=False) -> NetBuilder:
     """n_links consecutive links joined by pass-through distributors (lane k -> lane k).  Every `offramp_every` nodes a one-lane
     off-ramp leaves from lane 0 only, so exiting vehicles must reach lane 0 in the mandatory zone (`chgtvoie_dstfin`).
     Demand enters at the first link (lanes drawn uniformly); `preseed_density` (veh/m/lane) pre-seeds every lane.
-    The merges (on-ramp Convergents) of BASELINE config C3 are row A10 and not generated.
+    Every `onramp_every` nodes (offset by one from the off-ramps) the pass-through distributor is a `Convergent` instead (reseau.cpp:8300-8420):
+    a one-lane on-ramp of priority level 2 joins the main road (level 1); every upstream lane is an upstream lane of every merge point
+    (one per downstream lane), the ramp leads into lane 0.  The ramps have their own origins (`onramp_demand` veh/s each).
     `signal=(green, amber, red)` puts a fixed-time stop line on every lane at the end of link `signal_at` (default: the middle)."""
     rng = np.random.default_rng(seed)
     b = NetBuilder(n_steps=n_steps, seed=seed, chgtvoie=chgtvoie, dst_chgtvoie=dst_chgtvoie, accbornee=accbornee, relax=relax)
@@ -552,13 +555,26 @@ def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_st
     nodes = [b.add_node("E", "E0", (0.0, 0.0))]
     sig_j = (signal_at if signal_at is not None else n_links // 2) if signal else -1
     ctrl = b.add_ctrl(sum(signal), [dict(len=sum(signal), signals=[])]) if signal else -1
+    on_at = [j for j in range(1, n_links) if onramp_every and j % onramp_every == (1 if onramp_every > 1 else 0) and j != sig_j]
     for j in range(1, n_links):
-        nodes.append(b.add_node("R", f"R{j}", (j * length, 0.0), ctrl=ctrl if j == sig_j else -1))
+        nodes.append(b.add_node("C" if j in on_at else "R", f"{'CV' if j in on_at else 'R'}{j}", (j * length, 0.0), ctrl=ctrl if j == sig_j else -1))
     nodes.append(b.add_node("S", "S_end", (n_links * length, 0.0)))
     main = []
     for j in range(n_links):
-        main.append(b.add_link(f"M{j}", nodes[j], nodes[j + 1], n_lanes, length, vit_reg, "S" if j == n_links - 1 else "R",
+        main.append(b.add_link(f"M{j}", nodes[j], nodes[j + 1], n_lanes, length, vit_reg, "S" if j == n_links - 1 else ("C" if j + 1 in on_at else "R"),
                                geom=(j * length, 0.0, (j + 1) * length, 0.0)))
+    onramps = {}
+    for j in on_at:
+        e = b.add_node("E", f"EO{j}", (j * length - onramp_length, -60.0))
+        r = b.add_link(f"O{j}", e, nodes[j], 1, onramp_length, vit_reg * 0.8, "C", geom=(j * length - onramp_length, -60.0, j * length, 0.0))
+        b.add_succ(b.lane_of(r, 0), main[j], b.lane_of(main[j], 0), 1.0, 1)
+        onramps[j] = (e, r)
+        up = [b.lane_of(main[j - 1], k) for k in range(n_lanes)] + [b.lane_of(r, 0)]
+        pts = [dict(down_lane=b.lane_of(main[j], l), vam=[(ln, 1) for ln in up[:-1]] + [(up[-1], 2)]) for l in range(n_lanes)]
+        b.add_convergent(f"CV{j}", -1, main[j], [main[j - 1], r], pts, tf=[onramp_tf] * len(cl))
+        b.link_cam[main[j]] = [main[j - 1], r]
+        b.link_cav[main[j - 1]] = [main[j]]
+        b.link_cav[r] = [main[j]]
     ramps = {}
     for j in range(1, n_links):
         for k in range(n_lanes):
@@ -581,6 +597,13 @@ def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_st
         dests.append((x, offramp_share / len(ramps), [(ramp_routes[j], 1.0)]))
     if demand > 0:
         b.add_entry(nodes[0], main[0], [(1e12, demand)], dests, type_coefs=tc, exponential=exponential)
+    for j, (e, r) in onramps.items():                                   # ramp origins: through traffic and the off-ramps further down
+        dj = [(x_end, 1.0 - (offramp_share if any(jj > j for jj in ramps) else 0.0), [(b.add_route([r] + main[j:]), 1.0)])]
+        later = [jj for jj in ramps if jj > j]
+        for jj in later:
+            dj.append((ramps[jj][1], offramp_share / len(later), [(b.add_route([r] + main[j:jj] + [ramps[jj][0]]), 1.0)]))
+        if onramp_demand > 0:
+            b.add_entry(e, r, [(1e12, onramp_demand)], dj, type_coefs=tc, exponential=onramp_exponential)
     if preseed_density > 0:
         seeds = []
         for j, k in enumerate(main):
@@ -607,12 +630,52 @@ def corridor(n_links=10, length=500.0, n_lanes=3, vit_reg=25.0, demand=0.9, n_st
     return b
 
 
+# ---------------------------------------------------------------------------------------------
+# plain merge: two upstream links into one downstream link through a Convergent (reseau.cpp:6432-6473, :8300-8420)
+# ---------------------------------------------------------------------------------------------
+def ymerge(len_main=400.0, len_ramp=300.0, len_down=500.0, lanes_main=1, lanes_down=1, demand_main=0.3, demand_ramp=0.2, tf=0.0, vit_reg=20.0,
+           vit_ramp=None, n_steps=400, exit_capacity=-1.0, classes=None, type_coefs=None, prio_main=1, prio_ramp=2, seed=42, exponential=False,
+           tagreg=30.0, gamma=1.0, mu=1.0, pos_cpt_av=5.0, accbornee=False) -> NetBuilder:
+    """Main road (priority level `prio_main`) and a one-lane ramp (`prio_ramp`) merging into a downstream link; main lane k -> downstream lane
+    min(k, lanes_down - 1), ramp -> lane 0.  Every upstream lane is an upstream lane of every merge point, as the loader builds them."""
+    b = NetBuilder(n_steps=n_steps, seed=seed, accbornee=accbornee)
+    cl = classes or [VL]
+    for c in cl:
+        b.add_class(c)
+    em = b.add_node("E", "E_main", (0.0, 0.0))
+    er = b.add_node("E", "E_ramp", (len_main - len_ramp, -80.0))
+    m = b.add_node("C", "CV", (len_main, 0.0))
+    x = b.add_node("S", "S_end", (len_main + len_down, 0.0))
+    lm = b.add_link("MAIN", em, m, lanes_main, len_main, vit_reg, "C", geom=(0.0, 0.0, len_main, 0.0))
+    lr = b.add_link("RAMP", er, m, 1, len_ramp, vit_ramp or vit_reg, "C", geom=(len_main - len_ramp, -80.0, len_main, 0.0))
+    ld = b.add_link("DOWN", m, x, lanes_down, len_down, vit_reg, "S", geom=(len_main, 0.0, len_main + len_down, 0.0))
+    for k in range(lanes_main):
+        b.add_succ(b.lane_of(lm, k), ld, b.lane_of(ld, min(k, lanes_down - 1)), 1.0, 1)
+    b.add_succ(b.lane_of(lr, 0), ld, b.lane_of(ld, 0), 1.0, 1)
+    up = [(b.lane_of(lm, k), prio_main) for k in range(lanes_main)] + [(b.lane_of(lr, 0), prio_ramp)]
+    b.add_convergent("CV", -1, ld, [lm, lr], [dict(down_lane=b.lane_of(ld, l), vam=list(up)) for l in range(lanes_down)],
+                     tagreg=tagreg, gamma=gamma, mu=mu, pos_cpt_av=pos_cpt_av, tf=[tf] * len(cl))
+    b.link_cam[ld] = [lm, lr]
+    b.link_cav[lm] = [ld]
+    b.link_cav[lr] = [ld]
+    ex = b.add_exit(x, ld, exit_capacity)
+    if demand_main > 0:
+        b.add_entry(em, lm, [(1e12, demand_main)], [(ex, 1.0, [(b.add_route([lm, ld]), 1.0)])], type_coefs=type_coefs, exponential=exponential)
+    if demand_ramp > 0:
+        b.add_entry(er, lr, [(1e12, demand_ramp)], [(ex, 1.0, [(b.add_route([lr, ld]), 1.0)])], type_coefs=type_coefs, exponential=exponential)
+    return b
+
+
 def config(name: str, **kw) -> NetBuilder:
     """Named BASELINE.json configurations."""
     if name == "C1":
         return single_link(**kw)
     if name == "C2":
         return grid(n=10, n_steps=1800, demand_per_lane=0.2, demand_duration=1200.0, **kw)
+    if name == "C3":    # 10 km arterial, 3 lanes, 2 classes, lane changing, on-ramp Convergents and off-ramp Repartiteurs every 1 km, ~0.06 veh/m/lane pre-seeded
+        kw.setdefault("n_steps", 600)
+        return corridor(n_links=20, length=500.0, n_lanes=3, demand=1.2, offramp_every=2, offramp_share=0.1, onramp_every=2, onramp_demand=0.2,
+                        preseed_density=0.06, chgtvoie=True, **kw)
     if name == "C4":
         return grid(n=100, n_steps=300, demand_per_lane=0.0, preseed_per_lane=12.6, **kw)
     if name == "C5":

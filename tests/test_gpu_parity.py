@@ -98,8 +98,51 @@ def test_grid_rectangular_mixed(synth):
 
 
 def test_c2_config(synth):
-    """BASELINE config C2 (10x10 grid, ~20k vehicles at peak), first 400 steps."""
-    s = run_parity(synth.config("C2"), 400, check_every=10)
+    """BASELINE config C2 (10x10 signalised grid with its merge points, ~20k vehicles at peak): the full 1800 steps."""
+    s = run_parity(synth.config("C2"), 1800, check_every=10)
+    _check(s)
+    assert s["merge_ins"] == s["merge_ins_oracle"] > 10000
+
+
+# ---- merge points (row A10) ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(),                                                            # ramp + main road, one lane each
+    dict(tf=6.0, demand_ramp=0.5, demand_main=0.0),                    # follow-up time: imposed approach speed of the branch head
+    dict(demand_main=0.75, demand_ramp=0.3, vit_reg=14.0),             # dense priority stream: refusals, ramp queue
+    dict(lanes_main=2, lanes_down=2, demand_main=0.8),                 # multi-lane merge: inner-lane follower draw, one point per downstream lane
+    dict(lanes_main=3, lanes_down=2, demand_main=1.0, demand_ramp=0.25),
+    dict(exit_capacity=0.25, demand_main=0.3),                         # congested downstream: sensor-based supply / demand test with draws
+    dict(exit_capacity=0.3, demand_main=0.4, demand_ramp=0.3, exponential=True),
+    dict(prio_main=2, prio_ramp=1),                                    # the ramp has the right of way
+    dict(accbornee=True, demand_main=0.5),
+], ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items()) or "default")
+def test_plain_merge(synth, kw):
+    classes = [synth.VL, synth.PL] if kw.get("lanes_main", 1) > 1 else None
+    s = run_parity(synth.ymerge(n_steps=500, classes=classes, type_coefs=[0.8, 0.2] if classes else None, **kw), 500)
+    _check(s)
+    assert s["merge_ins"] == s["merge_ins_oracle"] > 0
+
+
+def test_corridor_with_on_and_off_ramps(synth):
+    """Small C3: three lanes, two vehicle types, lane changing, on-ramp Convergents and off-ramp distributors."""
+    b = synth.corridor(n_links=8, length=400.0, n_lanes=3, demand=1.1, offramp_every=2, onramp_every=2, onramp_demand=0.25, preseed_density=0.05,
+                       shuffle=True, n_steps=400)
+    s = run_parity(b, 400)
+    _check(s)
+    assert s["merge_ins"] == s["merge_ins_oracle"] > 100
+
+
+def test_c3_config_prefix(synth):
+    """BASELINE config C3 geometry (10 km, on / off ramps every km, lane changing, two types), first 300 steps."""
+    s = run_parity(synth.config("C3"), 300, check_every=5)
+    _check(s)
+
+
+def test_lane_changing_without_origins(synth):
+    """Pre-seeded corridor, no demand: the random stream is advanced on the device by the next-lane memo draws of every step, and the
+    lane-change acceptance draws of the next step must come after them (the stream lives on the device)."""
+    b = synth.corridor(n_links=6, length=500.0, n_lanes=3, demand=0.0, offramp_every=2, preseed_density=0.06, shuffle=True, n_steps=200)
+    s = run_parity(b, 200)
     _check(s)
 
 
@@ -110,8 +153,9 @@ def test_c4_full_size_prefix_and_invariants(synth, pkg):
     import os
     import tempfile
     b = synth.config("C4")
-    s = run_parity(b, 6, check_every=3)
+    s = run_parity(b, 50, check_every=10)
     _check(s)
+    assert s["merge_ins"] == s["merge_ins_oracle"] > 100000
     fd, path = tempfile.mkstemp(suffix=".symflat")
     os.close(fd)
     b.write(path)

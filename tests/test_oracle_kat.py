@@ -165,3 +165,67 @@ def test_gipps_idm_run_and_respect_leader(synth, law):
             p = p[p > -1e-300]
             assert (np.diff(p) <= 1e-9).all()     # ids increase upstream: positions must not increase with id
     assert o.n > 5
+
+
+# ---- merge points (row A10): answers derivable by hand from convergent.cpp:333-990 and AbstractCarFollowing.cpp:336-664 -------
+def test_merge_alone_on_the_ramp_inserts_at_the_crossing_instant(synth):
+    """No traffic on the priority branch, free flow downstream: every ramp vehicle inserts (no refusal), keeps the position the car
+    following law gave it (free flow over ta = dt - tr from the merge = what was left of the step), and the point records the
+    crossing instant t - dt + tr with tr = dt * (L - pos1) / travelled distance (AbstractCarFollowing.cpp:544-547, convergent.cpp:818)."""
+    v, Lr = 16.0, 300.0
+    b = synth.ymerge(demand_main=0.0, demand_ramp=0.2, vit_reg=v, len_ramp=Lr, n_steps=200)
+    o = _oracle(b)
+    ramp_lane = b.lane_of(1, 0)
+    prev = {}
+    last_seen = 0.0
+    for k in range(1, 151):
+        o.step()
+        s = o.state()
+        t_last, _ = o.merge_state()
+        for i, vid in enumerate(s["id"]):
+            if vid in prev and prev[vid][0] == ramp_lane and s["lane"][i] != ramp_lane:       # crossed the merge during this step
+                p1 = prev[vid][1]
+                tr = (Lr - p1) / v
+                assert abs(t_last[0] - (k - 1.0 + tr)) < 1e-9
+                assert abs(s["pos"][i] - (p1 + v - Lr)) < 1e-9 and abs(s["vit"][i] - v) < 1e-9
+                last_seen = t_last[0]
+        prev = {vid: (s["lane"][i], s["pos"][i]) for i, vid in enumerate(s["id"])}
+    assert last_seen > 0 and o.counter(5) == 0 and o.counter(4) > 20                            # no refusal, every crossing is an insertion
+
+
+def test_merge_follow_up_time_spaces_the_insertions(synth):
+    """Downstream condition (AbstractCarFollowing.cpp:385-391): t - last passage >= max(Tf, 1/Qmax).  With Tf = 6 s and a ramp vehicle every
+    2 s the insertions are exactly Tf apart once the ramp queues: the head of the non-priority branch is held to the speed that brings
+    it to the merge when the follow-up time has elapsed (Convergent::CalculVitesseLeader, convergent.cpp:1121-1168) and inserts at
+    tr = dt - (t - (last + Tf)) (AbstractCarFollowing.cpp:589-593)."""
+    tf, Lr = 6.0, 300.0
+    b = synth.ymerge(demand_main=0.0, demand_ramp=0.5, tf=tf, vit_reg=16.0, len_ramp=Lr, n_steps=300)
+    o = _oracle(b)
+    ramp_lane = b.lane_of(1, 0)
+    instants = []
+    for k in range(1, 251):
+        o.step()
+        t_last, _ = o.merge_state()
+        if not instants or t_last[0] != instants[-1]:
+            instants.append(float(t_last[0]))
+        s = o.state()
+        on_ramp = s["lane"] == ramp_lane
+        if on_ramp.any():
+            assert s["pos"][on_ramp].max() <= Lr + 1e-12
+    gaps = np.diff([t for t in instants if t > 0])
+    assert len(gaps) > 15 and gaps.min() >= tf - 1e-9
+    assert np.allclose(gaps[-10:], tf, atol=1e-9)               # saturated ramp: one insertion per follow-up time
+    assert o.n > 40                                               # the queue on the ramp (2 s headways in, 6 s out)
+
+
+def test_merge_priority_stream_blocks_the_ramp(synth):
+    """A dense priority stream leaves no gap of `dlag` upstream of the merge: ramp vehicles are refused and queue; without the stream
+    the same ramp flows freely.  Dense = followers less than (vx_am - w) / (-Kx w) apart (AbstractCarFollowing.cpp:529-585)."""
+    dense = _oracle(synth.ymerge(demand_main=0.75, demand_ramp=0.3, vit_reg=14.0, n_steps=400))
+    free = _oracle(synth.ymerge(demand_main=0.0, demand_ramp=0.3, vit_reg=14.0, n_steps=400))
+    for _ in range(300):
+        dense.step()
+        free.step()
+    assert free.counter(5) == 0
+    assert dense.counter(5) > 3 * dense.counter(4) > 0          # far more refusals than insertions
+    assert dense.n > free.n + 20                                   # the ramp queue
