@@ -33,7 +33,8 @@ enum { SYMGPU_CNT_TIES = 0,      /* equal-position leader candidates met (reseau
        SYMGPU_CNT_MRG_INS = 10,     /* merge points: insertions (PointDeConvergence::CalculInsertion accepted) */
        SYMGPU_CNT_MRG_REFUS = 11,   /* merge points: insertions refused (vehicle held at the end of its branch) */
        SYMGPU_CNT_MRG_SERIAL = 12,  /* merge points processed one by one because they shared a vehicle with another point */
-       SYMGPU_CNT_MRG_VALUES = 13   /* merge points whose decision consumed values of the random stream (congested branch) */ };
+       SYMGPU_CNT_MRG_VALUES = 13,  /* merge points whose decision consumed values of the random stream (congested branch) */
+       SYMGPU_CNT_MRG_DRAWS = 14    /* draws of the random stream made by the merge phase */ };
 
 /* Replaces Reseau::LoadReseauXML + InitSimuTrafic for an already flattened network (include/symflat.h). */
 int symgpu_create(const char* symflat_path, int device, symgpu_ctx** out);

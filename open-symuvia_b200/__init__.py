@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("SYMB200_LIB", os.path.join(_HERE, "libSymuViaB200.so"
 _LIB = None
 
 (CNT_TIES, CNT_LOOPS, CNT_CREATED, CNT_PASSES, CNT_LAUNCHES, CNT_SLOTS, CNT_CTX_OVERFLOW, CNT_LANE_CHANGES, CNT_LC_EVENTS, CNT_LC_REEVAL,
- CNT_MRG_INS, CNT_MRG_REFUS, CNT_MRG_SERIAL, CNT_MRG_VALUES) = range(14)
+ CNT_MRG_INS, CNT_MRG_REFUS, CNT_MRG_SERIAL, CNT_MRG_VALUES, CNT_MRG_DRAWS) = range(15)
 
 
 class SymGpuError(RuntimeError):

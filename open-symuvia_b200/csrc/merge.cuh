@@ -53,6 +53,8 @@ struct DevMrg {
   int* cand_up;                                                            // upstream lane -> first vehicle that crossed it entirely this step
   int *own_min, *own_max;                                                  // per vehicle slot: lowest / highest point that touches it
   int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw, *flist; double* proba;   // per point, this step; flist: the points the walk must visit (unordered)
+  int* res;                                                               // per point: 1 inserted, 2 refused this step (summed by k_mrg_apply)
+  unsigned long long *kf, *kfo; int *fsorted, *rbuf; int rbuf_cap;                       // kf: per point, draws known before the walk (low 40 bits) | visit flag (bit 40); kfo: its exclusive scan = offset in the stream | rank in the visit list
   int *nused, *nvoie;                                                      // per vehicle: intermediate lanes used this step; m_pNextVoie (sticky)
   double* mrgx;                                                            // per order position: phase A -> phase B side record (6 doubles)
   DevRng* rng; unsigned* draws;                                            // the stream (device copy) and the cumulative count of count-only draws
@@ -391,7 +393,7 @@ __device__ inline int vehicule_en_attente(const MrgView& W, int lane) {
   return -1;
 }
 
-struct MrgDraw { DevRng* rng; };   // serial mode: the positioned stream
+struct RngCursor { const int* buf; int pos; int cap; int overflow; };   // serial visits draw from the look-ahead values of k_mrg_walk
 
 // PointDeConvergence::CalculInsertion convergent.cpp:333-990 + AbstractCarFollowing::TestConvergentInsertion (:336-664).
 // mode MM_PROBE   : nothing written; A collects the vehicles the point reads at index 0 or writes, and the count-only draws
@@ -460,7 +462,9 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
   // ---- TestConvergentInsertion -----------------------------------------------------------------------------------------
   bool ins = false; double tr = 0, ta = 0; int rand_numbers = M.pt_rand[p];
   int drawn = 0;                                                                          // serial mode: count-only draws consumed from the stream so far
-  auto flush = [&]() { if (mode == MM_SERIAL) { for (; drawn < A.ndraw; drawn++) rng_next(rng); } };
+  RngCursor* cur = (RngCursor*)rng;                                                       // serial mode draws from the look-ahead values of k_mrg_walk
+  auto draw = [&]() { const int v = cur->pos < cur->cap ? cur->buf[cur->pos] : 0; if (cur->pos >= cur->cap) cur->overflow = 1; cur->pos++; return v; };
+  auto flush = [&]() { if (mode == MM_SERIAL) { for (; drawn < A.ndraw; drawn++) draw(); } };
   if (!free_flow) {                                                                                                         // :343-377
     const double q2g = M.cvg_gamma[c] * offre / (1 + M.cvg_gamma[c]);
     if (demande2 < q2g) { ins = true; rand_numbers = 0; }
@@ -469,8 +473,8 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
       if (probe) { M.pre[p] = A.ndraw; M.kmax[p] = rand_numbers; M.proba[p] = proba; return MS_VALUES; }   // decided by k_mrg_walk from the stream's values
       if (mode == MM_EVAL) return MS_OVERFLOW;                                                                              // unreachable: the probe saw the same state
       if (mode == MM_DECIDED) { const int d = M.decide[p]; ins = d >> 16; rand_numbers -= d & 0xffff; }
-      else { flush(); rng_next(rng);                                                                                       // one draw, unused; the loop bound is re-read after every decrement (:362-374)
-        for (int k = 0; k < rand_numbers; k++) { const double r = rng_next(rng) / 32767.0; rand_numbers--; if (r < proba) { ins = true; break; } } }
+      else { flush(); draw();                                                                                              // one draw, unused; the loop bound is re-read after every decrement (:362-374)
+        for (int k = 0; k < rand_numbers; k++) { const double r = draw() / 32767.0; rand_numbers--; if (r < proba) { ins = true; break; } } }
     }
   } else {
     rand_numbers = 0;                                                                                                       // :381
@@ -499,6 +503,7 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
       { const int w = vehicule_amont(W, A, TAmP, fmin(N.link_vreg[TAmP], M.vx0));
         if (w >= 0 && !(V.oflags[w] & O_LINK1NULL)) vit_am = fmin(P.cls[V.cls[w]].vx, N.link_vreg[N.lane_link[V.lane[w]]]);
         else vit_am = fmin(M.max_vit_max, N.link_vreg[TAmP]); }
+      if (probe) return MS_DONE;                                                                                            // every vehicle touched and every draw counted: the rest is arithmetic
       double dlag;
       if (demande1 <= q1mu) dlag = (-k.w + vit_am) / (-k.kx * k.w);
       else { const double eta = (demande1 - q1mu) / (1 / tmbar - q1mu); dlag = (-k.w + vit_am) / (-k.kx * k.w) * (1 - eta); }
@@ -519,7 +524,7 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
   if (probe) return MS_DONE;
   flush();                                                                                // count-only draws (values unused: every movement has one target lane)
   M.pt_rand[p] = rand_numbers; M.pt_free[p] = free_flow;
-  if (!ins) { immobilise(W, att, VAmNP, false); atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_REFUS], 1ULL); return MS_DONE; }   // :967-987
+  if (!ins) { immobilise(W, att, VAmNP, false); M.res[p] = 2; return MS_DONE; }   // :967-987
   int la[kMrgLanes]; const int nla = ctx_lanes_of(W, att, la);
   if (free_flow) {                                                                                                          // :656-836
     int L2 = -1; double pl = 0;
@@ -552,7 +557,7 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
           V.vit_n[fol] = (dfol + (P.dt - ta) * V.vit_n[fol]) / P.dt; set_acc_m(W, fol, (V.vit_n[fol] - V.vit[fol]) / P.dt);
         }
         M.pt_last[p] = W.inst - P.dt + tr;
-        atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_INS], 1ULL);
+        M.res[p] = 1;
         return MS_DONE;
       }
     }
@@ -572,7 +577,7 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
       trav += fmin(ep, llen) - sp; }
     V.vit_n[att] = d / P.dt; set_acc_m(W, att, (V.vit_n[att] - V.vit[att]) / P.dt); }
   M.pt_last[p] = W.inst - P.dt;
-  atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_INS], 1ULL);
+  M.res[p] = 1;
   if (fol >= 0) {                                                                                                           // :908-958
     const double pos = mlink1(W, fol) == TAmP ? N.lane_len[VAmP] - mpos1(W, fol) : N.lane_len[VAmP] + N.lane_len[V.lane[fol]] - mpos1(W, fol);
     int lf[kMrgLanes]; const int nlf = ctx_lanes_of(W, fol, lf);
@@ -586,6 +591,11 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
   return MS_DONE;
 }
 
+// out of line: the ordered visit of k_mrg_walk is a tight loop that must not inherit this function's register pressure
+__device__ __noinline__ void merge_point_serial(const MrgView* W, int q, RngCursor* C) {
+  MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
+  merge_point(*W, q, MM_SERIAL, A, (DevRng*)C);
+}
 // ---- kernels ----------------------------------------------------------------------------------------------------------------
 // CarrefourAFeuxEx::UpdateConvergents CarrefourAFeuxEx.cpp:1386-1593.  pt_mode: 0 = re-ranked from the colours, 1 = single upstream
 // lane (level 1), 2 = left at the reference levels (no controller, or behind the `break` of :1428-1436).
@@ -617,7 +627,7 @@ __global__ void k_mrg_probe(DevNet N, DevVeh V, DevMrg M, const int* order, cons
   MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
   int st = merge_point(W, p, MM_PROBE, A, nullptr);
   if (A.overflow) st = MS_OVERFLOW;
-  M.st[p] = st; M.ninv[p] = A.ninv; M.ndraw[p] = 0;
+  M.st[p] = st; M.ninv[p] = A.ninv; M.ndraw[p] = 0; M.kf[p] = st == MS_VALUES ? (unsigned long long)(A.ndraw + 1) : 0ULL;
   for (int k = 0; k < A.ninv; k++) { M.inv[p * kMrgInv + k] = A.inv[k]; atomicMin(&M.own_min[A.inv[k]], p); atomicMax(&M.own_max[A.inv[k]], p); }
 }
 __global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
@@ -629,127 +639,217 @@ __global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const
   if (st == MS_NONE) return;
   bool clean = st != MS_OVERFLOW;
   for (int k = 0; k < M.ninv[p] && clean; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p) clean = false; }
-  if (!clean) { M.st[p] = MS_DIRTY; M.flist[atomicAdd(n_flag, 1)] = p; return; }
-  if (st == MS_VALUES) { M.flist[atomicAdd(n_flag, 1)] = p; return; }                      // decided by the walk, applied by k_mrg_apply
+  if (!clean) { M.st[p] = MS_DIRTY; M.kf[p] = 1ULL << 40; return; }                         // visited by the walk, draws unknown until then
+  if (st == MS_VALUES) { M.kf[p] |= 1ULL << 40; return; }                      // decided by the walk, applied by k_mrg_apply
   const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
   MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
   st = merge_point(W, p, MM_EVAL, A, nullptr);
-  M.st[p] = st; M.ndraw[p] = A.ndraw;
-  if (A.ndraw) M.flist[atomicAdd(n_flag, 1)] = p;
+  M.st[p] = st; M.ndraw[p] = A.ndraw; M.kf[p] = (unsigned long long)A.ndraw;                                // count-only draws: an offset for the points after this one, nothing to visit
 }
-// advance the stream by `n` accepted draws (RandManager::myRand = mt19937 + bucket rejection), one block of 256 threads
-__device__ inline void rng_skip_block(DevRng* r, unsigned n, unsigned* sh_new, int* sh_rej) {
-  const int tid = threadIdx.x; const int B = blockDim.x;
-  unsigned left = n;
+// ---- the random stream on the device -----------------------------------------------------------------------------------------
+// RandManager::myRand = boost::mt19937 + uniform_int<>(0, 0x7FFE) by bucket rejection (RandManager.cpp:26-30).  One block of 256 threads
+// advances a state held in shared memory: a twist of the 624 words has four dependency phases (words 0..226 only need old words,
+// 227..453 need the new 0..226, 454..622 the new 227..453, word 623 the new 0 and 396); the tempered outputs of a block of words are
+// produced in parallel and a rejected value (4 in 2^32) sends that block through a serial compaction.
+struct MtShared { unsigned mt[624]; unsigned nw[624]; int idx; unsigned count; };
+__device__ inline void mt_twist(MtShared& S) {
+  const int tid = threadIdx.x;
+  auto f = [&](const unsigned* lo, const unsigned* hi, const unsigned* far) { const unsigned y = (*lo & 0x80000000u) | (*hi & 0x7fffffffu); return *far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); };
+  if (tid < 227) S.nw[tid] = f(&S.mt[tid], &S.mt[tid + 1], &S.mt[tid + 397]);
+  __syncthreads();
+  if (tid < 227) S.nw[227 + tid] = f(&S.mt[227 + tid], &S.mt[228 + tid], &S.nw[tid]);
+  __syncthreads();
+  if (tid < 169) S.nw[454 + tid] = f(&S.mt[454 + tid], &S.mt[455 + tid], &S.nw[227 + tid]);
+  __syncthreads();
+  if (tid == 0) S.nw[623] = f(&S.mt[623], &S.nw[0], &S.nw[396]);
+  __syncthreads();
+  for (int i = tid; i < 624; i += blockDim.x) S.mt[i] = S.nw[i];
+  __syncthreads();
+}
+// consume `n` accepted draws; out != nullptr: their values are stored (out[0..n))
+__device__ inline void rng_advance(MtShared& S, unsigned n, int* out) {
+  const int tid = threadIdx.x; const unsigned bucket = 0xFFFFFFFFu / 32767u;
+  unsigned left = n, written = 0; int idx = S.idx;                        // uniform over the block
   while (left > 0) {
-    __syncthreads();
-    if (r->idx >= 624) {                                                                   // twist, four dependency phases
-      for (int ph = 0; ph < 4; ph++) {
-        const int a = ph == 0 ? 0 : ph == 1 ? 227 : ph == 2 ? 454 : 623, b = ph == 0 ? 227 : ph == 1 ? 454 : ph == 2 ? 623 : 624;
-        for (int i = a + tid; i < b; i += B) { const unsigned y = (r->mt[i] & 0x80000000u) | (r->mt[(i + 1) % 624] & 0x7fffffffu);
-          sh_new[i] = r->mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
-        __syncthreads();
-        for (int i = a + tid; i < b; i += B) r->mt[i] = sh_new[i];
-        __syncthreads();
-      }
-      if (tid == 0) r->idx = 0;
-      __syncthreads();
-    }
-    const int idx = r->idx; const unsigned m = min(left, (unsigned)(624 - idx));
-    if (tid == 0) *sh_rej = 0;
-    __syncthreads();
-    int rej = 0;
-    for (unsigned k = tid; k < m; k += B) { unsigned y = r->mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-      if (y / (0xFFFFFFFFu / 32767u) > 32766u) rej++; }
-    if (rej) atomicAdd(sh_rej, rej);
-    __syncthreads();
-    left -= m - (unsigned)*sh_rej;
-    __syncthreads();
-    if (tid == 0) { r->idx = idx + (int)m; }
+    if (idx >= 624) { mt_twist(S); idx = 0; }
+    const unsigned m = min(left, (unsigned)(624 - idx));
+    int rej = 0; unsigned vals[3]; int nv = 0;
+    for (unsigned k = tid; k < m; k += blockDim.x) { unsigned y = S.mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+      const unsigned v = y / bucket; vals[nv++] = v; if (v > 32766u) rej++; }
+    const int nrej = __syncthreads_count(rej);
+    if (nrej == 0) { if (out) { int q = 0; for (unsigned k = tid; k < m; k += blockDim.x) out[written + k] = (int)vals[q++]; } written += m; left -= m; }
+    else { if (out && tid == 0) { unsigned w = written; for (unsigned k = 0; k < m; k++) { unsigned y = S.mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+          const unsigned v = y / bucket; if (v <= 32766u) out[w++] = (int)v; } }
+      written += m - nrej; left -= m - nrej; }
+    idx += (int)m;
   }
   __syncthreads();
-  if (tid == 0) r->count += n;
+  if (tid == 0) { S.idx = idx; S.count += n; }
   __syncthreads();
 }
-__global__ void k_rng_skip(DevRng* r, const int* n_ptr, int n_imm) {
-  __shared__ unsigned sh_new[624]; __shared__ int sh_rej;
+__device__ inline void mt_load(MtShared& S, const DevRng* r) { for (int k = threadIdx.x; k < 624; k += blockDim.x) S.mt[k] = r->mt[k]; if (threadIdx.x == 0) { S.idx = r->idx; S.count = r->count; } __syncthreads(); }
+__device__ inline void mt_store(const MtShared& S, DevRng* r) { __syncthreads(); for (int k = threadIdx.x; k < 624; k += blockDim.x) r->mt[k] = S.mt[k]; if (threadIdx.x == 0) { r->idx = S.idx; r->count = S.count; } }
+__global__ void __launch_bounds__(256) k_rng_skip(DevRng* r, const int* n_ptr, int n_imm) {
+  __shared__ MtShared S;
   const unsigned n = n_ptr ? (unsigned)*n_ptr : (unsigned)n_imm;
-  rng_skip_block(r, n, sh_new, &sh_rej);
+  if (n == 0) return;
+  mt_load(S, r); rng_advance(S, n, nullptr); mt_store(S, r);
 }
-// networks without merge points: the count-only draws of the step's car-following phase (next-lane memos) still advance the stream
-__global__ void k_rng_ctx(DevRng* r, const unsigned* draws, unsigned* seen, const int* guard) {
-  __shared__ unsigned sh_new[624]; __shared__ int sh_rej;
+// the count-only draws of the step's car-following phase (next-lane memos, counted in *draws) advance the stream before the merge points draw
+__global__ void __launch_bounds__(256) k_rng_ctx(DevRng* r, const unsigned* draws, unsigned* seen, const int* guard) {
+  __shared__ MtShared S;
   if (guard && *guard == 0) return;
   const unsigned now = *draws; const unsigned n = now - *seen;
-  rng_skip_block(r, n, sh_new, &sh_rej);
+  if (n) { mt_load(S, r); rng_advance(S, n, nullptr); mt_store(S, r); }
   if (threadIdx.x == 0) *seen = now;
 }
-// The points in Liste_convergents order: stream offsets, the draws that need values, the points that share vehicles.
-// `ctx_draws` - `*seen` = count-only draws of this step's car-following phase (next-lane memos), which precede the merge phase
-// in the stream.  out[0] = draws consumed by the merge phase.
+// exclusive scan of 64-bit words (block scan, scan of the block sums, add): the packed (draw count | visit flag) of every point
+typedef unsigned long long u64;
+__global__ void __launch_bounds__(1024) k_scan64_block(const u64* in, u64* out, u64* bsum, int n) {
+  __shared__ u64 wsum[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x; const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u64 v = i < n ? in[i] : 0ULL; u64 incl = v;
+  for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) wsum[w] = incl;
+  __syncthreads();
+  if (w == 0) { u64 s2 = wsum[lane]; for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, s2, o); if (lane >= o) s2 += t; } wsum[lane] = s2; }
+  __syncthreads();
+  const u64 off = w ? wsum[w - 1] : 0ULL;
+  if (i < n) out[i] = off + incl - v;
+  if (threadIdx.x == 1023) bsum[blockIdx.x] = off + incl;
+}
+__global__ void k_scan64_sums(u64* bsum, int nb) { if (threadIdx.x || blockIdx.x) return; u64 c = 0; for (int b = 0; b < nb; b++) { const u64 t = bsum[b]; bsum[b] = c; c += t; } bsum[nb] = c; }
+__global__ void k_scan64_add(u64* out, const u64* bsum, int n) { const int i = blockIdx.x * 1024 + threadIdx.x; if (i < n) out[i] += bsum[blockIdx.x]; }
+// the visit list in point order: rank = flag part of the scan
+__global__ void k_mrg_list(DevMrg M) { const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p < M.n_pt && ((M.kf[p] >> 40) & 1)) M.fsorted[(int)(M.kfo[p] >> 40)] = p; }
+// The points that need the stream's VALUES (congested test) or share a vehicle with another point, in Liste_convergents order.  Every
+// other point's draws are count-only and already summed (koff = exclusive scan of `known` in point order); the values the visited
+// points may consume are generated ahead into rbuf, the visit itself is one thread over shared-memory records, and the stream is then
+// advanced by what was really consumed.  out[0] = draws of the merge phase.
 __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start,
-                                                  const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const int* n_flag,
-                                                  unsigned* seen, int* out, const int* guard) {
-  constexpr int kList = 2048;
-  __shared__ unsigned sh_new[624]; __shared__ int sh_rej; __shared__ int sh_list[kList]; __shared__ int sh_sorted[kList]; __shared__ DevRng srng;
+                                                  const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const u64* kf_total,
+                                                  int* out, const int* guard) {
+  constexpr int kBatch = 512, kRc = 6144;
+  __shared__ int sh_rb[kRc];                                                               // the look-ahead values, when they fit: thread 0 reads them one by one
+  __shared__ MtShared S; __shared__ int e_pt[kBatch], e_off[kBatch], e_pre[kBatch], e_kmax[kBatch], e_thr[kBatch], e_used[kBatch], e_scan[kBatch]; __shared__ unsigned char e_st[kBatch], e_ins[kBatch];
+  __shared__ int sh_next, sh_flag;
+  __shared__ int sh_red[8]; __shared__ int sh_total;
   if (guard && *guard == 0) return;
   const int tid = threadIdx.x;
-  for (int k = tid; k < 624; k += 256) srng.mt[k] = M.rng->mt[k];                          // the stream works in shared memory and goes back at the end
-  if (tid == 0) { srng.idx = M.rng->idx; srng.count = M.rng->count; }
+#ifdef SYM_WALK_TIMING
+  long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0;
+#endif
+  const u64 tot = *kf_total; const int nf = (int)(tot >> 40); const int known_total = (int)(tot & ((1ULL << 40) - 1));
+  if (nf == 0) {                                                                           // only count-only draws this step
+    if (known_total) { mt_load(S, M.rng); rng_advance(S, (unsigned)known_total, nullptr); mt_store(S, M.rng); }
+    if (tid == 0) { out[0] = known_total; M.counters[SYMGPU_CNT_MRG_DRAWS] += known_total; }
+    return;
+  }
+  // upper bound of the values the visited points may consume
+  int ub = 0;
+  for (int k = tid; k < nf; k += 256) { const int q = M.fsorted[k]; ub += M.st[q] == MS_VALUES ? M.kmax[q] : 256; }
+  for (int o = 16; o; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
+  if ((tid & 31) == 0) sh_red[tid >> 5] = ub;
   __syncthreads();
-  const unsigned now = *M.draws; const unsigned pre = now - *seen;
-  rng_skip_block(&srng, pre, sh_new, &sh_rej);
-  const int nf = *n_flag;
-  int total = 0;
-  if (nf > 0) {
-    const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
-    auto visit = [&](int q) {
-      const int st = M.st[q];
-      if (st == MS_DIRTY) { MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; const unsigned c0 = srng.count;
-        merge_point(W, q, MM_SERIAL, A, &srng); total += (int)(srng.count - c0); M.st[q] = MS_DONE; M.counters[SYMGPU_CNT_MRG_SERIAL]++; }
-      else if (st == MS_VALUES) {
-        for (int d = 0; d < M.pre[q]; d++) rng_next(&srng);
-        rng_next(&srng); int used = 0; bool ins = false; const double proba = M.proba[q];
-        int rn = M.kmax[q];
-        for (int d = 0; d < rn; d++) { const double r = rng_next(&srng) / 32767.0; rn--; used++; if (r < proba) { ins = true; break; } }
-        M.decide[q] = ((int)ins << 16) | used; total += M.pre[q] + 1 + used; M.counters[SYMGPU_CNT_MRG_VALUES]++; }
-      else { for (int d = 0; d < M.ndraw[q]; d++) rng_next(&srng); total += M.ndraw[q]; }
-    };
-    if (nf <= kList) {                                                                     // the usual case: a short list, ordered by a rank sort in shared memory
-      for (int k = tid; k < nf; k += 256) sh_list[k] = M.flist[k];
+  if (tid == 0) { int t = 0; for (int w = 0; w < 8; w++) t += sh_red[w]; sh_total = t; }
+  __syncthreads();
+#ifdef SYM_WALK_TIMING
+  tq1 = clock64();
+#endif
+  int U = known_total + sh_total; int overflow = 0;
+  if (U > M.rbuf_cap) { U = M.rbuf_cap; overflow = 1; }
+  mt_load(S, M.rng);
+  rng_advance(S, (unsigned)U, M.rbuf);                                                     // look-ahead values (the state S is discarded afterwards)
+  __threadfence_block(); __syncthreads();
+  const int* vals = M.rbuf;
+  if (U <= kRc) { for (int k = tid; k < U; k += 256) sh_rb[k] = M.rbuf[k]; vals = sh_rb; __syncthreads(); }
+  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+#ifdef SYM_WALK_TIMING
+  tq2 = clock64();
+#endif
+  int extra = 0;                                                                           // draws consumed by the visited points beyond `known`
+  int n_values = 0, n_serial = 0;
+  for (int b0 = 0; b0 < nf; b0 += kBatch) {
+    const int nb = min(kBatch, nf - b0);
+    __syncthreads();
+    for (int k = tid; k < nb; k += 256) { const int q = M.fsorted[b0 + k]; e_pt[k] = q; e_off[k] = (int)(M.kfo[q] & ((1ULL << 40) - 1)); e_pre[k] = M.pre[q]; e_kmax[k] = M.kmax[q]; e_st[k] = (unsigned char)M.st[q];
+      // the test `draw / 32767.0 < proba` as an integer threshold (exactly: the quotient is monotonic in the draw), so that the ordered visit is integer work
+      const double pr = M.proba[q]; int T = (int)fmin(fmax(ceil(pr * 32767.0), 0.0), 32767.0); if (!(pr == pr)) T = 0;
+      while (T <= 32766 && (T / 32767.0 < pr)) T++; while (T > 0 && !((T - 1) / 32767.0 < pr)) T--;
+      e_thr[k] = T; }
+    __syncthreads();
+    // Ordered visit without a serial loop.  A VALUES entry consumes `used` draws: tests go on while k < m_nRandNumbers, which is
+    // decremented per test, i.e. at most lim = ceil(n / 2) of them, fewer when one succeeds (AbstractCarFollowing.cpp:362-374).  Where an
+    // entry's draws start depends on what the entries before it consumed, so: assume used = lim everywhere, prefix-sum, let every
+    // entry test its draws in parallel, repeat while an assumption was wrong.  Entries before the first wrong one are final, so every
+    // round fixes at least one more; a round that changes nothing is the sequential result.
+    int k0 = 0;
+    while (k0 < nb) {
+      if (tid == 0) sh_next = nb;
       __syncthreads();
-      for (int k = tid; k < nf; k += 256) { const int v = sh_list[k]; int r = 0; for (int j = 0; j < nf; j++) r += sh_list[j] < v; sh_sorted[r] = v; }
+      for (int k = k0 + tid; k < nb; k += 256) if (e_st[k] != MS_VALUES) atomicMin(&sh_next, k);
       __syncthreads();
-      if (tid == 0) for (int k = 0; k < nf; k++) visit(sh_sorted[k]);
-    } else {                                                                               // many: scan the points 256 at a time
-      __shared__ int wbase[8]; __shared__ int sh_n;
-      for (int base = 0; base < M.n_pt; base += 256) {
+      const int k1 = sh_next; const int ns = k1 - k0;
+      for (int k = k0 + tid; k < k1; k += 256) e_used[k] = (e_kmax[k] + 1) >> 1;
+      for (;;) {
         __syncthreads();
-        const int p = base + tid; bool f = false;
-        if (p < M.n_pt) { const int st = M.st[p]; f = st == MS_VALUES || st == MS_DIRTY || M.ndraw[p] > 0; }
-        const unsigned m = __ballot_sync(0xffffffffu, f);
-        if ((tid & 31) == 0) wbase[tid >> 5] = __popc(m);
+        { const int i0 = k0 + 2 * tid, i1 = i0 + 1; const int a = i0 < k1 ? e_used[i0] : 0, b2 = i1 < k1 ? e_used[i1] : 0; int incl = a + b2;   // exclusive scan of e_used over [k0, k1)
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+          if ((tid & 31) == 31) sh_red[tid >> 5] = incl;
+          if (tid == 0) sh_flag = 0;
+          __syncthreads();
+          int off = 0; for (int w = 0; w < (tid >> 5); w++) off += sh_red[w];
+          const int ex = off + incl - (a + b2);
+          if (i0 < k1) e_scan[i0] = ex; if (i1 < k1) e_scan[i1] = ex + a; }
         __syncthreads();
-        if (tid == 0) { int s2 = 0; for (int w = 0; w < 8; w++) { int t = wbase[w]; wbase[w] = s2; s2 += t; } sh_n = s2; }
+        for (int k = k0 + tid; k < k1; k += 256) { const int start = e_off[k] + extra + e_scan[k] + e_pre[k] + 1; const int lim = (e_kmax[k] + 1) >> 1; const int thr = e_thr[k];
+          int u = lim; bool ins = false;
+          for (int d = 0; d < lim; d++) { const int pos = start + d; if ((pos < U ? vals[pos] : 32767) < thr) { u = d + 1; ins = true; break; } }
+          e_ins[k] = ins; if (u != e_used[k]) { e_used[k] = u; sh_flag = 1; } }
         __syncthreads();
-        if (f) sh_list[wbase[tid >> 5] + __popc(m & ((1u << (tid & 31)) - 1))] = p;
-        __syncthreads();
-        if (tid == 0) for (int k = 0; k < sh_n; k++) visit(sh_list[k]);
+        if (!sh_flag) break;
       }
+      for (int k = k0 + tid; k < k1; k += 256) M.decide[e_pt[k]] = ((int)e_ins[k] << 16) | e_used[k];
+      if (ns > 0) extra += e_scan[k1 - 1] + e_used[k1 - 1];
+      n_values += ns;
+      if (k1 < nb) {                                                                         // an entry that shares a vehicle with another point: literally, now
+        if (tid == 0) { const int q = e_pt[k1]; RngCursor C{vals, e_off[k1] + extra, U, 0};
+          merge_point_serial(&W, q, &C);
+          sh_red[0] = C.pos - (e_off[k1] + extra); sh_red[1] = C.overflow; M.st[q] = MS_DONE; }
+        __syncthreads();
+        extra += sh_red[0]; overflow |= sh_red[1]; n_serial++;
+        __syncthreads();
+      }
+      k0 = k1 + 1;
     }
   }
   __syncthreads();
-  for (int k = tid; k < 624; k += 256) M.rng->mt[k] = srng.mt[k];
-  if (tid == 0) { M.rng->idx = srng.idx; M.rng->count = srng.count; *seen = now; out[0] = total; }
+  if (tid == 0) { sh_total = known_total + extra; M.counters[SYMGPU_CNT_MRG_VALUES] += n_values; M.counters[SYMGPU_CNT_MRG_SERIAL] += n_serial; if (overflow) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL); }
+  __syncthreads();
+#ifdef SYM_WALK_TIMING
+  tq3 = clock64();
+#endif
+  const int total = sh_total;
+  mt_load(S, M.rng); rng_advance(S, (unsigned)total, nullptr); mt_store(S, M.rng);         // the stream itself advances by what was consumed
+#ifdef SYM_WALK_TIMING
+  if (tid == 0) printf("walk nf %d U %d known %d extra %d | sort+ub %lld gen %lld loop %lld final %lld cycles\n", nf, U, known_total, extra, tq1 - tq0, tq2 - tq1, tq3 - tq2, clock64() - tq3);
+#endif
+  if (tid == 0) { out[0] = total; M.counters[SYMGPU_CNT_MRG_DRAWS] += total; }
 }
 __global__ void k_mrg_apply(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
                             const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
   if (guard && *guard == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= M.n_pt) return;
-  if (M.st[p] == MS_VALUES) { const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
-    MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; merge_point(W, p, MM_DECIDED, A, nullptr); }
-  for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; M.own_min[x] = INT_MAX; M.own_max[x] = -1; }   // marks back to idle for the next step
+  int res = 0;
+  if (p < M.n_pt) {
+    if (M.st[p] == MS_VALUES) { const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+      MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; merge_point(W, p, MM_DECIDED, A, nullptr); }
+    for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; M.own_min[x] = INT_MAX; M.own_max[x] = -1; }   // marks back to idle for the next step
+    res = M.res[p]; M.res[p] = 0;
+  }
+  const unsigned mi = __ballot_sync(0xffffffffu, res == 1), mr = __ballot_sync(0xffffffffu, res == 2);     // statistics: one atomic per warp
+  if ((threadIdx.x & 31) == 0) { if (mi) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_INS], (unsigned long long)__popc(mi));
+    if (mr) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_REFUS], (unsigned long long)__popc(mr)); }
 }
 // Reseau::UpdateConvergents reseau.cpp:2432-2600 (integer counts) after SensorsManager::UpdateTabNbVeh (:462-527): the slot the
 // rotation exposes is cleared first (k_mrg_rotate), then every vehicle left on the network counts where it crossed a sensor.

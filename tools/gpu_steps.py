@@ -12,4 +12,4 @@ t0 = time.time()
 for k in range(steps):
     g.step()
 print("vehicles", g.n, "steps", steps, "last_step_ms", g.last_step_ms, "wall", time.time() - t0,
-      {k: g.counter(getattr(pkg, k)) for k in ("CNT_MRG_INS", "CNT_MRG_REFUS", "CNT_MRG_SERIAL", "CNT_MRG_VALUES", "CNT_PASSES", "CNT_LOOPS", "CNT_TIES")}, "rng", g.rng_count)
+      {k: g.counter(getattr(pkg, k)) for k in ("CNT_MRG_INS", "CNT_MRG_REFUS", "CNT_MRG_SERIAL", "CNT_MRG_VALUES", "CNT_MRG_DRAWS", "CNT_PASSES", "CNT_LOOPS", "CNT_TIES")}, "rng", g.rng_count)
