@@ -28,12 +28,14 @@ sys.path.insert(0, ROOT)
 B_ALG = 128.0   # algorithmic bytes per vehicle-step
 
 
-def make_workload(name: str, rank: int, world: int, path: str):
-    """C4 tile per GPU: world GPUs simulate ONE (100*world) x 100 grid (~1M vehicles per GPU, C5-style strips); the file
-    holds the whole network and the vehicles of strip `rank` (global ids).  Generated by csrc/gen_grid.cpp."""
+def make_workload(name: str, rank: int, world: int, path: str, partitioned: bool = False):
+    """C4: the 100x100 signalised grid with its merge points (csrc/gen_grid.cpp), ~1M pre-seeded vehicles.  N GPUs: one such network per
+    GPU (replicas: the merge points' random draws are ordered over the whole network, so a network with merges is not partitioned yet).
+    `partitioned` (merge-free networks only): ONE (100*world) x 100 grid cut into strips, the file holds the whole network and the
+    vehicles of strip `rank` (global ids); boundary tails and migrating vehicles are exchanged every step (NCCL)."""
     synth = importlib.import_module("open-symuvia_b200.synth")
     if name == "C5":        # BASELINE configs[4]: ONE 300x300 grid, ~10M vehicles, cut into `world` vertical strips (strong scaling)
-        n_own, n_tot = synth.fast_grid(path, 300, 300, per_lane=14.0, seed=42, route_len=24, n_steps=100, rank=rank, world=world)
+        n_own, n_tot = synth.fast_grid(path, 300, 300, per_lane=14.0, seed=42, route_len=24, n_steps=100, rank=rank, world=world, merges=(world == 1))
         info = dict(n_init=n_own, n_total=n_tot, n_classes=1)
         hdr = flat_section_counts(path)
         info["n_links"] = hdr["link_i"] // 8
@@ -42,7 +44,10 @@ def make_workload(name: str, rank: int, world: int, path: str):
     tile = {"C4": 100, "C4small": 20}.get(name)
     if tile is None:
         raise SystemExit(f"unknown workload {name}")
-    n_own, n_tot = synth.fast_grid(path, tile * world, tile, per_lane=12.6, seed=42, route_len=24, n_steps=300, rank=rank, world=world)
+    if partitioned and world > 1:
+        n_own, n_tot = synth.fast_grid(path, tile * world, tile, per_lane=12.6, seed=42, route_len=24, n_steps=300, rank=rank, world=world, merges=False)
+    else:
+        n_own, n_tot = synth.fast_grid(path, tile, tile, per_lane=12.6, seed=42 + rank, route_len=24, n_steps=300, rank=0, world=1, merges=True)
     info = dict(n_init=n_own, n_total=n_tot, n_classes=1)
     hdr = flat_section_counts(path)
     info["n_links"] = hdr["link_i"] // 8
@@ -132,6 +137,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--cpu-steps", type=int, default=10, help="oracle steps for cpu_baseline (bounded sample)")
+    ap.add_argument("--partitioned", action="store_true", help="N > 1: one merge-free network cut into N strips with NCCL exchange instead of N replicas")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,9 +174,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # N > 1: ONE network (same file on every rank) cut into N vertical strips; every rank owns the vehicles of its strip
-    info = make_workload(a.workload, rank, world, path)
+    partitioned = world > 1 and (a.partitioned or a.workload == "C5")
+    info = make_workload(a.workload, rank, world, path, partitioned)
     run = None
-    if world > 1:
+    if partitioned:
         part_mod = importlib.import_module("open-symuvia_b200.partition")
         flat = importlib.import_module("open-symuvia_b200.flat")
         node_xy = flat.read(path)["node_xy"]
@@ -302,8 +309,11 @@ def main():
     line = {"metric": "vehicle-steps/sec", "value": value, "unit": "vehicle-steps/s", "n_gpus": world, "steps": a.steps, "warmup": warm,
             "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True, "scaling": ("strong" if a.workload == "C5" else "weak"), "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": dict(base_cfg, parallelism=("1 GPU" if world == 1 else (f"one {100 * world}x100 grid cut into {world} vertical strips of 100x100 junctions" if a.workload != "C5" else f"the 300x300 grid cut into {world} vertical strips") +
-                                                      ", one per GPU; per step: all_to_all of boundary-lane tails + one fixed-size all_to_all of migrating vehicles (NCCL)"),
+            "config": dict(base_cfg, parallelism=("1 GPU" if world == 1 else
+                                                  f"{world} replicas, one C4 network (with merge points) per GPU, different seeds, no data-path collective (merge points are not partitioned yet: DESIGN.md section 8)" if not partitioned else
+                                                  (f"one MERGE-FREE {100 * world}x100 grid cut into {world} vertical strips of 100x100 junctions" if a.workload != "C5" else f"the merge-free 300x300 grid cut into {world} vertical strips") +
+                                                  ", one per GPU; per step: all_to_all of boundary-lane tails + one fixed-size all_to_all of migrating vehicles (NCCL)"),
+                           merge_points=not partitioned,
                            vehicles_per_gpu=info["n_init"], lanes_per_gpu=info["n_lanes"]),
             "e2e": {"value": e2e, "unit": "vehicle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(rows) * 32,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps, "d2h_copy_ms_per_step": copy_ms / max(1, e2e_steps),

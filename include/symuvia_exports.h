@@ -13,7 +13,7 @@ extern "C" {
 /* Symubruit.cpp:4241-4264 — load, run every step, unload. 0 = ok, 1 = load failure. */
 int SymRunEx(char* sFile);
 /* Symubruit.cpp:4266-4269 — returns the bool load result as int (1 ok, 0 failure). Accepts the reference's
- * ROOT_SYMUBRUIT XML (subset) or an already flattened *.symflat file. */
+ * ROOT_SYMUBRUIT XML (the subset read by csrc/xmlnet.h, listed in INTEGRATION.md) or an already flattened *.symflat file. */
 int SymLoadNetworkEx(char* sFile);
 /* Symubruit.cpp:4271-4274 */
 void SymUnloadCurrentNetworkEx(void);
@@ -28,6 +28,8 @@ bool SymRunNextStepLiteEx(bool bTrace, bool* bNEnd);
 int SymCreateVehicleEx(char* sType, char* sOrigin, char* sDestination, int nLane, double dbt);
 /* Symubruit.cpp:2303 — releases strings returned by the library. */
 void SymRunDeleteStr(char* str);
+/* Not a SymuVia export: flattens a ROOT_SYMUBRUIT document into a SYMFLAT1 file (host only, no CUDA). 0 = ok. */
+int symflat_from_xml(const char* xml_path, const char* out_symflat_path);
 
 #ifdef __cplusplus
 }

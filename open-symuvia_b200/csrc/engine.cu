@@ -31,6 +31,7 @@
 #include "engine_internal.h"
 #include "flatnet.h"
 #include "micro.cuh"
+#include "xmlnet.h"
 
 using namespace symb200;
 
@@ -526,6 +527,7 @@ struct symgpu_ctx {
         node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, nused, nvoie, row_sens, flag, out;
     DBuf<double> cvg_gamma, cvg_mu, cvg_poscpt, cvg_tf, sens_pos, pt_last, proba, mrgx; DBuf<unsigned> seen; DBuf<unsigned long long> kf, kfo, kbsum; } mg;
   bool host_rng_fresh = true;                                      // the host copy of the random stream equals the device's
+  std::vector<signed char> cls_of_id;                               // vehicle type by vehicle id (output writers)
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
   struct ApiVeh { int id, cls, entry, dest, lane; double dbt; };
   std::vector<ApiVeh> api_queue;                                   // Reseau::m_VehiclesToCreate (reseau.cpp:2233-2240)
@@ -607,6 +609,8 @@ static int build_merge(symgpu_ctx* c);
 static double max_debit_max(const symgpu_ctx* c);
 extern "C" const char* symgpu_last_error(void) { return g_err.c_str(); }
 const symb200::FlatNet& symgpu_internal_net(symgpu_ctx* c) { return c->net; }
+int symgpu_internal_class_of(symgpu_ctx* c, int id) { return id >= 0 && id < (int)c->cls_of_id.size() ? c->cls_of_id[id] : -1; }
+static void note_class(symgpu_ctx* c, int id, int cls) { if (id < 0) return; if (id >= (int)c->cls_of_id.size()) c->cls_of_id.resize(std::max<size_t>((size_t)id + 1, c->cls_of_id.size() * 2), -1); c->cls_of_id[id] = (signed char)cls; }
 int symgpu_internal_create_vehicle(symgpu_ctx* c, int cls, int entry, int dest, int lane, double dbt) {
   int id = c->last_id++;                                             // IncLastIdVeh at request time
   c->api_queue.push_back({id, cls, entry, dest, lane, dbt});
@@ -620,7 +624,9 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { g_err = "no usable CUDA device (this library has no CPU path)"; return SYMGPU_E_NODEVICE; }
   CK(cudaSetDevice(device));
   auto c = new symgpu_ctx(); c->device = device;
-  if (!c->net.load(path)) { g_err = c->net.error; delete c; return SYMGPU_E_LOAD; }
+  { const size_t pl = strlen(path); const bool flat = pl > 8 && !strcmp(path + pl - 8, ".symflat");
+    // anything else is read as a ROOT_SYMUBRUIT document (xmlnet.h: the subset of SURVEY.md Appendix B) and flattened in memory
+    if (flat ? !c->net.load(path) : !flat_from_xml(path, c->net, c->net.error)) { g_err = c->net.error; delete c; return SYMGPU_E_LOAD; } }
   FlatNet& f = c->net;
   const int T = f.n_cls(), L = f.n_lanes(), K = f.n_links();
   if (T > kMaxCls) { g_err = "too many vehicle classes"; delete c; return SYMGPU_E_UNSUPPORTED; }
@@ -720,7 +726,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   // initial vehicles (reseau.cpp:1293-1340): already on the network, state at index 0
   { std::vector<HostRow> rows(f.n_init());
     for (int v = 0; v < f.n_init(); v++) { HostRow& r = rows[v]; r.status = ST_ALIVE; r.id = f.iv_id.empty() ? c->last_id++ : f.iv_id[v]; if (!f.iv_id.empty()) c->last_id = std::max(c->last_id, r.id + 1); r.cls = f.iv_i[4 * v]; r.lane = f.iv_i[4 * v + 1];
-      r.route = f.iv_i[4 * v + 2]; r.rpos = f.iv_i[4 * v + 3]; r.pos = f.iv_f[3 * v]; r.vit = f.iv_f[3 * v + 1]; r.acc = f.iv_f[3 * v + 2]; r.tcre = 0; r.hent = 0; }
+      r.route = f.iv_i[4 * v + 2]; r.rpos = f.iv_i[4 * v + 3]; r.pos = f.iv_f[3 * v]; r.vit = f.iv_f[3 * v + 1]; r.acc = f.iv_f[3 * v + 2]; r.tcre = 0; r.hent = 0; note_class(c, r.id, r.cls); }
     int rc = upload_rows(c, 0, rows); if (rc != SYMGPU_OK) { delete c; return rc; }
     c->n_slots = c->n_alive = f.n_init(); }
   *out = c;
@@ -910,7 +916,7 @@ static void create_api_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, s
     EntryLane& el = e.lanes[nv];
     if (!owns_lane(c, el.lane)) continue;
     c->created++;
-    HostVeh hv{a.id, a.cls, route, el.lane, a.dbt, inst - dt + a.dbt};
+    HostVeh hv{a.id, a.cls, route, el.lane, a.dbt, inst - dt + a.dbt}; note_class(c, a.id, a.cls);
     if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);
     else { HostRow r{ST_ALIVE, a.id, a.cls, route, 0, el.lane, SYM_UNDEF, c->P.cls[a.cls].vx, 0.0, a.dbt, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el);
       el.pret_slot = -2; /* ready vehicle registered, slot assigned at upload */ }
@@ -944,7 +950,7 @@ static void create_vehicles(symgpu_ctx* c, std::vector<HostRow>& new_rows, std::
       EntryLane& el = e.lanes[nv];
       if (!owns_lane(c, el.lane)) continue;
       c->created++;
-      HostVeh hv{id, tv, route, el.lane, tcre, inst - dt + tcre};
+      HostVeh hv{id, tv, route, el.lane, tcre, inst - dt + tcre}; note_class(c, id, tv);
       (void)f;
       if (el.pret_slot != -1 || !el.queue.empty() || el.pool_slot != -1) el.queue.push_back(hv);   // :794-800
       else { HostRow r{ST_NEW, id, tv, route, 0, el.lane, SYM_UNDEF, c->P.cls[tv].vx, 0.0, tcre, hv.hent}; new_rows.push_back(r); new_row_lane.push_back(&el);

@@ -718,7 +718,14 @@ __global__ void __launch_bounds__(1024) k_scan64_block(const u64* in, u64* out, 
   if (i < n) out[i] = off + incl - v;
   if (threadIdx.x == 1023) bsum[blockIdx.x] = off + incl;
 }
-__global__ void k_scan64_sums(u64* bsum, int nb) { if (threadIdx.x || blockIdx.x) return; u64 c = 0; for (int b = 0; b < nb; b++) { const u64 t = bsum[b]; bsum[b] = c; c += t; } bsum[nb] = c; }
+__global__ void k_scan64_sums(u64* bsum, int nb) {                       // one warp: exclusive scan of the block sums, total in bsum[nb]
+  const int lane = threadIdx.x; u64 carry = 0;
+  for (int b0 = 0; b0 < nb; b0 += 32) { const int b = b0 + lane; const u64 v = b < nb ? bsum[b] : 0ULL; u64 incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (b < nb) bsum[b] = carry + incl - v;
+    carry += __shfl_sync(0xffffffffu, incl, 31); }
+  if (lane == 0) bsum[nb] = carry;
+}
 __global__ void k_scan64_add(u64* out, const u64* bsum, int n) { const int i = blockIdx.x * 1024 + threadIdx.x; if (i < n) out[i] += bsum[blockIdx.x]; }
 // the visit list in point order: rank = flag part of the scan
 __global__ void k_mrg_list(DevMrg M) { const int p = blockIdx.x * blockDim.x + threadIdx.x; if (p < M.n_pt && ((M.kf[p] >> 40) & 1)) M.fsorted[(int)(M.kfo[p] >> 40)] = p; }

@@ -9,6 +9,7 @@
 
 #include "../../include/symuvia_exports.h"
 #include "engine_internal.h"
+#include "xmlnet.h"
 
 namespace {
 symgpu_ctx* g_net = nullptr;          // theApp.GetNetwork(DEFAULT_NETWORK_ID)
@@ -20,12 +21,9 @@ bool ends_with(const std::string& s, const char* suf) { size_t n = strlen(suf); 
 void fmt2(std::string& out, double x) { char b[48]; snprintf(b, sizeof b, "%.2f", x); out += b; }
 
 // <INST> fragment: XMLDocTrafic::AddInstant (XMLDocTrafic.cpp:345-395) + AddTrajectoire (:2210-2330)
-void build_inst(symgpu_ctx* c, std::string& out) {
+void build_inst(symgpu_ctx* c, std::string& out, int n, const std::vector<int>& id, const std::vector<int>& lane, const std::vector<double>& pos,
+                const std::vector<double>& vit, const std::vector<double>& acc) {
   const symb200::FlatNet& f = symgpu_internal_net(c);
-  int n = symgpu_num_vehicles(c);
-  std::vector<int> id(n), lane(n), flags(n);
-  std::vector<double> pos(n), vit(n), acc(n);
-  if (n) symgpu_get_state(c, n, id.data(), lane.data(), nullptr, flags.data(), pos.data(), vit.data(), acc.data(), nullptr, nullptr);
   out.clear();
   out.reserve(160 + (size_t)n * 120);
   char b[96];
@@ -45,21 +43,27 @@ void build_inst(symgpu_ctx* c, std::string& out) {
     out += "\" voie=\""; out += std::to_string(num + 1);
     out += "\" dst=\""; fmt2(out, pos[k]); out += "\" abs=\""; fmt2(out, x); out += "\" ord=\""; fmt2(out, y); out += "\" z=\"0.00\" vit=\"";
     fmt2(out, vit[k]); out += "\" acc=\""; fmt2(out, acc[k]); out += "\" type=\"";
-    int cl = flags[k] >> 8; out += cl < (int)f.cls_names.size() ? f.cls_names[cl] : std::to_string(cl);
+    int cl = symgpu_internal_class_of(c, id[k]); out += cl >= 0 && cl < (int)f.cls_names.size() ? f.cls_names[cl] : std::to_string(cl);
     out += "\"/>";
   }
   out += "</TRAJS><STREAMS/><LINKS/><SGTS/><FEUX/><ENTREES/><REGULATIONS/></INST>";
 }
 
-bool run_next_step(char* out_xml, bool* end) {
+// the rows come packed, in m_LstVehicles order, through the trajectory path of the C-ABI (one copy per field on the side stream)
+std::vector<int> g_id, g_lane; std::vector<double> g_pos, g_vit, g_acc;
+bool run_next_step(char* out_xml, bool* end, bool release_at_end) {
   if (!g_net) return false;                                         // Symubruit.cpp:146-150
-  int r = symgpu_step(g_net);
+  int r;
+  if (out_xml) { const size_t cap = (size_t)symgpu_num_vehicles(g_net) + 65536;
+    if (g_id.size() < cap) { g_id.resize(cap); g_lane.resize(cap); g_pos.resize(cap); g_vit.resize(cap); g_acc.resize(cap); }
+    r = symgpu_step_traj(g_net, (int)g_id.size(), g_id.data(), g_lane.data(), g_pos.data(), g_vit.data(), g_acc.data()); }
+  else r = symgpu_step(g_net);
   if (r < 0) return false;
   const symb200::FlatNet& f = symgpu_internal_net(g_net);
   bool fin = symgpu_time(g_net) >= f.params[SYMFLAT_P_NSTEPS] * f.params[SYMFLAT_P_DT] - 1e-9;   // reseau.cpp:2427
-  if (out_xml) { build_inst(g_net, g_last_inst); strcpy(out_xml, g_last_inst.c_str()); }        // Symubruit.cpp:1013
+  if (out_xml) { build_inst(g_net, g_last_inst, r, g_id, g_lane, g_pos, g_vit, g_acc); strcpy(out_xml, g_last_inst.c_str()); }   // Symubruit.cpp:1013
   if (end) *end = fin;
-  if (fin) { symgpu_destroy(g_net); g_net = nullptr; }                                          // Symubruit.cpp:1010-1011
+  if (fin && release_at_end) { symgpu_destroy(g_net); g_net = nullptr; }                        // Symubruit.cpp:1010-1011: only the char* overload releases the networks
   return true;
 }
 }  // namespace
@@ -69,13 +73,7 @@ extern "C" {
 int SymLoadNetworkEx(char* sFile) {
   if (!sFile) return 0;
   if (g_net) { symgpu_destroy(g_net); g_net = nullptr; }
-  std::string p(sFile);
-  if (!ends_with(p, ".symflat")) {
-    // The ROOT_SYMUBRUIT XML front end (Xerces/XQilla in the reference, reseau.cpp:4931-9612) is host-only and
-    // out of the hot path; networks are flattened offline (open-symuvia_b200/synth.py).
-    fprintf(stderr, "SymLoadNetworkEx: only flattened *.symflat inputs are accepted by this build (%s)\n", sFile);
-    return 0;
-  }
+  // a ROOT_SYMUBRUIT document (the subset of csrc/xmlnet.h) or an already flattened *.symflat file: symgpu_create reads both
   symgpu_ctx* c = nullptr;
   if (symgpu_create(sFile, 0, &c) != SYMGPU_OK) { fprintf(stderr, "SymLoadNetworkEx: %s\n", symgpu_last_error()); return 0; }
   g_net = c;
@@ -84,14 +82,15 @@ int SymLoadNetworkEx(char* sFile) {
 
 void SymUnloadCurrentNetworkEx(void) { if (g_net) { symgpu_destroy(g_net); g_net = nullptr; } }
 
-bool SymRunNextStepEx(char* sOutputXmlFlow, bool bTrace, bool* bNEnd) { (void)bTrace; return run_next_step(sOutputXmlFlow, bNEnd); }
+bool SymRunNextStepEx(char* sOutputXmlFlow, bool bTrace, bool* bNEnd) { (void)bTrace; return run_next_step(sOutputXmlFlow, bNEnd, true); }
 
-bool SymRunNextStepLiteEx(bool bTrace, bool* bNEnd) { (void)bTrace; return run_next_step(nullptr, bNEnd); }
+bool SymRunNextStepLiteEx(bool bTrace, bool* bNEnd) { (void)bTrace; return run_next_step(nullptr, bNEnd, false); }   // Symubruit.cpp:1051-1060: the network stays loaded
 
 int SymRunEx(char* sFile) {
   if (!SymLoadNetworkEx(sFile)) return 1;
   bool end = false;
-  while (!end) if (!run_next_step(nullptr, &end)) { SymUnloadCurrentNetworkEx(); return 1; }
+  while (!end) if (!run_next_step(nullptr, &end, false)) { SymUnloadCurrentNetworkEx(); return 1; }
+  SymUnloadCurrentNetworkEx();
   return 0;
 }
 
@@ -112,5 +111,14 @@ int SymCreateVehicleEx(char* sType, char* sOrigin, char* sDestination, int nLane
 }
 
 void SymRunDeleteStr(char* str) { delete[] str; }                   // Symubruit.cpp:2303
+
+// Host-only helper (no CUDA): flattens a ROOT_SYMUBRUIT document into a SYMFLAT1 file, so that the flattening the XML front end does
+// (internal junction links, stop lines, merge points and their priorities) can be inspected and fed to other tools.  0 = ok.
+int symflat_from_xml(const char* xml_path, const char* out_path) {
+  if (!xml_path || !out_path) return 1;
+  symb200::FlatNet f; std::string err;
+  if (!symb200::flat_from_xml(xml_path, f, err)) { fprintf(stderr, "symflat_from_xml: %s\n", err.c_str()); return 1; }
+  return f.save(out_path) ? 0 : 1;
+}
 
 }  // extern "C"

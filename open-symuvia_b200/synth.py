@@ -50,6 +50,7 @@ class NetBuilder:
         self.link_f: List[List[float]] = []
         self.link_names: List[str] = []
         self.link_geom: List[Tuple[float, float, float, float]] = []
+        self.link_lane_w: List[float] = []
         self.lanes: List[List[int]] = []
         self.lane_f: List[float] = []
         self.succ: List[List[Tuple[int, int, int, float]]] = []     # per lane
@@ -79,8 +80,9 @@ class NetBuilder:
 
     def add_link(self, name: str, up: int, down: int, n_lanes: int, length: float, vit_reg: float,
                  type_aval: str, brick: int = -1, prev_lane: int = -1, geom=(0.0, 0.0, 0.0, 0.0),
-                 lane_lengths: Optional[List[float]] = None) -> int:
+                 lane_lengths: Optional[List[float]] = None, lane_w: float = 3.0) -> int:
         k = len(self.links)
+        self.link_lane_w.append(lane_w)
         first = len(self.lanes)
         self.links.append([first, n_lanes, up, down, ord(type_aval), brick, 0, 0])
         self.link_f.append([length, vit_reg])
@@ -230,10 +232,28 @@ class NetBuilder:
                 flat.extend(d.get(k, []))
                 off[k + 1] = len(flat)
             return off, np.asarray(flat, np.int32)
-        lcam_off, lcam = csr(self.link_cam)
-        lcav_off, lcav = csr(self.link_cav)
+        # distributors and plain merges: m_LstTuyAv of the downstream connection / m_LstTuyAm of the upstream one follow the allowed
+        # movements (first appearance, lane order), like csrc/xmlnet.h; junctions and merges filled theirs when they were generated
+        cam = {k: list(v) for k, v in self.link_cam.items()}
+        cav = {k: list(v) for k, v in self.link_cav.items()}
+        plain = {c["down_link"] for c in self.cvgs if c["node"] < 0}
+        for k in range(K):
+            if self.links[k][5] >= 0:
+                continue
+            first, nl = self.links[k][0], self.links[k][1]
+            for ln in range(first, first + nl):
+                for (key, nx, dr, rate) in self.succ[ln]:
+                    o_ = self.lanes[nx][0]
+                    if self.links[o_][5] >= 0:
+                        continue
+                    if o_ not in cav.setdefault(k, []):
+                        cav[k].append(o_)
+                    if o_ not in plain and k not in cam.setdefault(o_, []):
+                        cam[o_].append(k)
+        lcam_off, lcam = csr(cam)
+        lcav_off, lcav = csr(cav)
         merge = {}
-        if cv or self.link_cam or self.link_cav:
+        if cv or len(lcam) or len(lcav):
             merge = {"cvg_i": I(cvg_i, 8), "cvg_f": D(cvg_f, 4), "cvg_tf": D(cvg_tf), "cvgam_i": np.asarray(cvgam, np.int32),
                      "pt_i": I(pt_i, 4), "ptam_i": I(ptam_i, 2), "cafmvt_i": I(mv_i, 5), "cafmvt_links": np.asarray(mv_l, np.int32),
                      "lcam_off": lcam_off, "lcam_links": lcam, "lcav_off": lcav_off, "lcav_links": lcav,
@@ -262,6 +282,144 @@ class NetBuilder:
 
     def write(self, path: str) -> None:
         F.write(path, self.sections())
+
+    # -- the same network as a ROOT_SYMUBRUIT document (subset read by csrc/xmlnet.h) -------------
+    def to_xml(self, path: str) -> None:
+        """Reference-format input: what a SymuVia build (or `SymLoadNetworkEx` of this library) loads.  Junction-internal links, stop
+        lines, merge points and their priority levels are NOT written: the loader derives them (CarrefourAFeuxEx::Init)."""
+        from xml.sax.saxutils import quoteattr as q
+
+        def num(x):
+            return "infini" if x >= 1e9 else repr(float(x))
+
+        def hms(sec):
+            sec = float(sec)
+            h, r = divmod(sec, 3600.0)
+            m, s_ = divmod(r, 60.0)
+            return f"{int(h):02d}:{int(m):02d}:{s_:09.6f}"
+        T = len(self.classes)
+        ext = [k for k in range(len(self.links)) if self.links[k][5] < 0]
+        caf_nodes = sorted({self.links[k][5] for k in range(len(self.links)) if self.links[k][5] >= 0})
+        plain_cvg = {c["name"]: c for c in self.cvgs if c["node"] < 0}
+        o = ['<?xml version="1.0" encoding="UTF-8"?>', '<ROOT_SYMUBRUIT version="2.05">']
+        P = self.params
+        o.append(f' <SIMULATIONS><SIMULATION id="simu" pasdetemps={q(num(P[F.P_DT]))} debut="00:00:00" fin={q(hms(P[F.P_DT] * P[F.P_NSTEPS]))} loipoursuite="exacte" '
+                 f'comportementflux="iti" seed="{int(P[F.P_SEED])}" date="2020-01-01"/></SIMULATIONS>')
+        o.append(f' <TRAFICS><TRAFIC id="trafic" accbornee="{"true" if P[F.P_ACCBORNEE] else "false"}" coeffrelax={q(num(P[F.P_RELAX]))} chgtvoie="{"true" if P[F.P_CHGTVOIE] else "false"}" '
+                 f'chgtvoie_dstfin={q(num(P[F.P_DSTCHGT]))} chgtvoie_dstfin_force={q(num(P[F.P_DST_FORCE]))} chgtvoie_dstfin_force_phi={q(num(P[F.P_PHI_FORCE] or 1.0))} traversees="false" '
+                 'PeriodeAgregationCapteurs="30" Gamma="1" Mu="1" ti="0" pos_cpt_Av="5">')
+        o.append('  <TYPES_DE_VEHICULE>')
+        for c in self.classes:
+            law = {F.LAW_NEWELL: "newell", F.LAW_GIPPS: "gipps", F.LAW_IDM: "idm"}[c["law"]]
+            o.append(f'   <TYPE_DE_VEHICULE id={q(c["name"])} w={q(num(c["w"]))} kx={q(num(c["kx"]))} vx={q(num(c["vx"]))} espacement_arret={q(num(c["esp"]))} deceleration={q(num(c["decel"]))} '
+                     f'chgtvoie_tau={q(num(c["tau_lc"]))} pi_rabattement={q(num(c["pi_rab"]))} loi="{law}"><ACCELERATION_PLAGES>'
+                     + "".join(f'<ACCELERATION_PLAGE ax={q(num(ax))} vit_sup={q(num(vs))}/>' for (ax, vs) in c["plages"][:4]) + '</ACCELERATION_PLAGES></TYPE_DE_VEHICULE>')
+        o.append('  </TYPES_DE_VEHICULE>')
+        o.append('  <EXTREMITES>')
+        exit_of_node = {n: (k, cap) for (n, k, cap) in self.exits}
+        for e in self.entries:
+            nl = self.links[e["link"]][1]
+            lc = e["lane_coefs"] or [1.0 / nl] * nl
+            tc = e["type_coefs"] or ([1.0] + [0.0] * (T - 1))
+            kind = "distributionExponentielle" if e["exponential"] else "demande"
+            o.append(f'   <EXTREMITE id={q(self.node_names[e["node"]])} typeCreationVehicule="{kind}"><FLUX_GLOBAL><FLUX><DEMANDES>'
+                     + "".join(f'<DEMANDE niveau={q(num(lv))} duree={q(repr(float(du)))}/>' for (du, lv) in e["demand"]) + '</DEMANDES>'
+                     f'<REP_VOIES><REP_VOIE coeffs={q(" ".join(repr(float(x)) for x in lc))}/></REP_VOIES>'
+                     f'<REP_TYPEVEHICULES><REP_TYPEVEHICULE coeffs={q(" ".join(repr(float(x)) for x in tc))}/></REP_TYPEVEHICULES><REP_DESTINATIONS><REP_DESTINATION>'
+                     + "".join(f'<DESTINATION sortie={q(self.node_names[self.exits[x][0]])} coeffOD={q(repr(float(co)))}>'
+                               + "".join(f'<ROUTE id="R{r}" coeffAffectation={q(repr(float(rc)))}/>' for (r, rc) in rts) + '</DESTINATION>' for (x, co, rts) in e["dests"])
+                     + '</REP_DESTINATION></REP_DESTINATIONS></FLUX></FLUX_GLOBAL></EXTREMITE>')
+        for (n, k, cap) in self.exits:
+            o.append(f'   <EXTREMITE id={q(self.node_names[n])}>' + (f'<CAPACITES><CAPACITE valeur={q(repr(float(cap)))}/></CAPACITES>' if cap >= 0 else '') + '</EXTREMITE>')
+        o.append('  </EXTREMITES>')
+        # allowed movements per connection
+        o.append('  <CONNEXIONS_INTERNES>')
+        by_node: Dict[int, Dict[int, list]] = {}
+        for k in ext:
+            first, nl, up, down = self.links[k][:4]
+            for n_ in range(nl):
+                ln = first + n_
+                for (key, nx, dr, rate) in self.succ[ln]:
+                    tgt = nx
+                    if self.links[self.lanes[nx][0]][5] >= 0:          # junction-internal lane: the movement ends on the lane it leads to
+                        tgt = self.succ[nx][0][1]
+                    tl, tn = self.lanes[tgt][0], self.lanes[tgt][1]
+                    ligne = 0.0
+                    for (c_, ul, un, dl, dn, pos) in self.sl[ln]:
+                        if dl == tl and dn == tn:
+                            ligne = pos - self.lane_f[ln]
+                    by_node.setdefault(down, {}).setdefault(ln, []).append((tl, tn, rate, ligne))
+        for node in sorted(by_node):
+            name = self.node_names[node]
+            extra = ""
+            cv = plain_cvg.get(name) or next((c for c in self.cvgs if c["node"] == node), None)
+            if cv is not None:
+                extra = f' PeriodeAgregationCapteurs={q(num(cv["tagreg"]))} Gamma={q(num(cv["gamma"]))} Mu={q(num(cv["mu"]))} pos_cpt_Av={q(num(cv["pos_cpt_av"]))}'
+            o.append(f'   <CONNEXION_INTERNE id={q(name)}{extra}><MOUVEMENTS_AUTORISES>')
+            for ln in sorted(by_node[node]):
+                o.append(f'    <MOUVEMENT_AUTORISE id_troncon_amont={q(self.link_names[self.lanes[ln][0]])} num_voie_amont="{self.lanes[ln][1] + 1}"><MOUVEMENT_SORTIES>'
+                         + "".join(f'<MOUVEMENT_SORTIE id_troncon_aval={q(self.link_names[tl])} num_voie_aval="{tn + 1}" taux_utilisation={q(repr(float(rate)))} ligne_feu={q(repr(float(lg)))}/>'
+                                   for (tl, tn, rate, lg) in by_node[node][ln]) + '</MOUVEMENT_SORTIES></MOUVEMENT_AUTORISE>')
+            o.append('   </MOUVEMENTS_AUTORISES>')
+            if cv is not None and cv["tf"]:
+                o.append('   <LISTE_TEMPS_INSERTION>' + "".join(f'<TEMPS_INSERTION id_typevehicule={q(self.classes[i]["name"])} ti={q(repr(float(t)))}/>' for i, t in enumerate(cv["tf"])) + '</LISTE_TEMPS_INSERTION>')
+            o.append('   </CONNEXION_INTERNE>')
+        o.append('  </CONNEXIONS_INTERNES>')
+        o.append('  <CONTROLEURS_DE_FEUX>')
+        for ci, c in enumerate(self.ctrl):
+            o.append(f'   <CONTROLEUR_DE_FEUX id="CF{ci}" duree_vert_min="0" duree_rouge_degagement="0"><PLANS_DE_FEUX><PLAN_DE_FEUX id="P0" debut="00:00:00"><SEQUENCES>'
+                     + "".join(f'<SEQUENCE duree_totale={q(repr(float(sq["len"])))}><SIGNAUX_ACTIFS>'
+                               + "".join(f'<SIGNAL_ACTIF troncon_entree={q(self.link_names[li])} troncon_sortie={q(self.link_names[lo])} duree_vert={q(repr(float(g)))} duree_orange={q(repr(float(a)))} '
+                                         f'duree_retard_allumage={q(repr(float(d)))}/>' for (li, lo, g, a, d) in sq["signals"]) + '</SIGNAUX_ACTIFS></SEQUENCE>' for sq in c["seqs"])
+                     + '</SEQUENCES></PLAN_DE_FEUX></PLANS_DE_FEUX></CONTROLEUR_DE_FEUX>')
+        o.append('  </CONTROLEURS_DE_FEUX>')
+        o.append(' </TRAFIC></TRAFICS>')
+        o.append(' <RESEAUX><RESEAU id="reseau">')
+        o.append('  <TRONCONS>')
+        for k in ext:
+            first, nl, up, down = self.links[k][:4]
+            g = self.link_geom[k]
+            o.append(f'   <TRONCON id={q(self.link_names[k])} id_eltamont={q(self.node_names[up])} id_eltaval={q(self.node_names[down])} extremite_amont="{repr(float(g[0]))} {repr(float(g[1]))}" '
+                     f'extremite_aval="{repr(float(g[2]))} {repr(float(g[3]))}" largeur_voie={q(repr(float(self.link_lane_w[k])))} nb_voie="{nl}" vit_reg={q(repr(float(self.link_f[k][1])))} '
+                     f'longueur={q(repr(float(self.link_f[k][0])))}/>')
+        o.append('  </TRONCONS>')
+
+        def ctl(n):
+            c = self.nodes[n][1]
+            return f' controleur_de_feux="CF{c}"' if c >= 0 else ''
+        o.append('  <CONNEXIONS>')
+        o.append('   <EXTREMITES>' + "".join(f'<EXTREMITE id={q(self.node_names[n])}/>' for n in range(len(self.nodes)) if chr(self.nodes[n][0]) in "ES") + '</EXTREMITES>')
+        o.append('   <REPARTITEURS>' + "".join(f'<REPARTITEUR id={q(self.node_names[n])}{ctl(n)}/>' for n in range(len(self.nodes)) if chr(self.nodes[n][0]) == "R") + '</REPARTITEURS>')
+        o.append('   <CONVERGENTS>')
+        for n in range(len(self.nodes)):
+            if chr(self.nodes[n][0]) == "C" and n not in caf_nodes:
+                cv = plain_cvg[self.node_names[n]]
+                prio = {}
+                for (ln, niv) in cv["points"][0]["vam"]:
+                    prio[self.lanes[ln][0]] = niv
+                o.append(f'    <CONVERGENT id={q(self.node_names[n])} id_TAv={q(self.link_names[cv["down_link"]])}><TRONCONS_AMONT>'
+                         + "".join(f'<TRONCON_AMONT id={q(self.link_names[a])} priorite="{prio[a]}"/>' for a in cv["am_links"]) + '</TRONCONS_AMONT></CONVERGENT>')
+        o.append('   </CONVERGENTS>')
+        o.append('   <CARREFOURSAFEUX>')
+        for n in caf_nodes:
+            vmax = next(self.link_f[k][1] for k in range(len(self.links)) if self.links[k][5] == n)
+            o.append(f'    <CARREFOURAFEUX id={q(self.node_names[n])} vit_max={q(repr(float(vmax)))}{ctl(n)}/>')
+        o.append('   </CARREFOURSAFEUX>')
+        o.append('  </CONNEXIONS>')
+        o.append('  <ROUTES>')
+        for r, links in enumerate(self.routes):
+            o.append(f'   <ROUTE id="R{r}"><TRONCONS_>' + "".join(f'<TRONCON_ id={q(self.link_names[k])}/>' for k in links) + '</TRONCONS_></ROUTE>')
+        o.append('  </ROUTES>')
+        o.append('  <INIT><TRAJS>')
+        for v, ((c, ln, rt, rp), (pos, vit, acc)) in enumerate(zip(self.iv_i, self.iv_f)):
+            o.append(f'   <TRAJ id="{v}" tron={q(self.link_names[self.lanes[ln][0]])} voie="{self.lanes[ln][1] + 1}" dst={q(repr(float(pos)))} vit={q(repr(float(vit)))} acc={q(repr(float(acc)))} '
+                     f'type_veh={q(self.classes[c]["name"])} route="R{rt}"/>')
+        o.append('  </TRAJS></INIT>')
+        o.append(' </RESEAU></RESEAUX>')
+        o.append(' <SCENARIOS><SCENARIO id="scenario" simulation_id="simu" trafic_id="trafic" reseau_id="reseau" dirout="out" prefout="run"/></SCENARIOS>')
+        o.append('</ROOT_SYMUBRUIT>')
+        with open(path, "w", encoding="utf-8") as f:
+            f.write("\n".join(o) + "\n")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -406,7 +564,7 @@ def grid(n=10, block=200.0, n_lanes=2, vit_reg=13.89, setback=12.0, lane_w=3.0, 
         for (_, _, k, a, o, din) in sorted(by_node[node], key=lambda t: (t[0].encode(), t[1].encode(), t[2])):
             ax, ay = lane_pt(a, k, True)
             ox, oy = lane_pt(o, k, False)
-            ln = math.hypot(ox - ax, oy - ay)
+            ln = math.sqrt((ox - ax) * (ox - ax) + (oy - ay) * (oy - ay))     # the same operations as csrc/xmlnet.h (no hypot: its rounding differs between libraries)
             ent_lane = b.lane_of(a, k)
             il = b.add_link(f"I{b.link_names[a]}_{b.link_names[o]}_{k + 1}", node, node, 1, ln, vit_reg,
                             "C" if exit_in_count[o] > 1 else "R", brick=node, prev_lane=ent_lane,

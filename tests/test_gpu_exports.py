@@ -58,7 +58,30 @@ def test_lite_and_run_exports(pkg, synth, tmp_path):
         if end:
             break
     assert n == 50
+    ok, end, _ = sv.step(lite=True)                   # the Lite overload leaves the network loaded at the end of the run (Symubruit.cpp:1051-1060)
+    assert ok and end
+    sv.unload()
+    assert sv.step(lite=True)[0] is False
     assert sv.run(p) == 0 and sv.run(str(tmp_path / "nope.symflat")) == 1
+
+
+def test_load_reference_format_xml(pkg, synth, tmp_path):
+    """SymLoadNetworkEx on a ROOT_SYMUBRUIT document (csrc/xmlnet.h rebuilds the junction-internal links, stop lines and merge points):
+    same <TRAJ> output as the oracle on the generator's own flat tables, on a signalised grid with merges and on a ramp merge."""
+    for b, steps in ((synth.grid(n=3, n_steps=100, demand_per_lane=0.3, preseed_per_lane=4, shuffle=True), 100),
+                     (synth.ymerge(lanes_main=2, lanes_down=2, demand_main=0.8, n_steps=120, classes=[synth.VL, synth.PL], type_coefs=[0.8, 0.2]), 120)):
+        p, x = str(tmp_path / "g.symflat"), str(tmp_path / "g.xml")
+        b.write(p)
+        b.to_xml(x)
+        o = Oracle(p, len(b.links), len(b.classes))
+        sv = pkg.SymuVia()
+        assert sv.load(x) is True
+        for k in range(steps):
+            ok, end, xml = sv.step()
+            n = o.step()
+            assert ok and end == (k == steps - 1)
+            assert f'nbVeh="{n}"' in xml
+            assert TRAJ.findall(xml) == _expected(o, b), f"step {k + 1}"
 
 
 def test_create_vehicle_export(pkg, synth, tmp_path):
