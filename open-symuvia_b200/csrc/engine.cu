@@ -524,8 +524,8 @@ struct symgpu_ctx {
   struct Mrg { bool on = false; int n_upd = 0, n_rows = 0; DevMrg h; DBuf<DevMrg> d;
     DBuf<int> link_cvg, cvg_node, cvg_down, cvg_pt0, cvg_npt, cvg_am0, cvg_nam, cvg_win, cvg_sens0, cvg_am, pt_cvg, pt_down, pt_vam0, pt_nvam, pt_mode, pt_pm0, vam_lane, vam_ref, vam_niv,
         pm_vam, pm_sl, pm_occ0, pm_occ, lane_pt, lane_vam, sens_link, sens_cnt0, sens_win, cnt, lsens0, lsens, lcam0, lcam, lcav0, lcav, lmv0, lmv_ent, lmv_exit, fm0, fm_exit, fm_tl0, fm_ntl, fm_tl,
-        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, nused, nvoie, row_sens, flag, out;
-    DBuf<double> cvg_gamma, cvg_mu, cvg_poscpt, cvg_tf, sens_pos, pt_last, proba, mrgx; DBuf<unsigned> seen; DBuf<unsigned long long> kf, kfo, kbsum; } mg;
+        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, dlist, nused, nvoie, row_sens, flag, out;
+    DBuf<double> cvg_gamma, cvg_mu, cvg_poscpt, cvg_tf, sens_pos, pt_last, proba, mrgx; DBuf<unsigned> seen; DBuf<unsigned long long> kf, kfo, kbsum, mark; } mg;
   bool host_rng_fresh = true;                                      // the host copy of the random stream equals the device's
   std::vector<signed char> cls_of_id;                               // vehicle type by vehicle id (output writers)
   std::vector<HostEntry> entries; std::vector<ExitRow> last_exited; int last_id = 0;
@@ -876,7 +876,8 @@ static int build_merge(symgpu_ctx* c) {
   const size_t cap = c->v_status.n;
   CK(g.pt_last.alloc(std::max(1, np))); CK(g.pt_rand.alloc(std::max(1, np))); CK(g.pt_free.alloc(std::max(1, np))); CK(g.cand_up.alloc(L)); CK(cudaMemset(g.cand_up.p, 0xff, L * sizeof(int)));
   { std::vector<int> mx(cap, INT_MAX), mn(cap, -1); CK(g.own_min.upload(mx)); CK(g.own_max.upload(mn)); }
-  for (DBuf<int>* b : {&g.st, &g.ninv, &g.pre, &g.kmax, &g.decide, &g.ndraw, &g.flist, &g.fsorted, &g.res}) CK(b->alloc(std::max(1, np)));
+  for (DBuf<int>* b : {&g.st, &g.ninv, &g.pre, &g.kmax, &g.decide, &g.ndraw, &g.flist, &g.fsorted, &g.res, &g.dlist}) CK(b->alloc(std::max(1, np)));
+  CK(g.mark.alloc(cap));
   CK(g.rbuf.alloc(1 << 20)); CK(g.kbsum.alloc(np / 1024 + 3)); CK(g.kf.alloc(std::max(1, np))); CK(g.kfo.alloc(std::max(1, np)));
   CK(g.inv.alloc((size_t)std::max(1, np) * kMrgInv)); CK(g.proba.alloc(std::max(1, np))); CK(g.nused.alloc(cap)); CK(g.nvoie.alloc(cap)); CK(cudaMemset(g.nvoie.p, 0xff, cap * sizeof(int)));
   CK(g.mrgx.alloc(((size_t)cap + 32) * kMrgX)); CK(g.flag.alloc(1)); CK(g.out.alloc(1)); CK(g.seen.alloc(1));
@@ -890,7 +891,7 @@ static int build_merge(symgpu_ctx* c) {
   h.lcam0 = g.lcam0.p; h.lcam = g.lcam.p; h.lcav0 = g.lcav0.p; h.lcav = g.lcav.p; h.lmv0 = g.lmv0.p; h.lmv_ent = g.lmv_ent.p; h.lmv_exit = g.lmv_exit.p;
   h.fm0 = g.fm0.p; h.fm_exit = g.fm_exit.p; h.fm_tl0 = g.fm_tl0.p; h.fm_ntl = g.fm_ntl.p; h.fm_tl = g.fm_tl.p; h.node_type = g.node_type.p;
   h.pt_last = g.pt_last.p; h.pt_rand = g.pt_rand.p; h.pt_free = g.pt_free.p; h.cand_up = g.cand_up.p; h.own_min = g.own_min.p; h.own_max = g.own_max.p;
-  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.flist = g.flist.p; h.proba = g.proba.p; h.kf = g.kf.p; h.kfo = g.kfo.p; h.fsorted = g.fsorted.p; h.rbuf = g.rbuf.p; h.rbuf_cap = 1 << 20; h.res = g.res.p;
+  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.flist = g.flist.p; h.proba = g.proba.p; h.kf = g.kf.p; h.kfo = g.kfo.p; h.fsorted = g.fsorted.p; h.rbuf = g.rbuf.p; h.rbuf_cap = 1 << 20; h.res = g.res.p; h.dlist = g.dlist.p; h.n_dirty = g.flag.p; h.mark = g.mark.p;
   h.nused = g.nused.p; h.nvoie = g.nvoie.p; h.mrgx = g.mrgx.p; h.rng = c->lc_rng.p; h.draws = c->draws.p; h.counters = c->counters.p;
   std::vector<DevMrg> one_h(1, h); CK(g.d.upload(one_h));
   return SYMGPU_OK;
@@ -1153,7 +1154,9 @@ static int step_back(symgpu_ctx* c) {
       if (c->mg.on && n_sorted > 0) { auto& g = c->mg; const int Gp = G(g.h.n_pt);
         KBEGIN(c, KID_MERGE); cudaMemsetAsync(g.flag.p, 0, sizeof(int), s);
         k_mrg_probe<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
-        k_mrg_eval<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, g.flag.p, guard); LAUNCH(c);
+        k_mrg_classify<<<Gp, B, 0, s>>>(g.h, guard); LAUNCH(c);
+        k_mrg_eval<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        k_mrg_dirty<<<1, 256, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
         { const int np = g.h.n_pt, nbk = (np + 1023) / 1024;                              // offset of every point's draws in the stream and rank of the visited points: one scan
           k_scan64_block<<<nbk, 1024, 0, s>>>(g.kf.p, g.kfo.p, g.kbsum.p, np); LAUNCH(c);
           k_scan64_sums<<<1, 32, 0, s>>>(g.kbsum.p, nbk); LAUNCH(c);

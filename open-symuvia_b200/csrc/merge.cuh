@@ -54,6 +54,7 @@ struct DevMrg {
   int *own_min, *own_max;                                                  // per vehicle slot: lowest / highest point that touches it
   int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw, *flist; double* proba;   // per point, this step; flist: the points the walk must visit (unordered)
   int* res;                                                               // per point: 1 inserted, 2 refused this step (summed by k_mrg_apply)
+  int *dlist, *n_dirty; unsigned long long* mark;                         // points that share a vehicle with another point; per vehicle: (round << 32 | ~point) of the lowest unfinished point touching it
   unsigned long long *kf, *kfo; int *fsorted, *rbuf; int rbuf_cap;                       // kf: per point, draws known before the walk (low 40 bits) | visit flag (bit 40); kfo: its exclusive scan = offset in the stream | rank in the visit list
   int *nused, *nvoie;                                                      // per vehicle: intermediate lanes used this step; m_pNextVoie (sticky)
   double* mrgx;                                                            // per order position: phase A -> phase B side record (6 doubles)
@@ -591,6 +592,27 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
   return MS_DONE;
 }
 
+// The ordered visit of the value-drawing points whose number of tests depends on the values (k_mrg_walk), by one warp: entry after entry,
+// the tests of one entry done by the lanes together.  rec[k] = (offset of the first tested value without the draws of the visited points
+// before it, test limit, integer threshold, 0); cpre[k] = draws of the entries before k whose consumption does not depend on values;
+// out[k] = (inserted << 16) | tests made.  Stops at the first entry that is not a value-drawing point.  Out of line: its registers are its own.
+__device__ __noinline__ int walk_hard_run(const int4* rec, const int* cpre, const unsigned char* st, const int* hidx, int j0, int nh, int* out, int* hused,
+                                          int extra, int* H_io, const int* vals, int U) {
+  const int lane = threadIdx.x & 31; int H = *H_io; int j = j0;
+  for (; j < nh; j++) {
+    const int k = hidx[j]; if (st[k] != MS_VALUES) break;
+    const int4 r = rec[k]; const int start = r.x + extra + cpre[k] + H, lim = r.y, thr = r.z;
+    int used = lim, ins = 0;
+    for (int d0 = 0; d0 < lim; d0 += 32) { const int d = d0 + lane, pos = start + d;
+      const bool hit = d < lim && (pos < U ? vals[pos] : 32767) < thr;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) { used = d0 + __ffs(m); ins = 1; break; } }
+    if (lane == 0) { out[k] = (ins << 16) | used; hused[k] = used; }
+    H += used;
+  }
+  *H_io = H;
+  return j;
+}
 // out of line: the ordered visit of k_mrg_walk is a tight loop that must not inherit this function's register pressure
 __device__ __noinline__ void merge_point_serial(const MrgView* W, int q, RngCursor* C) {
   MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
@@ -630,21 +652,61 @@ __global__ void k_mrg_probe(DevNet N, DevVeh V, DevMrg M, const int* order, cons
   M.st[p] = st; M.ninv[p] = A.ninv; M.ndraw[p] = 0; M.kf[p] = st == MS_VALUES ? (unsigned long long)(A.ndraw + 1) : 0ULL;
   for (int k = 0; k < A.ninv; k++) { M.inv[p * kMrgInv + k] = A.inv[k]; atomicMin(&M.own_min[A.inv[k]], p); atomicMax(&M.own_max[A.inv[k]], p); }
 }
-__global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
-                           const int* posidx, const double* rows, double inst, int n_upd, int* n_flag, const int* guard) {
+// after every probe: points whose vehicles no other point touches are "clean"; the others go to the list of k_mrg_dirty
+__global__ void k_mrg_classify(DevMrg M, const int* guard) {
   if (guard && *guard == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= M.n_pt) return;
-  int st = M.st[p];
+  const int st = M.st[p];
   if (st == MS_NONE) return;
   bool clean = st != MS_OVERFLOW;
   for (int k = 0; k < M.ninv[p] && clean; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p) clean = false; }
-  if (!clean) { M.st[p] = MS_DIRTY; M.kf[p] = 1ULL << 40; return; }                         // visited by the walk, draws unknown until then
-  if (st == MS_VALUES) { M.kf[p] |= 1ULL << 40; return; }                      // decided by the walk, applied by k_mrg_apply
+  if (!clean) { M.st[p] = MS_DIRTY; M.kf[p] = 1ULL << 40; M.dlist[atomicAdd(M.n_dirty, 1)] = p; return; }   // visited by the walk unless k_mrg_dirty settles it
+  if (st == MS_VALUES) M.kf[p] |= 1ULL << 40;                                                // decided by the walk, applied by k_mrg_apply
+}
+__global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
+                           const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= M.n_pt || M.st[p] != MS_DONE) return;                                             // clean points that need no values of the stream
   const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
   MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
-  st = merge_point(W, p, MM_EVAL, A, nullptr);
-  M.st[p] = st; M.ndraw[p] = A.ndraw; M.kf[p] = (unsigned long long)A.ndraw;                                // count-only draws: an offset for the points after this one, nothing to visit
+  const int st = merge_point(W, p, MM_EVAL, A, nullptr);
+  M.st[p] = st; M.ndraw[p] = A.ndraw; M.kf[p] = (unsigned long long)A.ndraw;               // count-only draws: an offset for the points after this one, nothing to visit
+}
+// Points that share a vehicle with another point must be processed in point order — but only relative to the points they share with.
+// One block, rounds: every unfinished point stamps its vehicles with (round, point), lowest point wins; a point that holds all its
+// vehicles is processed now (after a fresh probe: what it touches may have changed; anything unexpected leaves it to the walk, and so
+// does a decision that needs values of the stream).  Points processed in the same round touch disjoint vehicles.
+__global__ void __launch_bounds__(256) k_mrg_dirty(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
+                                                   const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
+  __shared__ int s_progress;
+  if (guard && *guard == 0) return;
+  const int nd = *M.n_dirty; if (nd == 0) return;
+  const int tid = threadIdx.x;
+  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+  for (int round = 0; round < 6; round++) {
+    const unsigned long long base = ((unsigned long long)((unsigned)n_upd * 8u + (unsigned)round + 1u)) << 32;
+    for (int d = tid; d < nd; d += 256) { const int p = M.dlist[d]; if (M.st[p] != MS_DIRTY) continue;
+      for (int k = 0; k < M.ninv[p]; k++) atomicMax(&M.mark[M.inv[p * kMrgInv + k]], base | (unsigned long long)(0xFFFFFFFFu - (unsigned)p)); }
+    if (tid == 0) s_progress = 0;
+    __threadfence(); __syncthreads();
+    for (int d = tid; d < nd; d += 256) { const int p = M.dlist[d]; if (M.st[p] != MS_DIRTY) continue;
+      const unsigned long long key = base | (unsigned long long)(0xFFFFFFFFu - (unsigned)p);
+      bool ready = true; for (int k = 0; k < M.ninv[p] && ready; k++) ready = M.mark[M.inv[p * kMrgInv + k]] == key;
+      if (!ready) continue;
+      MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
+      const int st = merge_point(W, p, MM_PROBE, A, nullptr);
+      bool ok = !A.overflow && st != MS_VALUES;
+      for (int k = 0; k < A.ninv && ok; k++) ok = M.mark[A.inv[k]] == key;                     // everything it touches NOW is its own
+      if (!ok) continue;                                                                       // left to the walk (literal, in order); the points behind it in its cluster wait with it
+      if (st == MS_DONE) { MrgAcc B; B.ninv = 0; B.ndraw = 0; B.overflow = false; merge_point(W, p, MM_EVAL, B, nullptr); M.ndraw[p] = B.ndraw; M.kf[p] = (unsigned long long)B.ndraw; }
+      else { M.ndraw[p] = 0; M.kf[p] = 0ULL; }
+      M.st[p] = MS_DONE; s_progress = 1; }
+    __threadfence(); __syncthreads();
+    if (!s_progress) break;
+    __syncthreads();
+  }
 }
 // ---- the random stream on the device -----------------------------------------------------------------------------------------
 // RandManager::myRand = boost::mt19937 + uniform_int<>(0, 0x7FFE) by bucket rejection (RandManager.cpp:26-30).  One block of 256 threads
@@ -736,10 +798,10 @@ __global__ void k_mrg_list(DevMrg M) { const int p = blockIdx.x * blockDim.x + t
 __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start,
                                                   const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const u64* kf_total,
                                                   int* out, const int* guard) {
-  constexpr int kBatch = 512, kRc = 6144;
+  constexpr int kBatch = 512, kRc = 4096;
   __shared__ int sh_rb[kRc];                                                               // the look-ahead values, when they fit: thread 0 reads them one by one
-  __shared__ MtShared S; __shared__ int e_pt[kBatch], e_off[kBatch], e_pre[kBatch], e_kmax[kBatch], e_thr[kBatch], e_used[kBatch], e_scan[kBatch]; __shared__ unsigned char e_st[kBatch], e_ins[kBatch];
-  __shared__ int sh_next, sh_flag;
+  __shared__ MtShared S; __shared__ int4 e_rec[kBatch]; __shared__ int e_pt[kBatch], e_res[kBatch], e_cpre[kBatch], e_hpre[kBatch], e_hused[kBatch], e_hidx[kBatch]; __shared__ unsigned char e_st[kBatch];
+  __shared__ int sh_next, sh_red2[8], sh_ctot, sh_nh, sh_H;
   __shared__ int sh_red[8]; __shared__ int sh_total;
   if (guard && *guard == 0) return;
   const int tid = threadIdx.x;
@@ -775,63 +837,70 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
   tq2 = clock64();
 #endif
   int extra = 0;                                                                           // draws consumed by the visited points beyond `known`
-  int n_values = 0, n_serial = 0;
+  int n_values_t = 0, n_serial = 0;                                                        // n_values_t: per thread, summed at the end
   for (int b0 = 0; b0 < nf; b0 += kBatch) {
     const int nb = min(kBatch, nf - b0);
     __syncthreads();
-    for (int k = tid; k < nb; k += 256) { const int q = M.fsorted[b0 + k]; e_pt[k] = q; e_off[k] = (int)(M.kfo[q] & ((1ULL << 40) - 1)); e_pre[k] = M.pre[q]; e_kmax[k] = M.kmax[q]; e_st[k] = (unsigned char)M.st[q];
+    for (int k = tid; k < nb; k += 256) { const int q = M.fsorted[b0 + k]; e_pt[k] = q; e_st[k] = (unsigned char)M.st[q];
       // the test `draw / 32767.0 < proba` as an integer threshold (exactly: the quotient is monotonic in the draw), so that the ordered visit is integer work
       const double pr = M.proba[q]; int T = (int)fmin(fmax(ceil(pr * 32767.0), 0.0), 32767.0); if (!(pr == pr)) T = 0;
       while (T <= 32766 && (T / 32767.0 < pr)) T++; while (T > 0 && !((T - 1) / 32767.0 < pr)) T--;
-      e_thr[k] = T; }
+      const int off = (int)(M.kfo[q] & ((1ULL << 40) - 1));
+      // VALUES: offset of the first tested value = point offset + count-only draws + the unused draw; tests while k < m_nRandNumbers, decremented per test: ceil(n / 2) at most
+      e_rec[k] = e_st[k] == MS_VALUES ? make_int4(off + M.pre[q] + 1, (M.kmax[q] + 1) >> 1, T, 0) : make_int4(off + 1, 0, 0, 0); }
     __syncthreads();
-    // Ordered visit without a serial loop.  A VALUES entry consumes `used` draws: tests go on while k < m_nRandNumbers, which is
-    // decremented per test, i.e. at most lim = ceil(n / 2) of them, fewer when one succeeds (AbstractCarFollowing.cpp:362-374).  Where an
-    // entry's draws start depends on what the entries before it consumed, so: assume used = lim everywhere, prefix-sum, let every
-    // entry test its draws in parallel, repeat while an assumption was wrong.  Entries before the first wrong one are final, so every
-    // round fixes at least one more; a round that changes nothing is the sequential result.
-    int k0 = 0;
-    while (k0 < nb) {
-      if (tid == 0) sh_next = nb;
+    // Entries whose consumption does not depend on the values (one test at most: AbstractCarFollowing.cpp:362-374 tests while k < m_nRandNumbers,
+    // decremented per test) are offsets for the others and decided afterwards, in parallel; only the "hard" ones (two tests or more, and the
+    // points left to a literal visit) are walked in order.
+    { const int i0 = 2 * tid, i1 = i0 + 1;                                                     // e_cpre = exclusive scan of the constant consumptions; hard entries compacted in order
+      auto cons = [&](int k) { return k < nb && e_st[k] == MS_VALUES && e_rec[k].y <= 1 ? e_rec[k].y : 0; };
+      auto hard = [&](int k) { return k < nb && !(e_st[k] == MS_VALUES && e_rec[k].y <= 1) ? 1 : 0; };
+      const int a = cons(i0), b2 = cons(i1), ha = hard(i0), hb = hard(i1); int incl = a + b2, hincl = ha + hb;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o), t2 = __shfl_up_sync(0xffffffffu, hincl, o); if ((tid & 31) >= o) { incl += t; hincl += t2; } }
+      if ((tid & 31) == 31) { sh_red[tid >> 5] = incl; sh_red2[tid >> 5] = hincl; }
       __syncthreads();
-      for (int k = k0 + tid; k < nb; k += 256) if (e_st[k] != MS_VALUES) atomicMin(&sh_next, k);
+      int off = 0, hoff = 0; for (int w = 0; w < (tid >> 5); w++) { off += sh_red[w]; hoff += sh_red2[w]; }
+      const int ex = off + incl - (a + b2), hex = hoff + hincl - (ha + hb);
+      if (i0 < nb) { e_cpre[i0] = ex; e_hused[i0] = 0; if (ha) e_hidx[hex] = i0; }
+      if (i1 < nb) { e_cpre[i1] = ex + a; e_hused[i1] = 0; if (hb) e_hidx[hex + ha] = i1; }
+      if (tid == 255) { sh_ctot = off + incl; sh_nh = hoff + hincl; }
+      __syncthreads(); }
+    const int nh = sh_nh; const int ctot = sh_ctot;
+    if (tid == 0) sh_H = 0;
+    __syncthreads();
+    for (int j = 0; j < nh;) {                                                                 // the ordered part
+      if (tid < 32) { int H = sh_H; const int jn = walk_hard_run(e_rec, e_cpre, e_st, e_hidx, j, nh, e_res, e_hused, extra, &H, vals, U); if (tid == 0) { sh_H = H; sh_next = jn; } }
       __syncthreads();
-      const int k1 = sh_next; const int ns = k1 - k0;
-      for (int k = k0 + tid; k < k1; k += 256) e_used[k] = (e_kmax[k] + 1) >> 1;
-      for (;;) {
-        __syncthreads();
-        { const int i0 = k0 + 2 * tid, i1 = i0 + 1; const int a = i0 < k1 ? e_used[i0] : 0, b2 = i1 < k1 ? e_used[i1] : 0; int incl = a + b2;   // exclusive scan of e_used over [k0, k1)
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
-          if ((tid & 31) == 31) sh_red[tid >> 5] = incl;
-          if (tid == 0) sh_flag = 0;
-          __syncthreads();
-          int off = 0; for (int w = 0; w < (tid >> 5); w++) off += sh_red[w];
-          const int ex = off + incl - (a + b2);
-          if (i0 < k1) e_scan[i0] = ex; if (i1 < k1) e_scan[i1] = ex + a; }
-        __syncthreads();
-        for (int k = k0 + tid; k < k1; k += 256) { const int start = e_off[k] + extra + e_scan[k] + e_pre[k] + 1; const int lim = (e_kmax[k] + 1) >> 1; const int thr = e_thr[k];
-          int u = lim; bool ins = false;
-          for (int d = 0; d < lim; d++) { const int pos = start + d; if ((pos < U ? vals[pos] : 32767) < thr) { u = d + 1; ins = true; break; } }
-          e_ins[k] = ins; if (u != e_used[k]) { e_used[k] = u; sh_flag = 1; } }
-        __syncthreads();
-        if (!sh_flag) break;
-      }
-      for (int k = k0 + tid; k < k1; k += 256) M.decide[e_pt[k]] = ((int)e_ins[k] << 16) | e_used[k];
-      if (ns > 0) extra += e_scan[k1 - 1] + e_used[k1 - 1];
-      n_values += ns;
-      if (k1 < nb) {                                                                         // an entry that shares a vehicle with another point: literally, now
-        if (tid == 0) { const int q = e_pt[k1]; RngCursor C{vals, e_off[k1] + extra, U, 0};
+      j = sh_next;
+      if (j < nh) {                                                                            // a point that shares a vehicle with another point and was not settled by k_mrg_dirty: literally, now
+        if (tid == 0) { const int k = e_hidx[j]; const int q = e_pt[k]; const int at = e_rec[k].x - 1 + extra + e_cpre[k] + sh_H; RngCursor C{vals, at, U, 0};
           merge_point_serial(&W, q, &C);
-          sh_red[0] = C.pos - (e_off[k1] + extra); sh_red[1] = C.overflow; M.st[q] = MS_DONE; }
+          e_hused[k] = C.pos - at; sh_H += C.pos - at; sh_red[1] = C.overflow; M.st[q] = MS_DONE; }
         __syncthreads();
-        extra += sh_red[0]; overflow |= sh_red[1]; n_serial++;
+        overflow |= sh_red[1]; n_serial++; j++;
         __syncthreads();
       }
-      k0 = k1 + 1;
     }
+    { const int i0 = 2 * tid, i1 = i0 + 1;                                                     // e_hpre = exclusive scan of what the hard entries consumed
+      const int a = i0 < nb ? e_hused[i0] : 0, b2 = i1 < nb ? e_hused[i1] : 0; int incl = a + b2;
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+      __syncthreads();
+      if ((tid & 31) == 31) sh_red[tid >> 5] = incl;
+      __syncthreads();
+      int off = 0; for (int w = 0; w < (tid >> 5); w++) off += sh_red[w];
+      const int ex = off + incl - (a + b2);
+      if (i0 < nb) e_hpre[i0] = ex; if (i1 < nb) e_hpre[i1] = ex + a;
+      __syncthreads(); }
+    for (int k = tid; k < nb; k += 256) if (e_st[k] == MS_VALUES) {                            // decisions out; the easy ones are made here
+      int d = e_res[k];
+      if (e_rec[k].y <= 1) { const int pos = e_rec[k].x + extra + e_cpre[k] + e_hpre[k]; const bool ins = e_rec[k].y == 1 && (pos < U ? vals[pos] : 32767) < e_rec[k].z; d = ((int)ins << 16) | e_rec[k].y; }
+      M.decide[e_pt[k]] = d; n_values_t++; }
+    extra += ctot + sh_H;
+    __syncthreads();
   }
   __syncthreads();
-  if (tid == 0) { sh_total = known_total + extra; M.counters[SYMGPU_CNT_MRG_VALUES] += n_values; M.counters[SYMGPU_CNT_MRG_SERIAL] += n_serial; if (overflow) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL); }
+  if (n_values_t) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_VALUES], (unsigned long long)n_values_t);
+  if (tid == 0) { sh_total = known_total + extra; M.counters[SYMGPU_CNT_MRG_SERIAL] += n_serial; if (overflow) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL); }
   __syncthreads();
 #ifdef SYM_WALK_TIMING
   tq3 = clock64();
