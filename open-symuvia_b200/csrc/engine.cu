@@ -518,13 +518,13 @@ struct symgpu_ctx {
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
-  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_fill = false /* k_final listed vehicles for k_ctx_fill */, aux_wait = false /* the step has work on the side stream */, dbg_sync = false, dbg_failed = false, coop_loops = true; cudaStream_t aux = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
+  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_fill = false /* k_final listed vehicles for k_ctx_fill */, aux_wait = false /* the step has work on the side stream */, dbg_sync = false, dbg_failed = false, coop_loops = true; cudaStream_t aux = nullptr, aux2 = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr, ev_fork = nullptr, ev_rng = nullptr, ev_dirty = nullptr, ev_sens = nullptr; bool rng_wait = false, sens_wait = false;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
   // merge points (merge.cuh): static tables, per-point state, sensors, per-step records; the device copy of the struct for the kernels that take a pointer
   struct Mrg { bool on = false; int n_upd = 0, n_rows = 0; DevMrg h; DBuf<DevMrg> d;
     DBuf<int> link_cvg, cvg_node, cvg_down, cvg_pt0, cvg_npt, cvg_am0, cvg_nam, cvg_win, cvg_sens0, cvg_am, pt_cvg, pt_down, pt_vam0, pt_nvam, pt_mode, pt_pm0, vam_lane, vam_ref, vam_niv,
         pm_vam, pm_sl, pm_occ0, pm_occ, lane_pt, lane_vam, sens_link, sens_cnt0, sens_win, cnt, lsens0, lsens, lcam0, lcam, lcav0, lcav, lmv0, lmv_ent, lmv_exit, fm0, fm_exit, fm_tl0, fm_ntl, fm_tl,
-        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, dlist, nused, nvoie, row_sens, flag, out;
+        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, dlist, nused, nvoie, ulanes, row_sens, flag, out;
     DBuf<double> cvg_gamma, cvg_mu, cvg_poscpt, cvg_tf, sens_pos, pt_last, proba, mrgx; DBuf<unsigned> seen; DBuf<unsigned long long> kf, kfo, kbsum, mark; } mg;
   bool host_rng_fresh = true;                                      // the host copy of the random stream equals the device's
   std::vector<signed char> cls_of_id;                               // vehicle type by vehicle id (output writers)
@@ -712,7 +712,9 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   { const char* e = getenv("SYMGPU_CTXCACHE"); c->use_cc = !(e && !strcmp(e, "0")); }                    // SYMGPU_CTXCACHE=0: every vehicle walks the tables every step (cross-check)
   if (c->use_cc) { CK(c->cc_lane.alloc(cap)); CK(cudaMemset(c->cc_lane.p, 0xff, cap * sizeof(int))); CK(c->cc_id.alloc(cap)); CK(cudaMemset(c->cc_id.p, 0xff, cap * sizeof(int)));
     CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); CK(cudaMemset(c->cc.p, 0xff, cap * sizeof(CtxCache))); }   // key (-1, -1): matches no vehicle
-  CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&c->cc_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->cc_done, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->aux2, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&c->ev_fork, &c->ev_rng, &c->ev_dirty, &c->ev_sens}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->cc_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->cc_done, cudaEventDisableTiming));
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
   if (c->chgtvoie) { CK(c->lc_kind.alloc(2 * cap)); CK(c->lc_code.alloc(3 * cap)); CK(c->lc_tl_pre.alloc(3 * cap)); CK(c->lc_rfol.alloc(3 * cap)); CK(c->lc_rtgt.alloc(3 * cap));
@@ -752,6 +754,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
   for (int k = 0; k < kTrajBufs; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
   c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
+  if (c->aux2) cudaStreamDestroy(c->aux2); for (cudaEvent_t e : {c->ev_fork, c->ev_rng, c->ev_dirty, c->ev_sens}) if (e) cudaEventDestroy(e);
   if (c->aux) cudaStreamDestroy(c->aux); if (c->cc_go) cudaEventDestroy(c->cc_go); if (c->cc_done) cudaEventDestroy(c->cc_done);
   if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); if (c->t_packed) cudaEventDestroy(c->t_packed); for (int k = 0; k < kTrajBufs; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
@@ -879,8 +882,8 @@ static int build_merge(symgpu_ctx* c) {
   for (DBuf<int>* b : {&g.st, &g.ninv, &g.pre, &g.kmax, &g.decide, &g.ndraw, &g.flist, &g.fsorted, &g.res, &g.dlist}) CK(b->alloc(std::max(1, np)));
   CK(g.mark.alloc(cap));
   CK(g.rbuf.alloc(1 << 20)); CK(g.kbsum.alloc(np / 1024 + 3)); CK(g.kf.alloc(std::max(1, np))); CK(g.kfo.alloc(std::max(1, np)));
-  CK(g.inv.alloc((size_t)std::max(1, np) * kMrgInv)); CK(g.proba.alloc(std::max(1, np))); CK(g.nused.alloc(cap)); CK(g.nvoie.alloc(cap)); CK(cudaMemset(g.nvoie.p, 0xff, cap * sizeof(int)));
-  CK(g.mrgx.alloc(((size_t)cap + 32) * kMrgX)); CK(g.flag.alloc(1)); CK(g.out.alloc(1)); CK(g.seen.alloc(1));
+  CK(g.inv.alloc((size_t)std::max(1, np) * kMrgInv)); CK(g.proba.alloc(std::max(1, np))); CK(g.nused.alloc(cap)); CK(g.ulanes.alloc(cap * 3)); CK(g.nvoie.alloc(cap)); CK(cudaMemset(g.nvoie.p, 0xff, cap * sizeof(int)));
+  CK(g.mrgx.alloc(((size_t)cap + 32) * kMrgX)); CK(g.flag.alloc(1)); CK(g.out.alloc(2)); CK(g.seen.alloc(1));
   h.n_cvg = nc; h.n_pt = np; h.n_sens = (int)sens_link.size(); h.n_cls = T;
   h.max_debit_max = max_debit_max(c); h.max_vit_max = 0; for (int i = 0; i < T; i++) h.max_vit_max = std::max(h.max_vit_max, c->P.cls[i].vx); h.vx0 = c->P.cls[0].vx;
   h.link_cvg = g.link_cvg.p; h.cvg_node = g.cvg_node.p; h.cvg_down = g.cvg_down.p; h.cvg_pt0 = g.cvg_pt0.p; h.cvg_npt = g.cvg_npt.p; h.cvg_am0 = g.cvg_am0.p; h.cvg_nam = g.cvg_nam.p; h.cvg_win = g.cvg_win.p;
@@ -891,8 +894,8 @@ static int build_merge(symgpu_ctx* c) {
   h.lcam0 = g.lcam0.p; h.lcam = g.lcam.p; h.lcav0 = g.lcav0.p; h.lcav = g.lcav.p; h.lmv0 = g.lmv0.p; h.lmv_ent = g.lmv_ent.p; h.lmv_exit = g.lmv_exit.p;
   h.fm0 = g.fm0.p; h.fm_exit = g.fm_exit.p; h.fm_tl0 = g.fm_tl0.p; h.fm_ntl = g.fm_ntl.p; h.fm_tl = g.fm_tl.p; h.node_type = g.node_type.p;
   h.pt_last = g.pt_last.p; h.pt_rand = g.pt_rand.p; h.pt_free = g.pt_free.p; h.cand_up = g.cand_up.p; h.own_min = g.own_min.p; h.own_max = g.own_max.p;
-  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.flist = g.flist.p; h.proba = g.proba.p; h.kf = g.kf.p; h.kfo = g.kfo.p; h.fsorted = g.fsorted.p; h.rbuf = g.rbuf.p; h.rbuf_cap = 1 << 20; h.res = g.res.p; h.dlist = g.dlist.p; h.n_dirty = g.flag.p; h.mark = g.mark.p;
-  h.nused = g.nused.p; h.nvoie = g.nvoie.p; h.mrgx = g.mrgx.p; h.rng = c->lc_rng.p; h.draws = c->draws.p; h.counters = c->counters.p;
+  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.flist = g.flist.p; h.proba = g.proba.p; h.kf = g.kf.p; h.kfo = g.kfo.p; h.fsorted = g.fsorted.p; h.rbuf = g.rbuf.p; h.rbuf_cap = 1 << 20; h.res = g.res.p; h.dlist = g.dlist.p; h.n_dirty = g.flag.p; h.mark = g.mark.p; h.sens_go = g.out.p + 1;
+  h.nused = g.nused.p; h.nvoie = g.nvoie.p; h.ulanes = g.ulanes.p; h.mrgx = g.mrgx.p; h.rng = c->lc_rng.p; h.draws = c->draws.p; h.counters = c->counters.p;
   std::vector<DevMrg> one_h(1, h); CK(g.d.upload(one_h));
   return SYMGPU_OK;
 }
@@ -1061,6 +1064,7 @@ static int step_front(symgpu_ctx* c) {
   }
   // lane changing (reseau.cpp:14181): sequential acceptance tests on the device random stream, then the lane order is rebuilt
   if (c->chgtvoie && n > 0) {
+    if (c->sens_wait) { CK(cudaStreamWaitEvent(s, c->ev_sens, 0)); c->sens_wait = false; }   // lane changing rewrites what the sensor kernel of the last step reads
     if (c->pack_wait) { CK(cudaStreamWaitEvent(s, c->t_packed, 0)); c->pack_wait = false; }
     const int K = c->net.n_links();
     KBEGIN(c, KID_LC);
@@ -1101,13 +1105,18 @@ static int step_back(symgpu_ctx* c) {
   auto G = [&](int cnt) { return (cnt + B - 1) / B; };
   const int by_id = c->mp.on ? 1 : 0;
   if (c->aux_wait) { CK(cudaStreamWaitEvent(s, c->cc_done, 0)); c->aux_wait = false; }
+  if (c->sens_wait) { CK(cudaStreamWaitEvent(s, c->ev_sens, 0)); c->sens_wait = false; }   // the merge sensors of the last step were counted beside this step's lane ordering
   if (c->mg.on) {                                                         // merge points: candidates of the step, priority levels from this step's signal colours
     KBEGIN(c, KID_MERGE); CK(cudaMemsetAsync(c->mg.cand_up.p, 0xff, L * sizeof(int), s));
     k_mrg_rank<<<G(c->mg.h.n_pt), B, 0, s>>>(c->mg.h, c->sl_col.p, c->lane_count.p); KEND(c); }
   if (n > 0) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW],
-                                                                                             c->mg.on ? c->mg.d.p : nullptr, c->t); KEND(c); }
+                                                                                             c->mg.on ? c->mg.d.p : nullptr, c->t); KEND(c);
+      if (c->mg.on && !has_entries && c->profile != 1) {                     // this step's count-only draws are final: the stream passes them beside the relaxation
+        CK(cudaEventRecord(c->ev_fork, s)); CK(cudaStreamWaitEvent(c->aux2, c->ev_fork, 0));
+        k_rng_ctx<<<1, 256, 0, c->aux2>>>(c->lc_rng.p, c->draws.p, c->mg.seen.p, nullptr); LAUNCH(c);
+        CK(cudaEventRecord(c->ev_rng, c->aux2)); c->rng_wait = true; } }
     // dependency-ordered follow phase (flow.cuh): segments -> dataflow rounds -> loop cutting when a round stalls
     if (n_sorted > 0) {
     KBEGIN(c, KID_SEG); k_seg<<<G(n_sorted), B, 0, s>>>(c->dv, c->df, n_sorted, c->s_lane.p, c->lane_count.p, c->lane_start.p, by_id); KEND(c);
@@ -1155,14 +1164,19 @@ static int step_back(symgpu_ctx* c) {
         KBEGIN(c, KID_MERGE); cudaMemsetAsync(g.flag.p, 0, sizeof(int), s);
         k_mrg_probe<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
         k_mrg_classify<<<Gp, B, 0, s>>>(g.h, guard); LAUNCH(c);
+        const bool side = c->profile != 1;                                          // the points that share vehicles are settled beside the clean ones
+        if (side) { cudaEventRecord(c->ev_fork, s); cudaStreamWaitEvent(c->aux2, c->ev_fork, 0); }
+        k_mrg_dirty<<<1, 256, 0, side ? c->aux2 : s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        if (side) cudaEventRecord(c->ev_dirty, c->aux2);
         k_mrg_eval<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
-        k_mrg_dirty<<<1, 256, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        if (side) cudaStreamWaitEvent(s, c->ev_dirty, 0);
         { const int np = g.h.n_pt, nbk = (np + 1023) / 1024;                              // offset of every point's draws in the stream and rank of the visited points: one scan
           k_scan64_block<<<nbk, 1024, 0, s>>>(g.kf.p, g.kfo.p, g.kbsum.p, np); LAUNCH(c);
           k_scan64_sums<<<1, 32, 0, s>>>(g.kbsum.p, nbk); LAUNCH(c);
           if (nbk > 1) { k_scan64_add<<<nbk, 1024, 0, s>>>(g.kfo.p, g.kbsum.p, np); LAUNCH(c); }
           k_mrg_list<<<Gp, B, 0, s>>>(g.h); LAUNCH(c); }
-        k_rng_ctx<<<1, 256, 0, s>>>(c->lc_rng.p, c->draws.p, g.seen.p, guard); LAUNCH(c);
+        if (c->rng_wait) { cudaStreamWaitEvent(s, c->ev_rng, 0); c->rng_wait = false; }
+        else { k_rng_ctx<<<1, 256, 0, s>>>(c->lc_rng.p, c->draws.p, g.seen.p, guard); LAUNCH(c); }
         k_mrg_walk<<<1, 256, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, g.kbsum.p + (g.h.n_pt + 1023) / 1024, g.out.p, guard); LAUNCH(c);
         k_mrg_apply<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); KEND(c); }
       else if (!c->mp.on) { k_rng_ctx<<<1, 256, 0, s>>>(c->lc_rng.p, c->draws.p, c->mg.seen.p, guard); LAUNCH(c); }
@@ -1172,8 +1186,11 @@ static int step_back(symgpu_ctx* c) {
                                                                                 c->next_sortie.p, c->t, c->P.dt, c->P.duree, guard); }
       KEND(c);
       if (c->mg.on && c->mg.h.n_sens > 0) { auto& g = c->mg;                  // merge sensors (reseau.cpp:14425-14458): rotate the windows, count the crossings of the step
-        KBEGIN(c, KID_MERGE); k_mrg_rotate<<<G(g.n_rows), B, 0, s>>>(g.h, g.n_upd + 1, g.n_rows, g.row_sens.p, guard); LAUNCH(c);
-        k_mrg_sensors<<<G(n), B, 0, s>>>(c->dn, c->dv, g.h, n, c->f_posidx.p, c->order.p, c->rows.p, g.n_upd + 1, guard); KEND(c); }
+        const bool side = c->profile != 1; cudaStream_t q = side ? c->aux2 : s;       // beside the next step's lane ordering (step_back waits for ev_sens)
+        KBEGIN(c, KID_MERGE); if (side) { cudaEventRecord(c->ev_fork, s); cudaStreamWaitEvent(q, c->ev_fork, 0); }
+        k_mrg_rotate<<<G(g.n_rows), B, 0, q>>>(g.h, g.n_upd + 1, g.n_rows, g.row_sens.p); LAUNCH(c);
+        k_mrg_sensors<<<G(n), B, 0, q>>>(c->dn, c->dv, g.h, n, g.n_upd + 1); LAUNCH(c);
+        if (side) { cudaEventRecord(c->ev_sens, q); c->sens_wait = true; } KEND0(c); }
     }
     cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(c->h_stat + 7, c->draws.p, sizeof(unsigned), cudaMemcpyDeviceToHost, s);

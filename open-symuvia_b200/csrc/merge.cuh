@@ -54,9 +54,10 @@ struct DevMrg {
   int *own_min, *own_max;                                                  // per vehicle slot: lowest / highest point that touches it
   int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw, *flist; double* proba;   // per point, this step; flist: the points the walk must visit (unordered)
   int* res;                                                               // per point: 1 inserted, 2 refused this step (summed by k_mrg_apply)
+  int* sens_go;                                                           // update count the sensor kernel may run for (set by k_mrg_apply once the step is certain)
   int *dlist, *n_dirty; unsigned long long* mark;                         // points that share a vehicle with another point; per vehicle: (round << 32 | ~point) of the lowest unfinished point touching it
   unsigned long long *kf, *kfo; int *fsorted, *rbuf; int rbuf_cap;                       // kf: per point, draws known before the walk (low 40 bits) | visit flag (bit 40); kfo: its exclusive scan = offset in the stream | rank in the visit list
-  int *nused, *nvoie;                                                      // per vehicle: intermediate lanes used this step; m_pNextVoie (sticky)
+  int *nused, *nvoie, *ulanes;                                             // per vehicle: intermediate lanes used this step (count, first three of them); m_pNextVoie (sticky)
   double* mrgx;                                                            // per order position: phase A -> phase B side record (6 doubles)
   DevRng* rng; unsigned* draws;                                            // the stream (device copy) and the cumulative count of count-only draws
   long long* counters;
@@ -379,6 +380,7 @@ __device__ inline void mrg_load(const DevMrg* M, int p, int hdr, MrgA* a) {
 // started the step ON the lane are found in its slice, vehicule_en_attente).
 __device__ inline void mrg_register(const DevNet& n, const DevMrg* M, int i, int p, const int* lanes, int kf) {
   M->nused[i] = kf > 0 ? kf - 1 : 0;
+  for (int k = 1; k < kf && k <= 3; k++) M->ulanes[i * 3 + k - 1] = lanes[k];               // for the sensor counts at the end of the step (k_mrg_sensors)
   if (p < 0) return;
   for (int k = 1; k < kf; k++) if (M->link_cvg[n.lane_link[lanes[k]]] >= 0) atomicMax(&M->cand_up[lanes[k]], p);
 }
@@ -917,6 +919,7 @@ __global__ void k_mrg_apply(DevNet N, DevVeh V, DevMrg M, const int* order, cons
   if (guard && *guard == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   int res = 0;
+  if (p == 0) *M.sens_go = n_upd + 1;
   if (p < M.n_pt) {
     if (M.st[p] == MS_VALUES) { const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
       MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; merge_point(W, p, MM_DECIDED, A, nullptr); }
@@ -929,8 +932,8 @@ __global__ void k_mrg_apply(DevNet N, DevVeh V, DevMrg M, const int* order, cons
 }
 // Reseau::UpdateConvergents reseau.cpp:2432-2600 (integer counts) after SensorsManager::UpdateTabNbVeh (:462-527): the slot the
 // rotation exposes is cleared first (k_mrg_rotate), then every vehicle left on the network counts where it crossed a sensor.
-__global__ void k_mrg_rotate(DevMrg M, int n_upd_after, int n_rows, const int* row_sens, const int* guard) {
-  if (guard && *guard == 0) return;
+__global__ void k_mrg_rotate(DevMrg M, int n_upd_after, int n_rows, const int* row_sens) {
+  if (*M.sens_go != n_upd_after) return;                                                   // the step was not finished by this pass (relaxation still open)
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const int s = row_sens[2 * r]; const int win = M.sens_win[s];
@@ -941,8 +944,8 @@ __device__ inline void sens_hit(const DevNet& N, const DevMrg& M, int s, int cls
   const int last = min(n_upd_after - 1, win - 1); const int head = max(0, n_upd_after - win) % max(1, win);
   if (last >= 0) atomicAdd(&M.cnt[M.sens_cnt0[s] + (cls * nl + N.lane_num[lane]) * win + (head + last) % win], 1);
 }
-__global__ void k_mrg_sensors(DevNet N, DevVeh V, DevMrg M, int n, const int* posidx, const int* order, const double* rows, int n_upd_after, const int* guard) {
-  if (guard && *guard == 0) return;
+__global__ void k_mrg_sensors(DevNet N, DevVeh V, DevMrg M, int n, int n_upd_after) {
+  if (*M.sens_go != n_upd_after) return;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= n || V.status[x] != ST_ALIVE) return;                                           // after k_final: the vehicles still on the network; index n = end of this step
   const double p0 = V.pos_n[x];
@@ -954,13 +957,10 @@ __global__ void k_mrg_sensors(DevNet N, DevVeh V, DevMrg M, int n, const int* po
     if (p1 < xs && (p0 >= xs || k1 != k0)) sens_hit(N, M, s, cls, l1, n_upd_after); }
   if (k1 != k0) {
     for (int q = M.lsens0[k0]; q < M.lsens0[k0 + 1]; q++) { const int s = M.lsens[q]; if (p0 >= M.sens_pos[s]) sens_hit(N, M, s, cls, l0, n_upd_after); }
-    const int nu = M.nused[x];
-    if (nu > 0) { int lanes[kMrgLanes]; int nl = 0;
-      const int p = posidx[x]; const Row r = row_at(rows, p); const int hn = (hi32(r[R_I0]) >> 8) & 15;
-      if (order[p] == x && hn <= kRowLanes) { nl = hn; for (int k = 0; k < nl; k++) lanes[k] = lo32(r[R_REC + kRecD * k + 4]); }
-      else { nl = V.ctx_nl[x]; for (int k = 0; k < nl; k++) lanes[k] = V.ctx_lane[x * kMaxCtx + k]; }
-      for (int k = 1; k <= nu && k < nl; k++) { const int kk = N.lane_link[lanes[k]];
-        for (int q = M.lsens0[kk]; q < M.lsens0[kk + 1]; q++) sens_hit(N, M, M.lsens[q], cls, lanes[k], n_upd_after); } }
+    const int nu = M.nused[x];                                                              // the intermediate lanes (Vehicule::m_LstUsedLanes) as they stand after the merge points
+    for (int k = 0; k < nu && k < 3; k++) { const int ln = M.ulanes[x * 3 + k]; const int kk = N.lane_link[ln];
+      for (int q = M.lsens0[kk]; q < M.lsens0[kk + 1]; q++) sens_hit(N, M, M.lsens[q], cls, ln, n_upd_after); }
+    if (nu > 3) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL);
   }
 }
 
