@@ -524,7 +524,7 @@ struct symgpu_ctx {
   struct Mrg { bool on = false; int n_upd = 0, n_rows = 0; DevMrg h; DBuf<DevMrg> d;
     DBuf<int> link_cvg, cvg_node, cvg_down, cvg_pt0, cvg_npt, cvg_am0, cvg_nam, cvg_win, cvg_sens0, cvg_am, pt_cvg, pt_down, pt_vam0, pt_nvam, pt_mode, pt_pm0, vam_lane, vam_ref, vam_niv,
         pm_vam, pm_sl, pm_occ0, pm_occ, lane_pt, lane_vam, sens_link, sens_cnt0, sens_win, cnt, lsens0, lsens, lcam0, lcam, lcav0, lcav, lmv0, lmv_ent, lmv_exit, fm0, fm_exit, fm_tl0, fm_ntl, fm_tl,
-        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, dlist, nused, nvoie, ulanes, row_sens, flag, out;
+        node_type, pt_rand, pt_free, cand_up, own_min, own_max, st, inv, ninv, pre, kmax, decide, ndraw, flist, fsorted, rbuf, res, dlist, nused, nvoie, ulanes, sens_row0, row_tot, row_sens, flag, out;
     DBuf<double> cvg_gamma, cvg_mu, cvg_poscpt, cvg_tf, sens_pos, pt_last, proba, mrgx; DBuf<unsigned> seen; DBuf<unsigned long long> kf, kfo, kbsum, mark; } mg;
   bool host_rng_fresh = true;                                      // the host copy of the random stream equals the device's
   std::vector<signed char> cls_of_id;                               // vehicle type by vehicle id (output writers)
@@ -791,7 +791,7 @@ static int build_merge(symgpu_ctx* c) {
   const int K = f.n_links(), L = f.n_lanes(), T = f.n_cls(), nc = f.n_cvg(), np = f.n_pt();
   g.on = nc > 0;
   std::vector<int> link_cvg(K, -1), cvg_node(nc), cvg_down(nc), cvg_pt0(nc), cvg_npt(nc), cvg_am0(nc), cvg_nam(nc), cvg_win(nc), cvg_sens0(nc), cvg_am;
-  std::vector<double> cvg_gamma(nc), cvg_mu(nc), cvg_poscpt(nc), sens_pos; std::vector<int> sens_link, sens_cnt0, sens_win, row_sens;
+  std::vector<double> cvg_gamma(nc), cvg_mu(nc), cvg_poscpt(nc), sens_pos; std::vector<int> sens_link, sens_cnt0, sens_win, row_sens, sens_row0;
   size_t cnt_total = 0;
   for (int k = 0; k < nc; k++) { const int* r = &f.cvg_i[8 * k]; cvg_node[k] = r[0]; cvg_down[k] = r[1]; cvg_pt0[k] = r[2]; cvg_npt[k] = r[3]; cvg_am0[k] = r[4]; cvg_nam[k] = r[5];
     cvg_gamma[k] = f.cvg_f[4 * k + 1]; cvg_mu[k] = f.cvg_f[4 * k + 2]; cvg_poscpt[k] = f.cvg_f[4 * k + 3];
@@ -799,7 +799,7 @@ static int build_merge(symgpu_ctx* c) {
     if (cvg_win[k] < 1) { g_err = "merge sensor window shorter than one time step"; return SYMGPU_E_UNSUPPORTED; }
     cvg_sens0[k] = (int)sens_link.size();
     auto add = [&](int link, double pos) { const int nl = f.link_i[8 * link + 1]; const int s = (int)sens_link.size();
-      sens_link.push_back(link); sens_pos.push_back(pos); sens_win.push_back(cvg_win[k]); sens_cnt0.push_back((int)cnt_total);
+      sens_link.push_back(link); sens_pos.push_back(pos); sens_win.push_back(cvg_win[k]); sens_cnt0.push_back((int)cnt_total); sens_row0.push_back((int)row_sens.size() / 2);
       for (int q = 0; q < T * nl; q++) { row_sens.push_back(s); row_sens.push_back(q); }
       cnt_total += (size_t)T * nl * cvg_win[k]; };
     add(cvg_down[k], cvg_poscpt[k]);                                                       // "CptTav" (FinInit :239)
@@ -872,7 +872,7 @@ static int build_merge(symgpu_ctx* c) {
   CK(g.cvg_poscpt.upload(cvg_poscpt)); CK(g.cvg_tf.upload(f.cvg_tf)); CK(g.pt_cvg.upload(pt_cvg)); CK(g.pt_down.upload(pt_down)); CK(g.pt_vam0.upload(pt_vam0)); CK(g.pt_nvam.upload(pt_nvam));
   CK(g.pt_mode.upload(pt_mode)); CK(g.pt_pm0.upload(pt_pm0)); CK(g.vam_lane.upload(vam_lane)); CK(g.vam_ref.upload(vam_ref)); CK(g.vam_niv.upload(vam_ref)); CK(g.pm_vam.upload(pm_vam)); CK(g.pm_sl.upload(pm_sl));
   CK(g.pm_occ0.upload(pm_occ0)); CK(g.pm_occ.upload(pm_occ)); CK(g.lane_pt.upload(lane_pt)); CK(g.lane_vam.upload(lane_vam)); CK(g.sens_link.upload(sens_link)); CK(g.sens_cnt0.upload(sens_cnt0));
-  CK(g.sens_win.upload(sens_win)); CK(g.sens_pos.upload(sens_pos)); CK(g.cnt.alloc(std::max<size_t>(1, cnt_total))); CK(g.lsens0.upload(lsens0)); CK(g.lsens.upload(lsens));
+  CK(g.sens_win.upload(sens_win)); { if (sens_row0.empty()) sens_row0.push_back(0); CK(g.sens_row0.upload(sens_row0)); CK(g.row_tot.alloc(std::max<size_t>(1, row_sens.size() / 2))); } CK(g.sens_pos.upload(sens_pos)); CK(g.cnt.alloc(std::max<size_t>(1, cnt_total))); CK(g.lsens0.upload(lsens0)); CK(g.lsens.upload(lsens));
   CK(g.lcam0.upload(f.lcam_off)); CK(g.lcam.upload(lcam_l)); CK(g.lcav0.upload(f.lcav_off)); CK(g.lcav.upload(lcav_l)); CK(g.lmv0.upload(lmv0)); CK(g.lmv_ent.upload(lmv_ent)); CK(g.lmv_exit.upload(lmv_exit));
   CK(g.fm0.upload(fm0)); CK(g.fm_exit.upload(fm_exit)); CK(g.fm_tl0.upload(fm_tl0)); CK(g.fm_ntl.upload(fm_ntl)); CK(g.fm_tl.upload(fm_tl)); CK(g.node_type.upload(node_type)); CK(g.row_sens.upload(row_sens));
   g.n_rows = (int)row_sens.size() / 2; if (sens_link.empty()) g.n_rows = 0;
@@ -890,7 +890,7 @@ static int build_merge(symgpu_ctx* c) {
   h.cvg_sens0 = g.cvg_sens0.p; h.cvg_am = g.cvg_am.p; h.cvg_gamma = g.cvg_gamma.p; h.cvg_mu = g.cvg_mu.p; h.cvg_poscpt = g.cvg_poscpt.p; h.cvg_tf = g.cvg_tf.p;
   h.pt_cvg = g.pt_cvg.p; h.pt_down = g.pt_down.p; h.pt_vam0 = g.pt_vam0.p; h.pt_nvam = g.pt_nvam.p; h.pt_mode = g.pt_mode.p; h.pt_pm0 = g.pt_pm0.p; h.vam_lane = g.vam_lane.p; h.vam_ref = g.vam_ref.p; h.vam_niv = g.vam_niv.p;
   h.pm_vam = g.pm_vam.p; h.pm_sl = g.pm_sl.p; h.pm_occ0 = g.pm_occ0.p; h.pm_occ = g.pm_occ.p; h.lane_pt = g.lane_pt.p; h.lane_vam = g.lane_vam.p;
-  h.sens_link = g.sens_link.p; h.sens_cnt0 = g.sens_cnt0.p; h.sens_pos = g.sens_pos.p; h.cnt = g.cnt.p; h.sens_win = g.sens_win.p; h.lsens0 = g.lsens0.p; h.lsens = g.lsens.p;
+  h.sens_link = g.sens_link.p; h.sens_cnt0 = g.sens_cnt0.p; h.sens_pos = g.sens_pos.p; h.cnt = g.cnt.p; h.sens_win = g.sens_win.p; h.sens_row0 = g.sens_row0.p; h.row_tot = g.row_tot.p; h.lsens0 = g.lsens0.p; h.lsens = g.lsens.p;
   h.lcam0 = g.lcam0.p; h.lcam = g.lcam.p; h.lcav0 = g.lcav0.p; h.lcav = g.lcav.p; h.lmv0 = g.lmv0.p; h.lmv_ent = g.lmv_ent.p; h.lmv_exit = g.lmv_exit.p;
   h.fm0 = g.fm0.p; h.fm_exit = g.fm_exit.p; h.fm_tl0 = g.fm_tl0.p; h.fm_ntl = g.fm_ntl.p; h.fm_tl = g.fm_tl.p; h.node_type = g.node_type.p;
   h.pt_last = g.pt_last.p; h.pt_rand = g.pt_rand.p; h.pt_free = g.pt_free.p; h.cand_up = g.cand_up.p; h.own_min = g.own_min.p; h.own_max = g.own_max.p;
@@ -1190,6 +1190,7 @@ static int step_back(symgpu_ctx* c) {
         KBEGIN(c, KID_MERGE); if (side) { cudaEventRecord(c->ev_fork, s); cudaStreamWaitEvent(q, c->ev_fork, 0); }
         k_mrg_rotate<<<G(g.n_rows), B, 0, q>>>(g.h, g.n_upd + 1, g.n_rows, g.row_sens.p); LAUNCH(c);
         k_mrg_sensors<<<G(n), B, 0, q>>>(c->dn, c->dv, g.h, n, g.n_upd + 1); LAUNCH(c);
+        k_mrg_sensors_sum<<<G(g.n_rows), B, 0, q>>>(g.h, g.n_upd + 1, g.n_rows, g.row_sens.p); LAUNCH(c);
         if (side) { cudaEventRecord(c->ev_sens, q); c->sens_wait = true; } KEND0(c); }
     }
     cudaMemcpyAsync(c->h_stat + 4, &c->stat.p[4], 3 * sizeof(int), cudaMemcpyDeviceToHost, s);

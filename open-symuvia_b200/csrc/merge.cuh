@@ -43,7 +43,7 @@ struct DevMrg {
   const int *pm_vam, *pm_sl, *pm_occ0, *pm_occ;                            // movements of the junction that pass through a point
   const int *lane_pt, *lane_vam;                                           // upstream lane -> its point (first in cvg order) and entry
   const int *sens_link, *sens_cnt0; const double* sens_pos; int* cnt;      // ponctual sensors; cnt: [type][lane][window] ring per sensor
-  const int *sens_win;
+  const int *sens_win; const int* sens_row0; int* row_tot;                 // row_tot[sens_row0[s] + type * n_lanes + lane]: the window sum the next step reads (k_mrg_sensors_sum)
   const int *lsens0, *lsens;                                               // link -> sensors (Tuyau::getListeCapteursConvergents)
   const int *lcam0, *lcam, *lcav0, *lcav;                                  // connections: m_LstTuyAm / m_LstTuyAv
   const int *lmv0, *lmv_ent, *lmv_exit;                                    // internal link -> (entry link, exit link) of its movements
@@ -257,10 +257,8 @@ __device__ inline int capteur_of(const MrgView& W, int c, int link) {           
 __device__ inline int nb_inst_of(int n_upd, int win) { return n_upd == 0 ? -1 : min(n_upd - 1, win - 1); }
 __device__ inline double cpt_somme(const MrgView& W, int s, int nvoie, int type) {
   const int link = W.M.sens_link[s]; const int nl = W.N.link_nl[link]; if (nvoie < 0 || nvoie >= nl) return 0;
-  const int win = W.M.sens_win[s]; const int kmax = min(nb_inst_of(W.n_upd, win), win); const int head = max(0, W.n_upd - win) % max(1, win);
-  double sum = 0;
-  for (int t = 0; t < W.M.n_cls; t++) if (type < 0 || t == type) { const int* a = W.M.cnt + W.M.sens_cnt0[s] + (t * nl + nvoie) * win;
-    for (int j = 0; j < kmax; j++) sum += (double)a[(head + j) % win]; }
+  double sum = 0;                                                                           // window sums are kept per (sensor, type, lane): counts are integers, any order of addition is exact
+  for (int t = 0; t < W.M.n_cls; t++) if (type < 0 || t == type) sum += (double)W.M.row_tot[W.M.sens_row0[s] + t * nl + nvoie];
   return sum;
 }
 __device__ inline double debit_moyen(const MrgView& W, int s, int nvoie) { if (s < 0) return 0; const int win = W.M.sens_win[s];
@@ -663,7 +661,12 @@ __global__ void k_mrg_classify(DevMrg M, const int* guard) {
   if (st == MS_NONE) return;
   bool clean = st != MS_OVERFLOW;
   for (int k = 0; k < M.ninv[p] && clean; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p) clean = false; }
-  if (!clean) { M.st[p] = MS_DIRTY; M.kf[p] = 1ULL << 40; M.dlist[atomicAdd(M.n_dirty, 1)] = p; return; }   // visited by the walk unless k_mrg_dirty settles it
+  if (!clean) { M.st[p] = MS_DIRTY; M.kf[p] = 1ULL << 40; const int dpos = atomicAdd(M.n_dirty, 1); M.dlist[dpos] = p;
+#ifdef SYM_MRG_DEBUG
+    if (dpos < 6) { for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p)
+      printf("dirty pt %d (down lane %d, nvam %d) inv[%d of %d] veh slot %d shared with points %d..%d\n", p, M.pt_down[p], M.pt_nvam[p], k, M.ninv[p], x, M.own_min[x], M.own_max[x]); } }
+#endif
+    return; }   // visited by the walk unless k_mrg_dirty settles it
   if (st == MS_VALUES) M.kf[p] |= 1ULL << 40;                                                // decided by the walk, applied by k_mrg_apply
 }
 __global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start, const int* lane_count,
@@ -938,6 +941,16 @@ __global__ void k_mrg_rotate(DevMrg M, int n_upd_after, int n_rows, const int* r
   if (r >= n_rows) return;
   const int s = row_sens[2 * r]; const int win = M.sens_win[s];
   if (n_upd_after > win) M.cnt[M.sens_cnt0[s] + row_sens[2 * r + 1] * win + (n_upd_after - win - 1) % win] = 0;
+}
+// after the counts of the step: what SensorsManager::GetDebitMoyen / GetNbVehTotal will sum during the next step (logical slots [0, min(m_nNbInst, W)))
+__global__ void k_mrg_sensors_sum(DevMrg M, int n_upd_after, int n_rows, const int* row_sens) {
+  if (*M.sens_go != n_upd_after) return;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const int s = row_sens[2 * r]; const int win = M.sens_win[s]; const int kmax = min(nb_inst_of(n_upd_after, win), win); const int head = max(0, n_upd_after - win) % max(1, win);
+  const int* a = M.cnt + M.sens_cnt0[s] + row_sens[2 * r + 1] * win; int sum = 0;
+  for (int j = 0; j < kmax; j++) sum += a[(head + j) % win];
+  M.row_tot[r] = sum;
 }
 __device__ inline void sens_hit(const DevNet& N, const DevMrg& M, int s, int cls, int lane, int n_upd_after) {
   const int win = M.sens_win[s]; const int nl = N.link_nl[M.sens_link[s]];

@@ -1,5 +1,5 @@
 """Ad-hoc: parity over random small grids (signals, demand, pre-seeded population, shuffled list order, 1-2 vehicle types):
-python tests/try_grid_fuzz.py [n_cases] [first_seed]"""
+python tools/fuzz_grid.py [n_cases] [first_seed]"""
 import importlib
 import os
 import sys

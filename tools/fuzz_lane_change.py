@@ -1,4 +1,4 @@
-"""Ad-hoc: lane-change parity over random corridor shapes and seeds:  python tests/try_lc_fuzz.py [n_cases] [first_seed]"""
+"""Ad-hoc: lane-change parity over random corridor shapes and seeds:  python tools/fuzz_lane_change.py [n_cases] [first_seed]"""
 import importlib
 import os
 import sys

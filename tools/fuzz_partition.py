@@ -1,5 +1,5 @@
 """Ad-hoc: partitioned runs (all ranks in one process, LocalGroup) against the oracle's partitioned mode over random grids:
-python tests/try_mp_fuzz.py [n_cases] [first_seed]"""
+python tools/fuzz_partition.py [n_cases] [first_seed]"""
 import importlib
 import os
 import sys
