@@ -72,3 +72,25 @@ def test_partitioned_grid_with_origins(pkg, synth, tmp_path, world):
     migrated, loops_gpu, loops_oracle = _run(pkg, synth, tmp_path, b, world, 220)
     assert migrated > 50
     assert loops_gpu == loops_oracle
+
+
+def test_nccl_two_ranks(tmp_path):
+    """The real multi-process path (partition.DistributedRun: one process per GPU, NCCL all_to_all of boundary tails and migrating
+    vehicles) against the oracle's partitioned mode, every step, bit for bit.  Needs two GPUs (skipped otherwise)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "mp.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29631",
+           os.path.join(root, "tools", "mp_parity_worker.py"), out, "80"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.load(open(out))
+    assert res["ok"], res
+    assert res["migrated"] > 20
