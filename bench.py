@@ -41,6 +41,10 @@ def make_workload(name: str, rank: int, world: int, path: str, partitioned: bool
         info["n_links"] = hdr["link_i"] // 8
         info["n_lanes"] = hdr["lane_i"] // 4
         return info
+    if name == "C3":        # BASELINE configs[2]: multi-lane multi-class arterial with lane changing, on-ramp Convergents and off-ramp distributors, ~100 k vehicles
+        b = synth.config("C3", km=1200, seed=42 + rank)
+        b.write(path)
+        return dict(n_init=len(b.iv_i), n_total=len(b.iv_i), n_classes=len(b.classes), n_links=len(b.links), n_lanes=len(b.lanes))
     tile = {"C4": 100, "C4small": 20}.get(name)
     if tile is None:
         raise SystemExit(f"unknown workload {name}")
@@ -112,21 +116,46 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_oracle_rate(path, info, steps, warmup=0):
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_oracle_rate(path, info, steps, warmup=0, repeats=1):
+    """vehicle-steps/s of the CPU oracle on ONE host core (the reference steps one network on one thread): `repeats` consecutive
+    samples of `steps` time steps each, the median rate is returned (median of 5)."""
     from oracle.binding import Oracle
     o = Oracle(path, info["n_links"], info["n_classes"])
     for _ in range(warmup):
         o.step()
-    tot = 0
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        tot += o.step()
-    dt = time.perf_counter() - t0
+    rates, tot_all, dt_all = [], 0, 0.0
+    for _ in range(repeats):
+        tot = 0
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            tot += o.step()
+        dt = time.perf_counter() - t0
+        rates.append(tot / dt)
+        tot_all += tot
+        dt_all += dt
     o.close()
-    return tot / dt, dt, tot
+    rates.sort()
+    return rates[len(rates) // 2], dt_all, tot_all
 
 
-NCU_DRAM_BYTES_PER_VEH_STEP = {"k_relax": 350.0, "k_context": 529.0}   # profiles/r1g_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)
+def measured_dram_bytes():
+    """{kernel group: DRAM bytes (read + write) per time step of C4} from the committed ncu capture (profiles/r2_dram_bytes.json, made by
+    tools/ncu_dram_summary.py from the CSV of `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`); {} when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r2_dram_bytes.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def main():
@@ -136,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C4")
-    ap.add_argument("--cpu-steps", type=int, default=10, help="oracle steps for cpu_baseline (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=15, help="oracle steps for cpu_baseline (bounded sample: 5 samples of cpu_steps / 5 steps)")
     ap.add_argument("--partitioned", action="store_true", help="N > 1: one merge-free network cut into N strips with NCCL exchange instead of N replicas")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -144,8 +173,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     warm = max(a.warmup, 3)
     base_cfg = {"workload": (f"{a.workload}: synthetic 100x100 signalised Manhattan grid per GPU, 200 m blocks, 2 lanes/dir, ~1M pre-seeded vehicles per GPU, "
-                             "Newell, dt=1 s, chgtvoie off (BASELINE.json configs[3])") if a.workload != "C5" else
-                            "C5: ONE synthetic 300x300 signalised Manhattan grid, ~10M pre-seeded vehicles in total, Newell, dt=1 s (BASELINE.json configs[4])",
+                             "Newell, dt=1 s, chgtvoie off, merge points at every junction exit (BASELINE.json configs[3])") if a.workload not in ("C5", "C3") else
+                            ("C5: ONE synthetic 300x300 signalised Manhattan grid, ~10M pre-seeded vehicles in total, Newell, dt=1 s (BASELINE.json configs[4])" if a.workload == "C5" else
+                             "C3: synthetic 1200 km 3-lane arterial, VL 85 % / PL 15 %, lane changing on, on-ramp Convergents and off-ramp distributors every km, ~100k vehicles pre-seeded + demand "
+                             "(BASELINE.json configs[2])"),
                 "working_set": "vehicle SoA + tables ~0.4 GB per GPU > 126 MB L2 (no L2 flush needed)"}
     path = f"/tmp/symuvia_bench_{a.workload}_{rank}.symflat"
 
@@ -154,12 +185,15 @@ def main():
         if rank != 0:
             return
         info = make_workload(a.workload, 0, 1, path)
-        rate, dt, tot = cpu_oracle_rate(path, info, a.steps, warmup=min(warm, 3))
+        rate, dt, tot = cpu_oracle_rate(path, info, a.steps, warmup=warm)
         line = {"impl": "reference", "metric": "vehicle-steps/sec", "value": rate, "unit": "vehicle-steps/s", "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": min(warm, 3), "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": dict(base_cfg, parallelism="1 host thread (the reference steps one network on one thread)"),
-                "cpu_baseline": {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port",
-                                 "sample": f"{a.steps} full time steps of {a.workload} ({tot} vehicle-steps)"},
+                "warmup": warm, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": dict(base_cfg, parallelism="1 GPU" if a.gpus == 1 else f"{a.gpus} replicas", merge_points=True, vehicles_per_gpu=info["n_init"], lanes_per_gpu=info["n_lanes"],
+                               reference_arm="CPU oracle (C++ restatement of the reference's algorithm: the reference itself cannot be built here), ONE host thread as the "
+                                             "reference steps a network, one C4 network whatever --gpus says: a RATE to compare with the per-GPU rate"),
+                "cpu_baseline": {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port", "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
+                                 "sample": f"{a.steps} full time steps of {a.workload} after {warm} warm-up steps ({tot} vehicle-steps, {dt:.1f} s)"},
                 "e2e": {"value": rate, "unit": "vehicle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
@@ -300,7 +334,8 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # DRAM bytes (read + write) of the dominant kernel's launches of one step, from the ncu --set full capture summarised in
             # profiles/r1g_summary.md (C4: k_relax 350 B, k_context 529 B per vehicle-step); other cases: not captured
-            "traffic": (NCU_DRAM_BYTES_PER_VEH_STEP[dom] * vsteps / max(1, a.steps) if dom in NCU_DRAM_BYTES_PER_VEH_STEP and a.workload == "C4" else None),
+            "traffic": (measured_dram_bytes().get(dom) if a.workload == "C4" and world == 1 else None),
+            "traffic_note": "DRAM bytes read + written by the group's launches of one C4 step, ncu capture committed as profiles/r2_dram_bytes.json (null: not captured for this workload)",
             "peak_source": peak_src, "launches_in_region": dom_launches, "avg_launch_ms": dom_ms / max(1, dom_launches),
             "alg_bytes_per_vehicle_step": B_ALG, "whole_step_frac": B_ALG * vsteps / (dev_ms / 1e3) / 1e9 / peak,
             "kernel_timed_in": dom_where,
@@ -321,9 +356,11 @@ def main():
             "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks, "roofline": roof,
             "loops_broken": g.counter(pkg.CNT_LOOPS), "follow_passes": g.counter(pkg.CNT_PASSES)}
     if rank == 0 and world == 1 and a.cpu_steps > 0:
-        rate, dt, tot = cpu_oracle_rate(path, info, a.cpu_steps)
-        line["cpu_baseline"] = {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port",
-                                "sample": f"first {a.cpu_steps} time steps of the same {a.workload} input ({tot} vehicle-steps, {dt:.1f} s)"}
+        per = max(1, a.cpu_steps // 5)
+        rate, dt, tot = cpu_oracle_rate(path, info, per, repeats=5)
+        line["cpu_baseline"] = {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port", "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
+                                "sample": f"median of 5 consecutive samples of {per} time steps of the same {a.workload} input ({tot} vehicle-steps, {dt:.1f} s in all); "
+                                          "the oracle keeps the reference's structure (id-ordered lane sets, linear neighbour scans, leader-first recursion), one thread"}
     if rank == 0:
         print(json.dumps(line))
     g.close()

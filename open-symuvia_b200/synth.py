@@ -832,7 +832,8 @@ def config(name: str, **kw) -> NetBuilder:
         return grid(n=10, n_steps=1800, demand_per_lane=0.2, demand_duration=1200.0, **kw)
     if name == "C3":    # 10 km arterial, 3 lanes, 2 classes, lane changing, on-ramp Convergents and off-ramp Repartiteurs every 1 km, ~0.06 veh/m/lane pre-seeded
         kw.setdefault("n_steps", 600)
-        return corridor(n_links=20, length=500.0, n_lanes=3, demand=1.2, offramp_every=2, offramp_share=0.1, onramp_every=2, onramp_demand=0.2,
+        km = kw.pop("km", 10)      # BASELINE.json quotes ~100 k vehicles: 0.06 veh/m/lane x 3 lanes needs ~550 km of such an arterial (km=550); km=10 is the geometry it names
+        return corridor(n_links=2 * km, length=500.0, n_lanes=3, demand=1.2, offramp_every=2, offramp_share=0.1, onramp_every=2, onramp_demand=0.2,
                         preseed_density=0.06, chgtvoie=True, **kw)
     if name == "C4":
         return grid(n=100, n_steps=300, demand_per_lane=0.0, preseed_per_lane=12.6, **kw)
