@@ -1200,7 +1200,7 @@ static int step_back(symgpu_ctx* c) {
   auto tally = [&](int nb, bool first_batch) -> bool {                   // counts the sweeps that changed something; true when one changed nothing
     bool done = false; int used = 0;
     for (int j = 1; j <= nb && !done; j++) { used = j; if (c->h_ctl->changed[j] == 0) done = true; else c->passes++; }
-    if (done && first_batch) c->relax_batch = std::min(kRelaxBatch, std::max(2, used + 1)); else if (!done) c->relax_batch = kRelaxBatch;
+    if (done && first_batch) c->relax_batch = std::min(kRelaxBatch, std::max(3, used + 2)); else if (!done) c->relax_batch = kRelaxBatch;   // one sweep of margin: a batch that falls short costs a host round trip
     return done;
   };
   const bool relax = n > 0 && n_sorted > 0;
