@@ -1,4 +1,6 @@
-"""DRAM traffic per kernel group and time step from an ncu CSV (profiles/): python tools/ncu_dram_summary.py launches.csv n_steps out.json
+"""DRAM traffic per kernel group and time step from an ncu CSV (profiles/): python tools/ncu_dram_summary.py launches.csv out.json
+
+Only whole time steps count: the launches between the first and the last k_reset (the first kernel of a step) of the capture.
 
 The CSV comes from
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --launch-skip S -c N --csv ...
@@ -21,7 +23,7 @@ def group_of(name):
 
 
 def main():
-    path, n_steps, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    path, out = sys.argv[1], sys.argv[-1]
     rows = list(csv.reader(open(path)))
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     H = rows[hdr]
@@ -29,8 +31,12 @@ def main():
     idi = H.index("ID")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "nsecond": 1.0, "msecond": 1e6}
     per = {}
+    marks = sorted({int(r[idi]) for r in rows[hdr + 1:] if len(r) > vi and r[idi].isdigit() and "k_reset" in r[ki]})
+    if len(marks) < 2:
+        raise SystemExit("the capture holds no whole time step")
+    n_steps = len(marks) - 1
     for r in rows[hdr + 1:]:
-        if len(r) <= vi or not r[idi].isdigit():
+        if len(r) <= vi or not r[idi].isdigit() or not (marks[0] <= int(r[idi]) < marks[-1]):
             continue
         g = group_of(r[ki])
         v = float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0)
@@ -45,6 +51,7 @@ def main():
               for g, d in per.items()}
     json.dump(res, open(out, "w"), indent=1, sort_keys=True)
     json.dump(detail, open(out.replace(".json", "_detail.json"), "w"), indent=1, sort_keys=True)
+    print(f"{n_steps} whole steps, launches {marks[0]}..{marks[-1] - 1}")
     for g in sorted(detail, key=lambda k: -detail[k]["ncu_time_us_per_step"]):
         print(f"{g:16s} {detail[g]['dram_bytes_per_step'] / 1e6:9.1f} MB/step {detail[g]['ncu_time_us_per_step']:8.1f} us/step {detail[g]['launches_per_step']:5.1f} launches/step")
 
