@@ -3,17 +3,20 @@
 // struct-of-arrays live in HBM; one call to symgpu_step() replaces Reseau::SimuTrafic phases
 // InitVehicules .. SupprimeVehicules (symuvia/src/reseau.cpp:2250-2258, :14152-14470).
 //
-// Step pipeline (all on one stream, no host round trip unless the network has origins):
+// Step pipeline (step stream + two side streams joined by events; one host synchronisation per step, on the relaxation's verdict):
 //   k_signals      A8   per stop line: colour + green fraction of this step (ControleurDeFeux.cpp:96-148)
-//   k_prepare      A2   per vehicle : lane membership histogram          (reseau.cpp:3901-3976)
-//   scan + k_scatter + k_lane_rank/links  A3: counting sort by lane, in-lane order by (position, id), own-lane
-//                       leader links, lane tail                          (reseau.cpp:3583-3820)
-//   k_context      A3/A5/A12 per vehicle: context lanes, leader, deltaN, free-flow distance
-//   k_follow_pass  A4-A7 per lane  : ordered chain front -> back (leader first, vehicule.cpp:1304-1309);
-//                       wavefront passes over the "lane head follows another lane's tail" dependency
-//   k_break_loop   A4   leader-recursion loop breaking                   (vehicule.cpp:1201-1216)
-//   k_entries      N1   first waiting vehicle of each origin lane        (usage/SymuViaTripNode.cpp:1642-1851)
-//   k_final        A13  finalisation, link counters, exits               (vehicule.cpp:4254-4583, reseau.cpp:3984)
+//   k_mrg_rank     A10  per merge point: priority levels inside signalised junctions (CarrefourAFeuxEx.cpp:1386-1593)
+//   k_reset/k_prepare/scan/k_scatter/k_lane_rank/k_lane_links  A2/A3: counting sort by lane, in-lane order by (position, id),
+//                       own-lane leader links, lane tail                  (reseau.cpp:3901-3976, :3583-3820)
+//   k_lc_*         A9   lane changing, only when the scenario enables it  (reseau.cpp:4219-4330)
+//   k_context      A3/A5/A12 per vehicle: context lanes, leader, deltaN, free-flow distance -> 256-byte row (rows.cuh)
+//   k_seg, k_cyc_* A4   segments of the leader graph, loops cut where the reference's recursion cuts them (vehicule.cpp:1201-1216)
+//   k_relax        A4-A7 chaotic relaxation of phase B to its unique fixed point (flow.cuh)
+//   k_place        A4   placement on the context lanes                    (vehicule.cpp:1367-1527)
+//   k_entries      N1   first waiting vehicle of each origin lane         (usage/SymuViaTripNode.cpp:1642-1851)
+//   k_mrg_probe .. k_mrg_apply  A10 merge points in Convergent id order   (merge.cuh; convergent.cpp:333-990)
+//   k_final        A13  finalisation, link counters, exits                (vehicule.cpp:4254-4583, reseau.cpp:3984)
+//   k_mrg_rotate/sensors/sensors_sum  A10 merge sensors, beside the next step's lane ordering (reseau.cpp:2432-2600)
 // There is no CPU fallback: without a CUDA device symgpu_create() fails.
 #include <cuda_runtime.h>
 

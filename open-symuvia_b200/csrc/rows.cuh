@@ -6,9 +6,9 @@
 //            "stop at lane end" rule, exit-capacity instant and THE stop line of the vehicle's movement with its
 //            colour and green fraction.  Packed into one 256-byte row per vehicle, stored at the vehicle's
 //            position in the lane order, so the rows of a segment are contiguous.
-//   phase B  (k_flow, dependency order) the leader's new speed -> congested distance -> min with the free-flow
-//            distance -> clamps -> travelled distance and speed.  Only reads the row (staged in shared memory)
-//            and the leader's speed.  NewellCarFollowing.cpp:204-398, vehicule.cpp:1317-1365, :1591-1708, :1799-1945.
+//   phase B  (k_relax, flow.cuh: relaxation over the cut leader graph) the leader's new speed -> congested distance -> min
+//            with the free-flow distance -> clamps -> travelled distance and speed.  Only reads the row and the leader's
+//            current new speed.  NewellCarFollowing.cpp:204-398, vehicule.cpp:1317-1365, :1591-1708, :1799-1945.
 //   phase C  (k_place, parallel)  acceleration, placement on the context lanes, destination test, bookkeeping.
 //            vehicule.cpp:1367-1527.
 // Every formula is evaluated with the same operations in the same order as follow_one() (micro.cuh), which stays
