@@ -34,6 +34,57 @@ __device__ inline int rng_next(DevRng* r) {                            // RandMa
   for (;;) { unsigned v = rng_raw(r) / bucket; if (v <= 32766u) return (int)v; }
 }
 
+// advances a state held in shared memory: a twist of the 624 words has four dependency phases (words 0..226 only need old words,
+// 227..453 need the new 0..226, 454..622 the new 227..453, word 623 the new 0 and 396); the tempered outputs of a block of words are
+// produced in parallel and a rejected value (4 in 2^32) sends that block through a serial compaction.
+struct MtShared { unsigned mt[624]; unsigned nw[624]; int idx; unsigned count; };
+__device__ inline void mt_twist(MtShared& S) {
+  const int tid = threadIdx.x;
+  auto f = [&](const unsigned* lo, const unsigned* hi, const unsigned* far) { const unsigned y = (*lo & 0x80000000u) | (*hi & 0x7fffffffu); return *far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); };
+  if (tid < 227) S.nw[tid] = f(&S.mt[tid], &S.mt[tid + 1], &S.mt[tid + 397]);
+  __syncthreads();
+  if (tid < 227) S.nw[227 + tid] = f(&S.mt[227 + tid], &S.mt[228 + tid], &S.nw[tid]);
+  __syncthreads();
+  if (tid < 169) S.nw[454 + tid] = f(&S.mt[454 + tid], &S.mt[455 + tid], &S.nw[227 + tid]);
+  __syncthreads();
+  if (tid == 0) S.nw[623] = f(&S.mt[623], &S.nw[0], &S.nw[396]);
+  __syncthreads();
+  for (int i = tid; i < 624; i += blockDim.x) S.mt[i] = S.nw[i];
+  __syncthreads();
+}
+// consume `n` accepted draws; out != nullptr: their values are stored (out[0..n))
+__device__ inline void rng_advance(MtShared& S, unsigned n, int* out) {
+  const int tid = threadIdx.x; const unsigned bucket = 0xFFFFFFFFu / 32767u;
+  unsigned left = n, written = 0; int idx = S.idx;                        // uniform over the block
+  while (left > 0) {
+    if (idx >= 624) { mt_twist(S); idx = 0; }
+    const unsigned m = min(left, (unsigned)(624 - idx));
+    int rej = 0; unsigned vals[3]; int nv = 0;
+    for (unsigned k = tid; k < m; k += blockDim.x) { unsigned y = S.mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+      const unsigned v = y / bucket; vals[nv++] = v; if (v > 32766u) rej++; }
+    const int nrej = __syncthreads_count(rej);
+    if (nrej == 0) { if (out) { int q = 0; for (unsigned k = tid; k < m; k += blockDim.x) out[written + k] = (int)vals[q++]; } written += m; left -= m; }
+    else { if (out && tid == 0) { unsigned w = written; for (unsigned k = 0; k < m; k++) { unsigned y = S.mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+          const unsigned v = y / bucket; if (v <= 32766u) out[w++] = (int)v; } }
+      written += m - nrej; left -= m - nrej; }
+    idx += (int)m;
+  }
+  __syncthreads();
+  if (tid == 0) { S.idx = idx; S.count += n; }
+  __syncthreads();
+}
+__device__ inline void mt_load(MtShared& S, const DevRng* r) { for (int k = threadIdx.x; k < 624; k += blockDim.x) S.mt[k] = r->mt[k]; if (threadIdx.x == 0) { S.idx = r->idx; S.count = r->count; } __syncthreads(); }
+__device__ inline void mt_store(const MtShared& S, DevRng* r) { __syncthreads(); for (int k = threadIdx.x; k < 624; k += blockDim.x) r->mt[k] = S.mt[k]; if (threadIdx.x == 0) { r->idx = S.idx; r->count = S.count; } }
+// one draw by a single thread from a state in shared memory (the rare case where the look-ahead buffer runs dry inside an event)
+__device__ inline int mt_next_serial(MtShared& S) {
+  const unsigned bucket = 0xFFFFFFFFu / 32767u;
+  for (;;) {
+    if (S.idx >= 624) { for (int i = 0; i < 624; i++) { unsigned y = (S.mt[i] & 0x80000000u) | (S.mt[(i + 1) % 624] & 0x7fffffffu); S.mt[i] = S.mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); } S.idx = 0; }
+    unsigned y = S.mt[S.idx++]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    const unsigned v = y / bucket; if (v <= 32766u) { S.count++; return (int)v; }
+  }
+}
+
 struct DevLc {
   const int *order, *lane_start, *lane_count;
   int *vdes, *voies_ok, *chgt, *delta_next, *link_delta_head, *moved; const int* posidx; const double* spos;   // spos: the lane order's sort keys (k_lane_rank)
@@ -83,7 +134,11 @@ __global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
 
 // ---- the sequential part (one thread) ----------------------------------------------------------------------------------
 // rb..srng: k_lc_walk draws through a buffer of upcoming values kept in shared memory (all null elsewhere: direct draws)
-struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; int* rb = nullptr; int* rb_pos = nullptr; int* rb_fill = nullptr; int* rb_base = nullptr; DevRng* srng = nullptr; };
+constexpr int kSnap = 384;
+// the vehicles currently on one link, copied to shared memory by k_lc_walk around a commit: the neighbour queries of that link
+// then scan this copy instead of chasing the lane slices through global memory
+struct LcSnap { int link, n; int v[kSnap], lane[kSnap], id[kSnap], prev[kSnap]; double p[kSnap]; };
+struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; int* rb = nullptr; int* rb_pos = nullptr; int* rb_fill = nullptr; int* rb_base = nullptr; MtShared* srng = nullptr; LcSnap* snap = nullptr; };
 constexpr int kRb = 2048;
 // make at least `need` upcoming draws available in the buffer (one thread)
 __device__ inline void lc_fill(const LcView& W, int need) {
@@ -91,8 +146,21 @@ __device__ inline void lc_fill(const LcView& W, int need) {
   if (fill - pos >= need) return;
   for (int k = pos; k < fill; k++) W.rb[k - pos] = W.rb[k];
   *W.rb_base += pos; fill -= pos; pos = 0;
-  while (fill < kRb) W.rb[fill++] = rng_next(W.srng);
+  while (fill < kRb) W.rb[fill++] = mt_next_serial(*W.srng);
   *W.rb_pos = pos; *W.rb_fill = fill;
+}
+// the same by the whole block (call sites are uniform; the buffer words were last written before a barrier)
+__device__ inline void lc_fill_block(const LcView& W, int need) {
+  const int pos = *W.rb_pos, fill = *W.rb_fill;
+  if (fill - pos >= need) return;
+  const int rem = fill - pos; int keep[(kRb + 255) / 256]; int nk = 0;
+  for (int k = threadIdx.x; k < rem; k += blockDim.x) keep[nk++] = W.rb[pos + k];
+  __syncthreads();
+  nk = 0; for (int k = threadIdx.x; k < rem; k += blockDim.x) W.rb[k] = keep[nk++];
+  __syncthreads();
+  rng_advance(*W.srng, (unsigned)(kRb - rem), W.rb + rem);
+  if (threadIdx.x == 0) { *W.rb_base += pos; *W.rb_pos = 0; *W.rb_fill = kRb; }
+  __syncthreads();
 }
 __device__ inline int lc_draw(const LcView& W) {                       // RandManager::myRand in list order
   if (!W.rb) return rng_next(W.C.rng);
@@ -160,7 +228,55 @@ __device__ inline int pick_first(const LcView& W, int* c, int n) {
     bool found = false; for (int j = 0; j < n && !found; j++) if (i != j && W.V.id[c[j]] == ld) found = true; if (!found) return c[i]; }
   return c[n - 1];
 }
+// ---- the same queries over the shared-memory copy of a link (LcSnap): every vehicle of the lane is visited, the filters are the same
+__device__ __forceinline__ bool snap_has(const LcView& W, int lane) { return W.snap && W.snap->link == W.N.lane_link[lane]; }
+__device__ inline int snap_pick_last(const LcSnap& S, int* c, int n) {
+  if (n == 0) return -1;
+  if (n == 1) return S.v[c[0]];
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (S.id[c[j]] < S.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
+  for (int i = 0; i < n; i++) { bool fol = false; for (int j = 0; j < n && !fol; j++) if (i != j && S.prev[c[j]] == S.id[c[i]]) fol = true; if (!fol) return S.v[c[i]]; }
+  return S.v[c[n - 1]];
+}
+__device__ inline int snap_pick_first(const LcSnap& S, int* c, int n) {
+  if (n == 0) return -1;
+  if (n == 1) return S.v[c[0]];
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (S.id[c[j]] < S.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
+  for (int i = 0; i < n; i++) { int ld = S.prev[c[i]]; if (ld < 0) return S.v[c[i]];
+    bool found = false; for (int j = 0; j < n && !found; j++) if (i != j && S.id[c[j]] == ld) found = true; if (!found) return S.v[c[i]]; }
+  return S.v[c[n - 1]];
+}
+__device__ inline int snap_near_aval(const LcView& W, int lane, double pos, int excl) {
+  const LcSnap& S = *W.snap; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 0.00001;
+  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane || S.v[i] == excl) continue; const double p = S.p[i];
+    if (p >= pos && p <= pv) { if (p == pv) { if (n < kTie) c[n++] = i; } else { n = 1; c[0] = i; pv = p; } } }
+  return snap_pick_last(S, c, n);
+}
+__device__ inline int snap_near_amont(const LcView& W, int lane, double pos, int excl) {
+  const LcSnap& S = *W.snap; int c[kTie]; int n = 0; double pt = -99999;
+  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane || S.v[i] == excl) continue; const double p = S.p[i];
+    if (pos > p && p >= pt) { if (p == pt) { if (n < kTie) c[n++] = i; } else { n = 1; c[0] = i; pt = p; } } }
+  if (n > 0 && (pos - pt) < 9999) return snap_pick_first(S, c, n);
+  return -1;
+}
+__device__ inline int snap_first_vehicule(const LcView& W, int lane) {
+  const LcSnap& S = *W.snap; int r = -1; double p = 0; int rid = -1;
+  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane) continue; const double q = S.p[i];
+    if (q > p || (q == p && (r < 0 || S.id[i] > rid))) { if (q >= p) { r = S.v[i]; p = q; rid = S.id[i]; } } }
+  return r;
+}
+__device__ inline int snap_prev_vehicule(const LcView& W, int v, int lane, double own) {
+  const LcSnap& S = *W.snap; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1;
+  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane || S.v[i] == v) continue; const double p = S.p[i];
+    if (p > own && p <= pv) { if (p == pv) { if (n < kTie) c[n++] = i; } else { n = 1; c[0] = i; pv = p; } } }
+  return snap_pick_last(S, c, n);
+}
+__device__ inline void snap_update(const LcView& W, int v, int lane, double pos) {            // v moved (one thread)
+  if (!W.snap || W.snap->link != W.N.lane_link[lane]) return;
+  LcSnap& S = *W.snap; for (int i = 0; i < S.n; i++) if (S.v[i] == v) { S.lane[i] = lane; S.p[i] = snap_pos(pos); return; }
+  S.link = -1;                                                                               // not in the copy: the copy cannot be trusted
+}
 __device__ inline int near_aval(const LcView& W, int lane, double pos, int excl) {           // reseau.cpp:3583-3640
+  if (snap_has(W, lane)) return snap_near_aval(W, lane, pos, excl);
   int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 0.00001;
   auto f = [&](int y) { double p = p1of(W, y); if (p >= pos && p <= pv && y != excl) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } };
   const int q0 = slice_lb(W, lane, pos);
@@ -168,6 +284,7 @@ __device__ inline int near_aval(const LcView& W, int lane, double pos, int excl)
   return pick_last(W, c, n);
 }
 __device__ inline int near_amont(const LcView& W, int lane, double pos, int excl) {          // reseau.cpp:3374-3436 (first stage; no previous lane in scope)
+  if (snap_has(W, lane)) return snap_near_amont(W, lane, pos, excl);
   int c[kTie]; int n = 0; double pt = -99999;
   auto f = [&](int y) { double p = p1of(W, y); if (pos > p && p >= pt && y != excl) { if (p == pt) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pt = p; } } };
   const int q1 = slice_lb(W, lane, pos);
@@ -176,6 +293,7 @@ __device__ inline int near_amont(const LcView& W, int lane, double pos, int excl
   return -1;
 }
 __device__ inline int first_vehicule(const LcView& W, int lane) {                            // reseau.cpp:3255-3295 (last maximum in id order)
+  if (snap_has(W, lane)) return snap_first_vehicule(W, lane);
   int r = -1; double p = 0; int rid = -1;
   auto f = [&](int y) { double q = p1of(W, y); if (q > p || (q == p && (r < 0 || W.V.id[y] > rid))) { if (q >= p) { r = y; p = q; rid = W.V.id[y]; } } };
   const int q1 = W.C.lane_start[lane] + W.C.lane_count[lane];
@@ -183,7 +301,9 @@ __device__ inline int first_vehicule(const LcView& W, int lane) {               
   return r;
 }
 __device__ inline int prev_vehicule(const LcView& W, int v) {                                // reseau.cpp:3650-3718
-  int lane = W.V.lane[v]; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1; double own = p1of(W, v);
+  int lane = W.V.lane[v];
+  if (snap_has(W, lane)) return snap_prev_vehicule(W, v, lane, p1of(W, v));
+  int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1; double own = p1of(W, v);
   auto f = [&](int y) { double p = p1of(W, y); if (p > own && p <= pv && y != v) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } };
   const int q0 = slice_ub(W, lane, own);
   for_slice(W, lane, q0, slice_group_fwd(W, lane, q0, v), f); for_moved(W, lane, f);
@@ -272,6 +392,7 @@ __device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol)
   if (fol >= 0 && W.N.lane_link[W.V.lane[fol]] == link) p = fmax(p, p1of(W, fol));
   W.V.pos[v] = p;
   lc_mark_moved(W, v);
+  snap_update(W, v, tgt, p);
   W.C.vdes[v] = -1;
   next_voie_draw(W, v, tgt);
   atomicAdd(W.C.n_changes, 1);
@@ -336,28 +457,33 @@ __device__ inline void lc_eval_stage(const DevParams& P, const LcView& W, int v,
   } while (0);
   W.C.code[slot] = code; W.C.tl_pre[slot] = tl_pre; W.C.rfol[slot] = rf; W.C.rtgt[slot] = rt; W.C.phi[slot] = phi;
 }
-// records of vehicle v for the passes >= from_pass; n = number of slots
-__device__ inline void lc_eval_vehicle(const DevParams& P, const LcView& W, int v, int n, int from_pass) {
+// records of vehicle v for the passes >= from_pass; n = number of slots.  part 0: the mandatory stage, 1 / 2: first / second candidate lane
+// of the discretionary pass (independent of each other: the walk spreads them over threads); lc_eval_kind then classifies the events.
+// returns what lc_eval_kind needs to know about the part: bit 0 = the part's pass applies to the vehicle, bit 1 = its record draws or tests
+__device__ inline int lc_eval_part(const DevParams& P, const LcView& W, int v, int n, int from_pass, int part) {
   const bool alive = W.V.status[v] == ST_ALIVE;
-  if (from_pass == 0) {
-    unsigned char k = 0;
-    if (alive && W.C.vdes[v] != -1) { lc_eval_stage(P, W, v, W.C.vdes[v], true, v); k = (W.C.code[v] != LC_FAIL || W.C.tl_pre[v] >= 0) ? 1 : 2; }
-    W.C.kind[v] = k;                                                  // 2: only marks the vehicle as handled (m_bDejaCalcule)
-  }
-  unsigned char k = 0;
-  if (alive && !W.C.chgt[v] && !W.C.had_mand[v]) {
-    int lane = W.V.lane[v]; int link = W.N.lane_link[lane]; int nl = W.N.link_nl[link];
-    if (nl >= 2) {
-      int nV = W.N.lane_num[lane]; int nVF = nV + 1, nVS = nV - 1;
-      if (W.C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
-      int mask = W.C.voies_ok[v];
-      W.C.code[n + v] = LC_FAIL; W.C.code[2 * n + v] = LC_FAIL; W.C.tl_pre[n + v] = -1; W.C.tl_pre[2 * n + v] = -1;
-      if (nVF >= 0 && nVF < nl && ((mask >> nVF) & 1)) lc_eval_stage(P, W, v, nVF, false, n + v);
-      if (nVS >= 0 && nVS < nl && ((mask >> nVS) & 1)) lc_eval_stage(P, W, v, nVS, false, 2 * n + v);
-      if (W.C.code[n + v] != LC_FAIL || W.C.tl_pre[n + v] >= 0 || W.C.code[2 * n + v] != LC_FAIL || W.C.tl_pre[2 * n + v] >= 0) k = 1;
-    }
-  }
-  W.C.kind[n + v] = k;
+  if (part == 0) { if (!(from_pass == 0 && alive && W.C.vdes[v] != -1)) return 0; lc_eval_stage(P, W, v, W.C.vdes[v], true, v); return 1 | ((W.C.code[v] != LC_FAIL || W.C.tl_pre[v] >= 0) ? 2 : 0); }
+  if (!(alive && !W.C.chgt[v] && !W.C.had_mand[v])) return 0;
+  const int lane = W.V.lane[v]; const int link = W.N.lane_link[lane]; const int nl = W.N.link_nl[link];
+  if (nl < 2) return 0;
+  const int nV = W.N.lane_num[lane]; int nVF = nV + 1, nVS = nV - 1;
+  if (W.C.ordre == 2) { nVF = nV - 1; nVS = nV + 1; }
+  const int tn = part == 1 ? nVF : nVS; const int slot = part == 1 ? n + v : 2 * n + v;
+  W.C.code[slot] = LC_FAIL; W.C.tl_pre[slot] = -1;
+  if (tn >= 0 && tn < nl && ((W.C.voies_ok[v] >> tn) & 1)) lc_eval_stage(P, W, v, tn, false, slot);
+  return 1 | ((W.C.code[slot] != LC_FAIL || W.C.tl_pre[slot] >= 0) ? 2 : 0);
+}
+// event kinds from the three parts' answers (r0 only when from_pass == 0)
+__device__ inline void lc_eval_kind(const LcView& W, int v, int n, int from_pass, int r0, int r1, int r2) {
+#ifdef SYM_LC_NOKIND
+  return;
+#endif
+  if (from_pass == 0) W.C.kind[v] = (r0 & 1) ? ((r0 & 2) ? 1 : 2) : 0;       // 2: only marks the vehicle as handled (m_bDejaCalcule)
+  W.C.kind[n + v] = ((r1 | r2) & 2) ? 1 : 0;
+}
+__device__ inline void lc_eval_vehicle(const DevParams& P, const LcView& W, int v, int n, int from_pass) {
+  const int r0 = lc_eval_part(P, W, v, n, from_pass, 0), r1 = lc_eval_part(P, W, v, n, from_pass, 1), r2 = lc_eval_part(P, W, v, n, from_pass, 2);
+  lc_eval_kind(W, v, n, from_pass, r0, r1, r2);
 }
 __global__ void k_lc_eval(DevNet N, DevVeh V, DevLc C, int n) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,9 +499,13 @@ __global__ void k_lc_eval(DevNet N, DevVeh V, DevLc C, int n) {
 struct LcDirty { bool dirty, full, preds; double xlo, xhi; };
 __device__ inline void lc_window(const LcView& W, int lane, double pos, int excl, LcDirty* d) {
   double lo = -1, hi = -1;
-  auto f = [&](int y) { if (y == excl) return; double p = p1of(W, y); if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } };
-  const int qa = slice_lb(W, lane, pos), qb = slice_ub(W, lane, pos);
-  for_slice(W, lane, slice_group_bwd(W, lane, qa, excl), qa, f); for_slice(W, lane, qb, slice_group_fwd(W, lane, qb, excl), f); for_moved(W, lane, f);
+  auto g = [&](double p) { if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } };
+  if (snap_has(W, lane)) { const LcSnap& S = *W.snap; for (int i = 0; i < S.n; i++) if (S.lane[i] == lane && S.v[i] != excl) g(S.p[i]); }
+  else {
+    auto f = [&](int y) { if (y == excl) return; g(p1of(W, y)); };
+    const int qa = slice_lb(W, lane, pos), qb = slice_ub(W, lane, pos);
+    for_slice(W, lane, slice_group_bwd(W, lane, qa, excl), qa, f); for_slice(W, lane, qb, slice_group_fwd(W, lane, qb, excl), f); for_moved(W, lane, f);
+  }
   const double len = W.N.lane_len[lane];
   if (lo < 0) { d->preds = true; d->xlo = -1; } else d->xlo = fmin(d->xlo, lo / len);
   d->xhi = hi < 0 ? 2.0 : fmax(d->xhi, hi / len);
@@ -414,19 +544,45 @@ __device__ inline void lc_run_event(const DevParams& P, const LcView& W, int ev,
     }
   }
 }
+// copies the vehicles currently on link K into the shared-memory snapshot (whole block); the snapshot stays disabled when the link holds
+// more vehicles than it has room for
+__device__ inline void snap_build(const LcView& W, LcSnap* S, int K) {
+  const int tid = threadIdx.x;
+  if (tid == 0) { S->n = 0; S->link = -1; }
+  __syncthreads();
+  const int l0 = W.N.link_first[K], l1 = l0 + W.N.link_nl[K] - 1;
+  const int a = W.C.lane_start[l0], b = W.C.lane_start[l1] + W.C.lane_count[l1];
+  auto put = [&](int y) { const int i = atomicAdd(&S->n, 1); if (i < kSnap) { S->v[i] = y; S->lane[i] = W.V.lane[y]; S->p[i] = p1of(W, y); S->id[i] = W.V.id[y]; S->prev[i] = W.V.prev_leader[y]; } };
+  for (int q = a + tid; q < b; q += blockDim.x) { const int y = W.C.order[q]; if (!W.C.moved[y] && W.V.status[y] == ST_ALIVE) put(y); }
+  if (tid == 0) for (int y = W.C.link_delta_head[K]; y >= 0; y = W.C.delta_next[y]) put(y);
+  __syncthreads();
+  if (tid == 0 && S->n <= kSnap) S->link = K;
+  __syncthreads();
+}
+constexpr int kLcList = 1024;
 __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc C, int n) {
   const DevParams& P = cP_ref();
-  __shared__ DevRng srng; __shared__ int rb[kRb]; __shared__ int rb_pos, rb_fill, rb_base;
-  __shared__ int s_wsum[kLcBlock / 32], s_stop, s_stop_off, s_total, s_dirty_link, s_full, s_preds; __shared__ double s_xlo, s_xhi;
-  LcView W{N, V, C, rb, &rb_pos, &rb_fill, &rb_base, &srng};
+  __shared__ MtShared srng; __shared__ LcSnap snap; __shared__ int rb[kRb]; __shared__ int rb_pos, rb_fill, rb_base;
+  __shared__ int s_wsum[kLcBlock / 32], s_stop, s_stop_off, s_total, s_dirty_link, s_full, s_preds, s_nlist, s_list[kLcList]; __shared__ unsigned char s_res[3 * kLcList]; __shared__ double s_xlo, s_xhi;
+  LcView W{N, V, C, rb, &rb_pos, &rb_fill, &rb_base, &srng, &snap};
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5; const int E = 2 * n;
-  for (int k = tid; k < 624; k += kLcBlock) srng.mt[k] = C.rng->mt[k];
-  if (tid == 0) { srng.idx = C.rng->idx; srng.count = 0; rb_pos = rb_fill = rb_base = 0; }
+  mt_load(srng, C.rng);
+  if (tid == 0) { rb_pos = rb_fill = rb_base = 0; snap.link = -1; snap.n = 0; }
   __syncthreads();
-  int base = 0; long long walked = 0;
+  int base = 0; long long walked = 0, reevals = 0;
+#ifdef SYM_LC_TIMING
+  long long tA = 0, tB = 0, tC = 0, t0 = clock64(), tF = 0, tS = 0, tW = 0, tP = 0, tK = 0, tP0 = 0, tK0 = 0; int nchunk = 0, nstop = 0, ndirty = 0, npreds = 0, nsnap = 0;
+#endif
   while (base < E) {
-    if (tid == 0) { lc_fill(W, 4 * kLcBlock + 8); s_stop = 0x7fffffff; }
+#ifdef SYM_LC_TIMING
+    long long c0 = clock64();
+#endif
+    lc_fill_block(W, 4 * kLcBlock + 8);
+    if (tid == 0) s_stop = 0x7fffffff;
     __syncthreads();
+#ifdef SYM_LC_TIMING
+    tF += clock64() - c0;
+#endif
     // every thread: its event under the assumption that all tests before it (and its own) are refused
     const int e = base + tid;
     int cnt = 0, nt = 0, toff[2]; double tphi[2]; bool hard = false, live = false;
@@ -466,42 +622,93 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
     }
     if (e == st) s_stop_off = off;
     __syncthreads();
+#ifdef SYM_LC_TIMING
+    long long c1 = clock64(); tA += c1 - c0; nchunk++;
+#endif
+    if (st == 0x7fffffff) { if (tid == 0) rb_pos += s_total; base += kLcBlock; __syncthreads(); continue; }
+    // the stop event: an accepted change or an event with side effects.  Its link is copied to shared memory first (unless it needs the literal code)
+    const int from_pass = st >= n; const int vcur = from_pass ? st - n : st;
+    const int K0 = N.lane_link[V.lane[vcur]];
+    const bool slow = from_pass ? (C.code[n + vcur] == LC_SLOW || C.code[2 * n + vcur] == LC_SLOW) : C.code[vcur] == LC_SLOW;
+    if (!slow) snap_build(W, &snap, K0); else { if (tid == 0) snap.link = -1; __syncthreads(); }
+#ifdef SYM_LC_TIMING
+    tS += clock64() - c1; nsnap += snap.n;
+#endif
     if (tid == 0) {
       s_dirty_link = -1;
-      if (st == 0x7fffffff) rb_pos += s_total;
-      else {
-        rb_pos += s_stop_off;
-        LcDirty d{false, false, false, 3.0, -1.0};
-        const int vv = st >= n ? st - n : st; const int link = N.lane_link[V.lane[vv]];
-        lc_run_event(P, W, st, n, &d);
-        if (d.dirty) { s_dirty_link = link; s_full = d.full; s_preds = d.preds; s_xlo = d.xlo; s_xhi = d.xhi; }
-      }
+      rb_pos += s_stop_off;
+      LcDirty d{false, false, false, 3.0, -1.0};
+      lc_run_event(P, W, st, n, &d);
+      if (d.dirty) { s_dirty_link = K0; s_full = d.full; s_preds = d.preds; s_xlo = d.xlo; s_xhi = d.xhi; }
+      s_nlist = 0;
     }
     __syncthreads();
-    if (st == 0x7fffffff) { base += kLcBlock; continue; }
+#ifdef SYM_LC_TIMING
+    long long c2 = clock64(); tB += c2 - c1;
+#endif
     base = st + 1;
     const int K = s_dirty_link;
+#ifdef SYM_LC_TIMING
+    nstop++; if (K >= 0) { ndirty++; if (s_preds) npreds++; }
+#endif
     if (K >= 0) {                                                     // re-evaluate the later events of link K (window) and, if needed, of the links that lead into it
-      const int from_pass = st >= n; const int vcur = from_pass ? st - n : st;
+      if (snap.link != K) snap_build(W, &snap, K);                    // (the copy followed the change; rebuilt after the literal code)
       const int upn = N.link_up[K]; const bool full = s_full, preds = s_preds;
       const double margin = 0.05 / N.link_len[K]; const double xlo = s_xlo - margin, xhi = s_xhi + margin;
-      for (int k = preds ? 0 : K; k < (preds ? N.n_links : K + 1); k++) {
-        if (k != K && N.link_down[k] != upn) continue;
-        const int l0 = N.link_first[k], l1 = l0 + N.link_nl[k] - 1;
-        const int a = C.lane_start[l0], b = C.lane_start[l1] + C.lane_count[l1];
-        for (int q = a + tid; q < b; q += kLcBlock) {
-          const int y = C.order[q];
-          if (k == K && !full) { const double x = p1of(W, y) / N.lane_len[V.lane[y]]; if (x < xlo || x > xhi) continue; }
-          if (from_pass == 0) lc_eval_vehicle(P, W, y, n, y > vcur ? 0 : 1);
-          else if (y > vcur) lc_eval_vehicle(P, W, y, n, 1);
-          else continue;
-          atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_REEVAL], 1ULL);
+      // which vehicles, from which pass on: entry = slot * 2 + (1 when only the discretionary pass is left)
+      auto want = [&](int y) { int fp; if (from_pass == 0) fp = y > vcur ? 0 : 1; else if (y > vcur) fp = 1; else return;
+        const int i = atomicAdd(&s_nlist, 1); if (i < kLcList) s_list[i] = y * 2 + fp; };
+      if (snap.link == K) { for (int i = tid; i < snap.n; i += kLcBlock) { if (!full) { const double x = snap.p[i] / N.lane_len[snap.lane[i]]; if (x < xlo || x > xhi) continue; } want(snap.v[i]); } }
+      else { const int l0 = N.link_first[K], l1 = l0 + N.link_nl[K] - 1; const int a = C.lane_start[l0], b = C.lane_start[l1] + C.lane_count[l1];
+        for (int q = a + tid; q < b; q += kLcBlock) { const int y = C.order[q]; if (!full) { const double x = p1of(W, y) / N.lane_len[V.lane[y]]; if (x < xlo || x > xhi) continue; } want(y); } }
+      if (preds) for (int k = tid; k < N.n_links; k += kLcBlock) { if (k == K || N.link_down[k] != upn) continue;
+          const int l0 = N.link_first[k], l1 = l0 + N.link_nl[k] - 1; const int a = C.lane_start[l0], b = C.lane_start[l1] + C.lane_count[l1];
+          for (int q = a; q < b; q++) want(C.order[q]); }
+      __syncthreads();
+#ifdef SYM_LC_TIMING
+      long long c3 = clock64(); tW += c3 - c2;
+#endif
+      const int nl = s_nlist;
+      if (nl <= kLcList) {
+        // one stage per thread, spread over the warps first: the stages of a window take different branches
+        for (int w = (tid & 31) * (kLcBlock / 32) + (tid >> 5); w < 3 * nl; w += kLcBlock) { const int ent = s_list[w / 3]; s_res[w] = (unsigned char)lc_eval_part(P, W, ent >> 1, n, ent & 1, w % 3); }
+#ifdef SYM_LC_TIMING
+        tP0 += clock64() - c3;
+#endif
+        __syncthreads();
+#ifdef SYM_LC_TIMING
+        long long c4 = clock64(); tP += c4 - c3;
+#endif
+        for (int w = tid; w < nl; w += kLcBlock) { const int ent = s_list[w]; lc_eval_kind(W, ent >> 1, n, ent & 1, s_res[3 * w], s_res[3 * w + 1], s_res[3 * w + 2]); }
+        if (tid == 0) reevals += nl;
+#ifdef SYM_LC_TIMING
+        tK0 += clock64() - c4; __syncthreads(); tK += clock64() - c4;
+#endif
+      } else {                                                        // more than the list holds: the plain loops
+        for (int k = preds ? 0 : K; k < (preds ? N.n_links : K + 1); k++) {
+          if (k != K && N.link_down[k] != upn) continue;
+          const int l0 = N.link_first[k], l1 = l0 + N.link_nl[k] - 1; const int a = C.lane_start[l0], b = C.lane_start[l1] + C.lane_count[l1];
+          for (int q = a + tid; q < b; q += kLcBlock) {
+            const int y = C.order[q];
+            if (k == K && !full) { const double x = p1of(W, y) / N.lane_len[V.lane[y]]; if (x < xlo || x > xhi) continue; }
+            if (from_pass == 0) lc_eval_vehicle(P, W, y, n, y > vcur ? 0 : 1);
+            else if (y > vcur) lc_eval_vehicle(P, W, y, n, 1);
+            else continue;
+            reevals++;
+          }
         }
       }
     }
     __syncthreads();
+#ifdef SYM_LC_TIMING
+    tC += clock64() - c2;
+#endif
   }
+#ifdef SYM_LC_TIMING
+  if (tid == 0) printf("lc_walk E %d chunks %d stops %d dirty %d preds %d | total %lld eval %lld (fill %lld) event %lld (snap %lld, %d entries) reeval %lld (collect %lld parts %lld [own %lld] kinds %lld [own %lld]) cycles\n", E, nchunk, nstop, ndirty, npreds, clock64() - t0, tA, tF, tB, tS, nsnap, tC, tW, tP, tP0, tK, tK0);
+#endif
   if (walked) atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_EVENTS], (unsigned long long)walked);
+  if (reevals) atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_REEVAL], (unsigned long long)reevals);
   if (tid == 0) C.n_changes[1] = rb_base + rb_pos;
 }
 // Reseau::ChangementDeVoie (reseau.cpp:4219-4330): one thread, m_LstVehicles (slot) order

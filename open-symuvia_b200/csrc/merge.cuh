@@ -715,47 +715,7 @@ __global__ void __launch_bounds__(256) k_mrg_dirty(DevNet N, DevVeh V, DevMrg M,
 }
 // ---- the random stream on the device -----------------------------------------------------------------------------------------
 // RandManager::myRand = boost::mt19937 + uniform_int<>(0, 0x7FFE) by bucket rejection (RandManager.cpp:26-30).  One block of 256 threads
-// advances a state held in shared memory: a twist of the 624 words has four dependency phases (words 0..226 only need old words,
-// 227..453 need the new 0..226, 454..622 the new 227..453, word 623 the new 0 and 396); the tempered outputs of a block of words are
-// produced in parallel and a rejected value (4 in 2^32) sends that block through a serial compaction.
-struct MtShared { unsigned mt[624]; unsigned nw[624]; int idx; unsigned count; };
-__device__ inline void mt_twist(MtShared& S) {
-  const int tid = threadIdx.x;
-  auto f = [&](const unsigned* lo, const unsigned* hi, const unsigned* far) { const unsigned y = (*lo & 0x80000000u) | (*hi & 0x7fffffffu); return *far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); };
-  if (tid < 227) S.nw[tid] = f(&S.mt[tid], &S.mt[tid + 1], &S.mt[tid + 397]);
-  __syncthreads();
-  if (tid < 227) S.nw[227 + tid] = f(&S.mt[227 + tid], &S.mt[228 + tid], &S.nw[tid]);
-  __syncthreads();
-  if (tid < 169) S.nw[454 + tid] = f(&S.mt[454 + tid], &S.mt[455 + tid], &S.nw[227 + tid]);
-  __syncthreads();
-  if (tid == 0) S.nw[623] = f(&S.mt[623], &S.nw[0], &S.nw[396]);
-  __syncthreads();
-  for (int i = tid; i < 624; i += blockDim.x) S.mt[i] = S.nw[i];
-  __syncthreads();
-}
-// consume `n` accepted draws; out != nullptr: their values are stored (out[0..n))
-__device__ inline void rng_advance(MtShared& S, unsigned n, int* out) {
-  const int tid = threadIdx.x; const unsigned bucket = 0xFFFFFFFFu / 32767u;
-  unsigned left = n, written = 0; int idx = S.idx;                        // uniform over the block
-  while (left > 0) {
-    if (idx >= 624) { mt_twist(S); idx = 0; }
-    const unsigned m = min(left, (unsigned)(624 - idx));
-    int rej = 0; unsigned vals[3]; int nv = 0;
-    for (unsigned k = tid; k < m; k += blockDim.x) { unsigned y = S.mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-      const unsigned v = y / bucket; vals[nv++] = v; if (v > 32766u) rej++; }
-    const int nrej = __syncthreads_count(rej);
-    if (nrej == 0) { if (out) { int q = 0; for (unsigned k = tid; k < m; k += blockDim.x) out[written + k] = (int)vals[q++]; } written += m; left -= m; }
-    else { if (out && tid == 0) { unsigned w = written; for (unsigned k = 0; k < m; k++) { unsigned y = S.mt[idx + k]; y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-          const unsigned v = y / bucket; if (v <= 32766u) out[w++] = (int)v; } }
-      written += m - nrej; left -= m - nrej; }
-    idx += (int)m;
-  }
-  __syncthreads();
-  if (tid == 0) { S.idx = idx; S.count += n; }
-  __syncthreads();
-}
-__device__ inline void mt_load(MtShared& S, const DevRng* r) { for (int k = threadIdx.x; k < 624; k += blockDim.x) S.mt[k] = r->mt[k]; if (threadIdx.x == 0) { S.idx = r->idx; S.count = r->count; } __syncthreads(); }
-__device__ inline void mt_store(const MtShared& S, DevRng* r) { __syncthreads(); for (int k = threadIdx.x; k < 624; k += blockDim.x) r->mt[k] = S.mt[k]; if (threadIdx.x == 0) { r->idx = S.idx; r->count = S.count; } }
+// MtShared / mt_twist / rng_advance / mt_load / mt_store: lanechange.cuh
 __global__ void __launch_bounds__(256) k_rng_skip(DevRng* r, const int* n_ptr, int n_imm) {
   __shared__ MtShared S;
   const unsigned n = n_ptr ? (unsigned)*n_ptr : (unsigned)n_imm;
