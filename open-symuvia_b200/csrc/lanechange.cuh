@@ -134,10 +134,11 @@ __global__ void k_lc_prepare(DevNet N, DevVeh V, DevLc C, int n) {
 
 // ---- the sequential part (one thread) ----------------------------------------------------------------------------------
 // rb..srng: k_lc_walk draws through a buffer of upcoming values kept in shared memory (all null elsewhere: direct draws)
-constexpr int kSnap = 384;
-// the vehicles currently on one link, copied to shared memory by k_lc_walk around a commit: the neighbour queries of that link
-// then scan this copy instead of chasing the lane slices through global memory
-struct LcSnap { int link, n; int v[kSnap], lane[kSnap], id[kSnap], prev[kSnap]; double p[kSnap]; };
+constexpr int kSnapLanes = 4, kSnapCap = 96;
+// the vehicles currently on one link, lane by lane, copied to shared memory by k_lc_walk around a commit: the neighbour queries of that
+// link then scan this copy (one 16-byte record per vehicle) instead of chasing the lane slices through global memory
+struct SnapE { double p; int v; int id; };
+struct LcSnap { int link, lane0, nl, over; int cnt[kSnapLanes]; double len[kSnapLanes]; SnapE e[kSnapLanes][kSnapCap]; int prev[kSnapLanes][kSnapCap]; };
 struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; int* rb = nullptr; int* rb_pos = nullptr; int* rb_fill = nullptr; int* rb_base = nullptr; MtShared* srng = nullptr; LcSnap* snap = nullptr; };
 constexpr int kRb = 2048;
 // make at least `need` upcoming draws available in the buffer (one thread)
@@ -212,7 +213,7 @@ __device__ inline void lc_mark_moved(const LcView& W, int v) {                  
 }
 __device__ inline double p1of(const LcView& W, int y) { return snap_pos(W.V.pos[y]); }
 // Reseau::GetLastVehicule (reseau.cpp:14041-14081) over candidates collected in id order
-__device__ inline int pick_last(const LcView& W, int* c, int n) {
+__device__ __noinline__ int pick_last(const LcView& W, int* c, int n) {
   if (n == 0) return -1;
   if (n == 1) return c[0];
   for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (W.V.id[c[j]] < W.V.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
@@ -220,7 +221,7 @@ __device__ inline int pick_last(const LcView& W, int* c, int n) {
   return c[n - 1];
 }
 // Reseau::GetFirstVehicule(list) (reseau.cpp:14084-14128)
-__device__ inline int pick_first(const LcView& W, int* c, int n) {
+__device__ __noinline__ int pick_first(const LcView& W, int* c, int n) {
   if (n == 0) return -1;
   if (n == 1) return c[0];
   for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (W.V.id[c[j]] < W.V.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
@@ -228,54 +229,79 @@ __device__ inline int pick_first(const LcView& W, int* c, int n) {
     bool found = false; for (int j = 0; j < n && !found; j++) if (i != j && W.V.id[c[j]] == ld) found = true; if (!found) return c[i]; }
   return c[n - 1];
 }
-// ---- the same queries over the shared-memory copy of a link (LcSnap): every vehicle of the lane is visited, the filters are the same
-__device__ __forceinline__ bool snap_has(const LcView& W, int lane) { return W.snap && W.snap->link == W.N.lane_link[lane]; }
-__device__ inline int snap_pick_last(const LcSnap& S, int* c, int n) {
-  if (n == 0) return -1;
-  if (n == 1) return S.v[c[0]];
-  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (S.id[c[j]] < S.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
-  for (int i = 0; i < n; i++) { bool fol = false; for (int j = 0; j < n && !fol; j++) if (i != j && S.prev[c[j]] == S.id[c[i]]) fol = true; if (!fol) return S.v[c[i]]; }
-  return S.v[c[n - 1]];
+// ---- the same queries over the shared-memory copy of a link (LcSnap): every vehicle of the lane is visited, the filters are the same.
+// First pass: the extreme position and how many vehicles share it (registers only); the tie rules run only when several do.
+__device__ __forceinline__ bool snap_has(const LcView& W, int lane) { return W.snap && W.snap->link >= 0 && (unsigned)(lane - W.snap->lane0) < (unsigned)W.snap->nl; }
+__device__ __noinline__ int snap_pick_last(const LcSnap& S, int li, int* c, int n) {
+  const SnapE* e = S.e[li]; const int* pr = S.prev[li];
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (e[c[j]].id < e[c[i]].id) { int t = c[i]; c[i] = c[j]; c[j] = t; }
+  for (int i = 0; i < n; i++) { bool fol = false; for (int j = 0; j < n && !fol; j++) if (i != j && pr[c[j]] == e[c[i]].id) fol = true; if (!fol) return e[c[i]].v; }
+  return e[c[n - 1]].v;
 }
-__device__ inline int snap_pick_first(const LcSnap& S, int* c, int n) {
-  if (n == 0) return -1;
-  if (n == 1) return S.v[c[0]];
-  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (S.id[c[j]] < S.id[c[i]]) { int t = c[i]; c[i] = c[j]; c[j] = t; }
-  for (int i = 0; i < n; i++) { int ld = S.prev[c[i]]; if (ld < 0) return S.v[c[i]];
-    bool found = false; for (int j = 0; j < n && !found; j++) if (i != j && S.id[c[j]] == ld) found = true; if (!found) return S.v[c[i]]; }
-  return S.v[c[n - 1]];
+__device__ __noinline__ int snap_pick_first(const LcSnap& S, int li, int* c, int n) {
+  const SnapE* e = S.e[li]; const int* pr = S.prev[li];
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (e[c[j]].id < e[c[i]].id) { int t = c[i]; c[i] = c[j]; c[j] = t; }
+  for (int i = 0; i < n; i++) { int ld = pr[c[i]]; if (ld < 0) return e[c[i]].v;
+    bool found = false; for (int j = 0; j < n && !found; j++) if (i != j && e[c[j]].id == ld) found = true; if (!found) return e[c[i]].v; }
+  return e[c[n - 1]].v;
 }
-__device__ inline int snap_near_aval(const LcView& W, int lane, double pos, int excl) {
-  const LcSnap& S = *W.snap; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 0.00001;
-  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane || S.v[i] == excl) continue; const double p = S.p[i];
-    if (p >= pos && p <= pv) { if (p == pv) { if (n < kTie) c[n++] = i; } else { n = 1; c[0] = i; pv = p; } } }
-  return snap_pick_last(S, c, n);
+// vehicles of the lane at position `at`, except `excl` (at most kTie, in copy order)
+__device__ __noinline__ int snap_ties(const LcSnap& S, int li, double at, int excl, int* c) {
+  const SnapE* e = S.e[li]; const int cnt = S.cnt[li]; int n = 0;
+  for (int i = 0; i < cnt; i++) if (e[i].p == at && e[i].v != excl && n < kTie) c[n++] = i;
+  return n;
 }
-__device__ inline int snap_near_amont(const LcView& W, int lane, double pos, int excl) {
-  const LcSnap& S = *W.snap; int c[kTie]; int n = 0; double pt = -99999;
-  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane || S.v[i] == excl) continue; const double p = S.p[i];
-    if (pos > p && p >= pt) { if (p == pt) { if (n < kTie) c[n++] = i; } else { n = 1; c[0] = i; pt = p; } } }
-  if (n > 0 && (pos - pt) < 9999) return snap_pick_first(S, c, n);
-  return -1;
+__device__ __forceinline__ int snap_near_aval(const LcView& W, int lane, double pos, int excl) {
+  const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
+  double pv = S.len[li] + 0.00001; int bv = -1, nt = 0;
+#pragma unroll 4
+  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
+    if (x.v != excl && x.p >= pos && x.p <= pv) { if (x.p == pv) { if (nt == 0) bv = x.v; nt++; } else { pv = x.p; bv = x.v; nt = 1; } } }
+  if (nt <= 1) return bv;
+  int c[kTie]; const int n = snap_ties(S, li, pv, excl, c);
+  return snap_pick_last(S, li, c, n);
 }
-__device__ inline int snap_first_vehicule(const LcView& W, int lane) {
-  const LcSnap& S = *W.snap; int r = -1; double p = 0; int rid = -1;
-  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane) continue; const double q = S.p[i];
-    if (q > p || (q == p && (r < 0 || S.id[i] > rid))) { if (q >= p) { r = S.v[i]; p = q; rid = S.id[i]; } } }
+__device__ __forceinline__ int snap_near_amont(const LcView& W, int lane, double pos, int excl) {
+  const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
+  double pt = -99999; int bv = -1, nt = 0;
+#pragma unroll 4
+  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
+    if (x.v != excl && pos > x.p && x.p >= pt) { if (x.p == pt) { if (nt == 0) bv = x.v; nt++; } else { pt = x.p; bv = x.v; nt = 1; } } }
+  if (nt == 0 || !((pos - pt) < 9999)) return -1;
+  if (nt == 1) return bv;
+  int c[kTie]; const int n = snap_ties(S, li, pt, excl, c);
+  return snap_pick_first(S, li, c, n);
+}
+__device__ __forceinline__ int snap_first_vehicule(const LcView& W, int lane) {
+  const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
+  int r = -1; double p = 0; int rid = -1;
+#pragma unroll 4
+  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
+    if (x.p > p || (x.p == p && (r < 0 || x.id > rid))) { if (x.p >= p) { r = x.v; p = x.p; rid = x.id; } } }
   return r;
 }
-__device__ inline int snap_prev_vehicule(const LcView& W, int v, int lane, double own) {
-  const LcSnap& S = *W.snap; int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1;
-  for (int i = 0; i < S.n; i++) { if (S.lane[i] != lane || S.v[i] == v) continue; const double p = S.p[i];
-    if (p > own && p <= pv) { if (p == pv) { if (n < kTie) c[n++] = i; } else { n = 1; c[0] = i; pv = p; } } }
-  return snap_pick_last(S, c, n);
+__device__ __forceinline__ int snap_prev_vehicule(const LcView& W, int v, int lane, double own) {
+  const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
+  double pv = S.len[li] + 1; int bv = -1, nt = 0;
+#pragma unroll 4
+  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
+    if (x.v != v && x.p > own && x.p <= pv) { if (x.p == pv) { if (nt == 0) bv = x.v; nt++; } else { pv = x.p; bv = x.v; nt = 1; } } }
+  if (nt <= 1) return bv;
+  int c[kTie]; const int n = snap_ties(S, li, pv, v, c);
+  return snap_pick_last(S, li, c, n);
 }
 __device__ inline void snap_update(const LcView& W, int v, int lane, double pos) {            // v moved (one thread)
-  if (!W.snap || W.snap->link != W.N.lane_link[lane]) return;
-  LcSnap& S = *W.snap; for (int i = 0; i < S.n; i++) if (S.v[i] == v) { S.lane[i] = lane; S.p[i] = snap_pos(pos); return; }
+  if (!snap_has(W, lane)) return;
+  LcSnap& S = *W.snap; const int ln = lane - S.lane0;
+  for (int li = 0; li < S.nl; li++) for (int i = 0; i < S.cnt[li]; i++) if (S.e[li][i].v == v) {
+    SnapE x = S.e[li][i]; const int pr = S.prev[li][i]; x.p = snap_pos(pos);
+    if (li == ln) { S.e[li][i] = x; return; }
+    const int last = --S.cnt[li]; S.e[li][i] = S.e[li][last]; S.prev[li][i] = S.prev[li][last];
+    if (S.cnt[ln] >= kSnapCap) { S.link = -1; return; }
+    const int k = S.cnt[ln]++; S.e[ln][k] = x; S.prev[ln][k] = pr; return; }
   S.link = -1;                                                                               // not in the copy: the copy cannot be trusted
 }
-__device__ inline int near_aval(const LcView& W, int lane, double pos, int excl) {           // reseau.cpp:3583-3640
+__device__ __noinline__ int near_aval(const LcView& W, int lane, double pos, int excl) {           // reseau.cpp:3583-3640
   if (snap_has(W, lane)) return snap_near_aval(W, lane, pos, excl);
   int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 0.00001;
   auto f = [&](int y) { double p = p1of(W, y); if (p >= pos && p <= pv && y != excl) { if (p == pv) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pv = p; } } };
@@ -283,7 +309,7 @@ __device__ inline int near_aval(const LcView& W, int lane, double pos, int excl)
   for_slice(W, lane, q0, slice_group_fwd(W, lane, q0, excl), f); for_moved(W, lane, f);
   return pick_last(W, c, n);
 }
-__device__ inline int near_amont(const LcView& W, int lane, double pos, int excl) {          // reseau.cpp:3374-3436 (first stage; no previous lane in scope)
+__device__ __noinline__ int near_amont(const LcView& W, int lane, double pos, int excl) {          // reseau.cpp:3374-3436 (first stage; no previous lane in scope)
   if (snap_has(W, lane)) return snap_near_amont(W, lane, pos, excl);
   int c[kTie]; int n = 0; double pt = -99999;
   auto f = [&](int y) { double p = p1of(W, y); if (pos > p && p >= pt && y != excl) { if (p == pt) { if (n < kTie) c[n++] = y; } else { n = 1; c[0] = y; pt = p; } } };
@@ -292,7 +318,7 @@ __device__ inline int near_amont(const LcView& W, int lane, double pos, int excl
   if (n > 0 && (pos - pt) < 9999) return pick_first(W, c, n);
   return -1;
 }
-__device__ inline int first_vehicule(const LcView& W, int lane) {                            // reseau.cpp:3255-3295 (last maximum in id order)
+__device__ __noinline__ int first_vehicule(const LcView& W, int lane) {                            // reseau.cpp:3255-3295 (last maximum in id order)
   if (snap_has(W, lane)) return snap_first_vehicule(W, lane);
   int r = -1; double p = 0; int rid = -1;
   auto f = [&](int y) { double q = p1of(W, y); if (q > p || (q == p && (r < 0 || W.V.id[y] > rid))) { if (q >= p) { r = y; p = q; rid = W.V.id[y]; } } };
@@ -300,7 +326,7 @@ __device__ inline int first_vehicule(const LcView& W, int lane) {               
   for_slice(W, lane, slice_group_bwd(W, lane, q1, -1), q1, f); for_moved(W, lane, f);
   return r;
 }
-__device__ inline int prev_vehicule(const LcView& W, int v) {                                // reseau.cpp:3650-3718
+__device__ __noinline__ int prev_vehicule(const LcView& W, int v) {                                // reseau.cpp:3650-3718
   int lane = W.V.lane[v];
   if (snap_has(W, lane)) return snap_prev_vehicule(W, v, lane, p1of(W, v));
   int c[kTie]; int n = 0; double pv = W.N.lane_len[lane] + 1; double own = p1of(W, v);
@@ -336,7 +362,7 @@ __device__ inline int next_voie_draw(const LcView& W, int v, int lane) {
   return nx;
 }
 // everything of TestLaneChange before the draw; false = refused without a draw
-__device__ inline bool lane_change_phi(const DevParams& P, const LcView& W, int v, double pv, int fol, int lead, int lead_orig, int tgt, bool force, double* phi_out) {   // AbstractCarFollowing.cpp:61-323
+__device__ __noinline__ bool lane_change_phi(const DevParams& P, const LcView& W, int v, double pv, int fol, int lead, int lead_orig, int tgt, bool force, double* phi_out) {   // AbstractCarFollowing.cpp:61-323
   const DevCls& c = P.cls[W.V.cls[v]]; double kc = c.w * c.kx / (c.w - c.vx);
   int lane = W.V.lane[v]; int link = W.N.lane_link[lane];
   double si;
@@ -384,7 +410,7 @@ __device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int
   double r = lc_draw(W) / 32767.0;                                   // AbstractCarFollowing.cpp:324-328
   return r < phi;
 }
-__device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol) {            // vehicule.cpp:2657-2711
+__device__ __noinline__ void changement_voie(const LcView& W, int v, int tgt, int fol) {            // vehicule.cpp:2657-2711
   W.C.chgt[v] = 1;
   int old = W.V.lane[v]; int link = W.N.lane_link[old];
   double p = p1of(W, v) * W.N.lane_len[tgt] / W.N.lane_len[old];
@@ -397,7 +423,7 @@ __device__ inline void changement_voie(const LcView& W, int v, int tgt, int fol)
   next_voie_draw(W, v, tgt);
   atomicAdd(W.C.n_changes, 1);
 }
-__device__ inline bool calcul_changement_voie(const DevParams& P, const LcView& W, int v, int tgt_num, bool force) {   // vehicule.cpp:2248-2457
+__device__ __noinline__ bool calcul_changement_voie(const DevParams& P, const LcView& W, int v, int tgt_num, bool force) {   // vehicule.cpp:2248-2457
   double p1 = p1of(W, v);
   if (p1 <= SYM_UNDEF) return false;
   if (W.C.chgt[v]) return false;
@@ -428,34 +454,52 @@ __device__ inline bool calcul_changement_voie(const DevParams& P, const LcView& 
 // ---- parallel evaluation / ordered commit -------------------------------------------------------------------------------
 // CalculChangementVoie without side effects: what the event (v, candidate lane) will do when its turn comes, provided
 // nothing changes on its link before.
-__device__ inline void lc_eval_stage(const DevParams& P, const LcView& W, int v, int tgt_num, bool force, int slot) {
+#ifdef SYM_LC_TIMING
+__device__ long long g_lcprof[12];
+#define LCP(i) do { if (W.snap) { long long t_ = clock64(); atomicAdd((unsigned long long*)&g_lcprof[i], (unsigned long long)(t_ - tp_)); tp_ = t_; } } while (0)
+#else
+#define LCP(i) do { } while (0)
+#endif
+__device__ __noinline__ void lc_eval_stage(const DevParams& P, const LcView& W, int v, int tgt_num, bool force, int slot) {
   unsigned char code = LC_FAIL; int tl_pre = -1, rf = -1, rt = -1; double phi = 0;
+#ifdef SYM_LC_TIMING
+  long long tp_ = clock64(); if (W.snap) atomicAdd((unsigned long long*)&g_lcprof[11], 1ULL);
+#endif
   do {
     double p1 = p1of(W, v);
     if (p1 <= SYM_UNDEF || W.C.chgt[v]) break;
     int lane = W.V.lane[v]; int link = W.N.lane_link[lane]; bool desired = W.C.vdes[v] != -1; bool oblig = W.N.lane_flags[lane] & 1;
+    LCP(0);
     if (first_vehicule(W, lane) == v && !oblig && !desired) break;
+    LCP(1);
     int tgt = W.N.link_first[link] + tgt_num;
     double ratio = W.N.lane_len[tgt] / W.N.lane_len[lane];
+    LCP(2);
     int same = near_aval(W, tgt, ratio * p1 - 0.01, v);
     if (same >= 0 && fabs(ratio * p1 - p1of(W, same)) < 0.01) {
       if (fabs(p1 - W.N.lane_len[lane]) < 0.01) code = LC_SLOW;       // move-back / swap: literal code at commit time
       break;
     }
+    LCP(3);
     double q = ratio * p1 + 0.001;
     int fol = near_amont(W, tgt, q, v);
     int lead = near_aval(W, tgt, q, v);
+    LCP(4);
     if (lead < 0 && (oblig || desired)) {
       int tl; int nx = next_voie(W.N, W.V.route[v], W.V.route_pos[v], tgt, &tl);
       tl_pre = tl;
       if (nx >= 0) lead = near_aval(W, nx, 0, -1);
     }
+    LCP(5);
     int lead_orig = prev_vehicule(W, v);
+    LCP(6);
     if (lead_orig < 0 && !oblig && !desired && !force) break;
     if (!lane_change_phi(P, W, v, p1, fol, lead, lead_orig, tgt, force, &phi)) break;
+    LCP(7);
     code = LC_TEST; rf = fol; rt = tgt;
   } while (0);
   W.C.code[slot] = code; W.C.tl_pre[slot] = tl_pre; W.C.rfol[slot] = rf; W.C.rtgt[slot] = rt; W.C.phi[slot] = phi;
+  LCP(8);
 }
 // records of vehicle v for the passes >= from_pass; n = number of slots.  part 0: the mandatory stage, 1 / 2: first / second candidate lane
 // of the discretionary pass (independent of each other: the walk spreads them over threads); lc_eval_kind then classifies the events.
@@ -497,10 +541,10 @@ __global__ void k_lc_eval(DevNet N, DevVeh V, DevLc C, int n) {
 // pos / lane length, which the lane-to-lane projection of vehicule.cpp:2300 preserves); `full`: the whole link;
 // `preds`: also the links leading into this one (their vehicles look at the first vehicle of the next lane, :2408-2420).
 struct LcDirty { bool dirty, full, preds; double xlo, xhi; };
-__device__ inline void lc_window(const LcView& W, int lane, double pos, int excl, LcDirty* d) {
+__device__ __noinline__ void lc_window(const LcView& W, int lane, double pos, int excl, LcDirty* d) {
   double lo = -1, hi = -1;
   auto g = [&](double p) { if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } };
-  if (snap_has(W, lane)) { const LcSnap& S = *W.snap; for (int i = 0; i < S.n; i++) if (S.lane[i] == lane && S.v[i] != excl) g(S.p[i]); }
+  if (snap_has(W, lane)) { const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li]; for (int i = 0; i < cnt; i++) if (e[i].v != excl) g(e[i].p); }
   else {
     auto f = [&](int y) { if (y == excl) return; g(p1of(W, y)); };
     const int qa = slice_lb(W, lane, pos), qb = slice_ub(W, lane, pos);
@@ -527,7 +571,7 @@ __device__ inline bool lc_run_stage(const DevParams& P, const LcView& W, int v, 
 }
 constexpr int kLcBlock = 256;
 // one event at its turn, literally (thread 0): the stop event of a chunk — an accepted change or an event with side effects
-__device__ inline void lc_run_event(const DevParams& P, const LcView& W, int ev, int n, LcDirty* d) {
+__device__ __noinline__ void lc_run_event(const DevParams& P, const LcView& W, int ev, int n, LcDirty* d) {
   const DevNet& N = W.N; const DevVeh& V = W.V; const DevLc& C = W.C;
   const int pass = ev >= n; const int v = pass ? ev - n : ev;
   if (!pass) {                                                        // mandatory pass (reseau.cpp:4238-4262)
@@ -546,17 +590,22 @@ __device__ inline void lc_run_event(const DevParams& P, const LcView& W, int ev,
 }
 // copies the vehicles currently on link K into the shared-memory snapshot (whole block); the snapshot stays disabled when the link holds
 // more vehicles than it has room for
-__device__ inline void snap_build(const LcView& W, LcSnap* S, int K) {
+__device__ __noinline__ void snap_build(const LcView& W, LcSnap* S, int K) {
   const int tid = threadIdx.x;
-  if (tid == 0) { S->n = 0; S->link = -1; }
+  const int l0 = W.N.link_first[K], nl = W.N.link_nl[K], l1 = l0 + nl - 1;
+  if (tid == 0) { S->link = -1; S->lane0 = l0; S->nl = nl; S->over = nl > kSnapLanes; }
+  if (tid < kSnapLanes) { S->cnt[tid] = 0; S->len[tid] = tid < nl ? W.N.lane_len[l0 + tid] : 0.0; }
   __syncthreads();
-  const int l0 = W.N.link_first[K], l1 = l0 + W.N.link_nl[K] - 1;
-  const int a = W.C.lane_start[l0], b = W.C.lane_start[l1] + W.C.lane_count[l1];
-  auto put = [&](int y) { const int i = atomicAdd(&S->n, 1); if (i < kSnap) { S->v[i] = y; S->lane[i] = W.V.lane[y]; S->p[i] = p1of(W, y); S->id[i] = W.V.id[y]; S->prev[i] = W.V.prev_leader[y]; } };
-  for (int q = a + tid; q < b; q += blockDim.x) { const int y = W.C.order[q]; if (!W.C.moved[y] && W.V.status[y] == ST_ALIVE) put(y); }
-  if (tid == 0) for (int y = W.C.link_delta_head[K]; y >= 0; y = W.C.delta_next[y]) put(y);
+  if (nl <= kSnapLanes) {
+    const int a = W.C.lane_start[l0], b = W.C.lane_start[l1] + W.C.lane_count[l1];
+    auto put = [&](int y) { const int li = W.V.lane[y] - l0; if ((unsigned)li >= (unsigned)nl) { S->over = 1; return; }
+      const int i = atomicAdd(&S->cnt[li], 1); if (i >= kSnapCap) { S->over = 1; return; }
+      S->e[li][i] = SnapE{p1of(W, y), y, W.V.id[y]}; S->prev[li][i] = W.V.prev_leader[y]; };
+    for (int q = a + tid; q < b; q += blockDim.x) { const int y = W.C.order[q]; if (!W.C.moved[y] && W.V.status[y] == ST_ALIVE) put(y); }
+    if (tid == 0) for (int y = W.C.link_delta_head[K]; y >= 0; y = W.C.delta_next[y]) put(y);
+  }
   __syncthreads();
-  if (tid == 0 && S->n <= kSnap) S->link = K;
+  if (tid == 0) { if (!S->over) S->link = K; else for (int li = 0; li < kSnapLanes; li++) S->cnt[li] = 0; }
   __syncthreads();
 }
 constexpr int kLcList = 1024;
@@ -567,7 +616,7 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
   LcView W{N, V, C, rb, &rb_pos, &rb_fill, &rb_base, &srng, &snap};
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5; const int E = 2 * n;
   mt_load(srng, C.rng);
-  if (tid == 0) { rb_pos = rb_fill = rb_base = 0; snap.link = -1; snap.n = 0; }
+  if (tid == 0) { rb_pos = rb_fill = rb_base = 0; snap.link = -1; snap.nl = 0; }
   __syncthreads();
   int base = 0; long long walked = 0, reevals = 0;
 #ifdef SYM_LC_TIMING
@@ -632,7 +681,7 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
     const bool slow = from_pass ? (C.code[n + vcur] == LC_SLOW || C.code[2 * n + vcur] == LC_SLOW) : C.code[vcur] == LC_SLOW;
     if (!slow) snap_build(W, &snap, K0); else { if (tid == 0) snap.link = -1; __syncthreads(); }
 #ifdef SYM_LC_TIMING
-    tS += clock64() - c1; nsnap += snap.n;
+    tS += clock64() - c1; nsnap += snap.cnt[0] + snap.cnt[1] + snap.cnt[2] + snap.cnt[3];
 #endif
     if (tid == 0) {
       s_dirty_link = -1;
@@ -658,7 +707,8 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
       // which vehicles, from which pass on: entry = slot * 2 + (1 when only the discretionary pass is left)
       auto want = [&](int y) { int fp; if (from_pass == 0) fp = y > vcur ? 0 : 1; else if (y > vcur) fp = 1; else return;
         const int i = atomicAdd(&s_nlist, 1); if (i < kLcList) s_list[i] = y * 2 + fp; };
-      if (snap.link == K) { for (int i = tid; i < snap.n; i += kLcBlock) { if (!full) { const double x = snap.p[i] / N.lane_len[snap.lane[i]]; if (x < xlo || x > xhi) continue; } want(snap.v[i]); } }
+      if (snap.link == K) { for (int idx = tid; idx < snap.nl * kSnapCap; idx += kLcBlock) { const int li = idx / kSnapCap, i = idx % kSnapCap; if (i >= snap.cnt[li]) continue;
+          if (!full) { const double x = snap.e[li][i].p / snap.len[li]; if (x < xlo || x > xhi) continue; } want(snap.e[li][i].v); } }
       else { const int l0 = N.link_first[K], l1 = l0 + N.link_nl[K] - 1; const int a = C.lane_start[l0], b = C.lane_start[l1] + C.lane_count[l1];
         for (int q = a + tid; q < b; q += kLcBlock) { const int y = C.order[q]; if (!full) { const double x = p1of(W, y) / N.lane_len[V.lane[y]]; if (x < xlo || x > xhi) continue; } want(y); } }
       if (preds) for (int k = tid; k < N.n_links; k += kLcBlock) { if (k == K || N.link_down[k] != upn) continue;
@@ -705,6 +755,7 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
 #endif
   }
 #ifdef SYM_LC_TIMING
+  if (tid == 0) { printf("stage prof (thread 0, %lld stages):", g_lcprof[11]); for (int i = 0; i < 9; i++) { printf(" %lld", g_lcprof[i]); g_lcprof[i] = 0; } g_lcprof[11] = 0; printf("\n"); }
   if (tid == 0) printf("lc_walk E %d chunks %d stops %d dirty %d preds %d | total %lld eval %lld (fill %lld) event %lld (snap %lld, %d entries) reeval %lld (collect %lld parts %lld [own %lld] kinds %lld [own %lld]) cycles\n", E, nchunk, nstop, ndirty, npreds, clock64() - t0, tA, tF, tB, tS, nsnap, tC, tW, tP, tP0, tK, tK0);
 #endif
   if (walked) atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_EVENTS], (unsigned long long)walked);

@@ -596,20 +596,23 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
 // the tests of one entry done by the lanes together.  rec[k] = (offset of the first tested value without the draws of the visited points
 // before it, test limit, integer threshold, 0); cpre[k] = draws of the entries before k whose consumption does not depend on values;
 // out[k] = (inserted << 16) | tests made.  Stops at the first entry that is not a value-drawing point.  Out of line: its registers are its own.
-__device__ __noinline__ int walk_hard_run(const int4* rec, const int* cpre, const unsigned char* st, const int* hidx, int j0, int nh, int* out, int* hused,
+__device__ __noinline__ int walk_hard_run(const int4* rec, const int* cpre, const unsigned char* st, const int* hidx, int j0, int nh, int* out, int* hpre,
                                           int extra, int* H_io, const int* vals, int U) {
   const int lane = threadIdx.x & 31; int H = *H_io; int j = j0;
   for (; j < nh; j++) {
+    if (lane == 0) hpre[j] = H;
     const int k = hidx[j]; if (st[k] != MS_VALUES) break;
     const int4 r = rec[k]; const int start = r.x + extra + cpre[k] + H, lim = r.y, thr = r.z;
+    if (start + lim > U) break;                                                              // the values are not generated yet: the block moves the window
     int used = lim, ins = 0;
-    for (int d0 = 0; d0 < lim; d0 += 32) { const int d = d0 + lane, pos = start + d;
-      const bool hit = d < lim && (pos < U ? vals[pos] : 32767) < thr;
+    for (int d0 = 0; d0 < lim; d0 += 32) { const int d = d0 + lane;
+      const bool hit = d < lim && vals[start + d] < thr;
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (m) { used = d0 + __ffs(m); ins = 1; break; } }
-    if (lane == 0) { out[k] = (ins << 16) | used; hused[k] = used; }
+    if (lane == 0) out[k] = (ins << 16) | used;
     H += used;
   }
+  if (lane == 0) hpre[j] = H;
   *H_io = H;
   return j;
 }
@@ -764,14 +767,16 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
                                                   const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const u64* kf_total,
                                                   int* out, const int* guard) {
   constexpr int kBatch = 512, kRc = 4096;
-  __shared__ int sh_rb[kRc];                                                               // the look-ahead values, when they fit: thread 0 reads them one by one
-  __shared__ MtShared S; __shared__ int4 e_rec[kBatch]; __shared__ int e_pt[kBatch], e_res[kBatch], e_cpre[kBatch], e_hpre[kBatch], e_hused[kBatch], e_hidx[kBatch]; __shared__ unsigned char e_st[kBatch];
-  __shared__ int sh_next, sh_red2[8], sh_ctot, sh_nh, sh_H;
+  // the stream's values around the walk's position: sh_rb holds positions [sh_B, sh_B + sh_F) of the step's merge draws, S generates what follows.
+  // Positions only grow, so the window slides forward; nothing is generated beyond what is consumed plus one window.
+  __shared__ int sh_rb[kRc]; __shared__ int sh_B, sh_F;
+  __shared__ MtShared S; __shared__ int4 e_rec[kBatch]; __shared__ int e_pt[kBatch], e_res[kBatch], e_cpre[kBatch], e_hj[kBatch], e_hpre[kBatch + 1], e_hidx[kBatch]; __shared__ unsigned char e_st[kBatch], e_done[kBatch];
+  __shared__ int sh_next, sh_red2[8], sh_ctot, sh_nh, sh_H, sh_min, sh_flag;
   __shared__ int sh_red[8]; __shared__ int sh_total;
   if (guard && *guard == 0) return;
   const int tid = threadIdx.x;
 #ifdef SYM_WALK_TIMING
-  long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0;
+  long long tq0 = clock64(), tq2 = 0, tq3 = 0; int n_refill = 0;
 #endif
   const u64 tot = *kf_total; const int nf = (int)(tot >> 40); const int known_total = (int)(tot & ((1ULL << 40) - 1));
   if (nf == 0) {                                                                           // only count-only draws this step
@@ -779,44 +784,48 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
     if (tid == 0) { out[0] = known_total; M.counters[SYMGPU_CNT_MRG_DRAWS] += known_total; }
     return;
   }
-  // upper bound of the values the visited points may consume
-  int ub = 0;
-  for (int k = tid; k < nf; k += 256) { const int q = M.fsorted[k]; ub += M.st[q] == MS_VALUES ? M.kmax[q] : 256; }
-  for (int o = 16; o; o >>= 1) ub += __shfl_xor_sync(0xffffffffu, ub, o);
-  if ((tid & 31) == 0) sh_red[tid >> 5] = ub;
-  __syncthreads();
-  if (tid == 0) { int t = 0; for (int w = 0; w < 8; w++) t += sh_red[w]; sh_total = t; }
-  __syncthreads();
-#ifdef SYM_WALK_TIMING
-  tq1 = clock64();
-#endif
-  int U = known_total + sh_total; int overflow = 0;
-  if (U > M.rbuf_cap) { U = M.rbuf_cap; overflow = 1; }
   mt_load(S, M.rng);
-  rng_advance(S, (unsigned)U, M.rbuf);                                                     // look-ahead values (the state S is discarded afterwards)
-  __threadfence_block(); __syncthreads();
-  const int* vals = M.rbuf;
-  if (U <= kRc) { for (int k = tid; k < U; k += 256) sh_rb[k] = M.rbuf[k]; vals = sh_rb; __syncthreads(); }
+  if (tid == 0) { sh_B = 0; sh_F = 0; }
+  __syncthreads();
+  // make the positions [lo, hi) available (hi - lo <= kRc, lo never below an earlier lo); whole block, uniform arguments
+  auto ensure = [&](int lo, int hi) {
+    const int B = sh_B, F = sh_F;
+    if (hi <= B + F) return;
+    __syncthreads();
+    const int keep = max(0, B + F - lo); int tmp[kRc / 256]; int nk = 0;
+    for (int k = tid; k < keep; k += 256) tmp[nk++] = sh_rb[lo - B + k];
+    __syncthreads();
+    nk = 0; for (int k = tid; k < keep; k += 256) sh_rb[k] = tmp[nk++];
+    __syncthreads();
+    if (lo > B + F) rng_advance(S, (unsigned)(lo - (B + F)), nullptr);
+    rng_advance(S, (unsigned)(kRc - keep), sh_rb + keep);
+    if (tid == 0) { sh_B = lo; sh_F = kRc; }
+    __syncthreads();
+#ifdef SYM_WALK_TIMING
+    n_refill++;
+#endif
+  };
   const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
 #ifdef SYM_WALK_TIMING
   tq2 = clock64();
 #endif
   int extra = 0;                                                                           // draws consumed by the visited points beyond `known`
-  int n_values_t = 0, n_serial = 0;                                                        // n_values_t: per thread, summed at the end
+  int n_values_t = 0, n_serial = 0, overflow = 0;                                          // n_values_t: per thread, summed at the end
   for (int b0 = 0; b0 < nf; b0 += kBatch) {
     const int nb = min(kBatch, nf - b0);
     __syncthreads();
-    for (int k = tid; k < nb; k += 256) { const int q = M.fsorted[b0 + k]; e_pt[k] = q; e_st[k] = (unsigned char)M.st[q];
+    for (int k = tid; k < nb; k += 256) { const int q = M.fsorted[b0 + k]; e_pt[k] = q; e_st[k] = (unsigned char)M.st[q]; e_done[k] = 0;
       // the test `draw / 32767.0 < proba` as an integer threshold (exactly: the quotient is monotonic in the draw), so that the ordered visit is integer work
       const double pr = M.proba[q]; int T = (int)fmin(fmax(ceil(pr * 32767.0), 0.0), 32767.0); if (!(pr == pr)) T = 0;
       while (T <= 32766 && (T / 32767.0 < pr)) T++; while (T > 0 && !((T - 1) / 32767.0 < pr)) T--;
       const int off = (int)(M.kfo[q] & ((1ULL << 40) - 1));
       // VALUES: offset of the first tested value = point offset + count-only draws + the unused draw; tests while k < m_nRandNumbers, decremented per test: ceil(n / 2) at most
-      e_rec[k] = e_st[k] == MS_VALUES ? make_int4(off + M.pre[q] + 1, (M.kmax[q] + 1) >> 1, T, 0) : make_int4(off + 1, 0, 0, 0); }
+      int lim = (M.kmax[q] + 1) >> 1; if (lim > kRc) { lim = kRc; overflow = 1; }              // (a point left alone for more than 2 * kRc steps)
+      e_rec[k] = e_st[k] == MS_VALUES ? make_int4(off + M.pre[q] + 1, lim, T, 0) : make_int4(off + 1, 0, 0, 0); }
     __syncthreads();
     // Entries whose consumption does not depend on the values (one test at most: AbstractCarFollowing.cpp:362-374 tests while k < m_nRandNumbers,
-    // decremented per test) are offsets for the others and decided afterwards, in parallel; only the "hard" ones (two tests or more, and the
-    // points left to a literal visit) are walked in order.
+    // decremented per test) are offsets for the others and decided in parallel once the ordered visit has passed them; only the "hard" ones
+    // (two tests or more, and the points left to a literal visit) are walked in order.
     { const int i0 = 2 * tid, i1 = i0 + 1;                                                     // e_cpre = exclusive scan of the constant consumptions; hard entries compacted in order
       auto cons = [&](int k) { return k < nb && e_st[k] == MS_VALUES && e_rec[k].y <= 1 ? e_rec[k].y : 0; };
       auto hard = [&](int k) { return k < nb && !(e_st[k] == MS_VALUES && e_rec[k].y <= 1) ? 1 : 0; };
@@ -826,46 +835,56 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
       __syncthreads();
       int off = 0, hoff = 0; for (int w = 0; w < (tid >> 5); w++) { off += sh_red[w]; hoff += sh_red2[w]; }
       const int ex = off + incl - (a + b2), hex = hoff + hincl - (ha + hb);
-      if (i0 < nb) { e_cpre[i0] = ex; e_hused[i0] = 0; if (ha) e_hidx[hex] = i0; }
-      if (i1 < nb) { e_cpre[i1] = ex + a; e_hused[i1] = 0; if (hb) e_hidx[hex + ha] = i1; }
+      if (i0 < nb) { e_cpre[i0] = ex; e_hj[i0] = hex; if (ha) e_hidx[hex] = i0; }                // e_hj: hard entries before this one = index of the next hard entry at or after it
+      if (i1 < nb) { e_cpre[i1] = ex + a; e_hj[i1] = hex + ha; if (hb) e_hidx[hex + ha] = i1; }
       if (tid == 255) { sh_ctot = off + incl; sh_nh = hoff + hincl; }
       __syncthreads(); }
     const int nh = sh_nh; const int ctot = sh_ctot;
     if (tid == 0) sh_H = 0;
     __syncthreads();
-    for (int j = 0; j < nh;) {                                                                 // the ordered part
-      if (tid < 32) { int H = sh_H; const int jn = walk_hard_run(e_rec, e_cpre, e_st, e_hidx, j, nh, e_res, e_hused, extra, &H, vals, U); if (tid == 0) { sh_H = H; sh_next = jn; } }
+    int easy_from = 0;
+    for (int j = 0;;) {                                                                        // the ordered part; e_hpre[j] = draws the hard entries before j consumed
+      if (tid < 32) { int H = sh_H; const int jn = walk_hard_run(e_rec, e_cpre, e_st, e_hidx, j, nh, e_res, e_hpre, extra, &H, sh_rb - sh_B, sh_B + sh_F); if (tid == 0) { sh_H = H; sh_next = jn; } }
       __syncthreads();
       j = sh_next;
-      if (j < nh) {                                                                            // a point that shares a vehicle with another point and was not settled by k_mrg_dirty: literally, now
-        if (tid == 0) { const int k = e_hidx[j]; const int q = e_pt[k]; const int at = e_rec[k].x - 1 + extra + e_cpre[k] + sh_H; RngCursor C{vals, at, U, 0};
-          merge_point_serial(&W, q, &C);
-          e_hused[k] = C.pos - at; sh_H += C.pos - at; sh_red[1] = C.overflow; M.st[q] = MS_DONE; }
+      // the easy entries the visit has passed: their positions are known; decided from the window (moved forward if they lie beyond it)
+      const int klim = j < nh ? e_hidx[j] : nb;
+      for (;;) {
+        if (tid == 0) sh_min = INT_MAX;
         __syncthreads();
-        overflow |= sh_red[1]; n_serial++; j++;
+        const int B = sh_B, G = sh_B + sh_F;
+        for (int k = easy_from + tid; k < klim; k += 256) if (e_st[k] == MS_VALUES && e_rec[k].y <= 1 && !e_done[k]) {
+          const int pos = e_rec[k].x + extra + e_cpre[k] + e_hpre[e_hj[k]];
+          if (e_rec[k].y == 1 && pos >= G) { atomicMin(&sh_min, pos); continue; }
+          const bool ins = e_rec[k].y == 1 && sh_rb[pos - B] < e_rec[k].z;
+          e_res[k] = ((int)ins << 16) | e_rec[k].y; e_done[k] = 1; }
         __syncthreads();
+        const int mn = sh_min;
+        if (mn == INT_MAX) break;
+        ensure(mn, mn + 1);
       }
+      easy_from = klim;
+      if (j >= nh) break;
+      const int k = e_hidx[j];
+      if (e_st[k] == MS_VALUES) { const int start = e_rec[k].x + extra + e_cpre[k] + sh_H; ensure(start, start + e_rec[k].y); continue; }   // the window moves to this entry
+      // a point that shares a vehicle with another point and was not settled by k_mrg_dirty: literally, now
+      const int at = e_rec[k].x - 1 + extra + e_cpre[k] + sh_H;
+      ensure(at, at + kRc);                                                                    // (rare: a whole window, whatever the point draws)
+      if (tid == 0) { const int q = e_pt[k]; RngCursor C{sh_rb - sh_B, at, sh_B + sh_F, 0};
+        merge_point_serial(&W, q, &C);
+        sh_H += C.pos - at; sh_flag = C.overflow; M.st[q] = MS_DONE; }
+      __syncthreads();
+      overflow |= sh_flag; n_serial++; j++;
+      __syncthreads();
     }
-    { const int i0 = 2 * tid, i1 = i0 + 1;                                                     // e_hpre = exclusive scan of what the hard entries consumed
-      const int a = i0 < nb ? e_hused[i0] : 0, b2 = i1 < nb ? e_hused[i1] : 0; int incl = a + b2;
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
-      __syncthreads();
-      if ((tid & 31) == 31) sh_red[tid >> 5] = incl;
-      __syncthreads();
-      int off = 0; for (int w = 0; w < (tid >> 5); w++) off += sh_red[w];
-      const int ex = off + incl - (a + b2);
-      if (i0 < nb) e_hpre[i0] = ex; if (i1 < nb) e_hpre[i1] = ex + a;
-      __syncthreads(); }
-    for (int k = tid; k < nb; k += 256) if (e_st[k] == MS_VALUES) {                            // decisions out; the easy ones are made here
-      int d = e_res[k];
-      if (e_rec[k].y <= 1) { const int pos = e_rec[k].x + extra + e_cpre[k] + e_hpre[k]; const bool ins = e_rec[k].y == 1 && (pos < U ? vals[pos] : 32767) < e_rec[k].z; d = ((int)ins << 16) | e_rec[k].y; }
-      M.decide[e_pt[k]] = d; n_values_t++; }
+    for (int k = tid; k < nb; k += 256) if (e_st[k] == MS_VALUES) { M.decide[e_pt[k]] = e_res[k]; n_values_t++; }   // decisions out
     extra += ctot + sh_H;
     __syncthreads();
   }
   __syncthreads();
   if (n_values_t) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_VALUES], (unsigned long long)n_values_t);
-  if (tid == 0) { sh_total = known_total + extra; M.counters[SYMGPU_CNT_MRG_SERIAL] += n_serial; if (overflow) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL); }
+  if (tid == 0) { sh_total = known_total + extra; M.counters[SYMGPU_CNT_MRG_SERIAL] += n_serial; }
+  if (overflow) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL);
   __syncthreads();
 #ifdef SYM_WALK_TIMING
   tq3 = clock64();
@@ -873,7 +892,7 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
   const int total = sh_total;
   mt_load(S, M.rng); rng_advance(S, (unsigned)total, nullptr); mt_store(S, M.rng);         // the stream itself advances by what was consumed
 #ifdef SYM_WALK_TIMING
-  if (tid == 0) printf("walk nf %d U %d known %d extra %d | sort+ub %lld gen %lld loop %lld final %lld cycles\n", nf, U, known_total, extra, tq1 - tq0, tq2 - tq1, tq3 - tq2, clock64() - tq3);
+  if (tid == 0) printf("walk nf %d known %d extra %d refills %d | setup %lld loop %lld final %lld cycles\n", nf, known_total, extra, n_refill, tq2 - tq0, tq3 - tq2, clock64() - tq3);
 #endif
   if (tid == 0) { out[0] = total; M.counters[SYMGPU_CNT_MRG_DRAWS] += total; }
 }
