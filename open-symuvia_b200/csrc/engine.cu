@@ -517,7 +517,7 @@ struct symgpu_ctx {
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DBuf<double> vl_used; DevFlow df; FlowCtl* h_ctl = nullptr; FlowCtl* h_ctl_seed = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
-  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, u_key, s_key; DBuf<int> lc_moved, u_order, u_id, u_lane, s_id, s_lane; bool lc_seq = false; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
+  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, u_key, s_key; DBuf<int> lc_moved, u_order, u_id, u_lane, s_id, s_lane; bool lc_seq = false; int side_mask = 15; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
@@ -712,6 +712,7 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
   { const char* e = getenv("SYMGPU_COOP_LOOPS"); int co = 0; cudaDeviceGetAttribute(&co, cudaDevAttrCooperativeLaunch, device); c->coop_loops = co && !(e && !strcmp(e, "0")); }
   { const char* e = getenv("SYMGPU_DEBUG_SYNC"); c->dbg_sync = e && !strcmp(e, "1"); }
+  { const char* e = getenv("SYMGPU_SIDE"); c->side_mask = e ? atoi(e) : 15; }                            // experiments: bit 0 signals, 1 early stream advance, 2 shared points, 3 sensors on side streams
   { const char* e = getenv("SYMGPU_CTXCACHE"); c->use_cc = !(e && !strcmp(e, "0")); }                    // SYMGPU_CTXCACHE=0: every vehicle walks the tables every step (cross-check)
   if (c->use_cc) { CK(c->cc_lane.alloc(cap)); CK(cudaMemset(c->cc_lane.p, 0xff, cap * sizeof(int))); CK(c->cc_id.alloc(cap)); CK(cudaMemset(c->cc_id.p, 0xff, cap * sizeof(int)));
     CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); CK(cudaMemset(c->cc.p, 0xff, cap * sizeof(CtxCache))); }   // key (-1, -1): matches no vehicle
@@ -1046,7 +1047,7 @@ static int step_front(symgpu_ctx* c) {
   if (n > 0) { KBEGIN(c, KID_PREPARE); k_prepare<<<G(n), B, 0, s>>>(c->dv, n, c->lane_count.p); KEND(c); }
   // side stream, beside this step's lane ordering: the signal states of the step (read from k_context on) and the context memos
   // of the vehicles the last step listed; step_back waits for both (the lane-change phase too: it moves vehicles to other lanes)
-  const bool side_sig = c->net.n_sl() > 0 && c->profile != 1;                 // per-kernel timing (profile) keeps everything on one stream
+  const bool side_sig = c->net.n_sl() > 0 && c->profile != 1 && (c->side_mask & 1);                 // per-kernel timing (profile) keeps everything on one stream
   if (side_sig || c->cc_fill) {
     if (c->mp.on || c->ext_stream) { CK(cudaEventRecord(c->cc_go, s)); CK(cudaStreamWaitEvent(c->aux, c->cc_go, 0)); }   // else: the host waited for the last step, nothing is in flight
     if (side_sig) { k_signals<<<G(c->net.n_sl()), B, 0, c->aux>>>(c->ds, c->sl_i.p, c->net.n_sl(), c->t, c->sl_col.p, c->sl_prop.p); LAUNCH(c); }
@@ -1116,7 +1117,7 @@ static int step_back(symgpu_ctx* c) {
     if (n_sorted > 0) { KBEGIN(c, KID_CONTEXT);
       k_context<<<(n_sorted + SYM_CTX_THREADS - 1) / SYM_CTX_THREADS, SYM_CTX_THREADS, 0, s>>>(c->dn, c->dv, c->dl, n_sorted, c->order.p, c->lane_tail.p, c->rows.p, c->draws.p, (int*)&c->counters.p[SYMGPU_CNT_CTX_OVERFLOW],
                                                                                              c->mg.on ? c->mg.d.p : nullptr, c->t); KEND(c);
-      if (c->mg.on && !has_entries && c->profile != 1) {                     // this step's count-only draws are final: the stream passes them beside the relaxation
+      if (c->mg.on && !has_entries && c->profile != 1 && (c->side_mask & 2)) {                     // this step's count-only draws are final: the stream passes them beside the relaxation
         CK(cudaEventRecord(c->ev_fork, s)); CK(cudaStreamWaitEvent(c->aux2, c->ev_fork, 0));
         k_rng_ctx<<<1, 256, 0, c->aux2>>>(c->lc_rng.p, c->draws.p, c->mg.seen.p, nullptr); LAUNCH(c);
         CK(cudaEventRecord(c->ev_rng, c->aux2)); c->rng_wait = true; } }
@@ -1167,7 +1168,7 @@ static int step_back(symgpu_ctx* c) {
         KBEGIN(c, KID_MERGE); cudaMemsetAsync(g.flag.p, 0, sizeof(int), s);
         k_mrg_probe<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
         k_mrg_classify<<<Gp, B, 0, s>>>(g.h, guard); LAUNCH(c);
-        const bool side = c->profile != 1;                                          // the points that share vehicles are settled beside the clean ones
+        const bool side = c->profile != 1 && (c->side_mask & 4);                    // the points that share vehicles are settled beside the clean ones
         if (side) { cudaEventRecord(c->ev_fork, s); cudaStreamWaitEvent(c->aux2, c->ev_fork, 0); }
         k_mrg_dirty<<<1, 256, 0, side ? c->aux2 : s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
         if (side) cudaEventRecord(c->ev_dirty, c->aux2);
@@ -1189,7 +1190,7 @@ static int step_back(symgpu_ctx* c) {
                                                                                 c->next_sortie.p, c->t, c->P.dt, c->P.duree, guard); }
       KEND(c);
       if (c->mg.on && c->mg.h.n_sens > 0) { auto& g = c->mg;                  // merge sensors (reseau.cpp:14425-14458): rotate the windows, count the crossings of the step
-        const bool side = c->profile != 1; cudaStream_t q = side ? c->aux2 : s;       // beside the next step's lane ordering (step_back waits for ev_sens)
+        const bool side = c->profile != 1 && (c->side_mask & 8); cudaStream_t q = side ? c->aux2 : s;       // beside the next step's lane ordering (step_back waits for ev_sens)
         KBEGIN(c, KID_MERGE); if (side) { cudaEventRecord(c->ev_fork, s); cudaStreamWaitEvent(q, c->ev_fork, 0); }
         k_mrg_rotate<<<G(g.n_rows), B, 0, q>>>(g.h, g.n_upd + 1, g.n_rows, g.row_sens.p); LAUNCH(c);
         k_mrg_sensors<<<G(n), B, 0, q>>>(c->dn, c->dv, g.h, n, g.n_upd + 1); LAUNCH(c);

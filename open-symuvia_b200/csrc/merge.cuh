@@ -29,7 +29,7 @@ namespace symb200 {
 
 constexpr int kMrgInv = 12;       // vehicles one merge point may touch (waiting candidates, followers, leader, upstream memo misses)
 constexpr int kMrgLanes = kMaxCtx;
-enum : int { MS_NONE = 0, MS_DONE = 1, MS_VALUES = 2, MS_DIRTY = 3, MS_OVERFLOW = 4 };
+enum : int { MS_NONE = 0, MS_DONE = 1, MS_VALUES = 2, MS_DIRTY = 3, MS_OVERFLOW = 4, MS_SETTLED = 5 };   // MS_SETTLED: a shared point k_mrg_dirty has processed (k_mrg_eval, which may run beside it, must not take it for a clean one)
 enum : int { MM_PROBE = 0, MM_EVAL = 1, MM_DECIDED = 2, MM_SERIAL = 3 };
 
 struct DevMrg {
@@ -707,10 +707,16 @@ __global__ void __launch_bounds__(256) k_mrg_dirty(DevNet N, DevVeh V, DevMrg M,
       const int st = merge_point(W, p, MM_PROBE, A, nullptr);
       bool ok = !A.overflow && st != MS_VALUES;
       for (int k = 0; k < A.ninv && ok; k++) ok = M.mark[A.inv[k]] == key;                     // everything it touches NOW is its own
+#ifdef SYM_MRG_DEBUG
+      if (!ok) { if (A.overflow || st == MS_VALUES) printf("upd %d round %d pt %d left: %s\n", n_upd, round, p, A.overflow ? "overflow" : "values");
+        else for (int k = 0; k < A.ninv; k++) if (M.mark[A.inv[k]] != key) { const int z = A.inv[k]; const int r0 = M.own_min[z], r1 = M.own_max[z];
+          printf("upd %d round %d pt %d left: veh %d (id %d) owners %d..%d st %d mark pt %d round %u\n", n_upd, round, p, z, V.id[z], r0, r1, r1 >= 0 ? M.st[r1] : -1,
+                 (int)(0xFFFFFFFFu - (unsigned)(M.mark[z] & 0xFFFFFFFFu)), (unsigned)(M.mark[z] >> 32) - (unsigned)n_upd * 8u - 1u); } }
+#endif
       if (!ok) continue;                                                                       // left to the walk (literal, in order); the points behind it in its cluster wait with it
       if (st == MS_DONE) { MrgAcc B; B.ninv = 0; B.ndraw = 0; B.overflow = false; merge_point(W, p, MM_EVAL, B, nullptr); M.ndraw[p] = B.ndraw; M.kf[p] = (unsigned long long)B.ndraw; }
       else { M.ndraw[p] = 0; M.kf[p] = 0ULL; }
-      M.st[p] = MS_DONE; s_progress = 1; }
+      M.st[p] = MS_SETTLED; s_progress = 1; }
     __threadfence(); __syncthreads();
     if (!s_progress) break;
     __syncthreads();

@@ -146,6 +146,31 @@ def test_lane_changing_without_origins(synth):
     _check(s)
 
 
+def test_side_streams_do_not_change_results(synth, pkg, monkeypatch):
+    """The merge phase settles the points that share a vehicle beside the clean ones, the merge sensors beside the next step's lane
+    ordering, the count-only draws beside the relaxation: with everything on one stream (SYMGPU_SIDE=0) the state must be the same,
+    step after step (a point settled by k_mrg_dirty used to be taken again by k_mrg_eval when it happened to run later)."""
+    import os
+    import tempfile
+    fd, path = tempfile.mkstemp(suffix=".symflat")
+    os.close(fd)
+    synth.fast_grid(path, 40, 40, 12.6, n_steps=100, merges=True)
+    monkeypatch.setenv("SYMGPU_SIDE", "15")
+    a = pkg.Engine(path)
+    monkeypatch.setenv("SYMGPU_SIDE", "0")
+    b = pkg.Engine(path)
+    os.unlink(path)
+    for k in range(80):
+        a.step()
+        b.step()
+        assert a.n == b.n and a.rng_count == b.rng_count, k
+        if k % 10 == 9:
+            sa, sb = a.state(), b.state()
+            for key in ("id", "lane", "pos", "vit", "acc"):
+                assert np.array_equal(sa[key], sb[key]), (k, key)
+    assert a.counter(pkg.CNT_MRG_INS) == b.counter(pkg.CNT_MRG_INS) > 1000
+
+
 def test_c4_full_size_prefix_and_invariants(synth, pkg):
     """BASELINE config C4 at full size (100x100, ~1M vehicles): oracle parity on the first steps, then
     size-independent invariants over a longer run: no follower passes its leader on a lane, positions stay
