@@ -177,13 +177,31 @@ __device__ inline void immobilise(const MrgView& W, int x, int lane, bool acc_si
   set_acc_m(W, x, acc_sic ? W.V.vit[x] / W.P.dt : (W.V.vit_n[x] - W.V.vit[x]) / W.P.dt);
   update_used(W, x);
 }
+// first index k in [k0, re) with route_links[k] == link, or re.  The route entries are read four at a time: the reads do not depend on
+// each other, only the early exit does (a merge point is a chain of dependent reads; this one was a quarter of it)
+__device__ inline int route_find(const MrgView& W, int k0, int re, int link) {
+  const int* rl = W.N.route_links;
+  for (int k = k0; k < re; k += 4) {
+    const int a = rl[k], b = rl[min(k + 1, re - 1)], c = rl[min(k + 2, re - 1)], d = rl[min(k + 3, re - 1)];
+    if (a == link) return k;
+    if (b == link && k + 1 < re) return k + 1;
+    if (c == link && k + 2 < re) return k + 2;
+    if (d == link && k + 3 < re) return k + 3;
+  }
+  return re;
+}
 // Vehicule::IsItineraire vehicule.cpp:4060-4160
 __device__ inline bool is_itineraire(const MrgView& W, int x, int link) {
   const int ro = W.N.route_off[W.V.route[x]], re = W.N.route_off[W.V.route[x] + 1];
-  for (int k = ro; k < re; k++) if (W.N.route_links[k] == link) return true;
+  if (route_find(W, ro, re, link) < re) return true;
   const int br = W.N.link_brick[link];
-  if (br >= 0) for (int k = ro; k + 1 < re; k++) if (W.N.link_down[W.N.route_links[k]] == br)
-    for (int m = W.M.lmv0[link]; m < W.M.lmv0[link + 1]; m++) if (W.M.lmv_ent[m] == W.N.route_links[k] && W.M.lmv_exit[m] == W.N.route_links[k + 1]) return true;
+  if (br >= 0) for (int k0 = ro; k0 + 1 < re; k0 += 4) {                                     // the link is inside a junction: a movement of the route goes through it
+    int rk[5], dn[4];
+    for (int j = 0; j < 5; j++) rk[j] = W.N.route_links[min(k0 + j, re - 1)];
+    for (int j = 0; j < 4; j++) dn[j] = W.N.link_down[rk[j]];
+    for (int j = 0; j < 4 && k0 + j + 1 < re; j++) if (dn[j] == br)
+      for (int m = W.M.lmv0[link]; m < W.M.lmv0[link + 1]; m++) if (W.M.lmv_ent[m] == rk[j] && W.M.lmv_exit[m] == rk[j + 1]) return true;
+  }
   return false;
 }
 // Vehicule::CalculPosition vehicule.cpp:4615-4760 over Reseau::ComputeItineraireComplet (reseau.cpp:14002-14032)
@@ -192,8 +210,18 @@ __device__ inline double calcul_position(const MrgView& W, int x, double tr, int
   const int l1 = W.V.lane[x]; const int k1 = W.N.lane_link[l1], kt = W.N.lane_link[lane];
   if (kt == k1) return p;
   const int ro = W.N.route_off[W.V.route[x]], re = W.N.route_off[W.V.route[x] + 1];
+  // The complete itinerary (links and the internal links of the first movement between two of them) is walked from its start to the vehicle's
+  // link k1, then on to kt.  Before k1 is met nothing is accumulated, so the walk may start where k1 first appears: at its first index in the
+  // route when it is a link of the route, or at the first pair (entry link, exit link) of the route that one of its movements joins when it is
+  // inside a junction (the internal links of other pairs cannot be k1).
+  int ks = re;
+  if (W.N.link_brick[k1] < 0) ks = route_find(W, ro, re, k1);
+  else {
+    for (int k = ro + 1; k < re && ks == re; k++) { const int prev = W.N.route_links[k - 1], cur = W.N.route_links[k];
+      for (int m = W.M.lmv0[k1]; m < W.M.lmv0[k1 + 1]; m++) if (W.M.lmv_ent[m] == prev && W.M.lmv_exit[m] == cur) { ks = k; break; } }
+  }
   bool started = false;
-  for (int k = ro; k < re; k++) {
+  for (int k = ks; k < re; k++) {
     const int cur = W.N.route_links[k];
     if (k > ro) {                                                                          // internal links of the first movement between route[k-1] and route[k]
       const int prev = W.N.route_links[k - 1];
@@ -664,7 +692,7 @@ __global__ void k_mrg_classify(DevMrg M, const int* guard) {
   if (st == MS_NONE) return;
   bool clean = st != MS_OVERFLOW;
   for (int k = 0; k < M.ninv[p] && clean; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p) clean = false; }
-  if (!clean) { M.st[p] = MS_DIRTY; M.kf[p] = 1ULL << 40; const int dpos = atomicAdd(M.n_dirty, 1); M.dlist[dpos] = p;
+  if (!clean) { M.st[p] = MS_DIRTY; M.decide[p] = st; M.kf[p] = 1ULL << 40; const int dpos = atomicAdd(M.n_dirty, 1); M.dlist[dpos] = p;   // decide[p]: what the probe found, for the first round of k_mrg_dirty
 #ifdef SYM_MRG_DEBUG
     if (dpos < 6) { for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; if (M.own_min[x] != p || M.own_max[x] != p)
       printf("dirty pt %d (down lane %d, nvam %d) inv[%d of %d] veh slot %d shared with points %d..%d\n", p, M.pt_down[p], M.pt_nvam[p], k, M.ninv[p], x, M.own_min[x], M.own_max[x]); } }
@@ -704,8 +732,9 @@ __global__ void __launch_bounds__(256) k_mrg_dirty(DevNet N, DevVeh V, DevMrg M,
       bool ready = true; for (int k = 0; k < M.ninv[p] && ready; k++) ready = M.mark[M.inv[p * kMrgInv + k]] == key;
       if (!ready) continue;
       MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
-      const int st = merge_point(W, p, MM_PROBE, A, nullptr);
-      bool ok = !A.overflow && st != MS_VALUES;
+      int st; bool ok;
+      if (round == 0) { st = M.decide[p]; ok = st != MS_OVERFLOW && st != MS_VALUES; }           // nothing it touches has changed since the probe of the step
+      else { st = merge_point(W, p, MM_PROBE, A, nullptr); ok = !A.overflow && st != MS_VALUES; }
       for (int k = 0; k < A.ninv && ok; k++) ok = M.mark[A.inv[k]] == key;                     // everything it touches NOW is its own
 #ifdef SYM_MRG_DEBUG
       if (!ok) { if (A.overflow || st == MS_VALUES) printf("upd %d round %d pt %d left: %s\n", n_upd, round, p, A.overflow ? "overflow" : "values");
