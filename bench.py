@@ -334,8 +334,8 @@ def main():
     roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # DRAM bytes (read + write) of the dominant kernel's launches of one step, from the ncu --set full capture summarised in
             # profiles/r1g_summary.md (C4: k_relax 350 B, k_context 529 B per vehicle-step); other cases: not captured
-            "traffic": (measured_dram_bytes().get(dom) if a.workload == "C4" and world == 1 else None),
-            "traffic_note": "DRAM bytes read + written by the group's launches of one C4 step, ncu capture committed as profiles/r2_dram_bytes.json (null: not captured for this workload)",
+            "traffic": (measured_dram_bytes().get(dom) if a.workload == "C4" and not partitioned else None),
+            "traffic_note": "DRAM bytes read + written by the group's launches of one C4 step, ncu capture committed as profiles/r2_dram_bytes.json (per GPU; null: not captured for this workload)",
             "peak_source": peak_src, "launches_in_region": dom_launches, "avg_launch_ms": dom_ms / max(1, dom_launches),
             "alg_bytes_per_vehicle_step": B_ALG, "whole_step_frac": B_ALG * vsteps / (dev_ms / 1e3) / 1e9 / peak,
             "kernel_timed_in": dom_where,
@@ -345,14 +345,16 @@ def main():
             "ms_per_step": 1e3 * t_max / a.steps, "higher_is_better": True, "scaling": ("strong" if a.workload == "C5" else "weak"), "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": dict(base_cfg, parallelism=("1 GPU" if world == 1 else
-                                                  f"{world} replicas, one C4 network (with merge points) per GPU, different seeds, no data-path collective (merge points are not partitioned yet: DESIGN.md section 8)" if not partitioned else
+                                                  f"{world} replicas, one C4 network (with merge points) per GPU, different seeds, no data-path collective (merge points are not partitioned yet: DESIGN.md section 7)" if not partitioned else
                                                   (f"one MERGE-FREE {100 * world}x100 grid cut into {world} vertical strips of 100x100 junctions" if a.workload != "C5" else f"the merge-free 300x300 grid cut into {world} vertical strips") +
                                                   ", one per GPU; per step: all_to_all of boundary-lane tails + one fixed-size all_to_all of migrating vehicles (NCCL)"),
                            merge_points=not partitioned,
                            vehicles_per_gpu=info["n_init"], lanes_per_gpu=info["n_lanes"]),
             "e2e": {"value": e2e, "unit": "vehicle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(rows) * 32,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps, "d2h_copy_ms_per_step": copy_ms / max(1, e2e_steps),
-                    "note": "symgpu_step_traj_async: rows of step k packed and copied to page-locked host buffers on a side stream while step k+1 runs; C4 has no origins so the per-step host input is empty"},
+                    "note": "symgpu_step_traj_async: rows of step k packed and copied to page-locked host buffers on a side stream while step k+1 runs; "
+                            + ("the origins' new vehicles (about 100 bytes each, a few per step) are uploaded by the engine inside the step and not counted in h2d_bytes_per_step" if a.workload == "C3"
+                               else "the workload has no origins, so the per-step host input is empty")},
             "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks, "roofline": roof,
             "loops_broken": g.counter(pkg.CNT_LOOPS), "follow_passes": g.counter(pkg.CNT_PASSES)}
     if rank == 0 and world == 1 and a.cpu_steps > 0:

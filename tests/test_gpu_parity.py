@@ -172,15 +172,16 @@ def test_side_streams_do_not_change_results(synth, pkg, monkeypatch):
 
 
 def test_c4_full_size_prefix_and_invariants(synth, pkg):
-    """BASELINE config C4 at full size (100x100, ~1M vehicles): oracle parity on the first steps, then
+    """BASELINE config C4 at full size (100x100, ~1M vehicles): oracle parity on the first 100 steps (tools/gpu_long_parity.py runs it
+    further: bit-exact through step 245, see DESIGN.md section 6 for what happens at step 246), then
     size-independent invariants over a longer run: no follower passes its leader on a lane, positions stay
     within the lane, the population only shrinks by exits."""
     import os
     import tempfile
     b = synth.config("C4")
-    s = run_parity(b, 50, check_every=10)
+    s = run_parity(b, 100, check_every=20)
     _check(s)
-    assert s["merge_ins"] == s["merge_ins_oracle"] > 100000
+    assert s["merge_ins"] == s["merge_ins_oracle"] > 300000
     fd, path = tempfile.mkstemp(suffix=".symflat")
     os.close(fd)
     b.write(path)
