@@ -139,6 +139,14 @@ constexpr int kSnapLanes = 4, kSnapCap = 96;
 // link then scan this copy (one 16-byte record per vehicle) instead of chasing the lane slices through global memory
 struct SnapE { double p; int v; int id; };
 struct LcSnap { int link, lane0, nl, over; int cnt[kSnapLanes]; double len[kSnapLanes]; SnapE e[kSnapLanes][kSnapCap]; int prev[kSnapLanes][kSnapCap]; };
+#ifdef SYM_LC_TIMING
+__device__ long long g_lcprof2[12];
+#define LCQ(i) do { long long t_ = clock64(); g_lcprof2[i] += t_ - tq_; tq_ = t_; } while (0)
+#define LCQ0 long long tq_ = clock64()
+#else
+#define LCQ(i) do { } while (0)
+#define LCQ0 do { } while (0)
+#endif
 struct LcView { const DevNet& N; const DevVeh& V; const DevLc& C; int* rb = nullptr; int* rb_pos = nullptr; int* rb_fill = nullptr; int* rb_base = nullptr; MtShared* srng = nullptr; LcSnap* snap = nullptr; };
 constexpr int kRb = 2048;
 // make at least `need` upcoming draws available in the buffer (one thread)
@@ -251,54 +259,67 @@ __device__ __noinline__ int snap_ties(const LcSnap& S, int li, double at, int ex
   for (int i = 0; i < cnt; i++) if (e[i].p == at && e[i].v != excl && n < kTie) c[n++] = i;
   return n;
 }
+// The scans keep no branch inside the loop (selects on the extreme position, then a count of the vehicles standing there) and read
+// the records four at a time before using them: the reads overlap and two threads of a warp scanning different lanes do not take turns.
+template <class F> __device__ __forceinline__ void snap_scan(const SnapE* e, int cnt, F f) {
+  for (int i0 = 0; i0 < cnt; i0 += 4) {
+    SnapE x[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[j] = e[min(i0 + j, cnt - 1)];
+#pragma unroll
+    for (int j = 0; j < 4; j++) f(x[j], i0 + j < cnt);
+  }
+}
 __device__ __forceinline__ int snap_near_aval(const LcView& W, int lane, double pos, int excl) {
   const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
-  double pv = S.len[li] + 0.00001; int bv = -1, nt = 0;
-#pragma unroll 4
-  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
-    if (x.v != excl && x.p >= pos && x.p <= pv) { if (x.p == pv) { if (nt == 0) bv = x.v; nt++; } else { pv = x.p; bv = x.v; nt = 1; } } }
+  const double bound = S.len[li] + 0.00001; double pv = DBL_MAX; int bv = -1;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { const bool better = in && x.v != excl && x.p >= pos && x.p <= bound && x.p < pv; pv = better ? x.p : pv; bv = better ? x.v : bv; });
+  if (bv < 0) return -1;
+  int nt = 0;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { nt += (in && x.p == pv && x.v != excl) ? 1 : 0; });
   if (nt <= 1) return bv;
   int c[kTie]; const int n = snap_ties(S, li, pv, excl, c);
   return snap_pick_last(S, li, c, n);
 }
 __device__ __forceinline__ int snap_near_amont(const LcView& W, int lane, double pos, int excl) {
   const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
-  double pt = -99999; int bv = -1, nt = 0;
-#pragma unroll 4
-  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
-    if (x.v != excl && pos > x.p && x.p >= pt) { if (x.p == pt) { if (nt == 0) bv = x.v; nt++; } else { pt = x.p; bv = x.v; nt = 1; } } }
-  if (nt == 0 || !((pos - pt) < 9999)) return -1;
-  if (nt == 1) return bv;
+  double pt = -DBL_MAX; int bv = -1;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { const bool better = in && x.v != excl && pos > x.p && x.p >= -99999 && x.p > pt; pt = better ? x.p : pt; bv = better ? x.v : bv; });
+  if (bv < 0 || !((pos - pt) < 9999)) return -1;
+  int nt = 0;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { nt += (in && x.p == pt && x.v != excl) ? 1 : 0; });
+  if (nt <= 1) return bv;
   int c[kTie]; const int n = snap_ties(S, li, pt, excl, c);
   return snap_pick_first(S, li, c, n);
 }
-__device__ __forceinline__ int snap_first_vehicule(const LcView& W, int lane) {
+__device__ __forceinline__ int snap_first_vehicule(const LcView& W, int lane) {               // the largest position (>= 0), the largest id among equals
   const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
-  int r = -1; double p = 0; int rid = -1;
-#pragma unroll 4
-  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
-    if (x.p > p || (x.p == p && (r < 0 || x.id > rid))) { if (x.p >= p) { r = x.v; p = x.p; rid = x.id; } } }
+  int r = -1; double p = -1; int rid = -1;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { const bool better = in && x.p >= 0 && (x.p > p || (x.p == p && x.id > rid)); p = better ? x.p : p; r = better ? x.v : r; rid = better ? x.id : rid; });
   return r;
 }
 __device__ __forceinline__ int snap_prev_vehicule(const LcView& W, int v, int lane, double own) {
   const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li];
-  double pv = S.len[li] + 1; int bv = -1, nt = 0;
-#pragma unroll 4
-  for (int i = 0; i < cnt; i++) { const SnapE x = e[i];
-    if (x.v != v && x.p > own && x.p <= pv) { if (x.p == pv) { if (nt == 0) bv = x.v; nt++; } else { pv = x.p; bv = x.v; nt = 1; } } }
+  const double bound = S.len[li] + 1; double pv = DBL_MAX; int bv = -1;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { const bool better = in && x.v != v && x.p > own && x.p <= bound && x.p < pv; pv = better ? x.p : pv; bv = better ? x.v : bv; });
+  if (bv < 0) return -1;
+  int nt = 0;
+  snap_scan(e, cnt, [&](const SnapE& x, bool in) { nt += (in && x.p == pv && x.v != v) ? 1 : 0; });
   if (nt <= 1) return bv;
   int c[kTie]; const int n = snap_ties(S, li, pv, v, c);
   return snap_pick_last(S, li, c, n);
 }
-__device__ inline void snap_update(const LcView& W, int v, int lane, double pos) {            // v moved (one thread)
+__device__ inline void snap_update(const LcView& W, int v, int old_lane, int lane, double pos) {            // v moved from old_lane (one thread)
   if (!snap_has(W, lane)) return;
-  LcSnap& S = *W.snap; const int ln = lane - S.lane0;
-  for (int li = 0; li < S.nl; li++) for (int i = 0; i < S.cnt[li]; i++) if (S.e[li][i].v == v) {
-    SnapE x = S.e[li][i]; const int pr = S.prev[li][i]; x.p = snap_pos(pos);
-    if (li == ln) { S.e[li][i] = x; return; }
-    const int last = --S.cnt[li]; S.e[li][i] = S.e[li][last]; S.prev[li][i] = S.prev[li][last];
-    if (S.cnt[ln] >= kSnapCap) { S.link = -1; return; }
-    const int k = S.cnt[ln]++; S.e[ln][k] = x; S.prev[ln][k] = pr; return; }
+  LcSnap& S = *W.snap; const int ln = lane - S.lane0, li = old_lane - S.lane0;
+  if ((unsigned)li < (unsigned)S.nl) { const int cnt = S.cnt[li]; int i = -1;
+    for (int k = 0; k < cnt; k++) i = S.e[li][k].v == v ? k : i;
+    if (i >= 0) {
+      SnapE x = S.e[li][i]; const int pr = S.prev[li][i]; x.p = snap_pos(pos);
+      if (li == ln) { S.e[li][i] = x; return; }
+      const int last = --S.cnt[li]; S.e[li][i] = S.e[li][last]; S.prev[li][i] = S.prev[li][last];
+      if (S.cnt[ln] >= kSnapCap) { S.link = -1; return; }
+      const int k = S.cnt[ln]++; S.e[ln][k] = x; S.prev[ln][k] = pr; return; } }
   S.link = -1;                                                                               // not in the copy: the copy cannot be trusted
 }
 __device__ __noinline__ int near_aval(const LcView& W, int lane, double pos, int excl) {           // reseau.cpp:3583-3640
@@ -411,16 +432,21 @@ __device__ inline bool test_lane_change(const DevParams& P, const LcView& W, int
   return r < phi;
 }
 __device__ __noinline__ void changement_voie(const LcView& W, int v, int tgt, int fol) {            // vehicule.cpp:2657-2711
+  LCQ0;
   W.C.chgt[v] = 1;
   int old = W.V.lane[v]; int link = W.N.lane_link[old];
   double p = p1of(W, v) * W.N.lane_len[tgt] / W.N.lane_len[old];
   W.V.lane[v] = tgt;
   if (fol >= 0 && W.N.lane_link[W.V.lane[fol]] == link) p = fmax(p, p1of(W, fol));
   W.V.pos[v] = p;
+  LCQ(2);
   lc_mark_moved(W, v);
-  snap_update(W, v, tgt, p);
+  LCQ(3);
+  snap_update(W, v, old, tgt, p);
+  LCQ(4);
   W.C.vdes[v] = -1;
   next_voie_draw(W, v, tgt);
+  LCQ(5);
   atomicAdd(W.C.n_changes, 1);
 }
 __device__ __noinline__ bool calcul_changement_voie(const DevParams& P, const LcView& W, int v, int tgt_num, bool force) {   // vehicule.cpp:2248-2457
@@ -544,7 +570,9 @@ struct LcDirty { bool dirty, full, preds; double xlo, xhi; };
 __device__ __noinline__ void lc_window(const LcView& W, int lane, double pos, int excl, LcDirty* d) {
   double lo = -1, hi = -1;
   auto g = [&](double p) { if (p < pos) { if (lo < 0 || p > lo) lo = p; } else if (p > pos) { if (hi < 0 || p < hi) hi = p; } };
-  if (snap_has(W, lane)) { const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li]; for (int i = 0; i < cnt; i++) if (e[i].v != excl) g(e[i].p); }
+  if (snap_has(W, lane)) { const LcSnap& S = *W.snap; const int li = lane - S.lane0; const SnapE* e = S.e[li]; const int cnt = S.cnt[li]; double l2 = -1, h2 = DBL_MAX;
+    snap_scan(e, cnt, [&](const SnapE& x, bool in0) { const bool in = in0 && x.v != excl; l2 = (in && x.p < pos && x.p > l2) ? x.p : l2; h2 = (in && x.p > pos && x.p < h2) ? x.p : h2; });
+    lo = l2; hi = h2 == DBL_MAX ? -1 : h2; }
   else {
     auto f = [&](int y) { if (y == excl) return; g(p1of(W, y)); };
     const int qa = slice_lb(W, lane, pos), qb = slice_ub(W, lane, pos);
@@ -556,17 +584,24 @@ __device__ __noinline__ void lc_window(const LcView& W, int lane, double pos, in
 }
 // one stage of an event at its turn (thread 0 of k_lc_walk)
 __device__ inline bool lc_run_stage(const DevParams& P, const LcView& W, int v, int slot, int tgt_num, bool force, LcDirty* d) {
+  LCQ0;
   const int code = W.C.code[slot];
   if (code == LC_SLOW) { d->dirty = d->full = d->preds = true; return calcul_changement_voie(P, W, v, tgt_num, force); }
   const int tl = W.C.tl_pre[slot];
   if (tl >= 0 && memo_touch(&W.V.memo[v * kMemo], tl)) lc_draw(W);
-  if (code != LC_TEST) return false;
+  if (code != LC_TEST) { LCQ(0); return false; }
   double r = lc_draw(W) / 32767.0;
-  if (!(r < W.C.phi[slot])) return false;
+  if (!(r < W.C.phi[slot])) { LCQ(0); return false; }
   d->dirty = true;
+  LCQ(0);
   lc_window(W, W.V.lane[v], p1of(W, v), v, d);
+  LCQ(1);
   changement_voie(W, v, W.C.rtgt[slot], W.C.rfol[slot]);
+#ifdef SYM_LC_TIMING
+  tq_ = clock64();
+#endif
   lc_window(W, W.V.lane[v], p1of(W, v), v, d);
+  LCQ(6);
   return true;
 }
 constexpr int kLcBlock = 256;
@@ -756,6 +791,7 @@ __global__ void __launch_bounds__(kLcBlock) k_lc_walk(DevNet N, DevVeh V, DevLc 
   }
 #ifdef SYM_LC_TIMING
   if (tid == 0) { printf("stage prof (thread 0, %lld stages):", g_lcprof[11]); for (int i = 0; i < 9; i++) { printf(" %lld", g_lcprof[i]); g_lcprof[i] = 0; } g_lcprof[11] = 0; printf("\n"); }
+  if (tid == 0) { printf("event prof:"); for (int i = 0; i < 7; i++) { printf(" %lld", g_lcprof2[i]); g_lcprof2[i] = 0; } printf("\n"); }
   if (tid == 0) printf("lc_walk E %d chunks %d stops %d dirty %d preds %d | total %lld eval %lld (fill %lld) event %lld (snap %lld, %d entries) reeval %lld (collect %lld parts %lld [own %lld] kinds %lld [own %lld]) cycles\n", E, nchunk, nstop, ndirty, npreds, clock64() - t0, tA, tF, tB, tS, nsnap, tC, tW, tP, tP0, tK, tK0);
 #endif
   if (walked) atomicAdd((unsigned long long*)&C.counters[SYMGPU_CNT_LC_EVENTS], (unsigned long long)walked);
