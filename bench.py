@@ -275,12 +275,6 @@ def main():
     def kernel_table():
         return {L.symgpu_kernel_name(k).decode(): (L.symgpu_kernel_ms(g.h, k), L.symgpu_kernel_launches(g.h, k)) for k in range(L.symgpu_kernel_count())}
     kms_timed = kernel_table()
-    # per-kernel breakdown: a second pass of K steps with every kernel group bracketed by events (not part of `value`)
-    L.symgpu_profile(g.h, 1)
-    vs1 = L.symgpu_vehicle_steps(g.h)
-    run_steps(a.steps)
-    vsteps_bd = L.symgpu_vehicle_steps(g.h) - vs1
-    kms = kernel_table()
     L.symgpu_profile(g.h, 0)
     t_max = allmax(dev_ms / 1e3)
     total_vsteps = allsum(float(vsteps))
@@ -323,6 +317,13 @@ def main():
     e2e_t = allmax(time.perf_counter() - t0)
     e2e = allsum(float(ev)) / e2e_t
     clocks = sampler.stop()
+    # per-kernel breakdown: a last pass of K steps with every kernel group bracketed by events (not part of `value`)
+    L.symgpu_profile(g.h, 1)
+    vs1 = L.symgpu_vehicle_steps(g.h)
+    run_steps(a.steps)
+    vsteps_bd = L.symgpu_vehicle_steps(g.h) - vs1
+    kms = kernel_table()
+    L.symgpu_profile(g.h, 0)
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------------
     peak, peak_src = peak_hbm()
     dom = max(kms, key=lambda k: kms[k][0])
@@ -356,7 +357,10 @@ def main():
                             + ("the origins' new vehicles (about 100 bytes each, a few per step) are uploaded by the engine inside the step and not counted in h2d_bytes_per_step" if a.workload == "C3"
                                else "the workload has no origins, so the per-step host input is empty")},
             "gpu_launches": int(launches), "wall_s": wall, "clocks": clocks, "roofline": roof,
-            "loops_broken": g.counter(pkg.CNT_LOOPS), "follow_passes": g.counter(pkg.CNT_PASSES)}
+            "loops_broken": g.counter(pkg.CNT_LOOPS), "follow_passes": g.counter(pkg.CNT_PASSES),
+            # which time steps of the run each pass covered (the simulation goes on from pass to pass; later steps of C4 are more congested and slower)
+            "step_windows": {"warmup": [1, warm], "value": [warm + 1, warm + a.steps], "e2e": [warm + a.steps + 1, warm + a.steps + e2e_steps],
+                             "kernel_breakdown": [warm + a.steps + e2e_steps + 1, warm + 2 * a.steps + e2e_steps]}}
     if rank == 0 and world == 1 and a.cpu_steps > 0:
         per = max(1, a.cpu_steps // 5)
         rate, dt, tot = cpu_oracle_rate(path, info, per, repeats=5)

@@ -517,11 +517,11 @@ struct symgpu_ctx {
   DBuf<unsigned long long> f_rootkey; DBuf<FlowCtl> f_ctl; DBuf<double> vl_used; DevFlow df; FlowCtl* h_ctl = nullptr; FlowCtl* h_ctl_seed = nullptr;
   DBuf<double> next_sortie; DBuf<long long> counters; DBuf<unsigned> draws; DBuf<ExitRow> exited; DBuf<EntryDesc> edesc; DBuf<int> eresult;
   // vehicles
-  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, u_key, s_key; DBuf<int> lc_moved, u_order, u_id, u_lane, s_id, s_lane; bool lc_seq = false; int side_mask = 15; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
+  DBuf<int> v_vdes, lc_voies_ok, lc_chgt, lc_delta_next, lc_link_head, lc_nchg, link_down, lc_tl_pre, lc_rfol, lc_rtgt, lc_had_mand; DBuf<unsigned char> lc_kind, lc_code; DBuf<double> lc_phi, u_key, s_key; DBuf<int> lc_moved, u_order, u_id, u_lane, s_id, s_lane; bool lc_seq = false; int side_mask = 31; DBuf<DevRng> lc_rng; DevLc dlc; bool chgtvoie = false;
   DBuf<int> v_status, v_id, v_cls, v_route, v_rpos, v_lane, v_lane_n, v_pl, v_flags, v_oflags, v_memo, v_ahead, v_computed, v_ctx_nl,
       v_ctx_lane, v_ctx_leader, v_ctx_flags;
   DBuf<double> v_pos, v_vit, v_acc, v_pos_n, v_vit_n, v_acc_n, v_dn, v_cpos, v_tcre, v_dstp, v_hent, v_tsort, v_ctx_gap, v_ctx_dn0, v_ctx_dfree;
-  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_fill = false /* k_final listed vehicles for k_ctx_fill */, aux_wait = false /* the step has work on the side stream */, dbg_sync = false, dbg_failed = false, coop_loops = true; cudaStream_t aux = nullptr, aux2 = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr, ev_fork = nullptr, ev_rng = nullptr, ev_dirty = nullptr, ev_sens = nullptr; bool rng_wait = false, sens_wait = false;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
+  DBuf<int> cc_lane, cc_id, cc_list, cc_cnt; DBuf<CtxCache> cc; bool use_cc = true, cc_fill = false /* k_final listed vehicles for k_ctx_fill */, aux_wait = false /* the step has work on the side stream */, dbg_sync = false, dbg_failed = false, coop_loops = true; cudaStream_t aux = nullptr, aux2 = nullptr; cudaEvent_t cc_go = nullptr, cc_done = nullptr, ev_fork = nullptr, ev_rng = nullptr, ev_dirty = nullptr, ev_sens = nullptr, ev_eval = nullptr; bool rng_wait = false, sens_wait = false;   // per-vehicle memo of the context walks (micro.cuh: CtxCache)
   DevNet dn; DevVeh dv; DevLaneDyn dl; DevSig ds;
   // merge points (merge.cuh): static tables, per-point state, sensors, per-step records; the device copy of the struct for the kernels that take a pointer
   struct Mrg { bool on = false; int n_upd = 0, n_rows = 0; DevMrg h; DBuf<DevMrg> d;
@@ -712,12 +712,12 @@ extern "C" int symgpu_create(const char* path, int device, symgpu_ctx** out) {
   CK(c->v_memo.alloc(cap * kMemo)); CK(c->v_ctx_lane.alloc(cap * kMaxCtx));
   { const char* e = getenv("SYMGPU_COOP_LOOPS"); int co = 0; cudaDeviceGetAttribute(&co, cudaDevAttrCooperativeLaunch, device); c->coop_loops = co && !(e && !strcmp(e, "0")); }
   { const char* e = getenv("SYMGPU_DEBUG_SYNC"); c->dbg_sync = e && !strcmp(e, "1"); }
-  { const char* e = getenv("SYMGPU_SIDE"); c->side_mask = e ? atoi(e) : 15; }                            // experiments: bit 0 signals, 1 early stream advance, 2 shared points, 3 sensors on side streams
+  { const char* e = getenv("SYMGPU_SIDE"); c->side_mask = e ? atoi(e) : 31; }                            // experiments: bit 0 signals, 1 early stream advance, 2 shared points, 3 sensors, 4 clean points on side streams
   { const char* e = getenv("SYMGPU_CTXCACHE"); c->use_cc = !(e && !strcmp(e, "0")); }                    // SYMGPU_CTXCACHE=0: every vehicle walks the tables every step (cross-check)
   if (c->use_cc) { CK(c->cc_lane.alloc(cap)); CK(cudaMemset(c->cc_lane.p, 0xff, cap * sizeof(int))); CK(c->cc_id.alloc(cap)); CK(cudaMemset(c->cc_id.p, 0xff, cap * sizeof(int)));
     CK(c->cc_list.alloc(cap)); CK(c->cc_cnt.alloc(1)); CK(c->cc.alloc(cap)); CK(cudaMemset(c->cc.p, 0xff, cap * sizeof(CtxCache))); }   // key (-1, -1): matches no vehicle
   CK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->aux2, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&c->ev_fork, &c->ev_rng, &c->ev_dirty, &c->ev_sens}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (cudaEvent_t* e : {&c->ev_fork, &c->ev_rng, &c->ev_dirty, &c->ev_sens, &c->ev_eval}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->cc_go, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->cc_done, cudaEventDisableTiming));
   CK(c->v_vdes.alloc(cap)); CK(cudaMemset(c->v_vdes.p, 0xff, cap * sizeof(int))); CK(c->lc_voies_ok.alloc(cap)); CK(c->lc_chgt.alloc(cap)); CK(c->lc_delta_next.alloc(cap));
   CK(c->lc_link_head.alloc(K)); CK(c->lc_nchg.alloc(2)); CK(c->lc_rng.alloc(1));
@@ -758,7 +758,7 @@ extern "C" void symgpu_destroy(symgpu_ctx* c) {
                           &c->v_dstp, &c->v_hent, &c->v_tsort, &c->v_ctx_gap, &c->v_ctx_dn0, &c->v_ctx_dfree}) b->free();
   for (int k = 0; k < kTrajBufs; k++) if (c->tbuf[k].registered) { cudaHostUnregister(c->tbuf[k].id); cudaHostUnregister(c->tbuf[k].lane); cudaHostUnregister(c->tbuf[k].pos); cudaHostUnregister(c->tbuf[k].vit); cudaHostUnregister(c->tbuf[k].acc); }
   c->t_flag.free(); c->t_off.free(); c->t_bsum.free(); c->t_id.free(); c->t_lane.free(); c->t_pos.free(); c->t_vit.free(); c->t_acc.free();
-  if (c->aux2) cudaStreamDestroy(c->aux2); for (cudaEvent_t e : {c->ev_fork, c->ev_rng, c->ev_dirty, c->ev_sens}) if (e) cudaEventDestroy(e);
+  if (c->aux2) cudaStreamDestroy(c->aux2); for (cudaEvent_t e : {c->ev_fork, c->ev_rng, c->ev_dirty, c->ev_sens, c->ev_eval}) if (e) cudaEventDestroy(e);
   if (c->aux) cudaStreamDestroy(c->aux); if (c->cc_go) cudaEventDestroy(c->cc_go); if (c->cc_done) cudaEventDestroy(c->cc_done);
   if (c->side) cudaStreamDestroy(c->side); if (c->t_ready) cudaEventDestroy(c->t_ready); if (c->t_packed) cudaEventDestroy(c->t_packed); for (int k = 0; k < kTrajBufs; k++) { if (c->t_done[k]) cudaEventDestroy(c->t_done[k]); if (c->t_begin[k]) cudaEventDestroy(c->t_begin[k]); }
   c->counters.free(); c->draws.free(); c->exited.free(); c->edesc.free(); c->f_rootkey.free(); c->f_ctl.free(); c->rows.free(); c->b_goal.free(); c->b_flags.free();
@@ -887,7 +887,7 @@ static int build_merge(symgpu_ctx* c) {
   CK(g.mark.alloc(cap));
   CK(g.rbuf.alloc(1 << 20)); CK(g.kbsum.alloc(np / 1024 + 3)); CK(g.kf.alloc(std::max(1, np))); CK(g.kfo.alloc(std::max(1, np)));
   CK(g.inv.alloc((size_t)std::max(1, np) * kMrgInv)); CK(g.proba.alloc(std::max(1, np))); CK(g.nused.alloc(cap)); CK(g.ulanes.alloc(cap * 3)); CK(g.nvoie.alloc(cap)); CK(cudaMemset(g.nvoie.p, 0xff, cap * sizeof(int)));
-  CK(g.mrgx.alloc(((size_t)cap + 32) * kMrgX)); CK(g.flag.alloc(1)); CK(g.out.alloc(2)); CK(g.seen.alloc(1));
+  CK(g.mrgx.alloc(((size_t)cap + 32) * kMrgX)); CK(g.flag.alloc(1)); CK(g.out.alloc(4)); CK(g.seen.alloc(1));
   h.n_cvg = nc; h.n_pt = np; h.n_sens = (int)sens_link.size(); h.n_cls = T;
   h.max_debit_max = max_debit_max(c); h.max_vit_max = 0; for (int i = 0; i < T; i++) h.max_vit_max = std::max(h.max_vit_max, c->P.cls[i].vx); h.vx0 = c->P.cls[0].vx;
   h.link_cvg = g.link_cvg.p; h.cvg_node = g.cvg_node.p; h.cvg_down = g.cvg_down.p; h.cvg_pt0 = g.cvg_pt0.p; h.cvg_npt = g.cvg_npt.p; h.cvg_am0 = g.cvg_am0.p; h.cvg_nam = g.cvg_nam.p; h.cvg_win = g.cvg_win.p;
@@ -898,7 +898,7 @@ static int build_merge(symgpu_ctx* c) {
   h.lcam0 = g.lcam0.p; h.lcam = g.lcam.p; h.lcav0 = g.lcav0.p; h.lcav = g.lcav.p; h.lmv0 = g.lmv0.p; h.lmv_ent = g.lmv_ent.p; h.lmv_exit = g.lmv_exit.p;
   h.fm0 = g.fm0.p; h.fm_exit = g.fm_exit.p; h.fm_tl0 = g.fm_tl0.p; h.fm_ntl = g.fm_ntl.p; h.fm_tl = g.fm_tl.p; h.node_type = g.node_type.p;
   h.pt_last = g.pt_last.p; h.pt_rand = g.pt_rand.p; h.pt_free = g.pt_free.p; h.cand_up = g.cand_up.p; h.own_min = g.own_min.p; h.own_max = g.own_max.p;
-  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.flist = g.flist.p; h.proba = g.proba.p; h.kf = g.kf.p; h.kfo = g.kfo.p; h.fsorted = g.fsorted.p; h.rbuf = g.rbuf.p; h.rbuf_cap = 1 << 20; h.res = g.res.p; h.dlist = g.dlist.p; h.n_dirty = g.flag.p; h.mark = g.mark.p; h.sens_go = g.out.p + 1;
+  h.st = g.st.p; h.inv = g.inv.p; h.ninv = g.ninv.p; h.pre = g.pre.p; h.kmax = g.kmax.p; h.decide = g.decide.p; h.ndraw = g.ndraw.p; h.flist = g.flist.p; h.proba = g.proba.p; h.kf = g.kf.p; h.kfo = g.kfo.p; h.fsorted = g.fsorted.p; h.rbuf = g.rbuf.p; h.rbuf_cap = 1 << 20; h.res = g.res.p; h.dlist = g.dlist.p; h.n_dirty = g.flag.p; h.mark = g.mark.p; h.sens_go = g.out.p + 1; h.eval_done = g.out.p + 2;
   h.nused = g.nused.p; h.nvoie = g.nvoie.p; h.ulanes = g.ulanes.p; h.mrgx = g.mrgx.p; h.rng = c->lc_rng.p; h.draws = c->draws.p; h.counters = c->counters.p;
   std::vector<DevMrg> one_h(1, h); CK(g.d.upload(one_h));
   return SYMGPU_OK;
@@ -1172,7 +1172,12 @@ static int step_back(symgpu_ctx* c) {
         if (side) { cudaEventRecord(c->ev_fork, s); cudaStreamWaitEvent(c->aux2, c->ev_fork, 0); }
         k_mrg_dirty<<<1, 256, 0, side ? c->aux2 : s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
         if (side) cudaEventRecord(c->ev_dirty, c->aux2);
-        k_mrg_eval<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        // the clean points that need no value of the stream run beside everything that follows (their draw counts are known from the probe): the
+        // ordered walk and the clean points it decides touch other vehicles; its literal visits wait for this kernel on the device (eval_done)
+        const bool eside = side && (c->side_mask & 16); cudaStream_t qe = eside ? c->aux : s;
+        if (eside) cudaStreamWaitEvent(qe, c->ev_fork, 0);
+        k_mrg_eval<<<Gp, B, 0, qe>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        if (eside) cudaEventRecord(c->ev_eval, qe);
         if (side) cudaStreamWaitEvent(s, c->ev_dirty, 0);
         { const int np = g.h.n_pt, nbk = (np + 1023) / 1024;                              // offset of every point's draws in the stream and rank of the visited points: one scan
           k_scan64_block<<<nbk, 1024, 0, s>>>(g.kf.p, g.kfo.p, g.kbsum.p, np); LAUNCH(c);
@@ -1181,8 +1186,10 @@ static int step_back(symgpu_ctx* c) {
           k_mrg_list<<<Gp, B, 0, s>>>(g.h); LAUNCH(c); }
         if (c->rng_wait) { cudaStreamWaitEvent(s, c->ev_rng, 0); c->rng_wait = false; }
         else { k_rng_ctx<<<1, 256, 0, s>>>(c->lc_rng.p, c->draws.p, g.seen.p, guard); LAUNCH(c); }
-        k_mrg_walk<<<1, 256, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, g.kbsum.p + (g.h.n_pt + 1023) / 1024, g.out.p, guard); LAUNCH(c);
-        k_mrg_apply<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); KEND(c); }
+        k_mrg_walk<<<1, 256, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, g.kbsum.p + (g.h.n_pt + 1023) / 1024, g.out.p, guard, Gp); LAUNCH(c);
+        k_mrg_apply<<<Gp, B, 0, s>>>(c->dn, c->dv, g.h, c->order.p, c->s_key.p, c->lane_start.p, c->lane_count.p, c->f_posidx.p, c->rows.p, c->t, g.n_upd, guard); LAUNCH(c);
+        if (eside) cudaStreamWaitEvent(s, c->ev_eval, 0);
+        k_mrg_tally<<<Gp, B, 0, s>>>(g.h, g.n_upd, guard); KEND(c); }
       else if (!c->mp.on) { k_rng_ctx<<<1, 256, 0, s>>>(c->lc_rng.p, c->draws.p, c->mg.seen.p, guard); LAUNCH(c); }
       if (c->use_cc) cudaMemsetAsync(c->cc_cnt.p, 0, sizeof(int), s);
       KBEGIN(c, KID_FINAL); k_final<<<G(n), B, 0, s>>>(c->dn, c->dv, n, T, c->P.dt, c->entre.p, c->sorti.p, c->exited.p, &c->stat.p[4], c->exit_winner.p, &c->stat.p[5], &c->stat.p[6], guard, c->cc_list.p, c->cc_cnt.p); LAUNCH(c);

@@ -54,7 +54,8 @@ struct DevMrg {
   int *own_min, *own_max;                                                  // per vehicle slot: lowest / highest point that touches it
   int *st, *inv, *ninv, *pre, *kmax, *decide, *ndraw, *flist; double* proba;   // per point, this step; flist: the points the walk must visit (unordered)
   int* res;                                                               // per point: 1 inserted, 2 refused this step (summed by k_mrg_apply)
-  int* sens_go;                                                           // update count the sensor kernel may run for (set by k_mrg_apply once the step is certain)
+  int* sens_go;                                                           // update count the sensor kernel may run for (set by k_mrg_tally once the step is certain)
+  int* eval_done;                                                         // blocks of k_mrg_eval that have finished this step (the walk's literal visits wait for all of them)
   int *dlist, *n_dirty; unsigned long long* mark;                         // points that share a vehicle with another point; per vehicle: (round << 32 | ~point) of the lowest unfinished point touching it
   unsigned long long *kf, *kfo; int *fsorted, *rbuf; int rbuf_cap;                       // kf: per point, draws known before the walk (low 40 bits) | visit flag (bit 40); kfo: its exclusive scan = offset in the stream | rank in the visit list
   int *nused, *nvoie, *ulanes;                                             // per vehicle: intermediate lanes used this step (count, first three of them); m_pNextVoie (sticky)
@@ -236,16 +237,19 @@ __device__ inline double calcul_position(const MrgView& W, int x, double tr, int
   }
   return 9999;
 }
+struct MrgAcc { int inv[kMrgInv]; int ninv; int ndraw; bool probe; bool overflow; int pmv[6], pmt[6]; int npm = 0; };   // pmv / pmt: memo entries a probe has already counted as drawn (a probe writes nothing)
+__device__ inline void touch(MrgAcc& A, int x) { if (x < 0) return; for (int k = 0; k < A.ninv; k++) if (A.inv[k] == x) return; if (A.ninv < kMrgInv) A.inv[A.ninv++] = x; else A.overflow = true; }
 // Vehicule::CalculNextVoie with its memoised draw (GetTirage, vehicule.cpp:1779-1795).  probe: nothing is written, a miss is
 // reported through *miss.  Returns the next lane; *ndraw is incremented when a draw is consumed.
-__device__ inline int next_voie_m(const MrgView& W, int x, int lane, bool probe, int* ndraw, bool* miss) {
+__device__ inline int next_voie_m(const MrgView& W, int x, int lane, bool probe, int* ndraw, bool* miss, MrgAcc* acc = nullptr) {
   int tl; const int nx = next_voie(W.N, W.V.route[x], W.V.route_pos[x], lane, &tl);
   if (tl >= 0) { int* memo = &W.V.memo[x * kMemo]; bool hit = false; for (int k = 0; k < kMemo; k++) if (memo[k] == tl) hit = true;
+    if (!hit && probe && acc) {                                                            // the evaluation would have memoised it at the first miss
+      for (int k = 0; k < acc->npm; k++) if (acc->pmv[k] == x && acc->pmt[k] == tl) hit = true;
+      if (!hit) { if (acc->npm < 6) { acc->pmv[acc->npm] = x; acc->pmt[acc->npm] = tl; acc->npm++; } else acc->overflow = true; } }
     if (!hit) { (*ndraw)++; if (miss) *miss = true; if (!probe) memo_touch(memo, tl); } }
   return nx;
 }
-struct MrgAcc { int inv[kMrgInv]; int ninv; int ndraw; bool probe; bool overflow; };
-__device__ inline void touch(MrgAcc& A, int x) { if (x < 0) return; for (int k = 0; k < A.ninv; k++) if (A.inv[k] == x) return; if (A.ninv < kMrgInv) A.inv[A.ninv++] = x; else A.overflow = true; }
 // Reseau::GetVehiculeAmont reseau.cpp:9638-9690: depth-first over the upstream connections, first lane of every link
 __device__ inline int vehicule_amont(const MrgView& W, MrgAcc& A, int link, double dst) {
   struct Fr { int link, it; double cum; } stk[6]; int sp = 0;
@@ -258,7 +262,7 @@ __device__ inline int vehicule_amont(const MrgView& W, MrgAcc& A, int link, doub
         int res = v; int lvl = sp - 1;
         while (lvl >= 0 && res >= 0) { const Fr& c = stk[lvl]; bool ok = false;
           if (dst > c.cum + W.N.link_len[c.link] - mpos1(W, res)) { bool miss = false; int nd = 0;
-            const int nx = next_voie_m(W, res, W.V.lane[res], A.probe, &nd, &miss); A.ndraw += nd; if (miss) touch(A, res);
+            const int nx = next_voie_m(W, res, W.V.lane[res], A.probe, &nd, &miss, &A); A.ndraw += nd; if (miss) touch(A, res);
             ok = nx == W.N.link_first[c.link]; }
           if (ok) lvl--; else break; }
         if (lvl < 0) return res;
@@ -465,12 +469,12 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
     if (lead < 0) { const int k1 = N.lane_link[V.lane[att]]; const int ta = N.link_type[k1]; int voie = V.lane[att]; const int nvoie = N.lane_num[voie];
       int next_link = (ta != 'S' && ta != 'P') ? k1 : -1;
       if (ta == 'C' && M.lcav0[k1 + 1] > M.lcav0[k1]) { next_link = M.lcav[M.lcav0[k1]];
-        voie = next_voie_m(W, att, voie, probe, &A.ndraw, nullptr);
+        voie = next_voie_m(W, att, voie, probe, &A.ndraw, nullptr, &A);
         if (voie < 0) voie = N.link_first[next_link] + min(nvoie, N.link_nl[next_link] - 1);
         lead = first_from_zero(W, voie, att); }
       if (lead < 0 && next_link >= 0) for (int q = M.lcav0[next_link]; q < M.lcav0[next_link + 1]; q++) { const int nn = M.lcav[q];
         if (!is_itineraire(W, att, nn)) continue;
-        voie = next_voie_m(W, att, voie, probe, &A.ndraw, nullptr);
+        voie = next_voie_m(W, att, voie, probe, &A.ndraw, nullptr, &A);
         if (voie < 0) voie = N.link_first[nn] + min(nvoie, N.link_nl[nn] - 1);
         const int l2 = first_from_zero(W, voie, att); if (l2 >= 0) lead = l2; }
     }
@@ -514,7 +518,7 @@ __device__ inline int merge_point(const MrgView& W, int p, int mode, MrgAcc& A, 
       if (f2 >= 0) {                                                                                                        // :395-461
         if (N.link_brick[TAmP] >= 0 && M.node_type[N.link_up[TAmP]] == 'C') {                                               // get_Type_amont() == 'D'
           const int ent = M.lcam0[TAmP + 1] > M.lcam0[TAmP] ? M.lcam[M.lcam0[TAmP]] : -1;
-          if (ent >= 0 && M.lcav0[ent + 1] - M.lcav0[ent] > 1) next_voie_m(W, f2, N.link_first[ent], probe, &A.ndraw, nullptr);   // :432
+          if (ent >= 0 && M.lcav0[ent + 1] - M.lcav0[ent] > 1) next_voie_m(W, f2, N.link_first[ent], probe, &A.ndraw, nullptr, &A);   // :432
         } else if (!is_itineraire(W, f2, M.cvg_down[c])) { f2 = -1; ins = true; }
       }
       if (N.link_nl[TAmP] > 1 && N.link_nl[M.cvg_down[c]] > 1 && nVoieGir == 0) {                                           // :472-500 (not a roundabout: one draw, then ignored)
@@ -655,6 +659,7 @@ __device__ __noinline__ void merge_point_serial(const MrgView* W, int q, RngCurs
 __global__ void k_mrg_rank(DevMrg M, const int* sl_col, const int* lane_count) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= M.n_pt) return;
+  if (p == 0) *M.eval_done = 0;
   M.pt_rand[p]++;                                                                          // convergent.cpp:366, every point, every step (nothing reads it before CalculInsertion)
   const int v0 = M.pt_vam0[p], n = M.pt_nvam[p]; const int mode = M.pt_mode[p];
   for (int a = v0; a < v0 + n; a++) M.vam_niv[a] = M.vam_ref[a];
@@ -680,7 +685,8 @@ __global__ void k_mrg_probe(DevNet N, DevVeh V, DevMrg M, const int* order, cons
   MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
   int st = merge_point(W, p, MM_PROBE, A, nullptr);
   if (A.overflow) st = MS_OVERFLOW;
-  M.st[p] = st; M.ninv[p] = A.ninv; M.ndraw[p] = 0; M.kf[p] = st == MS_VALUES ? (unsigned long long)(A.ndraw + 1) : 0ULL;
+  M.st[p] = st; M.ninv[p] = A.ninv; M.ndraw[p] = 0;
+  M.kf[p] = st == MS_VALUES ? (unsigned long long)(A.ndraw + 1) : st == MS_DONE ? (unsigned long long)A.ndraw : 0ULL;   // count-only draws: what the evaluation will consume (checked there)
   for (int k = 0; k < A.ninv; k++) { M.inv[p * kMrgInv + k] = A.inv[k]; atomicMin(&M.own_min[A.inv[k]], p); atomicMax(&M.own_max[A.inv[k]], p); }
 }
 // after every probe: points whose vehicles no other point touches are "clean"; the others go to the list of k_mrg_dirty
@@ -704,11 +710,15 @@ __global__ void k_mrg_eval(DevNet N, DevVeh V, DevMrg M, const int* order, const
                            const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
   if (guard && *guard == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= M.n_pt || M.st[p] != MS_DONE) return;                                             // clean points that need no values of the stream
-  const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
-  MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
-  const int st = merge_point(W, p, MM_EVAL, A, nullptr);
-  M.st[p] = st; M.ndraw[p] = A.ndraw; M.kf[p] = (unsigned long long)A.ndraw;               // count-only draws: an offset for the points after this one, nothing to visit
+  if (p < M.n_pt && M.st[p] == MS_DONE) {                                                    // clean points that need no values of the stream
+    const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+    MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false;
+    const int st = merge_point(W, p, MM_EVAL, A, nullptr);
+    M.st[p] = st; M.ndraw[p] = A.ndraw;
+    if ((unsigned long long)A.ndraw != M.kf[p]) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_CTX_OVERFLOW], 1ULL);   // the probe's count is the offset of the points after this one: it must be what the evaluation drew
+  }
+  __threadfence(); __syncthreads();                                                          // this block's points are done: the walk, which runs beside this kernel, waits for all blocks before a literal visit
+  if (threadIdx.x == 0) atomicAdd(M.eval_done, 1);
 }
 // Points that share a vehicle with another point must be processed in point order — but only relative to the points they share with.
 // One block, rounds: every unfinished point stamps its vehicles with (round, point), lowest point wins; a point that holds all its
@@ -800,7 +810,7 @@ __global__ void k_mrg_list(DevMrg M) { const int p = blockIdx.x * blockDim.x + t
 // advanced by what was really consumed.  out[0] = draws of the merge phase.
 __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, const int* order, const double* skey, const int* lane_start,
                                                   const int* lane_count, const int* posidx, const double* rows, double inst, int n_upd, const u64* kf_total,
-                                                  int* out, const int* guard) {
+                                                  int* out, const int* guard, int n_eval_blocks) {
   constexpr int kBatch = 512, kRc = 4096;
   // the stream's values around the walk's position: sh_rb holds positions [sh_B, sh_B + sh_F) of the step's merge draws, S generates what follows.
   // Positions only grow, so the window slides forward; nothing is generated beyond what is consumed plus one window.
@@ -906,6 +916,8 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
       const int at = e_rec[k].x - 1 + extra + e_cpre[k] + sh_H;
       ensure(at, at + kRc);                                                                    // (rare: a whole window, whatever the point draws)
       if (tid == 0) { const int q = e_pt[k]; RngCursor C{sh_rb - sh_B, at, sh_B + sh_F, 0};
+        { volatile int* done = M.eval_done; long long spins = 0; while (*done < n_eval_blocks && ++spins < (1LL << 26)) __nanosleep(200);   // the clean points (k_mrg_eval, beside this kernel) first, as when the kernels ran one after the other
+          if (*done < n_eval_blocks) C.overflow = 1; __threadfence(); }
         merge_point_serial(&W, q, &C);
         sh_H += C.pos - at; sh_flag = C.overflow; M.st[q] = MS_DONE; }
       __syncthreads();
@@ -935,15 +947,20 @@ __global__ void k_mrg_apply(DevNet N, DevVeh V, DevMrg M, const int* order, cons
                             const int* posidx, const double* rows, double inst, int n_upd, const int* guard) {
   if (guard && *guard == 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < M.n_pt && M.st[p] == MS_VALUES) { const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
+    MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; merge_point(W, p, MM_DECIDED, A, nullptr); }
+}
+// end of the merge phase (every point processed): ownership marks back to idle, statistics, go-ahead for the sensors of the step
+__global__ void k_mrg_tally(DevMrg M, int n_upd, const int* guard) {
+  if (guard && *guard == 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   int res = 0;
   if (p == 0) *M.sens_go = n_upd + 1;
   if (p < M.n_pt) {
-    if (M.st[p] == MS_VALUES) { const MrgView W{cP_ref(), N, V, M, order, skey, lane_start, lane_count, posidx, rows, inst, n_upd};
-      MrgAcc A; A.ninv = 0; A.ndraw = 0; A.overflow = false; merge_point(W, p, MM_DECIDED, A, nullptr); }
-    for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; M.own_min[x] = INT_MAX; M.own_max[x] = -1; }   // marks back to idle for the next step
+    for (int k = 0; k < M.ninv[p]; k++) { const int x = M.inv[p * kMrgInv + k]; M.own_min[x] = INT_MAX; M.own_max[x] = -1; }
     res = M.res[p]; M.res[p] = 0;
   }
-  const unsigned mi = __ballot_sync(0xffffffffu, res == 1), mr = __ballot_sync(0xffffffffu, res == 2);     // statistics: one atomic per warp
+  const unsigned mi = __ballot_sync(0xffffffffu, res == 1), mr = __ballot_sync(0xffffffffu, res == 2);     // one atomic per warp
   if ((threadIdx.x & 31) == 0) { if (mi) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_INS], (unsigned long long)__popc(mi));
     if (mr) atomicAdd((unsigned long long*)&M.counters[SYMGPU_CNT_MRG_REFUS], (unsigned long long)__popc(mr)); }
 }
