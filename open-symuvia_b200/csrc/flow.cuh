@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(256) k_cyc_rest(DevVeh V, DevFlow F, double* r
   unsigned phase = 0; const unsigned nb = gridDim.x;
   const int ns = __ldcg(&F.ctl->n_unres);
   if (ns == 0) return;                                   // every block sees the same count: no chain left open
+  // an open chain only runs through open fronts (a front that ends within kCycWalk steps is resolved, and so is everything that reaches it
+  // within the walk), so it is at most ns + kCycWalk segments long: 4^k * walk >= that is enough, whatever the host sized klev for
+  { int kl = 1; while ((1LL << (2 * kl)) * kCycWalk < (long long)ns + kCycWalk) kl++; kl++; if (kl < klev) klev = kl; }
   int flip = 0;
   for (int k = 0; k < klev; k++) {                     // A <- A^4, Mn <- min over the segments stepped over
     const int* A = flip ? F.A2 : F.A; const int* M = flip ? F.Mn2 : F.Mn;
