@@ -420,7 +420,12 @@ __device__ inline void mrg_register(const DevNet& n, const DevMrg* M, int i, int
 __device__ inline int vehicule_en_attente(const MrgView& W, int lane) {
   const int s = W.lane_start[lane]; const double lim = W.N.lane_len[lane] - W.M.max_vit_max * W.P.dt - 1.0;   // a vehicle further upstream cannot have left the lane
   for (int q = s + W.lane_count[lane] - 1; q >= s; q--) { if (mkey(W, q) < lim) break;
-    const int y = W.order[q]; if (W.V.lane_n[y] != lane) return y; }
+    const int y = W.order[q]; if (W.V.lane_n[y] != lane) {
+      // several vehicles standing at one place (the reference creates such twins when it pins vehicles at a lane end): they have the same leader,
+      // so the recursion computed — and registered — them in list order, and a slot index is a place in that list
+      int best = y; const double k = mkey(W, q);
+      for (int q2 = q - 1; q2 >= s && mkey(W, q2) == k; q2--) { const int y2 = W.order[q2]; if (W.V.lane_n[y2] != lane && y2 < best) best = y2; }
+      return best; } }
   const int k = W.M.cand_up[lane];
   if (k >= 0) { const int y = W.order[k]; if (W.V.lane_n[y] != lane) return y; }
   return -1;
