@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(256) k_mrg_walk(DevNet N, DevVeh V, DevMrg M, 
       if (e_st[k] == MS_VALUES) { const int start = e_rec[k].x + extra + e_cpre[k] + sh_H; ensure(start, start + e_rec[k].y); continue; }   // the window moves to this entry
       // a point that shares a vehicle with another point and was not settled by k_mrg_dirty: literally, now
       const int at = e_rec[k].x - 1 + extra + e_cpre[k] + sh_H;
-      ensure(at, at + kRc);                                                                    // (rare: a whole window, whatever the point draws)
+      ensure(at, at + min(kRc, 64 + M.pt_rand[e_pt[k]]));                                      // its count-only draws, the unused one, at most (m_nRandNumbers + 1) / 2 tests
       if (tid == 0) { const int q = e_pt[k]; RngCursor C{sh_rb - sh_B, at, sh_B + sh_F, 0};
         { volatile int* done = M.eval_done; long long spins = 0; while (*done < n_eval_blocks && ++spins < (1LL << 26)) __nanosleep(200);   // the clean points (k_mrg_eval, beside this kernel) first, as when the kernels ran one after the other
           if (*done < n_eval_blocks) C.overflow = 1; __threadfence(); }

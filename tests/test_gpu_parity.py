@@ -173,7 +173,7 @@ def test_side_streams_do_not_change_results(synth, pkg, monkeypatch):
 
 def test_c4_full_size_prefix_and_invariants(synth, pkg):
     """BASELINE config C4 at full size (100x100, ~1M vehicles): oracle parity on the first 100 steps (tools/gpu_long_parity.py runs it
-    further: bit-exact over 300 steps), then
+    further: bit-exact over 600 steps), then
     size-independent invariants over a longer run: no follower passes its leader on a lane, positions stay
     within the lane, the population only shrinks by exits."""
     import os
