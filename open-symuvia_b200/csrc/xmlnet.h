@@ -110,6 +110,7 @@ inline bool flat_from_xml(const char* path, FlatNet& F, std::string& err) {
   std::map<std::string, int> node_id; std::vector<const XmlNode*> node_xml; std::vector<double> node_xy;
   auto add_node = [&](const XmlNode* x, int type) { node_id[x->str("id")] = (int)F.node_names.size(); F.node_names.push_back(x->str("id")); F.node_i.insert(F.node_i.end(), {type, -1, 0, 0}); node_xml.push_back(x); node_xy.push_back(0); node_xy.push_back(0); };
   const XmlNode* cnx = res->kid("CONNEXIONS"); if (!cnx) { err = "RESEAU/CONNEXIONS missing"; return false; }
+  if (const XmlNode* gi = cnx->kid("GIRATOIRES")) if (!gi->kids.empty()) { err = "GIRATOIRES (roundabouts) are not supported"; return false; }
   if (auto* g = cnx->kid("EXTREMITES")) for (auto* x : g->all("EXTREMITE")) add_node(x, 'E');            // 'E' or 'S' once the links are known
   if (auto* g = cnx->kid("REPARTITEURS")) for (auto* x : g->all("REPARTITEUR")) add_node(x, 'R');
   if (auto* g = cnx->kid("CONVERGENTS")) for (auto* x : g->all("CONVERGENT")) add_node(x, 'C');

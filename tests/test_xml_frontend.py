@@ -62,3 +62,22 @@ def test_xml_errors_are_reported(pkg, tmp_path):
     bad.write_text("<ROOT_SYMUBRUIT><SIMULATIONS/></ROOT_SYMUBRUIT>")
     assert L.symflat_from_xml(str(bad).encode(), str(tmp_path / "o.symflat").encode()) != 0
     assert L.symflat_from_xml(str(tmp_path / "missing.xml").encode(), str(tmp_path / "o.symflat").encode()) != 0
+
+
+def test_unsupported_features_are_refused(pkg, synth, tmp_path):
+    """Roundabouts and conflict points inside junctions change the hot path: a document that uses them must not load as if it did not."""
+    L = pkg.lib()
+    L.symflat_from_xml.argtypes = [C.c_char_p, C.c_char_p]
+    px = tmp_path / "a.xml"
+    synth.grid(n=2, n_steps=50, demand_per_lane=0.2).to_xml(str(px))
+    doc = px.read_text()
+    out = str(tmp_path / "o.symflat").encode()
+    assert L.symflat_from_xml(str(px).encode(), out) == 0
+    assert "<CONNEXIONS>" in doc
+    g = tmp_path / "g.xml"
+    g.write_text(doc.replace("<CONNEXIONS>", "<CONNEXIONS><GIRATOIRES><GIRATOIRE id=\"G1\"/></GIRATOIRES>", 1))
+    assert L.symflat_from_xml(str(g).encode(), out) != 0
+    if 'traversees="false"' in doc:
+        t = tmp_path / "t.xml"
+        t.write_text(doc.replace('traversees="false"', 'traversees="true"', 1))
+        assert L.symflat_from_xml(str(t).encode(), out) != 0
