@@ -427,7 +427,12 @@ __device__ inline int vehicule_en_attente(const MrgView& W, int lane) {
       for (int q2 = q - 1; q2 >= s && mkey(W, q2) == k; q2--) { const int y2 = W.order[q2]; if (W.V.lane_n[y2] != lane && y2 < best) best = y2; }
       return best; } }
   const int k = W.M.cand_up[lane];
-  if (k >= 0) { const int y = W.order[k]; if (W.V.lane_n[y] != lane) return y; }
+  if (k >= 0) { const int y = W.order[k]; if (W.V.lane_n[y] != lane) {
+      // the same for vehicles that stood at one place on the lane before (side by side at a stop line) and crossed this one entirely together
+      int best = y; const double key = mkey(W, k); const int s0 = W.lane_start[W.V.lane[y]];
+      for (int k2 = k - 1; k2 >= s0 && mkey(W, k2) == key; k2--) { const int y2 = W.order[k2]; if (W.V.lane_n[y2] == lane || y2 > best) continue;
+        const int nu = min(W.M.nused[y2], 3); for (int j = 0; j < nu; j++) if (W.M.ulanes[y2 * 3 + j] == lane) best = y2; }
+      return best; } }
   return -1;
 }
 

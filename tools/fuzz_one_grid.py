@@ -1,6 +1,6 @@
 """One case of the grid campaign with every differing row printed: python tools/fuzz_one_grid.py [seed]   (3036: the one known difference)"""
 import importlib, os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tests import fuzz_cases
 from tests.parity import run_parity
 synth = importlib.import_module("open-symuvia_b200.synth")
