@@ -126,11 +126,12 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_oracle_rate(path, info, steps, warmup=0, repeats=1):
+def cpu_oracle_rate(path, info, steps, warmup=0, repeats=1, variant="faithful"):
     """vehicle-steps/s of the CPU oracle on ONE host core (the reference steps one network on one thread): `repeats` consecutive
-    samples of `steps` time steps each, the median rate is returned (median of 5)."""
+    samples of `steps` time steps each, the median rate is returned (median of 5).  variant "flat" = the
+    "sorted lanes" baseline (flat per-lane arrays instead of the reference's std::set; same results)."""
     from oracle.binding import Oracle
-    o = Oracle(path, info["n_links"], info["n_classes"])
+    o = Oracle(path, info["n_links"], info["n_classes"], variant=variant)
     for _ in range(warmup):
         o.step()
     rates, tot_all, dt_all = [], 0, 0.0
@@ -364,9 +365,12 @@ def main():
     if rank == 0 and world == 1 and a.cpu_steps > 0:
         per = max(1, a.cpu_steps // 5)
         rate, dt, tot = cpu_oracle_rate(path, info, per, repeats=5)
+        rate2, dt2, tot2 = cpu_oracle_rate(path, info, per, repeats=3, variant="flat")
         line["cpu_baseline"] = {"value": rate, "unit": "vehicle-steps/s", "cores": 1, "kind": "port", "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
                                 "sample": f"median of 5 consecutive samples of {per} time steps of the same {a.workload} input ({tot} vehicle-steps, {dt:.1f} s in all); "
-                                          "the oracle keeps the reference's structure (id-ordered lane sets, linear neighbour scans, leader-first recursion), one thread"}
+                                          "the oracle keeps the reference's structure (id-ordered lane sets, linear neighbour scans, leader-first recursion), one thread",
+                                # BASELINE.md section 3 asks for a second variant: flat per-lane arrays in id order instead of std::set (same results, better memory behaviour)
+                                "sorted_lanes": {"value": rate2, "unit": "vehicle-steps/s", "cores": 1, "sample": f"median of 3 samples of {per} time steps ({tot2} vehicle-steps, {dt2:.1f} s)"}}
     if rank == 0:
         print(json.dumps(line))
     g.close()

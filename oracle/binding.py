@@ -8,21 +8,22 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIB = {}
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "liboracle.so")
+def build(force: bool = False, variant: str = "faithful") -> str:
+    """variant "flat": the "sorted lanes" CPU baseline of BASELINE.md section 3 (flat per-lane arrays in id order instead of std::set; same results)."""
+    name = "liboracle.so" if variant == "faithful" else "liboracle_flat.so"
+    so = os.path.join(_HERE, name)
     src = os.path.join(_HERE, "oracle.cpp")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", _HERE, "-B", name], stdout=subprocess.DEVNULL)
     return so
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build())
+def lib(variant: str = "faithful"):
+    if variant not in _LIB:
+        L = C.CDLL(build(variant=variant))
         L.orc_load.restype = C.c_void_p
         L.orc_load.argtypes = [C.c_char_p]
         L.orc_free.argtypes = [C.c_void_p]
@@ -48,15 +49,15 @@ def lib():
         L.orc_rng_raw.argtypes = [C.c_void_p]
         L.orc_rng_raw.restype = C.c_uint
         L.orc_rng_free.argtypes = [C.c_void_p]
-        _LIB = L
-    return _LIB
+        _LIB[variant] = L
+    return _LIB[variant]
 
 
 class Oracle:
     """One simulation on the CPU oracle, loaded from a SYMFLAT1 file."""
 
-    def __init__(self, flat_path: str, n_links: int, n_classes: int = 1):
-        self.L = lib()
+    def __init__(self, flat_path: str, n_links: int, n_classes: int = 1, variant: str = "faithful"):
+        self.L = lib(variant)
         self.h = self.L.orc_load(flat_path.encode())
         if not self.h:
             raise RuntimeError(f"oracle: cannot load {flat_path}")

@@ -163,6 +163,20 @@ struct Veh {
   double res_tir_foll_int = -1;                                    // m_dbResTirFollInt (AbstractCarFollowing.cpp:484-497)
 };
 struct LessId { bool operator()(const Veh* a, const Veh* b) const { return a->id < b->id; } };   // tools.h:67-74
+#ifdef ORACLE_FLAT_LANES
+// "sorted lanes" variant of the CPU baseline: the per-lane vehicle set is a flat array kept in id order instead of a
+// red-black tree.  Same iteration order, hence the same results; what changes is the memory behaviour of InitVehicules and of the scans.
+struct LaneSet {
+  std::vector<Veh*> v;
+  void clear() { v.clear(); }
+  void insert(Veh* x) { auto it = std::lower_bound(v.begin(), v.end(), x, LessId()); if (it == v.end() || (*it)->id != x->id) v.insert(it, x); }
+  void erase(Veh* x) { auto it = std::lower_bound(v.begin(), v.end(), x, LessId()); if (it != v.end() && *it == x) v.erase(it); }
+  std::vector<Veh*>::const_iterator begin() const { return v.begin(); }
+  std::vector<Veh*>::const_iterator end() const { return v.end(); }
+};
+#else
+typedef std::set<Veh*, LessId> LaneSet;
+#endif
 
 struct Exited { int id; double inst; };
 
@@ -185,7 +199,7 @@ struct Sim {
   double t = 0; int ninst = 0; int last_id = 0; RandManager rnd;
   std::vector<Veh*> lst;                                           // m_LstVehicles (order is part of the contract)
   std::vector<std::unique_ptr<Veh>> owned;                         // everything ever created and still alive
-  std::vector<std::set<Veh*, LessId>> lane_set;                   // VoieMicro::m_LstVehiculesAnt (voie.h:240)
+  std::vector<LaneSet> lane_set;                                   // VoieMicro::m_LstVehiculesAnt (voie.h:240)
   std::vector<int> nb_entre, nb_sorti;                            // Tuyau::m_mapNbVehEntre/Sorti (tuyau.h:531-532), [link*T+cls]
   std::vector<Exited> exited;                                      // removed this step
   std::vector<Veh*> graveyard;

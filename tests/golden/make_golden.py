@@ -25,7 +25,7 @@ CASES = {
 }
 
 
-def run_case(name):
+def run_case(name, variant="faithful"):
     from oracle.binding import Oracle
     make, steps = CASES[name]
     b = make()
@@ -33,7 +33,7 @@ def run_case(name):
     os.close(fd)
     try:
         b.write(path)
-        o = Oracle(path, len(b.links), len(b.classes))
+        o = Oracle(path, len(b.links), len(b.classes), variant=variant)
         n_per_step = np.zeros(steps, np.int32)
         ex_id, ex_t = [], []
         for k in range(steps):

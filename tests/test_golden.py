@@ -20,9 +20,10 @@ def _load(name):
     return dict(np.load(os.path.join(HERE, "golden", name + ".npz")))
 
 
+@pytest.mark.parametrize("variant", ["faithful", "flat"])          # flat: the "sorted lanes" CPU baseline of bench.py (flat per-lane arrays), same results
 @pytest.mark.parametrize("name", sorted(make_golden.CASES))
-def test_oracle_reproduces_golden(name):
-    want, got = _load(name), make_golden.run_case(name)
+def test_oracle_reproduces_golden(name, variant):
+    want, got = _load(name), make_golden.run_case(name, variant)
     assert sorted(want) == sorted(got)
     for k in want:
         assert np.array_equal(np.asarray(want[k]), np.asarray(got[k])), k       # integers and fp64 bit for bit
