@@ -12,13 +12,17 @@
 //   k_mrg_rank    per point, start of the step: priority levels of the points inside signalised junctions from this step's
 //                 signal colours and the occupancy of the internal lanes at the end of the previous step
 //   (phase A/B)   rows.cuh: the speed imposed on the head of a non-priority branch and the pessimistic leader speed
-//   k_mrg_probe   per point, parallel, read-only: which vehicles the point would touch -> ownership marks (min / max point)
-//   k_mrg_eval    per point, parallel: points whose vehicles no other point touches ("clean") are processed at once, unless
-//                 their decision needs VALUES of the random stream (congested branch, AbstractCarFollowing.cpp:357-375)
-//   k_mrg_walk    one block, points in id order: stream offsets of every point from the draw counts, the draws of the points
-//                 that need values, and the few points that share a vehicle with another one, literally in order
+//   k_mrg_probe   per point, parallel, read-only: which vehicles the point would touch -> ownership marks (min / max point), its count-only
+//                 draws (exact: the probe remembers the memo entries it has counted), whether its decision needs VALUES of the stream
+//   k_mrg_classify  points whose vehicles no other point touches are "clean", the others "dirty"
+//   k_mrg_eval    per clean point that needs no value, parallel, on a side stream beside everything below (other vehicles): processed at once
+//   k_mrg_dirty   one block, beside k_mrg_eval: the dirty points in rounds that respect the point order wherever two of them share a vehicle
+//   k_scan64 / k_mrg_list  stream offset of every point from the draw counts, in point order; compact list of the points to visit
+//   k_mrg_walk    one block, points in id order: the draws of the clean points that need values (congested branch,
+//                 AbstractCarFollowing.cpp:357-375) against a sliding window of generated values, and the few dirty points left, literally
 //   k_mrg_apply   per point, parallel: the clean points whose decision the walk has just made
-//   k_mrg_sensors per vehicle, end of the step: merge sensor counts (integer atomics)
+//   k_mrg_tally   after the join: marks back to idle, insertion / refusal counts, go-ahead for the sensors
+//   k_mrg_rotate / k_mrg_sensors / k_mrg_sensors_sum  per vehicle, end of the step, beside the next step's lane ordering: merge sensor counts
 // Every arithmetic expression is the reference's, in its order (fp64, no contraction).
 #pragma once
 #include "lanechange.cuh"
